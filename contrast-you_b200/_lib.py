@@ -1,0 +1,95 @@
+"""ctypes binding of libcontrastyou_b200.so — the only door from Python into the CUDA kernels.
+
+The signatures mirror include/contrastyou_b200.h one to one.  Loading is lazy (first kernel call or an explicit
+``load()``) so that host-side helpers can be imported on machines without the library, but every compute entry
+point goes through :func:`lib` and raises ``RuntimeError`` if the shared object is missing — there is no fallback.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcontrastyou_b200.so")
+
+# dtype / variant / path codes (contrastyou_b200.h)
+CY_F32, CY_BF16, CY_F16 = 0, 1, 2
+CY_SUPCON, CY_SUPCON_EXCLUDE, CY_SELFPACED_HARD, CY_SELFPACED_SOFT = 0, 1, 2, 3
+CY_PATH_AUTO, CY_PATH_SIMT, CY_PATH_TCGEN05 = 0, 1, 2
+CY_NSTAT = 8
+CY_STAT_LOGDEN, CY_STAT_INVC, CY_STAT_COEF, CY_STAT_AUX = 0, 1, 2, 3
+
+_c = ctypes
+_vp, _i64, _i32, _f32, _f64, _sz = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_float, _c.c_double, _c.c_size_t
+
+# name -> (restype, argtypes); kept in header order so tests can diff it against include/contrastyou_b200.h
+SIGNATURES = {
+    "cy_abi_version": (_i32, []),
+    "cy_last_error": (_c.c_char_p, []),
+    "cy_device_sm_count": (_i32, []),
+    "cy_infonce_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32]),
+    "cy_infonce_fwd": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "cy_infonce_fwd_pass2": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _i32, _f32, _i32, _vp, _vp,
+                                    _sz, _vp]),
+    "cy_infonce_finalize": (_i32, [_i64, _i64, _i64, _f32, _i32, _i32, _vp, _vp, _vp]),
+    "cy_infonce_bwd": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _i32, _f32, _i32, _vp, _vp, _vp,
+                              _i64, _vp, _sz, _vp]),
+    "cy_infonce_masks": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp]),
+    "cy_labels_canonicalize": (_i32, [_vp, _i32, _i64, _vp, _vp]),
+    "cy_iic_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
+    "cy_iic_joint": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "cy_iic_epilogue": (_i32, [_vp, _i32, _i32, _i32, _f32, _f32, _f64, _vp, _vp, _vp, _vp, _vp]),
+    "cy_iic_bwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+}
+
+_LIB = None
+
+
+def load():
+    """dlopen the library and bind every symbol of SIGNATURES.  Raises RuntimeError when it is absent."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  contrast-you_b200 has no CPU / eager fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError here == header / library mismatch
+            fn.restype, fn.argtypes = res, args
+        if handle.cy_abi_version() != 1:
+            raise RuntimeError("libcontrastyou_b200.so: ABI version mismatch")
+        _LIB = handle
+    return _LIB
+
+
+def lib():
+    return load()
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().cy_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return {torch.float32: CY_F32, torch.bfloat16: CY_BF16, torch.float16: CY_F16}[t.dtype]
+    except KeyError:
+        raise TypeError(f"contrast-you_b200 kernels take float32 / bfloat16 / float16 tensors, got {t.dtype}") from None
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("contrast-you_b200 runs on CUDA tensors only (sm_100a kernels, no CPU fallback); "
+                               f"got a tensor on {t.device}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,190 @@
+// extern "C" surface of libcontrastyou_b200.so (see include/contrastyou_b200.h for the contract of every call).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cy {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// infonce_simt.cu
+int infonce_fwd_simt(const void*, int, int64_t, int64_t, int64_t, const int32_t*, const uint8_t*, int64_t, int64_t, float, int,
+                     int, float, float*, cudaStream_t);
+int infonce_finalize(int64_t, int64_t, int64_t, int, int, float*, float*, cudaStream_t);
+int infonce_bwd_simt(const void*, int, int64_t, int64_t, int64_t, const int32_t*, const uint8_t*, int64_t, int64_t, float, int,
+                     float, const float*, const float*, void*, int64_t, cudaStream_t);
+int infonce_masks(int64_t, const int32_t*, const uint8_t*, float*, float*, cudaStream_t);
+int labels_canonicalize(const void*, int, int64_t, int32_t*, cudaStream_t);
+// infonce_tc.cu
+bool infonce_tc_supported(int dtype, int64_t N, int64_t d, int64_t ldz, const uint8_t* codes, int variant);
+size_t infonce_tc_workspace_bytes(int64_t N, int64_t d);
+int infonce_fwd_tc(const void*, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, float*, void*, size_t,
+                   cudaStream_t);
+int infonce_bwd_tc(const void*, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, const float*, const float*,
+                   void*, int64_t, void*, size_t, cudaStream_t);
+// iic.cu
+size_t iic_workspace_bytes(int, int, int, int, int);
+int iic_joint(const void*, const void*, int, int, int, int, int, int, float*, void*, size_t, cudaStream_t);
+int iic_epilogue(const float*, int, int, int, float, float, double, float*, float*, float*, float*, cudaStream_t);
+int iic_bwd(const void*, const void*, int, int, int, int, int, int, const float*, const float*, void*, void*, cudaStream_t);
+
+static int check_infonce_args(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
+                              const uint8_t* codes, int64_t row_begin, int64_t row_end, int variant) {
+    CY_CHECK_ARG(z != nullptr, "z is null");
+    CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
+    CY_CHECK_ARG(N >= 2 && (N % 2) == 0, "N=%lld must be even (two stacked views)", (long long)N);
+    CY_CHECK_ARG(d >= 1 && ldz >= d, "d=%lld ldz=%lld", (long long)d, (long long)ldz);
+    CY_CHECK_ARG(labels != nullptr || codes != nullptr, "need labels or codes");
+    CY_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N, "rows [%lld,%lld) outside [0,%lld)",
+                 (long long)row_begin, (long long)row_end, (long long)N);
+    CY_CHECK_ARG(variant >= CY_SUPCON && variant <= CY_SELFPACED_SOFT, "unknown variant %d", variant);
+    return CY_OK;
+}
+
+// 0 = simt, 1 = tcgen05; negative = error
+static int resolve_path(int path, int dtype, int64_t N, int64_t d, int64_t ldz, const uint8_t* codes, int variant) {
+    const bool tc_ok = infonce_tc_supported(dtype, N, d, ldz, codes, variant);
+    if (path == CY_PATH_TCGEN05) {
+        if (!tc_ok) {
+            set_error("tcgen05 path needs bf16, d == 256, N %% 128 == 0, labels, variant SUPCON (got dtype=%d N=%lld d=%lld variant=%d)",
+                      dtype, (long long)N, (long long)d, variant);
+            return CY_ERR_UNSUPPORTED;
+        }
+        return 1;
+    }
+    if (path == CY_PATH_AUTO && tc_ok && N >= 1024) return 1;
+    if (d > 256) {
+        set_error("SIMT path supports d <= 256 (got %lld)", (long long)d);
+        return CY_ERR_UNSUPPORTED;
+    }
+    return 0;
+}
+
+}  // namespace cy
+
+using namespace cy;
+
+extern "C" {
+
+int cy_abi_version(void) { return CY_ABI_VERSION; }
+
+const char* cy_last_error(void) { return g_err; }
+
+int cy_device_sm_count(void) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    return n;
+}
+
+size_t cy_infonce_workspace_bytes(int64_t N, int64_t d, int dtype, int variant, int path) {
+    (void)variant;
+    if (path == CY_PATH_SIMT || dtype != CY_BF16) return 16;
+    return infonce_tc_workspace_bytes(N, d) + 16;
+}
+
+int cy_infonce_fwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, const uint8_t* codes,
+                   int64_t row_begin, int64_t row_end, float inv_t, int variant, int path, float* stats, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    int rc = check_infonce_args(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, variant);
+    if (rc) return rc;
+    CY_CHECK_ARG(stats != nullptr, "stats is null");
+    const int p = resolve_path(path, dtype, N, d, ldz, codes, variant);
+    if (p < 0) return p;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (p == 1) return infonce_fwd_tc(z, N, d, ldz, labels, row_begin, row_end, inv_t, stats, workspace, workspace_bytes, st);
+    return infonce_fwd_simt(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, inv_t, variant, 1, 0.f, stats, st);
+}
+
+int cy_infonce_fwd_pass2(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
+                         const uint8_t* codes, int64_t row_begin, int64_t row_end, float inv_t, int variant, float gamma,
+                         int path, float* stats, void* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace; (void)workspace_bytes;
+    int rc = check_infonce_args(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, variant);
+    if (rc) return rc;
+    CY_CHECK_ARG(variant != CY_SUPCON, "CY_SUPCON has no second pass");
+    if (path == CY_PATH_TCGEN05) { set_error("pass 2 runs on the SIMT path only"); return CY_ERR_UNSUPPORTED; }
+    if (d > 256) { set_error("SIMT path supports d <= 256 (got %lld)", (long long)d); return CY_ERR_UNSUPPORTED; }
+    return infonce_fwd_simt(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, inv_t, variant, 2, gamma, stats,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_infonce_finalize(int64_t N, int64_t row_begin, int64_t row_end, float inv_t, int variant, int pass, float* stats,
+                        float* out4, void* stream) {
+    (void)inv_t;
+    CY_CHECK_ARG(stats && out4, "null pointer");
+    CY_CHECK_ARG(pass == 1 || pass == 2, "pass must be 1 or 2");
+    return infonce_finalize(N, row_begin, row_end, variant, pass, stats, out4, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_infonce_bwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, const uint8_t* codes,
+                   int64_t row_begin, int64_t row_end, float inv_t, int variant, float gamma, int path, const float* stats,
+                   const float* gscale, void* dz, int64_t lddz, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_infonce_args(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, variant);
+    if (rc) return rc;
+    CY_CHECK_ARG(stats && gscale && dz && lddz >= d, "null pointer or lddz < d");
+    const int p = resolve_path(path, dtype, N, d, ldz, codes, variant);
+    if (p < 0) return p;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (p == 1)
+        return infonce_bwd_tc(z, N, d, ldz, labels, row_begin, row_end, inv_t, stats, gscale, dz, lddz, workspace,
+                              workspace_bytes, st);
+    return infonce_bwd_simt(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, inv_t, variant, gamma, stats, gscale, dz,
+                            lddz, st);
+}
+
+int cy_infonce_masks(int64_t N, const int32_t* labels, const uint8_t* codes, float* pos_mask, float* neg_mask, void* stream) {
+    CY_CHECK_ARG(N >= 2 && (N % 2) == 0 && (labels || codes), "bad arguments");
+    return infonce_masks(N, labels, codes, pos_mask, neg_mask, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_labels_canonicalize(const void* src, int src_kind, int64_t n, int32_t* dst, void* stream) {
+    CY_CHECK_ARG(src && dst && n >= 1 && (src_kind == 0 || src_kind == 1), "bad arguments");
+    return labels_canonicalize(src, src_kind, n, dst, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t cy_iic_workspace_bytes(int B, int K, int H, int W, int pad) {
+    if (B < 1 || K < 1 || H < 1 || W < 1 || pad < 0) return 0;
+    return iic_workspace_bytes(B, K, H, W, pad);
+}
+
+static int check_iic(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad) {
+    CY_CHECK_ARG(x && y, "null input");
+    CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
+    CY_CHECK_ARG(B >= 1 && K >= 1 && H >= 1 && W >= 1, "bad shape [%d,%d,%d,%d]", B, K, H, W);
+    CY_CHECK_ARG(pad >= 0, "negative padding %d", pad);
+    return CY_OK;
+}
+
+int cy_iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, float* joint, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+    int rc = check_iic(x, y, dtype, B, K, H, W, pad);
+    if (rc) return rc;
+    CY_CHECK_ARG(joint != nullptr, "joint is null");
+    return iic_joint(x, y, dtype, B, K, H, W, pad, joint, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_iic_epilogue(const float* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
+                    float* p00, float* p_ij, float* djoint, void* stream) {
+    CY_CHECK_ARG(joint && loss && p00 && K >= 1 && pad >= 0, "bad arguments");
+    return iic_epilogue(joint, K, pad, symmetric, lamda, eps, n_pixels, loss, p00, p_ij, djoint,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
+               const float* gscale, void* dx, void* dy, void* stream) {
+    int rc = check_iic(x, y, dtype, B, K, H, W, pad);
+    if (rc) return rc;
+    CY_CHECK_ARG(djoint && gscale && dx && dy, "null pointer");
+    return iic_bwd(x, y, dtype, B, K, H, W, pad, djoint, gscale, dx, dy, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,671 @@
+// IIC discrete-MI segmentation loss: joint accumulation, 900-float epilogue, adjoint.
+// Reference: contrastyou/losses/discreteMI.py:139-165 (IIDSegmentationLoss.forward), :225-243 (compute_joint_2D: the
+// F.conv2d with a B x H x W "filter"), :246-261 (padding == 0).  SURVEY.md Appendix A5/A6 for the closed forms.
+//
+// Data layout.  x, y: [B, K, H, W] contiguous.  A CTA stages one (TH x TW) pixel tile of one image in shared memory as
+// fp32 rows indexed [(hh * K + k) * XW + col] (hh = tile row incl. halo): consecutive (dy, k1) "roles" then sit on
+// consecutive shared-memory rows and, with XW/4 odd, 8 consecutive roles hit 8 distinct 16-byte bank groups.
+//
+// Forward (iic_joint_kernel): lane = role (dy, k1) [x k2-chunk], warp-level strips walk along w four pixels at a
+// time keeping a (4 + 2*PAD)-wide register window of x and broadcast float4 loads of y; every lane owns the
+// T x KC accumulators J[k1, k2chunk, dy, :].  Accumulators live in registers across all tiles of a persistent CTA
+// and are reduced once (shared-memory atomics, then one [K,K,T,T] partial per CTA); cy_iic_epilogue sums the partials
+// in a fixed order (deterministic).
+// Backward (iic_bwd_kernel): thread = 4 consecutive pixels x all output channels; dL/dJ (and its flipped transpose)
+// sit in shared memory and are read as warp-uniform float4 broadcasts.
+#include "common.cuh"
+
+namespace cy {
+
+constexpr int IIC_NT = 256;
+
+struct IICGeom {
+    int B, K, H, W, pad, T;
+    int TH, TW;          // tile (pixels)
+    int XW;              // shared row pitch (floats) of a halo tile row
+    int CO;              // smem column of the tile's first pixel column (so that float4 window loads are aligned)
+    int tiles_h, tiles_w, n_tiles;
+    int HH;              // TH + 2*pad
+};
+
+__host__ __device__ inline int iic_col_origin(int pad) {
+    // smallest CO >= pad with (CO + pad) % 4 == 0
+    int co = pad;
+    while ((co + pad) % 4) ++co;
+    return co;
+}
+
+// stage one halo tile of `src` (image b, tile origin h0,w0) into sm[(hh*K + k)*XW + c]; zero outside the image
+__device__ __forceinline__ void stage_tile(float* __restrict__ sm, const void* __restrict__ src, int dtype, const IICGeom& g,
+                                           int b, int h0, int w0, int halo) {
+    const int rows = g.TH + 2 * halo;
+    const int c_lo = g.CO - halo, c_hi = g.CO + g.TW + halo;   // [c_lo, c_hi)
+    const int ncol = c_hi - c_lo;
+    const int total = rows * g.K * ncol;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int c = idx % ncol;
+        const int rk = idx / ncol;
+        const int k = rk % g.K, hh = rk / g.K;
+        const int h = h0 + hh - halo, w = w0 + c - halo;
+        float v = 0.f;
+        if (h >= 0 && h < g.H && w >= 0 && w < g.W)
+            v = ld_as_float(src, dtype, (((size_t)b * g.K + k) * g.H + h) * g.W + w);
+        sm[(hh * g.K + k) * g.XW + c_lo + c] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- forward (fast)
+template <int PAD, int KC>
+__global__ void __launch_bounds__(IIC_NT)
+iic_joint_kernel(const void* __restrict__ x, const void* __restrict__ y, int dtype, IICGeom g, float* __restrict__ partials) {
+    constexpr int T = 2 * PAD + 1;
+    extern __shared__ __align__(16) float smem[];
+    const int K = g.K;
+    const int nchunk = (K + KC - 1) / KC;
+    const int R = T * K * nchunk;                 // roles
+    const int nslot = IIC_NT / R;
+    float* xs = smem;                                              // [(HH*K) * XW]
+    float* ys = xs + (size_t)g.HH * K * g.XW;                      // [(TH*K + KC) * YW], YW == XW
+    float* jsm = ys + (size_t)(g.TH * K + KC) * g.XW;              // [K*K*T*T]
+    const int nj = K * K * T * T;
+
+    const int tid = threadIdx.x;
+    const int slot = tid / R, role = tid % R;
+    const bool active = slot < nslot;
+    const int rr = role % (T * K), c2 = role / (T * K);            // rr = dy*K + k1
+    const int k2base = c2 * KC;
+
+    float acc[T][KC];
+#pragma unroll
+    for (int a = 0; a < T; ++a)
+#pragma unroll
+        for (int c = 0; c < KC; ++c) acc[a][c] = 0.f;
+
+    for (int i = tid; i < nj; i += IIC_NT) jsm[i] = 0.f;
+    // the KC padding rows behind the y tile are read (and their products discarded) when KC does not divide K
+    for (int i = tid; i < KC * g.XW; i += IIC_NT) ys[(size_t)g.TH * K * g.XW + i] = 0.f;
+
+    for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        const int b = tile / (g.tiles_h * g.tiles_w);
+        const int trem = tile % (g.tiles_h * g.tiles_w);
+        const int h0 = (trem / g.tiles_w) * g.TH, w0 = (trem % g.tiles_w) * g.TW;
+        __syncthreads();
+        stage_tile(xs, x, dtype, g, b, h0, w0, PAD);
+        stage_tile(ys - 0, y, dtype, g, b, h0, w0, 0);   // y tile: rows (h*K + k2), same pitch, columns at CO..
+        __syncthreads();
+        if (active) {
+            for (int h = slot; h < g.TH; h += nslot) {
+                const float* xr = xs + (size_t)(h * K + rr) * g.XW + (g.CO - PAD);
+                const float* yr = ys + (size_t)(h * K + k2base) * g.XW + g.CO;
+                float xw[4 + 2 * PAD];
+#pragma unroll
+                for (int e = 0; e < 2 * PAD; ++e) xw[4 + e] = xr[e];
+                for (int w = 0; w < g.TW; w += 4) {
+#pragma unroll
+                    for (int e = 0; e < 2 * PAD; ++e) xw[e] = xw[4 + e];
+                    const float4 nx = *reinterpret_cast<const float4*>(xr + 2 * PAD + w);
+                    xw[2 * PAD + 0] = nx.x; xw[2 * PAD + 1] = nx.y; xw[2 * PAD + 2] = nx.z; xw[2 * PAD + 3] = nx.w;
+#pragma unroll
+                    for (int kk = 0; kk < KC; ++kk) {
+                        const float4 yv = *reinterpret_cast<const float4*>(yr + (size_t)kk * g.XW + w);
+#pragma unroll
+                        for (int dx = 0; dx < T; ++dx) {
+                            float a = acc[dx][kk];
+                            a = fmaf(xw[dx + 0], yv.x, a);
+                            a = fmaf(xw[dx + 1], yv.y, a);
+                            a = fmaf(xw[dx + 2], yv.z, a);
+                            a = fmaf(xw[dx + 3], yv.w, a);
+                            acc[dx][kk] = a;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (active) {
+        const int dy = rr / K, k1 = rr % K;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            const int k2 = k2base + kk;
+            if (k2 < K) {
+#pragma unroll
+                for (int dx = 0; dx < T; ++dx) atomicAdd(&jsm[((k1 * K + k2) * T + dy) * T + dx], acc[dx][kk]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < nj; i += IIC_NT) partials[(size_t)blockIdx.x * nj + i] = jsm[i];
+}
+
+// ---------------------------------------------------------------------------------------------- forward (generic)
+// any K / pad: one J entry per thread iteration, two shared loads per FMA.  Correctness path for exotic shapes.
+__global__ void __launch_bounds__(IIC_NT)
+iic_joint_generic_kernel(const void* __restrict__ x, const void* __restrict__ y, int dtype, IICGeom g,
+                         float* __restrict__ partials) {
+    extern __shared__ __align__(16) float smem[];
+    const int K = g.K, T = g.T, pad = g.pad;
+    float* xs = smem;
+    float* ys = xs + (size_t)g.HH * K * g.XW;
+    const int nj = K * K * T * T;
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x, first = 1; tile < g.n_tiles; tile += gridDim.x, first = 0) {
+        const int b = tile / (g.tiles_h * g.tiles_w);
+        const int trem = tile % (g.tiles_h * g.tiles_w);
+        const int h0 = (trem / g.tiles_w) * g.TH, w0 = (trem % g.tiles_w) * g.TW;
+        __syncthreads();
+        stage_tile(xs, x, dtype, g, b, h0, w0, pad);
+        stage_tile(ys, y, dtype, g, b, h0, w0, 0);
+        __syncthreads();
+        for (int e = tid; e < nj; e += IIC_NT) {
+            const int dx = e % T, dy = (e / T) % T, k2 = (e / (T * T)) % K, k1 = e / (T * T * K);
+            float s = 0.f;
+            for (int h = 0; h < g.TH; ++h) {
+                const float* xr = xs + (size_t)((h + dy) * K + k1) * g.XW + g.CO - pad + dx;
+                const float* yr = ys + (size_t)(h * K + k2) * g.XW + g.CO;
+                for (int w = 0; w < g.TW; ++w) s = fmaf(xr[w], yr[w], s);
+            }
+            float* dst = partials + (size_t)blockIdx.x * nj + e;
+            *dst = first ? s : (*dst + s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- epilogue
+// One CTA.  Sums the per-CTA partial joints in a fixed order (fp64), then discreteMI.py:233-243 / :246-261 and
+// :154-165, and the analytic dLoss/dJoint.  All in fp64: 900 elements.
+__global__ void __launch_bounds__(256)
+iic_reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int nj, float* __restrict__ joint) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nj) return;
+    double s = 0.0;
+    for (int p = 0; p < n_partials; ++p) s += (double)partials[(size_t)p * nj + i];
+    joint[i] = (float)s;
+}
+
+__device__ double block_reduce_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    return t;
+}
+
+__device__ double block_reduce_min(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = red[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) t = fmin(t, red[i]);
+    return t;
+}
+
+// dynamic smem: double A[nj] (B matrix, [dd][k1][k2]), P[nj], G[nj], sdisp[TT], colsum[TT*K], rowsum[TT*K]
+__global__ void __launch_bounds__(256)
+iic_epilogue_kernel(const float* __restrict__ joint, int K, int pad, int symmetric, double lamda, double eps,
+                    double n_pixels, float* __restrict__ loss, float* __restrict__ p00, float* __restrict__ p_ij,
+                    float* __restrict__ djoint) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double red[8];
+    const int T = 2 * pad + 1, TT = T * T, KK = K * K, nj = KK * TT;
+    double* Bm = sm;
+    double* P = Bm + nj;
+    double* G = P + nj;
+    double* sd = G + nj;
+    double* asum = sd + TT;        // [TT][K]  sum over k1 -> function of k2 ("p_i_mat", dim 2)
+    double* bsum = asum + TT * K;  // [TT][K]  sum over k2 -> function of k1 ("p_j_mat", dim 3)
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // joint is [k1][k2][dd]; internal layout [dd][k1][k2]
+    auto JIDX = [&](int k1, int k2, int dd) { return (k1 * K + k2) * TT + dd; };
+    auto PIDX = [&](int dd, int k1, int k2) { return (dd * K + k1) * K + k2; };
+
+    double total = 1.0;
+    if (pad > 0) {
+        double mn = 1e300;
+        for (int i = tid; i < nj; i += nt) mn = fmin(mn, (double)joint[i]);
+        mn = block_reduce_min(mn, red);
+        for (int i = tid; i < nj; i += nt) {
+            const int dd = i % TT, k2 = (i / TT) % K, k1 = i / (TT * K);
+            Bm[PIDX(dd, k1, k2)] = (double)joint[i] - mn + 1e-8;
+        }
+        __syncthreads();
+        for (int dd = tid; dd < TT; dd += nt) {
+            double s = 0.0;
+            for (int e = 0; e < KK; ++e) s += Bm[dd * KK + e];
+            sd[dd] = s;
+        }
+        __syncthreads();
+        for (int i = tid; i < nj; i += nt) Bm[i] /= sd[i / KK];
+        __syncthreads();
+        double part = 0.0;
+        for (int i = tid; i < nj; i += nt) {
+            const int k2 = i % K, k1 = (i / K) % K, dd = i / KK;
+            const double c = symmetric ? 0.5 * (Bm[i] + Bm[PIDX(dd, k2, k1)]) : Bm[i];
+            P[i] = c;
+            part += c;
+        }
+        total = block_reduce_sum(part, red);
+        for (int i = tid; i < nj; i += nt) P[i] /= total;
+    } else {
+        for (int i = tid; i < nj; i += nt) Bm[i] = (double)joint[i] / n_pixels;   // TT == 1: layouts coincide
+        __syncthreads();
+        for (int i = tid; i < nj; i += nt) {
+            const int k2 = i % K, k1 = i / K;
+            P[i] = symmetric ? 0.5 * (Bm[i] + Bm[k2 * K + k1]) : Bm[i];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < TT * K; i += nt) {
+        const int dd = i / K, k = i % K;
+        double a = 0.0, b = 0.0;
+        for (int q = 0; q < K; ++q) {
+            a += P[PIDX(dd, q, k)];
+            b += P[PIDX(dd, k, q)];
+        }
+        asum[i] = a;
+        bsum[i] = b;
+    }
+    __syncthreads();
+    double lpart = 0.0, gpart = 0.0;
+    for (int i = tid; i < nj; i += nt) {
+        const int k2 = i % K, k1 = (i / K) % K, dd = i / KK;
+        const double p = P[i], a = asum[dd * K + k2], b = bsum[dd * K + k1];
+        lpart += -p * (log(p + eps) - lamda * log(a + eps) - lamda * log(b + eps));
+        const double gq = -(log(p + eps) + p / (p + eps) - lamda * (log(a + eps) + a / (a + eps)) -
+                            lamda * (log(b + eps) + b / (b + eps))) / (double)TT;
+        G[i] = gq;
+        gpart += gq * p;
+    }
+    const double L = block_reduce_sum(lpart, red);
+    const double gdotP = block_reduce_sum(gpart, red);
+    if (tid == 0) loss[0] = (float)(L / (double)TT);
+    for (int i = tid; i < KK; i += nt) p00[i] = (float)P[i];
+    if (p_ij)
+        for (int i = tid; i < nj; i += nt) p_ij[i] = (float)P[i];
+    if (!djoint) return;
+    if (pad > 0) {
+        for (int i = tid; i < nj; i += nt) G[i] = (G[i] - gdotP) / total;
+        __syncthreads();
+        // per displacement: dot = sum gB * B
+        for (int dd = tid; dd < TT; dd += nt) {
+            double dot = 0.0;
+            for (int k1 = 0; k1 < K; ++k1)
+                for (int k2 = 0; k2 < K; ++k2) {
+                    const double gb = symmetric ? 0.5 * (G[PIDX(dd, k1, k2)] + G[PIDX(dd, k2, k1)]) : G[PIDX(dd, k1, k2)];
+                    dot += gb * Bm[PIDX(dd, k1, k2)];
+                }
+            asum[dd] = dot;   // reuse
+        }
+        __syncthreads();
+        for (int i = tid; i < nj; i += nt) {
+            const int k2 = i % K, k1 = (i / K) % K, dd = i / KK;
+            const double gb = symmetric ? 0.5 * (G[i] + G[PIDX(dd, k2, k1)]) : G[i];
+            djoint[JIDX(k1, k2, dd)] = (float)((gb - asum[dd]) / sd[dd]);
+        }
+    } else {
+        for (int i = tid; i < nj; i += nt) {
+            const int k2 = i % K, k1 = i / K;
+            const double gb = symmetric ? 0.5 * (G[i] + G[k2 * K + k1]) : G[i];
+            djoint[i] = (float)(gb / n_pixels);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- backward
+// g tables in shared memory: gA[((k_in*T + dyy)*KP + k_out)*TP + dxx] for phase A (k_in = k1 over x, k_out = k2),
+// and the flipped transpose for phase B (k_in = k2 over y, k_out = k1, dy -> 2p-dy, dx -> 2p-dx).
+template <int PAD, int KC>
+__device__ __forceinline__ void bwd_phase(const float* __restrict__ tile, const float* __restrict__ gtab, const IICGeom& g,
+                                          int KP, int TP, int r, int q, int k_out_base, float (&acc)[KC][4]) {
+    constexpr int T = 2 * PAD + 1;
+    const int K = g.K;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+    for (int kin = 0; kin < K; ++kin) {
+#pragma unroll
+        for (int dyy = 0; dyy < T; ++dyy) {
+            const float* row = tile + (size_t)((r + dyy) * K + kin) * g.XW + (g.CO - PAD) + 4 * q;
+            float xw[4 + 2 * PAD];
+#pragma unroll
+            for (int e = 0; e < 2 * PAD; ++e) xw[e] = row[e];
+            const float4 nx = *reinterpret_cast<const float4*>(row + 2 * PAD);
+            xw[2 * PAD + 0] = nx.x; xw[2 * PAD + 1] = nx.y; xw[2 * PAD + 2] = nx.z; xw[2 * PAD + 3] = nx.w;
+            const float* gp = gtab + (size_t)((kin * T + dyy) * KP + k_out_base) * TP;
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+#pragma unroll
+                for (int dxx = 0; dxx < T; ++dxx) {
+                    const float gv = gp[c * TP + dxx];
+                    acc[c][0] = fmaf(gv, xw[dxx + 0], acc[c][0]);
+                    acc[c][1] = fmaf(gv, xw[dxx + 1], acc[c][1]);
+                    acc[c][2] = fmaf(gv, xw[dxx + 2], acc[c][2]);
+                    acc[c][3] = fmaf(gv, xw[dxx + 3], acc[c][3]);
+                }
+            }
+        }
+    }
+}
+
+template <int PAD, int KC>
+__global__ void __launch_bounds__(IIC_NT)
+iic_bwd_kernel(const void* __restrict__ x, const void* __restrict__ y, int dtype, IICGeom g, const float* __restrict__ djoint,
+               const float* __restrict__ gscale, void* __restrict__ dx_out, void* __restrict__ dy_out) {
+    constexpr int T = 2 * PAD + 1;
+    constexpr int TP = (T == 1) ? 1 : ((T <= 4) ? 4 : 8);
+    extern __shared__ __align__(16) float smem[];
+    const int K = g.K;
+    const int nchunk = (K + KC - 1) / KC;
+    const int KP = nchunk * KC;
+    float* xs = smem;
+    float* ys = xs + (size_t)g.HH * K * g.XW;
+    float* gA = ys + (size_t)g.HH * K * g.XW;
+    float* gB = gA + (size_t)K * T * KP * TP;
+    const int tid = threadIdx.x;
+    const float scale = gscale[0];
+
+    for (int i = tid; i < K * T * KP * TP; i += blockDim.x) {
+        const int dxx = i % TP, ko = (i / TP) % KP, dyy = (i / (TP * KP)) % T, kin = i / (TP * KP * T);
+        float a = 0.f, b = 0.f;
+        if (dxx < T && ko < K) {
+            a = djoint[((kin * K + ko) * T + dyy) * T + dxx] * scale;                       // g[k1=kin, k2=ko, dy, dx]
+            b = djoint[((ko * K + kin) * T + (T - 1 - dyy)) * T + (T - 1 - dxx)] * scale;   // g[k1=ko, k2=kin, flipped]
+        }
+        gA[i] = a;
+        gB[i] = b;
+    }
+
+    const int qpr = g.TW / 4;                 // 4-pixel groups per tile row
+    const int r = tid / qpr, q = tid % qpr;   // blockDim.x == TH * qpr
+
+    for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        const int b = tile / (g.tiles_h * g.tiles_w);
+        const int trem = tile % (g.tiles_h * g.tiles_w);
+        const int h0 = (trem / g.tiles_w) * g.TH, w0 = (trem % g.tiles_w) * g.TW;
+        __syncthreads();
+        stage_tile(xs, x, dtype, g, b, h0, w0, PAD);
+        stage_tile(ys, y, dtype, g, b, h0, w0, PAD);
+        __syncthreads();
+        const int h = h0 + r, w = w0 + 4 * q;
+        if (r < g.TH && h < g.H && w < g.W) {
+            float acc[KC][4];
+            for (int c2 = 0; c2 < nchunk; ++c2) {
+                // dL/dy[b, k2, h, w..w+3] = sum_{k1,dy,dx} g[k1,k2,dy,dx] x[b,k1,h+dy-p,w+dx-p]
+                bwd_phase<PAD, KC>(xs, gA, g, KP, TP, r, q, c2 * KC, acc);
+#pragma unroll
+                for (int c = 0; c < KC; ++c) {
+                    const int ko = c2 * KC + c;
+                    if (ko < K) {
+                        const size_t base = (((size_t)b * K + ko) * g.H + h) * g.W + w;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (w + e < g.W) st_from_float(dy_out, dtype, base + e, acc[c][e]);
+                    }
+                }
+                // dL/dx[b, k1, h, w..w+3] = sum_{k2,dy,dx} g[k1,k2,dy,dx] y[b,k2,h-dy+p,w-dx+p]
+                bwd_phase<PAD, KC>(ys, gB, g, KP, TP, r, q, c2 * KC, acc);
+#pragma unroll
+                for (int c = 0; c < KC; ++c) {
+                    const int ko = c2 * KC + c;
+                    if (ko < K) {
+                        const size_t base = (((size_t)b * K + ko) * g.H + h) * g.W + w;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (w + e < g.W) st_from_float(dx_out, dtype, base + e, acc[c][e]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// generic backward: any K / pad; one output element per thread, djoint read from global (L1-resident)
+__global__ void iic_bwd_generic_kernel(const void* __restrict__ x, const void* __restrict__ y, int dtype, int B, int K, int H,
+                                       int W, int pad, const float* __restrict__ djoint, const float* __restrict__ gscale,
+                                       void* __restrict__ dx_out, void* __restrict__ dy_out) {
+    const int T = 2 * pad + 1;
+    const size_t total = (size_t)B * K * H * W;
+    const float scale = gscale[0];
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int w = idx % W, h = (idx / W) % H, k = (idx / ((size_t)W * H)) % K, b = idx / ((size_t)W * H * K);
+        float sy = 0.f, sx = 0.f;
+        for (int ko = 0; ko < K; ++ko)
+            for (int dy = 0; dy < T; ++dy)
+                for (int dx = 0; dx < T; ++dx) {
+                    // dy-map: this element is y[b,k2=k]; partner x[b,k1=ko] at (h+dy-p, w+dx-p)
+                    int hh = h + dy - pad, ww = w + dx - pad;
+                    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                        sy = fmaf(djoint[((ko * K + k) * T + dy) * T + dx],
+                                  ld_as_float(x, dtype, (((size_t)b * K + ko) * H + hh) * W + ww), sy);
+                    // dx-map: this element is x[b,k1=k]; partner y[b,k2=ko] at (h-dy+p, w-dx+p)
+                    hh = h - dy + pad; ww = w - dx + pad;
+                    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                        sx = fmaf(djoint[((k * K + ko) * T + dy) * T + dx],
+                                  ld_as_float(y, dtype, (((size_t)b * K + ko) * H + hh) * W + ww), sx);
+                }
+        st_from_float(dy_out, dtype, idx, sy * scale);
+        st_from_float(dx_out, dtype, idx, sx * scale);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static int pick_kc(int K) {
+    const int opts[] = {4, 5, 8, 10, 16, 20};
+    for (int o : opts)
+        if (K <= o) return o;
+    return 8;   // chunked
+}
+
+static int sm_count_cached() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+static int pick_tw(int W, int maxtw) {
+    // multiple of 4, <= maxtw, minimising padded width then number of tiles
+    int best = 4, best_cost = 1 << 30;
+    for (int tw = 4; tw <= maxtw; tw += 4) {
+        const int tiles = (W + tw - 1) / tw;
+        const int cost = tiles * tw * 64 + tiles;   // padded pixels dominate
+        if (cost <= best_cost) { best_cost = cost; best = tw; }
+    }
+    return best;
+}
+
+static IICGeom make_geom(int B, int K, int H, int W, int pad, int TH, int TW) {
+    IICGeom g;
+    g.B = B; g.K = K; g.H = H; g.W = W; g.pad = pad; g.T = 2 * pad + 1;
+    g.TH = TH; g.TW = TW;
+    g.CO = iic_col_origin(pad);
+    int xw = g.CO + TW + pad;
+    xw = (xw + 3) / 4 * 4;
+    if (((xw / 4) & 1) == 0) xw += 4;       // XW/4 odd: conflict-free role rows
+    g.XW = xw;
+    g.HH = TH + 2 * pad;
+    g.tiles_h = (H + TH - 1) / TH;
+    g.tiles_w = (W + TW - 1) / TW;
+    g.n_tiles = B * g.tiles_h * g.tiles_w;
+    return g;
+}
+
+struct JointPlan {
+    IICGeom g;
+    int kc;          // 0 -> generic kernel
+    size_t smem;
+    int grid;
+};
+
+static JointPlan plan_joint(int B, int K, int H, int W, int pad) {
+    JointPlan p;
+    const int T = 2 * pad + 1;
+    const int kc = pick_kc(K);
+    const int nchunk = (K + kc - 1) / kc;
+    const bool fast = pad <= 3 && T * K * nchunk <= IIC_NT && T * kc <= 100;
+    const int TW = pick_tw(W, 64);
+    int TH = 8;
+    if (fast) {
+        const int nslot = IIC_NT / (T * K * nchunk);
+        TH = nslot < 4 ? 4 : (nslot > 16 ? 16 : nslot);
+    }
+    if (TH > H) TH = H;
+    const size_t budget = 100 * 1024;
+    for (;;) {
+        p.g = make_geom(B, K, H, W, pad, TH, TW);
+        p.smem = ((size_t)p.g.HH * K * p.g.XW + (size_t)(TH * K + kc) * p.g.XW + (size_t)K * K * T * T) * sizeof(float);
+        if (p.smem <= budget || TH <= 1) break;
+        TH = TH / 2;
+    }
+    p.kc = fast ? kc : 0;
+    const int sms = sm_count_cached();
+    p.grid = p.g.n_tiles < 2 * sms ? p.g.n_tiles : 2 * sms;
+    if (p.grid < 1) p.grid = 1;
+    return p;
+}
+
+size_t iic_workspace_bytes(int B, int K, int H, int W, int pad) {
+    const JointPlan p = plan_joint(B, K, H, W, pad);
+    const int T = 2 * pad + 1;
+    return (size_t)p.grid * K * K * T * T * sizeof(float);
+}
+
+template <int PAD, int KC>
+static int launch_joint(const void* x, const void* y, int dtype, const JointPlan& p, float* partials, cudaStream_t st) {
+    auto k = iic_joint_kernel<PAD, KC>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) { set_error("iic_joint smem attr (%zu B): %s", p.smem, cudaGetErrorString(e)); return (int)e; }
+    k<<<p.grid, IIC_NT, p.smem, st>>>(x, y, dtype, p.g, partials);
+    CY_CHECK_LAUNCH("iic_joint");
+    return CY_OK;
+}
+
+#define IIC_DISPATCH_KC(FN, PADV, ...)                                   \
+    switch (kc) {                                                        \
+        case 4: return FN<PADV, 4>(__VA_ARGS__);                         \
+        case 5: return FN<PADV, 5>(__VA_ARGS__);                         \
+        case 8: return FN<PADV, 8>(__VA_ARGS__);                         \
+        case 10: return FN<PADV, 10>(__VA_ARGS__);                       \
+        case 16: return FN<PADV, 16>(__VA_ARGS__);                       \
+        case 20: return FN<PADV, 20>(__VA_ARGS__);                       \
+    }
+
+#define IIC_DISPATCH(FN, ...)                                            \
+    switch (pad) {                                                       \
+        case 0: IIC_DISPATCH_KC(FN, 0, __VA_ARGS__) break;               \
+        case 1: IIC_DISPATCH_KC(FN, 1, __VA_ARGS__) break;               \
+        case 2: IIC_DISPATCH_KC(FN, 2, __VA_ARGS__) break;               \
+        case 3: IIC_DISPATCH_KC(FN, 3, __VA_ARGS__) break;               \
+    }
+
+static int dispatch_joint(int pad, int kc, const void* x, const void* y, int dtype, const JointPlan& p, float* partials,
+                          cudaStream_t st) {
+    IIC_DISPATCH(launch_joint, x, y, dtype, p, partials, st)
+    set_error("iic_joint: no instantiation for pad=%d kc=%d", pad, kc);
+    return CY_ERR_UNSUPPORTED;
+}
+
+int iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, float* joint, void* workspace,
+              size_t workspace_bytes, cudaStream_t st) {
+    const JointPlan p = plan_joint(B, K, H, W, pad);
+    const int T = 2 * pad + 1, nj = K * K * T * T;
+    const size_t need = (size_t)p.grid * nj * sizeof(float);
+    CY_CHECK_ARG(workspace && workspace_bytes >= need, "iic_joint: workspace %zu < %zu", workspace_bytes, need);
+    float* partials = reinterpret_cast<float*>(workspace);
+    int rc;
+    if (p.kc) {
+        rc = dispatch_joint(pad, p.kc, x, y, dtype, p, partials, st);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(iic_joint_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+        if (e != cudaSuccess) { set_error("iic_joint_generic smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        iic_joint_generic_kernel<<<p.grid, IIC_NT, p.smem, st>>>(x, y, dtype, p.g, partials);
+        CY_CHECK_LAUNCH("iic_joint_generic");
+        rc = CY_OK;
+    }
+    if (rc != CY_OK) return rc;
+    iic_reduce_partials_kernel<<<(nj + 255) / 256, 256, 0, st>>>(partials, p.grid, nj, joint);
+    CY_CHECK_LAUNCH("iic_reduce_partials");
+    return CY_OK;
+}
+
+int iic_epilogue(const float* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
+                 float* p00, float* p_ij, float* djoint, cudaStream_t st) {
+    const int T = 2 * pad + 1, TT = T * T, nj = K * K * TT;
+    const size_t smem = ((size_t)3 * nj + TT + 2 * TT * K) * sizeof(double);
+    if (smem > 200 * 1024) { set_error("iic_epilogue: K=%d pad=%d needs %zu B of shared memory", K, pad, smem); return CY_ERR_UNSUPPORTED; }
+    cudaError_t e = cudaFuncSetAttribute(iic_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("iic_epilogue smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    iic_epilogue_kernel<<<1, 256, smem, st>>>(joint, K, pad, symmetric, (double)lamda, (double)eps, n_pixels, loss, p00, p_ij, djoint);
+    CY_CHECK_LAUNCH("iic_epilogue");
+    return CY_OK;
+}
+
+struct BwdPlan {
+    IICGeom g;
+    int kc;
+    size_t smem;
+    int grid, threads;
+};
+
+template <int PAD, int KC>
+static int launch_bwd(const void* x, const void* y, int dtype, const BwdPlan& p, const float* djoint, const float* gscale,
+                      void* dx, void* dy, cudaStream_t st) {
+    auto k = iic_bwd_kernel<PAD, KC>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) { set_error("iic_bwd smem attr (%zu B): %s", p.smem, cudaGetErrorString(e)); return (int)e; }
+    k<<<p.grid, p.threads, p.smem, st>>>(x, y, dtype, p.g, djoint, gscale, dx, dy);
+    CY_CHECK_LAUNCH("iic_bwd");
+    return CY_OK;
+}
+
+static int dispatch_bwd(int pad, int kc, const void* x, const void* y, int dtype, const BwdPlan& p, const float* djoint,
+                        const float* gscale, void* dx, void* dy, cudaStream_t st) {
+    IIC_DISPATCH(launch_bwd, x, y, dtype, p, djoint, gscale, dx, dy, st)
+    set_error("iic_bwd: no instantiation for pad=%d kc=%d", pad, kc);
+    return CY_ERR_UNSUPPORTED;
+}
+
+int iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
+            const float* gscale, void* dx, void* dy, cudaStream_t st) {
+    const int T = 2 * pad + 1;
+    if (pad <= 3) {
+        BwdPlan p;
+        p.kc = pick_kc(K);
+        const int nchunk = (K + p.kc - 1) / p.kc, KP = nchunk * p.kc;
+        const int TP = (T == 1) ? 1 : ((T <= 4) ? 4 : 8);
+        const int TW = W >= 32 ? 32 : (W + 3) / 4 * 4;
+        int TH = IIC_NT / (TW / 4);
+        if (TH > H) TH = H;
+        const size_t budget = 110 * 1024;
+        for (;;) {
+            p.g = make_geom(B, K, H, W, pad, TH, TW);
+            p.smem = ((size_t)2 * p.g.HH * K * p.g.XW + (size_t)2 * K * T * KP * TP) * sizeof(float);
+            if (p.smem <= budget || TH <= 1) break;
+            TH /= 2;
+        }
+        if (p.smem <= 200 * 1024) {
+            p.threads = TH * (TW / 4);
+            if (p.threads < 32) p.threads = 32;
+            const int sms = sm_count_cached();
+            p.grid = p.g.n_tiles < 4 * sms ? p.g.n_tiles : 4 * sms;
+            return dispatch_bwd(pad, p.kc, x, y, dtype, p, djoint, gscale, dx, dy, st);
+        }
+    }
+    const size_t total = (size_t)B * K * H * W;
+    const int grid = (int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535);
+    iic_bwd_generic_kernel<<<grid, 256, 0, st>>>(x, y, dtype, B, K, H, W, pad, djoint, gscale, dx, dy);
+    CY_CHECK_LAUNCH("iic_bwd_generic");
+    return CY_OK;
+}
+
+}  // namespace cy

@@ -1,0 +1,242 @@
+"""Drop-in InfoNCE / supervised-contrastive losses backed by the sm_100a kernels of libcontrastyou_b200.so.
+
+Mirrors ``contrastyou/losses/contrastive.py`` of the reference: same class names, constructor and ``forward``
+signatures, side attributes and exceptions, so the hooks in ``semi_seg/hooks/infonce.py`` (:125-127, :163-167,
+:222-245) can hold these modules unchanged.  The modules own no parameters and no buffers (checkpoint
+compatibility, ``contrastyou/nn.py:129-138``).
+
+What differs by design: the 2n x 2n similarity / mask matrices are never materialised.  The forward makes one or
+two tiled sweeps that produce per-row statistics, the backward one sweep that rebuilds each tile and applies
+dZ = (1/t) (G + G^T) Z.  ``sim_exp`` / ``sim_logits`` / ``pos_mask`` / ``neg_mask`` /
+``sp_mask`` are computed lazily, only when a caller reads them (the hooks do on the first batch of an epoch).
+"""
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from .. import _lib as L
+
+__all__ = ["is_normalized", "SupConLoss1", "SelfPacedSupConLoss", "info_nce"]
+
+
+def is_normalized(feature: Tensor, dim=1):
+    """contrastive.py:9-11 — evaluated in the input dtype, exactly like the reference (bf16 / fp16 unit rows pass)."""
+    norms = feature.norm(dim=dim)
+    return torch.allclose(norms, torch.ones_like(norms))
+
+
+# ----------------------------------------------------------------------------------------------------- labels / masks
+def _canonical_labels(target, n: int, device) -> Tensor:
+    """[2n] int32 labels whose integer equality reproduces the reference comparison (contrastive.py:38-44).
+
+    python lists go through ``torch.Tensor(list)`` in the reference, i.e. float32 (labels >= 2**24 collide, -0.0 == 0.0,
+    NaN equals nothing); tensors are compared in their own dtype."""
+    lib = L.lib()
+    if isinstance(target, list):
+        target = torch.tensor(target, dtype=torch.float32)
+    if not isinstance(target, Tensor):
+        raise TypeError(f"target must be a list or a Tensor, got {type(target)}")
+    assert target.dim() == 1 and target.shape[0] == n, (target.shape, n)
+    target = target.to(device=device, non_blocking=True)
+    out = torch.empty(2 * n, dtype=torch.int32, device=device)
+    if target.dtype in (torch.float32, torch.float16, torch.bfloat16):
+        src, kind = target.to(torch.float32).contiguous(), 0      # exact widening
+    elif target.dtype in (torch.int32, torch.int16, torch.int8, torch.uint8, torch.bool):
+        src, kind = target.to(torch.int32).contiguous(), 1
+    else:
+        # 64-bit types: rank the distinct values (exact for any value range; costs one sort)
+        if target.dtype.is_floating_point:
+            target = torch.where(target == 0, torch.zeros_like(target), target)     # -0.0 == +0.0
+            nan = target != target
+            if bool(nan.any()):
+                raise ValueError("NaN labels are not supported for float64 targets")
+        src, kind = torch.unique(target, return_inverse=True)[1].to(torch.int32).contiguous(), 1
+    L.check(lib.cy_labels_canonicalize(src.data_ptr(), kind, n, out.data_ptr(), L.stream_ptr()), "cy_labels_canonicalize")
+    return out
+
+
+def _mask_codes(mask: Tensor, n: int, device) -> Tensor:
+    """explicit ``mask=`` path (contrastive.py:33-36): 1 -> positive, 0 -> negative, anything else -> neither."""
+    assert mask.shape == torch.Size([n, n])
+    mask = mask.to(device)
+    codes = torch.full((n, n), 2, dtype=torch.uint8, device=device)
+    codes[mask == 0] = 0
+    codes[mask == 1] = 1
+    return codes.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------- autograd glue
+class _InfoNCEFunction(torch.autograd.Function):
+    """z [N, d] (both views stacked) -> (loss, out4).  Rows [row_begin, row_end) are the ones this process owns."""
+
+    @staticmethod
+    def forward(ctx, z, labels, codes, inv_t, variant, gamma, path, row_begin, row_end, gather_stats):
+        lib = L.lib()
+        N, d = z.shape
+        dt = L.dtype_code(z)
+        st = L.stream_ptr()
+        stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=z.device)
+        out4 = torch.zeros(4, dtype=torch.float32, device=z.device)
+        ws_bytes = lib.cy_infonce_workspace_bytes(N, d, dt, variant, path)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+        lp, cp = L.ptr(labels), L.ptr(codes)
+        L.check(lib.cy_infonce_fwd(z.data_ptr(), dt, N, d, z.stride(0), lp, cp, row_begin, row_end, inv_t, variant, path,
+                                   stats.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd")
+        L.check(lib.cy_infonce_finalize(N, row_begin, row_end, inv_t, variant, 1, stats.data_ptr(), out4.data_ptr(), st),
+                "cy_infonce_finalize")
+        if variant != L.CY_SUPCON:
+            L.check(lib.cy_infonce_fwd_pass2(z.data_ptr(), dt, N, d, z.stride(0), lp, cp, row_begin, row_end, inv_t, variant,
+                                             gamma, L.CY_PATH_SIMT, stats.data_ptr(), ws.data_ptr(), ws_bytes, st),
+                    "cy_infonce_fwd_pass2")
+            L.check(lib.cy_infonce_finalize(N, row_begin, row_end, inv_t, variant, 2, stats.data_ptr(), out4.data_ptr(), st),
+                    "cy_infonce_finalize")
+        if gather_stats is not None:
+            gather_stats(stats, out4)       # sharded: all-gather the row statistics, all-reduce the scalars
+        ctx.save_for_backward(z, labels, codes, stats, ws)
+        ctx.cfg = (inv_t, variant, gamma, path, row_begin, row_end)
+        ctx.mark_non_differentiable(out4)
+        return out4[0].clone(), out4
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_out4):
+        lib = L.lib()
+        z, labels, codes, stats, ws = ctx.saved_tensors
+        inv_t, variant, gamma, path, row_begin, row_end = ctx.cfg
+        N, d = z.shape
+        gscale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        dz = torch.zeros_like(z) if (row_begin, row_end) != (0, N) else torch.empty_like(z)
+        L.check(lib.cy_infonce_bwd(z.data_ptr(), L.dtype_code(z), N, d, z.stride(0), L.ptr(labels), L.ptr(codes), row_begin,
+                                   row_end, inv_t, variant, gamma, path, stats.data_ptr(), gscale.data_ptr(), dz.data_ptr(),
+                                   dz.stride(0), ws.data_ptr(), ws.numel(), L.stream_ptr()), "cy_infonce_bwd")
+        return dz, None, None, None, None, None, None, None, None, None
+
+
+def info_nce(z: Tensor, labels: Optional[Tensor], codes: Optional[Tensor], temperature: float, variant: int = L.CY_SUPCON,
+             gamma: float = 1e6, path: int = L.CY_PATH_AUTO, rows=None, gather_stats=None):
+    """Functional entry: z [N, d] stacked views, int32 labels [N] (tiled) or uint8 codes [n, n] -> (loss, out4)."""
+    L.require_cuda(z, labels, codes)
+    if z.dim() != 2:
+        raise ValueError(f"expected [N, d] embeddings, got {tuple(z.shape)}")
+    if z.stride(1) != 1:
+        z = z.contiguous()
+    N = z.shape[0]
+    rb, re = (0, N) if rows is None else rows
+    return _InfoNCEFunction.apply(z, labels, codes, float(1.0 / temperature), int(variant), float(gamma), int(path),
+                                  int(rb), int(re), gather_stats)
+
+
+# ----------------------------------------------------------------------------------------------------- modules
+class _ContrastBase(nn.Module):
+    _variant = L.CY_SUPCON
+
+    def _prepare(self, proj_feat1, proj_feat2, target, mask):
+        L.require_cuda(proj_feat1, proj_feat2)
+        batch_size = proj_feat1.size(0)
+        device = proj_feat2.device
+        labels = codes = None
+        if mask is not None:
+            assert mask.shape == torch.Size([batch_size, batch_size])
+            codes = _mask_codes(mask, batch_size, device)
+        elif target is not None:
+            labels = _canonical_labels(target, batch_size, device)
+        else:  # SimCLR: only the twin view is positive
+            labels = torch.arange(batch_size, dtype=torch.int32, device=device).repeat(2)
+        assert is_normalized(proj_feat1) and is_normalized(proj_feat2), f"features need to be normalized first"
+        assert proj_feat1.shape == proj_feat2.shape, (proj_feat1.shape, proj_feat2.shape)
+        z = torch.cat([proj_feat1, proj_feat2], dim=0)
+        return z, labels, codes
+
+    # ---- lazily evaluated side channels (contrastive.py:79-82; read at semi_seg/hooks/infonce.py:235-242) ----
+    def _stash(self, z, labels, codes):
+        self._dbg = (z.detach(), labels, codes)
+        self._dbg_cache = {}
+
+    def _dense(self, name):
+        if not hasattr(self, "_dbg"):
+            raise AttributeError(name)
+        if name not in self._dbg_cache:
+            z, labels, codes = self._dbg
+            N = z.shape[0]
+            if name in ("pos_mask", "neg_mask"):
+                pos = torch.empty(N, N, dtype=torch.float32, device=z.device)
+                neg = torch.empty(N, N, dtype=torch.float32, device=z.device)
+                L.check(L.lib().cy_infonce_masks(N, L.ptr(labels), L.ptr(codes), pos.data_ptr(), neg.data_ptr(),
+                                                 L.stream_ptr()), "cy_infonce_masks")
+                self._dbg_cache.update(pos_mask=pos, neg_mask=neg)
+            else:  # plotting only: plain torch, follows contrastive.py:14-20 (shift by the global max)
+                zf = z.float()
+                logits = torch.mm(zf, zf.t()) / self._t
+                logits = logits - logits.max()
+                self._dbg_cache.update(sim_logits=logits, sim_exp=torch.exp(logits))
+        return self._dbg_cache[name]
+
+    sim_exp = property(lambda self: self._dense("sim_exp"))
+    sim_logits = property(lambda self: self._dense("sim_logits"))
+    pos_mask = property(lambda self: self._dense("pos_mask"))
+    neg_mask = property(lambda self: self._dense("neg_mask"))
+
+
+class SupConLoss1(_ContrastBase):
+    """contrastive.py:23-100.  ``path`` (keyword-only extra) pins the kernel family: "auto" | "simt" | "tcgen05"."""
+
+    def __init__(self, temperature=0.07, exclude_other_pos=False, *, path: str = "auto"):
+        super().__init__()
+        self._t = temperature
+        self._exclude_pos = exclude_other_pos
+        self._path = {"auto": L.CY_PATH_AUTO, "simt": L.CY_PATH_SIMT, "tcgen05": L.CY_PATH_TCGEN05}[path]
+
+    def forward(self, proj_feat1, proj_feat2, target=None, mask: Tensor = None, **kwargs):
+        z, labels, codes = self._prepare(proj_feat1, proj_feat2, target, mask)
+        variant = L.CY_SUPCON_EXCLUDE if self._exclude_pos else L.CY_SUPCON
+        loss, _ = info_nce(z, labels, codes, self._t, variant, path=self._path)
+        self._stash(z, labels, codes)
+        if torch.isnan(loss):
+            raise RuntimeError(loss)
+        return loss
+
+
+class SelfPacedSupConLoss(_ContrastBase):
+    """contrastive.py:103-212."""
+
+    def __repr__(self):
+        return f"{self.__class__.__name__} with T: {self._t}, method: {self._weight_update} gamma: {self.__gamma}"
+
+    def __init__(self, temperature=0.07, weight_update="hard", correct_grad=False, **kwargs):
+        super().__init__()
+        self._t = temperature
+        self._weight_update = weight_update
+        self.__gamma = 1e6
+        self._correct_grad = correct_grad
+
+    def forward(self, proj_feat1, proj_feat2, target=None, mask: Tensor = None, **kwargs):
+        z, labels, codes = self._prepare(proj_feat1, proj_feat2, target, mask)
+        variant = L.CY_SELFPACED_HARD if self._weight_update == "hard" else L.CY_SELFPACED_SOFT
+        loss, out4 = info_nce(z, labels, codes, self._t, variant, gamma=self.__gamma, path=L.CY_PATH_SIMT)
+        self._stash(z, labels, codes)
+        # contrastive.py:179-181 — a python float (host sync, as in the reference)
+        self.downgrade_ratio = (out4[1] / out4[2]).item()
+        if self._correct_grad:
+            if self.downgrade_ratio > 0:
+                loss = loss / self.downgrade_ratio
+        if torch.isnan(loss):
+            raise RuntimeError(loss)
+        return loss
+
+    @property
+    def sp_mask(self):
+        """contrastive.py:178, :197-204 — dense self-paced weights, rebuilt on demand (plotting only)."""
+        logits, e, pos, neg = self.sim_logits, self.sim_exp, self.pos_mask, self.neg_mask
+        llh = logits - torch.log((e * pos).sum(1, keepdim=True) + (e * neg).sum(1, keepdim=True) + 1e-16)
+        if self._weight_update == "hard":
+            w = (-llh <= self.__gamma).float()
+        else:
+            w = torch.max(1 + llh / self.__gamma, torch.zeros_like(llh))
+        return torch.max(w, 1 - pos)
+
+    def set_gamma(self, gamma):
+        self.__gamma = float(gamma)
+
+    @property
+    def age_param(self):
+        return self.__gamma

@@ -1,0 +1,201 @@
+"""Drop-in IIC discrete mutual-information losses backed by libcontrastyou_b200.so.
+
+Mirrors ``contrastyou/losses/discreteMI.py``: ``IIDSegmentationLoss`` (:127-170), ``IIDLoss`` (:90-124) and the
+joint builders ``compute_joint_2D`` (:225-243), ``compute_joint_2D_with_padding_zeros`` (:246-261), ``compute_joint``
+(:201-222), with unchanged signatures / attributes / exceptions (call sites: semi_seg/hooks/discretemi.py:47-76,
+:99-113, ccblock.py:315-339, midl.py:44-54, cc.py:39,:144-146).
+
+The reference builds the joint with ``F.conv2d`` using a B x H x W "filter"; here one streaming kernel accumulates
+the K x K x T x T joint straight from the two probability maps (cy_iic_joint), a single-CTA kernel does the 900-float
+normalisation / entropy epilogue together with its analytic derivative (cy_iic_epilogue) and one kernel applies the
+adjoint to produce both input gradients (cy_iic_bwd).
+"""
+import math
+import sys
+
+import torch
+from torch import Tensor, nn
+
+from .. import _lib as L
+
+__all__ = ["IIDSegmentationLoss", "IIDLoss", "compute_joint", "compute_joint_2D", "compute_joint_2D_with_padding_zeros",
+           "raw_joint", "simplex"]
+
+
+def simplex(t: Tensor, axis=1) -> bool:
+    """contrastyou/utils/general.py:68-77."""
+    _sum = t.sum(axis).type(torch.float32)
+    return torch.allclose(_sum, torch.ones_like(_sum, dtype=torch.float32), rtol=1e-4, atol=1e-4)
+
+
+def _check_pair(x: Tensor, y: Tensor):
+    L.require_cuda(x, y)
+    if x.dim() != 4 or x.shape != y.shape:
+        raise ValueError(f"expected two [B, K, H, W] maps of equal shape, got {tuple(x.shape)} and {tuple(y.shape)}")
+    if y.dtype != x.dtype:
+        y = y.to(x.dtype)
+    return x.contiguous(), y.contiguous()
+
+
+def _joint_forward(x, y, padding):
+    lib = L.lib()
+    B, K, H, W = x.shape
+    T = 2 * padding + 1
+    joint = torch.empty(K, K, T, T, dtype=torch.float32, device=x.device)
+    ws_bytes = lib.cy_iic_workspace_bytes(B, K, H, W, padding)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    L.check(lib.cy_iic_joint(x.data_ptr(), y.data_ptr(), L.dtype_code(x), B, K, H, W, padding, joint.data_ptr(),
+                             ws.data_ptr(), ws_bytes, L.stream_ptr()), "cy_iic_joint")
+    return joint
+
+
+def _joint_backward(x, y, padding, djoint, gscale):
+    lib = L.lib()
+    B, K, H, W = x.shape
+    dx, dy = torch.empty_like(x), torch.empty_like(y)
+    L.check(lib.cy_iic_bwd(x.data_ptr(), y.data_ptr(), L.dtype_code(x), B, K, H, W, padding, djoint.data_ptr(),
+                           gscale.data_ptr(), dx.data_ptr(), dy.data_ptr(), L.stream_ptr()), "cy_iic_bwd")
+    return dx, dy
+
+
+class _RawJoint(torch.autograd.Function):
+    """Differentiable raw joint J[k1,k2,dy,dx] = sum_{b,h,w} x[b,k1,h+dy-p,w+dx-p] y[b,k2,h,w] — what the reference's
+    ``F.conv2d(x^T, weight=y^T, padding=p)`` returns (discreteMI.py:227-232)."""
+
+    @staticmethod
+    def forward(ctx, x, y, padding):
+        ctx.save_for_backward(x, y)
+        ctx.padding = padding
+        return _joint_forward(x, y, padding)
+
+    @staticmethod
+    def backward(ctx, gJ):
+        x, y = ctx.saved_tensors
+        one = torch.ones(1, dtype=torch.float32, device=x.device)
+        dx, dy = _joint_backward(x, y, ctx.padding, gJ.to(torch.float32).contiguous(), one)
+        return dx, dy, None
+
+
+def raw_joint(x_out: Tensor, x_tf_out: Tensor, padding: int = 0) -> Tensor:
+    x, y = _check_pair(x_out, x_tf_out)
+    return _RawJoint.apply(x, y, int(padding))
+
+
+def compute_joint_2D(x_out: Tensor, x_tf_out: Tensor, *, symmetric: bool = True, padding: int = 0):
+    """discreteMI.py:225-243 — [T, T, K, K] joint with the reference's min-shift / normalisation quirks."""
+    p_i_j = raw_joint(x_out, x_tf_out, padding)
+    p_i_j = p_i_j - p_i_j.min().detach() + 1e-8
+    p_i_j = p_i_j.permute(2, 3, 0, 1)
+    p_i_j = p_i_j / p_i_j.sum(dim=[2, 3], keepdim=True)
+    if symmetric:
+        p_i_j = (p_i_j + p_i_j.permute(0, 1, 3, 2)) / 2.0
+    p_i_j = p_i_j / p_i_j.sum()
+    return p_i_j.contiguous()
+
+
+def compute_joint_2D_with_padding_zeros(x_out: Tensor, x_tf_out: Tensor, *, symmetric: bool = True):
+    """discreteMI.py:246-261 — [1, 1, K, K], divided by the pixel count, no shift / renormalisation."""
+    k = x_out.shape[1]
+    n = x_out.shape[0] * x_out.shape[2] * x_out.shape[3]
+    p_i_j = raw_joint(x_out, x_tf_out, 0).view(k, k) / n
+    if symmetric:
+        p_i_j = (p_i_j + p_i_j.t()) / 2.0
+    return p_i_j.view(1, 1, k, k).contiguous()
+
+
+def compute_joint(x_out: Tensor, x_tf_out: Tensor, symmetric=True) -> Tensor:
+    """discreteMI.py:201-222 — [K, K] joint of two [bn, K] simplices."""
+    assert simplex(x_out), f"x_out not normalized."
+    assert simplex(x_tf_out), f"x_tf_out not normalized."
+    bn, k = x_out.shape
+    assert x_tf_out.size()[0] == bn and x_tf_out.size()[1] == k
+    p_i_j = raw_joint(x_out.reshape(bn, k, 1, 1), x_tf_out.reshape(bn, k, 1, 1), 0).view(k, k)
+    if symmetric:
+        p_i_j = (p_i_j + p_i_j.t()) / 2.0
+    p_i_j = p_i_j / p_i_j.sum()
+    return p_i_j.contiguous()
+
+
+class _IIDSegFunction(torch.autograd.Function):
+    """(x, y) -> (loss, p_i_j[0][0]) with the fused epilogue; ``reduce_joint`` all-reduces the raw joint when the batch
+    is sharded over ranks (the epilogue is non-linear in J, so it must see the global joint)."""
+
+    @staticmethod
+    def forward(ctx, x, y, padding, symmetric, lamda, eps, reduce_joint):
+        lib = L.lib()
+        B, K, H, W = x.shape
+        T = 2 * padding + 1
+        joint = _joint_forward(x, y, padding)
+        n_pixels = float(B * H * W)
+        if reduce_joint is not None:
+            n_pixels = reduce_joint(joint, n_pixels)
+        loss = torch.empty(1, dtype=torch.float32, device=x.device)
+        p00 = torch.empty(K, K, dtype=torch.float32, device=x.device)
+        djoint = torch.empty(K, K, T, T, dtype=torch.float32, device=x.device)
+        L.check(lib.cy_iic_epilogue(joint.data_ptr(), K, padding, int(bool(symmetric)), float(lamda), float(eps), n_pixels,
+                                    loss.data_ptr(), p00.data_ptr(), None, djoint.data_ptr(), L.stream_ptr()),
+                "cy_iic_epilogue")
+        ctx.save_for_backward(x, y, djoint)
+        ctx.padding = padding
+        ctx.mark_non_differentiable(p00)
+        return loss.reshape(()), p00
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_p00):
+        x, y, djoint = ctx.saved_tensors
+        gscale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        dx, dy = _joint_backward(x, y, ctx.padding, djoint, gscale)
+        return dx, dy, None, None, None, None, None
+
+
+class IIDSegmentationLoss(nn.Module):
+    """discreteMI.py:127-170."""
+
+    def __init__(self, lamda=1.0, padding=0, eps: float = 1e-5, symmetric: bool = False) -> None:
+        super(IIDSegmentationLoss, self).__init__()
+        self.lamda = lamda
+        self.padding = padding
+        self._eps = eps
+        self.symmetric = symmetric
+        self._reduce_joint = None      # set by contrast_you_b200.distributed.shard_iic_loss
+
+    def forward(self, x_out: Tensor, x_tf_out: Tensor, mask: Tensor = None) -> Tensor:
+        if mask is not None:
+            x_out *= mask              # in place, like the reference (:142-144)
+            x_tf_out *= mask
+        if self.padding < 0:
+            raise ValueError(self.padding)
+        x, y = _check_pair(x_out, x_tf_out)
+        loss, p00 = _IIDSegFunction.apply(x, y, int(self.padding), bool(self.symmetric), float(self.lamda), float(self._eps),
+                                          self._reduce_joint)
+        self._p_i_j = p00
+        return loss
+
+    def get_joint_matrix(self):
+        if not hasattr(self, "_p_i_j"):
+            raise RuntimeError()
+        return self._p_i_j.detach().cpu().numpy()
+
+
+class IIDLoss(nn.Module):
+    """discreteMI.py:90-124 — returns (loss, loss_no_lamb, p_i_j); the 1e-10 guards are hard-coded in the reference."""
+
+    def __init__(self, lamb: float = 1.0, eps: float = sys.float_info.epsilon):
+        super().__init__()
+        self.lamb = float(lamb)
+        self.eps = float(eps)
+
+    def forward(self, x_out: Tensor, x_tf_out: Tensor):
+        assert len(x_out.shape) == 2, x_out.shape
+        assert simplex(x_out), f"x_out not normalized."
+        assert simplex(x_tf_out), f"x_tf_out not normalized."
+        _, k = x_out.size()
+        p_i_j = compute_joint(x_out, x_tf_out)
+        assert p_i_j.size() == (k, k)
+        p_i = p_i_j.sum(dim=1).view(k, 1).expand(k, k)
+        p_j = p_i_j.sum(dim=0).view(1, k).expand(k, k)
+        loss = -p_i_j * (torch.log(p_i_j + 1e-10) - self.lamb * torch.log(p_j + 1e-10) - self.lamb * torch.log(p_i + 1e-10))
+        loss = loss.sum()
+        loss_no_lamb = -p_i_j * (torch.log(p_i_j + 1e-10) - torch.log(p_j + 1e-10) - torch.log(p_i + 1e-10))
+        loss_no_lamb = loss_no_lamb.sum()
+        return loss, loss_no_lamb, p_i_j

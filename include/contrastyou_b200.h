@@ -1,0 +1,154 @@
+/*
+ * contrastyou_b200.h — C ABI of libcontrastyou_b200.so: the sm_100a kernels behind the drop-in InfoNCE / IIC
+ * loss modules of Contrast-You.
+ *
+ * The reference is pure Python/PyTorch: it has no FFI of its own.  Each entry point below replaces the chain of
+ * ATen calls that a reference function lowers to (cited as file:line under /root/reference); the binding a
+ * maintainer adds on the reference side is a ctypes stub inside a torch.autograd.Function.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller (torch allocator) unless
+ *     marked [host]; no allocation, no host synchronisation and no host<->device copy happens inside these calls;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 on success, CY_ERR_* (negative) on invalid arguments, or the positive cudaError_t of a failed
+ *     launch; cy_last_error() returns a thread-local description of the last failure;
+ *   - dtype codes describe the element type of embeddings / probability maps; accumulation is always fp32.
+ */
+#ifndef CONTRASTYOU_B200_H
+#define CONTRASTYOU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CY_ABI_VERSION 1
+
+/* element types of embeddings / probability maps */
+#define CY_F32 0
+#define CY_BF16 1
+#define CY_F16 2
+
+/* InfoNCE variants (cy_infonce_*: `variant`) */
+#define CY_SUPCON 0         /* SupConLoss1, exclude_other_pos=False      contrastive.py:92            */
+#define CY_SUPCON_EXCLUDE 1 /* SupConLoss1, exclude_other_pos=True       contrastive.py:87-90         */
+#define CY_SELFPACED_HARD 2 /* SelfPacedSupConLoss, weight_update="hard" contrastive.py:197-204       */
+#define CY_SELFPACED_SOFT 3 /* SelfPacedSupConLoss, weight_update="soft"                              */
+
+/* kernel family selection (cy_infonce_*: `path`) */
+#define CY_PATH_AUTO 0
+#define CY_PATH_SIMT 1    /* fp32 CUDA-core tiles: every variant, every mask source, d <= 256          */
+#define CY_PATH_TCGEN05 2 /* TMA -> smem -> tcgen05.mma -> TMEM; bf16 operands; label masks; d == 256  */
+
+/* error codes */
+#define CY_OK 0
+#define CY_ERR_ARG (-1)         /* inconsistent sizes / null pointers                                  */
+#define CY_ERR_UNSUPPORTED (-2) /* shape or variant outside what the selected path implements          */
+#define CY_ERR_DEVICE (-3)      /* not an sm_100 device                                                */
+
+int cy_abi_version(void);
+const char* cy_last_error(void);
+/* number of SMs of the current device (grid sizing of persistent kernels); <0 on error */
+int cy_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * InfoNCE / SupCon family.   Replaces exp_sim_temperature + SupConLoss1._forward / SelfPacedSupConLoss._forward
+ * (contrastyou/losses/contrastive.py:14-20, :51-100, :136-204) and their autograd backward.
+ *
+ *   z        [N, d] embeddings, both views stacked (rows [0,n) = proj_feat1, [n,2n) = proj_feat2, N = 2n), row
+ *            stride ldz elements, L2-normalised rows (asserted by the caller like contrastive.py:58)
+ *   labels   [N] int32, tiled over the views (labels[i+n] == labels[i]); P_ij = [labels_i == labels_j][i != j],
+ *            Neg_ij = [labels_i != labels_j]  (contrastive.py:38-44, :62-71).  SimCLR (:45-48) = arange(n) tiled.
+ *   codes    optional [n, n] uint8 for the explicit mask= path (:33-36): 1 = positive, 0 = negative, anything else
+ *            = neither; looked up as codes[(i % n) * n + (j % n)], diagonal i == j always cleared.  When non-NULL
+ *            it overrides labels.
+ *   rows     the call covers rows [row_begin, row_end) of the N x N problem against all N columns (single GPU:
+ *            0..N; row-sharded multi-GPU: the rank's block).
+ *
+ * Forward = cy_infonce_fwd (+ cy_infonce_fwd_pass2 for the variants that need the row sums first) and then
+ * cy_infonce_finalize.  All row statistics live in `stats`, a caller-owned float array of CY_NSTAT * N entries laid
+ * out [CY_NSTAT][N]; after finalize it holds what the backward needs for EVERY row it will meet as a column, so in
+ * the sharded case the caller all-gathers the stats rows (CY_STAT_LOGDEN, CY_STAT_INVC, CY_STAT_COEF) first.
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define CY_NSTAT 8
+#define CY_STAT_LOGDEN 0 /* log(sum_j M_ij E_ij + 1e-16), E = exp(S - 1/t), M = P + Neg                      */
+#define CY_STAT_INVC 1   /* 1 / c_i,  c_i = sum_j P_ij                                                       */
+#define CY_STAT_COEF 2   /* coefficient of E_ij in dL/dS_ij for row i (1/den_i, sw_i/(c_i den_i), ...)       */
+#define CY_STAT_AUX 3    /* variant specific: exclude -> A_i = neg_sum_i/(ratio_i+1e-4)                      */
+#define CY_STAT_POSL 4   /* sum_j P_ij (S_ij - 1/t)   (pass 1)  /  sum_j P_ij w_ij logp_ij (pass 2)          */
+#define CY_STAT_NEGC 5   /* sum_j Neg_ij                                                                     */
+#define CY_STAT_POSE 6   /* sum_j P_ij E_ij                                                                  */
+#define CY_STAT_SW 7     /* pass 2: sum_j P_ij w_ij (self-paced)  /  sum_j u_ij (exclude)                    */
+
+/* bytes of scratch the forward / backward need for this problem (split-column partial sums etc.) */
+size_t cy_infonce_workspace_bytes(int64_t N, int64_t d, int dtype, int variant, int path);
+
+int cy_infonce_fwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
+                   const uint8_t* codes, int64_t row_begin, int64_t row_end, float inv_t, int variant, int path,
+                   float* stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* second forward sweep for CY_SUPCON_EXCLUDE / CY_SELFPACED_*: needs stats of the owned rows from pass 1 (finalized
+ * with pass = 1).  gamma = self-paced age parameter (contrastive.py:206-212). */
+int cy_infonce_fwd_pass2(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
+                         const uint8_t* codes, int64_t row_begin, int64_t row_end, float inv_t, int variant,
+                         float gamma, int path, float* stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Row-level epilogue.  pass = 1 after cy_infonce_fwd, pass = 2 after cy_infonce_fwd_pass2.  When this is the last
+ * pass of the variant it writes out[0] = sum over owned rows of the per-row loss term / N  (the caller all-reduces
+ * it in the sharded case), out[1] = sum_ij P_ij w_ij, out[2] = sum_ij P_ij (self-paced downgrade ratio =
+ * out[1]/out[2], contrastive.py:179-181), out[3] = number of non-finite row terms (NaN check, :98-99). */
+int cy_infonce_finalize(int64_t N, int64_t row_begin, int64_t row_end, float inv_t, int variant, int pass,
+                        float* stats, float* out4, void* stream);
+
+/* Backward: dz[row_begin:row_end, :] = gscale[0] * (1/t) * sum_j (G_ij + G_ji) z_j  with G = dLoss/dS built on the
+ * fly from `stats` of rows i and j.  gscale is a DEVICE scalar: the upstream gradient
+ * of the loss (carries hook weight and GradScaler scale; for correct_grad also 1/downgrade_ratio).  dz has the dtype
+ * of z and row stride lddz; only the owned rows are written. */
+int cy_infonce_bwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
+                   const uint8_t* codes, int64_t row_begin, int64_t row_end, float inv_t, int variant, float gamma,
+                   int path, const float* stats, const float* gscale, void* dz, int64_t lddz, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* Materialise the [N, N] fp32 positive / negative masks with the SAME device predicate the loss kernels evaluate
+ * in-register (contrastive.py:62-71: repeat(2,2) and cleared diagonal).  Backs the lazily evaluated module attributes
+ * pos_mask / neg_mask (read by semi_seg/hooks/infonce.py:235-242 on the first batch of an epoch) and the bit-exact
+ * mask parity tests.  Either output may be NULL. */
+int cy_infonce_masks(int64_t N, const int32_t* labels, const uint8_t* codes, float* pos_mask, float* neg_mask,
+                     void* stream);
+
+/* Canonicalise a label vector to int32 so that integer equality == the reference's comparison.
+ * src_kind: 0 = float32 values (python lists go through torch.Tensor(list), contrastive.py:40: -0.0 == +0.0, NaN
+ * never equal), 1 = int32 (copied).  Writes dst[0:n] and dst[n:2n] (tiling over the two views). */
+int cy_labels_canonicalize(const void* src, int src_kind, int64_t n, int32_t* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * IIC discrete-MI segmentation loss.  Replaces compute_joint_2D / compute_joint_2D_with_padding_zeros
+ * (contrastyou/losses/discreteMI.py:225-261), IIDSegmentationLoss.forward (:139-165) and their autograd backward.
+ *
+ *   x, y     [B, K, H, W] contiguous probability maps (x_out, x_tf_out)
+ *   joint    raw joint [K, K, T, T] fp32, T = 2*pad+1:  J[k1,k2,dy,dx] = sum_{b,h,w} x[b,k1,h+dy-pad,w+dx-pad] *
+ *            y[b,k2,h,w]  — exactly what the F.conv2d call at discreteMI.py:229-232 returns.  Multi-GPU: every rank
+ *            accumulates its images, the caller all-reduces `joint`, then every rank runs the epilogue.
+ * ---------------------------------------------------------------------------------------------------------------- */
+size_t cy_iic_workspace_bytes(int B, int K, int H, int W, int pad);
+
+int cy_iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, float* joint,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Epilogue on the (global) raw joint: min-shift + 1e-8, per-displacement and global normalisation, optional
+ * symmetrisation (pad > 0, :233-243) or division by n_pixels (pad == 0, :246-261); marginals; loss (:154-165).
+ * Outputs: loss[1]; p00 [K,K] = p_i_j[0][0] (:152, get_joint_matrix); p_ij [T,T,K,K] (may be NULL);
+ * djoint [K,K,T,T] = dLoss/dJoint (may be NULL).  n_pixels = global B*H*W. */
+int cy_iic_epilogue(const float* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels,
+                    float* loss, float* p00, float* p_ij, float* djoint, void* stream);
+
+/* Backward: dx, dy [B,K,H,W] (dtype of x) = gscale[0] * adjoint of cy_iic_joint applied to djoint. */
+int cy_iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
+               const float* gscale, void* dx, void* dy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONTRASTYOU_B200_H */

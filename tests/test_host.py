@@ -1,0 +1,114 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol the header declares (no compute calls), the
+host-side mirrors (labels, point sampling, projector heads) match the golden fixtures, and the product path refuses
+to run without CUDA instead of falling back."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, load_golden
+
+import contrast_you_b200  # noqa: F401
+from contrast_you_b200 import _lib, labels as lab, sampling
+from contrast_you_b200 import projectors as P
+from contrast_you_b200.losses import SupConLoss1, SelfPacedSupConLoss, IIDSegmentationLoss, IIDLoss
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "contrastyou_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(cy_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_header_symbol():
+    names = _declared_symbols()
+    assert len(names) >= 14, names
+    handle = _lib.load()
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in contrastyou_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+    assert handle.cy_abi_version() == 1
+
+
+def test_argument_validation_needs_no_gpu():
+    handle = _lib.load()
+    # null pointers / bad sizes are rejected before anything touches the device
+    assert handle.cy_infonce_fwd(None, 0, 4, 8, 8, None, None, 0, 4, 1.0, 0, 0, None, None, 0, None) == -1
+    assert b"null" in handle.cy_last_error()
+    assert handle.cy_iic_joint(None, None, 0, 1, 2, 3, 3, 1, None, None, 0, None) == -1
+    assert handle.cy_iic_workspace_bytes(0, 1, 1, 1, 0) == 0
+
+
+def test_no_cpu_fallback():
+    f = torch.nn.functional.normalize(torch.randn(4, 8), dim=1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        SupConLoss1()(f, f, target=[0, 0, 1, 1])
+    x = torch.randn(2, 3, 4, 4).softmax(1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        IIDSegmentationLoss(padding=1)(x, x)
+
+
+def test_modules_own_no_state():
+    for m in (SupConLoss1(), SelfPacedSupConLoss(weight_update="soft", correct_grad=True), IIDSegmentationLoss(padding=1),
+              IIDLoss()):
+        assert len(m.state_dict()) == 0 and len(list(m.parameters())) == 0 and len(list(m.buffers())) == 0
+
+
+def test_module_surface_matches_reference():
+    c = SelfPacedSupConLoss()
+    assert c.age_param == 1e6
+    c.set_gamma(3)
+    assert c.age_param == 3.0 and isinstance(c.age_param, float)
+    m = IIDSegmentationLoss(lamda=1.5, padding=2, symmetric=True)
+    assert (m.lamda, m.padding, m.symmetric, m._eps) == (1.5, 2, True, 1e-5)
+    with pytest.raises(RuntimeError):
+        m.get_joint_matrix()
+    assert IIDLoss(lamb=2).lamb == 2.0
+
+
+def test_label_generators_golden():
+    cases = json.load(open(os.path.join(GOLDEN, "labels.json")))
+    assert lab.PartitionLabelGenerator()(partition_list=cases["partition"]["in"]) == cases["partition"]["out"]
+    assert lab.PatientLabelGenerator()(patient_list=cases["patient"]["in"]) == cases["patient"]["out"]
+    assert lab.ACDCCycleGenerator()(experiment_list=cases["cycle"]["in"]) == cases["cycle"]["out"]
+    assert lab.SIMCLRGenerator()(partition_list=cases["self"]["in"]) == cases["self"]["out"]
+    groups = [f"{p}_{e}" for p, e in zip(cases["patient"]["in"], cases["cycle"]["in"])]
+    part = cases["partition"]["in"]
+    assert lab.get_label("patient", "acdc", part, groups) == cases["patient"]["out"]
+    assert lab.get_label("cycle", "acdc", part, groups) == cases["cycle"]["out"]
+    assert lab.get_label("partition", "prostate_md", part, groups) == cases["partition"]["out"]
+    assert lab.get_label("self", "spleen", part, groups) == cases["self"]["out"]
+    with pytest.raises(NotImplementedError):
+        lab.get_label("cycle", "spleen", part, groups)
+    with pytest.raises(NotImplementedError):
+        lab.get_label("partition", "imagenet", part, groups)
+
+
+def test_region_extractor_golden():
+    for c in json.load(open(os.path.join(GOLDEN, "regions.json"))):
+        fm = torch.zeros(c["b"], c["c"], c["h"], c["w"])
+        hh, ww = torch.meshgrid(torch.arange(c["h"]), torch.arange(c["w"]), indexing="ij")
+        fm[:, 0], fm[:, 1] = hh.float(), ww.float()
+        state = np.random.get_state()[1].copy()
+        out = sampling.region_extractor(fm, point_nums=c["point_nums"], seed=c["seed"])
+        assert out.shape == (c["b"] * c["point_nums"], c["c"])
+        assert out[:, :2].long().tolist() == c["coords"]
+        assert (np.random.get_state()[1] == state).all()      # global numpy RNG untouched, like the reference's context
+
+
+@pytest.mark.parametrize("name", sorted(json.load(open(os.path.join(GOLDEN, "heads.json")))))
+def test_projector_heads_golden(name):
+    meta = json.load(open(os.path.join(GOLDEN, "heads.json")))[name]
+    g = load_golden("heads_" + name)
+    kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in meta["kwargs"].items()}
+    head = getattr(P, meta["class"])(**kw).double()
+    assert list(head.state_dict().keys()) == meta["keys"]           # checkpoint key layout
+    head.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd::")}, strict=True)
+    out = head(torch.from_numpy(g["feats"]).clone())
+    assert isinstance(out, list) == meta["is_list"]
+    outs = out if isinstance(out, list) else [out]
+    for i, o in enumerate(outs):
+        np.testing.assert_allclose(o.detach().numpy(), g[f"out{i}"], rtol=1e-10, atol=1e-12)
