@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the InfoNCE / IIC loss hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg2]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one fwd+bwd of SupConLoss1 over one batch of synthetic, L2-normalised embeddings (BASELINE.json
+`metric`: InfoNCE fwd+bwd pairs/s; pairs = N^2 per step).  Workload (all N): BASELINE config 4's shape, global InfoNCE
+N=65536, d=256, bf16, meta-labels randint(0,4096) — the shape north_star quotes the tensor-core target on; it fits
+one GPU because the N x N matrix is never materialised, and for N>1 the same problem is row-sharded (strong scaling:
+all-gather of embeddings + row statistics, no gradient collective).  `--workload cfg2` runs config 2's N=32768.
+
+The JSON line also carries the IIC-seg leg (config 3: 32 x 10 x 224 x 224 fp32, padding 1; pixels/s against the HBM
+roofline) under "iic", a CPU baseline ("cpu_baseline": the C/OpenMP oracle port timed on the host cores on a bounded
+sample), kernel-level rooflines measured with CUDA events around the C-ABI calls, and SM clocks sampled during the
+timed region.  `--impl reference` times the CPU port alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg4": dict(N=65536, d=256, classes=4096, name="cfg4 global InfoNCE N=65536 d=256 bf16 meta-labels(4096)"),
+    "cfg2": dict(N=32768, d=256, classes=0, name="cfg2 dense InfoNCE N=32768 (16 img x 1024 px x 2 views) d=256 bf16 self-labels"),
+}
+IIC_CFG = dict(B=32, K=10, H=224, W=224, pad=1)
+CPU_SAMPLE_N = 8192          # the reference materialises ~13 N x N fp32 tensors: 8192 is what fits / finishes in seconds
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = float(s[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_supcon_baseline(steps=1, warmup=0, seed=0):
+    """the C/OpenMP port of SupConLoss1 (oracle/oracle.c, float32 dot products like the reference's fp32 torch.mm) on
+    every host core, on a bounded sample: N=8192, d=256 (the reference itself cannot hold more: ~13 N x N fp32)."""
+    import numpy as np
+    from oracle import c_oracle
+    rng = np.random.default_rng(seed)
+    N, d = CPU_SAMPLE_N, 256
+    z = rng.standard_normal((N, d), dtype=np.float32)
+    z /= np.linalg.norm(z, axis=1, keepdims=True)
+    lab = np.tile(rng.integers(0, 512, N // 2).astype(np.int32), 2)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        c_oracle.supcon_fwd_bwd(z, lab, t=0.07, prec=0)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = statistics.median(times)
+    return dict(value=N * N / t, unit="pairs/s", cores=c_oracle.num_threads(), kind="port",
+                sample=f"SupConLoss1 fwd+bwd, N={N}, d={d}, fp32, C/OpenMP port of contrastive.py (oracle/oracle.c), "
+                       f"median of {steps} run(s), {t:.3f} s/step"), t
+
+
+def cpu_iic_baseline(steps=1, seed=0):
+    import numpy as np
+    from oracle import c_oracle
+    rng = np.random.default_rng(seed)
+    B, K, H, W, pad = 8, IIC_CFG["K"], IIC_CFG["H"], IIC_CFG["W"], IIC_CFG["pad"]
+
+    def sm(a):
+        e = np.exp(a - a.max(1, keepdims=True))
+        return (e / e.sum(1, keepdims=True)).astype(np.float32)
+    x = sm(2 * rng.standard_normal((B, K, H, W), dtype=np.float32))
+    y = sm(2 * rng.standard_normal((B, K, H, W), dtype=np.float32))
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        c_oracle.iic_fwd_bwd(x, y, pad, prec=0)
+        times.append(time.perf_counter() - t0)
+    t = statistics.median(times)
+    return dict(value=B * H * W / t, unit="pixels/s", cores=c_oracle.num_threads(), kind="port",
+                sample=f"IIDSegmentationLoss(padding=1) fwd+bwd, {B}x{K}x{H}x{W} fp32 (a quarter of config 3's batch), "
+                       f"C/OpenMP port of discreteMI.py, {t:.3f} s/step")
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path timed on the host cores (the reference is pure Python and
+    cannot travel to the GPU box; the oracle port is the stand-in, DESIGN.md "Measurement")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    base, t = cpu_supcon_baseline(steps=steps, warmup=1 if args.warmup else 0)
+    wl = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": "InfoNCE fwd+bwd pairs/s", "value": base["value"], "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": 1 if args.warmup else 0, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "note": f"CPU port timed on a bounded sample N={CPU_SAMPLE_N}; pairs/s is flat in N on CPU"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU legs
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-iic", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from contrast_you_b200 import _lib as L
+    from contrast_you_b200.losses import SupConLoss1, IIDSegmentationLoss
+    from contrast_you_b200.losses.contrastive import _canonical_labels
+    from contrast_you_b200 import distributed as cyd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = measured_peaks()
+    lib = L.load()
+    W_ = max(3, args.warmup)
+    K_ = max(1, args.steps)
+    wl = WORKLOADS[args.workload]
+    N, d = wl["N"], wl["d"]
+    n = N // 2
+    n_loc = n // world
+    assert n % world == 0
+
+    # ---- synthetic inputs (seeded; identical on every rank, each rank keeps its slice) in PINNED HOST memory
+    gen = torch.Generator().manual_seed(0)
+    z_host = torch.nn.functional.normalize(torch.randn(N, d, generator=gen), dim=1).to(torch.bfloat16)
+    lab_host = (torch.randint(0, wl["classes"], (n,), generator=gen) if wl["classes"] else torch.arange(n)).to(torch.int32)
+    sl = slice(rank * n_loc, (rank + 1) * n_loc)
+    f1_host = z_host[:n][sl].contiguous().pin_memory()
+    f2_host = z_host[n:][sl].contiguous().pin_memory()
+    lab_loc_host = lab_host[sl].contiguous().pin_memory()
+    f1_dev, f2_dev, lab_dev = f1_host.to(dev), f2_host.to(dev), lab_loc_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    crit = SupConLoss1(path=args.path) if world == 1 else cyd.ShardedSupConLoss(group=None, path=args.path)
+
+    def step(a, b, lab):
+        a = a.detach().requires_grad_()
+        b = b.detach().requires_grad_()
+        loss = crit(a, b, target=lab)
+        loss.backward()
+        return loss, a.grad, b.grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(fn, warmup, steps):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()                                   # L2 flush between timed iterations (outside the brackets)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            evs.append((e0, e1))
+        barrier()
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms
+
+    # ---- device-resident leg (`value`)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    total_ms = timed_loop(lambda: step(f1_dev, f2_dev, lab_dev), W_, K_)
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = total_ms / K_
+    value = N * N / (ms_per_step * 1e-3)
+
+    # ---- end-to-end leg: host buffers -> module -> loss back on the host, every step
+    def e2e_step():
+        a = f1_host.to(dev, non_blocking=True)
+        b = f2_host.to(dev, non_blocking=True)
+        lab = lab_loc_host.to(dev, non_blocking=True)
+        loss, _, _ = step(a, b, lab)
+        return loss.item()                                   # D2H read of the step's result
+    e2e_ms = timed_loop(e2e_step, 3, K_) / K_
+    h2d = f1_host.numel() * 2 * 2 + lab_loc_host.numel() * 4
+    e2e = {"value": N * N / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+           "ms_per_step": e2e_ms}
+
+    # ---- kernel-level roofline: CUDA events around the C-ABI calls themselves (single GPU problem: this rank's rows)
+    z_all = torch.cat([f1_dev, f2_dev]) if world == 1 else cyd.gather_rank_major(torch.cat([f1_dev, f2_dev]))
+    if world == 1:
+        labels = _canonical_labels(lab_dev, n, dev)
+        rb, re = 0, N
+    else:
+        raw_all = torch.empty(world * n_loc, dtype=lab_dev.dtype, device=dev)
+        dist.all_gather_into_tensor(raw_all, lab_dev)
+        labels = cyd.rank_major_labels(raw_all, world, lambda r, m: _canonical_labels(r, m, dev))
+        rb, re = cyd.row_range(n_loc)
+    path = {"auto": 0, "simt": 1, "tcgen05": 2}[args.path]
+    stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev)
+    out4 = torch.zeros(4, device=dev)
+    ws_b = lib.cy_infonce_workspace_bytes(N, d, L.CY_BF16, 0, path)
+    ws = torch.empty(ws_b, dtype=torch.uint8, device=dev)
+    one = torch.ones(1, device=dev)
+    dz = torch.empty_like(z_all)
+    st = L.stream_ptr()
+
+    def k_fwd():
+        L.check(lib.cy_infonce_fwd(z_all.data_ptr(), L.CY_BF16, N, d, d, labels.data_ptr(), None, rb, re, 1 / 0.07, 0, path,
+                                   stats.data_ptr(), ws.data_ptr(), ws_b, st), "fwd")
+
+    def k_fin():
+        L.check(lib.cy_infonce_finalize(N, rb, re, 1 / 0.07, 0, 1, stats.data_ptr(), out4.data_ptr(), st), "fin")
+
+    def k_bwd():
+        L.check(lib.cy_infonce_bwd(z_all.data_ptr(), L.CY_BF16, N, d, d, labels.data_ptr(), None, rb, re, 1 / 0.07, 0, 0.0, path,
+                                   stats.data_ptr(), one.data_ptr(), dz.data_ptr(), d, ws.data_ptr(), ws_b, st), "bwd")
+    k_fwd(); k_fin()
+    if world > 1:
+        cyd.make_stats_exchange(n_loc)(stats, out4)
+    kreps = max(3, min(K_, 10))
+    fwd_ms = timed_loop(k_fwd, 2, kreps) / kreps
+    bwd_ms = timed_loop(k_bwd, 2, kreps) / kreps
+    rows = re - rb
+    fwd_tf = 2.0 * rows * N * d / (fwd_ms * 1e-3) / 1e12
+    bwd_tf = 4.0 * rows * N * d / (bwd_ms * 1e-3) / 1e12
+    peak_tf = peaks["bf16_tflops"]
+    roofline = {"bound": "tensor", "kernel": "cy_infonce_bwd (recompute S tile + W.Z, 4*rows*N*d FLOP per launch)",
+                "achieved": bwd_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": bwd_tf / peak_tf, "traffic": None,
+                "peak_source": peaks["source"] + " bf16 burst",
+                "fwd": {"kernel": "cy_infonce_fwd (2*rows*N*d FLOP)", "ms": fwd_ms, "achieved": fwd_tf, "frac": fwd_tf / peak_tf},
+                "bwd_ms": bwd_ms,
+                "fwd_bwd_frac": (6.0 * rows * N * d / ((fwd_ms + bwd_ms) * 1e-3) / 1e12) / peak_tf}
+
+    line = {
+        "metric": "InfoNCE fwd+bwd pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K_, "warmup": W_,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": wl["name"], "N": N, "d": d, "temperature": 0.07, "path": args.path,
+                   "parallelism": f"rows{world}" if world > 1 else "single",
+                   "l2": "256 MiB buffer written between timed iterations (inputs are smaller than L2)"},
+        "e2e": e2e, "roofline": roofline, "clocks": clocks,
+        "gpu_launches": (4 * K_),      # per step: cy_labels_canonicalize, cy_infonce_fwd, cy_infonce_finalize, cy_infonce_bwd
+    }
+
+    # ---- IIC leg (config 3); weak scaling over the batch for world > 1
+    if not args.no_iic:
+        B, Kc, H, Wd, pad = (IIC_CFG[k] for k in ("B", "K", "H", "W", "pad"))
+        g2 = torch.Generator().manual_seed(1 + rank)
+        x_host = (2 * torch.randn(B, Kc, H, Wd, generator=g2)).softmax(1).pin_memory()
+        y_host = (2 * torch.randn(B, Kc, H, Wd, generator=g2)).softmax(1).pin_memory()
+        x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+        iic = IIDSegmentationLoss(padding=pad)
+        if world > 1:
+            cyd.shard_iic_loss(iic)
+
+        def iic_step(xa, ya):
+            xa = xa.detach().requires_grad_(); ya = ya.detach().requires_grad_()
+            loss = iic(xa, ya)
+            loss.backward()
+            return loss
+        px = B * H * Wd * world
+        iic_ms = timed_loop(lambda: iic_step(x_dev, y_dev), W_, K_) / K_
+        iic_e2e_ms = timed_loop(lambda: iic_step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True)).item(),
+                                2, max(3, K_ // 2)) / max(3, K_ // 2)
+        # kernel level
+        joint = torch.empty(Kc, Kc, 3, 3, device=dev)
+        wsj_b = lib.cy_iic_workspace_bytes(B, Kc, H, Wd, pad)
+        wsj = torch.empty(wsj_b, dtype=torch.uint8, device=dev)
+        dj = torch.randn(Kc, Kc, 3, 3, device=dev) * 1e-6
+        dxo, dyo = torch.empty_like(x_dev), torch.empty_like(y_dev)
+        j_ms = timed_loop(lambda: L.check(lib.cy_iic_joint(x_dev.data_ptr(), y_dev.data_ptr(), 0, B, Kc, H, Wd, pad, joint.data_ptr(),
+                                                           wsj.data_ptr(), wsj_b, st), "joint"), 2, kreps) / kreps
+        b_ms = timed_loop(lambda: L.check(lib.cy_iic_bwd(x_dev.data_ptr(), y_dev.data_ptr(), 0, B, Kc, H, Wd, pad, dj.data_ptr(),
+                                                         one.data_ptr(), dxo.data_ptr(), dyo.data_ptr(), st), "bwd"), 2, kreps) / kreps
+        bytes_map = 2 * B * Kc * H * Wd * 4
+        gbs = lambda by, ms: by / (ms * 1e-3) / 1e9
+        line["iic"] = {
+            "metric": "IIC-seg fwd+bwd pixels/s", "value": px / (iic_ms * 1e-3), "unit": "pixels/s", "ms_per_step": iic_ms,
+            "scaling": "weak", "dtype": "f32",
+            "config": {"workload": f"cfg3 IIDSegmentationLoss K={Kc} padding={pad} batch {B}x{H}x{Wd} per GPU"},
+            "e2e": {"value": px / (iic_e2e_ms * 1e-3), "unit": "pixels/s", "h2d_bytes_per_step": bytes_map, "d2h_bytes_per_step": 4},
+            "roofline": {"bound": "hbm", "kernel": "cy_iic_joint + cy_iic_bwd (3 x 2*B*K*H*W*4 B algorithmic)",
+                         "achieved": gbs(3 * bytes_map, j_ms + b_ms), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs(3 * bytes_map, j_ms + b_ms) / peaks["hbm_gbs"], "traffic": None,
+                         "joint": {"ms": j_ms, "achieved": gbs(bytes_map, j_ms), "frac": gbs(bytes_map, j_ms) / peaks["hbm_gbs"]},
+                         "bwd": {"ms": b_ms, "achieved": gbs(2 * bytes_map, b_ms), "frac": gbs(2 * bytes_map, b_ms) / peaks["hbm_gbs"]},
+                         "peak_source": peaks["source"] + " copy bandwidth"},
+            "gpu_launches": 4 * K_,     # cy_iic_joint (2 kernels), cy_iic_epilogue, cy_iic_bwd
+        }
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"], _ = cpu_supcon_baseline(steps=1)
+        if "iic" in line:
+            line["iic"]["cpu_baseline"] = cpu_iic_baseline(steps=1)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -38,7 +38,8 @@ SIGNATURES = {
     "cy_labels_canonicalize": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "cy_iic_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "cy_iic_joint": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
-    "cy_iic_epilogue": (_i32, [_vp, _i32, _i32, _i32, _f32, _f32, _f64, _vp, _vp, _vp, _vp, _vp]),
+    "cy_iic_epilogue_workspace_bytes": (_sz, [_i32, _i32]),
+    "cy_iic_epilogue": (_i32, [_vp, _i32, _i32, _i32, _f32, _f32, _f64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cy_iic_bwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
 }
 

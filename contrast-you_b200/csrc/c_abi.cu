@@ -33,7 +33,8 @@ int infonce_bwd_tc(const void*, int64_t, int64_t, int64_t, const int32_t*, int64
 // iic.cu
 size_t iic_workspace_bytes(int, int, int, int, int);
 int iic_joint(const void*, const void*, int, int, int, int, int, int, float*, void*, size_t, cudaStream_t);
-int iic_epilogue(const float*, int, int, int, float, float, double, float*, float*, float*, float*, cudaStream_t);
+size_t iic_epilogue_workspace_bytes(int, int);
+int iic_epilogue(const float*, int, int, int, float, float, double, float*, float*, float*, float*, void*, size_t, cudaStream_t);
 int iic_bwd(const void*, const void*, int, int, int, int, int, int, const float*, const float*, void*, void*, cudaStream_t);
 
 static int check_infonce_args(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
@@ -172,10 +173,15 @@ int cy_iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, i
     return iic_joint(x, y, dtype, B, K, H, W, pad, joint, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
+size_t cy_iic_epilogue_workspace_bytes(int K, int pad) {
+    if (K < 1 || pad < 0) return 0;
+    return iic_epilogue_workspace_bytes(K, pad);
+}
+
 int cy_iic_epilogue(const float* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
-                    float* p00, float* p_ij, float* djoint, void* stream) {
+                    float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes, void* stream) {
     CY_CHECK_ARG(joint && loss && p00 && K >= 1 && pad >= 0, "bad arguments");
-    return iic_epilogue(joint, K, pad, symmetric, lamda, eps, n_pixels, loss, p00, p_ij, djoint,
+    return iic_epilogue(joint, K, pad, symmetric, lamda, eps, n_pixels, loss, p00, p_ij, djoint, workspace, workspace_bytes,
                         reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -37,9 +37,9 @@ __host__ __device__ inline int iic_col_origin(int pad) {
 
 // stage one halo tile of `src` (image b, tile origin h0,w0) into sm[(hh*K + k)*XW + c]; zero outside the image
 __device__ __forceinline__ void stage_tile(float* __restrict__ sm, const void* __restrict__ src, int dtype, const IICGeom& g,
-                                           int b, int h0, int w0, int halo) {
+                                           int b, int h0, int w0, int halo, int origin) {
     const int rows = g.TH + 2 * halo;
-    const int c_lo = g.CO - halo, c_hi = g.CO + g.TW + halo;   // [c_lo, c_hi)
+    const int c_lo = origin - halo, c_hi = origin + g.TW + halo;   // [c_lo, c_hi): tile column 0 sits at `origin`
     const int ncol = c_hi - c_lo;
     const int total = rows * g.K * ncol;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
@@ -90,13 +90,13 @@ iic_joint_kernel(const void* __restrict__ x, const void* __restrict__ y, int dty
         const int trem = tile % (g.tiles_h * g.tiles_w);
         const int h0 = (trem / g.tiles_w) * g.TH, w0 = (trem % g.tiles_w) * g.TW;
         __syncthreads();
-        stage_tile(xs, x, dtype, g, b, h0, w0, PAD);
-        stage_tile(ys - 0, y, dtype, g, b, h0, w0, 0);   // y tile: rows (h*K + k2), same pitch, columns at CO..
+        stage_tile(xs, x, dtype, g, b, h0, w0, PAD, g.CO);
+        stage_tile(ys, y, dtype, g, b, h0, w0, 0, 0);    // y tile: rows (h*K + k2), same pitch, columns at 0..
         __syncthreads();
         if (active) {
             for (int h = slot; h < g.TH; h += nslot) {
                 const float* xr = xs + (size_t)(h * K + rr) * g.XW + (g.CO - PAD);
-                const float* yr = ys + (size_t)(h * K + k2base) * g.XW + g.CO;
+                const float* yr = ys + (size_t)(h * K + k2base) * g.XW;
                 float xw[4 + 2 * PAD];
 #pragma unroll
                 for (int e = 0; e < 2 * PAD; ++e) xw[4 + e] = xr[e];
@@ -154,15 +154,15 @@ iic_joint_generic_kernel(const void* __restrict__ x, const void* __restrict__ y,
         const int trem = tile % (g.tiles_h * g.tiles_w);
         const int h0 = (trem / g.tiles_w) * g.TH, w0 = (trem % g.tiles_w) * g.TW;
         __syncthreads();
-        stage_tile(xs, x, dtype, g, b, h0, w0, pad);
-        stage_tile(ys, y, dtype, g, b, h0, w0, 0);
+        stage_tile(xs, x, dtype, g, b, h0, w0, pad, g.CO);
+        stage_tile(ys, y, dtype, g, b, h0, w0, 0, 0);
         __syncthreads();
         for (int e = tid; e < nj; e += IIC_NT) {
             const int dx = e % T, dy = (e / T) % T, k2 = (e / (T * T)) % K, k1 = e / (T * T * K);
             float s = 0.f;
             for (int h = 0; h < g.TH; ++h) {
                 const float* xr = xs + (size_t)((h + dy) * K + k1) * g.XW + g.CO - pad + dx;
-                const float* yr = ys + (size_t)(h * K + k2) * g.XW + g.CO;
+                const float* yr = ys + (size_t)(h * K + k2) * g.XW;
                 for (int w = 0; w < g.TW; ++w) s = fmaf(xr[w], yr[w], s);
             }
             float* dst = partials + (size_t)blockIdx.x * nj + e;
@@ -211,11 +211,11 @@ __device__ double block_reduce_min(double v, double* red) {
 __global__ void __launch_bounds__(256)
 iic_epilogue_kernel(const float* __restrict__ joint, int K, int pad, int symmetric, double lamda, double eps,
                     double n_pixels, float* __restrict__ loss, float* __restrict__ p00, float* __restrict__ p_ij,
-                    float* __restrict__ djoint) {
+                    float* __restrict__ djoint, double* __restrict__ gscratch) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[8];
     const int T = 2 * pad + 1, TT = T * T, KK = K * K, nj = KK * TT;
-    double* Bm = sm;
+    double* Bm = gscratch ? gscratch : sm;      // large K / padding: the arrays live in the caller's workspace
     double* P = Bm + nj;
     double* G = P + nj;
     double* sd = G + nj;
@@ -389,8 +389,8 @@ iic_bwd_kernel(const void* __restrict__ x, const void* __restrict__ y, int dtype
         const int trem = tile % (g.tiles_h * g.tiles_w);
         const int h0 = (trem / g.tiles_w) * g.TH, w0 = (trem % g.tiles_w) * g.TW;
         __syncthreads();
-        stage_tile(xs, x, dtype, g, b, h0, w0, PAD);
-        stage_tile(ys, y, dtype, g, b, h0, w0, PAD);
+        stage_tile(xs, x, dtype, g, b, h0, w0, PAD, g.CO);
+        stage_tile(ys, y, dtype, g, b, h0, w0, PAD, g.CO);
         __syncthreads();
         const int h = h0 + r, w = w0 + 4 * q;
         if (r < g.TH && h < g.H && w < g.W) {
@@ -598,14 +598,29 @@ int iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int 
     return CY_OK;
 }
 
-int iic_epilogue(const float* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
-                 float* p00, float* p_ij, float* djoint, cudaStream_t st) {
+static size_t epilogue_scratch_doubles(int K, int pad) {
     const int T = 2 * pad + 1, TT = T * T, nj = K * K * TT;
-    const size_t smem = ((size_t)3 * nj + TT + 2 * TT * K) * sizeof(double);
-    if (smem > 200 * 1024) { set_error("iic_epilogue: K=%d pad=%d needs %zu B of shared memory", K, pad, smem); return CY_ERR_UNSUPPORTED; }
-    cudaError_t e = cudaFuncSetAttribute(iic_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return (size_t)3 * nj + TT + 2 * TT * K;
+}
+
+size_t iic_epilogue_workspace_bytes(int K, int pad) {
+    const size_t b = epilogue_scratch_doubles(K, pad) * sizeof(double);
+    return b > 160 * 1024 ? b : 0;      // small problems keep everything in shared memory
+}
+
+int iic_epilogue(const float* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
+                 float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    size_t smem = epilogue_scratch_doubles(K, pad) * sizeof(double);
+    double* gscratch = nullptr;
+    if (iic_epilogue_workspace_bytes(K, pad)) {
+        CY_CHECK_ARG(workspace && workspace_bytes >= smem, "iic_epilogue: K=%d pad=%d needs a %zu B workspace", K, pad, smem);
+        gscratch = reinterpret_cast<double*>(workspace);
+        smem = 0;
+    }
+    cudaError_t e = cudaFuncSetAttribute(iic_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem ? smem : 16));
     if (e != cudaSuccess) { set_error("iic_epilogue smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    iic_epilogue_kernel<<<1, 256, smem, st>>>(joint, K, pad, symmetric, (double)lamda, (double)eps, n_pixels, loss, p00, p_ij, djoint);
+    iic_epilogue_kernel<<<1, 256, smem, st>>>(joint, K, pad, symmetric, (double)lamda, (double)eps, n_pixels, loss, p00, p_ij,
+                                              djoint, gscratch);
     CY_CHECK_LAUNCH("iic_epilogue");
     return CY_OK;
 }

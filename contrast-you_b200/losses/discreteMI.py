@@ -132,9 +132,11 @@ class _IIDSegFunction(torch.autograd.Function):
         loss = torch.empty(1, dtype=torch.float32, device=x.device)
         p00 = torch.empty(K, K, dtype=torch.float32, device=x.device)
         djoint = torch.empty(K, K, T, T, dtype=torch.float32, device=x.device)
+        ws_bytes = lib.cy_iic_epilogue_workspace_bytes(K, padding)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
         L.check(lib.cy_iic_epilogue(joint.data_ptr(), K, padding, int(bool(symmetric)), float(lamda), float(eps), n_pixels,
-                                    loss.data_ptr(), p00.data_ptr(), None, djoint.data_ptr(), L.stream_ptr()),
-                "cy_iic_epilogue")
+                                    loss.data_ptr(), p00.data_ptr(), None, djoint.data_ptr(), L.ptr(ws), ws_bytes,
+                                    L.stream_ptr()), "cy_iic_epilogue")
         ctx.save_for_backward(x, y, djoint)
         ctx.padding = padding
         ctx.mark_non_differentiable(p00)

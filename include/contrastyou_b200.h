@@ -140,9 +140,13 @@ int cy_iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, i
 /* Epilogue on the (global) raw joint: min-shift + 1e-8, per-displacement and global normalisation, optional
  * symmetrisation (pad > 0, :233-243) or division by n_pixels (pad == 0, :246-261); marginals; loss (:154-165).
  * Outputs: loss[1]; p00 [K,K] = p_i_j[0][0] (:152, get_joint_matrix); p_ij [T,T,K,K] (may be NULL);
- * djoint [K,K,T,T] = dLoss/dJoint (may be NULL).  n_pixels = global B*H*W. */
+ * djoint [K,K,T,T] = dLoss/dJoint (may be NULL).  n_pixels = global B*H*W.  One CTA, fp64; its few arrays live in
+ * shared memory unless K*K*T*T is large, in which case cy_iic_epilogue_workspace_bytes() is non-zero and the caller
+ * passes that much device scratch. */
+size_t cy_iic_epilogue_workspace_bytes(int K, int pad);
 int cy_iic_epilogue(const float* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels,
-                    float* loss, float* p00, float* p_ij, float* djoint, void* stream);
+                    float* loss, float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 /* Backward: dx, dy [B,K,H,W] (dtype of x) = gscale[0] * adjoint of cy_iic_joint applied to djoint. */
 int cy_iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,

@@ -46,6 +46,7 @@ MULTIVERSION static float dot_f32(const float* a, const float* b, int64_t d) {
     int64_t k = 0;
     for (; k + 64 <= d; k += 64) {
         float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma omp simd reduction(+ : t0, t1, t2, t3)
         for (int u = 0; u < 16; ++u) {
             t0 += a[k + u] * b[k + u];
             t1 += a[k + 16 + u] * b[k + 16 + u];
@@ -60,6 +61,7 @@ MULTIVERSION static float dot_f32(const float* a, const float* b, int64_t d) {
 
 MULTIVERSION static double dot_f64(const float* a, const float* b, int64_t d) {
     double s = 0.0;
+#pragma omp simd reduction(+ : s)
     for (int64_t k = 0; k < d; ++k) s += (double)a[k] * (double)b[k];
     return s;
 }
@@ -72,6 +74,90 @@ MULTIVERSION static void axpy_f64(double w, const float* x, double* acc, int64_t
     for (int64_t k = 0; k < d; ++k) acc[k] += w * (double)x[k];
 }
 
+/* 4 rows against one column row: the column row is loaded once for four dot products / four axpys */
+MULTIVERSION static void dot4_f32(const float* a0, const float* a1, const float* a2, const float* a3, const float* b,
+                                  int64_t d, float out[4]) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma omp simd reduction(+ : s0, s1, s2, s3)
+    for (int64_t k = 0; k < d; ++k) {
+        const float bv = b[k];
+        s0 += a0[k] * bv; s1 += a1[k] * bv; s2 += a2[k] * bv; s3 += a3[k] * bv;
+    }
+    out[0] = s0; out[1] = s1; out[2] = s2; out[3] = s3;
+}
+
+MULTIVERSION static void axpy4_f32(const float w[4], const float* x, float* c0, float* c1, float* c2, float* c3, int64_t d) {
+    const float w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+    for (int64_t k = 0; k < d; ++k) {
+        const float xv = x[k];
+        c0[k] += w0 * xv; c1[k] += w1 * xv; c2[k] += w2 * xv; c3[k] += w3 * xv;
+    }
+}
+
+/* float32 fast form of oracle_supcon_fwd_bwd (prec == 0, N % 4 == 0): same arithmetic, rows processed four at a time.
+ * This is the leg bench.py times as the CPU baseline. */
+static int supcon_fwd_bwd_f32_blocked(const float* z, const int32_t* labels, int64_t N, int64_t d, double t, double* loss,
+                                      double* row_lse, double* row_cnt, float* dz) {
+    const float inv_t = (float)(1.0 / t);
+    double* D = (double*)malloc(sizeof(double) * (size_t)N);
+    double* ps = (double*)malloc(sizeof(double) * (size_t)N);
+    if (!D || !ps) return -2;
+    float m = -INFINITY;
+#pragma omp parallel for schedule(static) reduction(max : m)
+    for (int64_t i = 0; i < N; ++i) {
+        const float s = dot_f32(z + i * d, z + i * d, d) * inv_t;
+        if (s > m) m = s;
+    }
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < N; i += 4) {
+        const float* a0 = z + i * d;
+        double Dv[4] = {0, 0, 0, 0}, pv[4] = {0, 0, 0, 0}, cv[4] = {0, 0, 0, 0};
+        for (int64_t j = 0; j < N; ++j) {
+            float s[4];
+            dot4_f32(a0, a0 + d, a0 + 2 * d, a0 + 3 * d, z + j * d, d, s);
+            for (int r = 0; r < 4; ++r) {
+                if (j == i + r) continue;
+                const float sv = s[r] * inv_t;
+                Dv[r] += (double)expf(sv - m);
+                if (labels[j] == labels[i + r]) { pv[r] += (double)sv; cv[r] += 1.0; }
+            }
+        }
+        for (int r = 0; r < 4; ++r) {
+            D[i + r] = Dv[r]; ps[i + r] = pv[r]; row_cnt[i + r] = cv[r]; row_lse[i + r] = (double)m + log(Dv[r] + 1e-16);
+        }
+    }
+    double acc = 0.0;
+    for (int64_t i = 0; i < N; ++i) acc += ps[i] / row_cnt[i] - row_lse[i];
+    *loss = -acc / (double)N;
+    if (dz) {
+        memset(dz, 0, sizeof(float) * (size_t)N * (size_t)d);
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int64_t i = 0; i < N; i += 4) {
+            const float* a0 = z + i * d;
+            float* c0 = dz + i * d;
+            float invD[4], invc[4];
+            for (int r = 0; r < 4; ++r) { invD[r] = (float)(1.0 / (D[i + r] + 1e-16)); invc[r] = (float)(1.0 / row_cnt[i + r]); }
+            const float scale = inv_t / (float)N;
+            for (int64_t j = 0; j < N; ++j) {
+                float s[4], w[4];
+                dot4_f32(a0, a0 + d, a0 + 2 * d, a0 + 3 * d, z + j * d, d, s);
+                const float invDj = (float)(1.0 / (D[j] + 1e-16)), invcj = (float)(1.0 / row_cnt[j]);
+                for (int r = 0; r < 4; ++r) {
+                    float wv = 0.f;
+                    if (j != i + r) {
+                        wv = expf(s[r] * inv_t - m) * (invD[r] + invDj);
+                        if (labels[j] == labels[i + r]) wv -= invc[r] + invcj;
+                    }
+                    w[r] = wv * scale;
+                }
+                axpy4_f32(w, z + j * d, c0, c0 + d, c0 + 2 * d, c0 + 3 * d, d);
+            }
+        }
+    }
+    free(D); free(ps);
+    return 0;
+}
+
 /* ---------- SupCon, label path ----------
  * z       [N, d] float32, both views stacked (rows 0..n-1 view 1, n..2n-1 view 2)
  * labels  [N] int32, already tiled over the two views (label[i+n] == label[i]); SimCLR = arange(n) tiled
@@ -81,6 +167,7 @@ MULTIVERSION static void axpy_f64(double w, const float* x, double* acc, int64_t
 int oracle_supcon_fwd_bwd(const float* z, const int32_t* labels, int64_t N, int64_t d, double t, int prec,
                           double* loss, double* row_lse, double* row_cnt, float* dz) {
     if (N <= 0 || d <= 0) return -1;
+    if (prec == 0 && (N % 4) == 0) return supcon_fwd_bwd_f32_blocked(z, labels, N, d, t, loss, row_lse, row_cnt, dz);
     const double inv_t = 1.0 / t;
     double* D = (double*)malloc(sizeof(double) * (size_t)N);
     double* ps = (double*)malloc(sizeof(double) * (size_t)N);
@@ -142,11 +229,13 @@ int oracle_supcon_fwd_bwd(const float* z, const int32_t* labels, int64_t N, int6
 /* ---------- IIC ---------- */
 MULTIVERSION static double rowdot(const float* a, const float* b, int n) {
     double s = 0.0;
+#pragma omp simd reduction(+ : s)
     for (int i = 0; i < n; ++i) s += (double)a[i] * (double)b[i];
     return s;
 }
 MULTIVERSION static float rowdot_f32(const float* a, const float* b, int n) {
     float s = 0.f;
+#pragma omp simd reduction(+ : s)
     for (int i = 0; i < n; ++i) s += a[i] * b[i];
     return s;
 }
