@@ -329,3 +329,88 @@ def test_iid_golden(name):
     np.testing.assert_allclose(pij.detach().cpu().numpy(), g["p_i_j"], rtol=FP32_TOL)
     assert _relerr(x.grad.cpu().numpy(), g["grad_x"]) <= FP32_TOL
     assert _relerr(y.grad.cpu().numpy(), g["grad_y"]) <= FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 path
+def _tc_case(N, classes, seed):
+    torch.manual_seed(seed)
+    n = N // 2
+    z = torch.nn.functional.normalize(torch.randn(N, 256, device=DEV), dim=1).to(torch.bfloat16)
+    lab = torch.randint(0, classes, (n,)) if classes else torch.arange(n)
+    return z, lab, n
+
+
+@pytest.mark.parametrize("N,classes", [(256, 4), (1024, 16), (4096, 0), (8192, 512)])
+def test_tcgen05_matches_oracle_and_simt(N, classes):
+    """bf16 inputs, d=256: TMA + tcgen05 kernels vs the float64 C oracle on the same bf16-rounded inputs (1e-2 bar of
+    north_star for bf16) and vs the fp32 CUDA-core path (same inputs, tighter)."""
+    z, lab, n = _tc_case(N, classes, N)
+    out = {}
+    for path in ("tcgen05", "simt"):
+        f1, f2 = z[:n].clone().requires_grad_(), z[n:].clone().requires_grad_()
+        loss = SupConLoss1(path=path)(f1, f2, target=lab.tolist())
+        loss.backward()
+        out[path] = (loss.item(), torch.cat([f1.grad, f2.grad]).float().cpu().numpy())
+    o = c_oracle.supcon_fwd_bwd(z.float().cpu().numpy(), np.tile(lab.numpy().astype(np.int32), 2), t=0.07, prec=1)
+    assert out["tcgen05"][0] == pytest.approx(o["loss"], rel=1e-4)         # products are exact in fp32: far inside 1e-2
+    assert _relerr(out["tcgen05"][1], o["grad"]) <= BF16_TOL
+    assert out["tcgen05"][0] == pytest.approx(out["simt"][0], rel=1e-4)
+    assert _relerr(out["tcgen05"][1], out["simt"][1]) <= BF16_TOL
+
+
+def test_tcgen05_row_stats_match_simt():
+    """the per-row statistics (log-denominator, 1/c, coefficient) of both kernel families agree row by row"""
+    from contrast_you_b200.losses.contrastive import _canonical_labels
+    z, lab, n = _tc_case(2048, 32, 5)
+    N = 2 * n
+    labels = _canonical_labels(lab.tolist(), n, z.device)
+    lib = L.lib()
+    res = {}
+    for name, path in (("tc", L.CY_PATH_TCGEN05), ("simt", L.CY_PATH_SIMT)):
+        stats = torch.zeros(L.CY_NSTAT, N, device=DEV)
+        out4 = torch.zeros(4, device=DEV)
+        wsb = lib.cy_infonce_workspace_bytes(N, 256, L.CY_BF16, 0, path)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        L.check(lib.cy_infonce_fwd(z.data_ptr(), L.CY_BF16, N, 256, 256, labels.data_ptr(), None, 0, N, 1 / 0.07, 0, path,
+                                   stats.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr()), "fwd")
+        L.check(lib.cy_infonce_finalize(N, 0, N, 1 / 0.07, 0, 1, stats.data_ptr(), out4.data_ptr(), L.stream_ptr()), "fin")
+        res[name] = (stats.cpu().numpy(), out4.cpu().numpy())
+    for row in (L.CY_STAT_LOGDEN, L.CY_STAT_INVC, L.CY_STAT_COEF):
+        np.testing.assert_allclose(res["tc"][0][row], res["simt"][0][row], rtol=2e-4, atol=1e-6)
+    assert res["tc"][1][3] == 0 and res["simt"][1][3] == 0
+
+
+def test_tcgen05_row_sharded_equals_whole():
+    """row ranges (the multi-GPU sharding unit): two half-range launches reproduce the full-range loss and gradient"""
+    from contrast_you_b200.losses.contrastive import info_nce, _canonical_labels
+    z, lab, n = _tc_case(1024, 8, 9)
+    N = 2 * n
+    labels = _canonical_labels(lab.tolist(), n, z.device)
+    zf = z.clone().requires_grad_()
+    loss, _ = info_nce(zf, labels, None, 0.07, path=L.CY_PATH_TCGEN05)
+    loss.backward()
+    parts, grads = [], torch.zeros_like(z)
+    for rb, re in ((0, N // 2), (N // 2, N)):
+        zs = z.clone().requires_grad_()
+        stats_all = {}
+
+        def exchange(stats, out4, rb=rb, re=re):
+            # emulate the all-gather of row statistics with a second (full-range) evaluation
+            full = torch.zeros_like(stats)
+            o4 = torch.zeros(4, device=DEV)
+            lib = L.lib()
+            wsb = lib.cy_infonce_workspace_bytes(N, 256, L.CY_BF16, 0, L.CY_PATH_TCGEN05)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+            L.check(lib.cy_infonce_fwd(z.data_ptr(), L.CY_BF16, N, 256, 256, labels.data_ptr(), None, 0, N, 1 / 0.07, 0,
+                                       L.CY_PATH_TCGEN05, full.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr()), "fwd")
+            L.check(lib.cy_infonce_finalize(N, 0, N, 1 / 0.07, 0, 1, full.data_ptr(), o4.data_ptr(), L.stream_ptr()), "fin")
+            own = stats[:, rb:re].clone()
+            stats.copy_(full)
+            assert torch.allclose(stats[:3, rb:re], own[:3], rtol=1e-5)
+        l, _ = info_nce(zs, labels, None, 0.07, path=L.CY_PATH_TCGEN05, rows=(rb, re), gather_stats=exchange)
+        l.backward()
+        parts.append(l.item())
+        grads[rb:re] = zs.grad[rb:re]
+        assert float(zs.grad[:rb].abs().sum() + zs.grad[re:].abs().sum()) == 0.0
+    assert sum(parts) == pytest.approx(loss.item(), rel=1e-5)
+    assert _relerr(grads.float().cpu().numpy(), zf.grad.float().cpu().numpy()) <= 1e-6
