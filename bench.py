@@ -175,7 +175,7 @@ def main():
     import torch.distributed as dist
     from contrast_you_b200 import _lib as L
     from contrast_you_b200.losses import SupConLoss1, IIDSegmentationLoss
-    from contrast_you_b200.losses.contrastive import _canonical_labels
+    from contrast_you_b200.losses.contrastive import _canonical_labels, sort_rows_by_label
     from contrast_you_b200 import distributed as cyd
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -270,6 +270,11 @@ def main():
         dist.all_gather_into_tensor(raw_all, lab_dev)
         labels = cyd.rank_major_labels(raw_all, world, lambda r, m: _canonical_labels(r, m, dev))
         rb, re = cyd.row_range(n_loc)
+    # same row order as the module uses: each rank's row block sorted by label (losses/contrastive.py sort_rows_by_label)
+    with torch.no_grad():
+        for r in range(world):
+            z_all, labels = sort_rows_by_label(z_all, labels, r * 2 * n_loc, (r + 1) * 2 * n_loc)
+        z_all = z_all.contiguous()
     path = {"auto": 0, "simt": 1, "tcgen05": 2}[args.path]
     stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev)
     out4 = torch.zeros(4, device=dev)

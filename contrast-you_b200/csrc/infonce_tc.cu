@@ -50,7 +50,7 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                       int tiles_per_split, float c1, float* __restrict__ part) {
     using S = FwdSmem<BN>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);    // 1024-aligned, still a shared pointer
     uint8_t* sA = smem;
     uint8_t* sB = smem + S::OFF_B;
     int32_t* sLab = reinterpret_cast<int32_t*>(smem + S::OFF_LAB);
@@ -127,53 +127,91 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
         const int gi = row0 + row;
         const int32_t my_lab = labels[gi];
         int32_t* wlab = sLab + ew * (BN / 2);
-        float D = 0.f, posS = 0.f;
+        float D0 = 0.f, D1 = 0.f, D2 = 0.f, D3 = 0.f, posS = 0.f;
         int cnt = 0;
+        constexpr int NCH = BN / 64;                       // 32-column chunks per warp and tile
+        // label range of this warp's 32 rows: a column chunk whose label range does not intersect it holds no positive
+        // pair, whatever the order of the rows (callers that sort rows by label make this the common case)
+        const int32_t row_lo = __reduce_min_sync(0xffffffffu, my_lab), row_hi = __reduce_max_sync(0xffffffffu, my_lab);
+        int32_t lab_next[NCH];
+        if (ct0 < ct1) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) lab_next[c] = labels[ct0 * BN + h * (BN / 2) + c * 32 + lane];
+        }
         Ring<S::NACC> acc;
         for (int ct = ct0; ct < ct1; ++ct, acc.next()) {
             const uint32_t a = acc.stage();
             const int jbase = ct * BN + h * (BN / 2);          // first global column of this warp's half
             __syncwarp();
+            int32_t cmin = lab_next[0], cmax = lab_next[0];
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) wlab[c * 32 + lane] = labels[jbase + c * 32 + lane];
+            for (int c = 0; c < NCH; ++c) {
+                wlab[c * 32 + lane] = lab_next[c];
+                cmin = min(cmin, lab_next[c]);
+                cmax = max(cmax, lab_next[c]);
+            }
+            const bool may_have_pos = __reduce_max_sync(0xffffffffu, cmax) >= row_lo && __reduce_min_sync(0xffffffffu, cmin) <= row_hi;
             __syncwarp();
+            if (ct + 1 < ct1) {                                // next tile's labels travel while this tile is processed
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) lab_next[c] = labels[jbase + BN + c * 32 + lane];
+            }
             mbar_wait(acc_full + a, acc.phase());
             tc_fence_after();
-            const bool diag_tile = (gi >= jbase) && (gi < jbase + BN / 2);   // warp-uniform up to the 32-row group
-            const bool any_diag = __any_sync(0xffffffffu, diag_tile);
+            uint32_t r[NCH][32];
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + a * BN + h * (BN / 2) + c * 32, r);
-                tmem_ld_wait();
-                if (!any_diag) {
+            for (int c = 0; c < NCH; ++c)
+                tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + a * BN + h * (BN / 2) + c * 32, r[c]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + a);         // values are in registers: hand the accumulator back now
+            const bool diag_tile = (gi >= jbase) && (gi < jbase + BN / 2);   // uniform per warp (32-row groups)
+            if (!may_have_pos) {                              // (a diagonal chunk always intersects: i is its own label)
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+                    for (int e4 = 0; e4 < 8; ++e4) {
+                        D0 += ex2_approx(fmaf(__uint_as_float(r[c][e4 * 4 + 0]), c1, -c1));
+                        D1 += ex2_approx(fmaf(__uint_as_float(r[c][e4 * 4 + 1]), c1, -c1));
+                        D2 += ex2_approx(fmaf(__uint_as_float(r[c][e4 * 4 + 2]), c1, -c1));
+                        D3 += ex2_approx(fmaf(__uint_as_float(r[c][e4 * 4 + 3]), c1, -c1));
+                    }
+                }
+            } else if (!__any_sync(0xffffffffu, diag_tile)) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
 #pragma unroll
                     for (int e4 = 0; e4 < 8; ++e4) {
                         const int4 lj = *reinterpret_cast<const int4*>(wlab + c * 32 + e4 * 4);
-                        const int32_t lv[4] = {lj.x, lj.y, lj.z, lj.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float s = __uint_as_float(r[e4 * 4 + u]);
-                            D += ex2_approx(fmaf(s, c1, -c1));
-                            if (lv[u] == my_lab) { cnt += 1; posS += s; }
-                        }
+                        const float s0 = __uint_as_float(r[c][e4 * 4 + 0]), s1 = __uint_as_float(r[c][e4 * 4 + 1]);
+                        const float s2 = __uint_as_float(r[c][e4 * 4 + 2]), s3 = __uint_as_float(r[c][e4 * 4 + 3]);
+                        D0 += ex2_approx(fmaf(s0, c1, -c1));
+                        D1 += ex2_approx(fmaf(s1, c1, -c1));
+                        D2 += ex2_approx(fmaf(s2, c1, -c1));
+                        D3 += ex2_approx(fmaf(s3, c1, -c1));
+                        if (lj.x == my_lab) { cnt += 1; posS += s0; }
+                        if (lj.y == my_lab) { cnt += 1; posS += s1; }
+                        if (lj.z == my_lab) { cnt += 1; posS += s2; }
+                        if (lj.w == my_lab) { cnt += 1; posS += s3; }
                     }
-                } else {
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
                         const int j = jbase + c * 32 + e;
-                        const float s = __uint_as_float(r[e]);
+                        const float sv = __uint_as_float(r[c][e]);
                         if (j != gi) {
-                            D += ex2_approx(fmaf(s, c1, -c1));
-                            if (wlab[c * 32 + e] == my_lab) { cnt += 1; posS += s; }
+                            D0 += ex2_approx(fmaf(sv, c1, -c1));
+                            if (wlab[c * 32 + e] == my_lab) { cnt += 1; posS += sv; }
                         }
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + a);
         }
+        const float D = (D0 + D1) + (D2 + D3);
         const int slot = blockIdx.y * 2 + h;
         float* p = part + (size_t)slot * 3 * N;
         p[gi] = D;
@@ -222,12 +260,13 @@ struct BwdCfg {
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict__ labels,
-                      const float* __restrict__ stats, int N, int row_begin, float c1, const float* __restrict__ gscale,
-                      float out_scale, __nv_bfloat16* __restrict__ dz, int64_t lddz) {
+                      const float* __restrict__ stats, int N, int row_begin, int tiles_per_split, float c1,
+                      const float* __restrict__ gscale, float out_scale, __nv_bfloat16* __restrict__ dz, int64_t lddz,
+                      float* __restrict__ dz32) {
     using C = BwdCfg;
     constexpr int BN = C::BN;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);    // 1024-aligned, still a shared pointer
     uint8_t* sA = smem;
     uint8_t* sB = smem + C::OFF_B;
     uint8_t* sW = smem + C::OFF_W;
@@ -245,7 +284,11 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = row_begin + blockIdx.x * TC_BM;
-    const int nt = N / BN;
+    // column tiles [t0, t1) of this CTA (blockIdx.y splits the columns so that small row ranges still fill the chip)
+    const int t0 = blockIdx.y * tiles_per_split;
+    const int t1 = min(N / BN, t0 + tiles_per_split);
+    const int nt = t1 - t0;
+    if (nt <= 0) return;
 
     if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
     if (warp == 1 && lane == 0) {
@@ -276,7 +319,7 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                 mbar_wait(b_empty + s, ring.phase() ^ 1u);
                 mbar_arrive_expect_tx(b_full + s, C::B_BYTES);
                 uint8_t* dst = sB + s * C::B_BYTES;
-                for (int kb = 0; kb < TC_KBLK; ++kb) tma_load_2d(dst + kb * (BN * 128), &tmap, b_full + s, kb * 64, t * BN);
+                for (int kb = 0; kb < TC_KBLK; ++kb) tma_load_2d(dst + kb * (BN * 128), &tmap, b_full + s, kb * 64, (t0 + t) * BN);
             }
         }
     } else if (warp == 1) {
@@ -318,7 +361,7 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                     // A: W [128 x 64] K-major, 32 B per k-step.  B: Zj read MN-major: N = d (4 groups of 64, LBO = BN*128),
                     // K = j (8-row groups, SBO = 1024); one k-step = 16 rows of j = 2048 B.
                     umma_bf16(tmem_dz, smem_desc(w_addr + ks * 32, 16, 1024), smem_desc(b_addr + ks * 2048, BN * 128, 1024),
-                              idesc2, (t | ks) != 0);
+                              idesc2, (t | ks) != 0);      // t counts from this CTA's first tile
                 umma_commit(w_empty + w);
                 umma_commit(b_empty + s);
             }
@@ -332,16 +375,27 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
         const float coef_i = stats[(size_t)CY_STAT_COEF * N + gi];
         const float invc_i = stats[(size_t)CY_STAT_INVC * N + gi];
         float* wcol = sCol + ew * 96;                 // [0,32) labels (as int bits), [32,64) coef_j, [64,96) invc_j
+        const int32_t row_lo = __reduce_min_sync(0xffffffffu, my_lab), row_hi = __reduce_max_sync(0xffffffffu, my_lab);
+        float nx_lab = __int_as_float(labels[t0 * BN + h * 32 + lane]);
+        float nx_coef = stats[(size_t)CY_STAT_COEF * N + t0 * BN + h * 32 + lane];
+        float nx_invc = stats[(size_t)CY_STAT_INVC * N + t0 * BN + h * 32 + lane];
         Ring<C::NS> sacc;
         Ring<C::NW> wr;
         for (int t = 0; t < nt; ++t, sacc.next(), wr.next()) {
             const uint32_t a = sacc.stage(), w = wr.stage();
-            const int jbase = t * BN + h * 32;
+            const int jbase = (t0 + t) * BN + h * 32;
             __syncwarp();
-            wcol[lane] = __int_as_float(labels[jbase + lane]);
-            wcol[32 + lane] = stats[(size_t)CY_STAT_COEF * N + jbase + lane];
-            wcol[64 + lane] = stats[(size_t)CY_STAT_INVC * N + jbase + lane];
+            wcol[lane] = nx_lab;
+            wcol[32 + lane] = nx_coef;
+            wcol[64 + lane] = nx_invc;
+            const bool may_have_pos = __reduce_max_sync(0xffffffffu, __float_as_int(nx_lab)) >= row_lo &&
+                                      __reduce_min_sync(0xffffffffu, __float_as_int(nx_lab)) <= row_hi;
             __syncwarp();
+            if (t + 1 < nt) {                             // next tile's column statistics travel during this tile
+                nx_lab = __int_as_float(labels[jbase + BN + lane]);
+                nx_coef = stats[(size_t)CY_STAT_COEF * N + jbase + BN + lane];
+                nx_invc = stats[(size_t)CY_STAT_INVC * N + jbase + BN + lane];
+            }
             mbar_wait(s_full + a, sacc.phase());
             tc_fence_after();
             uint32_t r[32];
@@ -351,20 +405,48 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty + a);      // S values are in registers: the accumulator can be reused
             uint32_t packed[16];
+            if (!may_have_pos) {                          // no positive pair in this 32 x 32 block: W = E (coef_i + coef_j)
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-                float wv[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const float s = __uint_as_float(r[e + u]);
-                    const float E = ex2_approx(fmaf(s, c1, -c1));
-                    float v = E * (coef_i + wcol[32 + e + u]);
-                    if (__float_as_int(wcol[e + u]) == my_lab) v -= invc_i + wcol[64 + e + u];
-                    if (jbase + e + u == gi) v = 0.f;
-                    wv[u] = v;
+                for (int e4 = 0; e4 < 8; ++e4) {
+                    const float4 cj = *reinterpret_cast<const float4*>(wcol + 32 + e4 * 4);
+                    const float w0 = ex2_approx(fmaf(__uint_as_float(r[e4 * 4 + 0]), c1, -c1)) * (coef_i + cj.x);
+                    const float w1 = ex2_approx(fmaf(__uint_as_float(r[e4 * 4 + 1]), c1, -c1)) * (coef_i + cj.y);
+                    const float w2 = ex2_approx(fmaf(__uint_as_float(r[e4 * 4 + 2]), c1, -c1)) * (coef_i + cj.z);
+                    const float w3 = ex2_approx(fmaf(__uint_as_float(r[e4 * 4 + 3]), c1, -c1)) * (coef_i + cj.w);
+                    __nv_bfloat162 b01 = __floats2bfloat162_rn(w0, w1);
+                    __nv_bfloat162 b23 = __floats2bfloat162_rn(w2, w3);
+                    packed[e4 * 2] = *reinterpret_cast<uint32_t*>(&b01);
+                    packed[e4 * 2 + 1] = *reinterpret_cast<uint32_t*>(&b23);
                 }
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(wv[0], wv[1]);
-                packed[e >> 1] = *reinterpret_cast<uint32_t*>(&b2);
+            } else {
+                const bool diag_tile = __any_sync(0xffffffffu, (gi >= jbase) && (gi < jbase + 32));
+#pragma unroll
+                for (int e4 = 0; e4 < 8; ++e4) {
+                    const int4 lj = *reinterpret_cast<const int4*>(wcol + e4 * 4);
+                    const float4 cj = *reinterpret_cast<const float4*>(wcol + 32 + e4 * 4);
+                    const float4 ij = *reinterpret_cast<const float4*>(wcol + 64 + e4 * 4);
+                    const int lv[4] = {lj.x, lj.y, lj.z, lj.w};
+                    const float cv[4] = {cj.x, cj.y, cj.z, cj.w};
+                    const float iv[4] = {ij.x, ij.y, ij.z, ij.w};
+                    float wv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float sv = __uint_as_float(r[e4 * 4 + u]);
+                        const float E = ex2_approx(fmaf(sv, c1, -c1));
+                        float v = E * (coef_i + cv[u]);
+                        if (lv[u] == my_lab) v -= invc_i + iv[u];
+                        wv[u] = v;
+                    }
+                    if (diag_tile) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (jbase + e4 * 4 + u == gi) wv[u] = 0.f;
+                    }
+                    __nv_bfloat162 b01 = __floats2bfloat162_rn(wv[0], wv[1]);
+                    __nv_bfloat162 b23 = __floats2bfloat162_rn(wv[2], wv[3]);
+                    packed[e4 * 2] = *reinterpret_cast<uint32_t*>(&b01);
+                    packed[e4 * 2 + 1] = *reinterpret_cast<uint32_t*>(&b23);
+                }
             }
             mbar_wait(w_empty + w, wr.phase() ^ 1u);
             // row `row` of the [128 x 64] bf16 tile: 128 B, this warp's half = 16-byte chunks 4h..4h+3, swizzled by row % 8
@@ -382,29 +464,64 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
         // dZ rows of this CTA: TMEM -> registers -> bf16 -> global
         mbar_wait(dz_full, 0);
         tc_fence_after();
-        const float scale = gscale[0] * out_scale;
-        __nv_bfloat16* out = dz + (size_t)gi * lddz + h * 128;
+        if (dz32 == nullptr) {
+            const float scale = gscale[0] * out_scale;
+            __nv_bfloat16* out = dz + (size_t)gi * lddz + h * 128;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_dz + (uint32_t(q * 32) << 16) + h * 128 + c * 32, r);
-            tmem_ld_wait();
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_dz + (uint32_t(q * 32) << 16) + h * 128 + c * 32, r);
+                tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 32; e += 8) {
-                uint32_t pk[4];
+                for (int e = 0; e < 32; e += 8) {
+                    uint32_t pk[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(r[e + 2 * u]) * scale,
-                                                              __uint_as_float(r[e + 2 * u + 1]) * scale);
-                    pk[u] = *reinterpret_cast<uint32_t*>(&b2);
+                    for (int u = 0; u < 4; ++u) {
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(r[e + 2 * u]) * scale,
+                                                                  __uint_as_float(r[e + 2 * u + 1]) * scale);
+                        pk[u] = *reinterpret_cast<uint32_t*>(&b2);
+                    }
+                    *reinterpret_cast<uint4*>(out + c * 32 + e) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
-                *reinterpret_cast<uint4*>(out + c * 32 + e) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        } else {
+            // column-split launch: partial row-block gradients meet in an fp32 accumulator (vector reductions at L2)
+            float* out = dz32 + (size_t)(gi - row_begin) * TC_D + h * 128;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_dz + (uint32_t(q * 32) << 16) + h * 128 + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; e += 4)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c * 32 + e),
+                                 "f"(__uint_as_float(r[e])), "f"(__uint_as_float(r[e + 1])), "f"(__uint_as_float(r[e + 2])),
+                                 "f"(__uint_as_float(r[e + 3]))
+                                 : "memory");
             }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// fp32 split accumulator -> bf16 gradient rows (scaled by gscale / (t N))
+__global__ void infonce_tc_convert_kernel(const float* __restrict__ dz32, int64_t rows, int64_t row_begin,
+                                          const float* __restrict__ gscale, float out_scale, __nv_bfloat16* __restrict__ dz,
+                                          int64_t lddz) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread = 8 consecutive columns
+    if (idx >= rows * (TC_D / 8)) return;
+    const int64_t r = idx / (TC_D / 8);
+    const int c = (int)(idx % (TC_D / 8)) * 8;
+    const float scale = gscale[0] * out_scale;
+    const float4 a = *reinterpret_cast<const float4*>(dz32 + r * TC_D + c);
+    const float4 b = *reinterpret_cast<const float4*>(dz32 + r * TC_D + c + 4);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x * scale, a.y * scale), p1 = __floats2bfloat162_rn(a.z * scale, a.w * scale);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x * scale, b.y * scale), p3 = __floats2bfloat162_rn(b.z * scale, b.w * scale);
+    *reinterpret_cast<uint4*>(dz + (row_begin + r) * lddz + c) =
+        make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
+                   *reinterpret_cast<uint32_t*>(&p3));
 }
 
 // ------------------------------------------------------------------------------------------------------------ host
@@ -446,7 +563,7 @@ bool infonce_tc_supported(int dtype, int64_t N, int64_t d, int64_t ldz, const ui
 
 constexpr int FWD_BN = 128;
 
-static int fwd_splits(int64_t N, int64_t rows) {
+static int sm_count() {
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -454,6 +571,26 @@ static int fwd_splits(int64_t N, int64_t rows) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
+    return sms;
+}
+
+// column splits of the backward: minimise waves x tiles-per-CTA (one CTA per SM), at least 16 tiles per CTA
+static int bwd_splits(int64_t N, int64_t rows) {
+    const int64_t sms = sm_count(), rb = rows / TC_BM, nt = N / BwdCfg::BN;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= 16; ++s) {
+        if (s > 1 && nt / s < 16) break;
+        const int64_t tps = (nt + s - 1) / s;
+        const int64_t waves = (rb * s + sms - 1) / sms;
+        const double cost = (double)waves * (double)(tps + 6);      // + fixed per-CTA cost (A load, drain) in tile units
+        if (cost < best_cost * 0.97) { best_cost = cost; best = s; }
+    }
+    return best;
+}
+
+static int fwd_splits(int64_t N, int64_t rows) {
+    const int sms = sm_count();
     const int64_t rb = rows / TC_BM, ctiles = N / FWD_BN;
     // enough CTAs for ~8 waves, but at least 8 column tiles per CTA so the A load and the prologue amortise
     int64_t want = (8LL * sms + rb - 1) / rb;
@@ -467,7 +604,9 @@ size_t infonce_tc_workspace_bytes(int64_t N, int64_t d) {
     if (d != TC_D || (N % 128) != 0) return 0;
     // worst case over row ranges: a single 128-row block -> the most column splits
     const int smax = fwd_splits(N, TC_BM);
-    return (size_t)smax * 2 * 3 * (size_t)N * sizeof(float);
+    const size_t fwd = (size_t)smax * 2 * 3 * (size_t)N * sizeof(float);
+    const size_t bwd = (size_t)N * TC_D * sizeof(float);            // fp32 split accumulator, worst case rows == N
+    return fwd > bwd ? fwd : bwd;
 }
 
 int infonce_fwd_tc(const void* z, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, int64_t row_begin, int64_t row_end,
@@ -502,7 +641,7 @@ int infonce_fwd_tc(const void* z, int64_t N, int64_t d, int64_t ldz, const int32
 int infonce_bwd_tc(const void* z, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, int64_t row_begin, int64_t row_end,
                    float inv_t, const float* stats, const float* gscale, void* dz, int64_t lddz, void* workspace,
                    size_t workspace_bytes, cudaStream_t st) {
-    (void)workspace; (void)workspace_bytes; (void)d;
+    (void)d;
     const int64_t rows = row_end - row_begin;
     if (rows <= 0) return CY_OK;
     CY_CHECK_ARG((rows % TC_BM) == 0 && (row_begin % TC_BM) == 0, "tcgen05 path: row range must be 128-aligned");
@@ -513,10 +652,28 @@ int infonce_bwd_tc(const void* z, int64_t N, int64_t d, int64_t ldz, const int32
     if (rc) return rc;
     cudaError_t e = cudaFuncSetAttribute(infonce_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdCfg::TOTAL);
     if (e != cudaSuccess) { set_error("bwd_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    infonce_bwd_tc_kernel<<<(unsigned)(rows / TC_BM), TC_THREADS, BwdCfg::TOTAL, st>>>(
-        tmap, labels, stats, (int)N, (int)row_begin, inv_t * LOG2E, gscale, inv_t / (float)N,
-        reinterpret_cast<__nv_bfloat16*>(dz), lddz);
+    const int splits = bwd_splits(N, rows);
+    const int nt = (int)(N / BwdCfg::BN);
+    const int tps = (nt + splits - 1) / splits;
+    float* dz32 = nullptr;
+    if (splits > 1) {
+        const size_t need = (size_t)rows * TC_D * sizeof(float);
+        CY_CHECK_ARG(workspace && workspace_bytes >= need, "infonce_bwd_tc: workspace %zu < %zu", workspace_bytes, need);
+        dz32 = reinterpret_cast<float*>(workspace);
+        e = cudaMemsetAsync(dz32, 0, need, st);
+        if (e != cudaSuccess) { set_error("bwd_tc memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    dim3 grid((unsigned)(rows / TC_BM), (unsigned)splits);
+    infonce_bwd_tc_kernel<<<grid, TC_THREADS, BwdCfg::TOTAL, st>>>(
+        tmap, labels, stats, (int)N, (int)row_begin, tps, inv_t * LOG2E, gscale, inv_t / (float)N,
+        reinterpret_cast<__nv_bfloat16*>(dz), lddz, dz32);
     CY_CHECK_LAUNCH("infonce_bwd_tc");
+    if (dz32) {
+        const int64_t n8 = rows * (TC_D / 8);
+        infonce_tc_convert_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dz32, rows, row_begin, gscale, inv_t / (float)N,
+                                                                              reinterpret_cast<__nv_bfloat16*>(dz), lddz);
+        CY_CHECK_LAUNCH("infonce_tc_convert");
+    }
     return CY_OK;
 }
 

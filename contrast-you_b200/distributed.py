@@ -113,7 +113,7 @@ class ShardedSupConLoss(torch.nn.Module):
         self._path = {"auto": L.CY_PATH_AUTO, "simt": L.CY_PATH_SIMT, "tcgen05": L.CY_PATH_TCGEN05}[path]
 
     def forward(self, proj_feat1: Tensor, proj_feat2: Tensor, target=None, mask: Optional[Tensor] = None, **kwargs):
-        from .losses.contrastive import info_nce, _canonical_labels, is_normalized
+        from .losses.contrastive import info_nce, _canonical_labels, is_normalized, sort_rows_by_label, tensor_core_eligible
         if mask is not None:
             raise NotImplementedError("the sharded loss derives masks from labels (explicit [n,n] masks are per-process)")
         assert is_normalized(proj_feat1) and is_normalized(proj_feat2), f"features need to be normalized first"
@@ -131,6 +131,10 @@ class ShardedSupConLoss(torch.nn.Module):
         dist.all_gather_into_tensor(raw_all, raw.contiguous(), group=self._group)
         labels = rank_major_labels(raw_all, world, lambda r, n: _canonical_labels(r, n, device))
         z_all = gather_rank_major(torch.cat([proj_feat1, proj_feat2], dim=0), self._group)
+        if tensor_core_eligible(z_all, labels, None, L.CY_SUPCON, self._path):
+            # sort every rank's row block by label (ownership of rows is unchanged): see sort_rows_by_label
+            for r in range(world):
+                z_all, labels = sort_rows_by_label(z_all, labels, r * 2 * n_local, (r + 1) * 2 * n_local)
         loss, _ = info_nce(z_all, labels, None, self._t, L.CY_SUPCON, path=self._path, rows=row_range(n_local, self._group),
                            gather_stats=make_stats_exchange(n_local, self._group))
         if torch.isnan(loss):

@@ -112,8 +112,30 @@ class _InfoNCEFunction(torch.autograd.Function):
         return dz, None, None, None, None, None, None, None, None, None
 
 
+def tensor_core_eligible(z: Tensor, labels, codes, variant: int, path: int) -> bool:
+    """mirror of the C-side dispatch (c_abi.cu resolve_path): does this call run on the tcgen05 kernels?"""
+    N, d = z.shape
+    ok = (z.dtype == torch.bfloat16 and d == 256 and N % 128 == 0 and N >= 256 and codes is None and labels is not None
+          and variant == L.CY_SUPCON)
+    return ok and (path == L.CY_PATH_TCGEN05 or (path == L.CY_PATH_AUTO and N >= 1024))
+
+
+def sort_rows_by_label(z: Tensor, labels: Tensor, lo: int = 0, hi: Optional[int] = None):
+    """Permute rows [lo, hi) so that equal labels are adjacent.  The loss is invariant under a simultaneous permutation
+    of rows and labels (the mask depends on label equality and i == j only) and autograd routes the gradient back
+    through ``index_select``.  With sorted rows the positive pairs of a row block sit in a few column tiles, so the
+    tensor-core kernels take their mask-free inner loop on every other tile (label-range test per 32 x 32 block)."""
+    hi = z.shape[0] if hi is None else hi
+    order = torch.argsort(labels[lo:hi], stable=True) + lo
+    if lo != 0 or hi != z.shape[0]:
+        idx = torch.arange(z.shape[0], device=z.device)
+        idx[lo:hi] = order
+        order = idx
+    return z.index_select(0, order), labels.index_select(0, order).contiguous()
+
+
 def info_nce(z: Tensor, labels: Optional[Tensor], codes: Optional[Tensor], temperature: float, variant: int = L.CY_SUPCON,
-             gamma: float = 1e6, path: int = L.CY_PATH_AUTO, rows=None, gather_stats=None):
+             gamma: float = 1e6, path: int = L.CY_PATH_AUTO, rows=None, gather_stats=None, sort_rows: bool = False):
     """Functional entry: z [N, d] stacked views, int32 labels [N] (tiled) or uint8 codes [n, n] -> (loss, out4)."""
     L.require_cuda(z, labels, codes)
     if z.dim() != 2:
@@ -121,6 +143,8 @@ def info_nce(z: Tensor, labels: Optional[Tensor], codes: Optional[Tensor], tempe
     if z.stride(1) != 1:
         z = z.contiguous()
     N = z.shape[0]
+    if sort_rows and rows is None and tensor_core_eligible(z, labels, codes, variant, path):
+        z, labels = sort_rows_by_label(z, labels)
     rb, re = (0, N) if rows is None else rows
     return _InfoNCEFunction.apply(z, labels, codes, float(1.0 / temperature), int(variant), float(gamma), int(path),
                                   int(rb), int(re), gather_stats)
@@ -189,7 +213,7 @@ class SupConLoss1(_ContrastBase):
     def forward(self, proj_feat1, proj_feat2, target=None, mask: Tensor = None, **kwargs):
         z, labels, codes = self._prepare(proj_feat1, proj_feat2, target, mask)
         variant = L.CY_SUPCON_EXCLUDE if self._exclude_pos else L.CY_SUPCON
-        loss, _ = info_nce(z, labels, codes, self._t, variant, path=self._path)
+        loss, _ = info_nce(z, labels, codes, self._t, variant, path=self._path, sort_rows=True)
         self._stash(z, labels, codes)
         if torch.isnan(loss):
             raise RuntimeError(loss)
