@@ -13,6 +13,8 @@
 // in a fixed order (deterministic).
 // Backward (iic_bwd_kernel): thread = 4 consecutive pixels x all output channels; dL/dJ (and its flipped transpose)
 // sit in shared memory and are read as warp-uniform float4 broadcasts.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cy {
@@ -534,10 +536,25 @@ static JointPlan plan_joint(int B, int K, int H, int W, int pad) {
     return p;
 }
 
+// iic_tma.cu (TMA + packed-FMA fast path; returns CY_ERR_UNSUPPORTED for shapes it does not take)
+int iic_joint_tma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, float* partials, int* n_partials,
+                  cudaStream_t st);
+int iic_bwd_tma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
+                const float* gscale, void* dx, void* dy, cudaStream_t st);
+
+static bool tma_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("CY_IIC_TMA");     // CY_IIC_TMA=0 pins the SIMT kernels (A/B measurements)
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
 size_t iic_workspace_bytes(int B, int K, int H, int W, int pad) {
-    const JointPlan p = plan_joint(B, K, H, W, pad);
+    (void)B; (void)H; (void)W;
     const int T = 2 * pad + 1;
-    return (size_t)p.grid * K * K * T * T * sizeof(float);
+    return (size_t)2 * sm_count_cached() * K * K * T * T * sizeof(float);     // one partial joint per persistent CTA
 }
 
 template <int PAD, int KC>
@@ -583,6 +600,16 @@ int iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int 
     CY_CHECK_ARG(workspace && workspace_bytes >= need, "iic_joint: workspace %zu < %zu", workspace_bytes, need);
     float* partials = reinterpret_cast<float*>(workspace);
     int rc;
+    if (tma_enabled()) {
+        int np = 0;
+        rc = iic_joint_tma(x, y, dtype, B, K, H, W, pad, partials, &np, st);
+        if (rc == CY_OK) {
+            iic_reduce_partials_kernel<<<(nj + 255) / 256, 256, 0, st>>>(partials, np, nj, joint);
+            CY_CHECK_LAUNCH("iic_reduce_partials");
+            return CY_OK;
+        }
+        if (rc != CY_ERR_UNSUPPORTED) return rc;
+    }
     if (p.kc) {
         rc = dispatch_joint(pad, p.kc, x, y, dtype, p, partials, st);
     } else {
@@ -653,6 +680,10 @@ static int dispatch_bwd(int pad, int kc, const void* x, const void* y, int dtype
 int iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
             const float* gscale, void* dx, void* dy, cudaStream_t st) {
     const int T = 2 * pad + 1;
+    if (tma_enabled()) {
+        const int rc = iic_bwd_tma(x, y, dtype, B, K, H, W, pad, djoint, gscale, dx, dy, st);
+        if (rc != CY_ERR_UNSUPPORTED) return rc;
+    }
     if (pad <= 3) {
         BwdPlan p;
         p.kc = pick_kc(K);

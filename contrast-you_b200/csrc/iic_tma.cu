@@ -1,0 +1,506 @@
+// IIC joint / adjoint, B200 fast path: TMA-fed halo tiles + packed fp32 FMAs (fma.rn.f32x2).
+//
+// Same mathematics and the same thread->work mapping as csrc/iic.cu (see the header there); what changes is how the
+// probability maps reach shared memory and how the FMA pipe is fed:
+//   * x, y [B,K,H,W] fp32 are described by 3-D tensor maps (W,H,B*K).  One `cp.async.bulk.tensor.3d` per operand and
+//     tile brings the (K x rows x cols) box — halo included, out-of-image elements zero-filled by the TMA unit — into a
+//     multi-stage ring guarded by full/empty mbarriers; a dedicated producer warp issues the copies, so staging costs
+//     the compute warps nothing (the SIMT kernels spend ~40 % of their instructions on index math and stores).
+//   * the inner products are issued as fma.rn.f32x2: accumulators are (even pixel, odd pixel) pairs, the window of x
+//     is kept as two register copies (even / odd aligned pairs), y and dL/dJ arrive as natural pairs.
+// Layout of a staged box: [k][row][col] fp32 (col fastest).  Forward: lane = role (k1, dy) with rows-per-box == T
+// (mod 8) and box-width/4 odd, so the 8 lanes of an LDS.128 phase read 8 distinct 16-byte bank groups.
+// Eligibility (host side, iic_tma_supported): fp32, W % 4 == 0, 16-byte aligned bases, padding <= 3, T*K*chunks <= 32.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cy {
+
+using namespace tc;
+
+// shared with infonce_tc.cu
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encode_fn();
+
+struct IICTmaGeom {
+    int B, K, H, W;
+    int TH, TW;        // pixels per tile
+    int HH, XWB;       // halo box: rows, columns (floats)
+    int CO;            // box column of the tile's first pixel
+    int tiles_h, tiles_w, n_tiles;
+    int x_stage_floats, y_stage_floats;   // per stage, each rounded up to 32 floats (128 B)
+};
+
+// x, y are viewed as 3-D tensors (W, H, B*K): channel k of image b is plane b*K + k
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// d = a * b + d on two packed fp32 lanes
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+#ifdef CY_NO_F32X2
+    d.x = fmaf(a.x, b.x, d.x);
+    d.y = fmaf(a.y, b.y, d.y);
+#else
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(reinterpret_cast<unsigned long long&>(d))
+        : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+#endif
+}
+
+constexpr int JT_COMPUTE_WARPS = 9;                 // one per tile row (TH == 9)
+constexpr int JT_THREADS = (JT_COMPUTE_WARPS + 1) * 32;
+constexpr int JT_STAGES = 3;
+
+// ------------------------------------------------------------------------------------------------------ forward
+template <int PAD, int KC>
+__global__ void __launch_bounds__(JT_THREADS, 1)
+iic_joint_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, IICTmaGeom g,
+                     float* __restrict__ partials) {
+    constexpr int T = 2 * PAD + 1;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    float* stage0 = reinterpret_cast<float*>(smem);
+    const int stage_floats = g.x_stage_floats + g.y_stage_floats;
+    const int K = g.K;
+    const int nj = K * K * T * T;
+    float* jsm = stage0 + (size_t)JT_STAGES * stage_floats;
+    uint64_t* full = reinterpret_cast<uint64_t*>(jsm + ((nj + 31) & ~31));
+    uint64_t* empty = full + JT_STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < JT_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, JT_COMPUTE_WARPS); }
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < nj; i += JT_THREADS) jsm[i] = 0.f;
+    __syncthreads();
+
+    const uint32_t stage_bytes = (uint32_t)(K * g.HH * g.XWB + K * g.TH * g.TW) * 4u;
+
+    if (warp == JT_COMPUTE_WARPS) {
+        if (elect_one()) {
+            prefetch_tmap(&tmx);
+            prefetch_tmap(&tmy);
+            Ring<JT_STAGES> ring;
+            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ring.next()) {
+                const int b = tile / (g.tiles_h * g.tiles_w);
+                const int trem = tile % (g.tiles_h * g.tiles_w);
+                const int h0 = (trem / g.tiles_w) * g.TH, w0 = (trem % g.tiles_w) * g.TW;
+                const uint32_t s = ring.stage();
+                mbar_wait(empty + s, ring.phase() ^ 1u);
+                mbar_arrive_expect_tx(full + s, stage_bytes);
+                float* xs = stage0 + (size_t)s * stage_floats;
+                tma_load_3d(xs, &tmx, full + s, w0 - g.CO, h0 - PAD, b * K);
+                tma_load_3d(xs + g.x_stage_floats, &tmy, full + s, w0, h0, b * K);
+            }
+        }
+    } else {
+        const int nchunk = (K + KC - 1) / KC;
+        const int R = T * K * nchunk;                  // <= 32 (host guarantees)
+        const bool active = lane < R;
+        const int role = active ? lane : 0;
+        const int c2 = role / (T * K), rr = role % (T * K);
+        const int k1 = rr / T, dy = rr % T;            // k1-major: consecutive lanes -> consecutive (k1*HH + dy) mod 8
+        const int k2base = c2 * KC;
+        const int h = warp;                            // tile row owned by this warp
+        float2 acc[T][KC];
+#pragma unroll
+        for (int a = 0; a < T; ++a)
+#pragma unroll
+            for (int c = 0; c < KC; ++c) acc[a][c] = make_float2(0.f, 0.f);
+
+        Ring<JT_STAGES> ring;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ring.next()) {
+            const uint32_t s = ring.stage();
+            mbar_wait(full + s, ring.phase());
+            const float* xs = stage0 + (size_t)s * stage_floats;
+            const float* ys = xs + g.x_stage_floats;
+            if (active) {
+                // box row of this role; box column c holds image column w0 - CO + c (CO = 4: TMA needs a 16-byte aligned
+                // innermost start coordinate, so the halo cannot start at w0 - PAD)
+                const float* xr = xs + (size_t)(k1 * g.HH + h + dy) * g.XWB;
+                const float* yr = ys + (size_t)(k2base * g.TH + h) * g.TW;
+                const int ystride = g.TH * g.TW;
+                float a[12];                                   // box columns w .. w+11 of the current step
+                if (PAD > 0) {
+                    const float4 f0 = *reinterpret_cast<const float4*>(xr), f1 = *reinterpret_cast<const float4*>(xr + 4);
+                    a[4] = f0.x; a[5] = f0.y; a[6] = f0.z; a[7] = f0.w;
+                    a[8] = f1.x; a[9] = f1.y; a[10] = f1.z; a[11] = f1.w;
+                }
+                for (int w = 0; w < g.TW; w += 4) {
+                    float xw[4 + 2 * PAD];
+                    if (PAD > 0) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) a[e] = a[e + 4];
+                        const float4 f = *reinterpret_cast<const float4*>(xr + w + 8);
+                        a[8] = f.x; a[9] = f.y; a[10] = f.z; a[11] = f.w;
+#pragma unroll
+                        for (int i = 0; i < 4 + 2 * PAD; ++i) xw[i] = a[4 - PAD + i];
+                    } else {
+                        const float4 f = *reinterpret_cast<const float4*>(xr + w);
+                        xw[0] = f.x; xw[1] = f.y; xw[2] = f.z; xw[3] = f.w;
+                    }
+                    // pairs (xw[i], xw[i+1]) for every start i in [0, 2 + 2*PAD]
+                    float2 xp[3 + 2 * PAD];
+#pragma unroll
+                    for (int i = 0; i < 3 + 2 * PAD; ++i) xp[i] = make_float2(xw[i], xw[i + 1]);
+#pragma unroll
+                    for (int kk = 0; kk < KC; ++kk) {
+                        float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (k2base + kk < K) yv = *reinterpret_cast<const float4*>(yr + (size_t)kk * ystride + w);
+                        const float2 y01 = make_float2(yv.x, yv.y), y23 = make_float2(yv.z, yv.w);
+#pragma unroll
+                        for (int dx = 0; dx < T; ++dx) {
+                            ffma2(acc[dx][kk], xp[dx], y01);          // pixels w+0, w+1 pair with window columns dx+0, dx+1
+                            ffma2(acc[dx][kk], xp[dx + 2], y23);      // pixels w+2, w+3
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+        }
+        if (active) {
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) {
+                const int k2 = k2base + kk;
+                if (k2 < K) {
+#pragma unroll
+                    for (int dx = 0; dx < T; ++dx)
+                        atomicAdd(&jsm[((k1 * K + k2) * T + dy) * T + dx], acc[dx][kk].x + acc[dx][kk].y);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nj; i += JT_THREADS) partials[(size_t)blockIdx.x * nj + i] = jsm[i];
+}
+
+// ------------------------------------------------------------------------------------------------------ backward
+constexpr int BT_TW = 32, BT_TH = 32;
+constexpr int BT_THREADS = BT_TH * (BT_TW / 4) + 32;     // 256 compute threads + producer warp
+constexpr int BT_STAGES = 3;     // ring of single-operand halo boxes: x(t), y(t), x(t+1), y(t+1), ...
+
+// one output map (dL/dy from the x tile with gA, or dL/dx from the y tile with gB) for 4 pixels x KC channels
+template <int PAD, int KC>
+__device__ __forceinline__ void bwd_phase_f2(const float* __restrict__ tile, const float2* __restrict__ gtab, int K, int HH,
+                                             int XWB, int CO, int KP, int r, int q, int k_out_base, float2 (&acc)[KC][2]) {
+    constexpr int T = 2 * PAD + 1;
+    constexpr int TP = 4;                      // (g,g) pairs per (k_in, dy, k_out), padded to 4 -> two LDS.128
+#pragma unroll
+    for (int c = 0; c < KC; ++c) acc[c][0] = acc[c][1] = make_float2(0.f, 0.f);
+    for (int kin = 0; kin < K; ++kin) {
+#pragma unroll
+        for (int dyy = 0; dyy < T; ++dyy) {
+            const float* row = tile + (size_t)(kin * HH + r + dyy) * XWB + 4 * q;    // box col = image col - w0 + CO
+            float xw[4 + 2 * PAD];
+            if (PAD > 0) {
+                const float4 f0 = *reinterpret_cast<const float4*>(row), f1 = *reinterpret_cast<const float4*>(row + 4);
+                const float4 f2 = *reinterpret_cast<const float4*>(row + 8);
+                const float a[12] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
+#pragma unroll
+                for (int i = 0; i < 4 + 2 * PAD; ++i) xw[i] = a[4 - PAD + i];      // CO == 4 whenever PAD > 0
+            } else {
+                const float4 f = *reinterpret_cast<const float4*>(row);
+                xw[0] = f.x; xw[1] = f.y; xw[2] = f.z; xw[3] = f.w;
+            }
+            float2 xp[3 + 2 * PAD];
+#pragma unroll
+            for (int i = 0; i < 3 + 2 * PAD; ++i) xp[i] = make_float2(xw[i], xw[i + 1]);
+            const float2* gp = gtab + (size_t)((kin * T + dyy) * KP + k_out_base) * TP;
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                const float4 g01 = *reinterpret_cast<const float4*>(gp + c * TP);          // (g0,g0,g1,g1)
+                float4 g23 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (T > 2) g23 = *reinterpret_cast<const float4*>(gp + c * TP + 2);
+                const float2 gv[4] = {make_float2(g01.x, g01.y), make_float2(g01.z, g01.w), make_float2(g23.x, g23.y),
+                                      make_float2(g23.z, g23.w)};
+#pragma unroll
+                for (int dxx = 0; dxx < (T < 4 ? T : 4); ++dxx) {
+                    ffma2(acc[c][0], gv[dxx], xp[dxx]);
+                    ffma2(acc[c][1], gv[dxx], xp[dxx + 2]);
+                }
+            }
+        }
+    }
+}
+
+template <int PAD, int KC>
+__global__ void __launch_bounds__(BT_THREADS, 1)
+iic_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, IICTmaGeom g,
+                   const float* __restrict__ djoint, const float* __restrict__ gscale, float* __restrict__ dx_out,
+                   float* __restrict__ dy_out) {
+    constexpr int T = 2 * PAD + 1;
+    constexpr int TP = 4;
+    static_assert(T <= 4, "the packed backward keeps one float4 pair-block per displacement row: padding <= 1");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    float* stage0 = reinterpret_cast<float*>(smem);
+    const int K = g.K;
+    const int nchunk = (K + KC - 1) / KC, KP = nchunk * KC;
+    const int stage_floats = g.x_stage_floats;
+    float2* gA = reinterpret_cast<float2*>(stage0 + (size_t)BT_STAGES * stage_floats);
+    const int gsz = K * T * KP * TP;
+    float2* gB = gA + gsz;
+    uint64_t* full = reinterpret_cast<uint64_t*>(gB + gsz);
+    uint64_t* empty = full + BT_STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NCW = (BT_THREADS - 32) / 32;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < BT_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NCW); }
+        fence_barrier_init();
+    }
+    const float scale = gscale[0];
+    for (int i = threadIdx.x; i < gsz; i += BT_THREADS) {
+        const int dxx = i % TP, ko = (i / TP) % KP, dyy = (i / (TP * KP)) % T, kin = i / (TP * KP * T);
+        float a = 0.f, b = 0.f;
+        if (dxx < T && ko < K) {
+            a = djoint[((kin * K + ko) * T + dyy) * T + dxx] * scale;                       // g[k1=kin, k2=ko, dy, dx]
+            b = djoint[((ko * K + kin) * T + (T - 1 - dyy)) * T + (T - 1 - dxx)] * scale;   // g[k1=ko, k2=kin] flipped
+        }
+        gA[i] = make_float2(a, a);
+        gB[i] = make_float2(b, b);
+    }
+    __syncthreads();
+
+    const uint32_t stage_bytes = (uint32_t)(K * g.HH * g.XWB) * 4u;
+    if (warp == NCW) {
+        if (elect_one()) {
+            prefetch_tmap(&tmx);
+            prefetch_tmap(&tmy);
+            Ring<BT_STAGES> ring;
+            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+                const int b = tile / (g.tiles_h * g.tiles_w);
+                const int trem = tile % (g.tiles_h * g.tiles_w);
+                const int h0 = (trem / g.tiles_w) * g.TH, w0 = (trem % g.tiles_w) * g.TW;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half, ring.next()) {
+                    const uint32_t s = ring.stage();
+                    mbar_wait(empty + s, ring.phase() ^ 1u);
+                    mbar_arrive_expect_tx(full + s, stage_bytes);
+                    tma_load_3d(stage0 + (size_t)s * stage_floats, half ? &tmy : &tmx, full + s, w0 - g.CO, h0 - PAD, b * K);
+                }
+            }
+        }
+    } else {
+        const int r = threadIdx.x / (BT_TW / 4), q = threadIdx.x % (BT_TW / 4);
+        Ring<BT_STAGES> ring;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+            const int b = tile / (g.tiles_h * g.tiles_w);
+            const int trem = tile % (g.tiles_h * g.tiles_w);
+            const int h0 = (trem / g.tiles_w) * g.TH, w0 = (trem % g.tiles_w) * g.TW;
+            const int h = h0 + r, w = w0 + 4 * q;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half, ring.next()) {
+                // half 0: x box -> dL/dy = sum_{k1,dy,dx} g[k1,k2,dy,dx] x[b,k1,h+dy-p,w+dx-p]
+                // half 1: y box -> dL/dx = sum_{k2,dy,dx} g[k1,k2,dy,dx] y[b,k2,h-dy+p,w-dx+p]   (flipped table gB)
+                const uint32_t s = ring.stage();
+                mbar_wait(full + s, ring.phase());
+                const float* box = stage0 + (size_t)s * stage_floats;
+                const float2* gtab = half ? gB : gA;
+                float* out = half ? dx_out : dy_out;
+                if (h < g.H && w < g.W) {
+                    float2 acc[KC][2];
+                    for (int c2 = 0; c2 < nchunk; ++c2) {
+                        bwd_phase_f2<PAD, KC>(box, gtab, K, g.HH, g.XWB, g.CO, KP, r, q, c2 * KC, acc);
+#pragma unroll
+                        for (int c = 0; c < KC; ++c) {
+                            const int ko = c2 * KC + c;
+                            if (ko < K)      // W % 4 == 0 and w % 4 == 0: the four pixels are inside the row together
+                                *reinterpret_cast<float4*>(out + (((size_t)b * K + ko) * g.H + h) * g.W + w) =
+                                    make_float4(acc[c][0].x, acc[c][0].y, acc[c][1].x, acc[c][1].y);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + s);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------ host
+// box column of the tile's first pixel: the TMA start coordinate w0 - CO must be a multiple of 4 floats (16 bytes)
+static int col_origin(int pad) { return pad > 0 ? 4 : 0; }
+
+static int make_map3d(CUtensorMap* m, const void* base, int B, int K, int H, int W, int box_w, int box_h) {
+    EncodeTiledFn fn = tensor_map_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CY_ERR_DEVICE; }
+    cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)K * (cuuint64_t)B};
+    cuuint64_t gstride[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)K};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3d) failed (%d)", (int)r); return CY_ERR_ARG; }
+    return CY_OK;
+}
+
+static int pick_kc_tma(int K) {
+    const int opts[] = {4, 5, 8, 10, 16, 20};
+    for (int o : opts)
+        if (K <= o) return o;
+    return 0;
+}
+
+static int sm_count_tma() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int pick_tw_fwd(int W) {
+    int best = 4, best_cost = 1 << 30;
+    for (int tw = 4; tw <= 64; tw += 4) {
+        const int tiles = (W + tw - 1) / tw;
+        const int cost = tiles * tw * 64 + tiles;
+        if (cost <= best_cost) { best_cost = cost; best = tw; }
+    }
+    return best;
+}
+
+static bool fwd_geom(int B, int K, int H, int W, int pad, IICTmaGeom* g, int* kc, size_t* smem) {
+    const int T = 2 * pad + 1;
+    if (pad > 3 || (W % 4) != 0 || K > 256) return false;
+    *kc = pick_kc_tma(K);
+    if (!*kc) return false;
+    const int nchunk = (K + *kc - 1) / *kc;
+    if (T * K * nchunk > 32 || T * *kc > 64) return false;
+    g->B = B; g->K = K; g->H = H; g->W = W;
+    g->TH = JT_COMPUTE_WARPS;                 // 9 rows: HH = 9 + 2p == T (mod 8)
+    g->TW = pick_tw_fwd(W);
+    g->CO = col_origin(pad);
+    g->HH = g->TH + 2 * pad;
+    int xwb = pad > 0 ? g->TW + 8 : g->TW;      // the sliding window reads three aligned float4 per step
+    if (((xwb / 4) & 1) == 0) xwb += 4;
+    g->XWB = xwb;
+    if (xwb > 256 || g->HH > 256) return false;
+    g->tiles_h = (H + g->TH - 1) / g->TH;
+    g->tiles_w = (W + g->TW - 1) / g->TW;
+    g->n_tiles = B * g->tiles_h * g->tiles_w;
+    g->x_stage_floats = (K * g->HH * g->XWB + 31) & ~31;
+    g->y_stage_floats = (K * g->TH * g->TW + 31) & ~31;
+    const int nj = K * K * T * T;
+    *smem = ((size_t)JT_STAGES * (g->x_stage_floats + g->y_stage_floats) + ((nj + 31) & ~31)) * 4 + 2 * JT_STAGES * 8 + 128 + 64;
+    return *smem <= 220 * 1024;
+}
+
+int iic_joint_tma_grid(int B, int K, int H, int W, int pad) {
+    IICTmaGeom g; int kc; size_t smem;
+    if (!fwd_geom(B, K, H, W, pad, &g, &kc, &smem)) return 0;
+    const int sms = sm_count_tma();
+    return g.n_tiles < sms ? g.n_tiles : sms;
+}
+
+template <int PAD, int KC>
+static int launch_joint_tma(const CUtensorMap& tmx, const CUtensorMap& tmy, const IICTmaGeom& g, size_t smem, int grid,
+                            float* partials, cudaStream_t st) {
+    if constexpr ((2 * PAD + 1) * KC > 64) {       // accumulator pairs would not fit the register file: not instantiated
+        return CY_ERR_UNSUPPORTED;
+    } else {
+    auto k = iic_joint_tma_kernel<PAD, KC>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("iic_joint_tma smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
+    k<<<grid, JT_THREADS, smem, st>>>(tmx, tmy, g, partials);
+    CY_CHECK_LAUNCH("iic_joint_tma");
+    return CY_OK;
+    }
+}
+
+#define TMA_DISPATCH_KC(FN, PADV, ...)                                  \
+    switch (kc) {                                                        \
+        case 4: return FN<PADV, 4>(__VA_ARGS__);                         \
+        case 5: return FN<PADV, 5>(__VA_ARGS__);                         \
+        case 8: return FN<PADV, 8>(__VA_ARGS__);                         \
+        case 10: return FN<PADV, 10>(__VA_ARGS__);                       \
+        case 16: return FN<PADV, 16>(__VA_ARGS__);                       \
+        case 20: return FN<PADV, 20>(__VA_ARGS__);                       \
+    }
+
+// returns CY_ERR_UNSUPPORTED when the shape is not eligible (the caller then takes the SIMT kernels)
+int iic_joint_tma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, float* partials, int* n_partials,
+                  cudaStream_t st) {
+    IICTmaGeom g; int kc; size_t smem;
+    if (dtype != CY_F32 || !aligned16(x) || !aligned16(y) || !fwd_geom(B, K, H, W, pad, &g, &kc, &smem)) return CY_ERR_UNSUPPORTED;
+    CUtensorMap tmx, tmy;
+    int rc = make_map3d(&tmx, x, B, K, H, W, g.XWB, g.HH);
+    if (rc) return rc;
+    rc = make_map3d(&tmy, y, B, K, H, W, g.TW, g.TH);
+    if (rc) return rc;
+    const int grid = iic_joint_tma_grid(B, K, H, W, pad);
+    *n_partials = grid;
+    switch (pad) {
+        case 0: TMA_DISPATCH_KC(launch_joint_tma, 0, tmx, tmy, g, smem, grid, partials, st) break;
+        case 1: TMA_DISPATCH_KC(launch_joint_tma, 1, tmx, tmy, g, smem, grid, partials, st) break;
+        case 2: TMA_DISPATCH_KC(launch_joint_tma, 2, tmx, tmy, g, smem, grid, partials, st) break;
+        case 3: TMA_DISPATCH_KC(launch_joint_tma, 3, tmx, tmy, g, smem, grid, partials, st) break;
+    }
+    return CY_ERR_UNSUPPORTED;
+}
+
+template <int PAD, int KC>
+static int launch_bwd_tma(const CUtensorMap& tmx, const CUtensorMap& tmy, const IICTmaGeom& g, size_t smem, int grid,
+                          const float* djoint, const float* gscale, float* dx, float* dy, cudaStream_t st) {
+    auto k = iic_bwd_tma_kernel<PAD, KC>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("iic_bwd_tma smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
+    k<<<grid, BT_THREADS, smem, st>>>(tmx, tmy, g, djoint, gscale, dx, dy);
+    CY_CHECK_LAUNCH("iic_bwd_tma");
+    return CY_OK;
+}
+
+int iic_bwd_tma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
+                const float* gscale, void* dx, void* dy, cudaStream_t st) {
+    if (dtype != CY_F32 || pad > 1 || (W % 4) != 0 || !aligned16(x) || !aligned16(y) || !aligned16(dx) || !aligned16(dy))
+        return CY_ERR_UNSUPPORTED;
+    const int kc = pick_kc_tma(K);
+    if (!kc) return CY_ERR_UNSUPPORTED;
+    const int T = 2 * pad + 1;
+    IICTmaGeom g;
+    g.B = B; g.K = K; g.H = H; g.W = W;
+    g.TH = BT_TH; g.TW = BT_TW;
+    g.CO = col_origin(pad);
+    g.HH = g.TH + 2 * pad;
+    g.XWB = pad > 0 ? g.TW + 8 : g.TW;
+    g.tiles_h = (H + g.TH - 1) / g.TH;
+    g.tiles_w = (W + g.TW - 1) / g.TW;
+    g.n_tiles = B * g.tiles_h * g.tiles_w;
+    g.x_stage_floats = (K * g.HH * g.XWB + 31) & ~31;
+    g.y_stage_floats = g.x_stage_floats;
+    const int nchunk = (K + kc - 1) / kc, KP = nchunk * kc;
+    const size_t smem = (size_t)BT_STAGES * g.x_stage_floats * 4 + (size_t)2 * K * T * KP * 4 * 8 + 2 * BT_STAGES * 8 + 128 + 64;
+    if (smem > 220 * 1024) return CY_ERR_UNSUPPORTED;
+    CUtensorMap tmx, tmy;
+    int rc = make_map3d(&tmx, x, B, K, H, W, g.XWB, g.HH);
+    if (rc) return rc;
+    rc = make_map3d(&tmy, y, B, K, H, W, g.XWB, g.HH);
+    if (rc) return rc;
+    const int sms = sm_count_tma();
+    const int grid = g.n_tiles < sms ? g.n_tiles : sms;
+    float* dxf = reinterpret_cast<float*>(dx);
+    float* dyf = reinterpret_cast<float*>(dy);
+    switch (pad) {
+        case 0: TMA_DISPATCH_KC(launch_bwd_tma, 0, tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st) break;
+        case 1: TMA_DISPATCH_KC(launch_bwd_tma, 1, tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st) break;
+    }
+    return CY_ERR_UNSUPPORTED;
+}
+
+}  // namespace cy

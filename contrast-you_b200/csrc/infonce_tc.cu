@@ -529,7 +529,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn encode_fn() {
+EncodeTiledFn tensor_map_encode_fn() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -543,7 +543,7 @@ static EncodeTiledFn encode_fn() {
 
 // [N, 256] bf16, row pitch ldz elements; box = 64 columns (128 B, the swizzle span) x 64 rows
 static int make_tmap(CUtensorMap* m, const void* z, int64_t N, int64_t ldz) {
-    EncodeTiledFn fn = encode_fn();
+    EncodeTiledFn fn = tensor_map_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CY_ERR_DEVICE; }
     cuuint64_t gdim[2] = {(cuuint64_t)TC_D, (cuuint64_t)N};
     cuuint64_t gstride[1] = {(cuuint64_t)ldz * 2};
