@@ -12,6 +12,7 @@
 // (mod 8) and box-width/4 odd, so the 8 lanes of an LDS.128 phase read 8 distinct 16-byte bank groups.
 // Eligibility (host side, iic_tma_supported): fp32, W % 4 == 0, 16-byte aligned bases, padding <= 3, T*K*chunks <= 32.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -55,16 +56,46 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
 #endif
 }
 
+// packed-pair plumbing: values travel as 64-bit registers so that ptxas sees one clean dataflow per pair
+typedef unsigned long long u64;
+__device__ __forceinline__ void ffma2_u(u64& d, const u64 a, const u64 b) {
+#ifdef CY_NO_F32X2
+    float2 dd = reinterpret_cast<float2&>(d);
+    const float2 aa = reinterpret_cast<const float2&>(a), bb = reinterpret_cast<const float2&>(b);
+    dd.x = fmaf(aa.x, bb.x, dd.x);
+    dd.y = fmaf(aa.y, bb.y, dd.y);
+    d = reinterpret_cast<u64&>(dd);
+#else
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+#endif
+}
+__device__ __forceinline__ u64 pack_hi_lo(const u64 left, const u64 right) {     // (hi half of left, lo half of right)
+    uint32_t l0, l1, r0, r1;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(l0), "=r"(l1) : "l"(left));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(r0), "=r"(r1) : "l"(right));
+    u64 o;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(o) : "r"(l1), "r"(r0));
+    return o;
+}
+// pair (column c, column c+1) of a 12-column window held as six even-aligned 64-bit pairs v[0..5]
+template <int C>
+__device__ __forceinline__ u64 window_pair(const u64 (&v)[6]) {
+    if constexpr ((C & 1) == 0) return v[C / 2];
+    else return pack_hi_lo(v[(C - 1) / 2], v[(C + 1) / 2]);
+}
+
 constexpr int JT_COMPUTE_WARPS = 9;                 // one per tile row (TH == 9)
 constexpr int JT_THREADS = (JT_COMPUTE_WARPS + 1) * 32;
-constexpr int JT_STAGES = 3;
 
 // ------------------------------------------------------------------------------------------------------ forward
-template <int PAD, int KC>
-__global__ void __launch_bounds__(JT_THREADS, 1)
+// PK = true : packed fma.rn.f32x2, 3 stages, 1 CTA / SM (accumulator pairs cost 2*T*KC registers)
+// PK = false: scalar FFMA, 2 stages, 2 CTAs / SM (same FMA-pipe throughput on sm_100; twice the resident warps)
+template <int PAD, int KC, bool PK>
+__global__ void __launch_bounds__(JT_THREADS, PK ? 1 : 2)
 iic_joint_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, IICTmaGeom g,
                      float* __restrict__ partials) {
     constexpr int T = 2 * PAD + 1;
+    constexpr int JT_STAGES = PK ? 3 : 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     float* stage0 = reinterpret_cast<float*>(smem);
@@ -111,11 +142,16 @@ iic_joint_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
         const int k1 = rr / T, dy = rr % T;            // k1-major: consecutive lanes -> consecutive (k1*HH + dy) mod 8
         const int k2base = c2 * KC;
         const int h = warp;                            // tile row owned by this warp
-        float2 acc[T][KC];
+        u64 acc[PK ? T : 1][PK ? KC : 1];    // (even-pixel partial sum, odd-pixel partial sum) as packed fp32 pairs
+        float accs[PK ? 1 : T][PK ? 1 : KC];  // scalar variant
 #pragma unroll
-        for (int a = 0; a < T; ++a)
+        for (int a = 0; a < (PK ? T : 1); ++a)
 #pragma unroll
-            for (int c = 0; c < KC; ++c) acc[a][c] = make_float2(0.f, 0.f);
+            for (int c = 0; c < (PK ? KC : 1); ++c) acc[a][c] = 0ull;
+#pragma unroll
+        for (int a = 0; a < (PK ? 1 : T); ++a)
+#pragma unroll
+            for (int c = 0; c < (PK ? 1 : KC); ++c) accs[a][c] = 0.f;
 
         Ring<JT_STAGES> ring;
         for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ring.next()) {
@@ -129,40 +165,68 @@ iic_joint_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
                 const float* xr = xs + (size_t)(k1 * g.HH + h + dy) * g.XWB;
                 const float* yr = ys + (size_t)(k2base * g.TH + h) * g.TW;
                 const int ystride = g.TH * g.TW;
-                float a[12];                                   // box columns w .. w+11 of the current step
-                if (PAD > 0) {
-                    const float4 f0 = *reinterpret_cast<const float4*>(xr), f1 = *reinterpret_cast<const float4*>(xr + 4);
-                    a[4] = f0.x; a[5] = f0.y; a[6] = f0.z; a[7] = f0.w;
-                    a[8] = f1.x; a[9] = f1.y; a[10] = f1.z; a[11] = f1.w;
-                }
-                for (int w = 0; w < g.TW; w += 4) {
-                    float xw[4 + 2 * PAD];
-                    if (PAD > 0) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) a[e] = a[e + 4];
-                        const float4 f = *reinterpret_cast<const float4*>(xr + w + 8);
-                        a[8] = f.x; a[9] = f.y; a[10] = f.z; a[11] = f.w;
-#pragma unroll
-                        for (int i = 0; i < 4 + 2 * PAD; ++i) xw[i] = a[4 - PAD + i];
-                    } else {
-                        const float4 f = *reinterpret_cast<const float4*>(xr + w);
-                        xw[0] = f.x; xw[1] = f.y; xw[2] = f.z; xw[3] = f.w;
-                    }
-                    // pairs (xw[i], xw[i+1]) for every start i in [0, 2 + 2*PAD]
-                    float2 xp[3 + 2 * PAD];
-#pragma unroll
-                    for (int i = 0; i < 3 + 2 * PAD; ++i) xp[i] = make_float2(xw[i], xw[i + 1]);
+                // One step = 4 pixels (columns w..w+3 of the tile).  The x window of a step spans three aligned float4
+                // (box columns w..w+11); the step loop is unrolled by three with rotating names so that the window never
+                // has to be shifted through registers.  Rows of y beyond K (KC does not divide K) read the zero-padded /
+                // stale tail of the stage; their accumulators are discarded.
+                auto step = [&](const ulonglong2& p, const ulonglong2& c, const ulonglong2& n, int w) {
+                  if constexpr (!PK) {
+                    const float4 pf = reinterpret_cast<const float4&>(p), cf = reinterpret_cast<const float4&>(c);
+                    const float4 nf = reinterpret_cast<const float4&>(n);
+                    const float a[12] = {pf.x, pf.y, pf.z, pf.w, cf.x, cf.y, cf.z, cf.w, nf.x, nf.y, nf.z, nf.w};
 #pragma unroll
                     for (int kk = 0; kk < KC; ++kk) {
-                        float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (k2base + kk < K) yv = *reinterpret_cast<const float4*>(yr + (size_t)kk * ystride + w);
-                        const float2 y01 = make_float2(yv.x, yv.y), y23 = make_float2(yv.z, yv.w);
+                        const float4 yv = *reinterpret_cast<const float4*>(yr + (size_t)kk * ystride + w);
 #pragma unroll
                         for (int dx = 0; dx < T; ++dx) {
-                            ffma2(acc[dx][kk], xp[dx], y01);          // pixels w+0, w+1 pair with window columns dx+0, dx+1
-                            ffma2(acc[dx][kk], xp[dx + 2], y23);      // pixels w+2, w+3
+                            float t = accs[dx][kk];
+                            t = fmaf(a[4 - PAD + dx + 0], yv.x, t);
+                            t = fmaf(a[4 - PAD + dx + 1], yv.y, t);
+                            t = fmaf(a[4 - PAD + dx + 2], yv.z, t);
+                            t = fmaf(a[4 - PAD + dx + 3], yv.w, t);
+                            accs[dx][kk] = t;
                         }
                     }
+                  } else {
+                    const u64 v[6] = {p.x, p.y, c.x, c.y, n.x, n.y};        // columns (0,1) (2,3) ... (10,11) of the window
+                    u64 xp[3 + 2 * PAD];                                     // xp[i] = columns (4-PAD+i, 5-PAD+i)
+                    xp[0] = window_pair<4 - PAD>(v);
+                    xp[1] = window_pair<5 - PAD>(v);
+                    xp[2] = window_pair<6 - PAD>(v);
+                    if constexpr (PAD >= 1) { xp[3] = window_pair<7 - PAD>(v); xp[4] = window_pair<8 - PAD>(v); }
+                    if constexpr (PAD >= 2) { xp[5] = window_pair<9 - PAD>(v); xp[6] = window_pair<10 - PAD>(v); }
+                    if constexpr (PAD >= 3) { xp[7] = window_pair<11 - PAD>(v); xp[8] = window_pair<12 - PAD>(v); }
+#pragma unroll
+                    for (int kk = 0; kk < KC; ++kk) {
+                        const ulonglong2 yv = *reinterpret_cast<const ulonglong2*>(yr + (size_t)kk * ystride + w);
+#pragma unroll
+                        for (int dx = 0; dx < T; ++dx) {
+                            ffma2_u(acc[dx][kk], xp[dx], yv.x);          // pixels w+0, w+1 pair with window columns dx+0, dx+1
+                            ffma2_u(acc[dx][kk], xp[dx + 2], yv.y);      // pixels w+2, w+3
+                        }
+                    }
+                  }
+                };
+                if (PAD > 0) {
+                    ulonglong2 p = *reinterpret_cast<const ulonglong2*>(xr), c = *reinterpret_cast<const ulonglong2*>(xr + 4), n;
+                    int w = 0;
+                    for (; w + 12 <= g.TW; w += 12) {
+                        n = *reinterpret_cast<const ulonglong2*>(xr + w + 8);
+                        step(p, c, n, w);
+                        p = *reinterpret_cast<const ulonglong2*>(xr + w + 12);
+                        step(c, n, p, w + 4);
+                        c = *reinterpret_cast<const ulonglong2*>(xr + w + 16);
+                        step(n, p, c, w + 8);
+                    }
+                    for (; w < g.TW; w += 4) {
+                        n = *reinterpret_cast<const ulonglong2*>(xr + w + 8);
+                        step(p, c, n, w);
+                        p = c;
+                        c = n;
+                    }
+                } else {
+                    const ulonglong2 z4 = make_ulonglong2(0ull, 0ull);
+                    for (int w = 0; w < g.TW; w += 4) step(z4, *reinterpret_cast<const ulonglong2*>(xr + w), z4, w);
                 }
             }
             __syncwarp();
@@ -175,7 +239,16 @@ iic_joint_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
                 if (k2 < K) {
 #pragma unroll
                     for (int dx = 0; dx < T; ++dx)
-                        atomicAdd(&jsm[((k1 * K + k2) * T + dy) * T + dx], acc[dx][kk].x + acc[dx][kk].y);
+                    {
+                        float v;
+                        if constexpr (PK) {
+                            const float2 pr = reinterpret_cast<const float2&>(acc[dx][kk]);
+                            v = pr.x + pr.y;
+                        } else {
+                            v = accs[dx][kk];
+                        }
+                        atomicAdd(&jsm[((k1 * K + k2) * T + dy) * T + dx], v);
+                    }
                 }
             }
         }
@@ -233,7 +306,45 @@ __device__ __forceinline__ void bwd_phase_f2(const float* __restrict__ tile, con
     }
 }
 
+// scalar variant of the phase: dL/dJ rows are float4 (g0, g1, g2, 0) broadcasts, half the shared-memory wavefronts of
+// the packed form and half the accumulator registers; same FMA-pipe time on sm_100
 template <int PAD, int KC>
+__device__ __forceinline__ void bwd_phase_f1(const float* __restrict__ tile, const float4* __restrict__ gtab, int K, int HH,
+                                             int XWB, int KP, int r, int q, int k_out_base, float (&acc)[KC][4]) {
+    constexpr int T = 2 * PAD + 1;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+    for (int kin = 0; kin < K; ++kin) {
+#pragma unroll
+        for (int dyy = 0; dyy < T; ++dyy) {
+            const float* row = tile + (size_t)(kin * HH + r + dyy) * XWB + 4 * q;
+            float xw[4 + 2 * PAD];
+            if (PAD > 0) {
+                const float4 f0 = *reinterpret_cast<const float4*>(row), f1 = *reinterpret_cast<const float4*>(row + 4);
+                const float4 f2 = *reinterpret_cast<const float4*>(row + 8);
+                const float a[12] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
+#pragma unroll
+                for (int i = 0; i < 4 + 2 * PAD; ++i) xw[i] = a[4 - PAD + i];
+            } else {
+                const float4 f = *reinterpret_cast<const float4*>(row);
+                xw[0] = f.x; xw[1] = f.y; xw[2] = f.z; xw[3] = f.w;
+            }
+            const float4* gp = gtab + (size_t)((kin * T + dyy) * KP + k_out_base);
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                const float4 g4 = gp[c];
+                const float gv[3] = {g4.x, g4.y, g4.z};
+#pragma unroll
+                for (int dxx = 0; dxx < T; ++dxx) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[c][e] = fmaf(gv[dxx], xw[dxx + e], acc[c][e]);
+                }
+            }
+        }
+    }
+}
+
+template <int PAD, int KC, bool PK>
 __global__ void __launch_bounds__(BT_THREADS, 1)
 iic_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, IICTmaGeom g,
                    const float* __restrict__ djoint, const float* __restrict__ gscale, float* __restrict__ dx_out,
@@ -248,7 +359,7 @@ iic_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
     const int nchunk = (K + KC - 1) / KC, KP = nchunk * KC;
     const int stage_floats = g.x_stage_floats;
     float2* gA = reinterpret_cast<float2*>(stage0 + (size_t)BT_STAGES * stage_floats);
-    const int gsz = K * T * KP * TP;
+    const int gsz = K * T * KP * TP;      // packed: TP (g,g) float2 pairs per row; scalar: the same bytes hold 2 float4 rows, 1 used
     float2* gB = gA + gsz;
     uint64_t* full = reinterpret_cast<uint64_t*>(gB + gsz);
     uint64_t* empty = full + BT_STAGES;
@@ -267,8 +378,13 @@ iic_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
             a = djoint[((kin * K + ko) * T + dyy) * T + dxx] * scale;                       // g[k1=kin, k2=ko, dy, dx]
             b = djoint[((ko * K + kin) * T + (T - 1 - dyy)) * T + (T - 1 - dxx)] * scale;   // g[k1=ko, k2=kin] flipped
         }
-        gA[i] = make_float2(a, a);
-        gB[i] = make_float2(b, b);
+        if constexpr (PK) {
+            gA[i] = make_float2(a, a);
+            gB[i] = make_float2(b, b);
+        } else {       // float4 rows (g0, g1, g2, 0) indexed [(kin*T + dyy)*KP + ko]
+            reinterpret_cast<float*>(gA)[i] = a;
+            reinterpret_cast<float*>(gB)[i] = b;
+        }
     }
     __syncthreads();
 
@@ -309,15 +425,27 @@ iic_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
                 const float2* gtab = half ? gB : gA;
                 float* out = half ? dx_out : dy_out;
                 if (h < g.H && w < g.W) {
-                    float2 acc[KC][2];
                     for (int c2 = 0; c2 < nchunk; ++c2) {
-                        bwd_phase_f2<PAD, KC>(box, gtab, K, g.HH, g.XWB, g.CO, KP, r, q, c2 * KC, acc);
+                        if constexpr (PK) {
+                            float2 acc[KC][2];
+                            bwd_phase_f2<PAD, KC>(box, gtab, K, g.HH, g.XWB, g.CO, KP, r, q, c2 * KC, acc);
 #pragma unroll
-                        for (int c = 0; c < KC; ++c) {
-                            const int ko = c2 * KC + c;
-                            if (ko < K)      // W % 4 == 0 and w % 4 == 0: the four pixels are inside the row together
-                                *reinterpret_cast<float4*>(out + (((size_t)b * K + ko) * g.H + h) * g.W + w) =
-                                    make_float4(acc[c][0].x, acc[c][0].y, acc[c][1].x, acc[c][1].y);
+                            for (int c = 0; c < KC; ++c) {
+                                const int ko = c2 * KC + c;
+                                if (ko < K)      // W % 4 == 0 and w % 4 == 0: the four pixels are inside the row together
+                                    *reinterpret_cast<float4*>(out + (((size_t)b * K + ko) * g.H + h) * g.W + w) =
+                                        make_float4(acc[c][0].x, acc[c][0].y, acc[c][1].x, acc[c][1].y);
+                            }
+                        } else {
+                            float acc[KC][4];
+                            bwd_phase_f1<PAD, KC>(box, reinterpret_cast<const float4*>(gtab), K, g.HH, g.XWB, KP, r, q, c2 * KC, acc);
+#pragma unroll
+                            for (int c = 0; c < KC; ++c) {
+                                const int ko = c2 * KC + c;
+                                if (ko < K)
+                                    *reinterpret_cast<float4*>(out + (((size_t)b * K + ko) * g.H + h) * g.W + w) =
+                                        make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+                            }
                         }
                     }
                 }
@@ -376,7 +504,17 @@ static int pick_tw_fwd(int W) {
     return best;
 }
 
+static bool packed_fwd() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("CY_IIC_PACKED");     // 1: fma.rn.f32x2 forward, 0: scalar forward at twice the occupancy
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on == 1;
+}
+
 static bool fwd_geom(int B, int K, int H, int W, int pad, IICTmaGeom* g, int* kc, size_t* smem) {
+    const int JT_STAGES = packed_fwd() ? 3 : 2;
     const int T = 2 * pad + 1;
     if (pad > 3 || (W % 4) != 0 || K > 256) return false;
     *kc = pick_kc_tma(K);
@@ -395,8 +533,10 @@ static bool fwd_geom(int B, int K, int H, int W, int pad, IICTmaGeom* g, int* kc
     g->tiles_h = (H + g->TH - 1) / g->TH;
     g->tiles_w = (W + g->TW - 1) / g->TW;
     g->n_tiles = B * g->tiles_h * g->tiles_w;
-    g->x_stage_floats = (K * g->HH * g->XWB + 31) & ~31;
-    g->y_stage_floats = (K * g->TH * g->TW + 31) & ~31;
+    // x: the unrolled window may load up to two float4 past the last needed column of the LAST row of the box;
+    // y: unpredicated reads cover nchunk*KC planes
+    g->x_stage_floats = (K * g->HH * g->XWB + 16 + 31) & ~31;
+    g->y_stage_floats = (nchunk * *kc * g->TH * g->TW + 31) & ~31;
     const int nj = K * K * T * T;
     *smem = ((size_t)JT_STAGES * (g->x_stage_floats + g->y_stage_floats) + ((nj + 31) & ~31)) * 4 + 2 * JT_STAGES * 8 + 128 + 64;
     return *smem <= 220 * 1024;
@@ -405,7 +545,7 @@ static bool fwd_geom(int B, int K, int H, int W, int pad, IICTmaGeom* g, int* kc
 int iic_joint_tma_grid(int B, int K, int H, int W, int pad) {
     IICTmaGeom g; int kc; size_t smem;
     if (!fwd_geom(B, K, H, W, pad, &g, &kc, &smem)) return 0;
-    const int sms = sm_count_tma();
+    const int sms = sm_count_tma() * (packed_fwd() ? 1 : 2);
     return g.n_tiles < sms ? g.n_tiles : sms;
 }
 
@@ -415,7 +555,7 @@ static int launch_joint_tma(const CUtensorMap& tmx, const CUtensorMap& tmy, cons
     if constexpr ((2 * PAD + 1) * KC > 64) {       // accumulator pairs would not fit the register file: not instantiated
         return CY_ERR_UNSUPPORTED;
     } else {
-    auto k = iic_joint_tma_kernel<PAD, KC>;
+    auto k = packed_fwd() ? iic_joint_tma_kernel<PAD, KC, true> : iic_joint_tma_kernel<PAD, KC, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("iic_joint_tma smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
     k<<<grid, JT_THREADS, smem, st>>>(tmx, tmy, g, partials);
@@ -458,7 +598,12 @@ int iic_joint_tma(const void* x, const void* y, int dtype, int B, int K, int H, 
 template <int PAD, int KC>
 static int launch_bwd_tma(const CUtensorMap& tmx, const CUtensorMap& tmy, const IICTmaGeom& g, size_t smem, int grid,
                           const float* djoint, const float* gscale, float* dx, float* dy, cudaStream_t st) {
-    auto k = iic_bwd_tma_kernel<PAD, KC>;
+    static int pk = -1;
+    if (pk < 0) {
+        const char* e = getenv("CY_IIC_PACKED_BWD");
+        pk = (e && e[0] == '1') ? 1 : 0;      // default: scalar FFMA (measured faster: fewer shared-memory wavefronts)
+    }
+    auto k = pk ? iic_bwd_tma_kernel<PAD, KC, true> : iic_bwd_tma_kernel<PAD, KC, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("iic_bwd_tma smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
     k<<<grid, BT_THREADS, smem, st>>>(tmx, tmy, g, djoint, gscale, dx, dy);
