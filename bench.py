@@ -47,47 +47,68 @@ def measured_peaks():
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
-    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons sampled every ~10 ms DURING the timed region (NVML in a thread; nvidia-smi fallback)."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self, index):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.sm, self.mx, self.reasons = index, [], None, set()
+        self._stop = threading.Event()
+        self.thread = None
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES so that LOCAL_RANK maps to the right physical GPU
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self._stop.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:  # noqa
+                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.01)
+        except Exception:  # noqa
+            self._smi()
+
+    def _smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                     "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        for line in proc.stdout:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 6:
-                self.samples.append(parts)
+                try:
+                    self.sm.append(float(parts[0])); self.mx = float(parts[1])
+                except ValueError:
+                    pass
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+            if self._stop.is_set():
+                proc.terminate()
+                break
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for s in self.samples:
-            try:
-                sm.append(float(s[0])); mx = float(s[1])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop.set()
+        if self.thread:
+            self.thread.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline

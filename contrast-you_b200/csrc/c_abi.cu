@@ -26,9 +26,9 @@ int labels_canonicalize(const void*, int, int64_t, int32_t*, cudaStream_t);
 // infonce_tc.cu
 bool infonce_tc_supported(int dtype, int64_t N, int64_t d, int64_t ldz, const uint8_t* codes, int variant);
 size_t infonce_tc_workspace_bytes(int64_t N, int64_t d);
-int infonce_fwd_tc(const void*, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, float*, void*, size_t,
+int infonce_fwd_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, float*, void*, size_t,
                    cudaStream_t);
-int infonce_bwd_tc(const void*, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, const float*, const float*,
+int infonce_bwd_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, const float*, const float*,
                    void*, int64_t, void*, size_t, cudaStream_t);
 // iic.cu
 size_t iic_workspace_bytes(int, int, int, int, int);
@@ -55,7 +55,7 @@ static int resolve_path(int path, int dtype, int64_t N, int64_t d, int64_t ldz, 
     const bool tc_ok = infonce_tc_supported(dtype, N, d, ldz, codes, variant);
     if (path == CY_PATH_TCGEN05) {
         if (!tc_ok) {
-            set_error("tcgen05 path needs bf16, d == 256, N %% 128 == 0, labels, variant SUPCON (got dtype=%d N=%lld d=%lld variant=%d)",
+            set_error("tcgen05 path needs bf16 / fp16, d == 256, N %% 128 == 0, labels, variant SUPCON (got dtype=%d N=%lld d=%lld variant=%d)",
                       dtype, (long long)N, (long long)d, variant);
             return CY_ERR_UNSUPPORTED;
         }
@@ -88,7 +88,7 @@ int cy_device_sm_count(void) {
 
 size_t cy_infonce_workspace_bytes(int64_t N, int64_t d, int dtype, int variant, int path) {
     (void)variant;
-    if (path == CY_PATH_SIMT || dtype != CY_BF16) return 16;
+    if (path == CY_PATH_SIMT || dtype == CY_F32) return 16;
     return infonce_tc_workspace_bytes(N, d) + 16;
 }
 
@@ -101,7 +101,7 @@ int cy_infonce_fwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, 
     const int p = resolve_path(path, dtype, N, d, ldz, codes, variant);
     if (p < 0) return p;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (p == 1) return infonce_fwd_tc(z, N, d, ldz, labels, row_begin, row_end, inv_t, stats, workspace, workspace_bytes, st);
+    if (p == 1) return infonce_fwd_tc(z, dtype, N, d, ldz, labels, row_begin, row_end, inv_t, stats, workspace, workspace_bytes, st);
     return infonce_fwd_simt(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, inv_t, variant, 1, 0.f, stats, st);
 }
 
@@ -136,7 +136,7 @@ int cy_infonce_bwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, 
     if (p < 0) return p;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (p == 1)
-        return infonce_bwd_tc(z, N, d, ldz, labels, row_begin, row_end, inv_t, stats, gscale, dz, lddz, workspace,
+        return infonce_bwd_tc(z, dtype, N, d, ldz, labels, row_begin, row_end, inv_t, stats, gscale, dz, lddz, workspace,
                               workspace_bytes, st);
     return infonce_bwd_simt(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, inv_t, variant, gamma, stats, gscale, dz,
                             lddz, st);

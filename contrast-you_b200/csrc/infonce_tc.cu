@@ -47,7 +47,7 @@ struct FwdSmem {
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict__ labels, int N, int row_begin,
-                      int tiles_per_split, float c1, float* __restrict__ part) {
+                      int tiles_per_split, float c1, float* __restrict__ part, uint32_t idesc) {
     using S = FwdSmem<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);    // 1024-aligned, still a shared pointer
@@ -100,8 +100,7 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc = idesc_bf16_f32(TC_BM, BN, 0, 0);
-            const uint32_t a_addr = smem_u32(sA);
+            const uint32_t a_addr = smem_u32(sA);        // idesc: M128 x N(BN) x K16, both operands K-major, bf16 or fp16
             mbar_wait(a_full, 0);
             Ring<S::NSTAGE> ring;
             Ring<S::NACC> acc;
@@ -258,11 +257,29 @@ struct BwdCfg {
     static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024;
 };
 
+// two 16-bit elements of the embedding dtype from two floats
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    if constexpr (F16) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+
+// F16: fp16 embeddings.  W is then stored as fp16 scaled by 2^10 (softmax-sized weights below 6e-8 would flush to zero in
+// fp16; scaled, the flush threshold drops to 6e-11 while the largest weight, ~2, stays far from 65504); the scale is
+// undone in out_scale by the host.
+template <bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict__ labels,
                       const float* __restrict__ stats, int N, int row_begin, int tiles_per_split, float c1,
-                      const float* __restrict__ gscale, float out_scale, __nv_bfloat16* __restrict__ dz, int64_t lddz,
-                      float* __restrict__ dz32) {
+                      const float* __restrict__ gscale, float out_scale, void* __restrict__ dz_v, int64_t lddz,
+                      float* __restrict__ dz32, uint32_t idesc1, uint32_t idesc2) {
+    uint16_t* dz = reinterpret_cast<uint16_t*>(dz_v);
+    constexpr float WS = F16 ? 1024.f : 1.f;
     using C = BwdCfg;
     constexpr int BN = C::BN;
     extern __shared__ uint8_t smem_raw[];
@@ -324,8 +341,7 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc1 = idesc_bf16_f32(TC_BM, BN, 0, 0);      // S  = Zi (K-major) x Zj (K-major)
-            constexpr uint32_t idesc2 = idesc_bf16_f32(TC_BM, TC_D, 0, 1);    // dZ += W (K-major) x Zj (MN-major)
+            // idesc1: S = Zi (K-major) x Zj (K-major), M128 N64;  idesc2: dZ += W (K-major) x Zj (MN-major), M128 N256
             const uint32_t a_addr = smem_u32(sA);
             mbar_wait(a_full, 0);
             Ring<C::NSTAGE> ring1;      // stage / phase of the tile whose MMA1 is issued next
@@ -372,13 +388,13 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
         const int row = q * 32 + lane;
         const int gi = row0 + row;
         const int32_t my_lab = labels[gi];
-        const float coef_i = stats[(size_t)CY_STAT_COEF * N + gi];
-        const float invc_i = stats[(size_t)CY_STAT_INVC * N + gi];
+        const float coef_i = stats[(size_t)CY_STAT_COEF * N + gi] * WS;
+        const float invc_i = stats[(size_t)CY_STAT_INVC * N + gi] * WS;
         float* wcol = sCol + ew * 96;                 // [0,32) labels (as int bits), [32,64) coef_j, [64,96) invc_j
         const int32_t row_lo = __reduce_min_sync(0xffffffffu, my_lab), row_hi = __reduce_max_sync(0xffffffffu, my_lab);
         float nx_lab = __int_as_float(labels[t0 * BN + h * 32 + lane]);
-        float nx_coef = stats[(size_t)CY_STAT_COEF * N + t0 * BN + h * 32 + lane];
-        float nx_invc = stats[(size_t)CY_STAT_INVC * N + t0 * BN + h * 32 + lane];
+        float nx_coef = stats[(size_t)CY_STAT_COEF * N + t0 * BN + h * 32 + lane] * WS;
+        float nx_invc = stats[(size_t)CY_STAT_INVC * N + t0 * BN + h * 32 + lane] * WS;
         Ring<C::NS> sacc;
         Ring<C::NW> wr;
         for (int t = 0; t < nt; ++t, sacc.next(), wr.next()) {
@@ -393,8 +409,8 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
             __syncwarp();
             if (t + 1 < nt) {                             // next tile's column statistics travel during this tile
                 nx_lab = __int_as_float(labels[jbase + BN + lane]);
-                nx_coef = stats[(size_t)CY_STAT_COEF * N + jbase + BN + lane];
-                nx_invc = stats[(size_t)CY_STAT_INVC * N + jbase + BN + lane];
+                nx_coef = stats[(size_t)CY_STAT_COEF * N + jbase + BN + lane] * WS;
+                nx_invc = stats[(size_t)CY_STAT_INVC * N + jbase + BN + lane] * WS;
             }
             mbar_wait(s_full + a, sacc.phase());
             tc_fence_after();
@@ -413,10 +429,8 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                     const float w1 = ex2_approx(fmaf(__uint_as_float(r[e4 * 4 + 1]), c1, -c1)) * (coef_i + cj.y);
                     const float w2 = ex2_approx(fmaf(__uint_as_float(r[e4 * 4 + 2]), c1, -c1)) * (coef_i + cj.z);
                     const float w3 = ex2_approx(fmaf(__uint_as_float(r[e4 * 4 + 3]), c1, -c1)) * (coef_i + cj.w);
-                    __nv_bfloat162 b01 = __floats2bfloat162_rn(w0, w1);
-                    __nv_bfloat162 b23 = __floats2bfloat162_rn(w2, w3);
-                    packed[e4 * 2] = *reinterpret_cast<uint32_t*>(&b01);
-                    packed[e4 * 2 + 1] = *reinterpret_cast<uint32_t*>(&b23);
+                    packed[e4 * 2] = pack2<F16>(w0, w1);
+                    packed[e4 * 2 + 1] = pack2<F16>(w2, w3);
                 }
             } else {
                 const bool diag_tile = __any_sync(0xffffffffu, (gi >= jbase) && (gi < jbase + 32));
@@ -442,10 +456,8 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                         for (int u = 0; u < 4; ++u)
                             if (jbase + e4 * 4 + u == gi) wv[u] = 0.f;
                     }
-                    __nv_bfloat162 b01 = __floats2bfloat162_rn(wv[0], wv[1]);
-                    __nv_bfloat162 b23 = __floats2bfloat162_rn(wv[2], wv[3]);
-                    packed[e4 * 2] = *reinterpret_cast<uint32_t*>(&b01);
-                    packed[e4 * 2 + 1] = *reinterpret_cast<uint32_t*>(&b23);
+                    packed[e4 * 2] = pack2<F16>(wv[0], wv[1]);
+                    packed[e4 * 2 + 1] = pack2<F16>(wv[2], wv[3]);
                 }
             }
             mbar_wait(w_empty + w, wr.phase() ^ 1u);
@@ -466,7 +478,7 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
         tc_fence_after();
         if (dz32 == nullptr) {
             const float scale = gscale[0] * out_scale;
-            __nv_bfloat16* out = dz + (size_t)gi * lddz + h * 128;
+            uint16_t* out = dz + (size_t)gi * lddz + h * 128;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t r[32];
@@ -476,11 +488,8 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                 for (int e = 0; e < 32; e += 8) {
                     uint32_t pk[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(r[e + 2 * u]) * scale,
-                                                                  __uint_as_float(r[e + 2 * u + 1]) * scale);
-                        pk[u] = *reinterpret_cast<uint32_t*>(&b2);
-                    }
+                    for (int u = 0; u < 4; ++u)
+                        pk[u] = pack2<F16>(__uint_as_float(r[e + 2 * u]) * scale, __uint_as_float(r[e + 2 * u + 1]) * scale);
                     *reinterpret_cast<uint4*>(out + c * 32 + e) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             }
@@ -507,8 +516,9 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
 }
 
 // fp32 split accumulator -> bf16 gradient rows (scaled by gscale / (t N))
+template <bool F16>
 __global__ void infonce_tc_convert_kernel(const float* __restrict__ dz32, int64_t rows, int64_t row_begin,
-                                          const float* __restrict__ gscale, float out_scale, __nv_bfloat16* __restrict__ dz,
+                                          const float* __restrict__ gscale, float out_scale, uint16_t* __restrict__ dz,
                                           int64_t lddz) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread = 8 consecutive columns
     if (idx >= rows * (TC_D / 8)) return;
@@ -517,11 +527,9 @@ __global__ void infonce_tc_convert_kernel(const float* __restrict__ dz32, int64_
     const float scale = gscale[0] * out_scale;
     const float4 a = *reinterpret_cast<const float4*>(dz32 + r * TC_D + c);
     const float4 b = *reinterpret_cast<const float4*>(dz32 + r * TC_D + c + 4);
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x * scale, a.y * scale), p1 = __floats2bfloat162_rn(a.z * scale, a.w * scale);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x * scale, b.y * scale), p3 = __floats2bfloat162_rn(b.z * scale, b.w * scale);
     *reinterpret_cast<uint4*>(dz + (row_begin + r) * lddz + c) =
-        make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
-                   *reinterpret_cast<uint32_t*>(&p3));
+        make_uint4(pack2<F16>(a.x * scale, a.y * scale), pack2<F16>(a.z * scale, a.w * scale),
+                   pack2<F16>(b.x * scale, b.y * scale), pack2<F16>(b.z * scale, b.w * scale));
 }
 
 // ------------------------------------------------------------------------------------------------------------ host
@@ -542,14 +550,15 @@ EncodeTiledFn tensor_map_encode_fn() {
 }
 
 // [N, 256] bf16, row pitch ldz elements; box = 64 columns (128 B, the swizzle span) x 64 rows
-static int make_tmap(CUtensorMap* m, const void* z, int64_t N, int64_t ldz) {
+static int make_tmap(CUtensorMap* m, const void* z, int64_t N, int64_t ldz, int dtype) {
     EncodeTiledFn fn = tensor_map_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CY_ERR_DEVICE; }
     cuuint64_t gdim[2] = {(cuuint64_t)TC_D, (cuuint64_t)N};
     cuuint64_t gstride[1] = {(cuuint64_t)ldz * 2};
     cuuint32_t box[2] = {64, 64};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(z), gdim, gstride, box, estr,
+    CUresult r = fn(m, dtype == CY_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void*>(z), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CY_ERR_ARG; }
@@ -557,7 +566,7 @@ static int make_tmap(CUtensorMap* m, const void* z, int64_t N, int64_t ldz) {
 }
 
 bool infonce_tc_supported(int dtype, int64_t N, int64_t d, int64_t ldz, const uint8_t* codes, int variant) {
-    return dtype == CY_BF16 && d == TC_D && (N % 128) == 0 && N >= 256 && (ldz % 8) == 0 && codes == nullptr &&
+    return (dtype == CY_BF16 || dtype == CY_F16) && d == TC_D && (N % 128) == 0 && N >= 256 && (ldz % 8) == 0 && codes == nullptr &&
            variant == CY_SUPCON && N < (int64_t(1) << 30);
 }
 
@@ -609,7 +618,7 @@ size_t infonce_tc_workspace_bytes(int64_t N, int64_t d) {
     return fwd > bwd ? fwd : bwd;
 }
 
-int infonce_fwd_tc(const void* z, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, int64_t row_begin, int64_t row_end,
+int infonce_fwd_tc(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, int64_t row_begin, int64_t row_end,
                    float inv_t, float* stats, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     const int64_t rows = row_end - row_begin;
     if (rows <= 0) return CY_OK;
@@ -620,8 +629,9 @@ int infonce_fwd_tc(const void* z, int64_t N, int64_t d, int64_t ldz, const int32
     const size_t need = (size_t)nslot * 3 * (size_t)N * sizeof(float);
     CY_CHECK_ARG(workspace && workspace_bytes >= need, "infonce_fwd_tc: workspace %zu < %zu", workspace_bytes, need);
     CUtensorMap tmap;
-    int rc = make_tmap(&tmap, z, N, ldz);
+    int rc = make_tmap(&tmap, z, N, ldz, dtype);
     if (rc) return rc;
+    const int fmt = dtype == CY_F16 ? 0 : 1;
     using S = FwdSmem<FWD_BN>;
     auto k = infonce_fwd_tc_kernel<FWD_BN>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
@@ -630,7 +640,7 @@ int infonce_fwd_tc(const void* z, int64_t N, int64_t d, int64_t ldz, const int32
     const int tps = (ctiles + splits - 1) / splits;
     dim3 grid((unsigned)(rows / TC_BM), (unsigned)splits);
     k<<<grid, TC_THREADS, S::TOTAL, st>>>(tmap, labels, (int)N, (int)row_begin, tps, inv_t * LOG2E,
-                                          reinterpret_cast<float*>(workspace));
+                                          reinterpret_cast<float*>(workspace), idesc_f16kind_f32(TC_BM, FWD_BN, 0, 0, fmt));
     CY_CHECK_LAUNCH("infonce_fwd_tc");
     infonce_tc_reduce_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(reinterpret_cast<float*>(workspace), nslot, (int)N,
                                                                             (int)row_begin, (int)row_end, inv_t, stats);
@@ -638,7 +648,7 @@ int infonce_fwd_tc(const void* z, int64_t N, int64_t d, int64_t ldz, const int32
     return CY_OK;
 }
 
-int infonce_bwd_tc(const void* z, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, int64_t row_begin, int64_t row_end,
+int infonce_bwd_tc(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, int64_t row_begin, int64_t row_end,
                    float inv_t, const float* stats, const float* gscale, void* dz, int64_t lddz, void* workspace,
                    size_t workspace_bytes, cudaStream_t st) {
     (void)d;
@@ -648,9 +658,13 @@ int infonce_bwd_tc(const void* z, int64_t N, int64_t d, int64_t ldz, const int32
     CY_CHECK_ARG((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(dz) & 15) == 0 && (lddz % 8) == 0,
                  "tcgen05 path: z / dz must be 16-byte aligned");
     CUtensorMap tmap;
-    int rc = make_tmap(&tmap, z, N, ldz);
+    int rc = make_tmap(&tmap, z, N, ldz, dtype);
     if (rc) return rc;
-    cudaError_t e = cudaFuncSetAttribute(infonce_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdCfg::TOTAL);
+    const bool f16 = dtype == CY_F16;
+    const int fmt = f16 ? 0 : 1;
+    auto kern = f16 ? infonce_bwd_tc_kernel<true> : infonce_bwd_tc_kernel<false>;
+    const float out_scale = (inv_t / (float)N) * (f16 ? (1.f / 1024.f) : 1.f);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdCfg::TOTAL);
     if (e != cudaSuccess) { set_error("bwd_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     const int splits = bwd_splits(N, rows);
     const int nt = (int)(N / BwdCfg::BN);
@@ -664,14 +678,18 @@ int infonce_bwd_tc(const void* z, int64_t N, int64_t d, int64_t ldz, const int32
         if (e != cudaSuccess) { set_error("bwd_tc memset: %s", cudaGetErrorString(e)); return (int)e; }
     }
     dim3 grid((unsigned)(rows / TC_BM), (unsigned)splits);
-    infonce_bwd_tc_kernel<<<grid, TC_THREADS, BwdCfg::TOTAL, st>>>(
-        tmap, labels, stats, (int)N, (int)row_begin, tps, inv_t * LOG2E, gscale, inv_t / (float)N,
-        reinterpret_cast<__nv_bfloat16*>(dz), lddz, dz32);
+    kern<<<grid, TC_THREADS, BwdCfg::TOTAL, st>>>(tmap, labels, stats, (int)N, (int)row_begin, tps, inv_t * LOG2E, gscale, out_scale,
+                                                  dz, lddz, dz32, idesc_f16kind_f32(TC_BM, BwdCfg::BN, 0, 0, fmt),
+                                                  idesc_f16kind_f32(TC_BM, TC_D, 0, 1, fmt));
     CY_CHECK_LAUNCH("infonce_bwd_tc");
     if (dz32) {
         const int64_t n8 = rows * (TC_D / 8);
-        infonce_tc_convert_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dz32, rows, row_begin, gscale, inv_t / (float)N,
-                                                                              reinterpret_cast<__nv_bfloat16*>(dz), lddz);
+        if (f16)
+            infonce_tc_convert_kernel<true><<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dz32, rows, row_begin, gscale, out_scale,
+                                                                                        reinterpret_cast<uint16_t*>(dz), lddz);
+        else
+            infonce_tc_convert_kernel<false><<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dz32, rows, row_begin, gscale, out_scale,
+                                                                                         reinterpret_cast<uint16_t*>(dz), lddz);
         CY_CHECK_LAUNCH("infonce_tc_convert");
     }
     return CY_OK;

@@ -123,9 +123,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 // Instruction descriptor (32 bit) for kind::f16 with bf16 A/B and fp32 D:
 //   [4,6) D fmt: 1 = f32   [7,10) A fmt: 1 = bf16   [10,13) B fmt: 1 = bf16   [15] A major (0 = K)   [16] B major
 //   [17,23) N >> 3         [24,29) M >> 4
+//   fmt: 1 = bf16, 0 = fp16 (both operands)
+__host__ __device__ constexpr uint32_t idesc_f16kind_f32(int M, int N, int a_mn_major, int b_mn_major, int fmt) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn_major << 15) |
+           ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return idesc_f16kind_f32(M, N, a_mn_major, b_mn_major, 1);
 }
 
 __device__ __forceinline__ bool elect_one() {

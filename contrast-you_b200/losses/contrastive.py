@@ -115,7 +115,7 @@ class _InfoNCEFunction(torch.autograd.Function):
 def tensor_core_eligible(z: Tensor, labels, codes, variant: int, path: int) -> bool:
     """mirror of the C-side dispatch (c_abi.cu resolve_path): does this call run on the tcgen05 kernels?"""
     N, d = z.shape
-    ok = (z.dtype == torch.bfloat16 and d == 256 and N % 128 == 0 and N >= 256 and codes is None and labels is not None
+    ok = (z.dtype in (torch.bfloat16, torch.float16) and d == 256 and N % 128 == 0 and N >= 256 and codes is None and labels is not None
           and variant == L.CY_SUPCON)
     return ok and (path == L.CY_PATH_TCGEN05 or (path == L.CY_PATH_AUTO and N >= 1024))
 

@@ -332,19 +332,20 @@ def test_iid_golden(name):
 
 
 # ------------------------------------------------------------------------------------------------ tcgen05 path
-def _tc_case(N, classes, seed):
+def _tc_case(N, classes, seed, dtype=torch.bfloat16):
     torch.manual_seed(seed)
     n = N // 2
-    z = torch.nn.functional.normalize(torch.randn(N, 256, device=DEV), dim=1).to(torch.bfloat16)
+    z = torch.nn.functional.normalize(torch.randn(N, 256, device=DEV), dim=1).to(dtype)
     lab = torch.randint(0, classes, (n,)) if classes else torch.arange(n)
     return z, lab, n
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("N,classes", [(256, 4), (1024, 16), (4096, 0), (8192, 512)])
-def test_tcgen05_matches_oracle_and_simt(N, classes):
+def test_tcgen05_matches_oracle_and_simt(N, classes, dtype):
     """bf16 inputs, d=256: TMA + tcgen05 kernels vs the float64 C oracle on the same bf16-rounded inputs (1e-2 bar of
     north_star for bf16) and vs the fp32 CUDA-core path (same inputs, tighter)."""
-    z, lab, n = _tc_case(N, classes, N)
+    z, lab, n = _tc_case(N, classes, N, dtype)
     out = {}
     for path in ("tcgen05", "simt"):
         f1, f2 = z[:n].clone().requires_grad_(), z[n:].clone().requires_grad_()
