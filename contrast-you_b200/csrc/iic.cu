@@ -542,6 +542,21 @@ int iic_joint_tma(const void* x, const void* y, int dtype, int B, int K, int H, 
 int iic_bwd_tma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
                 const float* gscale, void* dx, void* dy, cudaStream_t st);
 
+// iic_mma.cu (tensor-pipe path: bf16 hi/lo split mma.sync fed from TMA boxes; CY_ERR_UNSUPPORTED for shapes it does not take)
+int iic_joint_mma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, float* partials, int* n_partials,
+                  cudaStream_t st);
+int iic_bwd_mma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
+                const float* gscale, void* dx, void* dy, cudaStream_t st);
+
+static bool mma_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("CY_IIC_MMA");     // CY_IIC_MMA=0 pins the CUDA-core kernels (A/B measurements)
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
 static bool tma_enabled() {
     static int on = -1;
     if (on < 0) {
@@ -600,6 +615,16 @@ int iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int 
     CY_CHECK_ARG(workspace && workspace_bytes >= need, "iic_joint: workspace %zu < %zu", workspace_bytes, need);
     float* partials = reinterpret_cast<float*>(workspace);
     int rc;
+    if (mma_enabled()) {
+        int np = 0;
+        rc = iic_joint_mma(x, y, dtype, B, K, H, W, pad, partials, &np, st);
+        if (rc == CY_OK) {
+            iic_reduce_partials_kernel<<<(nj + 255) / 256, 256, 0, st>>>(partials, np, nj, joint);
+            CY_CHECK_LAUNCH("iic_reduce_partials");
+            return CY_OK;
+        }
+        if (rc != CY_ERR_UNSUPPORTED) return rc;
+    }
     if (tma_enabled()) {
         int np = 0;
         rc = iic_joint_tma(x, y, dtype, B, K, H, W, pad, partials, &np, st);
@@ -680,6 +705,10 @@ static int dispatch_bwd(int pad, int kc, const void* x, const void* y, int dtype
 int iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
             const float* gscale, void* dx, void* dy, cudaStream_t st) {
     const int T = 2 * pad + 1;
+    if (mma_enabled()) {
+        const int rc = iic_bwd_mma(x, y, dtype, B, K, H, W, pad, djoint, gscale, dx, dy, st);
+        if (rc != CY_ERR_UNSUPPORTED) return rc;
+    }
     if (tma_enabled()) {
         const int rc = iic_bwd_tma(x, y, dtype, B, K, H, W, pad, djoint, gscale, dx, dy, st);
         if (rc != CY_ERR_UNSUPPORTED) return rc;

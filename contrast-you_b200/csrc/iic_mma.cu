@@ -1,0 +1,592 @@
+// IIC joint / adjoint on the tensor pipe: warp-level mma.sync.m16n8k16 (bf16 hi/lo split, fp32 accumulate) fed from
+// TMA-staged fp32 halo boxes.  Reference: contrastyou/losses/discreteMI.py:225-243 (compute_joint_2D) and its autograd.
+//
+// Why mma.sync and not tcgen05 here: the contraction is tiny in M and N (K*T = 30 rows/columns at config 3) and huge in
+// the reduction dimension (pixels).  profiles/probes/probe_umma_small.cu measured a floor of ~45 cycles per tcgen05.mma
+// for M<=128, N<=64 tiles read from shared memory (operand fetch is bound by the 128 B/clk port, which the fp32->bf16
+// conversion pass would share), i.e. >= 2.8 clk/pixel/SM, against 3.0 clk/pixel/SM for the register-fed HMMA form below,
+// which needs no operand re-layout at all (shifted fragments are plain shared-memory loads).
+//
+// Precision: every fp32 value v is split as v = hi + lo, hi = bf16(v), lo = bf16(v - hi) (both round-to-nearest, so
+// the dropped lo*lo term is zero-mean); products use hi*hi + lo*hi + hi*lo: error <= 2^-16 relative per product,
+// fp32 accumulation — well inside the 1e-4 parity bar.
+//
+// Forward (iic_joint_mma_kernel):  J[k1,k2,dy,dx] = sum x[k1,h+dy-p,w'] * y[k2,h,w'-dx+p]   (w' = w+dx-p)
+//   D[(dx,k2) , (k1,dy)] += A[(dx,k2), pixel] * B[pixel, (k1,dy)]        A: shifted rows of y,  B: rows of x
+//   K*T = 30 combinations fill 30 of the 32 rows / columns of 2 x 4 MMA tiles (94 %).  The k index of one MMA covers 16
+//   consecutive pixels of one image row; k-slot (2q, 2q+1, 2q+8, 2q+9) of lane quad q holds pixels (q, q+4, q+8, q+12),
+//   so every fragment element is one conflict-free LDS.32 and a displacement is an address offset.
+// Backward (iic_bwd_mma_kernel):   out[o,h,w] = sum_{c,dy,dx} Wt[o,c,dy,dx] * in[c,h+dy-p,w+dx-p]
+//   D[o (16), pixel (8)] += Wt[o, (c,dy,dx)] * col[(c,dy,dx), pixel];  the weights (dL/dJ, scaled; flipped for dL/dx)
+//   stay in registers as pre-split A fragments for the whole kernel, half of the warps produce dL/dy from the x box and
+//   half dL/dx from the y box.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cy {
+
+using namespace tc;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encode_fn();
+
+namespace {
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// first MMA of a chain: C = 0
+__device__ __forceinline__ void mma_bf16_16816_z(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.f));
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// (v0, v1) -> packed bf16 pairs (v0 in the low half): hi = rn(v), lo = rn(v - hi); v - hi is exact in fp32
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
+    const float r0 = v0 - __uint_as_float(hi << 16);
+    const float r1 = v1 - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+
+struct MmaGeom {
+    int B, K, H, W, pad, T;
+    int TH, TW;              // tile: TH image rows x TW columns
+    int HH;                  // TH + 2 * pad
+    int XW;                  // forward: x box pitch (TW + 4);  backward: pitch of both boxes
+    int YW, CO;              // forward: y box pitch (TW + 12), first column = w0 - CO; backward: CO of both boxes
+    int tiles_h, tiles_w, n_tiles;
+    int x_stage_floats, y_stage_floats;
+    int n_combo;             // K * T
+    int stages;
+};
+
+// ring of `n` stages with a runtime depth (the depth is chosen on the host from the shared-memory budget)
+struct RingN {
+    uint32_t s = 0, ph = 0;
+    __device__ __forceinline__ uint32_t stage() const { return s; }
+    __device__ __forceinline__ uint32_t phase() const { return ph; }
+    __device__ __forceinline__ void next(uint32_t n) {
+        if (++s == n) { s = 0; ph ^= 1u; }
+    }
+};
+constexpr int MAX_STAGES = 4;
+
+// ------------------------------------------------------------------------------------------------------ forward
+// MT m-tiles (16 rows of (dx,k2) each), NT n-tiles (8 columns of (k1,dy)) split over NSPLIT warps per pixel row, NCH chunks
+// of 16 pixels per tile row.  The HMMA accumulator truncates on every add, so a chain is kept to the 3 split terms of
+// one 16-pixel step (the first MMA takes C = 0) and the result is added to the running sums with round-to-nearest FADDs:
+// the joint then carries no bias that grows with the number of pixels (needed for the padding = 0 loss, whose value is
+// a 1e-3 residual of O(1) terms).
+template <int MT, int NTW, int NSPLIT, int NCH>
+__global__ void __launch_bounds__((9 * NSPLIT + 1) * 32, NSPLIT == 1 ? 2 : 1)
+iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, MmaGeom g,
+                     float* __restrict__ partials) {
+    constexpr int NCW = 9 * NSPLIT;
+    constexpr int THREADS = (NCW + 1) * 32;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    float* stage0 = reinterpret_cast<float*>(smem);
+    const int stage_floats = g.x_stage_floats + g.y_stage_floats;
+    const int K = g.K, T = g.T;
+    const int nj = K * K * T * T;
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + (size_t)g.stages * stage_floats);
+    uint64_t* empty = full + MAX_STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < g.stages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NCW); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const uint32_t stage_bytes = (uint32_t)(K * g.HH * g.XW + K * g.TH * g.YW) * 4u;
+    float acc[MT][NTW][4];
+#pragma unroll
+    for (int a = 0; a < MT; ++a)
+#pragma unroll
+        for (int b2 = 0; b2 < NTW; ++b2)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][b2][c] = 0.f;
+    const int gq = lane >> 2, q = lane & 3;          // fragment row / column group, k-slot quad
+    const int split = warp % NSPLIT;
+
+    if (warp == NCW) {
+        if (elect_one()) {
+            prefetch_tmap(&tmx);
+            prefetch_tmap(&tmy);
+            RingN ring;
+            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ring.next(g.stages)) {
+                const int b = tile / (g.tiles_h * g.tiles_w);
+                const int trem = tile % (g.tiles_h * g.tiles_w);
+                const int h0 = (trem / g.tiles_w) * g.TH, w0 = (trem % g.tiles_w) * g.TW;
+                const uint32_t s = ring.stage();
+                mbar_wait(empty + s, ring.phase() ^ 1u);
+                mbar_arrive_expect_tx(full + s, stage_bytes);
+                float* xs = stage0 + (size_t)s * stage_floats;
+                tma_load_3d(xs, &tmx, full + s, w0, h0 - g.pad, b * K);
+                tma_load_3d(xs + g.x_stage_floats, &tmy, full + s, w0 - g.CO, h0, b * K);
+            }
+        }
+    } else {
+        const int row = warp / NSPLIT;
+        // shared-memory byte offsets (relative to the stage) of this lane's fragment rows; combinations past K*T read
+        // in-bounds garbage whose accumulator rows / columns are never written out
+        const int limit = stage_floats - 16 * NCH - 16;
+        uint32_t xoff[NTW], yoff[MT][2];
+#pragma unroll
+        for (int tn = 0; tn < NTW; ++tn) {
+            const int cb = 8 * (split * NTW + tn) + gq;               // (k1, dy) = (cb / T, cb % T)
+            const int o = ((cb / T) * g.HH + row + (cb % T)) * g.XW + q;
+            xoff[tn] = 4u * (uint32_t)((cb < g.n_combo || o < limit) ? o : limit);
+        }
+#pragma unroll
+        for (int tm = 0; tm < MT; ++tm)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int ca = 16 * tm + 8 * hf + gq;                 // (dx, k2) = (ca / K, ca % K)
+                int o = g.x_stage_floats + ((ca % K) * g.TH + row) * g.YW + q + g.CO + g.pad - (ca / K);
+                if (ca >= g.n_combo) o = o < limit ? (o < 0 ? 0 : o) : limit;
+                yoff[tm][hf] = 4u * (uint32_t)o;
+            }
+        const uint32_t stage0_addr = smem_u32(stage0);
+        const uint32_t stage_stride = (uint32_t)stage_floats * 4u;
+
+        RingN ring;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ring.next(g.stages)) {
+            const uint32_t s = ring.stage();
+            mbar_wait(full + s, ring.phase());
+            const uint32_t sb = stage0_addr + s * stage_stride;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                uint32_t bh[NTW][2], bl[NTW][2];
+#pragma unroll
+                for (int tn = 0; tn < NTW; ++tn) {
+                    const uint32_t p = sb + xoff[tn] + ch * 64;
+                    const float v0 = lds_f32(p), v1 = lds_f32(p + 16), v2 = lds_f32(p + 32), v3 = lds_f32(p + 48);
+                    split_pair(v0, v1, bh[tn][0], bl[tn][0]);
+                    split_pair(v2, v3, bh[tn][1], bl[tn][1]);
+                }
+#pragma unroll
+                for (int tm = 0; tm < MT; ++tm) {
+                    const uint32_t p0 = sb + yoff[tm][0] + ch * 64, p1 = sb + yoff[tm][1] + ch * 64;
+                    const float a0 = lds_f32(p0), a1 = lds_f32(p0 + 16), a2 = lds_f32(p0 + 32), a3 = lds_f32(p0 + 48);
+                    const float c0 = lds_f32(p1), c1 = lds_f32(p1 + 16), c2 = lds_f32(p1 + 32), c3 = lds_f32(p1 + 48);
+                    uint32_t ah[4], al[4];
+                    split_pair(a0, a1, ah[0], al[0]);
+                    split_pair(c0, c1, ah[1], al[1]);
+                    split_pair(a2, a3, ah[2], al[2]);
+                    split_pair(c2, c3, ah[3], al[3]);
+                    float d[NTW][4];
+#pragma unroll
+                    for (int tn = 0; tn < NTW; ++tn) mma_bf16_16816_z(d[tn], ah, bh[tn]);
+#pragma unroll
+                    for (int tn = 0; tn < NTW; ++tn) mma_bf16_16816(d[tn], al, bh[tn]);
+#pragma unroll
+                    for (int tn = 0; tn < NTW; ++tn) mma_bf16_16816(d[tn], ah, bl[tn]);
+#pragma unroll
+                    for (int tn = 0; tn < NTW; ++tn)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[tm][tn][c] += d[tn][c];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+        }
+    }
+    // per-CTA reduction over the compute warps through shared memory (the ring is idle now), in a fixed order
+    __syncthreads();
+    constexpr int NV = MT * NTW * 4;                 // accumulator values per lane
+    float* red = stage0;                             // [NCW][NV][32]
+    if (warp < NCW) {
+#pragma unroll
+        for (int tm = 0; tm < MT; ++tm)
+#pragma unroll
+            for (int tn = 0; tn < NTW; ++tn)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) red[(warp * NV + (tm * NTW + tn) * 4 + c) * 32 + lane] = acc[tm][tn][c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nj; i += THREADS) partials[(size_t)blockIdx.x * nj + i] = 0.f;
+    __syncthreads();
+    for (int e = threadIdx.x; e < NSPLIT * NV * 32; e += THREADS) {
+        const int sp = e / (NV * 32), v = (e / 32) % NV, ln = e % 32;
+        float sum = 0.f;
+        for (int r = 0; r < 9; ++r) sum += red[((r * NSPLIT + sp) * NV + v) * 32 + ln];
+        const int c = v & 3, tn = (v >> 2) % NTW, tm = (v >> 2) / NTW;
+        const int ca = 16 * tm + (ln >> 2) + (c >> 1) * 8;
+        const int cb = 8 * (sp * NTW + tn) + 2 * (ln & 3) + (c & 1);
+        if (ca < g.n_combo && cb < g.n_combo) {
+            const int dx = ca / K, k2 = ca % K, k1 = cb / T, dy = cb % T;
+            partials[(size_t)blockIdx.x * nj + ((k1 * K + k2) * T + dy) * T + dx] = sum;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------ backward
+// padding = 1, K <= 10.  One warp walks an 8-pixel column strip of the box row by row.  For box row r' the B operand
+// col[(c,dx), pixel] = in[c, r', pixel + dx - 1] (K*3 <= 30 of 32 k-slots, 2 k-steps) is loaded and split ONCE and
+// multiplied by all (dy, o) weight rows at once (K*3 <= 30 of 32 rows, 2 m-tiles): D[(dy,o), pixel] is this row's
+// contribution to output row r' - dy.  Row slots 0..2 of the two m-tiles hold (dy = slot, o = lane group) for o < 8,
+// so the three rows that make up one output row meet in the same thread (rolling accumulators, plain FADDs); slot 3
+// holds the 3 x (K - 8) remaining (dy, o >= 8) rows, whose partial sums meet through two warp shuffles.
+// The weights (dL/dJ * gscale; flipped for dL/dx) stay in registers as pre-split A fragments for the whole kernel; half
+// of the warps produce dL/dy from the x box and half dL/dx from the y box.
+constexpr int BW_WARPS_PER_GROUP = 4;
+constexpr int BW_THREADS = (2 * BW_WARPS_PER_GROUP + 1) * 32;
+
+template <int TWV>
+__global__ void __launch_bounds__(BW_THREADS, 2)
+iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, MmaGeom g,
+                   const float* __restrict__ djoint, const float* __restrict__ gscale, float* __restrict__ dx_out,
+                   float* __restrict__ dy_out) {
+    constexpr int T = 3, TH = 9, HH = TH + 2, XW = TWV + 8, NSTRIP = TWV / 8, CO = 4;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    float* stage0 = reinterpret_cast<float*>(smem);
+    const int K = g.K, KX = K > 8 ? K - 8 : 0;
+    const int stage_floats = 2 * g.x_stage_floats;
+    float* wtab = stage0 + (size_t)g.stages * stage_floats;          // [2][K][K][T][T] scaled weights
+    const int nj = K * K * T * T;
+    uint64_t* full = reinterpret_cast<uint64_t*>(wtab + ((2 * nj + 31) & ~31));
+    uint64_t* empty = full + MAX_STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NCW = 2 * BW_WARPS_PER_GROUP;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < g.stages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NCW); }
+        fence_barrier_init();
+    }
+    const float scale = gscale[0];
+    for (int i = threadIdx.x; i < nj; i += BW_THREADS) {
+        // group 0 (dL/dy from x): Wt[o=k2][c=k1][dy][dx] = G[k1,k2,dy,dx]
+        // group 1 (dL/dx from y): Wt[o=k1][c=k2][dy][dx] = G[k1,k2,T-1-dy,T-1-dx]
+        const int dxx = i % T, dyy = (i / T) % T, c = (i / (T * T)) % K, o = i / (T * T * K);
+        wtab[i] = djoint[((c * K + o) * T + dyy) * T + dxx] * scale;
+        wtab[nj + i] = djoint[((o * K + c) * T + (T - 1 - dyy)) * T + (T - 1 - dxx)] * scale;
+    }
+    __syncthreads();
+
+    const uint32_t box_bytes = (uint32_t)(K * HH * XW) * 4u;
+    if (warp == NCW) {
+        if (elect_one()) {
+            prefetch_tmap(&tmx);
+            prefetch_tmap(&tmy);
+            RingN ring;
+            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ring.next(g.stages)) {
+                const int b = tile / (g.tiles_h * g.tiles_w);
+                const int trem = tile % (g.tiles_h * g.tiles_w);
+                const int h0 = (trem / g.tiles_w) * TH, w0 = (trem % g.tiles_w) * TWV;
+                const uint32_t s = ring.stage();
+                mbar_wait(empty + s, ring.phase() ^ 1u);
+                mbar_arrive_expect_tx(full + s, 2 * box_bytes);
+                float* xs = stage0 + (size_t)s * stage_floats;
+                tma_load_3d(xs, &tmx, full + s, w0 - CO, h0 - 1, b * K);
+                tma_load_3d(xs + g.x_stage_floats, &tmy, full + s, w0 - CO, h0 - 1, b * K);
+            }
+        }
+    } else {
+        const int gq = lane >> 2, q = lane & 3;
+        const int group = warp / BW_WARPS_PER_GROUP, wq = warp % BW_WARPS_PER_GROUP;
+        const float* wt = wtab + group * nj;
+        float* out = group ? dx_out : dy_out;
+        // A fragments.  Row of m-tile tm, half hf: slot = 2*tm + hf; slot < 3: (dy = slot, o = gq); slot 3: (dy, o) =
+        // (gq / KX, 8 + gq % KX).  k-slot pairs of k-step ks <-> this lane quad's own elements e = 4*ks + {0,1 | 2,3},
+        // element e <-> K-row R = q + 4*e = c * 3 + dx.
+        const int dy3 = KX ? gq / KX : 3;                 // >= 3: this lane's slot-3 row is unused
+        uint32_t ah[2][2][4], al[2][2][4];
+#pragma unroll
+        for (int tm = 0; tm < 2; ++tm)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                float w[2][4];
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int slot = 2 * tm + hf;
+                    const int dyy = slot < 3 ? slot : dy3;
+                    const int o = slot < 3 ? gq : 8 + (KX ? gq % KX : 0);
+                    const bool rv = dyy < 3 && o < K;
+#pragma unroll
+                    for (int e4 = 0; e4 < 4; ++e4) {
+                        const int R = q + 4 * (4 * ks + e4);
+                        const int c = R / 3, dxx = R % 3;
+                        w[hf][e4] = (rv && c < K) ? wt[((o * K + c) * T + dyy) * T + dxx] : 0.f;
+                    }
+                }
+                split_pair(w[0][0], w[0][1], ah[tm][ks][0], al[tm][ks][0]);
+                split_pair(w[1][0], w[1][1], ah[tm][ks][1], al[tm][ks][1]);
+                split_pair(w[0][2], w[0][3], ah[tm][ks][2], al[tm][ks][2]);
+                split_pair(w[1][2], w[1][3], ah[tm][ks][3], al[tm][ks][3]);
+            }
+        // byte offsets (within a box) of this lane's 8 K-rows at box row 0, strip 0; rows past K*3 carry zero weights and
+        // re-read row 0 (finite data)
+        uint32_t roff[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int R = q + 4 * j;
+            if (R >= K * 3) R = 0;
+            roff[j] = 4u * (uint32_t)((R / 3) * HH * XW + (R % 3) + gq + CO - 1);
+        }
+        const uint32_t stage0_addr = smem_u32(stage0);
+        RingN ring;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ring.next(g.stages)) {
+            const int b = tile / (g.tiles_h * g.tiles_w);
+            const int trem = tile % (g.tiles_h * g.tiles_w);
+            const int h0 = (trem / g.tiles_w) * TH, w0 = (trem % g.tiles_w) * TWV;
+            const uint32_t s = ring.stage();
+            mbar_wait(full + s, ring.phase());
+            const uint32_t box = stage0_addr + 4u * (uint32_t)(s * stage_floats + group * g.x_stage_floats);
+#pragma unroll 1
+            for (int strip = wq; strip < NSTRIP; strip += BW_WARPS_PER_GROUP) {
+                const uint32_t sbase = box + strip * 32;
+                const int w = w0 + 8 * strip + 2 * q;
+                float* orow = out + (((size_t)b * K + gq) * g.H + h0) * g.W + w;       // (o = gq, row h0)
+                const size_t ostride8 = (size_t)8 * g.H * g.W;
+                float accA[3][2], acc3[3][2];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) accA[i][0] = accA[i][1] = acc3[i][0] = acc3[i][1] = 0.f;
+#pragma unroll
+                for (int rp = 0; rp < HH; ++rp) {
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = lds_f32(sbase + roff[j] + rp * XW * 4);
+                    uint32_t bh[2][2], bl[2][2];
+                    split_pair(v[0], v[1], bh[0][0], bl[0][0]);
+                    split_pair(v[2], v[3], bh[0][1], bl[0][1]);
+                    split_pair(v[4], v[5], bh[1][0], bl[1][0]);
+                    split_pair(v[6], v[7], bh[1][1], bl[1][1]);
+                    float d[2][4];
+#pragma unroll
+                    for (int tm = 0; tm < 2; ++tm) mma_bf16_16816_z(d[tm], ah[tm][0], bh[0]);
+#pragma unroll
+                    for (int tm = 0; tm < 2; ++tm) mma_bf16_16816(d[tm], al[tm][0], bh[0]);
+#pragma unroll
+                    for (int tm = 0; tm < 2; ++tm) mma_bf16_16816(d[tm], ah[tm][0], bl[0]);
+#pragma unroll
+                    for (int tm = 0; tm < 2; ++tm) mma_bf16_16816(d[tm], ah[tm][1], bh[1]);
+#pragma unroll
+                    for (int tm = 0; tm < 2; ++tm) mma_bf16_16816(d[tm], al[tm][1], bh[1]);
+#pragma unroll
+                    for (int tm = 0; tm < 2; ++tm) mma_bf16_16816(d[tm], ah[tm][1], bl[1]);
+                    // slot s (rows 8*s .. 8*s+7 of the 32) = d[s / 2][2 * (s % 2) + {0, 1}]
+#pragma unroll
+                    for (int dyy = 0; dyy < 3; ++dyy) {
+                        const int r = rp - dyy;                       // output row fed by (box row rp, dy)
+                        if (r >= 0 && r < TH) {
+                            accA[r % 3][0] += d[dyy / 2][2 * (dyy % 2)];
+                            accA[r % 3][1] += d[dyy / 2][2 * (dyy % 2) + 1];
+                            if (dy3 == dyy) { acc3[r % 3][0] += d[1][2]; acc3[r % 3][1] += d[1][3]; }
+                        }
+                    }
+                    const int rc = rp - 2;                            // output row completed by this box row
+                    if (rc >= 0) {
+                        float t0 = acc3[rc % 3][0], t1 = acc3[rc % 3][1];
+                        if (KX) {                                     // rows (dy, o) of one o sit KX lane groups apart
+                            t0 += __shfl_down_sync(0xffffffffu, t0, 4 * KX) + __shfl_down_sync(0xffffffffu, t0, 8 * KX);
+                            t1 += __shfl_down_sync(0xffffffffu, t1, 4 * KX) + __shfl_down_sync(0xffffffffu, t1, 8 * KX);
+                        }
+                        if (h0 + rc < g.H && w < g.W) {   // W % 4 == 0 and w even: the pixel pair is inside the row together
+                            if (gq < K) *reinterpret_cast<float2*>(orow + (size_t)rc * g.W) = make_float2(accA[rc % 3][0], accA[rc % 3][1]);
+                            if (gq < KX) *reinterpret_cast<float2*>(orow + ostride8 + (size_t)rc * g.W) = make_float2(t0, t1);
+                        }
+                        accA[rc % 3][0] = accA[rc % 3][1] = acc3[rc % 3][0] = acc3[rc % 3][1] = 0.f;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+        }
+    }
+}
+
+int make_map3d(CUtensorMap* m, const void* base, int B, int K, int H, int W, int box_w, int box_h) {
+    EncodeTiledFn fn = tensor_map_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CY_ERR_DEVICE; }
+    cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)K * (cuuint64_t)B};
+    cuuint64_t gstride[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)K};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3d) failed (%d)", (int)r); return CY_ERR_ARG; }
+    return CY_OK;
+}
+
+int sm_count_mma() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// tile width: 32 or 64 columns, whichever wastes fewer columns on the ragged edge (ties -> 64: fewer barrier rounds)
+int pick_tw(int W) {
+    const int w32 = (W + 31) / 32 * 32, w64 = (W + 63) / 64 * 64;
+    return w64 <= w32 ? 64 : 32;
+}
+
+bool fwd_geom(int B, int K, int H, int W, int pad, MmaGeom* g, int* mt, int* ntw, int* nsplit, size_t* smem) {
+    const int T = 2 * pad + 1;
+    // padding = 0 stays on the fp32 CUDA-core kernels: its loss is a ~1e-3 residual of O(1) terms, so the joint needs
+    // full fp32 products (the bf16 hi/lo split is good to ~1e-6 only), and at K*K MACs per pixel it is HBM-bound there
+    if (pad < 1 || pad > 3 || (W % 4) != 0 || K > 256) return false;
+    const int nc = K * T;
+    *mt = (nc + 15) / 16;
+    const int nt = (nc + 7) / 8;
+    if (*mt > 4) return false;
+    if (*mt * nt <= 8) { *nsplit = 1; *ntw = nt; }
+    else if (*mt * ((nt + 1) / 2) <= 16) { *nsplit = 2; *ntw = (nt + 1) / 2; }
+    else return false;
+    g->B = B; g->K = K; g->H = H; g->W = W; g->pad = pad; g->T = T;
+    g->TH = 9;                        // HH = 9 + 2p == T (mod 8): fragment rows (k1, dy) land on distinct bank groups
+    g->HH = g->TH + 2 * pad;
+    g->CO = 4;
+    g->n_combo = nc;
+    const int nj = K * K * T * T;
+    const size_t budget = (*nsplit == 1) ? 113 * 1024 : 225 * 1024;
+    // widest tile (fewest barrier rounds) that does not waste columns and still leaves a 2-deep ring
+    const int first = pick_tw(W);
+    for (int tw = first; tw >= 32; tw -= 32) {
+        g->TW = tw;
+        g->XW = tw + 4;               // == 4 (mod 32)
+        g->YW = tw + 12;              // (YW / 4) odd: the K planes of one row start on distinct bank groups
+        g->tiles_h = (H + g->TH - 1) / g->TH;
+        g->tiles_w = (W + tw - 1) / tw;
+        g->n_tiles = B * g->tiles_h * g->tiles_w;
+        g->x_stage_floats = (K * g->HH * g->XW + 31) & ~31;
+        g->y_stage_floats = (K * g->TH * g->YW + 31) & ~31;
+        for (int st = MAX_STAGES - 1; st >= 2; --st) {
+            *smem = (size_t)st * (g->x_stage_floats + g->y_stage_floats) * 4 + 2 * MAX_STAGES * 8 + 128 + 64;
+            const size_t red = (size_t)9 * *nsplit * *mt * *ntw * 4 * 32 * 4;      // epilogue reduction buffer reuses the ring
+            if (*smem <= budget && (size_t)st * (g->x_stage_floats + g->y_stage_floats) * 4 >= red) { g->stages = st; return true; }
+        }
+    }
+    return false;
+}
+
+template <int MT, int NTW, int NSPLIT, int NCH>
+int launch_joint_mma(const CUtensorMap& tmx, const CUtensorMap& tmy, const MmaGeom& g, size_t smem, int grid, float* partials,
+                     cudaStream_t st) {
+    auto k = iic_joint_mma_kernel<MT, NTW, NSPLIT, NCH>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("iic_joint_mma smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
+    k<<<grid, (9 * NSPLIT + 1) * 32, smem, st>>>(tmx, tmy, g, partials);
+    CY_CHECK_LAUNCH("iic_joint_mma");
+    return CY_OK;
+}
+
+}  // namespace
+
+// returns CY_ERR_UNSUPPORTED when the shape is not eligible (the caller then takes the CUDA-core kernels)
+int iic_joint_mma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, float* partials, int* n_partials,
+                  cudaStream_t st) {
+    MmaGeom g; int mt, ntw, nsplit; size_t smem;
+    if (dtype != CY_F32 || !aligned16(x) || !aligned16(y) || !fwd_geom(B, K, H, W, pad, &g, &mt, &ntw, &nsplit, &smem))
+        return CY_ERR_UNSUPPORTED;
+    CUtensorMap tmx, tmy;
+    int rc = make_map3d(&tmx, x, B, K, H, W, g.XW, g.HH);
+    if (rc) return rc;
+    rc = make_map3d(&tmy, y, B, K, H, W, g.YW, g.TH);
+    if (rc) return rc;
+    const int cap = sm_count_mma() * (nsplit == 1 ? 2 : 1);
+    const int grid = g.n_tiles < cap ? g.n_tiles : cap;
+    *n_partials = grid;
+#define CY_JM(MTV, NTWV, NSV)                                                                                     \
+    if (mt == MTV && ntw == NTWV && nsplit == NSV) {                                                              \
+        if (g.TW == 32) return launch_joint_mma<MTV, NTWV, NSV, 2>(tmx, tmy, g, smem, grid, partials, st);       \
+        if (g.TW == 64) return launch_joint_mma<MTV, NTWV, NSV, 4>(tmx, tmy, g, smem, grid, partials, st);       \
+    }
+    CY_JM(1, 1, 1) CY_JM(1, 2, 1) CY_JM(2, 3, 1) CY_JM(2, 4, 1) CY_JM(3, 3, 2) CY_JM(4, 4, 2)
+#undef CY_JM
+    return CY_ERR_UNSUPPORTED;
+}
+
+int iic_joint_mma_max_partials() { return 2 * sm_count_mma(); }
+
+namespace {
+
+template <int TWV>
+int launch_bwd_mma(const CUtensorMap& tmx, const CUtensorMap& tmy, const MmaGeom& g, size_t smem, int grid, const float* djoint,
+                   const float* gscale, float* dx, float* dy, cudaStream_t st) {
+    auto k = iic_bwd_mma_kernel<TWV>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("iic_bwd_mma smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
+    k<<<grid, BW_THREADS, smem, st>>>(tmx, tmy, g, djoint, gscale, dx, dy);
+    CY_CHECK_LAUNCH("iic_bwd_mma");
+    return CY_OK;
+}
+
+}  // namespace
+
+int iic_bwd_mma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
+                const float* gscale, void* dx, void* dy, cudaStream_t st) {
+    if (dtype != CY_F32 || pad != 1 || (W % 4) != 0 || K > 10 || !aligned16(x) || !aligned16(y) || !aligned16(dx) || !aligned16(dy))
+        return CY_ERR_UNSUPPORTED;
+    const int T = 3;
+    MmaGeom g;
+    g.B = B; g.K = K; g.H = H; g.W = W; g.pad = pad; g.T = T;
+    g.TH = 9;
+    g.HH = g.TH + 2;
+    g.CO = 4;
+    g.n_combo = K * T;
+    const int nj = K * K * T * T;
+    size_t smem = 0;
+    bool ok = false;
+    for (int tw = pick_tw(W); tw >= 32 && !ok; tw -= 32) {
+        g.TW = tw;
+        g.XW = tw + 8;                  // == 8 (mod 32) and HH * XW == 24 (mod 32): the 4 K-rows of a load hit disjoint banks
+        g.YW = g.XW;
+        g.tiles_h = (H + g.TH - 1) / g.TH;
+        g.tiles_w = (W + tw - 1) / tw;
+        g.n_tiles = B * g.tiles_h * g.tiles_w;
+        g.x_stage_floats = (K * g.HH * g.XW + 31) & ~31;
+        g.y_stage_floats = g.x_stage_floats;
+        for (int stg = MAX_STAGES - 1; stg >= 2 && !ok; --stg) {
+            smem = ((size_t)stg * 2 * g.x_stage_floats + ((2 * nj + 31) & ~31)) * 4 + 2 * MAX_STAGES * 8 + 128 + 64;
+            if (smem <= 113 * 1024) { g.stages = stg; ok = true; }
+        }
+    }
+    if (!ok) return CY_ERR_UNSUPPORTED;
+    CUtensorMap tmx, tmy;
+    int rc = make_map3d(&tmx, x, B, K, H, W, g.XW, g.HH);
+    if (rc) return rc;
+    rc = make_map3d(&tmy, y, B, K, H, W, g.XW, g.HH);
+    if (rc) return rc;
+    const int cap = 2 * sm_count_mma();
+    const int grid = g.n_tiles < cap ? g.n_tiles : cap;
+    float* dxf = reinterpret_cast<float*>(dx);
+    float* dyf = reinterpret_cast<float*>(dy);
+    if (g.TW == 32) return launch_bwd_mma<32>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
+    if (g.TW == 64) return launch_bwd_mma<64>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
+    return CY_ERR_UNSUPPORTED;
+}
+
+}  // namespace cy

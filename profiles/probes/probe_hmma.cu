@@ -1,0 +1,65 @@
+// Probe: legacy warp-level mma.sync (HMMA) bf16 m16n8k16 throughput per SM on sm_100a, as a function of resident warps.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o probe_hmma probe_hmma.cu ; run: ./probe_hmma
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int NACC>
+__global__ void hmma_loop(float* out, int iters, long long* cycles) {
+    float acc[NACC][4];
+    uint32_t a[4], b[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = 0x3f803f80u + threadIdx.x + i;
+    b[0] = 0x3f803f80u + threadIdx.x;
+    b[1] = 0x3f803f80u - threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < NACC; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) mma_bf16(acc[j], a, b);
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) s += acc[j][0] + acc[j][1] + acc[j][2] + acc[j][3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+int main() {
+    float* out;
+    long long* cyc;
+    cudaMalloc(&out, 148 * 1024 * 4 * 4);
+    cudaMalloc(&cyc, 148 * 8 * 8);
+    const int iters = 4096;
+    const int NACC = 12;
+    for (int warps = 4; warps <= 32; warps *= 2) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        hmma_loop<NACC><<<148, warps * 32>>>(out, 16, cyc);
+        cudaEventRecord(e0);
+        hmma_loop<NACC><<<148, warps * 32>>>(out, iters, cyc);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaDeviceSynchronize();
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        long long c;
+        cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+        const double macs = (double)warps * iters * NACC * 16 * 8 * 16;
+        printf("warps/SM %2d: %s  %.3f ms  cycles %lld  -> %.1f MAC/clk/SM  (%.1f TFLOP/s chip)\n", warps, cudaGetErrorString(e), ms, c,
+               macs / (double)c, 2.0 * macs * 148 / (ms * 1e-3) / 1e12);
+    }
+    return 0;
+}
