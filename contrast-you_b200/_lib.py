@@ -88,8 +88,11 @@ def require_cuda(*tensors):
                                f"got a tensor on {t.device}")
 
 
-def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def stream_ptr(device=None) -> int:
+    """Raw cudaStream_t of torch's current stream (the kernels must launch there: SURVEY.md §8b).  Goes through the C
+    accessor: ``torch.cuda.current_stream()`` builds a Python Stream object and costs ~20 us per call."""
+    idx = torch.cuda.current_device() if device is None or device.index is None else device.index
+    return torch._C._cuda_getCurrentRawStream(idx)
 
 
 def ptr(t):

@@ -176,14 +176,26 @@ iic_joint_generic_kernel(const void* __restrict__ x, const void* __restrict__ y,
 // ---------------------------------------------------------------------------------------------- epilogue
 // One CTA.  Sums the per-CTA partial joints in a fixed order (fp64), then discreteMI.py:233-243 / :246-261 and
 // :154-165, and the analytic dLoss/dJoint.  All in fp64: 900 elements.
-__global__ void __launch_bounds__(256)
+// block = 32 joint entries (lanes) x 32 warps striding over the partials; fixed summation order: deterministic
+constexpr int RED_WARPS = 32;
+__global__ void __launch_bounds__(32 * RED_WARPS)
 iic_reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int nj, float* __restrict__ joint) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nj) return;
+    __shared__ double acc[RED_WARPS][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
     double s = 0.0;
-    for (int p = 0; p < n_partials; ++p) s += (double)partials[(size_t)p * nj + i];
-    joint[i] = (float)s;
+    if (i < nj)
+        for (int p = w; p < n_partials; p += RED_WARPS) s += (double)partials[(size_t)p * nj + i];
+    acc[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && i < nj) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < RED_WARPS; ++k) t += acc[k][lane];
+        joint[i] = (float)t;
+    }
 }
+static inline int reduce_grid(int nj) { return (nj + 31) / 32; }
 
 __device__ double block_reduce_sum(double v, double* red) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -195,6 +207,15 @@ __device__ double block_reduce_sum(double v, double* red) {
     double t = 0.0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
     return t;
+}
+
+// sum of v[0..n) by one warp (fixed order per lane, then a butterfly): every lane returns the total
+__device__ __forceinline__ double warp_sum_n(const double* v, int n, int lane) {
+    double s = 0.0;
+    for (int e = lane; e < n; e += 32) s += v[e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
 }
 
 __device__ double block_reduce_min(double v, double* red) {
@@ -210,13 +231,15 @@ __device__ double block_reduce_min(double v, double* red) {
 }
 
 // dynamic smem: double A[nj] (B matrix, [dd][k1][k2]), P[nj], G[nj], sdisp[TT], colsum[TT*K], rowsum[TT*K]
-__global__ void __launch_bounds__(256)
+constexpr int EPI_THREADS = 1024;
+__global__ void __launch_bounds__(EPI_THREADS)
 iic_epilogue_kernel(const float* __restrict__ joint, int K, int pad, int symmetric, double lamda, double eps,
                     double n_pixels, float* __restrict__ loss, float* __restrict__ p00, float* __restrict__ p_ij,
                     float* __restrict__ djoint, double* __restrict__ gscratch) {
     extern __shared__ __align__(16) double sm[];
-    __shared__ double red[8];
+    __shared__ double red[32];
     const int T = 2 * pad + 1, TT = T * T, KK = K * K, nj = KK * TT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     double* Bm = gscratch ? gscratch : sm;      // large K / padding: the arrays live in the caller's workspace
     double* P = Bm + nj;
     double* G = P + nj;
@@ -238,10 +261,9 @@ iic_epilogue_kernel(const float* __restrict__ joint, int K, int pad, int symmetr
             Bm[PIDX(dd, k1, k2)] = (double)joint[i] - mn + 1e-8;
         }
         __syncthreads();
-        for (int dd = tid; dd < TT; dd += nt) {
-            double s = 0.0;
-            for (int e = 0; e < KK; ++e) s += Bm[dd * KK + e];
-            sd[dd] = s;
+        for (int dd = warp; dd < TT; dd += nwarp) {          // one warp per displacement
+            const double s = warp_sum_n(Bm + dd * KK, KK, lane);
+            if (lane == 0) sd[dd] = s;
         }
         __syncthreads();
         for (int i = tid; i < nj; i += nt) Bm[i] /= sd[i / KK];
@@ -296,14 +318,16 @@ iic_epilogue_kernel(const float* __restrict__ joint, int K, int pad, int symmetr
         for (int i = tid; i < nj; i += nt) G[i] = (G[i] - gdotP) / total;
         __syncthreads();
         // per displacement: dot = sum gB * B
-        for (int dd = tid; dd < TT; dd += nt) {
+        for (int dd = warp; dd < TT; dd += nwarp) {          // one warp per displacement
             double dot = 0.0;
-            for (int k1 = 0; k1 < K; ++k1)
-                for (int k2 = 0; k2 < K; ++k2) {
-                    const double gb = symmetric ? 0.5 * (G[PIDX(dd, k1, k2)] + G[PIDX(dd, k2, k1)]) : G[PIDX(dd, k1, k2)];
-                    dot += gb * Bm[PIDX(dd, k1, k2)];
-                }
-            asum[dd] = dot;   // reuse
+            for (int e = lane; e < KK; e += 32) {
+                const int k1 = e / K, k2 = e % K;
+                const double gb = symmetric ? 0.5 * (G[PIDX(dd, k1, k2)] + G[PIDX(dd, k2, k1)]) : G[PIDX(dd, k1, k2)];
+                dot += gb * Bm[PIDX(dd, k1, k2)];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            if (lane == 0) asum[dd] = dot;   // reuse
         }
         __syncthreads();
         for (int i = tid; i < nj; i += nt) {
@@ -619,7 +643,7 @@ int iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int 
         int np = 0;
         rc = iic_joint_mma(x, y, dtype, B, K, H, W, pad, partials, &np, st);
         if (rc == CY_OK) {
-            iic_reduce_partials_kernel<<<(nj + 255) / 256, 256, 0, st>>>(partials, np, nj, joint);
+            iic_reduce_partials_kernel<<<reduce_grid(nj), 32 * RED_WARPS, 0, st>>>(partials, np, nj, joint);
             CY_CHECK_LAUNCH("iic_reduce_partials");
             return CY_OK;
         }
@@ -629,7 +653,7 @@ int iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int 
         int np = 0;
         rc = iic_joint_tma(x, y, dtype, B, K, H, W, pad, partials, &np, st);
         if (rc == CY_OK) {
-            iic_reduce_partials_kernel<<<(nj + 255) / 256, 256, 0, st>>>(partials, np, nj, joint);
+            iic_reduce_partials_kernel<<<reduce_grid(nj), 32 * RED_WARPS, 0, st>>>(partials, np, nj, joint);
             CY_CHECK_LAUNCH("iic_reduce_partials");
             return CY_OK;
         }
@@ -645,7 +669,7 @@ int iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int 
         rc = CY_OK;
     }
     if (rc != CY_OK) return rc;
-    iic_reduce_partials_kernel<<<(nj + 255) / 256, 256, 0, st>>>(partials, p.grid, nj, joint);
+    iic_reduce_partials_kernel<<<reduce_grid(nj), 32 * RED_WARPS, 0, st>>>(partials, p.grid, nj, joint);
     CY_CHECK_LAUNCH("iic_reduce_partials");
     return CY_OK;
 }
@@ -669,9 +693,13 @@ int iic_epilogue(const float* joint, int K, int pad, int symmetric, float lamda,
         gscratch = reinterpret_cast<double*>(workspace);
         smem = 0;
     }
-    cudaError_t e = cudaFuncSetAttribute(iic_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem ? smem : 16));
-    if (e != cudaSuccess) { set_error("iic_epilogue smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    iic_epilogue_kernel<<<1, 256, smem, st>>>(joint, K, pad, symmetric, (double)lamda, (double)eps, n_pixels, loss, p00, p_ij,
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(iic_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("iic_epilogue smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_smem = smem;
+    }
+    iic_epilogue_kernel<<<1, EPI_THREADS, smem, st>>>(joint, K, pad, symmetric, (double)lamda, (double)eps, n_pixels, loss, p00, p_ij,
                                               djoint, gscratch);
     CY_CHECK_LAUNCH("iic_epilogue");
     return CY_OK;

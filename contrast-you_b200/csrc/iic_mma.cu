@@ -7,9 +7,9 @@
 // conversion pass would share), i.e. >= 2.8 clk/pixel/SM, against 3.0 clk/pixel/SM for the register-fed HMMA form below,
 // which needs no operand re-layout at all (shifted fragments are plain shared-memory loads).
 //
-// Precision: every fp32 value v is split as v = hi + lo, hi = bf16(v), lo = bf16(v - hi) (both round-to-nearest, so
-// the dropped lo*lo term is zero-mean); products use hi*hi + lo*hi + hi*lo: error <= 2^-16 relative per product,
-// fp32 accumulation — well inside the 1e-4 parity bar.
+// Precision: every fp32 value v is split as v = hi + lo, hi = bf16(v) rounded, lo = bf16(v - hi) (signed, so the dropped
+// lo*lo term and the truncation of lo are zero-mean); products use hi*hi + lo*hi + hi*lo: error <= 2^-16 relative per
+// product, fp32 accumulation — well inside the 1e-4 parity bar.
 //
 // Forward (iic_joint_mma_kernel):  J[k1,k2,dy,dx] = sum x[k1,h+dy-p,w'] * y[k2,h,w'-dx+p]   (w' = w+dx-p)
 //   D[(dx,k2) , (k1,dy)] += A[(dx,k2), pixel] * B[pixel, (k1,dy)]        A: shifted rows of y,  B: rows of x
@@ -45,25 +45,37 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 }
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
 // first MMA of a chain: C = 0
 __device__ __forceinline__ void mma_bf16_16816_z(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
         : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.f));
 }
+// plain (non-volatile) shared-memory load from a 32-bit shared address: ptxas may hoist it above the volatile MMAs of
+// the previous step (software pipelining), but not above the mbarrier wait (memory clobber)
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
+    return *reinterpret_cast<const float*>(__cvta_shared_to_generic(addr));
 }
 
-// (v0, v1) -> packed bf16 pairs (v0 in the low half): hi = rn(v), lo = rn(v - hi); v - hi is exact in fp32
+// (v0, v1) -> packed bf16 pairs (v0 in the low half), v = hi + lo.
+// hi = v rounded to bf16 (round-half-up on the bit pattern), lo = v - hi (exact in fp32, signed, |lo| <= 2^-9 |v|)
+// truncated to bf16.  Integer / FADD / PRMT only: cvt.rn.bf16x2.f32 (F2FP) issues on the XU pipe at 1/16 rate and was the
+// measured bottleneck of the first version of these kernels (profiles/README.md).
 __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const uint32_t h0 = (__float_as_uint(v0) + 0x8000u) & 0xffff0000u;
+    const uint32_t h1 = (__float_as_uint(v1) + 0x8000u) & 0xffff0000u;
+    hi = __byte_perm(h0, h1, 0x7632);
+    const float r0 = v0 - __uint_as_float(h0);
+    const float r1 = v1 - __uint_as_float(h1);
+    lo = __byte_perm(__float_as_uint(r0), __float_as_uint(r1), 0x7632);
+}
+// one-time split of the adjoint weights: both parts round-to-nearest
+__device__ __forceinline__ void split_pair_rn(float v0, float v1, uint32_t& hi, uint32_t& lo) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
     const float r0 = v0 - __uint_as_float(hi << 16);
     const float r1 = v1 - __uint_as_float(hi & 0xffff0000u);
@@ -73,13 +85,15 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
 struct MmaGeom {
     int B, K, H, W, pad, T;
     int TH, TW;              // tile: TH image rows x TW columns
-    int HH;                  // TH + 2 * pad
+    int BH;                  // rows of a staged box without halo (>= TH; 9 keeps the bank layout)
+    int HH;                  // BH + 2 * pad
     int XW;                  // forward: x box pitch (TW + 4);  backward: pitch of both boxes
     int YW, CO;              // forward: y box pitch (TW + 12), first column = w0 - CO; backward: CO of both boxes
     int tiles_h, tiles_w, n_tiles;
     int x_stage_floats, y_stage_floats;
     int n_combo;             // K * T
     int stages;
+    int debug_skip;          // CY_IIC_DEBUG_SKIP=1: stage the boxes but skip the arithmetic (data-movement floor; results invalid)
 };
 
 // ring of `n` stages with a runtime depth (the depth is chosen on the host from the shared-memory budget)
@@ -92,6 +106,7 @@ struct RingN {
     }
 };
 constexpr int MAX_STAGES = 4;
+constexpr int FW_ROWS = 8;       // image rows per forward tile = row-warps per split (the staged boxes keep 9 / 9 + 2p rows: bank layout)
 
 // ------------------------------------------------------------------------------------------------------ forward
 // MT m-tiles (16 rows of (dx,k2) each), NT n-tiles (8 columns of (k1,dy)) split over NSPLIT warps per pixel row, NCH chunks
@@ -100,11 +115,11 @@ constexpr int MAX_STAGES = 4;
 // the joint then carries no bias that grows with the number of pixels (needed for the padding = 0 loss, whose value is
 // a 1e-3 residual of O(1) terms).
 template <int MT, int NTW, int NSPLIT, int NCH>
-__global__ void __launch_bounds__((9 * NSPLIT + 1) * 32, NSPLIT == 1 ? 2 : 1)
+__global__ void __launch_bounds__(FW_ROWS * NSPLIT * 32, NSPLIT == 1 ? 2 : 1)
 iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, MmaGeom g,
                      float* __restrict__ partials) {
-    constexpr int NCW = 9 * NSPLIT;
-    constexpr int THREADS = (NCW + 1) * 32;
+    constexpr int NCW = FW_ROWS * NSPLIT;
+    constexpr int THREADS = NCW * 32;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     float* stage0 = reinterpret_cast<float*>(smem);
@@ -118,10 +133,32 @@ iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
     if (threadIdx.x == 0) {
         for (int i = 0; i < g.stages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NCW); }
         fence_barrier_init();
+        prefetch_tmap(&tmx);
+        prefetch_tmap(&tmy);
     }
     __syncthreads();
 
-    const uint32_t stage_bytes = (uint32_t)(K * g.HH * g.XW + K * g.TH * g.YW) * 4u;
+    const uint32_t stage_bytes = (uint32_t)(K * g.HH * g.XW + K * g.BH * g.YW) * 4u;
+    // thread 0 is also the TMA producer.  produce(it, block) requests the it-th tile of this CTA into stage it % stages
+    // once every warp has released that stage; with block == false it gives up (returns false) if they have not yet.
+    auto produce = [&](int it, bool block) -> bool {
+        const int tile = blockIdx.x + it * (int)gridDim.x;
+        if (tile >= g.n_tiles) return true;
+        const uint32_t s = (uint32_t)it % (uint32_t)g.stages, ph = ((uint32_t)it / (uint32_t)g.stages) & 1u;
+        if (block) mbar_wait(empty + s, ph ^ 1u);
+        else if (!mbar_try_wait(empty + s, ph ^ 1u)) return false;
+        const int b = tile / (g.tiles_h * g.tiles_w);
+        const int trem = tile % (g.tiles_h * g.tiles_w);
+        const int h0 = (trem / g.tiles_w) * g.TH, w0 = (trem % g.tiles_w) * g.TW;
+        mbar_arrive_expect_tx(full + s, stage_bytes);
+        float* xs = stage0 + (size_t)s * stage_floats;
+        tma_load_3d(xs, &tmx, full + s, w0, h0 - g.pad, b * K);
+        tma_load_3d(xs + g.x_stage_floats, &tmy, full + s, w0 - g.CO, h0, b * K);
+        return true;
+    };
+    if (threadIdx.x == 0)
+        for (int it = 0; it < g.stages - 1; ++it) produce(it, true);
+
     float acc[MT][NTW][4];
 #pragma unroll
     for (int a = 0; a < MT; ++a)
@@ -131,25 +168,7 @@ iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
             for (int c = 0; c < 4; ++c) acc[a][b2][c] = 0.f;
     const int gq = lane >> 2, q = lane & 3;          // fragment row / column group, k-slot quad
     const int split = warp % NSPLIT;
-
-    if (warp == NCW) {
-        if (elect_one()) {
-            prefetch_tmap(&tmx);
-            prefetch_tmap(&tmy);
-            RingN ring;
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ring.next(g.stages)) {
-                const int b = tile / (g.tiles_h * g.tiles_w);
-                const int trem = tile % (g.tiles_h * g.tiles_w);
-                const int h0 = (trem / g.tiles_w) * g.TH, w0 = (trem % g.tiles_w) * g.TW;
-                const uint32_t s = ring.stage();
-                mbar_wait(empty + s, ring.phase() ^ 1u);
-                mbar_arrive_expect_tx(full + s, stage_bytes);
-                float* xs = stage0 + (size_t)s * stage_floats;
-                tma_load_3d(xs, &tmx, full + s, w0, h0 - g.pad, b * K);
-                tma_load_3d(xs + g.x_stage_floats, &tmy, full + s, w0 - g.CO, h0, b * K);
-            }
-        }
-    } else {
+    {
         const int row = warp / NSPLIT;
         // shared-memory byte offsets (relative to the stage) of this lane's fragment rows; combinations past K*T read
         // in-bounds garbage whose accumulator rows / columns are never written out
@@ -166,7 +185,7 @@ iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 const int ca = 16 * tm + 8 * hf + gq;                 // (dx, k2) = (ca / K, ca % K)
-                int o = g.x_stage_floats + ((ca % K) * g.TH + row) * g.YW + q + g.CO + g.pad - (ca / K);
+                int o = g.x_stage_floats + ((ca % K) * g.BH + row) * g.YW + q + g.CO + g.pad - (ca / K);
                 if (ca >= g.n_combo) o = o < limit ? (o < 0 ? 0 : o) : limit;
                 yoff[tm][hf] = 4u * (uint32_t)o;
             }
@@ -174,12 +193,16 @@ iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
         const uint32_t stage_stride = (uint32_t)stage_floats * 4u;
 
         RingN ring;
-        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ring.next(g.stages)) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ring.next(g.stages), ++it) {
             const uint32_t s = ring.stage();
             mbar_wait(full + s, ring.phase());
             const uint32_t sb = stage0_addr + s * stage_stride;
+            // refill the stage released one iteration ago as early as the other warps allow (without stalling on them)
+            bool refilled = threadIdx.x != 0 || produce(it + g.stages - 1, false);
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) {
+            for (int ch = 0; ch < (g.debug_skip ? 0 : NCH); ++ch) {
+                if (ch > 0 && !refilled) refilled = produce(it + g.stages - 1, false);
                 uint32_t bh[NTW][2], bl[NTW][2];
 #pragma unroll
                 for (int tn = 0; tn < NTW; ++tn) {
@@ -198,7 +221,7 @@ iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
                     split_pair(c0, c1, ah[1], al[1]);
                     split_pair(a2, a3, ah[2], al[2]);
                     split_pair(c2, c3, ah[3], al[3]);
-                    float d[NTW][4];
+                    float d[NTW][4];           // NTW independent chains of 3 dependent HMMAs, issued interleaved
 #pragma unroll
                     for (int tn = 0; tn < NTW; ++tn) mma_bf16_16816_z(d[tn], ah, bh[tn]);
 #pragma unroll
@@ -211,6 +234,7 @@ iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
                         for (int c = 0; c < 4; ++c) acc[tm][tn][c] += d[tn][c];
                 }
             }
+            if (!refilled) produce(it + g.stages - 1, true);       // every warp has moved on from that stage by now
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + s);
         }
@@ -219,21 +243,18 @@ iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
     __syncthreads();
     constexpr int NV = MT * NTW * 4;                 // accumulator values per lane
     float* red = stage0;                             // [NCW][NV][32]
-    if (warp < NCW) {
 #pragma unroll
-        for (int tm = 0; tm < MT; ++tm)
+    for (int tm = 0; tm < MT; ++tm)
 #pragma unroll
-            for (int tn = 0; tn < NTW; ++tn)
+        for (int tn = 0; tn < NTW; ++tn)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) red[(warp * NV + (tm * NTW + tn) * 4 + c) * 32 + lane] = acc[tm][tn][c];
-    }
-    __syncthreads();
+            for (int c = 0; c < 4; ++c) red[(warp * NV + (tm * NTW + tn) * 4 + c) * 32 + lane] = acc[tm][tn][c];
     for (int i = threadIdx.x; i < nj; i += THREADS) partials[(size_t)blockIdx.x * nj + i] = 0.f;
     __syncthreads();
     for (int e = threadIdx.x; e < NSPLIT * NV * 32; e += THREADS) {
         const int sp = e / (NV * 32), v = (e / 32) % NV, ln = e % 32;
         float sum = 0.f;
-        for (int r = 0; r < 9; ++r) sum += red[((r * NSPLIT + sp) * NV + v) * 32 + ln];
+        for (int r = 0; r < FW_ROWS; ++r) sum += red[((r * NSPLIT + sp) * NV + v) * 32 + ln];
         const int c = v & 3, tn = (v >> 2) % NTW, tm = (v >> 2) / NTW;
         const int ca = 16 * tm + (ln >> 2) + (c >> 1) * 8;
         const int cb = 8 * (sp * NTW + tn) + 2 * (ln & 3) + (c & 1);
@@ -254,7 +275,7 @@ iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
 // The weights (dL/dJ * gscale; flipped for dL/dx) stay in registers as pre-split A fragments for the whole kernel; half
 // of the warps produce dL/dy from the x box and half dL/dx from the y box.
 constexpr int BW_WARPS_PER_GROUP = 4;
-constexpr int BW_THREADS = (2 * BW_WARPS_PER_GROUP + 1) * 32;
+constexpr int BW_THREADS = 2 * BW_WARPS_PER_GROUP * 32;
 
 template <int TWV>
 __global__ void __launch_bounds__(BW_THREADS, 2)
@@ -289,24 +310,28 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
     __syncthreads();
 
     const uint32_t box_bytes = (uint32_t)(K * HH * XW) * 4u;
-    if (warp == NCW) {
-        if (elect_one()) {
-            prefetch_tmap(&tmx);
-            prefetch_tmap(&tmy);
-            RingN ring;
-            for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ring.next(g.stages)) {
-                const int b = tile / (g.tiles_h * g.tiles_w);
-                const int trem = tile % (g.tiles_h * g.tiles_w);
-                const int h0 = (trem / g.tiles_w) * TH, w0 = (trem % g.tiles_w) * TWV;
-                const uint32_t s = ring.stage();
-                mbar_wait(empty + s, ring.phase() ^ 1u);
-                mbar_arrive_expect_tx(full + s, 2 * box_bytes);
-                float* xs = stage0 + (size_t)s * stage_floats;
-                tma_load_3d(xs, &tmx, full + s, w0 - CO, h0 - 1, b * K);
-                tma_load_3d(xs + g.x_stage_floats, &tmy, full + s, w0 - CO, h0 - 1, b * K);
-            }
-        }
-    } else {
+    // thread 0 is also the TMA producer (see iic_joint_mma_kernel)
+    auto produce = [&](int it, bool block) -> bool {
+        const int tile = blockIdx.x + it * (int)gridDim.x;
+        if (tile >= g.n_tiles) return true;
+        const uint32_t s = (uint32_t)it % (uint32_t)g.stages, ph = ((uint32_t)it / (uint32_t)g.stages) & 1u;
+        if (block) mbar_wait(empty + s, ph ^ 1u);
+        else if (!mbar_try_wait(empty + s, ph ^ 1u)) return false;
+        const int b = tile / (g.tiles_h * g.tiles_w);
+        const int trem = tile % (g.tiles_h * g.tiles_w);
+        const int h0 = (trem / g.tiles_w) * TH, w0 = (trem % g.tiles_w) * TWV;
+        mbar_arrive_expect_tx(full + s, 2 * box_bytes);
+        float* xs = stage0 + (size_t)s * stage_floats;
+        tma_load_3d(xs, &tmx, full + s, w0 - CO, h0 - 1, b * K);
+        tma_load_3d(xs + g.x_stage_floats, &tmy, full + s, w0 - CO, h0 - 1, b * K);
+        return true;
+    };
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmx);
+        prefetch_tmap(&tmy);
+        for (int it = 0; it < g.stages - 1; ++it) produce(it, true);
+    }
+    {
         const int gq = lane >> 2, q = lane & 3;
         const int group = warp / BW_WARPS_PER_GROUP, wq = warp % BW_WARPS_PER_GROUP;
         const float* wt = wtab + group * nj;
@@ -334,10 +359,10 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
                         w[hf][e4] = (rv && c < K) ? wt[((o * K + c) * T + dyy) * T + dxx] : 0.f;
                     }
                 }
-                split_pair(w[0][0], w[0][1], ah[tm][ks][0], al[tm][ks][0]);
-                split_pair(w[1][0], w[1][1], ah[tm][ks][1], al[tm][ks][1]);
-                split_pair(w[0][2], w[0][3], ah[tm][ks][2], al[tm][ks][2]);
-                split_pair(w[1][2], w[1][3], ah[tm][ks][3], al[tm][ks][3]);
+                split_pair_rn(w[0][0], w[0][1], ah[tm][ks][0], al[tm][ks][0]);
+                split_pair_rn(w[1][0], w[1][1], ah[tm][ks][1], al[tm][ks][1]);
+                split_pair_rn(w[0][2], w[0][3], ah[tm][ks][2], al[tm][ks][2]);
+                split_pair_rn(w[1][2], w[1][3], ah[tm][ks][3], al[tm][ks][3]);
             }
         // byte offsets (within a box) of this lane's 8 K-rows at box row 0, strip 0; rows past K*3 carry zero weights and
         // re-read row 0 (finite data)
@@ -350,24 +375,29 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
         }
         const uint32_t stage0_addr = smem_u32(stage0);
         RingN ring;
-        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ring.next(g.stages)) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ring.next(g.stages), ++it) {
             const int b = tile / (g.tiles_h * g.tiles_w);
             const int trem = tile % (g.tiles_h * g.tiles_w);
             const int h0 = (trem / g.tiles_w) * TH, w0 = (trem % g.tiles_w) * TWV;
             const uint32_t s = ring.stage();
             mbar_wait(full + s, ring.phase());
             const uint32_t box = stage0_addr + 4u * (uint32_t)(s * stage_floats + group * g.x_stage_floats);
+            bool refilled = threadIdx.x != 0 || produce(it + g.stages - 1, false);
 #pragma unroll 1
-            for (int strip = wq; strip < NSTRIP; strip += BW_WARPS_PER_GROUP) {
+            for (int strip = wq; strip < (g.debug_skip ? 0 : NSTRIP); strip += BW_WARPS_PER_GROUP) {
                 const uint32_t sbase = box + strip * 32;
                 const int w = w0 + 8 * strip + 2 * q;
-                float* orow = out + (((size_t)b * K + gq) * g.H + h0) * g.W + w;       // (o = gq, row h0)
+                float* op = out + (((size_t)b * K + gq) * g.H + h0) * g.W + w;       // (o = gq, row h0); + W per finished row
                 const size_t ostride8 = (size_t)8 * g.H * g.W;
+                const int rows_ok = g.H - h0;                 // W % 4 == 0 and w even: a pixel pair is inside the row together
+                const bool st0 = w < g.W && gq < K, st1 = w < g.W && gq < KX;
                 float accA[3][2], acc3[3][2];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) accA[i][0] = accA[i][1] = acc3[i][0] = acc3[i][1] = 0.f;
 #pragma unroll
                 for (int rp = 0; rp < HH; ++rp) {
+                    if ((rp == 3 || rp == 7) && !refilled) refilled = produce(it + g.stages - 1, false);
                     float v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = lds_f32(sbase + roff[j] + rp * XW * 4);
@@ -376,7 +406,7 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
                     split_pair(v[2], v[3], bh[0][1], bl[0][1]);
                     split_pair(v[4], v[5], bh[1][0], bl[1][0]);
                     split_pair(v[6], v[7], bh[1][1], bl[1][1]);
-                    float d[2][4];
+                    float d[2][4];                // two independent chains of six dependent HMMAs, issued interleaved
 #pragma unroll
                     for (int tm = 0; tm < 2; ++tm) mma_bf16_16816_z(d[tm], ah[tm][0], bh[0]);
 #pragma unroll
@@ -406,14 +436,14 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
                             t0 += __shfl_down_sync(0xffffffffu, t0, 4 * KX) + __shfl_down_sync(0xffffffffu, t0, 8 * KX);
                             t1 += __shfl_down_sync(0xffffffffu, t1, 4 * KX) + __shfl_down_sync(0xffffffffu, t1, 8 * KX);
                         }
-                        if (h0 + rc < g.H && w < g.W) {   // W % 4 == 0 and w even: the pixel pair is inside the row together
-                            if (gq < K) *reinterpret_cast<float2*>(orow + (size_t)rc * g.W) = make_float2(accA[rc % 3][0], accA[rc % 3][1]);
-                            if (gq < KX) *reinterpret_cast<float2*>(orow + ostride8 + (size_t)rc * g.W) = make_float2(t0, t1);
-                        }
+                        if (st0 && rc < rows_ok) *reinterpret_cast<float2*>(op) = make_float2(accA[rc % 3][0], accA[rc % 3][1]);
+                        if (st1 && rc < rows_ok) *reinterpret_cast<float2*>(op + ostride8) = make_float2(t0, t1);
+                        op += g.W;
                         accA[rc % 3][0] = accA[rc % 3][1] = acc3[rc % 3][0] = acc3[rc % 3][1] = 0.f;
                     }
                 }
             }
+            if (!refilled) produce(it + g.stages - 1, true);       // every warp has moved on from that stage by now
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + s);
         }
@@ -432,6 +462,12 @@ int make_map3d(CUtensorMap* m, const void* base, int B, int K, int H, int W, int
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3d) failed (%d)", (int)r); return CY_ERR_ARG; }
     return CY_OK;
+}
+
+int debug_skip() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("CY_IIC_DEBUG_SKIP"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v;
 }
 
 int sm_count_mma() {
@@ -466,8 +502,9 @@ bool fwd_geom(int B, int K, int H, int W, int pad, MmaGeom* g, int* mt, int* ntw
     else if (*mt * ((nt + 1) / 2) <= 16) { *nsplit = 2; *ntw = (nt + 1) / 2; }
     else return false;
     g->B = B; g->K = K; g->H = H; g->W = W; g->pad = pad; g->T = T;
-    g->TH = 9;                        // HH = 9 + 2p == T (mod 8): fragment rows (k1, dy) land on distinct bank groups
-    g->HH = g->TH + 2 * pad;
+    g->TH = FW_ROWS;
+    g->BH = 9;                        // HH = 9 + 2p == T (mod 8): fragment rows (k1, dy) land on distinct bank groups
+    g->HH = g->BH + 2 * pad;
     g->CO = 4;
     g->n_combo = nc;
     const int nj = K * K * T * T;
@@ -482,10 +519,10 @@ bool fwd_geom(int B, int K, int H, int W, int pad, MmaGeom* g, int* mt, int* ntw
         g->tiles_w = (W + tw - 1) / tw;
         g->n_tiles = B * g->tiles_h * g->tiles_w;
         g->x_stage_floats = (K * g->HH * g->XW + 31) & ~31;
-        g->y_stage_floats = (K * g->TH * g->YW + 31) & ~31;
+        g->y_stage_floats = (K * g->BH * g->YW + 31) & ~31;
         for (int st = MAX_STAGES - 1; st >= 2; --st) {
             *smem = (size_t)st * (g->x_stage_floats + g->y_stage_floats) * 4 + 2 * MAX_STAGES * 8 + 128 + 64;
-            const size_t red = (size_t)9 * *nsplit * *mt * *ntw * 4 * 32 * 4;      // epilogue reduction buffer reuses the ring
+            const size_t red = (size_t)FW_ROWS * *nsplit * *mt * *ntw * 4 * 32 * 4;      // epilogue reduction buffer reuses the ring
             if (*smem <= budget && (size_t)st * (g->x_stage_floats + g->y_stage_floats) * 4 >= red) { g->stages = st; return true; }
         }
     }
@@ -496,9 +533,13 @@ template <int MT, int NTW, int NSPLIT, int NCH>
 int launch_joint_mma(const CUtensorMap& tmx, const CUtensorMap& tmy, const MmaGeom& g, size_t smem, int grid, float* partials,
                      cudaStream_t st) {
     auto k = iic_joint_mma_kernel<MT, NTW, NSPLIT, NCH>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("iic_joint_mma smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
-    k<<<grid, (9 * NSPLIT + 1) * 32, smem, st>>>(tmx, tmy, g, partials);
+    static size_t attr_smem = 0;          // one process drives one device: raise the opt-in limit only when it grows
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("iic_joint_mma smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
+        attr_smem = smem;
+    }
+    k<<<grid, FW_ROWS * NSPLIT * 32, smem, st>>>(tmx, tmy, g, partials);
     CY_CHECK_LAUNCH("iic_joint_mma");
     return CY_OK;
 }
@@ -511,10 +552,11 @@ int iic_joint_mma(const void* x, const void* y, int dtype, int B, int K, int H, 
     MmaGeom g; int mt, ntw, nsplit; size_t smem;
     if (dtype != CY_F32 || !aligned16(x) || !aligned16(y) || !fwd_geom(B, K, H, W, pad, &g, &mt, &ntw, &nsplit, &smem))
         return CY_ERR_UNSUPPORTED;
+    g.debug_skip = debug_skip();
     CUtensorMap tmx, tmy;
     int rc = make_map3d(&tmx, x, B, K, H, W, g.XW, g.HH);
     if (rc) return rc;
-    rc = make_map3d(&tmy, y, B, K, H, W, g.YW, g.TH);
+    rc = make_map3d(&tmy, y, B, K, H, W, g.YW, g.BH);
     if (rc) return rc;
     const int cap = sm_count_mma() * (nsplit == 1 ? 2 : 1);
     const int grid = g.n_tiles < cap ? g.n_tiles : cap;
@@ -537,8 +579,12 @@ template <int TWV>
 int launch_bwd_mma(const CUtensorMap& tmx, const CUtensorMap& tmy, const MmaGeom& g, size_t smem, int grid, const float* djoint,
                    const float* gscale, float* dx, float* dy, cudaStream_t st) {
     auto k = iic_bwd_mma_kernel<TWV>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("iic_bwd_mma smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("iic_bwd_mma smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
+        attr_smem = smem;
+    }
     k<<<grid, BW_THREADS, smem, st>>>(tmx, tmy, g, djoint, gscale, dx, dy);
     CY_CHECK_LAUNCH("iic_bwd_mma");
     return CY_OK;
@@ -575,6 +621,7 @@ int iic_bwd_mma(const void* x, const void* y, int dtype, int B, int K, int H, in
         }
     }
     if (!ok) return CY_ERR_UNSUPPORTED;
+    g.debug_skip = debug_skip();
     CUtensorMap tmx, tmy;
     int rc = make_map3d(&tmx, x, B, K, H, W, g.XW, g.HH);
     if (rc) return rc;

@@ -37,15 +37,31 @@ def _check_pair(x: Tensor, y: Tensor):
     return x.contiguous(), y.contiguous()
 
 
-def _joint_forward(x, y, padding):
+_WORKSPACES = {}
+
+
+def _workspace(nbytes: int, device, stream: int):
+    """Scratch for the per-CTA partial joints, cached per (device, stream): launches on one stream are ordered, so the
+    buffer can be reused by the next call without a fresh allocation (the loss is called once per hook per batch)."""
+    key = (device.index, stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def _joint_forward(x, y, padding, joint=None):
     lib = L.lib()
     B, K, H, W = x.shape
     T = 2 * padding + 1
-    joint = torch.empty(K, K, T, T, dtype=torch.float32, device=x.device)
+    if joint is None:
+        joint = torch.empty(K, K, T, T, dtype=torch.float32, device=x.device)
+    st = L.stream_ptr()
     ws_bytes = lib.cy_iic_workspace_bytes(B, K, H, W, padding)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    ws = _workspace(ws_bytes, x.device, st)
     L.check(lib.cy_iic_joint(x.data_ptr(), y.data_ptr(), L.dtype_code(x), B, K, H, W, padding, joint.data_ptr(),
-                             ws.data_ptr(), ws_bytes, L.stream_ptr()), "cy_iic_joint")
+                             ws.data_ptr(), ws_bytes, st), "cy_iic_joint")
     return joint
 
 
@@ -125,13 +141,14 @@ class _IIDSegFunction(torch.autograd.Function):
         lib = L.lib()
         B, K, H, W = x.shape
         T = 2 * padding + 1
-        joint = _joint_forward(x, y, padding)
+        nj = K * K * T * T
+        buf = torch.empty(1 + K * K + 2 * nj, dtype=torch.float32, device=x.device)      # one allocation for the small outputs
+        loss, p00 = buf[:1], buf[1:1 + K * K].view(K, K)
+        djoint, joint = buf[1 + K * K:1 + K * K + nj].view(K, K, T, T), buf[1 + K * K + nj:].view(K, K, T, T)
+        _joint_forward(x, y, padding, joint)
         n_pixels = float(B * H * W)
         if reduce_joint is not None:
             n_pixels = reduce_joint(joint, n_pixels)
-        loss = torch.empty(1, dtype=torch.float32, device=x.device)
-        p00 = torch.empty(K, K, dtype=torch.float32, device=x.device)
-        djoint = torch.empty(K, K, T, T, dtype=torch.float32, device=x.device)
         ws_bytes = lib.cy_iic_epilogue_workspace_bytes(K, padding)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
         L.check(lib.cy_iic_epilogue(joint.data_ptr(), K, padding, int(bool(symmetric)), float(lamda), float(eps), n_pixels,
@@ -145,7 +162,9 @@ class _IIDSegFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss, _grad_p00):
         x, y, djoint = ctx.saved_tensors
-        gscale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        gscale = grad_loss
+        if gscale.dtype != torch.float32 or gscale.numel() != 1 or not gscale.is_contiguous():
+            gscale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         dx, dy = _joint_backward(x, y, ctx.padding, djoint, gscale)
         return dx, dy, None, None, None, None, None
 

@@ -43,6 +43,20 @@ int main() {
     cudaMalloc(&out, 148 * 1024 * 4 * 4);
     cudaMalloc(&cyc, 148 * 8 * 8);
     const int iters = 4096;
+    // dependent-issue latency: one warp per SMSP, NACC independent accumulator chains
+    {
+        long long c;
+        hmma_loop<1><<<148, 128>>>(out, iters, cyc); cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("1 warp/SMSP, 1 chain : %.1f cycles per dependent HMMA\n", (double)c / iters);
+        hmma_loop<2><<<148, 128>>>(out, iters, cyc); cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("1 warp/SMSP, 2 chains: %.1f cycles per HMMA\n", (double)c / iters / 2);
+        hmma_loop<4><<<148, 128>>>(out, iters, cyc); cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("1 warp/SMSP, 4 chains: %.1f cycles per HMMA\n", (double)c / iters / 4);
+        hmma_loop<2><<<148, 512>>>(out, iters, cyc); cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("4 warps/SMSP, 2 chains: %.1f cycles per HMMA per SMSP\n", (double)c / iters / 2 / 4);
+        hmma_loop<1><<<148, 512>>>(out, iters, cyc); cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("4 warps/SMSP, 1 chain : %.1f cycles per HMMA per SMSP\n", (double)c / iters / 4);
+    }
     const int NACC = 12;
     for (int warps = 4; warps <= 32; warps *= 2) {
         cudaEvent_t e0, e1;
