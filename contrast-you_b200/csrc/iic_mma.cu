@@ -17,9 +17,9 @@
 //   consecutive pixels of one image row; k-slot (2q, 2q+1, 2q+8, 2q+9) of lane quad q holds pixels (q, q+4, q+8, q+12),
 //   so every fragment element is one conflict-free LDS.32 and a displacement is an address offset.
 // Backward (iic_bwd_mma_kernel):   out[o,h,w] = sum_{c,dy,dx} Wt[o,c,dy,dx] * in[c,h+dy-p,w+dx-p]
-//   D[o (16), pixel (8)] += Wt[o, (c,dy,dx)] * col[(c,dy,dx), pixel];  the weights (dL/dJ, scaled; flipped for dL/dx)
-//   stay in registers as pre-split A fragments for the whole kernel, half of the warps produce dL/dy from the x box and
-//   half dL/dx from the y box.
+//   D[o (16), pixel (8)] += Wt_dy[o, (c,dx)] * col[(c,dx), pixel] per box row, accumulated over dy in rolling HMMA
+//   accumulators; the weights (dL/dJ, scaled; flipped for dL/dx) stay in registers as pre-split A fragments for the
+//   whole kernel, half of the warps produce dL/dy from the x box and half dL/dx from the y box.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -201,7 +201,7 @@ iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
             // refill the stage released one iteration ago as early as the other warps allow (without stalling on them)
             bool refilled = threadIdx.x != 0 || produce(it + g.stages - 1, false);
 #pragma unroll
-            for (int ch = 0; ch < (g.debug_skip ? 0 : NCH); ++ch) {
+            for (int ch = 0; ch < (g.debug_skip == 1 ? 0 : NCH); ++ch) {
                 if (ch > 0 && !refilled) refilled = produce(it + g.stages - 1, false);
                 uint32_t bh[NTW][2], bl[NTW][2];
 #pragma unroll
@@ -266,19 +266,21 @@ iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------------ backward
-// padding = 1, K <= 10.  One warp walks an 8-pixel column strip of the box row by row.  For box row r' the B operand
-// col[(c,dx), pixel] = in[c, r', pixel + dx - 1] (K*3 <= 30 of 32 k-slots, 2 k-steps) is loaded and split ONCE and
-// multiplied by all (dy, o) weight rows at once (K*3 <= 30 of 32 rows, 2 m-tiles): D[(dy,o), pixel] is this row's
-// contribution to output row r' - dy.  Row slots 0..2 of the two m-tiles hold (dy = slot, o = lane group) for o < 8,
-// so the three rows that make up one output row meet in the same thread (rolling accumulators, plain FADDs); slot 3
-// holds the 3 x (K - 8) remaining (dy, o >= 8) rows, whose partial sums meet through two warp shuffles.
+// padding = 1, K <= 16.  One warp walks an 8-pixel column strip of the box row by row.  For box row r' the B operand
+// col[(c,dx), pixel] = in[c, r', pixel + dx - 1] (K*3 k-slots, KS k-steps of 16) is loaded and split ONCE and used by
+// the three output rows it feeds: acc[r' - dy] += Wt_dy[o, (c,dx)] * col for dy = 0..2 — three independent HMMA chains
+// whose accumulators roll through the strip, so an output row is complete (18 chained HMMAs at K = 10) when its third
+// box row has been consumed and goes straight from the accumulator registers to global memory.
 // The weights (dL/dJ * gscale; flipped for dL/dx) stay in registers as pre-split A fragments for the whole kernel; half
 // of the warps produce dL/dy from the x box and half dL/dx from the y box.
 constexpr int BW_WARPS_PER_GROUP = 4;
 constexpr int BW_THREADS = 2 * BW_WARPS_PER_GROUP * 32;
 
-template <int TWV>
-__global__ void __launch_bounds__(BW_THREADS, 2)
+#ifndef CY_BW_CTAS
+#define CY_BW_CTAS 2
+#endif
+template <int TWV, int KS>
+__global__ void __launch_bounds__(BW_THREADS, CY_BW_CTAS)
 iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, MmaGeom g,
                    const float* __restrict__ djoint, const float* __restrict__ gscale, float* __restrict__ dx_out,
                    float* __restrict__ dy_out) {
@@ -286,11 +288,13 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     float* stage0 = reinterpret_cast<float*>(smem);
-    const int K = g.K, KX = K > 8 ? K - 8 : 0;
+    const int K = g.K;
     const int stage_floats = 2 * g.x_stage_floats;
-    float* wtab = stage0 + (size_t)g.stages * stage_floats;          // [2][K][K][T][T] scaled weights
+    // [2][K][K][T][T] scaled weights: only read while the A fragments are built, so the table borrows the last stage
+    // of the ring (the prologue requests tiles for stages 0 .. stages-2 only; a CTA-wide barrier ends the borrow)
+    float* wtab = stage0 + (size_t)(g.stages - 1) * stage_floats;
     const int nj = K * K * T * T;
-    uint64_t* full = reinterpret_cast<uint64_t*>(wtab + ((2 * nj + 31) & ~31));
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + (size_t)g.stages * stage_floats);
     uint64_t* empty = full + MAX_STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -336,44 +340,40 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
         const int group = warp / BW_WARPS_PER_GROUP, wq = warp % BW_WARPS_PER_GROUP;
         const float* wt = wtab + group * nj;
         float* out = group ? dx_out : dy_out;
-        // A fragments.  Row of m-tile tm, half hf: slot = 2*tm + hf; slot < 3: (dy = slot, o = gq); slot 3: (dy, o) =
-        // (gq / KX, 8 + gq % KX).  k-slot pairs of k-step ks <-> this lane quad's own elements e = 4*ks + {0,1 | 2,3},
-        // element e <-> K-row R = q + 4*e = c * 3 + dx.
-        const int dy3 = KX ? gq / KX : 3;                 // >= 3: this lane's slot-3 row is unused
-        uint32_t ah[2][2][4], al[2][2][4];
+        // A fragments per dy: row o = gq (+8); k-slot pairs of k-step ks <-> this lane quad's own elements
+        // e = 4*ks + {0,1 | 2,3}, element e <-> K-row R = q + 4*e = c * 3 + dx
+        uint32_t ah[3][KS][4], al[3][KS][4];
 #pragma unroll
-        for (int tm = 0; tm < 2; ++tm)
+        for (int dyy = 0; dyy < 3; ++dyy)
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
+            for (int ks = 0; ks < KS; ++ks) {
                 float w[2][4];
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
-                    const int slot = 2 * tm + hf;
-                    const int dyy = slot < 3 ? slot : dy3;
-                    const int o = slot < 3 ? gq : 8 + (KX ? gq % KX : 0);
-                    const bool rv = dyy < 3 && o < K;
+                    const int o = gq + 8 * hf;
 #pragma unroll
                     for (int e4 = 0; e4 < 4; ++e4) {
                         const int R = q + 4 * (4 * ks + e4);
                         const int c = R / 3, dxx = R % 3;
-                        w[hf][e4] = (rv && c < K) ? wt[((o * K + c) * T + dyy) * T + dxx] : 0.f;
+                        w[hf][e4] = (o < K && c < K) ? wt[((o * K + c) * T + dyy) * T + dxx] : 0.f;
                     }
                 }
-                split_pair_rn(w[0][0], w[0][1], ah[tm][ks][0], al[tm][ks][0]);
-                split_pair_rn(w[1][0], w[1][1], ah[tm][ks][1], al[tm][ks][1]);
-                split_pair_rn(w[0][2], w[0][3], ah[tm][ks][2], al[tm][ks][2]);
-                split_pair_rn(w[1][2], w[1][3], ah[tm][ks][3], al[tm][ks][3]);
+                split_pair_rn(w[0][0], w[0][1], ah[dyy][ks][0], al[dyy][ks][0]);
+                split_pair_rn(w[1][0], w[1][1], ah[dyy][ks][1], al[dyy][ks][1]);
+                split_pair_rn(w[0][2], w[0][3], ah[dyy][ks][2], al[dyy][ks][2]);
+                split_pair_rn(w[1][2], w[1][3], ah[dyy][ks][3], al[dyy][ks][3]);
             }
-        // byte offsets (within a box) of this lane's 8 K-rows at box row 0, strip 0; rows past K*3 carry zero weights and
-        // re-read row 0 (finite data)
-        uint32_t roff[8];
+        // byte offsets (within a box) of this lane's 4*KS K-rows at box row 0, strip 0; rows past K*3 carry zero weights
+        // and re-read row 0 (finite data)
+        uint32_t roff[4 * KS];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4 * KS; ++j) {
             int R = q + 4 * j;
             if (R >= K * 3) R = 0;
             roff[j] = 4u * (uint32_t)((R / 3) * HH * XW + (R % 3) + gq + CO - 1);
         }
         const uint32_t stage0_addr = smem_u32(stage0);
+        __syncthreads();                                  // every warp has built its fragments: the last stage is free
         RingN ring;
         int it = 0;
         for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ring.next(g.stages), ++it) {
@@ -385,61 +385,46 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
             const uint32_t box = stage0_addr + 4u * (uint32_t)(s * stage_floats + group * g.x_stage_floats);
             bool refilled = threadIdx.x != 0 || produce(it + g.stages - 1, false);
 #pragma unroll 1
-            for (int strip = wq; strip < (g.debug_skip ? 0 : NSTRIP); strip += BW_WARPS_PER_GROUP) {
+            for (int strip = wq; strip < (g.debug_skip == 1 ? 0 : NSTRIP); strip += BW_WARPS_PER_GROUP) {
                 const uint32_t sbase = box + strip * 32;
                 const int w = w0 + 8 * strip + 2 * q;
                 float* op = out + (((size_t)b * K + gq) * g.H + h0) * g.W + w;       // (o = gq, row h0); + W per finished row
                 const size_t ostride8 = (size_t)8 * g.H * g.W;
                 const int rows_ok = g.H - h0;                 // W % 4 == 0 and w even: a pixel pair is inside the row together
-                const bool st0 = w < g.W && gq < K, st1 = w < g.W && gq < KX;
-                float accA[3][2], acc3[3][2];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) accA[i][0] = accA[i][1] = acc3[i][0] = acc3[i][1] = 0.f;
+                const bool st0 = w < g.W && gq < K && g.debug_skip != 2, st1 = w < g.W && gq + 8 < K && g.debug_skip != 2;
+                float acc[3][4];                              // rolling: output row r lives in acc[r % 3]
 #pragma unroll
                 for (int rp = 0; rp < HH; ++rp) {
                     if ((rp == 3 || rp == 7) && !refilled) refilled = produce(it + g.stages - 1, false);
-                    float v[8];
+                    uint32_t bh[KS][2], bl[KS][2];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = lds_f32(sbase + roff[j] + rp * XW * 4);
-                    uint32_t bh[2][2], bl[2][2];
-                    split_pair(v[0], v[1], bh[0][0], bl[0][0]);
-                    split_pair(v[2], v[3], bh[0][1], bl[0][1]);
-                    split_pair(v[4], v[5], bh[1][0], bl[1][0]);
-                    split_pair(v[6], v[7], bh[1][1], bl[1][1]);
-                    float d[2][4];                // two independent chains of six dependent HMMAs, issued interleaved
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const float v0 = lds_f32(sbase + roff[4 * ks + 0] + rp * XW * 4), v1 = lds_f32(sbase + roff[4 * ks + 1] + rp * XW * 4);
+                        const float v2 = lds_f32(sbase + roff[4 * ks + 2] + rp * XW * 4), v3 = lds_f32(sbase + roff[4 * ks + 3] + rp * XW * 4);
+                        split_pair(v0, v1, bh[ks][0], bl[ks][0]);
+                        split_pair(v2, v3, bh[ks][1], bl[ks][1]);
+                    }
+                    // three independent chains (one per dy), issued interleaved term by term
 #pragma unroll
-                    for (int tm = 0; tm < 2; ++tm) mma_bf16_16816_z(d[tm], ah[tm][0], bh[0]);
+                    for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-                    for (int tm = 0; tm < 2; ++tm) mma_bf16_16816(d[tm], al[tm][0], bh[0]);
+                        for (int term = 0; term < 3; ++term) {
 #pragma unroll
-                    for (int tm = 0; tm < 2; ++tm) mma_bf16_16816(d[tm], ah[tm][0], bl[0]);
-#pragma unroll
-                    for (int tm = 0; tm < 2; ++tm) mma_bf16_16816(d[tm], ah[tm][1], bh[1]);
-#pragma unroll
-                    for (int tm = 0; tm < 2; ++tm) mma_bf16_16816(d[tm], al[tm][1], bh[1]);
-#pragma unroll
-                    for (int tm = 0; tm < 2; ++tm) mma_bf16_16816(d[tm], ah[tm][1], bl[1]);
-                    // slot s (rows 8*s .. 8*s+7 of the 32) = d[s / 2][2 * (s % 2) + {0, 1}]
-#pragma unroll
-                    for (int dyy = 0; dyy < 3; ++dyy) {
-                        const int r = rp - dyy;                       // output row fed by (box row rp, dy)
-                        if (r >= 0 && r < TH) {
-                            accA[r % 3][0] += d[dyy / 2][2 * (dyy % 2)];
-                            accA[r % 3][1] += d[dyy / 2][2 * (dyy % 2) + 1];
-                            if (dy3 == dyy) { acc3[r % 3][0] += d[1][2]; acc3[r % 3][1] += d[1][3]; }
+                            for (int dyy = 0; dyy < 3; ++dyy) {
+                                const int r = rp - dyy;               // output row fed by (box row rp, dy)
+                                if (r < 0 || r >= TH) continue;
+                                const uint32_t (&a)[4] = term == 1 ? al[dyy][ks] : ah[dyy][ks];
+                                const uint32_t (&bb)[2] = term == 2 ? bl[ks] : bh[ks];
+                                if (dyy == 0 && ks == 0 && term == 0) mma_bf16_16816_z(acc[r % 3], a, bb);    // first touch of row r
+                                else mma_bf16_16816(acc[r % 3], a, bb);
+                            }
                         }
                     }
                     const int rc = rp - 2;                            // output row completed by this box row
                     if (rc >= 0) {
-                        float t0 = acc3[rc % 3][0], t1 = acc3[rc % 3][1];
-                        if (KX) {                                     // rows (dy, o) of one o sit KX lane groups apart
-                            t0 += __shfl_down_sync(0xffffffffu, t0, 4 * KX) + __shfl_down_sync(0xffffffffu, t0, 8 * KX);
-                            t1 += __shfl_down_sync(0xffffffffu, t1, 4 * KX) + __shfl_down_sync(0xffffffffu, t1, 8 * KX);
-                        }
-                        if (st0 && rc < rows_ok) *reinterpret_cast<float2*>(op) = make_float2(accA[rc % 3][0], accA[rc % 3][1]);
-                        if (st1 && rc < rows_ok) *reinterpret_cast<float2*>(op + ostride8) = make_float2(t0, t1);
+                        if (st0 && rc < rows_ok) *reinterpret_cast<float2*>(op) = make_float2(acc[rc % 3][0], acc[rc % 3][1]);
+                        if (st1 && rc < rows_ok) *reinterpret_cast<float2*>(op + ostride8) = make_float2(acc[rc % 3][2], acc[rc % 3][3]);
                         op += g.W;
-                        accA[rc % 3][0] = accA[rc % 3][1] = acc3[rc % 3][0] = acc3[rc % 3][1] = 0.f;
                     }
                 }
             }
@@ -466,7 +451,7 @@ int make_map3d(CUtensorMap* m, const void* base, int B, int K, int H, int W, int
 
 int debug_skip() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("CY_IIC_DEBUG_SKIP"); v = (e && e[0] == '1') ? 1 : 0; }
+    if (v < 0) { const char* e = getenv("CY_IIC_DEBUG_SKIP"); v = e ? atoi(e) : 0; }
     return v;
 }
 
@@ -575,10 +560,10 @@ int iic_joint_mma_max_partials() { return 2 * sm_count_mma(); }
 
 namespace {
 
-template <int TWV>
+template <int TWV, int KS>
 int launch_bwd_mma(const CUtensorMap& tmx, const CUtensorMap& tmy, const MmaGeom& g, size_t smem, int grid, const float* djoint,
                    const float* gscale, float* dx, float* dy, cudaStream_t st) {
-    auto k = iic_bwd_mma_kernel<TWV>;
+    auto k = iic_bwd_mma_kernel<TWV, KS>;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -594,7 +579,7 @@ int launch_bwd_mma(const CUtensorMap& tmx, const CUtensorMap& tmy, const MmaGeom
 
 int iic_bwd_mma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
                 const float* gscale, void* dx, void* dy, cudaStream_t st) {
-    if (dtype != CY_F32 || pad != 1 || (W % 4) != 0 || K > 10 || !aligned16(x) || !aligned16(y) || !aligned16(dx) || !aligned16(dy))
+    if (dtype != CY_F32 || pad != 1 || (W % 4) != 0 || K > 16 || !aligned16(x) || !aligned16(y) || !aligned16(dx) || !aligned16(dy))
         return CY_ERR_UNSUPPORTED;
     const int T = 3;
     MmaGeom g;
@@ -616,8 +601,8 @@ int iic_bwd_mma(const void* x, const void* y, int dtype, int B, int K, int H, in
         g.x_stage_floats = (K * g.HH * g.XW + 31) & ~31;
         g.y_stage_floats = g.x_stage_floats;
         for (int stg = MAX_STAGES - 1; stg >= 2 && !ok; --stg) {
-            smem = ((size_t)stg * 2 * g.x_stage_floats + ((2 * nj + 31) & ~31)) * 4 + 2 * MAX_STAGES * 8 + 128 + 64;
-            if (smem <= 113 * 1024) { g.stages = stg; ok = true; }
+            smem = (size_t)stg * 2 * g.x_stage_floats * 4 + 2 * MAX_STAGES * 8 + 128 + 64;
+            if (smem <= (size_t)(227 / CY_BW_CTAS - 1) * 1024 && 2 * g.x_stage_floats >= 2 * nj) { g.stages = stg; ok = true; }
         }
     }
     if (!ok) return CY_ERR_UNSUPPORTED;
@@ -627,12 +612,17 @@ int iic_bwd_mma(const void* x, const void* y, int dtype, int B, int K, int H, in
     if (rc) return rc;
     rc = make_map3d(&tmy, y, B, K, H, W, g.XW, g.HH);
     if (rc) return rc;
-    const int cap = 2 * sm_count_mma();
+    const int cap = CY_BW_CTAS * sm_count_mma();
     const int grid = g.n_tiles < cap ? g.n_tiles : cap;
     float* dxf = reinterpret_cast<float*>(dx);
     float* dyf = reinterpret_cast<float*>(dy);
-    if (g.TW == 32) return launch_bwd_mma<32>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
-    if (g.TW == 64) return launch_bwd_mma<64>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
+    const int ks = (K * T + 15) / 16;              // k-steps: K <= 5 -> 1, K <= 10 -> 2, K <= 16 -> 3
+    if (g.TW == 32 && ks == 1) return launch_bwd_mma<32, 1>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
+    if (g.TW == 32 && ks == 2) return launch_bwd_mma<32, 2>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
+    if (g.TW == 32 && ks == 3) return launch_bwd_mma<32, 3>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
+    if (g.TW == 64 && ks == 1) return launch_bwd_mma<64, 1>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
+    if (g.TW == 64 && ks == 2) return launch_bwd_mma<64, 2>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
+    if (g.TW == 64 && ks == 3) return launch_bwd_mma<64, 3>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
     return CY_ERR_UNSUPPORTED;
 }
 

@@ -37,6 +37,36 @@ __global__ void hmma_loop(float* out, int iters, long long* cycles) {
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// operands vary between consecutive HMMAs (NA distinct A fragments, NB distinct B fragments), as in a real kernel
+template <int NACC, int NA, int NB>
+__global__ void hmma_loop_var(float* out, int iters, long long* cycles) {
+    float acc[NACC][4];
+    uint32_t a[NA][4], b[NB][2];
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[k][i] = 0x3f803f80u + threadIdx.x + i + 7 * k;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) { b[k][0] = 0x3f803f80u + threadIdx.x + k; b[k][1] = 0x3f803f80u - threadIdx.x - k; }
+#pragma unroll
+    for (int j = 0; j < NACC; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) mma_bf16(acc[j], a[j % NA], b[(j / NA) % NB]);
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) s += acc[j][0] + acc[j][1] + acc[j][2] + acc[j][3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 int main() {
     float* out;
     long long* cyc;
@@ -56,6 +86,19 @@ int main() {
         printf("4 warps/SMSP, 2 chains: %.1f cycles per HMMA per SMSP\n", (double)c / iters / 2 / 4);
         hmma_loop<1><<<148, 512>>>(out, iters, cyc); cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
         printf("4 warps/SMSP, 1 chain : %.1f cycles per HMMA per SMSP\n", (double)c / iters / 4);
+    }
+    {
+        long long c;
+        hmma_loop_var<8, 4, 2><<<148, 512>>>(out, iters, cyc); cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("4 warps/SMSP, 8 chains, 4 A x 2 B fragments: %.1f cycles per HMMA per SMSP\n", (double)c / iters / 8 / 4);
+        hmma_loop_var<8, 2, 4><<<148, 512>>>(out, iters, cyc); cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("4 warps/SMSP, 8 chains, 2 A x 4 B fragments: %.1f cycles per HMMA per SMSP\n", (double)c / iters / 8 / 4);
+        hmma_loop_var<8, 1, 8><<<148, 512>>>(out, iters, cyc); cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("4 warps/SMSP, 8 chains, 1 A x 8 B fragments: %.1f cycles per HMMA per SMSP\n", (double)c / iters / 8 / 4);
+        hmma_loop_var<8, 8, 1><<<148, 512>>>(out, iters, cyc); cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("4 warps/SMSP, 8 chains, 8 A x 1 B fragments: %.1f cycles per HMMA per SMSP\n", (double)c / iters / 8 / 4);
+        hmma_loop_var<8, 4, 2><<<148, 128>>>(out, iters, cyc); cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("1 warp/SMSP,  8 chains, 4 A x 2 B fragments: %.1f cycles per HMMA per SMSP\n", (double)c / iters / 8);
     }
     const int NACC = 12;
     for (int warps = 4; warps <= 32; warps *= 2) {
