@@ -1,0 +1,111 @@
+// Feeders of the InfoNCE kernels: one pass that stacks the two views, applies the label-sort permutation and runs the
+// reference's `is_normalized` assertion on the device; and its adjoint (scatter of dZ back to the two views).
+// Reference: contrastyou/losses/contrastive.py:9-11 (is_normalized: allclose(norm, 1) evaluated in the input dtype),
+// :15 (torch.cat of the two views), :58 (the assertion).  The permutation is this implementation's own (rows sorted by
+// label so that the tensor-core kernels take their mask-free inner loop; the loss is permutation invariant).
+#include "common.cuh"
+
+namespace cy {
+
+namespace {
+
+__device__ __forceinline__ float round_to_dtype(float v, int dtype) {
+    if (dtype == CY_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+    if (dtype == CY_F16) return __half2float(__float2half_rn(v));
+    return v;
+}
+
+// one warp per output row; 16-byte accesses when the row pitch allows it
+template <int ESIZE>
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const uint8_t* __restrict__ f1, const uint8_t* __restrict__ f2, int dtype, int64_t n, int64_t d,
+                 int64_t ld1, int64_t ld2, const int64_t* __restrict__ order, uint8_t* __restrict__ z, int* __restrict__ bad_rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= 2 * n) return;
+    const int64_t src = order ? order[row] : row;
+    const uint8_t* s = src < n ? f1 + src * ld1 * ESIZE : f2 + (src - n) * ld2 * ESIZE;
+    uint8_t* o = z + row * d * ESIZE;
+    const bool vec = ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(o)) & 15) == 0 && (d * ESIZE) % 16 == 0;
+    float ss = 0.f;
+    if (vec) {
+        constexpr int PER = 16 / ESIZE;
+        for (int64_t c = lane; c < d / PER; c += 32) {
+            const uint4 v = *reinterpret_cast<const uint4*>(s + c * 16);
+            *reinterpret_cast<uint4*>(o + c * 16) = v;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (ESIZE == 4) {
+                    const float a = __uint_as_float(w[k]);
+                    ss = fmaf(a, a, ss);
+                } else if (dtype == CY_BF16) {
+                    const float a = __uint_as_float(w[k] << 16), b = __uint_as_float(w[k] & 0xffff0000u);
+                    ss = fmaf(a, a, ss);
+                    ss = fmaf(b, b, ss);
+                } else {
+                    const __half2 h = *reinterpret_cast<const __half2*>(&w[k]);
+                    const float2 f = __half22float2(h);
+                    ss = fmaf(f.x, f.x, ss);
+                    ss = fmaf(f.y, f.y, ss);
+                }
+            }
+        }
+    } else {
+        for (int64_t c = lane; c < d; c += 32) {
+            const float a = ld_as_float(s, dtype, c);
+            st_from_float(o, dtype, c, a);
+            ss = fmaf(a, a, ss);
+        }
+    }
+    ss = warp_sum(ss);
+    if (lane == 0 && bad_rows) {
+        // torch: norm accumulated in fp32, rounded to the tensor dtype; allclose(norm, 1): |norm - 1| <= 1e-8 + 1e-5 * 1
+        const float nrm = round_to_dtype(sqrtf(ss), dtype);
+        if (!(fabsf(nrm - 1.f) <= 1e-8f + 1e-5f)) atomicAdd(bad_rows, 1);
+    }
+}
+
+template <int ESIZE>
+__global__ void __launch_bounds__(256)
+unpack_rows_kernel(const uint8_t* __restrict__ dz, int64_t n, int64_t d, int64_t lddz, const int64_t* __restrict__ order,
+                   uint8_t* __restrict__ g1, uint8_t* __restrict__ g2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= 2 * n) return;
+    const int64_t dst = order ? order[row] : row;
+    const uint8_t* s = dz + row * lddz * ESIZE;
+    uint8_t* o = dst < n ? g1 + dst * d * ESIZE : g2 + (dst - n) * d * ESIZE;
+    const bool vec = ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(o)) & 15) == 0 && (d * ESIZE) % 16 == 0;
+    if (vec) {
+        for (int64_t c = lane; c < d * ESIZE / 16; c += 32) *reinterpret_cast<uint4*>(o + c * 16) = *reinterpret_cast<const uint4*>(s + c * 16);
+    } else {
+        for (int64_t c = lane; c < d * ESIZE; c += 32) o[c] = s[c];
+    }
+}
+
+}  // namespace
+
+int infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_t d, int64_t ld1, int64_t ld2, const int64_t* order,
+                 void* z, int* bad_rows, cudaStream_t st) {
+    const unsigned grid = (unsigned)((2 * n + 7) / 8);
+    if (dtype == CY_F32)
+        pack_rows_kernel<4><<<grid, 256, 0, st>>>((const uint8_t*)f1, (const uint8_t*)f2, dtype, n, d, ld1, ld2, order, (uint8_t*)z, bad_rows);
+    else
+        pack_rows_kernel<2><<<grid, 256, 0, st>>>((const uint8_t*)f1, (const uint8_t*)f2, dtype, n, d, ld1, ld2, order, (uint8_t*)z, bad_rows);
+    CY_CHECK_LAUNCH("infonce_pack");
+    return CY_OK;
+}
+
+int infonce_unpack(const void* dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* order, void* g1, void* g2,
+                   cudaStream_t st) {
+    const unsigned grid = (unsigned)((2 * n + 7) / 8);
+    if (dtype == CY_F32)
+        unpack_rows_kernel<4><<<grid, 256, 0, st>>>((const uint8_t*)dz, n, d, lddz, order, (uint8_t*)g1, (uint8_t*)g2);
+    else
+        unpack_rows_kernel<2><<<grid, 256, 0, st>>>((const uint8_t*)dz, n, d, lddz, order, (uint8_t*)g1, (uint8_t*)g2);
+    CY_CHECK_LAUNCH("infonce_unpack");
+    return CY_OK;
+}
+
+}  // namespace cy

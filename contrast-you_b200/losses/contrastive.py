@@ -112,6 +112,40 @@ class _InfoNCEFunction(torch.autograd.Function):
         return dz, None, None, None, None, None, None, None, None, None
 
 
+class _PackViews(torch.autograd.Function):
+    """(proj_feat1, proj_feat2) -> z [2n, d]: ``torch.cat`` of the two views (contrastive.py:15) with the rows taken in
+    ``order`` (a permutation of 0..2n-1 or None) and the ``is_normalized`` assertion (:9-11, :58) evaluated on the device
+    in the same pass (``bad`` counts the offending rows; the module reads it together with the NaN check, one host sync
+    per forward instead of three).  Backward scatters dz to the two views."""
+
+    @staticmethod
+    def forward(ctx, f1, f2, order, check):
+        lib = L.lib()
+        n, d = f1.shape
+        z = torch.empty(2 * n, d, dtype=f1.dtype, device=f1.device)
+        bad = torch.zeros(1, dtype=torch.int32, device=f1.device) if check else None
+        L.check(lib.cy_infonce_pack(f1.data_ptr(), f2.data_ptr(), L.dtype_code(f1), n, d, f1.stride(0), f2.stride(0),
+                                    L.ptr(order), z.data_ptr(), L.ptr(bad), L.stream_ptr(f1.device)), "cy_infonce_pack")
+        ctx.order = order
+        ctx.shape = (n, d)
+        if bad is None:
+            bad = torch.zeros(0, dtype=torch.int32, device=f1.device)
+        ctx.mark_non_differentiable(bad)
+        return z, bad
+
+    @staticmethod
+    def backward(ctx, dz, _grad_bad):
+        lib = L.lib()
+        n, d = ctx.shape
+        if dz.stride(1) != 1:
+            dz = dz.contiguous()
+        g1 = torch.empty(n, d, dtype=dz.dtype, device=dz.device)
+        g2 = torch.empty(n, d, dtype=dz.dtype, device=dz.device)
+        L.check(lib.cy_infonce_unpack(dz.data_ptr(), L.dtype_code(dz), n, d, dz.stride(0), L.ptr(ctx.order), g1.data_ptr(),
+                                      g2.data_ptr(), L.stream_ptr(dz.device)), "cy_infonce_unpack")
+        return g1, g2, None, None
+
+
 def tensor_core_eligible(z: Tensor, labels, codes, variant: int, path: int) -> bool:
     """mirror of the C-side dispatch (c_abi.cu resolve_path): does this call run on the tcgen05 kernels?"""
     N, d = z.shape
@@ -154,7 +188,7 @@ def info_nce(z: Tensor, labels: Optional[Tensor], codes: Optional[Tensor], tempe
 class _ContrastBase(nn.Module):
     _variant = L.CY_SUPCON
 
-    def _prepare(self, proj_feat1, proj_feat2, target, mask):
+    def _prepare(self, proj_feat1, proj_feat2, target, mask, sort=False):
         L.require_cuda(proj_feat1, proj_feat2)
         batch_size = proj_feat1.size(0)
         device = proj_feat2.device
@@ -166,21 +200,46 @@ class _ContrastBase(nn.Module):
             labels = _canonical_labels(target, batch_size, device)
         else:  # SimCLR: only the twin view is positive
             labels = torch.arange(batch_size, dtype=torch.int32, device=device).repeat(2)
-        assert is_normalized(proj_feat1) and is_normalized(proj_feat2), f"features need to be normalized first"
         assert proj_feat1.shape == proj_feat2.shape, (proj_feat1.shape, proj_feat2.shape)
-        z = torch.cat([proj_feat1, proj_feat2], dim=0)
+        self._views = (proj_feat1.detach(), proj_feat2.detach(), labels, codes)      # lazy side channels (original row order)
+        self._dbg_cache = {}
+        fused = (proj_feat1.dim() == 2 and proj_feat1.dtype == proj_feat2.dtype and proj_feat1.device == proj_feat2.device
+                 and proj_feat1.dtype in (torch.float32, torch.bfloat16, torch.float16))
+        if not fused:
+            assert is_normalized(proj_feat1) and is_normalized(proj_feat2), f"features need to be normalized first"
+            self._bad = None
+            return torch.cat([proj_feat1, proj_feat2], dim=0), labels, codes
+        f1 = proj_feat1 if proj_feat1.stride(1) == 1 else proj_feat1.contiguous()
+        f2 = proj_feat2 if proj_feat2.stride(1) == 1 else proj_feat2.contiguous()
+        order = None
+        if sort and codes is None and self._sorts_rows(f1, labels):
+            order = torch.argsort(labels)          # equal labels adjacent: the loss is invariant under row permutations
+            labels = labels.index_select(0, order)
+        z, bad = _PackViews.apply(f1, f2, order, __debug__)
+        self._bad = bad if __debug__ else None
         return z, labels, codes
 
-    # ---- lazily evaluated side channels (contrastive.py:79-82; read at semi_seg/hooks/infonce.py:235-242) ----
-    def _stash(self, z, labels, codes):
-        self._dbg = (z.detach(), labels, codes)
-        self._dbg_cache = {}
+    def _sorts_rows(self, f1, labels) -> bool:
+        return False
 
+    def _host_checks(self, loss: Tensor):
+        """the reference's two assertions / errors in ONE device->host read: un-normalised rows (contrastive.py:58,
+        AssertionError) and a NaN loss (:98-99, RuntimeError(loss))."""
+        if self._bad is not None:
+            bad, val = torch.stack((self._bad[0].to(torch.float32), loss.detach().to(torch.float32))).tolist()
+            assert bad == 0, f"features need to be normalized first"
+        else:
+            val = loss.item()
+        if val != val:
+            raise RuntimeError(loss)
+
+    # ---- lazily evaluated side channels (contrastive.py:79-82; read at semi_seg/hooks/infonce.py:235-242) ----
     def _dense(self, name):
-        if not hasattr(self, "_dbg"):
+        if not hasattr(self, "_views"):
             raise AttributeError(name)
         if name not in self._dbg_cache:
-            z, labels, codes = self._dbg
+            f1, f2, labels, codes = self._views
+            z = torch.cat([f1, f2], dim=0)
             N = z.shape[0]
             if name in ("pos_mask", "neg_mask"):
                 pos = torch.empty(N, N, dtype=torch.float32, device=z.device)
@@ -211,13 +270,18 @@ class SupConLoss1(_ContrastBase):
         self._path = {"auto": L.CY_PATH_AUTO, "simt": L.CY_PATH_SIMT, "tcgen05": L.CY_PATH_TCGEN05}[path]
 
     def forward(self, proj_feat1, proj_feat2, target=None, mask: Tensor = None, **kwargs):
-        z, labels, codes = self._prepare(proj_feat1, proj_feat2, target, mask)
+        z, labels, codes = self._prepare(proj_feat1, proj_feat2, target, mask, sort=True)
         variant = L.CY_SUPCON_EXCLUDE if self._exclude_pos else L.CY_SUPCON
-        loss, _ = info_nce(z, labels, codes, self._t, variant, path=self._path, sort_rows=True)
-        self._stash(z, labels, codes)
-        if torch.isnan(loss):
-            raise RuntimeError(loss)
+        loss, _ = info_nce(z, labels, codes, self._t, variant, path=self._path, sort_rows=False)
+        self._host_checks(loss)
         return loss
+
+    def _sorts_rows(self, f1, labels) -> bool:
+        n, d = f1.shape
+        variant = L.CY_SUPCON_EXCLUDE if self._exclude_pos else L.CY_SUPCON
+        ok = (f1.dtype in (torch.bfloat16, torch.float16) and d == 256 and (2 * n) % 128 == 0 and 2 * n >= 256
+              and variant == L.CY_SUPCON)
+        return ok and (self._path == L.CY_PATH_TCGEN05 or (self._path == L.CY_PATH_AUTO and 2 * n >= 1024))
 
 
 class SelfPacedSupConLoss(_ContrastBase):
@@ -237,14 +301,12 @@ class SelfPacedSupConLoss(_ContrastBase):
         z, labels, codes = self._prepare(proj_feat1, proj_feat2, target, mask)
         variant = L.CY_SELFPACED_HARD if self._weight_update == "hard" else L.CY_SELFPACED_SOFT
         loss, out4 = info_nce(z, labels, codes, self._t, variant, gamma=self.__gamma, path=L.CY_PATH_SIMT)
-        self._stash(z, labels, codes)
         # contrastive.py:179-181 — a python float (host sync, as in the reference)
         self.downgrade_ratio = (out4[1] / out4[2]).item()
         if self._correct_grad:
             if self.downgrade_ratio > 0:
                 loss = loss / self.downgrade_ratio
-        if torch.isnan(loss):
-            raise RuntimeError(loss)
+        self._host_checks(loss)
         return loss
 
     @property

@@ -123,6 +123,20 @@ int cy_infonce_masks(int64_t N, const int32_t* labels, const uint8_t* codes, flo
  * never equal), 1 = int32 (copied).  Writes dst[0:n] and dst[n:2n] (tiling over the two views). */
 int cy_labels_canonicalize(const void* src, int src_kind, int64_t n, int32_t* dst, void* stream);
 
+/* Feeder of cy_infonce_fwd: stacks the two views into z [2n, d] (contiguous), z[i] = source row order[i] of
+ * cat(f1, f2) (contrastive.py:15; `order` = a permutation of 0..2n-1 as int64, or NULL for the identity — the modules
+ * pass the label sort so that equal labels are adjacent), and runs the reference's `is_normalized` assertion
+ * (contrastive.py:9-11, :58) on the device: *bad_rows is incremented once per source row whose L2 norm, rounded to the
+ * element type like torch's `norm`, is not within 1e-8 + 1e-5 of 1.  ld1 / ld2: row pitches of f1 / f2 in elements.
+ * bad_rows may be NULL (python -O: the reference's assert is stripped too). */
+int cy_infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_t d, int64_t ld1, int64_t ld2,
+                    const int64_t* order, void* z, int32_t* bad_rows, void* stream);
+
+/* Adjoint of cy_infonce_pack: scatters dz [2n, d] (row pitch lddz) back to the two views, g(order[i]) = dz[i];
+ * g1, g2 are contiguous [n, d]. */
+int cy_infonce_unpack(const void* dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* order, void* g1,
+                      void* g2, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * IIC discrete-MI segmentation loss.  Replaces compute_joint_2D / compute_joint_2D_with_padding_zeros
  * (contrastyou/losses/discreteMI.py:225-261), IIDSegmentationLoss.forward (:139-165) and their autograd backward.
