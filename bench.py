@@ -112,6 +112,15 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
+def ncu_traffic():
+    """DRAM bytes per launch measured by ncu (profiles/r1_traffic.json, exported from the committed --set full captures)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
 def cpu_supcon_baseline(steps=1, warmup=0, seed=0):
     """the C/OpenMP port of SupConLoss1 (oracle/oracle.c, float32 dot products like the reference's fp32 torch.mm) on
     every host core, on a bounded sample: N=8192, d=256 (the reference itself cannot hold more: ~13 N x N fp32)."""
@@ -325,8 +334,12 @@ def main():
     fwd_tf = 2.0 * rows * N * d / (fwd_ms * 1e-3) / 1e12
     bwd_tf = 4.0 * rows * N * d / (bwd_ms * 1e-3) / 1e12
     peak_tf = peaks["bf16_tflops"]
+    traffic = ncu_traffic()
     roofline = {"bound": "tensor", "kernel": "cy_infonce_bwd (recompute S tile + W.Z, 4*rows*N*d FLOP per launch)",
-                "achieved": bwd_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": bwd_tf / peak_tf, "traffic": None,
+                "achieved": bwd_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": bwd_tf / peak_tf,
+                # DRAM bytes per launch from the committed ncu capture of this exact workload (1 GPU, N=65536)
+                "traffic": traffic.get("infonce_bwd_tc_kernel<0> N=65536 d=256 bf16", {}).get("bytes")
+                if (world == 1 and N == 65536 and path != 1) else None,
                 "peak_source": peaks["source"] + " bf16 burst",
                 "fwd": {"kernel": "cy_infonce_fwd (2*rows*N*d FLOP)", "ms": fwd_ms, "achieved": fwd_tf, "frac": fwd_tf / peak_tf},
                 "bwd_ms": bwd_ms,
@@ -340,7 +353,9 @@ def main():
                    "parallelism": f"rows{world}" if world > 1 else "single",
                    "l2": "256 MiB buffer written between timed iterations (inputs are smaller than L2)"},
         "e2e": e2e, "roofline": roofline, "clocks": clocks,
-        "gpu_launches": (4 * K_),      # per step: cy_labels_canonicalize, cy_infonce_fwd, cy_infonce_finalize, cy_infonce_bwd
+        # kernels of libcontrastyou_b200.so per step: labels_canonicalize, pack_rows, infonce_fwd_tc + tc_reduce,
+        # infonce_finalize, infonce_bwd_tc + tc_convert, unpack_rows (single GPU; the sharded step has no pack / unpack)
+        "gpu_launches": ((8 if world == 1 else 6) * K_),
     }
 
     # ---- IIC leg (config 3); weak scaling over the batch for world > 1
@@ -382,7 +397,9 @@ def main():
             "e2e": {"value": px / (iic_e2e_ms * 1e-3), "unit": "pixels/s", "h2d_bytes_per_step": bytes_map, "d2h_bytes_per_step": 4},
             "roofline": {"bound": "hbm", "kernel": "cy_iic_joint + cy_iic_bwd (3 x 2*B*K*H*W*4 B algorithmic)",
                          "achieved": gbs(3 * bytes_map, j_ms + b_ms), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": gbs(3 * bytes_map, j_ms + b_ms) / peaks["hbm_gbs"], "traffic": None,
+                         "frac": gbs(3 * bytes_map, j_ms + b_ms) / peaks["hbm_gbs"],
+                         "traffic": (traffic.get("iic_joint_mma_kernel<2,4,1,2> cfg3", {}).get("bytes", 0)
+                                     + traffic.get("iic_bwd_mma_kernel<32,2> cfg3", {}).get("bytes", 0)) or None,
                          "joint": {"ms": j_ms, "achieved": gbs(bytes_map, j_ms), "frac": gbs(bytes_map, j_ms) / peaks["hbm_gbs"]},
                          "bwd": {"ms": b_ms, "achieved": gbs(2 * bytes_map, b_ms), "frac": gbs(2 * bytes_map, b_ms) / peaks["hbm_gbs"]},
                          "peak_source": peaks["source"] + " copy bandwidth"},
