@@ -101,9 +101,74 @@ def make_joint_reduce(group=None):
     return reduce
 
 
+class _ShardedInfoNCE(torch.autograd.Function):
+    """z_loc [2*n_loc, d] (this rank's stacked views, rows already in their final order) -> (loss, out4).
+
+    forward : all-gather z (rank-major), forward strip of the owned rows, ONE all-gather that carries the four row-statistic
+              vectors of the strip plus the four partial scalars of every rank.
+    backward: one backward strip -> the complete gradient of the owned rows, written straight into a [2*n_loc, d]
+              buffer (no N x d zero fill, no gradient collective)."""
+
+    @staticmethod
+    def forward(ctx, z_loc, labels_all, inv_t, path, group):
+        lib = L.lib()
+        world, rank = _ws(group)
+        rows_loc, d = z_loc.shape
+        N = world * rows_loc
+        rb, re = rank * rows_loc, (rank + 1) * rows_loc
+        dev = z_loc.device
+        dt = L.dtype_code(z_loc)
+        st = L.stream_ptr(dev)
+        z_all = torch.empty(N, d, dtype=z_loc.dtype, device=dev)
+        dist.all_gather_into_tensor(z_all, z_loc.contiguous(), group=group)
+        stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev)
+        out4 = torch.zeros(4, dtype=torch.float32, device=dev)
+        ws_bytes = lib.cy_infonce_workspace_bytes(N, d, dt, L.CY_SUPCON, path)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        L.check(lib.cy_infonce_fwd(z_all.data_ptr(), dt, N, d, d, labels_all.data_ptr(), None, rb, re, inv_t, L.CY_SUPCON, path,
+                                   stats.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd")
+        L.check(lib.cy_infonce_finalize(N, rb, re, inv_t, L.CY_SUPCON, 1, stats.data_ptr(), out4.data_ptr(), st),
+                "cy_infonce_finalize")
+        # exchange: [4 stat rows of the strip | 4 scalars] per rank, one collective
+        rows4 = list(_STAT_ROWS)
+        send = torch.cat([stats[rows4, rb:re].reshape(-1), out4])
+        recv = torch.empty(world, send.numel(), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        stats[rows4] = recv[:, :4 * rows_loc].view(world, 4, rows_loc).permute(1, 0, 2).reshape(4, N)
+        out4 = recv[:, 4 * rows_loc:].sum(dim=0)
+        ctx.save_for_backward(z_all, labels_all, stats, ws)
+        ctx.cfg = (inv_t, path, rb, re)
+        ctx.mark_non_differentiable(out4)
+        return out4[0].clone(), out4
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_out4):
+        lib = L.lib()
+        z_all, labels_all, stats, ws = ctx.saved_tensors
+        inv_t, path, rb, re = ctx.cfg
+        N, d = z_all.shape
+        gscale = grad_loss
+        if gscale.dtype != torch.float32 or gscale.numel() != 1 or not gscale.is_contiguous():
+            gscale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        dz_loc = torch.empty(re - rb, d, dtype=z_all.dtype, device=z_all.device)
+        # the kernels index dz by GLOBAL row: hand them the address row rb would have in a full [N, d] gradient
+        dz_base = dz_loc.data_ptr() - rb * d * dz_loc.element_size()
+        L.check(lib.cy_infonce_bwd(z_all.data_ptr(), L.dtype_code(z_all), N, d, d, labels_all.data_ptr(), None, rb, re, inv_t,
+                                   L.CY_SUPCON, 0.0, path, stats.data_ptr(), gscale.data_ptr(), dz_base, d, ws.data_ptr(),
+                                   ws.numel(), L.stream_ptr(z_all.device)), "cy_infonce_bwd")
+        return dz_loc, None, None, None, None
+
+
+_STAT_ROWS = (L.CY_STAT_LOGDEN, L.CY_STAT_INVC, L.CY_STAT_COEF, L.CY_STAT_AUX)
+
+
 class ShardedSupConLoss(torch.nn.Module):
     """Global-batch SupConLoss1 over all ranks of ``group`` (label / SimCLR masks).  Same forward signature as the
-    single-process module; every rank passes its local views and labels."""
+    single-process module; every rank passes its local views and labels.
+
+    Per step and rank: canonical labels of all ranks (one tiny all-gather), a LOCAL sort of the owned rows by label
+    (the loss is invariant under row permutations inside a rank's block; the other ranks' blocks arrive sorted), one
+    pack kernel (cat + permutation + is_normalized), then ``_ShardedInfoNCE`` (two more collectives)."""
 
     def __init__(self, temperature=0.07, *, group=None, grad_scale: float = 1.0, path: str = "auto"):
         super().__init__()
@@ -113,13 +178,16 @@ class ShardedSupConLoss(torch.nn.Module):
         self._path = {"auto": L.CY_PATH_AUTO, "simt": L.CY_PATH_SIMT, "tcgen05": L.CY_PATH_TCGEN05}[path]
 
     def forward(self, proj_feat1: Tensor, proj_feat2: Tensor, target=None, mask: Optional[Tensor] = None, **kwargs):
-        from .losses.contrastive import info_nce, _canonical_labels, is_normalized, sort_rows_by_label, tensor_core_eligible
+        from .losses.contrastive import _canonical_labels, _PackViews
         if mask is not None:
             raise NotImplementedError("the sharded loss derives masks from labels (explicit [n,n] masks are per-process)")
-        assert is_normalized(proj_feat1) and is_normalized(proj_feat2), f"features need to be normalized first"
+        L.require_cuda(proj_feat1, proj_feat2)
         assert proj_feat1.shape == proj_feat2.shape, (proj_feat1.shape, proj_feat2.shape)
+        assert proj_feat1.dim() == 2 and proj_feat1.dtype == proj_feat2.dtype
         world, rank = _ws(self._group)
-        n_local = proj_feat1.shape[0]
+        n_local, d = proj_feat1.shape
+        rows_loc = 2 * n_local
+        N = world * rows_loc
         device = proj_feat1.device
         if target is None:      # SimCLR: globally unique ids
             raw = torch.arange(rank * n_local, (rank + 1) * n_local, dtype=torch.int32, device=device)
@@ -129,15 +197,24 @@ class ShardedSupConLoss(torch.nn.Module):
             raw = target.to(device)
         raw_all = torch.empty(world * n_local, dtype=raw.dtype, device=device)
         dist.all_gather_into_tensor(raw_all, raw.contiguous(), group=self._group)
-        labels = rank_major_labels(raw_all, world, lambda r, n: _canonical_labels(r, n, device))
-        z_all = gather_rank_major(torch.cat([proj_feat1, proj_feat2], dim=0), self._group)
-        if tensor_core_eligible(z_all, labels, None, L.CY_SUPCON, self._path):
-            # sort every rank's row block by label (ownership of rows is unchanged): see sort_rows_by_label
-            for r in range(world):
-                z_all, labels = sort_rows_by_label(z_all, labels, r * 2 * n_local, (r + 1) * 2 * n_local)
-        loss, _ = info_nce(z_all, labels, None, self._t, L.CY_SUPCON, path=self._path, rows=row_range(n_local, self._group),
-                           gather_stats=make_stats_exchange(n_local, self._group))
-        if torch.isnan(loss):
+        labels_all = rank_major_labels(raw_all, world, lambda r, n: _canonical_labels(r, n, device))      # [N]
+        order = None
+        tc = (proj_feat1.dtype in (torch.bfloat16, torch.float16) and d == 256 and rows_loc % 128 == 0 and N >= 256
+              and (self._path == L.CY_PATH_TCGEN05 or (self._path == L.CY_PATH_AUTO and N >= 1024)))
+        if tc:      # sort every rank's block by label; the permutation is needed for the owned block only
+            sorted_blocks, perm = labels_all.view(world, rows_loc).sort(dim=1)
+            order = perm[rank]
+            labels_all = sorted_blocks.reshape(-1)
+        f1 = proj_feat1 if proj_feat1.stride(1) == 1 else proj_feat1.contiguous()
+        f2 = proj_feat2 if proj_feat2.stride(1) == 1 else proj_feat2.contiguous()
+        z_loc, bad = _PackViews.apply(f1, f2, order, __debug__)
+        loss, _ = _ShardedInfoNCE.apply(z_loc, labels_all, float(1.0 / self._t), self._path, self._group)
+        if __debug__:
+            nbad, val = torch.stack((bad[0].to(torch.float32), loss.detach())).tolist()
+            assert nbad == 0, f"features need to be normalized first"
+        else:
+            val = loss.item()
+        if val != val:
             raise RuntimeError(loss)
         return loss * self._grad_scale if self._grad_scale != 1.0 else loss
 
