@@ -161,6 +161,56 @@ def iid_case(name, bn, K, seed, lamb=1.0):
     print(f"{name}: loss={loss.item()!r}")
 
 
+def sibling_cases():
+    """losses that reuse the IIC joint with a different epilogue: RedundancyCriterion
+    (redundancy_reduction.py:12-33), PUISegLoss (pica_loss.py:43-80), IMSATLoss / IMSATDynamicWeight / imsat_loss
+    (discreteMI.py:20-87, 275-297)."""
+    from contrastyou.losses.redundancy_reduction import RedundancyCriterion
+    from contrastyou.losses.pica_loss import PUISegLoss
+    from contrastyou.losses.discreteMI import IMSATLoss, IMSATDynamicWeight
+
+    def maps(B, K, H, W, seed):
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(B, K, H, W, dtype=torch.float64, generator=g).softmax(1).requires_grad_()
+        y = torch.randn(B, K, H, W, dtype=torch.float64, generator=g).softmax(1).requires_grad_()
+        return x, y
+
+    for name, sym, alpha, lamda in (("redundancy_sym", True, 0.3, 1.0), ("redundancy_asym", False, 0.7, 2.0)):
+        x, y = maps(2, 6, 16, 16, 40)
+        crit = RedundancyCriterion(symmetric=sym, lamda=lamda, alpha=alpha)
+        loss = crit(x, y)
+        loss.backward()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), x=_np(x), y=_np(y), loss=_np(loss), grad_x=_np(x.grad),
+                            grad_y=_np(y.grad), joint=crit.get_joint_matrix(), symmetric=np.bool_(sym), alpha=np.float64(alpha),
+                            lamda=np.float64(lamda))
+        print(f"{name}: loss={loss.item()!r}")
+    for name, pad, lamda in (("puiseg_pad1", 1, 2.0), ("puiseg_pad3", 3, 0.5)):
+        x, y = maps(2, 5, 14, 18, 41)
+        loss = PUISegLoss(lamda=lamda, padding=pad)(x, y)
+        loss.backward()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), x=_np(x), y=_np(y), loss=_np(loss), grad_x=_np(x.grad),
+                            grad_y=_np(y.grad), padding=np.int64(pad), lamda=np.float64(lamda))
+        print(f"{name}: loss={loss.item()!r}")
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(16, 5, dtype=torch.float64, generator=g).softmax(1).requires_grad_()
+    y = torch.randn(16, 5, dtype=torch.float64, generator=g).softmax(1).requires_grad_()
+    l2 = IMSATLoss(lamda=1.5)(x, y)
+    l2.backward()
+    gx2, gy2 = _np(x.grad).copy(), _np(y.grad).copy()
+    x.grad = None
+    l1 = IMSATLoss(lamda=1.5)(x)
+    l1.backward()
+    gx1 = _np(x.grad).copy()
+    x.grad = None
+    dyn = IMSATDynamicWeight(lamda=0.8)
+    ld = dyn(x)
+    ld.backward()
+    np.savez_compressed(os.path.join(HERE, "imsat.npz"), x=_np(x), y=_np(y), loss_pair=_np(l2), grad_x_pair=gx2, grad_y_pair=gy2,
+                        loss_single=_np(l1), grad_x_single=gx1, loss_dynamic=_np(ld), grad_x_dynamic=_np(x.grad),
+                        dynamic_weight_after=_np(dyn.dynamic_weight), lamda=np.float64(1.5), lamda_dynamic=np.float64(0.8))
+    print(f"imsat: pair={l2.item()!r} single={l1.item()!r} dynamic={ld.item()!r}")
+
+
 def _exec_defs(relpath, names, ns):
     """exec selected top-level defs of a reference source file (its module cannot be imported here because of
     absent third-party packages); the code object is the reference's own, nothing is restated."""
@@ -318,6 +368,7 @@ def main():
         # --- IIDLoss (discreteMI.py:90-124, 201-222)
         iid_case("iid_k20", 18, 20, 30)
         iid_case("iid_k5_lam2", 7, 5, 31, lamb=2.0)
+        sibling_cases()
         label_cases()
         region_cases()
         head_cases()

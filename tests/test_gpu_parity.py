@@ -415,3 +415,76 @@ def test_tcgen05_row_sharded_equals_whole():
         assert float(zs.grad[:rb].abs().sum() + zs.grad[re:].abs().sum()) == 0.0
     assert sum(parts) == pytest.approx(loss.item(), rel=1e-5)
     assert _relerr(grads.float().cpu().numpy(), zf.grad.float().cpu().numpy()) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ sibling losses
+from contrast_you_b200.losses import RedundancyCriterion, PUISegLoss     # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["redundancy_sym", "redundancy_asym"])
+def test_redundancy_golden(name):
+    g = load_golden(name)
+    x, y = _t(g["x"], grad=True), _t(g["y"], grad=True)
+    crit = RedundancyCriterion(symmetric=bool(g["symmetric"]), lamda=float(g["lamda"]), alpha=float(g["alpha"]))
+    loss = crit(x, y)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= FP32_TOL * max(abs(float(g["loss"])), 1e-2)
+    np.testing.assert_allclose(crit.get_joint_matrix(), g["joint"], rtol=FP32_TOL)
+    assert _relerr(x.grad.cpu().numpy(), g["grad_x"]) <= FP32_TOL
+    assert _relerr(y.grad.cpu().numpy(), g["grad_y"]) <= FP32_TOL
+
+
+@pytest.mark.parametrize("name", ["puiseg_pad1", "puiseg_pad3"])
+def test_puiseg_golden(name):
+    g = load_golden(name)
+    x, y = _t(g["x"], grad=True), _t(g["y"], grad=True)
+    loss = PUISegLoss(lamda=float(g["lamda"]), padding=int(g["padding"]))(x, y)
+    loss.backward()
+    assert loss.item() == pytest.approx(float(g["loss"]), rel=FP32_TOL)
+    assert _relerr(x.grad.cpu().numpy(), g["grad_x"]) <= FP32_TOL
+    assert _relerr(y.grad.cpu().numpy(), g["grad_y"]) <= FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------------ tensor-pipe IIC shapes
+@pytest.mark.parametrize("B,K,H,W,pad", [(3, 13, 50, 72, 1), (2, 4, 33, 128, 1), (2, 16, 40, 64, 1), (1, 10, 9, 32, 1),
+                                          (2, 10, 30, 44, 2), (2, 5, 23, 36, 3), (1, 20, 40, 40, 1)])
+def test_iic_tensor_pipe_shapes_vs_c_oracle(B, K, H, W, pad):
+    """shapes that take csrc/iic_mma.cu (fp32, W % 4 == 0): ragged tiles in both directions, every k-step count of the
+    adjoint (K <= 5, <= 10, <= 16), the split-over-two-warps forward (K*T > 32), paddings 2 and 3 (forward only)"""
+    torch.manual_seed(B * 100 + K)
+    x = (2 * torch.randn(B, K, H, W, device=DEV)).softmax(1).requires_grad_()
+    y = (2 * torch.randn(B, K, H, W, device=DEV)).softmax(1).requires_grad_()
+    J = raw_joint(x, y, pad)
+    Jo = c_oracle.iic_raw_joint(x.detach().cpu().numpy(), y.detach().cpu().numpy(), pad, prec=1)
+    assert _relerr(J.detach().cpu().numpy(), Jo) <= 2e-5
+    gJ = torch.randn_like(J)
+    (J * gJ).sum().backward()
+    gx, gy = OM.input_grads(x.detach().cpu().double().numpy(), y.detach().cpu().double().numpy(),
+                            gJ.cpu().double().numpy(), pad)
+    assert _relerr(x.grad.cpu().numpy(), gx) <= 3e-5
+    assert _relerr(y.grad.cpu().numpy(), gy) <= 3e-5
+
+
+# ------------------------------------------------------------------------------------------------ pack feeder
+def test_pack_feeder_strided_views_and_unnormalised_rows():
+    """the modules take views produced by torch.chunk (row pitch > d) and must raise the reference's AssertionError
+    for un-normalised features (contrastive.py:58) through the device-side counter"""
+    torch.manual_seed(3)
+    big = torch.nn.functional.normalize(torch.randn(64, 2, 32, device=DEV), dim=2)
+    f1, f2 = big[:, 0, :], big[:, 1, :]                      # row pitch 64 elements
+    assert f1.stride(0) == 64
+    a, b = f1.detach().clone().requires_grad_(), f2.detach().clone().requires_grad_()
+    lab = torch.randint(0, 4, (64,)).tolist()
+    l_ref = SupConLoss1()(a, b, target=lab)
+    l_ref.backward()
+    f1s, f2s = f1.detach().requires_grad_(), f2.detach().requires_grad_()
+    l = SupConLoss1()(f1s[:], f2s[:], target=lab)
+    l.backward()
+    assert l.item() == pytest.approx(l_ref.item(), rel=1e-6)
+    np.testing.assert_allclose(f1s.grad.cpu().numpy(), a.grad.cpu().numpy(), rtol=1e-5, atol=1e-8)
+    with pytest.raises(AssertionError):
+        SupConLoss1()(f1 * 1.01, f2, target=lab)
+    bf = torch.nn.functional.normalize(torch.randn(256, 256, device=DEV), dim=1).to(torch.bfloat16)
+    SupConLoss1()(bf[:128], bf[128:], target=list(range(128)))          # bf16 unit rows pass, as in the reference
+    with pytest.raises(AssertionError):
+        SupConLoss1()(bf[:128] * 1.02, bf[128:], target=list(range(128)))

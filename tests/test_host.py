@@ -112,3 +112,32 @@ def test_projector_heads_golden(name):
     outs = out if isinstance(out, list) else [out]
     for i, o in enumerate(outs):
         np.testing.assert_allclose(o.detach().numpy(), g[f"out{i}"], rtol=1e-10, atol=1e-12)
+
+
+def test_imsat_losses_match_reference_fixture():
+    """IMSATLoss / IMSATDynamicWeight (discreteMI.py:20-87, :275-297): pure host-side mirrors, checked on CPU in float64"""
+    import numpy as np
+    import torch
+    from conftest import load_golden
+    from contrast_you_b200.losses import IMSATLoss, IMSATDynamicWeight
+    g = load_golden("imsat")
+    x = torch.tensor(g["x"], requires_grad=True)
+    y = torch.tensor(g["y"], requires_grad=True)
+    loss = IMSATLoss(lamda=float(g["lamda"]))(x, y)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss_pair"])) < 1e-12
+    np.testing.assert_allclose(x.grad.numpy(), g["grad_x_pair"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(y.grad.numpy(), g["grad_y_pair"], rtol=1e-10, atol=1e-14)
+    x.grad = None
+    loss = IMSATLoss(lamda=float(g["lamda"]))(x)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss_single"])) < 1e-12
+    np.testing.assert_allclose(x.grad.numpy(), g["grad_x_single"], rtol=1e-10, atol=1e-14)
+    x.grad = None
+    dyn = IMSATDynamicWeight(lamda=float(g["lamda_dynamic"]))
+    loss = dyn(x)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss_dynamic"])) < 1e-12
+    np.testing.assert_allclose(x.grad.numpy(), g["grad_x_dynamic"], rtol=1e-10, atol=1e-14)
+    assert abs(float(dyn.dynamic_weight) - float(g["dynamic_weight_after"])) < 1e-12
+    assert "dynamic_weight" in dyn.state_dict()
