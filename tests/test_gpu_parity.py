@@ -488,3 +488,18 @@ def test_pack_feeder_strided_views_and_unnormalised_rows():
     SupConLoss1()(bf[:128], bf[128:], target=list(range(128)))          # bf16 unit rows pass, as in the reference
     with pytest.raises(AssertionError):
         SupConLoss1()(bf[:128] * 1.02, bf[128:], target=list(range(128)))
+
+
+# ------------------------------------------------------------------------------------------------ config 5 stand-in
+def test_pretrain_step_stand_in_runs():
+    """BASELINE config 5 (tiny shapes): U-Net taps -> projector heads -> both drop-in criteria under AMP -> optimizer step"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "pretrain_step.py"), "--steps", "2", "--warmup", "1",
+                          "--scans", "2", "--size", "64", "--max-channel", "128"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["n_gpus"] == 1 and line["value"] > 0
+    assert np.isfinite(line["last_losses"]["infonce"]) and np.isfinite(line["last_losses"]["discrete_mi"])
