@@ -279,7 +279,12 @@ constexpr int BW_THREADS = 2 * BW_WARPS_PER_GROUP * 32;
 #ifndef CY_BW_CTAS
 #define CY_BW_CTAS 2
 #endif
-template <int TWV, int KS>
+// TFORM (K <= 10): the weight rows are (dy, o) — 3*K <= 30 of the 32 rows of two m-tiles — so ONE set of 6*KS MMAs per
+// box row yields the contributions D[(dy,o), pixel] to all three output rows at once (12 instead of 18 MMAs at K = 10).
+// Row slots 0..2 hold (dy = slot, o = lane group < 8): the three contributions to an output row meet in the same thread
+// and are combined with rolling FADDs.  Slot 3 holds the (dy, o >= 8) rows; their contributions meet through a small
+// per-warp shared-memory strip (first touch stores, later touches add) that is flushed once per strip.
+template <int TWV, int KS, bool TFORM>
 __global__ void __launch_bounds__(BW_THREADS, CY_BW_CTAS)
 iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, MmaGeom g,
                    const float* __restrict__ djoint, const float* __restrict__ gscale, float* __restrict__ dx_out,
@@ -296,6 +301,7 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
     const int nj = K * K * T * T;
     uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + (size_t)g.stages * stage_floats);
     uint64_t* empty = full + MAX_STAGES;
+    float* slot3 = reinterpret_cast<float*>(empty + MAX_STAGES);      // TFORM: [warp][2 channels][TH rows][8 pixels]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NCW = 2 * BW_WARPS_PER_GROUP;
@@ -340,28 +346,41 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
         const int group = warp / BW_WARPS_PER_GROUP, wq = warp % BW_WARPS_PER_GROUP;
         const float* wt = wtab + group * nj;
         float* out = group ? dx_out : dy_out;
-        // A fragments per dy: row o = gq (+8); k-slot pairs of k-step ks <-> this lane quad's own elements
-        // e = 4*ks + {0,1 | 2,3}, element e <-> K-row R = q + 4*e = c * 3 + dx
-        uint32_t ah[3][KS][4], al[3][KS][4];
+        // A fragments.  k-slot pairs of k-step ks <-> this lane quad's own elements e = 4*ks + {0,1 | 2,3}, element e
+        // <-> K-row R = q + 4*e = c * 3 + dx.  Direct form: one m-tile per dy, row o = gq (+8).  T form: two m-tiles whose
+        // row slots (8 rows each) are (dy = 0), (dy = 1), (dy = 2) for o = gq, and slot 3 = (dy3, o3) = (gq / KX, 8 + gq % KX).
+        constexpr int NA = TFORM ? 2 : 3;
+        const int KX = K > 8 ? K - 8 : 0;
+        const int dy3 = (TFORM && KX && gq < 3 * KX) ? gq / KX : 3;      // 3: this lane has no slot-3 row
+        const int o3 = 8 + (KX ? gq % KX : 0);
+        uint32_t ah[NA][KS][4], al[NA][KS][4];
 #pragma unroll
-        for (int dyy = 0; dyy < 3; ++dyy)
+        for (int ia = 0; ia < NA; ++ia)
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 float w[2][4];
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
-                    const int o = gq + 8 * hf;
+                    int o, dyy;
+                    if constexpr (TFORM) {
+                        const int slot = 2 * ia + hf;
+                        dyy = slot < 3 ? slot : dy3;
+                        o = slot < 3 ? gq : o3;
+                    } else {
+                        dyy = ia;
+                        o = gq + 8 * hf;
+                    }
 #pragma unroll
                     for (int e4 = 0; e4 < 4; ++e4) {
                         const int R = q + 4 * (4 * ks + e4);
                         const int c = R / 3, dxx = R % 3;
-                        w[hf][e4] = (o < K && c < K) ? wt[((o * K + c) * T + dyy) * T + dxx] : 0.f;
+                        w[hf][e4] = (dyy < 3 && o < K && c < K) ? wt[((o * K + c) * T + dyy) * T + dxx] : 0.f;
                     }
                 }
-                split_pair_rn(w[0][0], w[0][1], ah[dyy][ks][0], al[dyy][ks][0]);
-                split_pair_rn(w[1][0], w[1][1], ah[dyy][ks][1], al[dyy][ks][1]);
-                split_pair_rn(w[0][2], w[0][3], ah[dyy][ks][2], al[dyy][ks][2]);
-                split_pair_rn(w[1][2], w[1][3], ah[dyy][ks][3], al[dyy][ks][3]);
+                split_pair_rn(w[0][0], w[0][1], ah[ia][ks][0], al[ia][ks][0]);
+                split_pair_rn(w[1][0], w[1][1], ah[ia][ks][1], al[ia][ks][1]);
+                split_pair_rn(w[0][2], w[0][3], ah[ia][ks][2], al[ia][ks][2]);
+                split_pair_rn(w[1][2], w[1][3], ah[ia][ks][3], al[ia][ks][3]);
             }
         // byte offsets (within a box) of this lane's 4*KS K-rows at box row 0, strip 0; rows past K*3 carry zero weights
         // and re-read row 0 (finite data)
@@ -392,6 +411,7 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
                 const size_t ostride8 = (size_t)8 * g.H * g.W;
                 const int rows_ok = g.H - h0;                 // W % 4 == 0 and w even: a pixel pair is inside the row together
                 const bool st0 = w < g.W && gq < K && g.debug_skip != 2, st1 = w < g.W && gq + 8 < K && g.debug_skip != 2;
+                if constexpr (!TFORM) {
                 float acc[3][4];                              // rolling: output row r lives in acc[r % 3]
 #pragma unroll
                 for (int rp = 0; rp < HH; ++rp) {
@@ -426,6 +446,69 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
                         if (st1 && rc < rows_ok) *reinterpret_cast<float2*>(op + ostride8) = make_float2(acc[rc % 3][2], acc[rc % 3][3]);
                         op += g.W;
                     }
+                }
+                } else {
+                // ---- T form
+                float* s3 = slot3 + warp * (2 * TH * 8);
+                // slot-3 lane: its (dy3, o3) contribution of box row rp goes to strip row rp - dy3
+                float* p3 = s3 + ((o3 - 8) * TH - dy3) * 8 + 2 * q;
+                float accA[3][2];                             // rolling: output row r (channels o = gq) lives in accA[r % 3]
+#pragma unroll
+                for (int rp = 0; rp < HH; ++rp) {
+                    if ((rp == 3 || rp == 7) && !refilled) refilled = produce(it + g.stages - 1, false);
+                    uint32_t bh[KS][2], bl[KS][2];
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const float v0 = lds_f32(sbase + roff[4 * ks + 0] + rp * XW * 4), v1 = lds_f32(sbase + roff[4 * ks + 1] + rp * XW * 4);
+                        const float v2 = lds_f32(sbase + roff[4 * ks + 2] + rp * XW * 4), v3 = lds_f32(sbase + roff[4 * ks + 3] + rp * XW * 4);
+                        split_pair(v0, v1, bh[ks][0], bl[ks][0]);
+                        split_pair(v2, v3, bh[ks][1], bl[ks][1]);
+                    }
+                    float d[2][4];                            // two independent chains (one per m-tile), issued interleaved
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {
+#pragma unroll
+                            for (int tm = 0; tm < 2; ++tm) {
+                                const uint32_t (&a)[4] = term == 1 ? al[tm][ks] : ah[tm][ks];
+                                const uint32_t (&bb)[2] = term == 2 ? bl[ks] : bh[ks];
+                                if (ks == 0 && term == 0) mma_bf16_16816_z(d[tm], a, bb);
+                                else mma_bf16_16816(d[tm], a, bb);
+                            }
+                        }
+                    }
+                    // slot s (rows 8*s .. 8*s+7 of the 32) = d[s / 2][2 * (s % 2) + {0, 1}]; slot dy feeds output row rp - dy
+                    if (rp < TH) { accA[rp % 3][0] = d[0][0]; accA[rp % 3][1] = d[0][1]; }                     // dy = 0: first touch
+                    if (rp >= 1 && rp - 1 < TH) { accA[(rp - 1) % 3][0] += d[0][2]; accA[(rp - 1) % 3][1] += d[0][3]; }
+                    if (rp >= 2) { accA[(rp - 2) % 3][0] += d[1][0]; accA[(rp - 2) % 3][1] += d[1][1]; }
+                    if (KX) {
+                        const int r3 = rp - dy3;
+                        if (dy3 == 0 && r3 < TH) *reinterpret_cast<float2*>(p3 + rp * 8) = make_float2(d[1][2], d[1][3]);
+                        else if (dy3 < 3 && r3 >= 0 && r3 < TH) {
+                            float2 t = *reinterpret_cast<float2*>(p3 + rp * 8);
+                            t.x += d[1][2];
+                            t.y += d[1][3];
+                            *reinterpret_cast<float2*>(p3 + rp * 8) = t;
+                        }
+                        __syncwarp();
+                    }
+                    const int rc = rp - 2;                            // output row completed by this box row
+                    if (rc >= 0) {
+                        if (st0 && rc < rows_ok) *reinterpret_cast<float2*>(op) = make_float2(accA[rc % 3][0], accA[rc % 3][1]);
+                        op += g.W;
+                    }
+                }
+                if (KX) {      // flush the slot-3 strip: [KX channels][TH rows][4 pixel pairs]
+                    for (int e = lane; e < KX * TH * 4; e += 32) {
+                        const int pp = e % 4, r = (e / 4) % TH, oc = e / (4 * TH);
+                        const int wq2 = w0 + 8 * strip + 2 * pp;
+                        if (r < rows_ok && wq2 < g.W && g.debug_skip != 2)
+                            *reinterpret_cast<float2*>(out + (((size_t)b * K + 8 + oc) * g.H + h0 + r) * g.W + wq2) =
+                                *reinterpret_cast<const float2*>(s3 + (oc * TH + r) * 8 + 2 * pp);
+                    }
+                    __syncwarp();
+                }
                 }
             }
             if (!refilled) produce(it + g.stages - 1, true);       // every warp has moved on from that stage by now
@@ -560,10 +643,10 @@ int iic_joint_mma_max_partials() { return 2 * sm_count_mma(); }
 
 namespace {
 
-template <int TWV, int KS>
+template <int TWV, int KS, bool TFORM>
 int launch_bwd_mma(const CUtensorMap& tmx, const CUtensorMap& tmy, const MmaGeom& g, size_t smem, int grid, const float* djoint,
                    const float* gscale, float* dx, float* dy, cudaStream_t st) {
-    auto k = iic_bwd_mma_kernel<TWV, KS>;
+    auto k = iic_bwd_mma_kernel<TWV, KS, TFORM>;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -601,7 +684,7 @@ int iic_bwd_mma(const void* x, const void* y, int dtype, int B, int K, int H, in
         g.x_stage_floats = (K * g.HH * g.XW + 31) & ~31;
         g.y_stage_floats = g.x_stage_floats;
         for (int stg = MAX_STAGES - 1; stg >= 2 && !ok; --stg) {
-            smem = (size_t)stg * 2 * g.x_stage_floats * 4 + 2 * MAX_STAGES * 8 + 128 + 64;
+            smem = (size_t)stg * 2 * g.x_stage_floats * 4 + 2 * MAX_STAGES * 8 + 128 + 64 + (size_t)BW_THREADS / 32 * 2 * 9 * 8 * 4;
             if (smem <= (size_t)(227 / CY_BW_CTAS - 1) * 1024 && 2 * g.x_stage_floats >= 2 * nj) { g.stages = stg; ok = true; }
         }
     }
@@ -617,12 +700,25 @@ int iic_bwd_mma(const void* x, const void* y, int dtype, int B, int K, int H, in
     float* dxf = reinterpret_cast<float*>(dx);
     float* dyf = reinterpret_cast<float*>(dy);
     const int ks = (K * T + 15) / 16;              // k-steps: K <= 5 -> 1, K <= 10 -> 2, K <= 16 -> 3
-    if (g.TW == 32 && ks == 1) return launch_bwd_mma<32, 1>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
-    if (g.TW == 32 && ks == 2) return launch_bwd_mma<32, 2>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
-    if (g.TW == 32 && ks == 3) return launch_bwd_mma<32, 3>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
-    if (g.TW == 64 && ks == 1) return launch_bwd_mma<64, 1>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
-    if (g.TW == 64 && ks == 2) return launch_bwd_mma<64, 2>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
-    if (g.TW == 64 && ks == 3) return launch_bwd_mma<64, 3>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st);
+    static int tform = -1;
+    // A/B switch.  Measured at config 3 (B200): direct form 96 us, T form 102 us — the T form issues 12 instead of 18 MMAs
+    // per box row but its 6-deep dependent chains and the slot-3 exchange leave the HMMA pipe idle more often (44 % vs
+    // 62 % busy), so the direct form is the default; CY_IIC_TFORM=1 selects the T form.
+    if (tform < 0) { const char* e = getenv("CY_IIC_TFORM"); tform = (e && e[0] == '1') ? 1 : 0; }
+#define CY_BW(TWV, KSV, TF) return launch_bwd_mma<TWV, KSV, TF>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st)
+    if (K <= 10 && tform) {
+        if (g.TW == 32 && ks == 1) CY_BW(32, 1, true);
+        if (g.TW == 32 && ks == 2) CY_BW(32, 2, true);
+        if (g.TW == 64 && ks == 1) CY_BW(64, 1, true);
+        if (g.TW == 64 && ks == 2) CY_BW(64, 2, true);
+    }
+    if (g.TW == 32 && ks == 1) CY_BW(32, 1, false);
+    if (g.TW == 32 && ks == 2) CY_BW(32, 2, false);
+    if (g.TW == 32 && ks == 3) CY_BW(32, 3, false);
+    if (g.TW == 64 && ks == 1) CY_BW(64, 1, false);
+    if (g.TW == 64 && ks == 2) CY_BW(64, 2, false);
+    if (g.TW == 64 && ks == 3) CY_BW(64, 3, false);
+#undef CY_BW
     return CY_ERR_UNSUPPORTED;
 }
 
