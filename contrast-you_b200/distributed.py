@@ -31,7 +31,7 @@ from torch import Tensor
 
 from . import _lib as L
 
-__all__ = ["row_range", "rank_major_labels", "gather_rank_major", "make_stats_exchange", "make_joint_reduce",
+__all__ = ["row_range", "rank_major_labels", "gather_rank_major", "make_stats_exchange", "exchange_strip_stats", "make_joint_reduce",
            "ShardedSupConLoss", "shard_iic_loss"]
 
 
@@ -129,13 +129,7 @@ class _ShardedInfoNCE(torch.autograd.Function):
                                    stats.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd")
         L.check(lib.cy_infonce_finalize(N, rb, re, inv_t, L.CY_SUPCON, 1, stats.data_ptr(), out4.data_ptr(), st),
                 "cy_infonce_finalize")
-        # exchange: [4 stat rows of the strip | 4 scalars] per rank, one collective
-        rows4 = list(_STAT_ROWS)
-        send = torch.cat([stats[rows4, rb:re].reshape(-1), out4])
-        recv = torch.empty(world, send.numel(), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(recv, send, group=group)
-        stats[rows4] = recv[:, :4 * rows_loc].view(world, 4, rows_loc).permute(1, 0, 2).reshape(4, N)
-        out4 = recv[:, 4 * rows_loc:].sum(dim=0)
+        out4 = exchange_strip_stats(stats, out4, rb, re, group)
         ctx.save_for_backward(z_all, labels_all, stats, ws)
         ctx.cfg = (inv_t, path, rb, re)
         ctx.mark_non_differentiable(out4)
@@ -160,6 +154,22 @@ class _ShardedInfoNCE(torch.autograd.Function):
 
 
 _STAT_ROWS = (L.CY_STAT_LOGDEN, L.CY_STAT_INVC, L.CY_STAT_COEF, L.CY_STAT_AUX)
+
+
+def exchange_strip_stats(stats: Tensor, out4: Tensor, rb: int, re: int, group=None) -> Tensor:
+    """ONE all-gather for what ``make_stats_exchange`` does with five collectives: every rank sends
+    [4 statistic rows of its strip | its 4 partial scalars]; on return ``stats`` holds the four rows for all N columns
+    (rank-major strips) and the summed scalar block is returned."""
+    world, _ = _ws(group)
+    rows_loc = re - rb
+    N = stats.shape[1]
+    rows4 = list(_STAT_ROWS)
+    send = torch.cat([stats[rows4, rb:re].reshape(-1), out4])
+    recv = torch.empty(world * send.numel(), dtype=stats.dtype, device=stats.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.view(world, send.numel())
+    stats[rows4] = recv[:, :4 * rows_loc].view(world, 4, rows_loc).permute(1, 0, 2).reshape(4, N)
+    return recv[:, 4 * rows_loc:].sum(dim=0)
 
 
 class ShardedSupConLoss(torch.nn.Module):

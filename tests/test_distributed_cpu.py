@@ -69,7 +69,14 @@ def _worker(rank, port, results):
         stats[L.CY_STAT_COEF, rb:re] = torch.from_numpy(1 / (D + 1e-16))
         out4 = torch.zeros(4, dtype=torch.float64)
         out4[0] = float(-((P * (S - m)).sum(1) / c - np.log(D + 1e-16)).sum() / N)
-        cyd.make_stats_exchange(n_loc)(stats, out4)                            # the product's exchange step
+        stats_b, out4_b = stats.clone(), out4.clone()
+        cyd.make_stats_exchange(n_loc)(stats, out4)                            # the product's exchange step (5 collectives)
+        out4_b = cyd.exchange_strip_stats(stats_b, out4_b, rb, re)             # ... and its one-collective form
+        assert torch.equal(stats_b, stats) and torch.allclose(out4_b, out4, rtol=1e-15, atol=0)
+        # local label sort used by ShardedSupConLoss: sorting every rank's block leaves the loss unchanged and the owned
+        # block's permutation maps sorted rows back to the original ones
+        sorted_blocks, perm = labels.view(WORLD, 2 * n_loc).sort(dim=1)
+        assert torch.equal(labels.view(WORLD, 2 * n_loc)[rank][perm[rank]], sorted_blocks[rank])
         coef, invc = stats[L.CY_STAT_COEF].numpy(), stats[L.CY_STAT_INVC].numpy()
         W = E * (coef[rb:re, None] + coef[None, :]) - P * (invc[rb:re, None] + invc[None, :])
         dz_all = torch.zeros(N, d, dtype=torch.float64)
