@@ -169,6 +169,65 @@ class _IIDSegFunction(torch.autograd.Function):
         return dx, dy, None, None, None, None, None
 
 
+class _IIDSegMultiFunction(torch.autograd.Function):
+    """S sub-head pairs in one autograd node: (x_0, y_0, ..., x_{S-1}, y_{S-1}) -> (mean loss, p00 of head 0).
+
+    The hooks evaluate ``sum(criterion(x1, x2) for x1, x2 in zip(prob1, prob2)) / len(prob1)`` over the sub-heads of a
+    cluster head (semi_seg/hooks/discretemi.py:111, ccblock.py:208-218): S python-level criterion calls, S autograd nodes
+    and ~8 small allocations each.  Here the S joints / epilogues / adjoints are enqueued back to back from one node
+    with one output buffer; the adjoint kernels get the head's share 1/S of the upstream gradient through ``gscale``."""
+
+    @staticmethod
+    def forward(ctx, padding, symmetric, lamda, eps, *maps):
+        lib = L.lib()
+        S = len(maps) // 2
+        x0 = maps[0]
+        B, K, H, W = x0.shape
+        T = 2 * padding + 1
+        nj = K * K * T * T
+        per = 1 + K * K + 2 * nj
+        buf = torch.empty(S, per, dtype=torch.float32, device=x0.device)
+        st = L.stream_ptr(x0.device)
+        ws_bytes = lib.cy_iic_workspace_bytes(B, K, H, W, padding)
+        ws = _workspace(ws_bytes, x0.device, st)
+        ews_bytes = lib.cy_iic_epilogue_workspace_bytes(K, padding)
+        ews = torch.empty(ews_bytes, dtype=torch.uint8, device=x0.device) if ews_bytes else None
+        dt = L.dtype_code(x0)
+        base = buf.data_ptr()
+        for s in range(S):
+            x, y = maps[2 * s], maps[2 * s + 1]
+            o = base + s * per * 4
+            loss_p, p00_p, dj_p, j_p = o, o + 4, o + 4 * (1 + K * K), o + 4 * (1 + K * K + nj)
+            L.check(lib.cy_iic_joint(x.data_ptr(), y.data_ptr(), dt, B, K, H, W, padding, j_p, ws.data_ptr(), ws_bytes, st),
+                    "cy_iic_joint")
+            L.check(lib.cy_iic_epilogue(j_p, K, padding, int(bool(symmetric)), float(lamda), float(eps), float(B * H * W),
+                                        loss_p, p00_p, None, dj_p, L.ptr(ews), ews_bytes, st), "cy_iic_epilogue")
+        ctx.save_for_backward(buf, *maps)
+        ctx.cfg = (padding, S, K, T, per)
+        p00 = buf[0, 1:1 + K * K].view(K, K)
+        ctx.mark_non_differentiable(p00)
+        return buf[:, 0].mean(), p00
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_p00):
+        lib = L.lib()
+        buf, *maps = ctx.saved_tensors
+        padding, S, K, T, per = ctx.cfg
+        B, _, H, W = maps[0].shape
+        gscale = (grad_loss.detach().to(torch.float32) / S).reshape(1).contiguous()
+        st = L.stream_ptr(buf.device)
+        dt = L.dtype_code(maps[0])
+        grads = []
+        for s in range(S):
+            x, y = maps[2 * s], maps[2 * s + 1]
+            dx, dy = torch.empty_like(x), torch.empty_like(y)
+            dj_p = buf.data_ptr() + (s * per + 1 + K * K) * 4
+            L.check(lib.cy_iic_bwd(x.data_ptr(), y.data_ptr(), dt, B, K, H, W, padding, dj_p, gscale.data_ptr(), dx.data_ptr(),
+                                   dy.data_ptr(), st), "cy_iic_bwd")
+            grads += [dx, dy]
+        return (None, None, None, None, *grads)
+
+
 class IIDSegmentationLoss(nn.Module):
     """discreteMI.py:127-170."""
 
@@ -189,6 +248,23 @@ class IIDSegmentationLoss(nn.Module):
         x, y = _check_pair(x_out, x_tf_out)
         loss, p00 = _IIDSegFunction.apply(x, y, int(self.padding), bool(self.symmetric), float(self.lamda), float(self._eps),
                                           self._reduce_joint)
+        self._p_i_j = p00
+        return loss
+
+    def forward_heads(self, x_outs, x_tf_outs) -> Tensor:
+        """mean of ``self(x, y)`` over the sub-head pairs, evaluated as ONE autograd node (extension).
+        Equivalent to ``sum(self(x, y) for x, y in zip(x_outs, x_tf_outs)) / len(x_outs)``; ``_p_i_j`` is head 0's."""
+        if self.padding < 0:
+            raise ValueError(self.padding)
+        assert len(x_outs) == len(x_tf_outs) and len(x_outs) >= 1
+        maps = []
+        for x, y in zip(x_outs, x_tf_outs):
+            x, y = _check_pair(x, y)
+            assert x.shape == x_outs[0].shape and x.dtype == x_outs[0].dtype, "sub-heads must share shape and dtype"
+            maps += [x, y]
+        if self._reduce_joint is not None:      # sharded batches need the joint all-reduce between the two kernels
+            return sum(self(x, y) for x, y in zip(x_outs, x_tf_outs)) / len(x_outs)
+        loss, p00 = _IIDSegMultiFunction.apply(int(self.padding), bool(self.symmetric), float(self.lamda), float(self._eps), *maps)
         self._p_i_j = p00
         return loss
 

@@ -85,6 +85,7 @@ def main():
     ap.add_argument("--clusters", type=int, default=10)
     ap.add_argument("--subheads", type=int, default=5)
     ap.add_argument("--no-amp", action="store_true")
+    ap.add_argument("--batched-heads", action="store_true", help="IIDSegmentationLoss.forward_heads instead of the python sum")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -123,7 +124,10 @@ def main():
             loss_nce = infonce(z1, z2, target=labels)
             # --- discrete-MI hook (discretemi.py:99-113): sub-head list, chunk, mean of the criterion over the heads
             pairs = [torch.chunk(p.float(), 2, 0) for p in probs]
-            loss_mi = sum(mi(a, b) for a, b in pairs) / len(pairs)
+            if args.batched_heads:
+                loss_mi = mi.forward_heads([a for a, _ in pairs], [b for _, b in pairs])
+            else:
+                loss_mi = sum(mi(a, b) for a, b in pairs) / len(pairs)
             c1.record()
             loss = loss_nce + 0.1 * loss_mi
         scaler.scale(loss).backward()

@@ -503,3 +503,22 @@ def test_pretrain_step_stand_in_runs():
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert line["n_gpus"] == 1 and line["value"] > 0
     assert np.isfinite(line["last_losses"]["infonce"]) and np.isfinite(line["last_losses"]["discrete_mi"])
+
+
+def test_iic_forward_heads_equals_python_loop():
+    """sub-head batching: one autograd node == the hooks' python sum over the heads"""
+    torch.manual_seed(11)
+    S, B, K, H, W = 5, 2, 10, 32, 32
+    xs = [(2 * torch.randn(B, K, H, W, device=DEV)).softmax(1).requires_grad_() for _ in range(S)]
+    ys = [(2 * torch.randn(B, K, H, W, device=DEV)).softmax(1).requires_grad_() for _ in range(S)]
+    crit = IIDSegmentationLoss(padding=1)
+    ref = sum(crit(x, y) for x, y in zip(xs, ys)) / S
+    ref.backward()
+    gref = [t.grad.clone() for t in xs + ys]
+    for t in xs + ys:
+        t.grad = None
+    loss = crit.forward_heads(xs, ys)
+    (3.0 * loss).backward()
+    assert loss.item() == pytest.approx(ref.item(), rel=1e-6)
+    for t, g in zip(xs + ys, gref):      # the adjoint weights carry different scales (3/S vs 1/S): bf16 hi/lo split rounding
+        assert _relerr(t.grad.cpu().numpy(), 3.0 * g.cpu().numpy()) <= 3e-5
