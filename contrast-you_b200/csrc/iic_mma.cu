@@ -58,6 +58,8 @@ __device__ __forceinline__ void mma_bf16_16816_z(float (&d)[4], const uint32_t (
 }
 // plain (non-volatile) shared-memory load from a 32-bit shared address: ptxas may hoist it above the volatile MMAs of
 // the previous step (software pipelining), but not above the mbarrier wait (memory clobber)
+// compiler-level ordering point between volatile asm statements (no instruction is emitted)
+__device__ __forceinline__ void mma_order_fence() { asm volatile("" ::: "memory"); }
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     return *reinterpret_cast<const float*>(__cvta_shared_to_generic(addr));
 }
@@ -200,27 +202,51 @@ iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
             const uint32_t sb = stage0_addr + s * stage_stride;
             // refill the stage released one iteration ago as early as the other warps allow (without stalling on them)
             bool refilled = threadIdx.x != 0 || produce(it + g.stages - 1, false);
+            // Software pipeline over the NCH * MT sub-steps (16 pixels x one m-tile) of this warp's tile row.  The warp
+            // issues in order, so source order is the schedule: raw loads of the NEXT sub-step's operands go out before
+            // the 3 * NTW MMAs of the current one, their hi/lo split follows the MMAs (in the shadow of 8 HMMA-pipe
+            // cycles each) and only the flush FADDs wait for the MMA results.
+            if (g.debug_skip != 1) {
+                uint32_t bh[NTW][2], bl[NTW][2], ah[4], al[4];
+                float rb[NTW][4], ra[2][4];
+                auto load_b = [&](int ch) {
 #pragma unroll
-            for (int ch = 0; ch < (g.debug_skip == 1 ? 0 : NCH); ++ch) {
-                if (ch > 0 && !refilled) refilled = produce(it + g.stages - 1, false);
-                uint32_t bh[NTW][2], bl[NTW][2];
+                    for (int tn = 0; tn < NTW; ++tn) {
+                        const uint32_t p = sb + xoff[tn] + ch * 64;
+                        rb[tn][0] = lds_f32(p); rb[tn][1] = lds_f32(p + 16); rb[tn][2] = lds_f32(p + 32); rb[tn][3] = lds_f32(p + 48);
+                    }
+                };
+                auto split_b = [&]() {
 #pragma unroll
-                for (int tn = 0; tn < NTW; ++tn) {
-                    const uint32_t p = sb + xoff[tn] + ch * 64;
-                    const float v0 = lds_f32(p), v1 = lds_f32(p + 16), v2 = lds_f32(p + 32), v3 = lds_f32(p + 48);
-                    split_pair(v0, v1, bh[tn][0], bl[tn][0]);
-                    split_pair(v2, v3, bh[tn][1], bl[tn][1]);
-                }
+                    for (int tn = 0; tn < NTW; ++tn) {
+                        split_pair(rb[tn][0], rb[tn][1], bh[tn][0], bl[tn][0]);
+                        split_pair(rb[tn][2], rb[tn][3], bh[tn][1], bl[tn][1]);
+                    }
+                };
+                auto load_a = [&](int ch, int tm) {
 #pragma unroll
-                for (int tm = 0; tm < MT; ++tm) {
-                    const uint32_t p0 = sb + yoff[tm][0] + ch * 64, p1 = sb + yoff[tm][1] + ch * 64;
-                    const float a0 = lds_f32(p0), a1 = lds_f32(p0 + 16), a2 = lds_f32(p0 + 32), a3 = lds_f32(p0 + 48);
-                    const float c0 = lds_f32(p1), c1 = lds_f32(p1 + 16), c2 = lds_f32(p1 + 32), c3 = lds_f32(p1 + 48);
-                    uint32_t ah[4], al[4];
-                    split_pair(a0, a1, ah[0], al[0]);
-                    split_pair(c0, c1, ah[1], al[1]);
-                    split_pair(a2, a3, ah[2], al[2]);
-                    split_pair(c2, c3, ah[3], al[3]);
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const uint32_t p = sb + yoff[tm][hf] + ch * 64;
+                        ra[hf][0] = lds_f32(p); ra[hf][1] = lds_f32(p + 16); ra[hf][2] = lds_f32(p + 32); ra[hf][3] = lds_f32(p + 48);
+                    }
+                };
+                auto split_a = [&]() {
+                    split_pair(ra[0][0], ra[0][1], ah[0], al[0]);
+                    split_pair(ra[1][0], ra[1][1], ah[1], al[1]);
+                    split_pair(ra[0][2], ra[0][3], ah[2], al[2]);
+                    split_pair(ra[1][2], ra[1][3], ah[3], al[3]);
+                };
+                load_b(0);
+                load_a(0, 0);
+                split_b();
+                split_a();
+#pragma unroll
+                for (int ss = 0; ss < NCH * MT; ++ss) {
+                    const int ch = ss / MT, tm = ss % MT;
+                    const bool more = ss + 1 < NCH * MT, new_chunk = more && (ss + 1) % MT == 0;
+                    if (tm == 0 && ch > 0 && !refilled) refilled = produce(it + g.stages - 1, false);
+                    if (more) load_a((ss + 1) / MT, (ss + 1) % MT);
+                    if (new_chunk) load_b(ch + 1);
                     float d[NTW][4];           // NTW independent chains of 3 dependent HMMAs, issued interleaved
 #pragma unroll
                     for (int tn = 0; tn < NTW; ++tn) mma_bf16_16816_z(d[tn], ah, bh[tn]);
@@ -228,6 +254,10 @@ iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
                     for (int tn = 0; tn < NTW; ++tn) mma_bf16_16816(d[tn], al, bh[tn]);
 #pragma unroll
                     for (int tn = 0; tn < NTW; ++tn) mma_bf16_16816(d[tn], ah, bl[tn]);
+                    mma_order_fence();
+                    if (more) split_a();
+                    if (new_chunk) split_b();
+                    mma_order_fence();
 #pragma unroll
                     for (int tn = 0; tn < NTW; ++tn)
 #pragma unroll
@@ -412,17 +442,25 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
                 const int rows_ok = g.H - h0;                 // W % 4 == 0 and w even: a pixel pair is inside the row together
                 const bool st0 = w < g.W && gq < K && g.debug_skip != 2, st1 = w < g.W && gq + 8 < K && g.debug_skip != 2;
                 if constexpr (!TFORM) {
+                // Software pipeline (the warp issues in order, so source order is the schedule): the loads of box row
+                // rp+1 are issued BEFORE the MMAs of row rp and converted AFTER them, i.e. in the shadow of the 18 x 8
+                // HMMA-pipe cycles; only the stores of a finished row wait for the MMA results.
                 float acc[3][4];                              // rolling: output row r lives in acc[r % 3]
+                uint32_t bh[KS][2], bl[KS][2];
+                float v[4 * KS];
+#pragma unroll
+                for (int j = 0; j < 4 * KS; ++j) v[j] = lds_f32(sbase + roff[j]);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    split_pair(v[4 * ks], v[4 * ks + 1], bh[ks][0], bl[ks][0]);
+                    split_pair(v[4 * ks + 2], v[4 * ks + 3], bh[ks][1], bl[ks][1]);
+                }
 #pragma unroll
                 for (int rp = 0; rp < HH; ++rp) {
                     if ((rp == 3 || rp == 7) && !refilled) refilled = produce(it + g.stages - 1, false);
-                    uint32_t bh[KS][2], bl[KS][2];
+                    if (rp + 1 < HH) {
 #pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-                        const float v0 = lds_f32(sbase + roff[4 * ks + 0] + rp * XW * 4), v1 = lds_f32(sbase + roff[4 * ks + 1] + rp * XW * 4);
-                        const float v2 = lds_f32(sbase + roff[4 * ks + 2] + rp * XW * 4), v3 = lds_f32(sbase + roff[4 * ks + 3] + rp * XW * 4);
-                        split_pair(v0, v1, bh[ks][0], bl[ks][0]);
-                        split_pair(v2, v3, bh[ks][1], bl[ks][1]);
+                        for (int j = 0; j < 4 * KS; ++j) v[j] = lds_f32(sbase + roff[j] + (rp + 1) * XW * 4);
                     }
                     // three independent chains (one per dy), issued interleaved term by term
 #pragma unroll
@@ -438,6 +476,20 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
                                 if (dyy == 0 && ks == 0 && term == 0) mma_bf16_16816_z(acc[r % 3], a, bb);    // first touch of row r
                                 else mma_bf16_16816(acc[r % 3], a, bb);
                             }
+                        }
+                    }
+                    if (rp + 1 < HH) {
+                        uint32_t nh[KS][2], nl[KS][2];
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            split_pair(v[4 * ks], v[4 * ks + 1], nh[ks][0], nl[ks][0]);
+                            split_pair(v[4 * ks + 2], v[4 * ks + 3], nh[ks][1], nl[ks][1]);
+                        }
+                        mma_order_fence();                            // keep the conversion below the MMAs above in the issue order
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            bh[ks][0] = nh[ks][0]; bh[ks][1] = nh[ks][1];
+                            bl[ks][0] = nl[ks][0]; bl[ks][1] = nl[ks][1];
                         }
                     }
                     const int rc = rp - 2;                            // output row completed by this box row
@@ -525,9 +577,12 @@ int make_map3d(CUtensorMap* m, const void* base, int B, int K, int H, int W, int
     cuuint64_t gstride[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
     cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)K};
     cuuint32_t estr[3] = {1, 1, 1};
+    static int promo = -1;
+    if (promo < 0) { const char* e = getenv("CY_IIC_L2PROMO"); promo = e ? atoi(e) : 2; }      // 0 none, 1 64 B, 2 128 B, 3 256 B
+    const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                      : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3d) failed (%d)", (int)r); return CY_ERR_ARG; }
     return CY_OK;
 }
