@@ -505,31 +505,59 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
                 // slot-3 lane: its (dy3, o3) contribution of box row rp goes to strip row rp - dy3
                 float* p3 = s3 + ((o3 - 8) * TH - dy3) * 8 + 2 * q;
                 float accA[3][2];                             // rolling: output row r (channels o = gq) lives in accA[r % 3]
+                // same software pipeline as the direct form: next row's loads before, its split after this row's MMAs
+                uint32_t bh[KS][2], bl[KS][2];
+                float v[4 * KS];
+#pragma unroll
+                for (int j = 0; j < 4 * KS; ++j) v[j] = lds_f32(sbase + roff[j]);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    split_pair(v[4 * ks], v[4 * ks + 1], bh[ks][0], bl[ks][0]);
+                    split_pair(v[4 * ks + 2], v[4 * ks + 3], bh[ks][1], bl[ks][1]);
+                }
 #pragma unroll
                 for (int rp = 0; rp < HH; ++rp) {
                     if ((rp == 3 || rp == 7) && !refilled) refilled = produce(it + g.stages - 1, false);
-                    uint32_t bh[KS][2], bl[KS][2];
+                    if (rp + 1 < HH) {
 #pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-                        const float v0 = lds_f32(sbase + roff[4 * ks + 0] + rp * XW * 4), v1 = lds_f32(sbase + roff[4 * ks + 1] + rp * XW * 4);
-                        const float v2 = lds_f32(sbase + roff[4 * ks + 2] + rp * XW * 4), v3 = lds_f32(sbase + roff[4 * ks + 3] + rp * XW * 4);
-                        split_pair(v0, v1, bh[ks][0], bl[ks][0]);
-                        split_pair(v2, v3, bh[ks][1], bl[ks][1]);
+                        for (int j = 0; j < 4 * KS; ++j) v[j] = lds_f32(sbase + roff[j] + (rp + 1) * XW * 4);
                     }
-                    float d[2][4];                            // two independent chains (one per m-tile), issued interleaved
+                    float dk[KS][2][4];                       // 2 * KS independent chains of three dependent HMMAs
 #pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
+                    for (int term = 0; term < 3; ++term) {
 #pragma unroll
-                        for (int term = 0; term < 3; ++term) {
+                        for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
                             for (int tm = 0; tm < 2; ++tm) {
                                 const uint32_t (&a)[4] = term == 1 ? al[tm][ks] : ah[tm][ks];
                                 const uint32_t (&bb)[2] = term == 2 ? bl[ks] : bh[ks];
-                                if (ks == 0 && term == 0) mma_bf16_16816_z(d[tm], a, bb);
-                                else mma_bf16_16816(d[tm], a, bb);
+                                if (term == 0) mma_bf16_16816_z(dk[ks][tm], a, bb);
+                                else mma_bf16_16816(dk[ks][tm], a, bb);
                             }
                         }
                     }
+                    if (rp + 1 < HH) {
+                        uint32_t nh[KS][2], nl[KS][2];
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            split_pair(v[4 * ks], v[4 * ks + 1], nh[ks][0], nl[ks][0]);
+                            split_pair(v[4 * ks + 2], v[4 * ks + 3], nh[ks][1], nl[ks][1]);
+                        }
+                        mma_order_fence();
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            bh[ks][0] = nh[ks][0]; bh[ks][1] = nh[ks][1];
+                            bl[ks][0] = nl[ks][0]; bl[ks][1] = nl[ks][1];
+                        }
+                    }
+                    float d[2][4];
+#pragma unroll
+                    for (int tm = 0; tm < 2; ++tm)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            d[tm][c] = dk[0][tm][c];
+                            if constexpr (KS > 1) d[tm][c] += dk[1][tm][c];
+                        }
                     // slot s (rows 8*s .. 8*s+7 of the 32) = d[s / 2][2 * (s % 2) + {0, 1}]; slot dy feeds output row rp - dy
                     if (rp < TH) { accA[rp % 3][0] = d[0][0]; accA[rp % 3][1] = d[0][1]; }                     // dy = 0: first touch
                     if (rp >= 1 && rp - 1 < TH) { accA[(rp - 1) % 3][0] += d[0][2]; accA[(rp - 1) % 3][1] += d[0][3]; }
