@@ -23,8 +23,8 @@ int infonce_bwd_simt(const void*, int, int64_t, int64_t, int64_t, const int32_t*
                      float, const float*, const float*, void*, int64_t, cudaStream_t);
 int infonce_masks(int64_t, const int32_t*, const uint8_t*, float*, float*, cudaStream_t);
 int labels_canonicalize(const void*, int, int64_t, int32_t*, cudaStream_t);
-int infonce_pack(const void*, const void*, int, int64_t, int64_t, int64_t, int64_t, const int64_t*, void*, int*, cudaStream_t);
-int infonce_unpack(const void*, int, int64_t, int64_t, int64_t, const int64_t*, void*, void*, cudaStream_t);
+int infonce_pack(const void*, const void*, int, int64_t, int64_t, int64_t, int64_t, const int64_t*, void*, int*, float*, cudaStream_t);
+int infonce_unpack(const void*, int, int64_t, int64_t, int64_t, const int64_t*, void*, void*, const void*, const float*, cudaStream_t);
 // infonce_tc.cu
 bool infonce_tc_supported(int dtype, int64_t N, int64_t d, int64_t ldz, const uint8_t* codes, int variant);
 size_t infonce_tc_workspace_bytes(int64_t N, int64_t d);
@@ -155,17 +155,18 @@ int cy_labels_canonicalize(const void* src, int src_kind, int64_t n, int32_t* ds
 }
 
 int cy_infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_t d, int64_t ld1, int64_t ld2,
-                    const int64_t* order, void* z, int32_t* bad_rows, void* stream) {
+                    const int64_t* order, void* z, int32_t* bad_rows, float* inv_norm, void* stream) {
     CY_CHECK_ARG(f1 && f2 && z && n >= 1 && d >= 1 && ld1 >= d && ld2 >= d, "bad arguments");
     CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
-    return infonce_pack(f1, f2, dtype, n, d, ld1, ld2, order, z, bad_rows, reinterpret_cast<cudaStream_t>(stream));
+    return infonce_pack(f1, f2, dtype, n, d, ld1, ld2, order, z, bad_rows, inv_norm, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int cy_infonce_unpack(const void* dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* order, void* g1,
-                      void* g2, void* stream) {
+                      void* g2, const void* z, const float* inv_norm, void* stream) {
     CY_CHECK_ARG(dz && g1 && g2 && n >= 1 && d >= 1 && lddz >= d, "bad arguments");
     CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
-    return infonce_unpack(dz, dtype, n, d, lddz, order, g1, g2, reinterpret_cast<cudaStream_t>(stream));
+    CY_CHECK_ARG((z == nullptr) == (inv_norm == nullptr), "z and inv_norm go together");
+    return infonce_unpack(dz, dtype, n, d, lddz, order, g1, g2, z, inv_norm, reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t cy_iic_workspace_bytes(int B, int K, int H, int W, int pad) {

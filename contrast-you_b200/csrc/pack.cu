@@ -19,7 +19,8 @@ __device__ __forceinline__ float round_to_dtype(float v, int dtype) {
 template <int ESIZE>
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const uint8_t* __restrict__ f1, const uint8_t* __restrict__ f2, int dtype, int64_t n, int64_t d,
-                 int64_t ld1, int64_t ld2, const int64_t* __restrict__ order, uint8_t* __restrict__ z, int* __restrict__ bad_rows) {
+                 int64_t ld1, int64_t ld2, const int64_t* __restrict__ order, uint8_t* __restrict__ z, int* __restrict__ bad_rows,
+                 float* __restrict__ inv_norm) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= 2 * n) return;
@@ -28,6 +29,19 @@ pack_rows_kernel(const uint8_t* __restrict__ f1, const uint8_t* __restrict__ f2,
     uint8_t* o = z + row * d * ESIZE;
     const bool vec = ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(o)) & 15) == 0 && (d * ESIZE) % 16 == 0;
     float ss = 0.f;
+    if (inv_norm) {
+        // fused F.normalize (contrastyou/projectors/nn.py:47-54, heads.py:20): z = f / max(||f||_2, 1e-12).  Two sweeps over
+        // the row (the second one hits L1); the reciprocal norm is kept for the adjoint.
+        for (int64_t c = lane; c < d; c += 32) {
+            const float a = ld_as_float(s, dtype, c);
+            ss = fmaf(a, a, ss);
+        }
+        ss = warp_sum(ss);
+        const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+        for (int64_t c = lane; c < d; c += 32) st_from_float(o, dtype, c, ld_as_float(s, dtype, c) * inv);
+        if (lane == 0) inv_norm[row] = inv;
+        return;
+    }
     if (vec) {
         constexpr int PER = 16 / ESIZE;
         for (int64_t c = lane; c < d / PER; c += 32) {
@@ -68,14 +82,25 @@ pack_rows_kernel(const uint8_t* __restrict__ f1, const uint8_t* __restrict__ f2,
 
 template <int ESIZE>
 __global__ void __launch_bounds__(256)
-unpack_rows_kernel(const uint8_t* __restrict__ dz, int64_t n, int64_t d, int64_t lddz, const int64_t* __restrict__ order,
-                   uint8_t* __restrict__ g1, uint8_t* __restrict__ g2) {
+unpack_rows_kernel(const uint8_t* __restrict__ dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* __restrict__ order,
+                   uint8_t* __restrict__ g1, uint8_t* __restrict__ g2, const uint8_t* __restrict__ z, const float* __restrict__ inv_norm) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= 2 * n) return;
     const int64_t dst = order ? order[row] : row;
     const uint8_t* s = dz + row * lddz * ESIZE;
     uint8_t* o = dst < n ? g1 + dst * d * ESIZE : g2 + (dst - n) * d * ESIZE;
+    if (inv_norm) {
+        // adjoint of z = f / ||f||:  g = (dz - z (z . dz)) / ||f||
+        const uint8_t* zr = z + row * d * ESIZE;
+        float dot = 0.f;
+        for (int64_t c = lane; c < d; c += 32) dot = fmaf(ld_as_float(s, dtype, c), ld_as_float(zr, dtype, c), dot);
+        dot = warp_sum(dot);
+        const float inv = inv_norm[row];
+        for (int64_t c = lane; c < d; c += 32)
+            st_from_float(o, dtype, c, (ld_as_float(s, dtype, c) - ld_as_float(zr, dtype, c) * dot) * inv);
+        return;
+    }
     const bool vec = ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(o)) & 15) == 0 && (d * ESIZE) % 16 == 0;
     if (vec) {
         for (int64_t c = lane; c < d * ESIZE / 16; c += 32) *reinterpret_cast<uint4*>(o + c * 16) = *reinterpret_cast<const uint4*>(s + c * 16);
@@ -87,23 +112,23 @@ unpack_rows_kernel(const uint8_t* __restrict__ dz, int64_t n, int64_t d, int64_t
 }  // namespace
 
 int infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_t d, int64_t ld1, int64_t ld2, const int64_t* order,
-                 void* z, int* bad_rows, cudaStream_t st) {
+                 void* z, int* bad_rows, float* inv_norm, cudaStream_t st) {
     const unsigned grid = (unsigned)((2 * n + 7) / 8);
     if (dtype == CY_F32)
-        pack_rows_kernel<4><<<grid, 256, 0, st>>>((const uint8_t*)f1, (const uint8_t*)f2, dtype, n, d, ld1, ld2, order, (uint8_t*)z, bad_rows);
+        pack_rows_kernel<4><<<grid, 256, 0, st>>>((const uint8_t*)f1, (const uint8_t*)f2, dtype, n, d, ld1, ld2, order, (uint8_t*)z, bad_rows, inv_norm);
     else
-        pack_rows_kernel<2><<<grid, 256, 0, st>>>((const uint8_t*)f1, (const uint8_t*)f2, dtype, n, d, ld1, ld2, order, (uint8_t*)z, bad_rows);
+        pack_rows_kernel<2><<<grid, 256, 0, st>>>((const uint8_t*)f1, (const uint8_t*)f2, dtype, n, d, ld1, ld2, order, (uint8_t*)z, bad_rows, inv_norm);
     CY_CHECK_LAUNCH("infonce_pack");
     return CY_OK;
 }
 
 int infonce_unpack(const void* dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* order, void* g1, void* g2,
-                   cudaStream_t st) {
+                   const void* z, const float* inv_norm, cudaStream_t st) {
     const unsigned grid = (unsigned)((2 * n + 7) / 8);
     if (dtype == CY_F32)
-        unpack_rows_kernel<4><<<grid, 256, 0, st>>>((const uint8_t*)dz, n, d, lddz, order, (uint8_t*)g1, (uint8_t*)g2);
+        unpack_rows_kernel<4><<<grid, 256, 0, st>>>((const uint8_t*)dz, dtype, n, d, lddz, order, (uint8_t*)g1, (uint8_t*)g2, (const uint8_t*)z, inv_norm);
     else
-        unpack_rows_kernel<2><<<grid, 256, 0, st>>>((const uint8_t*)dz, n, d, lddz, order, (uint8_t*)g1, (uint8_t*)g2);
+        unpack_rows_kernel<2><<<grid, 256, 0, st>>>((const uint8_t*)dz, dtype, n, d, lddz, order, (uint8_t*)g1, (uint8_t*)g2, (const uint8_t*)z, inv_norm);
     CY_CHECK_LAUNCH("infonce_unpack");
     return CY_OK;
 }

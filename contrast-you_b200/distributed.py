@@ -217,7 +217,7 @@ class ShardedSupConLoss(torch.nn.Module):
             labels_all = sorted_blocks.reshape(-1)
         f1 = proj_feat1 if proj_feat1.stride(1) == 1 else proj_feat1.contiguous()
         f2 = proj_feat2 if proj_feat2.stride(1) == 1 else proj_feat2.contiguous()
-        z_loc, bad = _PackViews.apply(f1, f2, order, __debug__)
+        z_loc, bad = _PackViews.apply(f1, f2, order, __debug__, False)
         loss, _ = _ShardedInfoNCE.apply(z_loc, labels_all, float(1.0 / self._t), self._path, self._group)
         if __debug__:
             nbad, val = torch.stack((bad[0].to(torch.float32), loss.detach())).tolist()

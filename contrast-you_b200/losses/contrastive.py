@@ -119,15 +119,18 @@ class _PackViews(torch.autograd.Function):
     per forward instead of three).  Backward scatters dz to the two views."""
 
     @staticmethod
-    def forward(ctx, f1, f2, order, check):
+    def forward(ctx, f1, f2, order, check, normalize):
         lib = L.lib()
         n, d = f1.shape
         z = torch.empty(2 * n, d, dtype=f1.dtype, device=f1.device)
-        bad = torch.zeros(1, dtype=torch.int32, device=f1.device) if check else None
+        bad = torch.zeros(1, dtype=torch.int32, device=f1.device) if (check and not normalize) else None
+        inv_norm = torch.empty(2 * n, dtype=torch.float32, device=f1.device) if normalize else None
         L.check(lib.cy_infonce_pack(f1.data_ptr(), f2.data_ptr(), L.dtype_code(f1), n, d, f1.stride(0), f2.stride(0),
-                                    L.ptr(order), z.data_ptr(), L.ptr(bad), L.stream_ptr(f1.device)), "cy_infonce_pack")
+                                    L.ptr(order), z.data_ptr(), L.ptr(bad), L.ptr(inv_norm), L.stream_ptr(f1.device)),
+                "cy_infonce_pack")
         ctx.order = order
         ctx.shape = (n, d)
+        ctx.norm = (z, inv_norm) if normalize else None
         if bad is None:
             bad = torch.zeros(0, dtype=torch.int32, device=f1.device)
         ctx.mark_non_differentiable(bad)
@@ -141,9 +144,10 @@ class _PackViews(torch.autograd.Function):
             dz = dz.contiguous()
         g1 = torch.empty(n, d, dtype=dz.dtype, device=dz.device)
         g2 = torch.empty(n, d, dtype=dz.dtype, device=dz.device)
+        z, inv_norm = ctx.norm if ctx.norm is not None else (None, None)
         L.check(lib.cy_infonce_unpack(dz.data_ptr(), L.dtype_code(dz), n, d, dz.stride(0), L.ptr(ctx.order), g1.data_ptr(),
-                                      g2.data_ptr(), L.stream_ptr(dz.device)), "cy_infonce_unpack")
-        return g1, g2, None, None
+                                      g2.data_ptr(), L.ptr(z), L.ptr(inv_norm), L.stream_ptr(dz.device)), "cy_infonce_unpack")
+        return g1, g2, None, None, None
 
 
 def tensor_core_eligible(z: Tensor, labels, codes, variant: int, path: int) -> bool:
@@ -205,7 +209,11 @@ class _ContrastBase(nn.Module):
         self._dbg_cache = {}
         fused = (proj_feat1.dim() == 2 and proj_feat1.dtype == proj_feat2.dtype and proj_feat1.device == proj_feat2.device
                  and proj_feat1.dtype in (torch.float32, torch.bfloat16, torch.float16))
+        normalize = bool(getattr(self, "_normalize_input", False))
         if not fused:
+            if normalize:
+                proj_feat1 = torch.nn.functional.normalize(proj_feat1, dim=1)
+                proj_feat2 = torch.nn.functional.normalize(proj_feat2, dim=1)
             assert is_normalized(proj_feat1) and is_normalized(proj_feat2), f"features need to be normalized first"
             self._bad = None
             return torch.cat([proj_feat1, proj_feat2], dim=0), labels, codes
@@ -215,8 +223,8 @@ class _ContrastBase(nn.Module):
         if sort and codes is None and self._sorts_rows(f1, labels):
             order = torch.argsort(labels)          # equal labels adjacent: the loss is invariant under row permutations
             labels = labels.index_select(0, order)
-        z, bad = _PackViews.apply(f1, f2, order, __debug__)
-        self._bad = bad if __debug__ else None
+        z, bad = _PackViews.apply(f1, f2, order, __debug__, normalize)
+        self._bad = bad if (__debug__ and not normalize) else None
         return z, labels, codes
 
     def _sorts_rows(self, f1, labels) -> bool:
@@ -240,6 +248,8 @@ class _ContrastBase(nn.Module):
         if name not in self._dbg_cache:
             f1, f2, labels, codes = self._views
             z = torch.cat([f1, f2], dim=0)
+            if getattr(self, "_normalize_input", False):
+                z = torch.nn.functional.normalize(z, dim=1)
             N = z.shape[0]
             if name in ("pos_mask", "neg_mask"):
                 pos = torch.empty(N, N, dtype=torch.float32, device=z.device)
@@ -263,10 +273,14 @@ class _ContrastBase(nn.Module):
 class SupConLoss1(_ContrastBase):
     """contrastive.py:23-100.  ``path`` (keyword-only extra) pins the kernel family: "auto" | "simt" | "tcgen05"."""
 
-    def __init__(self, temperature=0.07, exclude_other_pos=False, *, path: str = "auto"):
+    def __init__(self, temperature=0.07, exclude_other_pos=False, *, path: str = "auto", normalize_input: bool = False):
         super().__init__()
         self._t = temperature
         self._exclude_pos = exclude_other_pos
+        # extension (SURVEY.md §8f rank 1): take UN-normalised projections and L2-normalise them inside the pack kernel
+        # (pair it with ``ProjectionHead.forward(features, skip_normalize=True)``); the default keeps the reference's
+        # contract (inputs already normalised, asserted)
+        self._normalize_input = normalize_input
         self._path = {"auto": L.CY_PATH_AUTO, "simt": L.CY_PATH_SIMT, "tcgen05": L.CY_PATH_TCGEN05}[path]
 
     def forward(self, proj_feat1, proj_feat2, target=None, mask: Tensor = None, **kwargs):

@@ -48,7 +48,14 @@ class ProjectionHead(_ProjectorHeadBase):
         dims = (input_dim, hidden_dim, output_dim) if head_type == "mlp" else (input_dim, output_dim)
         self._header = _global_stack(self._pooling_module, dims, [_tail(normalize)])
 
-    def forward(self, features):
+    def forward(self, features, skip_normalize: bool = False):
+        """``skip_normalize=True`` (extension) stops before the parameter-free ``Normalize`` tail so that the criterion can
+        fuse the normalisation into its load stage (``SupConLoss1(normalize_input=True)``); the module tree — and with it
+        the checkpoint keys — is unchanged."""
+        if skip_normalize and isinstance(self._header[-1], Normalize):
+            for m in list(self._header)[:-1]:
+                features = m(features)
+            return features
         return self._header(features)
 
 

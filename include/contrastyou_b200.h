@@ -128,14 +128,18 @@ int cy_labels_canonicalize(const void* src, int src_kind, int64_t n, int32_t* ds
  * pass the label sort so that equal labels are adjacent), and runs the reference's `is_normalized` assertion
  * (contrastive.py:9-11, :58) on the device: *bad_rows is incremented once per source row whose L2 norm, rounded to the
  * element type like torch's `norm`, is not within 1e-8 + 1e-5 of 1.  ld1 / ld2: row pitches of f1 / f2 in elements.
- * bad_rows may be NULL (python -O: the reference's assert is stripped too). */
+ * bad_rows may be NULL (python -O: the reference's assert is stripped too).
+ * inv_norm != NULL fuses the projector's L2-normalise tail (contrastyou/projectors/nn.py:47-54, heads.py:20,116-117)
+ * into the same pass: z[i] = f / max(||f||_2, 1e-12) and inv_norm[i] [2n] keeps the reciprocal norm for the adjoint;
+ * the is_normalized check is skipped in that mode. */
 int cy_infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_t d, int64_t ld1, int64_t ld2,
-                    const int64_t* order, void* z, int32_t* bad_rows, void* stream);
+                    const int64_t* order, void* z, int32_t* bad_rows, float* inv_norm, void* stream);
 
 /* Adjoint of cy_infonce_pack: scatters dz [2n, d] (row pitch lddz) back to the two views, g(order[i]) = dz[i];
- * g1, g2 are contiguous [n, d]. */
+ * g1, g2 are contiguous [n, d].  With (z, inv_norm) from a normalising pack it also applies the Jacobian of the
+ * normalisation, g = (dz - z (z . dz)) * inv_norm; pass NULL, NULL otherwise. */
 int cy_infonce_unpack(const void* dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* order, void* g1,
-                      void* g2, void* stream);
+                      void* g2, const void* z, const float* inv_norm, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * IIC discrete-MI segmentation loss.  Replaces compute_joint_2D / compute_joint_2D_with_padding_zeros

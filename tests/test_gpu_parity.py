@@ -522,3 +522,27 @@ def test_iic_forward_heads_equals_python_loop():
     assert loss.item() == pytest.approx(ref.item(), rel=1e-6)
     for t, g in zip(xs + ys, gref):      # the adjoint weights carry different scales (3/S vs 1/S): bf16 hi/lo split rounding
         assert _relerr(t.grad.cpu().numpy(), 3.0 * g.cpu().numpy()) <= 3e-5
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, BF16_TOL)])
+def test_fused_normalize_feeder(dtype, tol):
+    """ProjectionHead(skip_normalize) + SupConLoss1(normalize_input=True) == the reference route
+    (Normalize tail in the head, criterion asserting unit rows): loss and gradients w.r.t. the raw projections"""
+    from contrast_you_b200.projectors import ProjectionHead
+    torch.manual_seed(21)
+    n, C = 128, 64
+    head = ProjectionHead(input_dim=C, hidden_dim=256, output_dim=256, head_type="mlp", normalize=True).to(DEV)
+    feats = torch.randn(2 * n, C, 4, 4, device=DEV)
+    lab = torch.randint(0, 6, (n,)).tolist()
+    raw = head(feats, skip_normalize=True).detach()
+    assert not torch.allclose(raw.norm(dim=1), torch.ones(2 * n, device=DEV))
+    # reference route, fp32 master: normalise with torch, then the default criterion
+    r32 = raw.clone().requires_grad_()
+    zn = torch.nn.functional.normalize(r32, dim=1)
+    l_ref = SupConLoss1()(zn[:n], zn[n:], target=lab)
+    l_ref.backward()
+    r = raw.to(dtype).requires_grad_()
+    loss = SupConLoss1(normalize_input=True)(r[:n], r[n:], target=lab)
+    loss.backward()
+    assert loss.item() == pytest.approx(l_ref.item(), rel=tol)
+    assert _relerr(r.grad.float().cpu().numpy(), r32.grad.cpu().numpy()) <= max(tol, 2e-5) * (3 if dtype != torch.float32 else 1)
