@@ -163,12 +163,12 @@ def exchange_strip_stats(stats: Tensor, out4: Tensor, rb: int, re: int, group=No
     world, _ = _ws(group)
     rows_loc = re - rb
     N = stats.shape[1]
-    rows4 = list(_STAT_ROWS)
-    send = torch.cat([stats[rows4, rb:re].reshape(-1), out4])
+    assert _STAT_ROWS == (0, 1, 2, 3)      # the four rows are the leading rows of `stats`: plain slices, no index tensors
+    send = torch.cat([stats[:4, rb:re].reshape(-1), out4])          # (a python index list would cost a pageable H2D + sync)
     recv = torch.empty(world * send.numel(), dtype=stats.dtype, device=stats.device)
     dist.all_gather_into_tensor(recv, send, group=group)
     recv = recv.view(world, send.numel())
-    stats[rows4] = recv[:, :4 * rows_loc].view(world, 4, rows_loc).permute(1, 0, 2).reshape(4, N)
+    stats[:4].view(4, world, rows_loc).copy_(recv[:, :4 * rows_loc].view(world, 4, rows_loc).permute(1, 0, 2))
     return recv[:, 4 * rows_loc:].sum(dim=0)
 
 

@@ -27,6 +27,9 @@ def is_normalized(feature: Tensor, dim=1):
 
 
 # ----------------------------------------------------------------------------------------------------- labels / masks
+_LABEL_CACHE = {}
+
+
 def _canonical_labels(target, n: int, device) -> Tensor:
     """[2n] int32 labels whose integer equality reproduces the reference comparison (contrastive.py:38-44).
 
@@ -34,7 +37,16 @@ def _canonical_labels(target, n: int, device) -> Tensor:
     NaN equals nothing); tensors are compared in their own dtype."""
     lib = L.lib()
     if isinstance(target, list):
-        target = torch.tensor(target, dtype=torch.float32)
+        # cached by content (SURVEY.md §8f rank 4): a python list costs a pageable H2D copy + stream sync on every call
+        key = (tuple(target), n, str(device))
+        hit = _LABEL_CACHE.get(key)
+        if hit is not None:
+            return hit
+        out = _canonical_labels(torch.tensor(target, dtype=torch.float32), n, device)
+        if len(_LABEL_CACHE) >= 64:
+            _LABEL_CACHE.pop(next(iter(_LABEL_CACHE)))
+        _LABEL_CACHE[key] = out
+        return out
     if not isinstance(target, Tensor):
         raise TypeError(f"target must be a list or a Tensor, got {type(target)}")
     assert target.dim() == 1 and target.shape[0] == n, (target.shape, n)
