@@ -32,6 +32,17 @@ constexpr int TC_KBLK = TC_D / 64;   // 64-element (128-byte) K blocks per row
 constexpr float LOG2E = 1.4426950408889634f;
 
 // ------------------------------------------------------------------------------------------------------------ forward
+// -DCY_FWD_EX2_POLY=1 sends every other exponential of the forward epilogue to the FMA-pipe polynomial (tc_common.cuh:
+// ex2_poly).  Measured on B200 at N = 65536: 1.757 ms vs 1.646 ms with all of them on MUFU — the epilogue is issue-bound,
+// not MUFU-bound, so the default keeps MUFU.
+#ifndef CY_FWD_EX2_POLY
+#define CY_FWD_EX2_POLY 0
+#endif
+#if CY_FWD_EX2_POLY
+#define EX2_ALT ex2_poly
+#else
+#define EX2_ALT ex2_approx
+#endif
 template <int BN>
 struct FwdSmem {
     static constexpr int NSTAGE = 2;
@@ -172,9 +183,9 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
 #pragma unroll
                     for (int e4 = 0; e4 < 8; ++e4) {
                         D0 += ex2_approx(fmaf(__uint_as_float(r[c][e4 * 4 + 0]), c1, -c1));
-                        D1 += ex2_approx(fmaf(__uint_as_float(r[c][e4 * 4 + 1]), c1, -c1));
+                        D1 += EX2_ALT(fmaf(__uint_as_float(r[c][e4 * 4 + 1]), c1, -c1));
                         D2 += ex2_approx(fmaf(__uint_as_float(r[c][e4 * 4 + 2]), c1, -c1));
-                        D3 += ex2_approx(fmaf(__uint_as_float(r[c][e4 * 4 + 3]), c1, -c1));
+                        D3 += EX2_ALT(fmaf(__uint_as_float(r[c][e4 * 4 + 3]), c1, -c1));
                     }
                 }
             } else if (!__any_sync(0xffffffffu, diag_tile)) {
@@ -186,9 +197,9 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                         const float s0 = __uint_as_float(r[c][e4 * 4 + 0]), s1 = __uint_as_float(r[c][e4 * 4 + 1]);
                         const float s2 = __uint_as_float(r[c][e4 * 4 + 2]), s3 = __uint_as_float(r[c][e4 * 4 + 3]);
                         D0 += ex2_approx(fmaf(s0, c1, -c1));
-                        D1 += ex2_approx(fmaf(s1, c1, -c1));
+                        D1 += EX2_ALT(fmaf(s1, c1, -c1));
                         D2 += ex2_approx(fmaf(s2, c1, -c1));
-                        D3 += ex2_approx(fmaf(s3, c1, -c1));
+                        D3 += EX2_ALT(fmaf(s3, c1, -c1));
                         if (lj.x == my_lab) { cnt += 1; posS += s0; }
                         if (lj.y == my_lab) { cnt += 1; posS += s1; }
                         if (lj.z == my_lab) { cnt += 1; posS += s2; }
@@ -242,12 +253,20 @@ __global__ void infonce_tc_reduce_kernel(const float* __restrict__ part, int nsl
 }
 
 // ------------------------------------------------------------------------------------------------------------ backward
+#ifndef CY_BWD_A_TMEM
+#define CY_BWD_A_TMEM 1
+#endif
+// CY_BWD_A_TMEM: the row block Zi (the A operand of S = Zi Zj^T) lives in TENSOR MEMORY (128 columns: two bf16 per column)
+// instead of shared memory.  An M128 N64 K16 MMA with both operands in shared memory fetches 6 KB and is bound by the
+// 128 B/clk shared-memory port (48 clk, profiles/probes/probe_umma_small.cu) instead of its 32 clk of math; with A in TMEM
+// it fetches 2 KB.  The 64 KB of shared memory this frees deepen the Zj ring.
 struct BwdCfg {
     static constexpr int BN = 64;
-    static constexpr int NSTAGE = 3;     // Zj ring (a stage lives from its MMA1 until its MMA2 retires)
-    static constexpr int NS = 4;         // S accumulators in TMEM (64 columns each) at columns [256, 512)
+    static constexpr bool A_TMEM = CY_BWD_A_TMEM != 0;
+    static constexpr int NSTAGE = A_TMEM ? 5 : 3;     // Zj ring (a stage lives from its MMA1 until its MMA2 retires)
+    static constexpr int NS = A_TMEM ? 2 : 4;         // S accumulators in TMEM (64 columns each), the last NS*64 columns
     static constexpr int NW = 2;         // W tiles in shared memory
-    static constexpr uint32_t A_BYTES = TC_BM * TC_D * 2;       // 64 KB
+    static constexpr uint32_t A_BYTES = A_TMEM ? 0 : TC_BM * TC_D * 2;       // 64 KB
     static constexpr uint32_t B_BYTES = BN * TC_D * 2;          // 32 KB
     static constexpr uint32_t W_BYTES = TC_BM * BN * 2;         // 16 KB
     static constexpr uint32_t OFF_B = A_BYTES;
@@ -277,7 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict__ labels,
                       const float* __restrict__ stats, int N, int row_begin, int tiles_per_split, float c1,
                       const float* __restrict__ gscale, float out_scale, void* __restrict__ dz_v, int64_t lddz,
-                      float* __restrict__ dz32, uint32_t idesc1, uint32_t idesc2) {
+                      float* __restrict__ dz32, uint32_t idesc1, uint32_t idesc2, const uint16_t* __restrict__ zrows, int64_t ldz) {
     uint16_t* dz = reinterpret_cast<uint16_t*>(dz_v);
     constexpr float WS = F16 ? 1024.f : 1.f;
     using C = BwdCfg;
@@ -309,7 +328,7 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
 
     if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
     if (warp == 1 && lane == 0) {
-        mbar_init(a_full, 1);
+        mbar_init(a_full, C::A_TMEM ? 8 : 1);
         for (int i = 0; i < C::NSTAGE; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         for (int i = 0; i < C::NS; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 8); }
         for (int i = 0; i < C::NW; ++i) { mbar_init(w_full + i, 8); mbar_init(w_empty + i, 1); }
@@ -322,14 +341,17 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_dz = tmem_base;             // columns [0, 256)
-    const uint32_t tmem_s = tmem_base + 256;        // NS x 64 columns
+    const uint32_t tmem_a = tmem_base + 256;        // A_TMEM: Zi, columns [256, 384)
+    const uint32_t tmem_s = tmem_base + 512 - C::NS * BN;        // NS x 64 columns
 
     if (warp == 0) {
         if (elect_one()) {
-            mbar_arrive_expect_tx(a_full, C::A_BYTES);
-            for (int kb = 0; kb < TC_KBLK; ++kb)
-                for (int hb = 0; hb < TC_BM / 64; ++hb)
-                    tma_load_2d(sA + kb * (TC_BM * 128) + hb * 8192, &tmap, a_full, kb * 64, row0 + hb * 64);
+            if constexpr (!C::A_TMEM) {
+                mbar_arrive_expect_tx(a_full, C::A_BYTES);
+                for (int kb = 0; kb < TC_KBLK; ++kb)
+                    for (int hb = 0; hb < TC_BM / 64; ++hb)
+                        tma_load_2d(sA + kb * (TC_BM * 128) + hb * 8192, &tmap, a_full, kb * 64, row0 + hb * 64);
+            }
             Ring<C::NSTAGE> ring;
             for (int t = 0; t < nt; ++t, ring.next()) {
                 const uint32_t s = ring.stage();
@@ -355,9 +377,14 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
 #pragma unroll
                 for (int kb = 0; kb < TC_KBLK; ++kb)
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_bf16(tmem_s + a * BN, smem_desc(a_addr + kb * (TC_BM * 128) + ks * 32, 16, 1024),
-                                  smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc1, (kb | ks) != 0);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if constexpr (C::A_TMEM)      // k-step (kb, ks) = elements 64*kb + 16*ks ..: 8 columns of Zi in TMEM
+                            umma_bf16_ts(tmem_s + a * BN, tmem_a + (kb * 4 + ks) * 8,
+                                         smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc1, (kb | ks) != 0);
+                        else
+                            umma_bf16(tmem_s + a * BN, smem_desc(a_addr + kb * (TC_BM * 128) + ks * 32, 16, 1024),
+                                      smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc1, (kb | ks) != 0);
+                    }
                 umma_commit(s_full + a);
                 ring1.next();
                 sacc.next();
@@ -390,6 +417,24 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
         const int32_t my_lab = labels[gi];
         const float coef_i = stats[(size_t)CY_STAT_COEF * N + gi] * WS;
         const float invc_i = stats[(size_t)CY_STAT_INVC * N + gi] * WS;
+        if constexpr (C::A_TMEM) {
+            // this thread's half row of Zi (128 elements = 64 packed columns) -> tensor memory lanes q*32.., columns h*64..
+            const uint4* src = reinterpret_cast<const uint4*>(zrows + (size_t)gi * ldz + h * 128);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const uint4 v = __ldg(src + c * 8 + e);
+                    r[4 * e] = v.x; r[4 * e + 1] = v.y; r[4 * e + 2] = v.z; r[4 * e + 3] = v.w;
+                }
+                tmem_st_32x32(tmem_a + (uint32_t(q * 32) << 16) + h * 64 + c * 32, r);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
         float* wcol = sCol + ew * 96;                 // [0,32) labels (as int bits), [32,64) coef_j, [64,96) invc_j
         const int32_t row_lo = __reduce_min_sync(0xffffffffu, my_lab), row_hi = __reduce_max_sync(0xffffffffu, my_lab);
         float nx_lab = __int_as_float(labels[t0 * BN + h * 32 + lane]);
@@ -680,7 +725,7 @@ int infonce_bwd_tc(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, 
     dim3 grid((unsigned)(rows / TC_BM), (unsigned)splits);
     kern<<<grid, TC_THREADS, BwdCfg::TOTAL, st>>>(tmap, labels, stats, (int)N, (int)row_begin, tps, inv_t * LOG2E, gscale, out_scale,
                                                   dz, lddz, dz32, idesc_f16kind_f32(TC_BM, BwdCfg::BN, 0, 0, fmt),
-                                                  idesc_f16kind_f32(TC_BM, TC_D, 0, 1, fmt));
+                                                  idesc_f16kind_f32(TC_BM, TC_D, 0, 1, fmt), reinterpret_cast<const uint16_t*>(z), ldz);
     CY_CHECK_LAUNCH("infonce_bwd_tc");
     if (dz32) {
         const int64_t n8 = rows * (TC_D / 8);
