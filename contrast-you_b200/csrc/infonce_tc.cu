@@ -283,8 +283,9 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
         __half2 h = __floats2half2_rn(a, b);
         return *reinterpret_cast<uint32_t*>(&h);
     } else {
-        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-        return *reinterpret_cast<uint32_t*>(&h);
+        // round-half-up on the bit patterns + one PRMT: F2FP.BF16.PACK_AB issues on the XU pipe (1/16 rate), which the
+        // exponentials of the same epilogue already keep busy
+        return __byte_perm(__float_as_uint(a) + 0x8000u, __float_as_uint(b) + 0x8000u, 0x7632);
     }
 }
 
