@@ -43,11 +43,19 @@ constexpr float LOG2E = 1.4426950408889634f;
 #else
 #define EX2_ALT ex2_approx
 #endif
+#ifndef CY_FWD_A_TMEM
+#define CY_FWD_A_TMEM 1
+#endif
+// CY_FWD_A_TMEM: Zi in tensor memory (columns [384, 512)), three S accumulators instead of four, three Zj stages instead
+// of two.  With both operands in shared memory an M128 N128 K16 MMA fetches 8 KB per 64 clk — the whole 128 B/clk port —
+// while TMA refills the ring through the same port (64 KB per 1024-clk tile): the forward was shared-memory bound at
+// ~2/3 tensor utilisation.  A in TMEM halves the operand fetch.
 template <int BN>
 struct FwdSmem {
-    static constexpr int NSTAGE = 2;
-    static constexpr int NACC = 512 / BN >= 4 ? 4 : 2;
-    static constexpr uint32_t A_BYTES = TC_BM * TC_D * 2;
+    static constexpr bool A_TMEM = CY_FWD_A_TMEM != 0 && BN == 128;
+    static constexpr int NSTAGE = A_TMEM ? 3 : 2;
+    static constexpr int NACC = A_TMEM ? 3 : (512 / BN >= 4 ? 4 : 2);
+    static constexpr uint32_t A_BYTES = A_TMEM ? 0 : TC_BM * TC_D * 2;
     static constexpr uint32_t B_BYTES = BN * TC_D * 2;
     static constexpr uint32_t OFF_B = A_BYTES;
     static constexpr uint32_t OFF_LAB = OFF_B + NSTAGE * B_BYTES;
@@ -58,7 +66,8 @@ struct FwdSmem {
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict__ labels, int N, int row_begin,
-                      int tiles_per_split, float c1, float* __restrict__ part, uint32_t idesc) {
+                      int tiles_per_split, float c1, float* __restrict__ part, uint32_t idesc, const uint16_t* __restrict__ zrows,
+                      int64_t ldz) {
     using S = FwdSmem<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);    // 1024-aligned, still a shared pointer
@@ -81,7 +90,7 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
 
     if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
     if (warp == 1 && lane == 0) {
-        mbar_init(a_full, 1);
+        mbar_init(a_full, S::A_TMEM ? 8 : 1);
         for (int i = 0; i < S::NSTAGE; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         for (int i = 0; i < S::NACC; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 8); }
         fence_barrier_init();
@@ -91,13 +100,16 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_a = tmem_base + 384;        // A_TMEM: Zi, columns [384, 512)
 
     if (warp == 0) {
         if (elect_one()) {
-            mbar_arrive_expect_tx(a_full, S::A_BYTES);
-            for (int kb = 0; kb < TC_KBLK; ++kb)
-                for (int hb = 0; hb < TC_BM / 64; ++hb)
-                    tma_load_2d(sA + kb * (TC_BM * 128) + hb * 8192, &tmap, a_full, kb * 64, row0 + hb * 64);
+            if constexpr (!S::A_TMEM) {
+                mbar_arrive_expect_tx(a_full, S::A_BYTES);
+                for (int kb = 0; kb < TC_KBLK; ++kb)
+                    for (int hb = 0; hb < TC_BM / 64; ++hb)
+                        tma_load_2d(sA + kb * (TC_BM * 128) + hb * 8192, &tmap, a_full, kb * 64, row0 + hb * 64);
+            }
             Ring<S::NSTAGE> ring;
             for (int ct = ct0; ct < ct1; ++ct, ring.next()) {
                 const uint32_t s = ring.stage();
@@ -124,9 +136,14 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
 #pragma unroll
                 for (int kb = 0; kb < TC_KBLK; ++kb)
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_bf16(tmem_base + a * BN, smem_desc(a_addr + kb * (TC_BM * 128) + ks * 32, 16, 1024),
-                                  smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc, (kb | ks) != 0);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if constexpr (S::A_TMEM)
+                            umma_bf16_ts(tmem_base + a * BN, tmem_a + (kb * 4 + ks) * 8,
+                                         smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc, (kb | ks) != 0);
+                        else
+                            umma_bf16(tmem_base + a * BN, smem_desc(a_addr + kb * (TC_BM * 128) + ks * 32, 16, 1024),
+                                      smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc, (kb | ks) != 0);
+                    }
                 umma_commit(b_empty + s);
                 umma_commit(acc_full + a);
             }
@@ -136,6 +153,24 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
         const int row = q * 32 + lane;
         const int gi = row0 + row;
         const int32_t my_lab = labels[gi];
+        if constexpr (S::A_TMEM) {
+            // this thread's half row of Zi (128 elements = 64 packed columns) -> tensor memory lanes q*32.., columns h*64..
+            const uint4* src = reinterpret_cast<const uint4*>(zrows + (size_t)gi * ldz + h * 128);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const uint4 v = __ldg(src + c * 8 + e);
+                    r[4 * e] = v.x; r[4 * e + 1] = v.y; r[4 * e + 2] = v.z; r[4 * e + 3] = v.w;
+                }
+                tmem_st_32x32(tmem_a + (uint32_t(q * 32) << 16) + h * 64 + c * 32, r);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
         int32_t* wlab = sLab + ew * (BN / 2);
         float D0 = 0.f, D1 = 0.f, D2 = 0.f, D3 = 0.f, posS = 0.f;
         int cnt = 0;
@@ -686,7 +721,8 @@ int infonce_fwd_tc(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, 
     const int tps = (ctiles + splits - 1) / splits;
     dim3 grid((unsigned)(rows / TC_BM), (unsigned)splits);
     k<<<grid, TC_THREADS, S::TOTAL, st>>>(tmap, labels, (int)N, (int)row_begin, tps, inv_t * LOG2E,
-                                          reinterpret_cast<float*>(workspace), idesc_f16kind_f32(TC_BM, FWD_BN, 0, 0, fmt));
+                                          reinterpret_cast<float*>(workspace), idesc_f16kind_f32(TC_BM, FWD_BN, 0, 0, fmt),
+                                          reinterpret_cast<const uint16_t*>(z), ldz);
     CY_CHECK_LAUNCH("infonce_fwd_tc");
     infonce_tc_reduce_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(reinterpret_cast<float*>(workspace), nslot, (int)N,
                                                                             (int)row_begin, (int)row_end, inv_t, stats);
