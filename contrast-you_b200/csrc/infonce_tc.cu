@@ -295,15 +295,24 @@ __global__ void infonce_tc_reduce_kernel(const float* __restrict__ part, int nsl
 // instead of shared memory.  An M128 N64 K16 MMA with both operands in shared memory fetches 6 KB and is bound by the
 // 128 B/clk shared-memory port (48 clk, profiles/probes/probe_umma_small.cu) instead of its 32 clk of math; with A in TMEM
 // it fetches 2 KB.  The 64 KB of shared memory this frees deepen the Zj ring.
+#ifndef CY_BWD_W_TMEM
+#define CY_BWD_W_TMEM 1
+#endif
+// CY_BWD_W_TMEM (needs A_TMEM): the weight tile W (A operand of dZ += W Zj) is written by the epilogue straight back into
+// the tensor-memory columns of the S accumulator it was computed from (bf16 pairs: 16 columns per 32-column half) and
+// read from there by the second MMA — no shared-memory W tile, no swizzled stores, no proxy fence, 32 KB less
+// shared-memory traffic per 128 x 64 tile.  The S slot is recycled by the in-order tensor pipe: MMA1(t+2) is issued
+// after MMA2(t), which is the last reader of slot t % 2.
 struct BwdCfg {
     static constexpr int BN = 64;
     static constexpr bool A_TMEM = CY_BWD_A_TMEM != 0;
-    static constexpr int NSTAGE = A_TMEM ? 5 : 3;     // Zj ring (a stage lives from its MMA1 until its MMA2 retires)
+    static constexpr bool W_TMEM = A_TMEM && CY_BWD_W_TMEM != 0;
+    static constexpr int NSTAGE = W_TMEM ? 6 : (A_TMEM ? 5 : 3);     // Zj ring (a stage lives from its MMA1 until its MMA2 retires)
     static constexpr int NS = A_TMEM ? 2 : 4;         // S accumulators in TMEM (64 columns each), the last NS*64 columns
     static constexpr int NW = 2;         // W tiles in shared memory
     static constexpr uint32_t A_BYTES = A_TMEM ? 0 : TC_BM * TC_D * 2;       // 64 KB
     static constexpr uint32_t B_BYTES = BN * TC_D * 2;          // 32 KB
-    static constexpr uint32_t W_BYTES = TC_BM * BN * 2;         // 16 KB
+    static constexpr uint32_t W_BYTES = W_TMEM ? 0 : TC_BM * BN * 2;         // 16 KB
     static constexpr uint32_t OFF_B = A_BYTES;
     static constexpr uint32_t OFF_W = OFF_B + NSTAGE * B_BYTES;
     static constexpr uint32_t OFF_COL = OFF_W + NW * W_BYTES;   // per epilogue warp: lab[32], coef[32], invc[32]
@@ -407,7 +416,7 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
             auto issue_mma1 = [&]() {
                 const uint32_t s = ring1.stage(), a = sacc.stage();
                 mbar_wait(b_full + s, ring1.phase());
-                mbar_wait(s_empty + a, sacc.phase() ^ 1u);
+                if constexpr (!C::W_TMEM) mbar_wait(s_empty + a, sacc.phase() ^ 1u);
                 tc_fence_after();
                 const uint32_t b_addr = smem_u32(sB + s * C::B_BYTES);
 #pragma unroll
@@ -436,11 +445,16 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                 const uint32_t w_addr = smem_u32(sW + w * C::W_BYTES);
                 const uint32_t b_addr = smem_u32(sB + s * C::B_BYTES);
 #pragma unroll
-                for (int ks = 0; ks < BN / 16; ++ks)
+                for (int ks = 0; ks < BN / 16; ++ks) {
                     // A: W [128 x 64] K-major, 32 B per k-step.  B: Zj read MN-major: N = d (4 groups of 64, LBO = BN*128),
                     // K = j (8-row groups, SBO = 1024); one k-step = 16 rows of j = 2048 B.
-                    umma_bf16(tmem_dz, smem_desc(w_addr + ks * 32, 16, 1024), smem_desc(b_addr + ks * 2048, BN * 128, 1024),
-                              idesc2, (t | ks) != 0);      // t counts from this CTA's first tile
+                    if constexpr (C::W_TMEM)      // W of tile t sits in S slot t % NS: half h at columns h*32 .. h*32+15, 8 per k-step
+                        umma_bf16_ts(tmem_dz, tmem_s + (uint32_t)(t % C::NS) * BN + (ks >> 1) * 32 + (ks & 1) * 8,
+                                     smem_desc(b_addr + ks * 2048, BN * 128, 1024), idesc2, (t | ks) != 0);
+                    else
+                        umma_bf16(tmem_dz, smem_desc(w_addr + ks * 32, 16, 1024), smem_desc(b_addr + ks * 2048, BN * 128, 1024),
+                                  idesc2, (t | ks) != 0);      // t counts from this CTA's first tile
+                }
                 umma_commit(w_empty + w);
                 umma_commit(b_empty + s);
             }
@@ -500,7 +514,8 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty + a);      // S values are in registers: the accumulator can be reused
+            // S values are in registers: the accumulator can be reused (W_TMEM: the slot is handed back by MMA2 instead)
+            if (!C::W_TMEM && lane == 0) mbar_arrive(s_empty + a);
             uint32_t packed[16];
             if (!may_have_pos) {                          // no positive pair in this 32 x 32 block: W = E (coef_i + coef_j)
 #pragma unroll
@@ -541,16 +556,24 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                     packed[e4 * 2 + 1] = pack2<F16>(wv[2], wv[3]);
                 }
             }
-            mbar_wait(w_empty + w, wr.phase() ^ 1u);
-            // row `row` of the [128 x 64] bf16 tile: 128 B, this warp's half = 16-byte chunks 4h..4h+3, swizzled by row % 8
-            uint8_t* wrow = sW + w * C::W_BYTES + row * 128;
+            if constexpr (C::W_TMEM) {
+                // in place: this warp's 32 x 32 block of S (columns h*32 ..) becomes 32 x 32 bf16 weights in columns h*32 .. +15
+                tc_fence_after();
+                tmem_st_32x16(tmem_s + (uint32_t(q * 32) << 16) + a * BN + h * 32, packed);
+                tmem_st_wait();
+                tc_fence_before();
+            } else {
+                mbar_wait(w_empty + w, wr.phase() ^ 1u);
+                // row `row` of the [128 x 64] bf16 tile: 128 B, this warp's half = 16-byte chunks 4h..4h+3, swizzled by row % 8
+                uint8_t* wrow = sW + w * C::W_BYTES + row * 128;
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                const int phys = ((4 * h + ch) ^ (row & 7)) << 4;
-                *reinterpret_cast<uint4*>(wrow + phys) =
-                    make_uint4(packed[4 * ch], packed[4 * ch + 1], packed[4 * ch + 2], packed[4 * ch + 3]);
+                for (int ch = 0; ch < 4; ++ch) {
+                    const int phys = ((4 * h + ch) ^ (row & 7)) << 4;
+                    *reinterpret_cast<uint4*>(wrow + phys) =
+                        make_uint4(packed[4 * ch], packed[4 * ch + 1], packed[4 * ch + 2], packed[4 * ch + 3]);
+                }
+                fence_proxy_async_smem();
             }
-            fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(w_full + w);
         }
