@@ -49,8 +49,11 @@ entropy_criterion = Entropy(reduction="none", eps=1e-8)      # semi_seg/hooks/mi
 
 
 class RedundancyCriterion(nn.Module):
-    """redundancy_reduction.py:12-54: cross-entropy of the padding-0 joint against alpha * I/k + (1 - alpha) * joint,
-    plus the marginal-entropy constraint."""
+    """redundancy_reduction.py:12-54.  With J the padding-0 joint (K x K, total mass 1), r = J.sum(1), c = J.sum(0):
+
+        loss = -sum(target * log(J + eps)) + lamda * sum(J * (log(c + eps)[None, :] + log(r + eps)[:, None]))
+        target = alpha * I / K + (1 - alpha) * J          (the target is NOT detached in the reference: it carries gradient)
+    """
 
     def __init__(self, *, eps: float = 1e-5, symmetric: bool = True, lamda: float = 1, alpha: float) -> None:
         super().__init__()
@@ -61,19 +64,15 @@ class RedundancyCriterion(nn.Module):
 
     def forward(self, x_out: Tensor, x_tf_out: Tensor):
         k = x_out.shape[1]
-        p_i_j = compute_joint_2D_with_padding_zeros(x_out, x_tf_out, symmetric=self.symmetric)
-        p_i_j = p_i_j.view(k, k)
-        self._p_i_j = p_i_j
-        target = ((self.onehot_label(k=k, device=p_i_j.device) / k) * self.alpha + p_i_j * (1 - self.alpha))
-        p_i = p_i_j.sum(dim=1).view(k, 1).expand(k, k)
-        p_j = p_i_j.sum(dim=0).view(1, k).expand(k, k)
-        constrained = (-p_i_j * (- self.lamda * torch.log(p_j + self._eps) - self.lamda * torch.log(p_i + self._eps))).sum()
-        pseudo_loss = -(target * (p_i_j + self._eps).log()).sum()
-        return pseudo_loss + constrained
-
-    @staticmethod
-    def onehot_label(k, device):
-        return torch.eye(k, device=device, dtype=torch.bool)
+        joint = compute_joint_2D_with_padding_zeros(x_out, x_tf_out, symmetric=self.symmetric).view(k, k)
+        self._p_i_j = joint
+        eye = torch.eye(k, device=joint.device, dtype=joint.dtype)
+        target = eye * (self.alpha / k) + joint * (1 - self.alpha)
+        log_rows = torch.log(joint.sum(dim=1, keepdim=True) + self._eps)       # [k, 1]
+        log_cols = torch.log(joint.sum(dim=0, keepdim=True) + self._eps)       # [1, k]
+        marginal_term = self.lamda * (joint * (log_cols + log_rows)).sum()
+        match_term = -(target * torch.log(joint + self._eps)).sum()
+        return match_term + marginal_term
 
     def kl_criterion(self, dist: Tensor, prior: Tensor):
         return -(prior * (dist + self._eps).log() + (1 - prior) * (1 - dist + self._eps).log()).mean()
@@ -84,13 +83,16 @@ class RedundancyCriterion(nn.Module):
         return self._p_i_j.detach().cpu().numpy()
 
     def set_ratio(self, alpha: float):
+        """0: entropy minimisation ... 1: Barlow-twins-like identity target (redundancy_reduction.py:46-54)"""
         assert 0 <= alpha <= 1, alpha
         self.alpha = alpha
 
 
 class PUISegLoss(nn.Module):
-    """pica_loss.py:43-80: the same conv-joint as IIC (padding p), min-shifted by 1e-16, normalised per displacement,
-    symmetrised, averaged over displacements; cross-entropy of its diagonal + the (literal) balance term."""
+    """pica_loss.py:43-80.  J = the IIC conv-joint with padding p, shifted by its global minimum (+1e-16), normalised per
+    displacement, symmetrised over (k1, k2) and averaged over the T x T displacements;
+    loss = mean(-I * log(J + 1e-16)) + lamda * (log n + sum(q log q)) with q = the class-mean of x at every pixel
+    (the reference reduces dim 0 of the PERMUTED [K, N, H, W] map, :70 — i.e. over the classes; kept literally)."""
 
     def __init__(self, lamda=2.0, padding=3):
         super().__init__()
@@ -99,40 +101,41 @@ class PUISegLoss(nn.Module):
 
     def forward(self, x_out, x_tf_out):
         assert x_out.shape == x_tf_out.shape, ('Inputs are required to have same shape')
-        p_i_j = raw_joint(x_out, x_tf_out, self.padding)                    # [k, k, T, T] == F.conv2d(x^T, weight=y^T)
-        p_i_j = p_i_j - p_i_j.min().detach() + 1e-16
-        p_i_j = p_i_j.permute(2, 3, 0, 1)
-        p_i_j = p_i_j / p_i_j.sum(dim=3, keepdim=True).sum(dim=2, keepdim=True)
-        p_i_j = (p_i_j + p_i_j.permute(0, 1, 3, 2)) / 2.0
-        p_i_j = p_i_j.mean(dim=[0, 1])
-        loss_ce = self.kl(p_i_j)
-        # the reference takes the mean over dim 0 of the PERMUTED map (k, n, h, w), i.e. over the classes (:70)
-        p = x_out.mean(1).view(-1)
-        loss_ne = math.log(p.size(0)) + (p * p.log()).sum()
-        return loss_ce + self.lamda * loss_ne
+        raw = raw_joint(x_out, x_tf_out, self.padding)                      # [K, K, T, T] == F.conv2d(x^T, weight=y^T)
+        shifted = raw - raw.min().detach() + 1e-16
+        per_disp = shifted / shifted.sum(dim=(0, 1), keepdim=True)
+        sym = 0.5 * (per_disp + per_disp.transpose(0, 1))
+        joint = sym.mean(dim=(2, 3))                                        # [K, K]
+        q = x_out.mean(dim=1).reshape(-1)
+        balance = math.log(q.numel()) + (q * q.log()).sum()
+        return self.kl(joint) + self.lamda * balance
 
     def kl(self, joint_p):
-        diagnal = torch.eye(joint_p.size(0), device=joint_p.device, dtype=torch.float)
-        return (-diagnal * torch.log(joint_p + 1e-16)).mean()
+        k = joint_p.size(0)
+        return -(torch.log(joint_p.diagonal() + 1e-16)).sum() / (k * k)
 
 
-def imsat_loss(prediction: Tensor, lamda: float = 1.0):
-    """discreteMI.py:275-285."""
-    pred = prediction.moveaxis(0, 1).reshape(prediction.shape[1], -1)
-    margin = pred.mean(1, keepdims=True)
-    mi = -entropy_criterion(pred.t()).mean() + entropy_criterion(margin.t()).mean() * lamda
-    return -mi
+def _class_major(prediction: Tensor) -> Tensor:
+    """[N, K, ...] -> [K, N * ...] (classification and segmentation inputs alike)"""
+    return prediction.moveaxis(0, 1).reshape(prediction.shape[1], -1)
 
 
 def imsat_with_entropy(prediction: Tensor):
-    """discreteMI.py:288-297."""
-    pred = prediction.moveaxis(0, 1).reshape(prediction.shape[1], -1)
-    margin = pred.mean(1, keepdims=True)
-    return entropy_criterion(margin.t()).mean(), entropy_criterion(pred.t()).mean()
+    """discreteMI.py:288-297 -> (entropy of the mean prediction, mean entropy of the predictions), eps 1e-8."""
+    per_class = _class_major(prediction)
+    marginal = entropy_criterion(per_class.mean(1, keepdim=True).t()).mean()
+    conditional = entropy_criterion(per_class.t()).mean()
+    return marginal, conditional
+
+
+def imsat_loss(prediction: Tensor, lamda: float = 1.0):
+    """discreteMI.py:275-285: -(lamda * H(mean prediction) - mean H(prediction))."""
+    marginal, conditional = imsat_with_entropy(prediction)
+    return conditional - lamda * marginal
 
 
 class IMSATLoss(nn.Module):
-    """discreteMI.py:20-52."""
+    """discreteMI.py:20-52: the IMSAT objective of one map, or the average over the two views when both are given."""
 
     def __init__(self, lamda: float = 1.0, eps: float = sys.float_info.epsilon):
         super().__init__()
@@ -140,18 +143,15 @@ class IMSATLoss(nn.Module):
         self.lamda = float(lamda)
 
     def forward(self, x_out: Tensor, x_tf_out: Tensor = None):
-        idenity_input = False
-        if x_tf_out is None:
-            idenity_input = True
-            x_tf_out = x_out
+        single = x_tf_out is None
+        other = x_out if single else x_tf_out
         assert len(x_out.shape) == 2, x_out.shape
         assert simplex(x_out), f"x_out not normalized."
-        assert simplex(x_tf_out), f"x_tf_out not normalized."
-        self.x_out = x_out
-        self.x_tf_out = x_tf_out
-        if not idenity_input:
-            return 0.5 * (imsat_loss(x_out, lamda=self.lamda) + imsat_loss(x_tf_out, lamda=self.lamda))
-        return imsat_loss(x_out, lamda=self.lamda)
+        assert simplex(other), f"x_tf_out not normalized."
+        self.x_out, self.x_tf_out = x_out, other
+        if single:
+            return imsat_loss(x_out, lamda=self.lamda)
+        return 0.5 * (imsat_loss(x_out, lamda=self.lamda) + imsat_loss(other, lamda=self.lamda))
 
     def get_joint_matrix(self):
         bn, k = self.x_out.shape
@@ -160,7 +160,8 @@ class IMSATLoss(nn.Module):
 
 
 class IMSATDynamicWeight(IMSATLoss):
-    """discreteMI.py:55-87 (the ``dynamic_weight`` buffer is part of the reference's state_dict)."""
+    """discreteMI.py:55-87: -w * H(mean) + mean H, where the buffer w drifts by 0.01 * (log K - H(mean)) per call
+    (``dynamic_weight`` is part of the reference's state_dict)."""
 
     def __init__(self, lamda: float = 1.0, use_dynamic: bool = True, eps: float = sys.float_info.epsilon):
         super().__init__(lamda, eps)
@@ -168,19 +169,13 @@ class IMSATDynamicWeight(IMSATLoss):
         self.use_dynamic_weight = use_dynamic
 
     def forward(self, x_out: Tensor, **kwargs):
-        device, dtype = x_out.device, x_out.dtype
-        self.dynamic_weight = self.dynamic_weight.to(device).to(dtype)
-        K = x_out.shape[1]
-        x_tf_out = x_out
+        self.dynamic_weight = self.dynamic_weight.to(device=x_out.device, dtype=x_out.dtype)
         assert len(x_out.shape) == 2, x_out.shape
         assert simplex(x_out), f"x_out not normalized."
-        assert simplex(x_tf_out), f"x_tf_out not normalized."
-        self.x_out = x_out
-        self.x_tf_out = x_tf_out
-        marg, cond = imsat_with_entropy(x_out)
-        mi = self.dynamic_weight * marg * -1.0 + cond
+        self.x_out = self.x_tf_out = x_out
+        marginal, conditional = imsat_with_entropy(x_out)
+        value = conditional - self.dynamic_weight * marginal
         if self.use_dynamic_weight:
             with torch.no_grad():
-                increment = (math.log(K) - marg.detach()) * 0.01
-                self.dynamic_weight = self.dynamic_weight + increment
-        return mi
+                self.dynamic_weight = self.dynamic_weight + 0.01 * (math.log(x_out.shape[1]) - marginal.detach())
+        return value
