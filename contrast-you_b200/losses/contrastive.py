@@ -244,7 +244,22 @@ class _ContrastBase(nn.Module):
 
     def _host_checks(self, loss: Tensor):
         """the reference's two assertions / errors in ONE device->host read: un-normalised rows (contrastive.py:58,
-        AssertionError) and a NaN loss (:98-99, RuntimeError(loss))."""
+        AssertionError) and a NaN loss (:98-99, RuntimeError(loss)).
+
+        ``deferred_checks=True`` (extension) replaces the read by two device-side counters that
+        ``raise_if_flagged()`` inspects whenever the caller chooses (e.g. once per epoch): the forward then has no host
+        synchronisation at all and — with tensor labels — can be captured in a CUDA graph
+        (``torch.cuda.make_graphed_callables``)."""
+        if getattr(self, "_deferred_checks", False):
+            nan = torch.isnan(loss.detach()).to(torch.int32).reshape(1)
+            bad = self._bad if self._bad is not None else torch.zeros_like(nan)
+            cur = torch.cat((bad.to(torch.int32), nan))
+            flags = getattr(self, "_flags", None)
+            if flags is None or flags.device != cur.device:
+                self._flags = cur.clone()
+            else:
+                flags.add_(cur)         # in place: the counter tensor keeps its address across CUDA-graph replays
+            return
         if self._bad is not None:
             bad, val = torch.stack((self._bad[0].to(torch.float32), loss.detach().to(torch.float32))).tolist()
             assert bad == 0, f"features need to be normalized first"
@@ -252,6 +267,18 @@ class _ContrastBase(nn.Module):
             val = loss.item()
         if val != val:
             raise RuntimeError(loss)
+
+    def raise_if_flagged(self):
+        """deferred_checks mode: one host read of the accumulated (un-normalised rows, NaN losses) counters; raises what
+        the reference would have raised at the offending step, then clears the counters."""
+        flags = getattr(self, "_flags", None)
+        if flags is None:
+            return
+        bad, nan = flags.tolist()
+        flags.zero_()
+        assert bad == 0, f"features need to be normalized first"
+        if nan:
+            raise RuntimeError(f"loss was NaN in {nan} forward call(s)")
 
     # ---- lazily evaluated side channels (contrastive.py:79-82; read at semi_seg/hooks/infonce.py:235-242) ----
     def _dense(self, name):
@@ -285,8 +312,10 @@ class _ContrastBase(nn.Module):
 class SupConLoss1(_ContrastBase):
     """contrastive.py:23-100.  ``path`` (keyword-only extra) pins the kernel family: "auto" | "simt" | "tcgen05"."""
 
-    def __init__(self, temperature=0.07, exclude_other_pos=False, *, path: str = "auto", normalize_input: bool = False):
+    def __init__(self, temperature=0.07, exclude_other_pos=False, *, path: str = "auto", normalize_input: bool = False,
+                 deferred_checks: bool = False):
         super().__init__()
+        self._deferred_checks = deferred_checks
         self._t = temperature
         self._exclude_pos = exclude_other_pos
         # extension (SURVEY.md §8f rank 1): take UN-normalised projections and L2-normalise them inside the pack kernel

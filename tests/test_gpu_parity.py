@@ -546,3 +546,71 @@ def test_fused_normalize_feeder(dtype, tol):
     loss.backward()
     assert loss.item() == pytest.approx(l_ref.item(), rel=tol)
     assert _relerr(r.grad.float().cpu().numpy(), r32.grad.cpu().numpy()) <= max(tol, 2e-5) * (3 if dtype != torch.float32 else 1)
+
+
+# ------------------------------------------------------------------------------------------------ deferred checks / CUDA graph
+def test_deferred_checks_and_cuda_graph_capture():
+    """with deferred_checks the forward has no host sync (device-side counters), so forward +
+    backward of the criterion can be captured in a CUDA graph; replays must equal the eager strict module"""
+    torch.manual_seed(31)
+    n = 18
+    f1 = torch.nn.functional.normalize(torch.randn(n, 256, device=DEV), dim=1)
+    f2 = torch.nn.functional.normalize(torch.randn(n, 256, device=DEV), dim=1)
+    lab = torch.randint(0, 3, (n,), device=DEV, dtype=torch.int32)
+    a, b = f1.clone().requires_grad_(), f2.clone().requires_grad_()
+    ref = SupConLoss1()(a, b, target=lab)
+    ref.backward()
+
+    crit = SupConLoss1(deferred_checks=True)
+    c, d = f1.clone().requires_grad_(), f2.clone().requires_grad_()
+    loss = crit(c, d, target=lab)
+    loss.backward()
+    assert loss.item() == pytest.approx(ref.item(), rel=1e-6)
+    np.testing.assert_allclose(c.grad.cpu().numpy(), a.grad.cpu().numpy(), rtol=1e-5, atol=1e-9)
+    crit.raise_if_flagged()                                  # nothing flagged
+    crit(f1 * 1.01, f2, target=lab)                          # no exception at the call ...
+    with pytest.raises(AssertionError):
+        crit.raise_if_flagged()                              # ... but the counter caught it
+    crit.raise_if_flagged()                                  # cleared
+
+    class Wrapped(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.crit = SupConLoss1(deferred_checks=True)
+
+        def forward(self, x, y):
+            return self.crit(x, y, target=lab)
+
+    mod = Wrapped()
+    sx, sy = f1.clone().requires_grad_(), f2.clone().requires_grad_()
+    graphed = torch.cuda.make_graphed_callables(mod, (sx, sy))
+    for trial in range(3):                                   # replays with fresh data in the same buffers' shapes
+        g1 = torch.nn.functional.normalize(torch.randn(n, 256, device=DEV), dim=1).requires_grad_()
+        g2 = torch.nn.functional.normalize(torch.randn(n, 256, device=DEV), dim=1).requires_grad_()
+        out = graphed(g1, g2)
+        out.backward()
+        e1, e2 = g1.detach().clone().requires_grad_(), g2.detach().clone().requires_grad_()
+        want = SupConLoss1()(e1, e2, target=lab)
+        want.backward()
+        assert out.item() == pytest.approx(want.item(), rel=1e-6)
+        np.testing.assert_allclose(g1.grad.cpu().numpy(), e1.grad.cpu().numpy(), rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(g2.grad.cpu().numpy(), e2.grad.cpu().numpy(), rtol=1e-5, atol=1e-9)
+    mod.crit.raise_if_flagged()
+
+
+def test_iic_cuda_graph_capture():
+    """IIDSegmentationLoss has no host synchronisation at all: forward + backward replay from a CUDA graph"""
+    torch.manual_seed(32)
+    B, K, H, W = 4, 10, 48, 64
+    crit = IIDSegmentationLoss(padding=1)
+    mk = lambda: (2 * torch.randn(B, K, H, W, device=DEV)).softmax(1).requires_grad_()
+    graphed = torch.cuda.make_graphed_callables(crit, (mk(), mk()))
+    for _ in range(2):
+        x, y = mk(), mk()
+        out = graphed(x, y)
+        out.backward()
+        xe, ye = x.detach().clone().requires_grad_(), y.detach().clone().requires_grad_()
+        want = IIDSegmentationLoss(padding=1)(xe, ye)
+        want.backward()
+        assert out.item() == pytest.approx(want.item(), rel=1e-6)
+        np.testing.assert_allclose(x.grad.cpu().numpy(), xe.grad.cpu().numpy(), rtol=1e-5, atol=1e-12)
