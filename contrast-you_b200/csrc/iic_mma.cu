@@ -76,6 +76,23 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
     const float r1 = v1 - __uint_as_float(h1);
     lo = __byte_perm(__float_as_uint(r0), __float_as_uint(r1), 0x7632);
 }
+// Position-pinned variants (volatile asm keeps the source order, which is the issue order of an in-order warp): used where
+// CUDA-core work is interleaved by hand between dependent HMMAs.
+__device__ __forceinline__ uint32_t lds_b32_pinned(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void split_pair_pinned(uint32_t v0, uint32_t v1, uint32_t& hi, uint32_t& lo) {
+    asm volatile(
+        "{\n\t.reg .b32 h0, h1, r0, r1;\n\t"
+        "add.u32 h0, %2, 0x8000;\n\tadd.u32 h1, %3, 0x8000;\n\t"
+        "and.b32 h0, h0, 0xffff0000;\n\tand.b32 h1, h1, 0xffff0000;\n\t"
+        "prmt.b32 %0, h0, h1, 0x7632;\n\t"
+        "sub.f32 r0, %2, h0;\n\tsub.f32 r1, %3, h1;\n\t"
+        "prmt.b32 %1, r0, r1, 0x7632;\n\t}"
+        : "=r"(hi), "=r"(lo) : "r"(v0), "r"(v1));
+}
 // one-time split of the adjoint weights: both parts round-to-nearest
 __device__ __forceinline__ void split_pair_rn(float v0, float v1, uint32_t& hi, uint32_t& lo) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
@@ -309,11 +326,11 @@ constexpr int BW_THREADS = 2 * BW_WARPS_PER_GROUP * 32;
 #ifndef CY_BW_CTAS
 #define CY_BW_CTAS 2
 #endif
-// TFORM (K <= 10): the weight rows are (dy, o) — 3*K <= 30 of the 32 rows of two m-tiles — so ONE set of 6*KS MMAs per
-// box row yields the contributions D[(dy,o), pixel] to all three output rows at once (12 instead of 18 MMAs at K = 10).
-// Row slots 0..2 hold (dy = slot, o = lane group < 8): the three contributions to an output row meet in the same thread
-// and are combined with rolling FADDs.  Slot 3 holds the (dy, o >= 8) rows; their contributions meet through a small
-// per-warp shared-memory strip (first touch stores, later touches add) that is flushed once per strip.
+// TFORM (K <= 10, default there): the weight rows are (dy, o) — 3*K <= 30 of the 32 rows of two m-tiles — so ONE set of
+// 6*KS MMAs per box row yields the contributions D[(dy,o), pixel] to all three output rows at once (12 instead of 18 MMAs
+// at K = 10).  Row slots 0..2 hold (dy = slot, o = lane group < 8): the three contributions to an output row meet in the
+// same thread, as the C operand of the next box row's MMA chain.  Slot 3 holds the (dy, o >= 8) rows; their partial sums
+// move between lane groups with one shuffle per box row (see the loop).  Measured 90 us vs 94 us (direct) on config 3.
 template <int TWV, int KS, bool TFORM>
 __global__ void __launch_bounds__(BW_THREADS, CY_BW_CTAS)
 iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, MmaGeom g,
@@ -331,7 +348,6 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
     const int nj = K * K * T * T;
     uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + (size_t)g.stages * stage_floats);
     uint64_t* empty = full + MAX_STAGES;
-    float* slot3 = reinterpret_cast<float*>(empty + MAX_STAGES);      // TFORM: [warp][2 channels][TH rows][8 pixels]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NCW = 2 * BW_WARPS_PER_GROUP;
@@ -500,95 +516,75 @@ iic_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
                     }
                 }
                 } else {
-                // ---- T form
-                float* s3 = slot3 + warp * (2 * TH * 8);
-                // slot-3 lane: its (dy3, o3) contribution of box row rp goes to strip row rp - dy3
-                float* p3 = s3 + ((o3 - 8) * TH - dy3) * 8 + 2 * q;
-                float accA[3][2];                             // rolling: output row r (channels o = gq) lives in accA[r % 3]
-                // same software pipeline as the direct form: next row's loads before, its split after this row's MMAs
-                uint32_t bh[KS][2], bl[KS][2];
-                float v[4 * KS];
+                // ---- T form.  Per box row rp ONE accumulate chain per m-tile, straight into the rolling partial sums:
+                //   m-tile 0: C = {0 (row rp, dy 0), p1 (row rp-1 after dy 0)}        -> D = {p1', p2'}
+                //   m-tile 1: C = {p2 (row rp-2 after dy 0,1), s3 (slot-3 pass)}      -> D = {row rp-2 complete, s3'}
+                // Slot 3 (channels 8 .. K-1) is a 3-stage systolic pass over the lane groups dy3 = 0, 1, 2: the partial sum
+                // of output row r starts in the dy3 = 0 lanes at box row r and moves up KX row groups per box row (one
+                // shuffle per register), so that it completes in the dy3 = 2 lanes at box row r+2, like the in-lane rows.
+                // The warp issues in order and a chain of 3*KS dependent HMMAs leaves ~12 idle issue cycles per pair, so the
+                // CUDA-core work of the row (loads of box row rp+1, stores of the row finished one step ago, the hi/lo
+                // split of row rp+1) is pinned BETWEEN the HMMA pairs instead of after them.
+                const int lim0 = st0 ? (rows_ok < TH ? rows_ok : TH) : 0;                       // rows this lane stores
+                const int lim3 = (KX && w < g.W && dy3 == 2 && g.debug_skip != 2) ? (rows_ok < TH ? rows_ok : TH) : 0;
+                float* op3 = out + (((size_t)b * K + o3) * g.H + h0) * g.W + w;
+                uint32_t bh[2][KS][2], bl[2][KS][2], v[4 * KS];
 #pragma unroll
-                for (int j = 0; j < 4 * KS; ++j) v[j] = lds_f32(sbase + roff[j]);
+                for (int j = 0; j < 4 * KS; ++j) v[j] = lds_b32_pinned(sbase + roff[j]);
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
-                    split_pair(v[4 * ks], v[4 * ks + 1], bh[ks][0], bl[ks][0]);
-                    split_pair(v[4 * ks + 2], v[4 * ks + 3], bh[ks][1], bl[ks][1]);
+                    split_pair_pinned(v[4 * ks], v[4 * ks + 1], bh[0][ks][0], bl[0][ks][0]);
+                    split_pair_pinned(v[4 * ks + 2], v[4 * ks + 3], bh[0][ks][1], bl[0][ks][1]);
                 }
+                float p1[2] = {0.f, 0.f}, p2[2] = {0.f, 0.f}, s3[2] = {0.f, 0.f}, done[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int rp = 0; rp < HH; ++rp) {
+                    const int cur = rp & 1, nxt = cur ^ 1;
+                    const bool more = rp + 1 < HH;
                     if ((rp == 3 || rp == 7) && !refilled) refilled = produce(it + g.stages - 1, false);
-                    if (rp + 1 < HH) {
+                    float d[2][4] = {{0.f, 0.f, p1[0], p1[1]}, {p2[0], p2[1], s3[0], s3[1]}};
+                    int piece = 0;
 #pragma unroll
-                        for (int j = 0; j < 4 * KS; ++j) v[j] = lds_f32(sbase + roff[j] + (rp + 1) * XW * 4);
-                    }
-                    float dk[KS][2][4];                       // 2 * KS independent chains of three dependent HMMAs
+                    for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-#pragma unroll
-                        for (int ks = 0; ks < KS; ++ks) {
+                        for (int term = 0; term < 3; ++term, ++piece) {
 #pragma unroll
                             for (int tm = 0; tm < 2; ++tm) {
                                 const uint32_t (&a)[4] = term == 1 ? al[tm][ks] : ah[tm][ks];
-                                const uint32_t (&bb)[2] = term == 2 ? bl[ks] : bh[ks];
-                                if (term == 0) mma_bf16_16816_z(dk[ks][tm], a, bb);
-                                else mma_bf16_16816(dk[ks][tm], a, bb);
+                                const uint32_t (&bb)[2] = term == 2 ? bl[cur][ks] : bh[cur][ks];
+                                mma_bf16_16816(d[tm], a, bb);
+                            }
+                            // CUDA-core piece that follows HMMA pair number `piece`
+                            if (piece == 0 && more) {
+#pragma unroll
+                                for (int j = 0; j < 4 * KS; ++j) v[j] = lds_b32_pinned(sbase + roff[j] + (rp + 1) * XW * 4);
+                            }
+                            if (piece == 1 && rp >= 3) {              // output row rp - 3 was finished by the previous box row
+                                mma_order_fence();
+                                if (rp - 3 < lim0) *reinterpret_cast<float2*>(op + (size_t)(rp - 3) * g.W) = make_float2(done[0], done[1]);
+                                if (rp - 3 < lim3) *reinterpret_cast<float2*>(op3 + (size_t)(rp - 3) * g.W) = make_float2(done[2], done[3]);
+                                mma_order_fence();
+                            }
+                            if (more) {
+                                const int first = 3 * KS - 2 * KS;            // the last 2*KS pairs carry one split each
+                                if (piece >= first) {
+                                    const int e = piece - first, ks2 = e / 2, hf2 = e % 2;
+                                    split_pair_pinned(v[4 * ks2 + 2 * hf2], v[4 * ks2 + 2 * hf2 + 1], bh[nxt][ks2][hf2], bl[nxt][ks2][hf2]);
+                                }
                             }
                         }
                     }
-                    if (rp + 1 < HH) {
-                        uint32_t nh[KS][2], nl[KS][2];
-#pragma unroll
-                        for (int ks = 0; ks < KS; ++ks) {
-                            split_pair(v[4 * ks], v[4 * ks + 1], nh[ks][0], nl[ks][0]);
-                            split_pair(v[4 * ks + 2], v[4 * ks + 3], nh[ks][1], nl[ks][1]);
-                        }
-                        mma_order_fence();
-#pragma unroll
-                        for (int ks = 0; ks < KS; ++ks) {
-                            bh[ks][0] = nh[ks][0]; bh[ks][1] = nh[ks][1];
-                            bl[ks][0] = nl[ks][0]; bl[ks][1] = nl[ks][1];
-                        }
-                    }
-                    float d[2][4];
-#pragma unroll
-                    for (int tm = 0; tm < 2; ++tm)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            d[tm][c] = dk[0][tm][c];
-                            if constexpr (KS > 1) d[tm][c] += dk[1][tm][c];
-                        }
-                    // slot s (rows 8*s .. 8*s+7 of the 32) = d[s / 2][2 * (s % 2) + {0, 1}]; slot dy feeds output row rp - dy
-                    if (rp < TH) { accA[rp % 3][0] = d[0][0]; accA[rp % 3][1] = d[0][1]; }                     // dy = 0: first touch
-                    if (rp >= 1 && rp - 1 < TH) { accA[(rp - 1) % 3][0] += d[0][2]; accA[(rp - 1) % 3][1] += d[0][3]; }
-                    if (rp >= 2) { accA[(rp - 2) % 3][0] += d[1][0]; accA[(rp - 2) % 3][1] += d[1][1]; }
+                    done[0] = d[1][0]; done[1] = d[1][1]; done[2] = d[1][2]; done[3] = d[1][3];
+                    p1[0] = d[0][0]; p1[1] = d[0][1];
+                    p2[0] = d[0][2]; p2[1] = d[0][3];
                     if (KX) {
-                        const int r3 = rp - dy3;
-                        if (dy3 == 0 && r3 < TH) *reinterpret_cast<float2*>(p3 + rp * 8) = make_float2(d[1][2], d[1][3]);
-                        else if (dy3 < 3 && r3 >= 0 && r3 < TH) {
-                            float2 t = *reinterpret_cast<float2*>(p3 + rp * 8);
-                            t.x += d[1][2];
-                            t.y += d[1][3];
-                            *reinterpret_cast<float2*>(p3 + rp * 8) = t;
-                        }
-                        __syncwarp();
-                    }
-                    const int rc = rp - 2;                            // output row completed by this box row
-                    if (rc >= 0) {
-                        if (st0 && rc < rows_ok) *reinterpret_cast<float2*>(op) = make_float2(accA[rc % 3][0], accA[rc % 3][1]);
-                        op += g.W;
+                        const float t0 = __shfl_up_sync(0xffffffffu, d[1][2], 4 * KX), t1 = __shfl_up_sync(0xffffffffu, d[1][3], 4 * KX);
+                        s3[0] = dy3 == 0 ? 0.f : t0;
+                        s3[1] = dy3 == 0 ? 0.f : t1;
                     }
                 }
-                if (KX) {      // flush the slot-3 strip: [KX channels][TH rows][4 pixel pairs]
-                    for (int e = lane; e < KX * TH * 4; e += 32) {
-                        const int pp = e % 4, r = (e / 4) % TH, oc = e / (4 * TH);
-                        const int wq2 = w0 + 8 * strip + 2 * pp;
-                        if (r < rows_ok && wq2 < g.W && g.debug_skip != 2)
-                            *reinterpret_cast<float2*>(out + (((size_t)b * K + 8 + oc) * g.H + h0 + r) * g.W + wq2) =
-                                *reinterpret_cast<const float2*>(s3 + (oc * TH + r) * 8 + 2 * pp);
-                    }
-                    __syncwarp();
-                }
+                if (HH - 3 < lim0) *reinterpret_cast<float2*>(op + (size_t)(HH - 3) * g.W) = make_float2(done[0], done[1]);
+                if (HH - 3 < lim3) *reinterpret_cast<float2*>(op3 + (size_t)(HH - 3) * g.W) = make_float2(done[2], done[3]);
                 }
             }
             if (!refilled) produce(it + g.stages - 1, true);       // every warp has moved on from that stage by now
@@ -767,7 +763,7 @@ int iic_bwd_mma(const void* x, const void* y, int dtype, int B, int K, int H, in
         g.x_stage_floats = (K * g.HH * g.XW + 31) & ~31;
         g.y_stage_floats = g.x_stage_floats;
         for (int stg = MAX_STAGES - 1; stg >= 2 && !ok; --stg) {
-            smem = (size_t)stg * 2 * g.x_stage_floats * 4 + 2 * MAX_STAGES * 8 + 128 + 64 + (size_t)BW_THREADS / 32 * 2 * 9 * 8 * 4;
+            smem = (size_t)stg * 2 * g.x_stage_floats * 4 + 2 * MAX_STAGES * 8 + 128 + 64;
             if (smem <= (size_t)(227 / CY_BW_CTAS - 1) * 1024 && 2 * g.x_stage_floats >= 2 * nj) { g.stages = stg; ok = true; }
         }
     }
@@ -784,10 +780,10 @@ int iic_bwd_mma(const void* x, const void* y, int dtype, int B, int K, int H, in
     float* dyf = reinterpret_cast<float*>(dy);
     const int ks = (K * T + 15) / 16;              // k-steps: K <= 5 -> 1, K <= 10 -> 2, K <= 16 -> 3
     static int tform = -1;
-    // A/B switch.  Measured at config 3 (B200): direct form 96 us, T form 102 us — the T form issues 12 instead of 18 MMAs
-    // per box row but its 6-deep dependent chains and the slot-3 exchange leave the HMMA pipe idle more often (44 % vs
-    // 62 % busy), so the direct form is the default; CY_IIC_TFORM=1 selects the T form.
-    if (tform < 0) { const char* e = getenv("CY_IIC_TFORM"); tform = (e && e[0] == '1') ? 1 : 0; }
+    // A/B switch.  Measured at config 3 (B200): direct form 94 us, T form 90 us (12 instead of 18 MMAs per box row, partial
+    // sums rolled through the C operands, CUDA-core work pinned between the HMMA pairs).  CY_IIC_TFORM=0 selects the
+    // direct form, which also serves 10 < K <= 16.
+    if (tform < 0) { const char* e = getenv("CY_IIC_TFORM"); tform = (e && e[0] == '0') ? 0 : 1; }
 #define CY_BW(TWV, KSV, TF) return launch_bwd_mma<TWV, KSV, TF>(tmx, tmy, g, smem, grid, djoint, gscale, dxf, dyf, st)
     if (K <= 10 && tform) {
         if (g.TW == 32 && ks == 1) CY_BW(32, 1, true);

@@ -59,7 +59,7 @@ int main() {
     void* p = nullptr; cudaDriverEntryPointQueryResult q;
     cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
     EncodeTiledFn fn = (EncodeTiledFn)p;
-    const int shapes[][3] = {{36, 11, 10}, {44, 9, 10}, {68, 11, 10}, {132, 11, 10}, {228, 11, 10}, {228, 3, 10}, {36, 11, 5}, {36, 110, 1}, {224, 16, 4}, {64, 64, 1}};
+    const int shapes[][3] = {{32, 11, 10}, {36, 11, 10}, {40, 9, 10}, {44, 9, 10}, {64, 11, 10}, {68, 11, 10}, {132, 11, 10}, {228, 11, 10}, {228, 3, 10}, {224, 16, 4}, {64, 64, 1}};
     for (auto& sh : shapes) {
         const int bw = sh[0], bh = sh[1], bk = sh[2];
         CUtensorMap tm;
