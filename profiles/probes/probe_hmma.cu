@@ -67,6 +67,36 @@ __global__ void hmma_loop_var(float* out, int iters, long long* cycles) {
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// does an HMMA hold the issue port?  Per iteration: 2 independent HMMAs + NALU independent integer adds (8 accumulators).
+// If CUDA-core instructions issue in the shadow of the HMMA pipe the time per iteration is max(16, 2 + NALU) per warp-slot,
+// if not it is 16 + NALU.
+template <int NALU>
+__global__ void hmma_alu_mix(float* out, int iters, long long* cycles) {
+    float acc[2][4] = {};
+    uint32_t a[4], b[2], x[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = 0x3f803f80u + threadIdx.x + i;
+    b[0] = 0x3f803f80u + threadIdx.x;
+    b[1] = 0x3f803f80u - threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 7 + i;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        mma_bf16(acc[0], a, b);
+        mma_bf16(acc[1], a, b);
+#pragma unroll
+        for (int j = 0; j < NALU; ++j) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[j % 8]) : "r"(x[(j + 3) % 8] | 1u));
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    uint32_t sx = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sx ^= x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc[0][0] + acc[1][1] + __uint_as_float(sx & 0xff);
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 int main() {
     float* out;
     long long* cyc;
@@ -99,6 +129,17 @@ int main() {
         printf("4 warps/SMSP, 8 chains, 8 A x 1 B fragments: %.1f cycles per HMMA per SMSP\n", (double)c / iters / 8 / 4);
         hmma_loop_var<8, 4, 2><<<148, 128>>>(out, iters, cyc); cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
         printf("1 warp/SMSP,  8 chains, 4 A x 2 B fragments: %.1f cycles per HMMA per SMSP\n", (double)c / iters / 8);
+    }
+    {
+        long long c;
+#define MIX(N) hmma_alu_mix<N><<<148, 512>>>(out, iters, cyc); cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost); \
+        printf("4 warps/SMSP, 2 HMMA + %2d int adds per iteration: %.1f cycles per iteration per SMSP (%.1f per warp)\n", N, (double)c / iters / 4, (double)c / iters);
+        MIX(0) MIX(4) MIX(8) MIX(16) MIX(24) MIX(32) MIX(48)
+#undef MIX
+#define MIX(N) hmma_alu_mix<N><<<148, 128>>>(out, iters, cyc); cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost); \
+        printf("1 warp/SMSP,  2 HMMA + %2d int adds per iteration: %.1f cycles per iteration\n", N, (double)c / iters);
+        MIX(0) MIX(8) MIX(16) MIX(32)
+#undef MIX
     }
     const int NACC = 12;
     for (int warps = 4; warps <= 32; warps *= 2) {

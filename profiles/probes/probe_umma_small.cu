@@ -42,7 +42,7 @@ constexpr int THREADS = 32 * 13;  // warps 0-3: issue / readout, warps 4-12: sha
 // smem operand layout: offset(r, c) = (r/8)*SBO + (c/8)*128 + (r%8)*16 + (c%8)*2,  SBO = (KTOT/8)*128
 __global__ void __launch_bounds__(THREADS, 1)
 umma_probe(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, float* __restrict__ D, int M, int N,
-           int loops, int hammer, long long* stats) {
+           int loops, int hammer, long long* stats, int ts = 0, int nacc = 1) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t SBO = (KTOT / 8) * 128;
     uint8_t* sa = smem;                          // 128 rows max
@@ -85,9 +85,15 @@ umma_probe(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict_
                 const uint64_t da = desc_noswz(smem_u32(sa) + j * 256, 128, SBO);
                 const uint64_t db = desc_noswz(smem_u32(sb) + j * 256, 128, SBO);
                 const uint32_t acc = (l | j) ? 1u : 0u;
+                const uint32_t dcol = tmem + (nacc > 1 ? (uint32_t)(j % nacc) * 32u : 0u);      // nacc > 1: independent accumulators (N <= 32)
+                if (ts)     // A operand from tensor memory (columns 96 + 8 j; contents are whatever is there: timing only)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                                 ::"r"(dcol), "r"(tmem + 96u + 8u * j), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                else
                 asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                              "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                             ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                             ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
             }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -186,6 +192,17 @@ int main(int argc, char** argv) {
     }
     printf("rows not found: %d of %d\n", bad, M);
     // throughput on all SMs
+    for (int ts = 0; ts <= 1; ++ts)
+        for (int nacc = 1; nacc <= (N <= 32 ? 3 : 1); ++nacc) {
+            const int loops = 2000;
+            cudaMemset(dS, 0, 148 * 2 * 8);
+            umma_probe<<<148, THREADS, smem>>>(dA, dB, dD, M, N, loops, 0, dS, ts, nacc);
+            e = cudaDeviceSynchronize();
+            long long st[4];
+            cudaMemcpy(st, dS, 32, cudaMemcpyDeviceToHost);
+            printf("%s, %d accumulator(s): %s  cycles/MMA %.2f\n", ts ? "A from TMEM" : "A from smem", nacc, cudaGetErrorString(e),
+                   st[0] / ((double)loops * (KTOT / 16)));
+        }
     for (int h = 0; h <= hammer; ++h) {
         const int loops = 2000;
         cudaMemset(dS, 0, 148 * 2 * 8);
