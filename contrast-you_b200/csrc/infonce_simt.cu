@@ -158,43 +158,67 @@ infonce_finalize_kernel(int64_t N, int64_t row_begin, int64_t row_end, int varia
                         float* __restrict__ out4) {
     float term_sum = 0.f, sw_sum = 0.f, c_sum = 0.f, bad = 0.f;
     const bool last = (variant == CY_SUPCON) ? (pass == 1) : (pass == 2);
-    for (int64_t i = row_begin + threadIdx.x; i < row_end; i += blockDim.x) {
-        float term = 0.f;
-        if (pass == 1) {
-            const float posE = stats[CY_STAT_POSE * N + i], negE = stats[CY_STAT_AUX * N + i];
-            const float c = stats[CY_STAT_INVC * N + i], nc = stats[CY_STAT_NEGC * N + i];
-            const float posL = stats[CY_STAT_POSL * N + i];
-            const float den = posE + negE + 1e-16f;
-            const float logden = logf(den);
-            const float invc = 1.f / c;
-            stats[CY_STAT_LOGDEN * N + i] = logden;
-            stats[CY_STAT_INVC * N + i] = invc;
-            stats[CY_STAT_POSE * N + i] = c;  // slot reused: positive count (needed by pass-2 finalize)
-            if (variant == CY_SUPCON) {
-                stats[CY_STAT_COEF * N + i] = 1.f / den;
-                term = -(posL * invc - logden);
-                // c == 0: the reference computes 0/0 = NaN (contrastive.py:95) -> posL*invc = 0*inf = NaN as well
-            } else if (variant == CY_SUPCON_EXCLUDE) {
-                const float ratio = nc / (c + nc);                       // contrastive.py:88 (float32)
-                stats[CY_STAT_AUX * N + i] = negE / (ratio + 1e-4f);     // A_i
-            }
-        } else {
-            const float posl2 = stats[CY_STAT_POSL * N + i], sw = stats[CY_STAT_SW * N + i];
-            const float invc = stats[CY_STAT_INVC * N + i], c = stats[CY_STAT_POSE * N + i];
-            term = -posl2 * invc;
-            if (variant == CY_SUPCON_EXCLUDE) {
-                const float nc = stats[CY_STAT_NEGC * N + i];
-                const float ratio = nc / (c + nc);
-                stats[CY_STAT_COEF * N + i] = sw * invc / (ratio + 1e-4f);
+    // one block walks all rows (fixed summation order); U rows per thread are loaded before any of them is stored so that the
+    // loads of a trip overlap (the stores go to the array the loads come from, which otherwise serialises the trips)
+    constexpr int U = 4;
+    for (int64_t i0 = row_begin + threadIdx.x; i0 < row_end; i0 += (int64_t)U * blockDim.x) {
+        float a0[U], a1[U], a2[U], a3[U], a4[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x;
+            const bool ok = i < row_end;
+            if (pass == 1) {
+                a0[u] = ok ? stats[CY_STAT_POSE * N + i] : 0.f;
+                a1[u] = ok ? stats[CY_STAT_AUX * N + i] : 0.f;
+                a2[u] = ok ? stats[CY_STAT_INVC * N + i] : 1.f;
+                a3[u] = ok ? stats[CY_STAT_NEGC * N + i] : 0.f;
+                a4[u] = ok ? stats[CY_STAT_POSL * N + i] : 0.f;
             } else {
-                stats[CY_STAT_COEF * N + i] = sw * invc * expf(-stats[CY_STAT_LOGDEN * N + i]);
-                sw_sum += sw;
-                c_sum += c;
+                a0[u] = ok ? stats[CY_STAT_POSL * N + i] : 0.f;
+                a1[u] = ok ? stats[CY_STAT_SW * N + i] : 0.f;
+                a2[u] = ok ? stats[CY_STAT_INVC * N + i] : 0.f;
+                a3[u] = ok ? stats[CY_STAT_POSE * N + i] : 0.f;
+                a4[u] = ok ? (variant == CY_SUPCON_EXCLUDE ? stats[CY_STAT_NEGC * N + i] : stats[CY_STAT_LOGDEN * N + i]) : 0.f;
             }
         }
-        if (last) {
-            if (!isfinite(term)) bad += 1.f;
-            term_sum += term;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x;
+            if (i >= row_end) break;
+            float term = 0.f;
+            if (pass == 1) {
+                const float posE = a0[u], negE = a1[u], c = a2[u], nc = a3[u], posL = a4[u];
+                const float den = posE + negE + 1e-16f;
+                const float logden = logf(den);
+                const float invc = 1.f / c;
+                stats[CY_STAT_LOGDEN * N + i] = logden;
+                stats[CY_STAT_INVC * N + i] = invc;
+                stats[CY_STAT_POSE * N + i] = c;  // slot reused: positive count (needed by pass-2 finalize)
+                if (variant == CY_SUPCON) {
+                    stats[CY_STAT_COEF * N + i] = 1.f / den;
+                    term = -(posL * invc - logden);
+                    // c == 0: the reference computes 0/0 = NaN (contrastive.py:95) -> posL*invc = 0*inf = NaN as well
+                } else if (variant == CY_SUPCON_EXCLUDE) {
+                    const float ratio = nc / (c + nc);                       // contrastive.py:88 (float32)
+                    stats[CY_STAT_AUX * N + i] = negE / (ratio + 1e-4f);     // A_i
+                }
+            } else {
+                const float posl2 = a0[u], sw = a1[u], invc = a2[u], c = a3[u];
+                term = -posl2 * invc;
+                if (variant == CY_SUPCON_EXCLUDE) {
+                    const float nc = a4[u];
+                    const float ratio = nc / (c + nc);
+                    stats[CY_STAT_COEF * N + i] = sw * invc / (ratio + 1e-4f);
+                } else {
+                    stats[CY_STAT_COEF * N + i] = sw * invc * expf(-a4[u]);
+                    sw_sum += sw;
+                    c_sum += c;
+                }
+            }
+            if (last) {
+                if (!isfinite(term)) bad += 1.f;
+                term_sum += term;
+            }
         }
     }
     __shared__ float red[4][32];

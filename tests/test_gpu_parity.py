@@ -447,10 +447,12 @@ def test_puiseg_golden(name):
 
 # ------------------------------------------------------------------------------------------------ tensor-pipe IIC shapes
 @pytest.mark.parametrize("B,K,H,W,pad", [(3, 13, 50, 72, 1), (2, 4, 33, 128, 1), (2, 16, 40, 64, 1), (1, 10, 9, 32, 1),
-                                          (2, 10, 30, 44, 2), (2, 5, 23, 36, 3), (1, 20, 40, 40, 1)])
+                                          (2, 10, 30, 44, 2), (2, 5, 23, 36, 3), (1, 20, 40, 40, 1),
+                                          (2, 9, 27, 40, 1), (2, 8, 19, 36, 1), (1, 6, 21, 68, 1)])
 def test_iic_tensor_pipe_shapes_vs_c_oracle(B, K, H, W, pad):
     """shapes that take csrc/iic_mma.cu (fp32, W % 4 == 0): ragged tiles in both directions, every k-step count of the
-    adjoint (K <= 5, <= 10, <= 16), the split-over-two-warps forward (K*T > 32), paddings 2 and 3 (forward only)"""
+    adjoint (K <= 5, <= 10, <= 16), the T-form adjoint with 0 / 1 / 2 channels in its shuffled row slot (K <= 8, 9, 10), the
+    split-over-two-warps forward (K*T > 32), paddings 2 and 3 (forward only)"""
     torch.manual_seed(B * 100 + K)
     x = (2 * torch.randn(B, K, H, W, device=DEV)).softmax(1).requires_grad_()
     y = (2 * torch.randn(B, K, H, W, device=DEV)).softmax(1).requires_grad_()
