@@ -180,11 +180,16 @@ class ShardedSupConLoss(torch.nn.Module):
     (the loss is invariant under row permutations inside a rank's block; the other ranks' blocks arrive sorted), one
     pack kernel (cat + permutation + is_normalized), then ``_ShardedInfoNCE`` (two more collectives)."""
 
-    def __init__(self, temperature=0.07, *, group=None, grad_scale: float = 1.0, path: str = "auto"):
+    def __init__(self, temperature=0.07, *, group=None, grad_scale: float = 1.0, path: str = "auto",
+                 deferred_checks: bool = False):
         super().__init__()
         self._t = temperature
         self._group = group
         self._grad_scale = float(grad_scale)
+        # deferred_checks: as in SupConLoss1 — device-side counters instead of the per-step host read, which makes the step
+        # (collectives included) capturable in a CUDA graph when the labels are a tensor
+        self._deferred_checks = deferred_checks
+        self._flags = None
         self._path = {"auto": L.CY_PATH_AUTO, "simt": L.CY_PATH_SIMT, "tcgen05": L.CY_PATH_TCGEN05}[path]
 
     def forward(self, proj_feat1: Tensor, proj_feat2: Tensor, target=None, mask: Optional[Tensor] = None, **kwargs):
@@ -219,6 +224,14 @@ class ShardedSupConLoss(torch.nn.Module):
         f2 = proj_feat2 if proj_feat2.stride(1) == 1 else proj_feat2.contiguous()
         z_loc, bad = _PackViews.apply(f1, f2, order, __debug__, False)
         loss, _ = _ShardedInfoNCE.apply(z_loc, labels_all, float(1.0 / self._t), self._path, self._group)
+        if self._deferred_checks:
+            nan = torch.isnan(loss.detach()).to(torch.int32).reshape(1)
+            cur = torch.cat((bad.to(torch.int32).reshape(1) if bad.numel() else torch.zeros_like(nan), nan))
+            if self._flags is None or self._flags.device != cur.device:
+                self._flags = cur.clone()
+            else:
+                self._flags.add_(cur)       # in place: the counters keep their address across CUDA-graph replays
+            return loss * self._grad_scale if self._grad_scale != 1.0 else loss
         if __debug__:
             nbad, val = torch.stack((bad[0].to(torch.float32), loss.detach())).tolist()
             assert nbad == 0, f"features need to be normalized first"
@@ -227,6 +240,16 @@ class ShardedSupConLoss(torch.nn.Module):
         if val != val:
             raise RuntimeError(loss)
         return loss * self._grad_scale if self._grad_scale != 1.0 else loss
+
+    def raise_if_flagged(self):
+        """deferred_checks mode: one host read of this rank's accumulated (un-normalised rows, NaN losses) counters"""
+        if self._flags is None:
+            return
+        nbad, nan = self._flags.tolist()
+        self._flags.zero_()
+        assert nbad == 0, f"features need to be normalized first"
+        if nan:
+            raise RuntimeError(f"loss was NaN in {nan} forward call(s)")
 
 
 def shard_iic_loss(criterion, group=None):
