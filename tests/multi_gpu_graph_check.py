@@ -9,10 +9,10 @@ sort, pack, Z all-gather, forward strip, statistics all-gather, backward strip, 
 device time per step of both, max over ranks.  Kept apart from multi_gpu_check.py: NCCL under stream capture is the one
 part of the stack that depends on the NCCL / driver pairing of the box.
 
-Status (round 1, B200 pool, torch 2.11 / NCCL 2.28.9): with ONE rank (`--nproc-per-node 1`, the three collectives still go
-through NCCL and are captured) replay is bit-identical to eager and 0.586 -> 0.449 ms/step at N = 16384.  With TWO ranks the
-script did not get past `make_graphed_callables` within 200 s, so multi-rank capture is NOT a supported mode yet and nothing
-in the test gate or in bench.py depends on it; run it under `timeout`."""
+Status (round 1, B200 pool, torch 2.11 / NCCL 2.28.9): one rank: replay bit-identical to eager, 0.586 -> 0.449 ms/step at
+N = 16384; two ranks at N = 8192: same loss, bf16 gradients within an ulp, 0.732 -> 0.219 ms/step.  Caveat found on the way:
+`dist.destroy_process_group()` blocks while captured graphs reference the communicator, so the script (and `bench.py
+--graph`) leave the teardown to process exit.  Run under `timeout`."""
 import argparse
 import os
 import sys
@@ -28,7 +28,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n-loc", type=int, default=4096, help="samples per view and rank")
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--watchdog", type=int, default=0, help="dump all python stacks and exit after this many seconds")
     args = ap.parse_args()
+    if args.watchdog:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -78,7 +82,8 @@ def main():
         e_loss = abs(le.item() - lg.item()) / abs(le.item())
         e_grad = max(((gae.float() - gag.float()).abs().max() / gae.float().abs().max()).item(),
                      ((gbe.float() - gbg.float()).abs().max() / gbe.float().abs().max()).item())
-        good = e_loss < 1e-6 and e_grad < 1e-6          # same kernels on the same inputs: identical up to atomics order
+        good = e_loss < 1e-6 and e_grad < 2e-2          # same kernels, same inputs: the bf16 gradients differ by at most an ulp
+                                                        # (fp32 atomics of the split backward commit in a different order)
         ok &= good
         print(f"[rank {rank}] batch {it}: eager {le.item():.6f} graph {lg.item():.6f} rel {e_loss:.1e} grad rel {e_grad:.1e} "
               f"{'OK' if good else 'FAIL'}", flush=True)
@@ -108,8 +113,12 @@ def main():
         print(f"N = {N} on {world} GPUs: eager {t_eager:.3f} ms/step ({N * N / t_eager / 1e9:.1f}e12 pairs/s), "
               f"graph replay {t_graph:.3f} ms/step ({N * N / t_graph / 1e9:.1f}e12 pairs/s)")
         print("graph replay parity OK" if flag.item() == 1.0 else "graph replay parity FAILED")
-    dist.destroy_process_group()
-    sys.exit(0 if flag.item() == 1.0 else 1)
+    # destroy_process_group() blocks while captured graphs still reference the communicator: leave the teardown to exit
+    code = 0 if flag.item() == 1.0 else 1
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(code)
 
 
 if __name__ == "__main__":
