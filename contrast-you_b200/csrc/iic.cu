@@ -580,8 +580,9 @@ static bool umma_enabled() {
     static int on = -1;
     if (on < 0) {
         // EXPERIMENTAL, off by default: CY_IIC_UMMA=1 routes the padding-1 adjoint through iic_umma.cu.  Parity holds, but at
-        // config 3 it runs at 150 us against 90 us for the mma.sync kernel (per-row handshakes between its warp roles are
-        // latency-bound, profiles/README.md) and one run in ~10 did not terminate, so it is not part of the tested product path.
+        // config 3 it runs at ~140 us against 90 us for the mma.sync kernel (per-row handshakes between its warp roles are
+        // latency-bound, profiles/README.md) and two of ~25 development runs did not terminate (not reproduced, cause open), so it is
+        // not part of the tested product path.
         const char* e = getenv("CY_IIC_UMMA");
         on = (e && e[0] == '1') ? 1 : 0;
     }

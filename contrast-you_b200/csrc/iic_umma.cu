@@ -153,7 +153,7 @@ iic_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_consta
                 const int b = u / per_image, trem = u % per_image;
                 const int h0 = (trem / g.tiles_w) * g.TH, w0 = (trem % g.tiles_w) * U_TWO;
                 const uint32_t s = (uint32_t)it % U_STAGES, ph = ((uint32_t)it / U_STAGES) & 1u;
-                mbar_wait_backoff(empty + s, ph ^ 1u, 256);
+                mbar_wait(empty + s, ph ^ 1u);
                 if (g.debug_skip == 3) { mbar_arrive(full + s); continue; }
                 mbar_arrive_expect_tx(full + s, (uint32_t)(K * HH * U_BOXW * 4));
                 tma_load_box(stage0 + (size_t)s * g.stage_bytes, side ? &tmy : &tmx, full + s, w0 - 4, h0 - 1, b * K);
@@ -223,7 +223,7 @@ iic_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_consta
         int it = 0;
         for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
             const uint32_t s = (uint32_t)it % U_STAGES, sph = ((uint32_t)it / U_STAGES) & 1u;
-            mbar_wait_backoff(full + s, sph);
+            mbar_wait(full + s, sph);
             const float* box = reinterpret_cast<const float*>(stage0 + (size_t)s * g.stage_bytes) + jj + 3;
             const int pstride = HH * U_BOXW;
             for (int rp = 0; rp < HH; ++rp, ++rc) {
@@ -252,7 +252,7 @@ iic_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_consta
                     }
                 }
                 if (timing) tph[0] += clock64() - tc0;
-                CY_T(1, mbar_wait_backoff(cempty + slot, ph ^ 1u));
+                CY_T(1, mbar_wait(cempty + slot, ph ^ 1u));
                 const long long tc1 = timing ? clock64() : 0;
                 tc_fence_after();
                 const uint32_t a = tmem + ((uint32_t)(quarter * 32) << 16) + slot * U_SLOT + 48;
@@ -289,7 +289,7 @@ iic_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_consta
             uint32_t v[3][VN], nv[3][VN];
             auto fetch = [&](uint32_t rcx, uint32_t (&dst)[3][VN]) {
                 const uint32_t slot = rcx % U_RING, ph = (rcx / U_RING) & 1u;
-                CY_T(0, mbar_wait_backoff(afull + slot, ph));
+                CY_T(0, mbar_wait(afull + slot, ph));
                 tc_fence_after();
                 const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + slot * U_SLOT + c0;
 #pragma unroll

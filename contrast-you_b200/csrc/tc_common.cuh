@@ -38,12 +38,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// wait with back-off: for roles that are not on the critical path — a spinning warp still takes issue slots from the warps
-// of its scheduler (measured: the single MMA-issuing thread of iic_umma.cu slowed down ~2x next to polling warps)
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns = 64) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
-}
-
 // ring position helper: stage index and phase parity of the it-th use of an S-deep ring
 template <int S>
 struct Ring {
