@@ -18,8 +18,12 @@
 //   so every fragment element is one conflict-free LDS.32 and a displacement is an address offset.
 // Backward (iic_bwd_mma_kernel):   out[o,h,w] = sum_{c,dy,dx} Wt[o,c,dy,dx] * in[c,h+dy-p,w+dx-p]
 //   D[o (16), pixel (8)] += Wt_dy[o, (c,dx)] * col[(c,dx), pixel] per box row, accumulated over dy in rolling HMMA
-//   accumulators; the weights (dL/dJ, scaled; flipped for dL/dx) stay in registers as pre-split A fragments for the
-//   whole kernel, half of the warps produce dL/dy from the x box and half dL/dx from the y box.
+//   accumulators (direct form), or D[(dy,o) (32), pixel (8)] with the dy contributions rolled through the C operands
+//   (T form, K <= 10, default); the weights (dL/dJ, scaled; flipped for dL/dx) stay in registers as pre-split A
+//   fragments for the whole kernel, half of the warps produce dL/dy from the x box and half dL/dx from the y box.
+//
+// What bounds these kernels (profiles/README.md): on sm_100a an mma.sync holds the issue port of its scheduler for its 8
+// pipe cycles, so per scheduler time = 8 * HMMAs + CUDA-core instructions; neither TMA nor HBM is the limiter.
 #include <cuda.h>
 #include <stdlib.h>
 
