@@ -141,3 +141,22 @@ def test_imsat_losses_match_reference_fixture():
     np.testing.assert_allclose(x.grad.numpy(), g["grad_x_dynamic"], rtol=1e-10, atol=1e-14)
     assert abs(float(dyn.dynamic_weight) - float(g["dynamic_weight_after"])) < 1e-12
     assert "dynamic_weight" in dyn.state_dict()
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours) prints ONE JSON line with the agreed keys,
+    the same metric / unit / config as our arm, and needs neither a GPU nor /root/reference."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "InfoNCE fwd+bwd pairs/s" and d["unit"] == "pairs/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["config"]["workload"].startswith("cfg4")
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
