@@ -121,64 +121,119 @@ def ncu_traffic():
         return {}
 
 
-def cpu_supcon_baseline(steps=1, warmup=0, seed=0):
-    """the C/OpenMP port of SupConLoss1 (oracle/oracle.c, float32 dot products like the reference's fp32 torch.mm) on
-    every host core, on a bounded sample: N=8192, d=256 (the reference itself cannot hold more: ~13 N x N fp32)."""
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _timed(fn, steps, warmup):
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        fn()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return statistics.median(times), times
+
+
+def cpu_supcon_baseline(steps=3, warmup=1, seed=0, want_port=True):
+    """SupConLoss1 fwd+bwd on the host cores, bounded sample N=8192, d=256, fp32 (the reference materialises ~13 N x N fp32
+    tensors: 8192 is what fits).  Primary figure: the reference's OWN module (baseline/_ref, torch CPU) when it is staged
+    (kind "reference"); the C/OpenMP port (oracle/oracle.c) is timed next to it (kind "port" when it is all there is).
+    Thread counts are set explicitly: torchrun exports OMP_NUM_THREADS=1 to its ranks."""
     import numpy as np
-    from oracle import c_oracle
+    from oracle import c_oracle, reference_arm
+    cores = host_cores()
+    c_oracle.set_num_threads(cores)
     rng = np.random.default_rng(seed)
     N, d = CPU_SAMPLE_N, 256
     z = rng.standard_normal((N, d), dtype=np.float32)
     z /= np.linalg.norm(z, axis=1, keepdims=True)
-    lab = np.tile(rng.integers(0, 512, N // 2).astype(np.int32), 2)
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        c_oracle.supcon_fwd_bwd(z, lab, t=0.07, prec=0)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    t = statistics.median(times)
-    return dict(value=N * N / t, unit="pairs/s", cores=c_oracle.num_threads(), kind="port",
-                sample=f"SupConLoss1 fwd+bwd, N={N}, d={d}, fp32, C/OpenMP port of contrastive.py (oracle/oracle.c), "
-                       f"median of {steps} run(s), {t:.3f} s/step"), t
+    lab_half = rng.integers(0, 512, N // 2).astype(np.int32)
+    lab = np.tile(lab_half, 2)
+    port = None
+    if want_port or not reference_arm.available():
+        t_port, _ = _timed(lambda: c_oracle.supcon_fwd_bwd(z, lab, t=0.07, prec=0), steps, warmup)
+        port = dict(value=N * N / t_port, unit="pairs/s", cores=c_oracle.num_threads(), kind="port", s_per_step=t_port,
+                    sample=f"SupConLoss1 fwd+bwd, N={N}, d={d}, fp32, C/OpenMP port of contrastive.py (oracle/oracle.c), "
+                           f"median of {steps} after {warmup} warm-up")
+    if not reference_arm.available():
+        return port, port["s_per_step"]
+    import torch
+    torch.set_num_threads(cores)
+    SupCon, _, _ = reference_arm.load()
+    zt = torch.from_numpy(z)
+    target = lab_half.tolist()
+    crit = SupCon()
+
+    def ref_step():
+        f1 = zt[:N // 2].clone().requires_grad_()
+        f2 = zt[N // 2:].clone().requires_grad_()
+        crit(f1, f2, target=target).backward()
+    t_ref, _ = _timed(ref_step, steps, warmup)
+    base = dict(value=N * N / t_ref, unit="pairs/s", cores=torch.get_num_threads(), kind="reference", s_per_step=t_ref,
+                sample=f"the reference's own contrastyou.losses.contrastive.SupConLoss1 (baseline/_ref, torch {torch.__version__} "
+                       f"CPU, fp32) fwd+bwd, N={N}, d={d}, median of {steps} after {warmup} warm-up")
+    if port is not None:
+        base["port"] = port
+    return base, t_ref
 
 
-def cpu_iic_baseline(steps=1, seed=0):
+def cpu_iic_baseline(steps=3, warmup=1, seed=0):
+    """IIDSegmentationLoss(padding=1) fwd+bwd at config 3's FULL batch (32 x 10 x 224 x 224 fp32) on the host cores"""
     import numpy as np
-    from oracle import c_oracle
+    from oracle import c_oracle, reference_arm
+    cores = host_cores()
+    c_oracle.set_num_threads(cores)
     rng = np.random.default_rng(seed)
-    B, K, H, W, pad = 8, IIC_CFG["K"], IIC_CFG["H"], IIC_CFG["W"], IIC_CFG["pad"]
+    B, K, H, W, pad = (IIC_CFG[k] for k in ("B", "K", "H", "W", "pad"))
 
     def sm(a):
         e = np.exp(a - a.max(1, keepdims=True))
         return (e / e.sum(1, keepdims=True)).astype(np.float32)
     x = sm(2 * rng.standard_normal((B, K, H, W), dtype=np.float32))
     y = sm(2 * rng.standard_normal((B, K, H, W), dtype=np.float32))
-    times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        c_oracle.iic_fwd_bwd(x, y, pad, prec=0)
-        times.append(time.perf_counter() - t0)
-    t = statistics.median(times)
-    return dict(value=B * H * W / t, unit="pixels/s", cores=c_oracle.num_threads(), kind="port",
-                sample=f"IIDSegmentationLoss(padding=1) fwd+bwd, {B}x{K}x{H}x{W} fp32 (a quarter of config 3's batch), "
-                       f"C/OpenMP port of discreteMI.py, {t:.3f} s/step")
+    t_port, _ = _timed(lambda: c_oracle.iic_fwd_bwd(x, y, pad, prec=0), steps, warmup)
+    port = dict(value=B * H * W / t_port, unit="pixels/s", cores=c_oracle.num_threads(), kind="port", s_per_step=t_port,
+                sample=f"IIDSegmentationLoss(padding=1) fwd+bwd, {B}x{K}x{H}x{W} fp32 (config 3, full batch), C/OpenMP port of "
+                       f"discreteMI.py, median of {steps} after {warmup} warm-up")
+    if not reference_arm.available():
+        return port
+    import torch
+    torch.set_num_threads(cores)
+    _, _, IIC = reference_arm.load()
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    crit = IIC(padding=pad)
+
+    def ref_step():
+        a, b = xt.clone().requires_grad_(), yt.clone().requires_grad_()
+        crit(a, b).backward()
+    t_ref, _ = _timed(ref_step, steps, warmup)
+    return dict(value=B * H * W / t_ref, unit="pixels/s", cores=torch.get_num_threads(), kind="reference", s_per_step=t_ref,
+                sample=f"the reference's own contrastyou.losses.discreteMI.IIDSegmentationLoss(padding=1) (baseline/_ref, torch CPU, "
+                       f"fp32) fwd+bwd, {B}x{K}x{H}x{W} (config 3, full batch), median of {steps} after {warmup} warm-up",
+                port=port)
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path timed on the host cores (the reference is pure Python and
-    cannot travel to the GPU box; the oracle port is the stand-in, DESIGN.md "Measurement")."""
+    """--impl reference: the reference's own CPU implementation of the path (baseline/_ref: its unmodified SupConLoss1 on
+    torch CPU; the C/OpenMP port when that directory is absent) on ALL host cores.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps = max(1, min(args.steps, 5))
-    base, t = cpu_supcon_baseline(steps=steps, warmup=1 if args.warmup else 0)
+    warm = 1 if args.warmup else 0
+    base, t = cpu_supcon_baseline(steps=steps, warmup=warm)
     wl = WORKLOADS[args.workload]
     line = {
         "impl": "reference", "metric": "InfoNCE fwd+bwd pairs/s", "value": base["value"], "unit": "pairs/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": 1 if args.warmup else 0, "ms_per_step": t * 1e3,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "note": f"CPU port timed on a bounded sample N={CPU_SAMPLE_N}; pairs/s is flat in N on CPU"},
+        "config": {"workload": wl["name"], "host_cores": host_cores(),
+                   "note": f"CPU reference timed on a bounded sample N={CPU_SAMPLE_N} (it materialises ~13 N x N fp32 tensors); "
+                           "pairs/s is flat in N on CPU"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -253,17 +308,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    counted = {"launches": 0}
+
     def timed_loop(fn, warmup, steps):
         for _ in range(warmup):
             fn()
         barrier()
         evs = []
+        launches0 = lib.cy_launch_count()
         for _ in range(steps):
             flush.zero_()                                   # L2 flush between timed iterations (outside the brackets)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record()
             evs.append((e0, e1))
         barrier()
+        counted["launches"] = lib.cy_launch_count() - launches0      # kernels of libcontrastyou_b200.so in the timed region
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
         if world > 1:
             t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -279,6 +338,49 @@ def main():
     clocks = sampler.stop() if sampler else None
     ms_per_step = total_ms / K_
     value = N * N / (ms_per_step * 1e-3)
+    value_launches = counted["launches"]
+
+    # ---- parity of exactly what was timed, OUTSIDE the timed region (VERDICT r1 #1b): N=1 against the float C oracle at
+    # full size; N>1: the sharded loss and this rank's gradient rows against a single-process evaluation of the gathered
+    # problem on the same GPU (max over ranks)
+    def parity_block():
+        loss, ga, gb = step(f1_dev, f2_dev, lab_dev)
+        got_loss = float(loss.item())
+        if world == 1:
+            if args.no_cpu:
+                return None
+            from oracle import c_oracle
+            c_oracle.set_num_threads(host_cores())
+            t0 = time.perf_counter()
+            import numpy as np
+            o = c_oracle.supcon_fwd_bwd(torch.cat([f1_dev, f2_dev]).float().cpu().numpy(),
+                                        np.tile(lab_dev.cpu().numpy().astype(np.int32), 2), t=0.07, prec=0)
+            ref_loss, ref_grad = o["loss"], torch.from_numpy(o["grad"])
+            got = torch.cat([ga, gb]).float().cpu()
+            against = f"C oracle (oracle/oracle.c, float32 dots, float64 row sums) at the full N={N}, {time.perf_counter() - t0:.1f} s"
+        else:
+            def gather(t):
+                out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+                dist.all_gather_into_tensor(out, t.contiguous())
+                return out
+            a_all, b_all, l_all = gather(f1_dev), gather(f2_dev), gather(lab_dev)
+            a_all.requires_grad_(); b_all.requires_grad_()
+            single = SupConLoss1(path=args.path)
+            ref = single(a_all, b_all, target=l_all)
+            ref.backward()
+            ref_loss = float(ref.item())
+            ref_grad = torch.cat([a_all.grad[sl], b_all.grad[sl]]).float().cpu()
+            got = torch.cat([ga, gb]).float().cpu()
+            against = f"single-process SupConLoss1 on the gathered N={N} problem, evaluated on every rank"
+        loss_rel = abs(got_loss - ref_loss) / abs(ref_loss)
+        grad_rel = float((got - ref_grad).abs().max() / ref_grad.abs().max())
+        if world > 1:
+            t = torch.tensor([loss_rel, grad_rel], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            loss_rel, grad_rel = float(t[0]), float(t[1])
+        return {"loss": got_loss, "ref_loss": ref_loss, "loss_rel": loss_rel, "grad_rel": grad_rel, "against": against,
+                "tolerance": {"loss_rel": 1e-4, "grad_rel": 1e-2}, "ok": bool(loss_rel <= 1e-4 and grad_rel <= 1e-2)}
+    parity = parity_block()
 
     # ---- end-to-end leg: host buffers -> module -> loss back on the host, every step
     def e2e_step():
@@ -382,9 +484,9 @@ def main():
                    "parallelism": f"rows{world}" if world > 1 else "single",
                    "l2": "256 MiB buffer written between timed iterations (inputs are smaller than L2)"},
         "e2e": e2e, "roofline": roofline, "clocks": clocks,
-        # kernels of libcontrastyou_b200.so per step: labels_canonicalize, pack_rows, infonce_fwd_tc + tc_reduce,
-        # infonce_finalize, infonce_bwd_tc + tc_convert, unpack_rows (single GPU; the sharded step has no pack / unpack)
-        "gpu_launches": ((8 if world == 1 else 6) * K_),
+        # kernels of libcontrastyou_b200.so launched inside the timed region of the `value` leg (cy_launch_count() difference)
+        "gpu_launches": int(value_launches),
+        "parity": parity,
     }
 
     # ---- IIC leg (config 3); weak scaling over the batch for world > 1
@@ -405,6 +507,22 @@ def main():
             return loss
         px = B * H * Wd * world
         iic_ms = timed_loop(lambda: iic_step(x_dev, y_dev), W_, K_) / K_
+        iic_launches = counted["launches"]
+        # parity of the timed IIC configuration against the C oracle (N=1, full batch), outside the timed region
+        iic_parity = None
+        if world == 1 and not args.no_cpu:
+            from oracle import c_oracle
+            c_oracle.set_num_threads(host_cores())
+            xa, ya = x_dev.detach().clone().requires_grad_(), y_dev.detach().clone().requires_grad_()
+            l_ = iic(xa, ya)
+            l_.backward()
+            o_ = c_oracle.iic_fwd_bwd(x_host.numpy(), y_host.numpy(), pad, prec=1)
+            lr = abs(float(l_.item()) - o_["loss"]) / abs(o_["loss"])
+            gr = max(float((xa.grad.cpu() - torch.from_numpy(o_["grad_x"])).abs().max() / abs(o_["grad_x"]).max()),
+                     float((ya.grad.cpu() - torch.from_numpy(o_["grad_y"])).abs().max() / abs(o_["grad_y"]).max()))
+            iic_parity = {"loss": float(l_.item()), "ref_loss": o_["loss"], "loss_rel": lr, "grad_rel": gr,
+                          "against": "C oracle (float64) at config 3's full size", "tolerance": {"loss_rel": 1e-4, "grad_rel": 1e-4},
+                          "ok": bool(lr <= 1e-4 and gr <= 1e-4)}
         iic_e2e_ms = timed_loop(lambda: iic_step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True)).item(),
                                 2, max(3, K_ // 2)) / max(3, K_ // 2)
         # kernel level
@@ -432,13 +550,13 @@ def main():
                          "joint": {"ms": j_ms, "achieved": gbs(bytes_map, j_ms), "frac": gbs(bytes_map, j_ms) / peaks["hbm_gbs"]},
                          "bwd": {"ms": b_ms, "achieved": gbs(2 * bytes_map, b_ms), "frac": gbs(2 * bytes_map, b_ms) / peaks["hbm_gbs"]},
                          "peak_source": peaks["source"] + " copy bandwidth"},
-            "gpu_launches": 4 * K_,     # cy_iic_joint (2 kernels), cy_iic_epilogue, cy_iic_bwd
+            "gpu_launches": int(iic_launches), "parity": iic_parity,
         }
 
     if rank == 0 and world == 1 and not args.no_cpu:
-        line["cpu_baseline"], _ = cpu_supcon_baseline(steps=1)
+        line["cpu_baseline"], _ = cpu_supcon_baseline(steps=3, warmup=1)
         if "iic" in line:
-            line["iic"]["cpu_baseline"] = cpu_iic_baseline(steps=1)
+            line["iic"]["cpu_baseline"] = cpu_iic_baseline(steps=3, warmup=1)
     if graphed is not None:
         line["graphed"] = graphed
     if rank == 0:

@@ -27,6 +27,7 @@ SIGNATURES = {
     "cy_abi_version": (_i32, []),
     "cy_last_error": (_c.c_char_p, []),
     "cy_device_sm_count": (_i32, []),
+    "cy_launch_count": (_c.c_ulonglong, []),
     "cy_infonce_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "cy_infonce_fwd": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "cy_infonce_fwd_pass2": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _i32, _f32, _i32, _vp, _vp,
@@ -99,3 +100,24 @@ def stream_ptr(device=None) -> int:
 
 def ptr(t):
     return None if t is None else t.data_ptr()
+
+
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def guard(t: torch.Tensor):
+    """Context that makes ``t``'s device current for the launches inside (the kernels launch in the current CUDA
+    context; a model living on cuda:1 without ``torch.cuda.set_device(1)`` must still work, like the reference does on
+    any device).  Free when the device is already current."""
+    idx = t.device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(idx)

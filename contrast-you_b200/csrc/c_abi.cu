@@ -2,9 +2,19 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace cy {
+
+// NVTX range around every compute entry point (header-only NVTX v3: a no-op unless a profiler is attached), so that an
+// nsys / ncu timeline shows the loss path by C-ABI call and the kernels nest under it.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define CY_NVTX(name) cy::NvtxRange nvtx_range__(name)
 
 static thread_local char g_err[512] = "";
 
@@ -13,6 +23,26 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev;
+}
+
+int device_sm_count() {
+    static int sms[CY_MAX_DEVICES] = {};
+    const int dev = current_device() % CY_MAX_DEVICES;
+    if (!sms[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
+    }
+    return sms[dev];
 }
 
 // infonce_simt.cu
@@ -53,12 +83,18 @@ static int check_infonce_args(const void* z, int dtype, int64_t N, int64_t d, in
 }
 
 // 0 = simt, 1 = tcgen05; negative = error
-static int resolve_path(int path, int dtype, int64_t N, int64_t d, int64_t ldz, const uint8_t* codes, int variant) {
-    const bool tc_ok = infonce_tc_supported(dtype, N, d, ldz, codes, variant);
+static int resolve_path(int path, int dtype, int64_t N, int64_t d, int64_t ldz, const uint8_t* codes, int variant,
+                        int64_t row_begin, int64_t row_end) {
+    // the tensor kernels work on 128-row blocks: a row range that is not 128-aligned (row-sharded ranks with an odd local
+    // batch) takes the CUDA-core kernels under CY_PATH_AUTO instead of failing; forward and backward see the same
+    // arguments and therefore take the same path
+    const bool rows_ok = (row_begin % 128) == 0 && ((row_end - row_begin) % 128) == 0;
+    const bool tc_ok = rows_ok && infonce_tc_supported(dtype, N, d, ldz, codes, variant);
     if (path == CY_PATH_TCGEN05) {
         if (!tc_ok) {
-            set_error("tcgen05 path needs bf16 / fp16, d == 256, N %% 128 == 0, labels, variant SUPCON (got dtype=%d N=%lld d=%lld variant=%d)",
-                      dtype, (long long)N, (long long)d, variant);
+            set_error("tcgen05 path needs bf16 / fp16, d == 256, N %% 128 == 0, a 128-aligned row range, labels, variant SUPCON "
+                      "(got dtype=%d N=%lld d=%lld variant=%d rows=[%lld,%lld))",
+                      dtype, (long long)N, (long long)d, variant, (long long)row_begin, (long long)row_end);
             return CY_ERR_UNSUPPORTED;
         }
         return 1;
@@ -88,6 +124,8 @@ int cy_device_sm_count(void) {
     return n;
 }
 
+unsigned long long cy_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 size_t cy_infonce_workspace_bytes(int64_t N, int64_t d, int dtype, int variant, int path) {
     (void)variant;
     if (path == CY_PATH_SIMT || dtype == CY_F32) return 16;
@@ -97,10 +135,11 @@ size_t cy_infonce_workspace_bytes(int64_t N, int64_t d, int dtype, int variant, 
 int cy_infonce_fwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, const uint8_t* codes,
                    int64_t row_begin, int64_t row_end, float inv_t, int variant, int path, float* stats, void* workspace,
                    size_t workspace_bytes, void* stream) {
+    CY_NVTX("cy_infonce_fwd");
     int rc = check_infonce_args(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, variant);
     if (rc) return rc;
     CY_CHECK_ARG(stats != nullptr, "stats is null");
-    const int p = resolve_path(path, dtype, N, d, ldz, codes, variant);
+    const int p = resolve_path(path, dtype, N, d, ldz, codes, variant, row_begin, row_end);
     if (p < 0) return p;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (p == 1) return infonce_fwd_tc(z, dtype, N, d, ldz, labels, row_begin, row_end, inv_t, stats, workspace, workspace_bytes, st);
@@ -110,6 +149,7 @@ int cy_infonce_fwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, 
 int cy_infonce_fwd_pass2(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
                          const uint8_t* codes, int64_t row_begin, int64_t row_end, float inv_t, int variant, float gamma,
                          int path, float* stats, void* workspace, size_t workspace_bytes, void* stream) {
+    CY_NVTX("cy_infonce_fwd_pass2");
     (void)workspace; (void)workspace_bytes;
     int rc = check_infonce_args(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, variant);
     if (rc) return rc;
@@ -122,6 +162,7 @@ int cy_infonce_fwd_pass2(const void* z, int dtype, int64_t N, int64_t d, int64_t
 
 int cy_infonce_finalize(int64_t N, int64_t row_begin, int64_t row_end, float inv_t, int variant, int pass, float* stats,
                         float* out4, void* stream) {
+    CY_NVTX("cy_infonce_finalize");
     (void)inv_t;
     CY_CHECK_ARG(stats && out4, "null pointer");
     CY_CHECK_ARG(pass == 1 || pass == 2, "pass must be 1 or 2");
@@ -131,10 +172,11 @@ int cy_infonce_finalize(int64_t N, int64_t row_begin, int64_t row_end, float inv
 int cy_infonce_bwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, const uint8_t* codes,
                    int64_t row_begin, int64_t row_end, float inv_t, int variant, float gamma, int path, const float* stats,
                    const float* gscale, void* dz, int64_t lddz, void* workspace, size_t workspace_bytes, void* stream) {
+    CY_NVTX("cy_infonce_bwd");
     int rc = check_infonce_args(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, variant);
     if (rc) return rc;
     CY_CHECK_ARG(stats && gscale && dz && lddz >= d, "null pointer or lddz < d");
-    const int p = resolve_path(path, dtype, N, d, ldz, codes, variant);
+    const int p = resolve_path(path, dtype, N, d, ldz, codes, variant, row_begin, row_end);
     if (p < 0) return p;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (p == 1)
@@ -145,17 +187,20 @@ int cy_infonce_bwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, 
 }
 
 int cy_infonce_masks(int64_t N, const int32_t* labels, const uint8_t* codes, float* pos_mask, float* neg_mask, void* stream) {
+    CY_NVTX("cy_infonce_masks");
     CY_CHECK_ARG(N >= 2 && (N % 2) == 0 && (labels || codes), "bad arguments");
     return infonce_masks(N, labels, codes, pos_mask, neg_mask, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int cy_labels_canonicalize(const void* src, int src_kind, int64_t n, int32_t* dst, void* stream) {
+    CY_NVTX("cy_labels_canonicalize");
     CY_CHECK_ARG(src && dst && n >= 1 && (src_kind == 0 || src_kind == 1), "bad arguments");
     return labels_canonicalize(src, src_kind, n, dst, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int cy_infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_t d, int64_t ld1, int64_t ld2,
                     const int64_t* order, void* z, int32_t* bad_rows, float* inv_norm, void* stream) {
+    CY_NVTX("cy_infonce_pack");
     CY_CHECK_ARG(f1 && f2 && z && n >= 1 && d >= 1 && ld1 >= d && ld2 >= d, "bad arguments");
     CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
     return infonce_pack(f1, f2, dtype, n, d, ld1, ld2, order, z, bad_rows, inv_norm, reinterpret_cast<cudaStream_t>(stream));
@@ -163,6 +208,7 @@ int cy_infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_
 
 int cy_infonce_unpack(const void* dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* order, void* g1,
                       void* g2, const void* z, const float* inv_norm, void* stream) {
+    CY_NVTX("cy_infonce_unpack");
     CY_CHECK_ARG(dz && g1 && g2 && n >= 1 && d >= 1 && lddz >= d, "bad arguments");
     CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
     CY_CHECK_ARG((z == nullptr) == (inv_norm == nullptr), "z and inv_norm go together");
@@ -184,6 +230,7 @@ static int check_iic(const void* x, const void* y, int dtype, int B, int K, int 
 
 int cy_iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, float* joint, void* workspace,
                  size_t workspace_bytes, void* stream) {
+    CY_NVTX("cy_iic_joint");
     int rc = check_iic(x, y, dtype, B, K, H, W, pad);
     if (rc) return rc;
     CY_CHECK_ARG(joint != nullptr, "joint is null");
@@ -197,6 +244,7 @@ size_t cy_iic_epilogue_workspace_bytes(int K, int pad) {
 
 int cy_iic_epilogue(const float* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
                     float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes, void* stream) {
+    CY_NVTX("cy_iic_epilogue");
     CY_CHECK_ARG(joint && loss && p00 && K >= 1 && pad >= 0, "bad arguments");
     return iic_epilogue(joint, K, pad, symmetric, lamda, eps, n_pixels, loss, p00, p_ij, djoint, workspace, workspace_bytes,
                         reinterpret_cast<cudaStream_t>(stream));
@@ -204,6 +252,7 @@ int cy_iic_epilogue(const float* joint, int K, int pad, int symmetric, float lam
 
 int cy_iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
                const float* gscale, void* dx, void* dy, void* stream) {
+    CY_NVTX("cy_iic_bwd");
     int rc = check_iic(x, y, dtype, B, K, H, W, pad);
     if (rc) return rc;
     CY_CHECK_ARG(djoint && gscale && dx && dy, "null pointer");

@@ -13,6 +13,17 @@ namespace cy {
 // thread-local error text behind cy_last_error()
 void set_error(const char* fmt, ...);
 
+// Per-DEVICE host-side caches (a process may drive several GPUs: the reference works on any device).
+constexpr int CY_MAX_DEVICES = 64;
+int current_device();       // cudaGetDevice(); 0 when the runtime cannot tell
+int device_sm_count();      // SM count of the current device, cached per device
+// dynamic shared memory opt-in of one kernel, remembered per device: need(smem) is true when the attribute has to be raised
+struct SmemAttrCache {
+    size_t granted[CY_MAX_DEVICES] = {};
+    bool need(size_t smem) const { return smem > granted[current_device() % CY_MAX_DEVICES]; }
+    void set(size_t smem) { granted[current_device() % CY_MAX_DEVICES] = smem; }
+};
+
 #define CY_CHECK_ARG(cond, ...)            \
     do {                                   \
         if (!(cond)) {                     \
@@ -21,8 +32,13 @@ void set_error(const char* fmt, ...);
         }                                  \
     } while (0)
 
+// every kernel launch of the library passes through CY_CHECK_LAUNCH: it also feeds cy_launch_count() (bench.py's
+// `gpu_launches` is this counter's difference over the timed region, not an estimate)
+void count_launch();
+
 #define CY_CHECK_LAUNCH(what)                                                    \
     do {                                                                         \
+        cy::count_launch();                                                      \
         cudaError_t e__ = cudaGetLastError();                                    \
         if (e__ != cudaSuccess) {                                                \
             cy::set_error("%s: %s", what, cudaGetErrorString(e__));              \

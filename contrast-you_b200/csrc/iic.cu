@@ -488,16 +488,7 @@ static int pick_kc(int K) {
     return 8;   // chunked
 }
 
-static int sm_count_cached() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+static int sm_count_cached() { return device_sm_count(); }
 
 static int pick_tw(int W, int maxtw) {
     // multiple of 4, <= maxtw, minimising padded width then number of tiles
@@ -572,7 +563,9 @@ int iic_joint_mma(const void* x, const void* y, int dtype, int B, int K, int H, 
 int iic_bwd_mma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
                 const float* gscale, void* dx, void* dy, cudaStream_t st);
 
-// iic_umma.cu (tcgen05 adjoint for padding = 1: TMA boxes -> bf16 hi/lo channels-last rows -> UMMA into TMEM)
+#ifdef CY_EXPERIMENTAL
+// iic_umma.cu (tcgen05 adjoint for padding = 1: TMA boxes -> bf16 hi/lo channels-last rows -> UMMA into TMEM).  Built
+// only with `make EXPERIMENTAL=1`: slower than the mma.sync adjoint and outside the test gate (profiles/README.md).
 int iic_bwd_umma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
                  const float* gscale, void* dx, void* dy, cudaStream_t st);
 
@@ -587,6 +580,7 @@ static bool umma_enabled() {
     }
     return on != 0;
 }
+#endif
 
 static bool mma_enabled() {
     static int on = -1;
@@ -709,11 +703,11 @@ int iic_epilogue(const float* joint, int K, int pad, int symmetric, float lamda,
         gscratch = reinterpret_cast<double*>(workspace);
         smem = 0;
     }
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
+    static SmemAttrCache attr;
+    if (attr.need(smem)) {
         cudaError_t e = cudaFuncSetAttribute(iic_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("iic_epilogue smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_smem = smem;
+        attr.set(smem);
     }
     iic_epilogue_kernel<<<1, EPI_THREADS, smem, st>>>(joint, K, pad, symmetric, (double)lamda, (double)eps, n_pixels, loss, p00, p_ij,
                                               djoint, gscratch);
@@ -749,10 +743,12 @@ static int dispatch_bwd(int pad, int kc, const void* x, const void* y, int dtype
 int iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
             const float* gscale, void* dx, void* dy, cudaStream_t st) {
     const int T = 2 * pad + 1;
+#ifdef CY_EXPERIMENTAL
     if (mma_enabled() && umma_enabled()) {
         const int rc = iic_bwd_umma(x, y, dtype, B, K, H, W, pad, djoint, gscale, dx, dy, st);
         if (rc != CY_ERR_UNSUPPORTED) return rc;
     }
+#endif
     if (mma_enabled()) {
         const int rc = iic_bwd_mma(x, y, dtype, B, K, H, W, pad, djoint, gscale, dx, dy, st);
         if (rc != CY_ERR_UNSUPPORTED) return rc;

@@ -617,22 +617,19 @@ int make_map3d(CUtensorMap* m, const void* base, int B, int K, int H, int W, int
     return CY_OK;
 }
 
+// CY_IIC_DEBUG_SKIP (phase timing: skips arithmetic / stores / loads, results INVALID) exists only in `make EXPERIMENTAL=1`
+// builds; the product library always computes.
 int debug_skip() {
+#ifdef CY_EXPERIMENTAL
     static int v = -1;
     if (v < 0) { const char* e = getenv("CY_IIC_DEBUG_SKIP"); v = e ? atoi(e) : 0; }
     return v;
+#else
+    return 0;
+#endif
 }
 
-int sm_count_mma() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+int sm_count_mma() { return device_sm_count(); }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -686,11 +683,11 @@ template <int MT, int NTW, int NSPLIT, int NCH>
 int launch_joint_mma(const CUtensorMap& tmx, const CUtensorMap& tmy, const MmaGeom& g, size_t smem, int grid, float* partials,
                      cudaStream_t st) {
     auto k = iic_joint_mma_kernel<MT, NTW, NSPLIT, NCH>;
-    static size_t attr_smem = 0;          // one process drives one device: raise the opt-in limit only when it grows
-    if (smem > attr_smem) {
+    static SmemAttrCache attr;            // raise the opt-in limit only when it grows (remembered per device)
+    if (attr.need(smem)) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("iic_joint_mma smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
-        attr_smem = smem;
+        attr.set(smem);
     }
     k<<<grid, FW_ROWS * NSPLIT * 32, smem, st>>>(tmx, tmy, g, partials);
     CY_CHECK_LAUNCH("iic_joint_mma");
@@ -732,11 +729,11 @@ template <int TWV, int KS, bool TFORM>
 int launch_bwd_mma(const CUtensorMap& tmx, const CUtensorMap& tmy, const MmaGeom& g, size_t smem, int grid, const float* djoint,
                    const float* gscale, float* dx, float* dy, cudaStream_t st) {
     auto k = iic_bwd_mma_kernel<TWV, KS, TFORM>;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
+    static SmemAttrCache attr;
+    if (attr.need(smem)) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("iic_bwd_mma smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
-        attr_smem = smem;
+        attr.set(smem);
     }
     k<<<grid, BW_THREADS, smem, st>>>(tmx, tmy, g, djoint, gscale, dx, dy);
     CY_CHECK_LAUNCH("iic_bwd_mma");

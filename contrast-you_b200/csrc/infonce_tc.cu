@@ -676,16 +676,7 @@ bool infonce_tc_supported(int dtype, int64_t N, int64_t d, int64_t ldz, const ui
 
 constexpr int FWD_BN = 128;
 
-static int sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
+static int sm_count() { return device_sm_count(); }
 
 // column splits of the backward: minimise waves x tiles-per-CTA (one CTA per SM), at least 16 tiles per CTA
 static int bwd_splits(int64_t N, int64_t rows) {

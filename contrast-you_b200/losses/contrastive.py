@@ -64,7 +64,9 @@ def _canonical_labels(target, n: int, device) -> Tensor:
             if bool(nan.any()):
                 raise ValueError("NaN labels are not supported for float64 targets")
         src, kind = torch.unique(target, return_inverse=True)[1].to(torch.int32).contiguous(), 1
-    L.check(lib.cy_labels_canonicalize(src.data_ptr(), kind, n, out.data_ptr(), L.stream_ptr()), "cy_labels_canonicalize")
+    with L.guard(out):
+        L.check(lib.cy_labels_canonicalize(src.data_ptr(), kind, n, out.data_ptr(), L.stream_ptr(out.device)),
+                "cy_labels_canonicalize")
     return out
 
 
@@ -87,24 +89,25 @@ class _InfoNCEFunction(torch.autograd.Function):
         lib = L.lib()
         N, d = z.shape
         dt = L.dtype_code(z)
-        st = L.stream_ptr()
-        stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=z.device)
-        out4 = torch.zeros(4, dtype=torch.float32, device=z.device)
-        ws_bytes = lib.cy_infonce_workspace_bytes(N, d, dt, variant, path)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
-        lp, cp = L.ptr(labels), L.ptr(codes)
-        L.check(lib.cy_infonce_fwd(z.data_ptr(), dt, N, d, z.stride(0), lp, cp, row_begin, row_end, inv_t, variant, path,
-                                   stats.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd")
-        L.check(lib.cy_infonce_finalize(N, row_begin, row_end, inv_t, variant, 1, stats.data_ptr(), out4.data_ptr(), st),
-                "cy_infonce_finalize")
-        if variant != L.CY_SUPCON:
-            L.check(lib.cy_infonce_fwd_pass2(z.data_ptr(), dt, N, d, z.stride(0), lp, cp, row_begin, row_end, inv_t, variant,
-                                             gamma, L.CY_PATH_SIMT, stats.data_ptr(), ws.data_ptr(), ws_bytes, st),
-                    "cy_infonce_fwd_pass2")
-            L.check(lib.cy_infonce_finalize(N, row_begin, row_end, inv_t, variant, 2, stats.data_ptr(), out4.data_ptr(), st),
+        with L.guard(z):
+            st = L.stream_ptr(z.device)
+            stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=z.device)
+            out4 = torch.zeros(4, dtype=torch.float32, device=z.device)
+            ws_bytes = lib.cy_infonce_workspace_bytes(N, d, dt, variant, path)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+            lp, cp = L.ptr(labels), L.ptr(codes)
+            L.check(lib.cy_infonce_fwd(z.data_ptr(), dt, N, d, z.stride(0), lp, cp, row_begin, row_end, inv_t, variant, path,
+                                       stats.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd")
+            L.check(lib.cy_infonce_finalize(N, row_begin, row_end, inv_t, variant, 1, stats.data_ptr(), out4.data_ptr(), st),
                     "cy_infonce_finalize")
-        if gather_stats is not None:
-            gather_stats(stats, out4)       # sharded: all-gather the row statistics, all-reduce the scalars
+            if variant != L.CY_SUPCON:
+                L.check(lib.cy_infonce_fwd_pass2(z.data_ptr(), dt, N, d, z.stride(0), lp, cp, row_begin, row_end, inv_t, variant,
+                                                 gamma, L.CY_PATH_SIMT, stats.data_ptr(), ws.data_ptr(), ws_bytes, st),
+                        "cy_infonce_fwd_pass2")
+                L.check(lib.cy_infonce_finalize(N, row_begin, row_end, inv_t, variant, 2, stats.data_ptr(), out4.data_ptr(), st),
+                        "cy_infonce_finalize")
+            if gather_stats is not None:
+                gather_stats(stats, out4)       # sharded: all-gather the row statistics, all-reduce the scalars
         ctx.save_for_backward(z, labels, codes, stats, ws)
         ctx.cfg = (inv_t, variant, gamma, path, row_begin, row_end)
         ctx.mark_non_differentiable(out4)
@@ -116,11 +119,12 @@ class _InfoNCEFunction(torch.autograd.Function):
         z, labels, codes, stats, ws = ctx.saved_tensors
         inv_t, variant, gamma, path, row_begin, row_end = ctx.cfg
         N, d = z.shape
-        gscale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
-        dz = torch.zeros_like(z) if (row_begin, row_end) != (0, N) else torch.empty_like(z)
-        L.check(lib.cy_infonce_bwd(z.data_ptr(), L.dtype_code(z), N, d, z.stride(0), L.ptr(labels), L.ptr(codes), row_begin,
-                                   row_end, inv_t, variant, gamma, path, stats.data_ptr(), gscale.data_ptr(), dz.data_ptr(),
-                                   dz.stride(0), ws.data_ptr(), ws.numel(), L.stream_ptr()), "cy_infonce_bwd")
+        with L.guard(z):
+            gscale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+            dz = torch.zeros_like(z) if (row_begin, row_end) != (0, N) else torch.empty_like(z)
+            L.check(lib.cy_infonce_bwd(z.data_ptr(), L.dtype_code(z), N, d, z.stride(0), L.ptr(labels), L.ptr(codes), row_begin,
+                                       row_end, inv_t, variant, gamma, path, stats.data_ptr(), gscale.data_ptr(), dz.data_ptr(),
+                                       dz.stride(0), ws.data_ptr(), ws.numel(), L.stream_ptr(z.device)), "cy_infonce_bwd")
         return dz, None, None, None, None, None, None, None, None, None
 
 
@@ -134,15 +138,19 @@ class _PackViews(torch.autograd.Function):
     def forward(ctx, f1, f2, order, check, normalize):
         lib = L.lib()
         n, d = f1.shape
-        z = torch.empty(2 * n, d, dtype=f1.dtype, device=f1.device)
-        bad = torch.zeros(1, dtype=torch.int32, device=f1.device) if (check and not normalize) else None
-        inv_norm = torch.empty(2 * n, dtype=torch.float32, device=f1.device) if normalize else None
-        L.check(lib.cy_infonce_pack(f1.data_ptr(), f2.data_ptr(), L.dtype_code(f1), n, d, f1.stride(0), f2.stride(0),
-                                    L.ptr(order), z.data_ptr(), L.ptr(bad), L.ptr(inv_norm), L.stream_ptr(f1.device)),
-                "cy_infonce_pack")
-        ctx.order = order
+        with L.guard(f1):
+            z = torch.empty(2 * n, d, dtype=f1.dtype, device=f1.device)
+            bad = torch.zeros(1, dtype=torch.int32, device=f1.device) if (check and not normalize) else None
+            inv_norm = torch.empty(2 * n, dtype=torch.float32, device=f1.device) if normalize else None
+            L.check(lib.cy_infonce_pack(f1.data_ptr(), f2.data_ptr(), L.dtype_code(f1), n, d, f1.stride(0), f2.stride(0),
+                                        L.ptr(order), z.data_ptr(), L.ptr(bad), L.ptr(inv_norm), L.stream_ptr(f1.device)),
+                    "cy_infonce_pack")
         ctx.shape = (n, d)
-        ctx.norm = (z, inv_norm) if normalize else None
+        ctx.has_order, ctx.normalize = order is not None, normalize
+        # saved through autograd (not as plain attributes): an output stored on ctx would keep the graph alive in a
+        # reference cycle that only the garbage collector frees
+        saved = ([order] if order is not None else []) + ([z, inv_norm] if normalize else [])
+        ctx.save_for_backward(*saved)
         if bad is None:
             bad = torch.zeros(0, dtype=torch.int32, device=f1.device)
         ctx.mark_non_differentiable(bad)
@@ -152,13 +160,16 @@ class _PackViews(torch.autograd.Function):
     def backward(ctx, dz, _grad_bad):
         lib = L.lib()
         n, d = ctx.shape
+        saved = list(ctx.saved_tensors)
+        order = saved.pop(0) if ctx.has_order else None
+        z, inv_norm = (saved[0], saved[1]) if ctx.normalize else (None, None)
         if dz.stride(1) != 1:
             dz = dz.contiguous()
-        g1 = torch.empty(n, d, dtype=dz.dtype, device=dz.device)
-        g2 = torch.empty(n, d, dtype=dz.dtype, device=dz.device)
-        z, inv_norm = ctx.norm if ctx.norm is not None else (None, None)
-        L.check(lib.cy_infonce_unpack(dz.data_ptr(), L.dtype_code(dz), n, d, dz.stride(0), L.ptr(ctx.order), g1.data_ptr(),
-                                      g2.data_ptr(), L.ptr(z), L.ptr(inv_norm), L.stream_ptr(dz.device)), "cy_infonce_unpack")
+        with L.guard(dz):
+            g1 = torch.empty(n, d, dtype=dz.dtype, device=dz.device)
+            g2 = torch.empty(n, d, dtype=dz.dtype, device=dz.device)
+            L.check(lib.cy_infonce_unpack(dz.data_ptr(), L.dtype_code(dz), n, d, dz.stride(0), L.ptr(order), g1.data_ptr(),
+                                          g2.data_ptr(), L.ptr(z), L.ptr(inv_norm), L.stream_ptr(dz.device)), "cy_infonce_unpack")
         return g1, g2, None, None, None
 
 
@@ -293,8 +304,9 @@ class _ContrastBase(nn.Module):
             if name in ("pos_mask", "neg_mask"):
                 pos = torch.empty(N, N, dtype=torch.float32, device=z.device)
                 neg = torch.empty(N, N, dtype=torch.float32, device=z.device)
-                L.check(L.lib().cy_infonce_masks(N, L.ptr(labels), L.ptr(codes), pos.data_ptr(), neg.data_ptr(),
-                                                 L.stream_ptr()), "cy_infonce_masks")
+                with L.guard(z):
+                    L.check(L.lib().cy_infonce_masks(N, L.ptr(labels), L.ptr(codes), pos.data_ptr(), neg.data_ptr(),
+                                                     L.stream_ptr(z.device)), "cy_infonce_masks")
                 self._dbg_cache.update(pos_mask=pos, neg_mask=neg)
             else:  # plotting only: plain torch, follows contrastive.py:14-20 (shift by the global max)
                 zf = z.float()

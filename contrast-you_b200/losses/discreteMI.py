@@ -42,7 +42,11 @@ _WORKSPACES = {}
 
 def _workspace(nbytes: int, device, stream: int):
     """Scratch for the per-CTA partial joints, cached per (device, stream): launches on one stream are ordered, so the
-    buffer can be reused by the next call without a fresh allocation (the loss is called once per hook per batch)."""
+    buffer can be reused by the next call without a fresh allocation (the loss is called once per hook per batch).
+    Not while a CUDA graph is being captured: that buffer belongs to the graph's private pool and its capture stream may
+    be recycled for eager work later, so captured calls get their own allocation."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
     key = (device.index, stream)
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
@@ -55,22 +59,24 @@ def _joint_forward(x, y, padding, joint=None):
     lib = L.lib()
     B, K, H, W = x.shape
     T = 2 * padding + 1
-    if joint is None:
-        joint = torch.empty(K, K, T, T, dtype=torch.float32, device=x.device)
-    st = L.stream_ptr()
-    ws_bytes = lib.cy_iic_workspace_bytes(B, K, H, W, padding)
-    ws = _workspace(ws_bytes, x.device, st)
-    L.check(lib.cy_iic_joint(x.data_ptr(), y.data_ptr(), L.dtype_code(x), B, K, H, W, padding, joint.data_ptr(),
-                             ws.data_ptr(), ws_bytes, st), "cy_iic_joint")
+    with L.guard(x):
+        if joint is None:
+            joint = torch.empty(K, K, T, T, dtype=torch.float32, device=x.device)
+        st = L.stream_ptr(x.device)
+        ws_bytes = lib.cy_iic_workspace_bytes(B, K, H, W, padding)
+        ws = _workspace(ws_bytes, x.device, st)
+        L.check(lib.cy_iic_joint(x.data_ptr(), y.data_ptr(), L.dtype_code(x), B, K, H, W, padding, joint.data_ptr(),
+                                 ws.data_ptr(), ws_bytes, st), "cy_iic_joint")
     return joint
 
 
 def _joint_backward(x, y, padding, djoint, gscale):
     lib = L.lib()
     B, K, H, W = x.shape
-    dx, dy = torch.empty_like(x), torch.empty_like(y)
-    L.check(lib.cy_iic_bwd(x.data_ptr(), y.data_ptr(), L.dtype_code(x), B, K, H, W, padding, djoint.data_ptr(),
-                           gscale.data_ptr(), dx.data_ptr(), dy.data_ptr(), L.stream_ptr()), "cy_iic_bwd")
+    with L.guard(x):
+        dx, dy = torch.empty_like(x), torch.empty_like(y)
+        L.check(lib.cy_iic_bwd(x.data_ptr(), y.data_ptr(), L.dtype_code(x), B, K, H, W, padding, djoint.data_ptr(),
+                               gscale.data_ptr(), dx.data_ptr(), dy.data_ptr(), L.stream_ptr(x.device)), "cy_iic_bwd")
     return dx, dy
 
 
@@ -149,15 +155,18 @@ class _IIDSegFunction(torch.autograd.Function):
         n_pixels = float(B * H * W)
         if reduce_joint is not None:
             n_pixels = reduce_joint(joint, n_pixels)
-        ws_bytes = lib.cy_iic_epilogue_workspace_bytes(K, padding)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
-        L.check(lib.cy_iic_epilogue(joint.data_ptr(), K, padding, int(bool(symmetric)), float(lamda), float(eps), n_pixels,
-                                    loss.data_ptr(), p00.data_ptr(), None, djoint.data_ptr(), L.ptr(ws), ws_bytes,
-                                    L.stream_ptr()), "cy_iic_epilogue")
+        with L.guard(x):
+            ws_bytes = lib.cy_iic_epilogue_workspace_bytes(K, padding)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+            L.check(lib.cy_iic_epilogue(joint.data_ptr(), K, padding, int(bool(symmetric)), float(lamda), float(eps), n_pixels,
+                                        loss.data_ptr(), p00.data_ptr(), None, djoint.data_ptr(), L.ptr(ws), ws_bytes,
+                                        L.stream_ptr(x.device)), "cy_iic_epilogue")
         ctx.save_for_backward(x, y, djoint)
         ctx.padding = padding
         ctx.mark_non_differentiable(p00)
-        return loss.reshape(()), p00
+        # the returned loss must not share storage (and hence a version counter) with the saved dL/dJ: callers scale losses
+        # in place (`loss *= w`), which would otherwise invalidate the backward
+        return loss.reshape(()).clone(), p00
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_p00):
@@ -186,6 +195,8 @@ class _IIDSegMultiFunction(torch.autograd.Function):
         T = 2 * padding + 1
         nj = K * K * T * T
         per = 1 + K * K + 2 * nj
+        if x0.device.index != torch.cuda.current_device():
+            torch.cuda.set_device(x0.device)      # (rare) model on a non-current device: make it current for the launches
         buf = torch.empty(S, per, dtype=torch.float32, device=x0.device)
         st = L.stream_ptr(x0.device)
         ws_bytes = lib.cy_iic_workspace_bytes(B, K, H, W, padding)
@@ -214,6 +225,8 @@ class _IIDSegMultiFunction(torch.autograd.Function):
         buf, *maps = ctx.saved_tensors
         padding, S, K, T, per = ctx.cfg
         B, _, H, W = maps[0].shape
+        if buf.device.index != torch.cuda.current_device():
+            torch.cuda.set_device(buf.device)
         gscale = (grad_loss.detach().to(torch.float32) / S).reshape(1).contiguous()
         st = L.stream_ptr(buf.device)
         dt = L.dtype_code(maps[0])
@@ -283,16 +296,13 @@ class IIDLoss(nn.Module):
         self.eps = float(eps)
 
     def forward(self, x_out: Tensor, x_tf_out: Tensor):
-        assert len(x_out.shape) == 2, x_out.shape
-        assert simplex(x_out), f"x_out not normalized."
-        assert simplex(x_tf_out), f"x_tf_out not normalized."
-        _, k = x_out.size()
-        p_i_j = compute_joint(x_out, x_tf_out)
-        assert p_i_j.size() == (k, k)
-        p_i = p_i_j.sum(dim=1).view(k, 1).expand(k, k)
-        p_j = p_i_j.sum(dim=0).view(1, k).expand(k, k)
-        loss = -p_i_j * (torch.log(p_i_j + 1e-10) - self.lamb * torch.log(p_j + 1e-10) - self.lamb * torch.log(p_i + 1e-10))
-        loss = loss.sum()
-        loss_no_lamb = -p_i_j * (torch.log(p_i_j + 1e-10) - torch.log(p_j + 1e-10) - torch.log(p_i + 1e-10))
-        loss_no_lamb = loss_no_lamb.sum()
-        return loss, loss_no_lamb, p_i_j
+        if x_out.dim() != 2:
+            raise AssertionError(x_out.shape)
+        joint = compute_joint(x_out, x_tf_out)                   # asserts both simplices (discreteMI.py:108-110, :210-211)
+        guard = 1e-10                                            # hard-coded in the reference (:118-123), not self.eps
+        log_rows = torch.log(joint.sum(dim=1, keepdim=True) + guard)      # [K, 1]
+        log_cols = torch.log(joint.sum(dim=0, keepdim=True) + guard)      # [1, K]
+        neg_entropy = (joint * torch.log(joint + guard)).sum()
+        marginals = (joint * (log_rows + log_cols)).sum()
+        # closed form of  -sum J (log J - lamb log p_j - lamb log p_i)  for lamb and for lamb = 1
+        return self.lamb * marginals - neg_entropy, marginals - neg_entropy, joint

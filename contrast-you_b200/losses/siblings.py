@@ -32,17 +32,12 @@ class Entropy(nn.Module):
         self._reduction = reduction
 
     def forward(self, input_: Tensor) -> Tensor:
-        assert input_.shape.__len__() >= 2
-        b, _, *s = input_.shape
+        if input_.dim() < 2:
+            raise AssertionError(f"Entropy expects [N, K, ...], got {tuple(input_.shape)}")
         assert simplex(input_), f"Entropy input should be a simplex"
-        e = input_ * (input_ + self._eps).log()
-        e = -1.0 * e.sum(1)
-        assert e.shape == torch.Size([b, *s])
-        if self._reduction == "mean":
-            return e.mean()
-        elif self._reduction == "sum":
-            return e.sum()
-        return e
+        per_sample = -(input_ * torch.log(input_ + self._eps)).sum(dim=1)      # [N, ...]: class axis reduced
+        reduce = {"mean": per_sample.mean, "sum": per_sample.sum, "none": lambda: per_sample}
+        return reduce[self._reduction]()
 
 
 entropy_criterion = Entropy(reduction="none", eps=1e-8)      # semi_seg/hooks/midl.py:13

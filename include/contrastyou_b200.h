@@ -52,6 +52,9 @@ int cy_abi_version(void);
 const char* cy_last_error(void);
 /* number of SMs of the current device (grid sizing of persistent kernels); <0 on error */
 int cy_device_sm_count(void);
+/* number of kernels this library has launched in the calling process so far (every launch site counts itself);
+ * monotonically increasing, used by bench.py to report `gpu_launches` as a measured difference */
+unsigned long long cy_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * InfoNCE / SupCon family.   Replaces exp_sim_temperature + SupConLoss1._forward / SelfPacedSupConLoss._forward

@@ -29,6 +29,7 @@ def lib():
         L = ctypes.CDLL(so)
         c_f, c_d, c_i32 = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
         L.oracle_num_threads.restype = ctypes.c_int
+        L.oracle_set_num_threads.argtypes = [ctypes.c_int]
         L.oracle_supcon_fwd_bwd.argtypes = [c_f, c_i32, ctypes.c_int64, ctypes.c_int64, ctypes.c_double, ctypes.c_int,
                                             c_d, c_d, c_d, c_f]
         L.oracle_iic_raw_joint.argtypes = [c_f, c_f] + [ctypes.c_int] * 6 + [c_d]
@@ -47,6 +48,11 @@ def _p(a, ct):
 
 def num_threads():
     return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n: int):
+    """explicit OpenMP team size (torchrun forces OMP_NUM_THREADS=1 on its ranks)"""
+    lib().oracle_set_num_threads(int(n))
 
 
 def supcon_fwd_bwd(z, labels, t=0.07, prec=1, want_grad=True):

@@ -318,6 +318,35 @@ def test_iic_full_size_properties():
     assert _relerr(xs.grad.cpu().numpy(), o["grad_x"]) <= FP32_TOL
 
 
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_iic_benchmark_size_vs_c_oracle(symmetric):
+    """BASELINE config 3 exactly as bench.py times it (32 x 10 x 224 x 224 fp32, padding 1): loss and both input gradients
+    against the float64 C oracle, fp32 bar 1e-4 (gradients relative to their max-norm)"""
+    torch.manual_seed(1)
+    B, K, H, W = 32, 10, 224, 224
+    x = (2 * torch.randn(B, K, H, W, device=DEV)).softmax(1).requires_grad_()
+    y = (2 * torch.randn(B, K, H, W, device=DEV)).softmax(1).requires_grad_()
+    loss = IIDSegmentationLoss(padding=1, symmetric=symmetric)(x, y)
+    loss.backward()
+    o = c_oracle.iic_fwd_bwd(x.detach().cpu().numpy(), y.detach().cpu().numpy(), 1, symmetric=symmetric)
+    assert loss.item() == pytest.approx(o["loss"], rel=FP32_TOL)
+    assert _relerr(x.grad.cpu().numpy(), o["grad_x"]) <= FP32_TOL
+    assert _relerr(y.grad.cpu().numpy(), o["grad_y"]) <= FP32_TOL
+
+
+def test_iic_loss_survives_inplace_scaling():
+    """callers scale the returned loss in place (`loss *= w`); the saved dL/dJ must not share its storage"""
+    torch.manual_seed(2)
+    x = torch.randn(2, 5, 16, 16, device=DEV).softmax(1).requires_grad_()
+    y = torch.randn(2, 5, 16, 16, device=DEV).softmax(1).requires_grad_()
+    ref = IIDSegmentationLoss(padding=1)(x, y)
+    gx = torch.autograd.grad(ref, x)[0]
+    loss = IIDSegmentationLoss(padding=1)(x, y)
+    loss *= 0.5
+    loss.backward()
+    assert _relerr(x.grad.cpu().numpy(), 0.5 * gx.cpu().numpy()) <= 1e-5
+
+
 @pytest.mark.parametrize("name", IID)
 def test_iid_golden(name):
     g = load_golden(name)
@@ -357,6 +386,46 @@ def test_tcgen05_matches_oracle_and_simt(N, classes, dtype):
     assert _relerr(out["tcgen05"][1], o["grad"]) <= BF16_TOL
     assert out["tcgen05"][0] == pytest.approx(out["simt"][0], rel=1e-4)
     assert _relerr(out["tcgen05"][1], out["simt"][1]) <= BF16_TOL
+
+
+@pytest.mark.parametrize("N,classes,name", [(65536, 4096, "cfg4"), (32768, 0, "cfg2")])
+def test_tcgen05_at_benchmark_size_vs_c_oracle(N, classes, name):
+    """the configurations bench.py TIMES (BASELINE config 4: N=65536, 4096 meta-labels — column-split backward; config 2:
+    N=32768 self-labels), through the default module path, against the chunked float64 C oracle on the same bf16-rounded
+    inputs: loss 1e-4, gradients 1e-2 of their max-norm (north_star's bf16 bar).  The oracle runs its float32-dot form
+    (prec=0: what the reference's fp32 torch.mm does, row sums in float64; validated against prec=1 in test_oracle.py) so
+    that a case costs ~15-30 s of host time instead of minutes."""
+    z, lab, n = _tc_case(N, classes, 1234 + N)
+    f1, f2 = z[:n].clone().requires_grad_(), z[n:].clone().requires_grad_()
+    lab_dev = lab.to(DEV)
+    loss = SupConLoss1()(f1, f2, target=lab_dev)
+    loss.backward()
+    o = c_oracle.supcon_fwd_bwd(z.float().cpu().numpy(), np.tile(lab.numpy().astype(np.int32), 2), t=0.07, prec=0)
+    assert loss.item() == pytest.approx(o["loss"], rel=1e-4)
+    got = torch.cat([f1.grad, f2.grad]).float().cpu().numpy()
+    assert np.isfinite(got).all()
+    assert _relerr(got, o["grad"]) <= BF16_TOL
+    # a gradient that is merely small everywhere would pass a max-norm test: check the direction too
+    cos = float((got.astype(np.float64) * o["grad"]).sum() / (np.linalg.norm(got.astype(np.float64)) * np.linalg.norm(o["grad"].astype(np.float64))))
+    assert cos > 0.9999
+
+
+def test_tcgen05_sharded_rows_not_128_aligned_fall_back():
+    """with path="auto" a row range that is not 128-aligned (8 ranks x n_local=96 -> 192 rows per rank) must take
+    the CUDA-core kernels instead of raising; the explicit tcgen05 path reports the reason"""
+    from contrast_you_b200.losses.contrastive import info_nce, _canonical_labels
+    z, lab, n = _tc_case(1536, 8, 77)
+    N = 2 * n
+    labels = _canonical_labels(lab.tolist(), n, z.device)
+    full, _ = info_nce(z.clone(), labels, None, 0.07, path=L.CY_PATH_SIMT)
+    total = 0.0
+    for r in range(8):
+        rb, re = r * 192, (r + 1) * 192
+        part, _ = info_nce(z.clone(), labels, None, 0.07, path=L.CY_PATH_AUTO, rows=(rb, re))
+        total += part.item()
+    assert total == pytest.approx(full.item(), rel=1e-5)
+    with pytest.raises(RuntimeError, match="128-aligned"):
+        info_nce(z.clone(), labels, None, 0.07, path=L.CY_PATH_TCGEN05, rows=(0, 192))
 
 
 def test_tcgen05_row_stats_match_simt():
