@@ -422,22 +422,22 @@ def main():
                            "static buffers inside the timed region"}
 
     # ---- kernel-level roofline: CUDA events around the C-ABI calls themselves (single GPU problem: this rank's rows)
-    z_all = torch.cat([f1_dev, f2_dev]) if world == 1 else cyd.gather_rank_major(torch.cat([f1_dev, f2_dev]))
-    if world == 1:
-        labels = _canonical_labels(lab_dev, n, dev)
-        rb, re = 0, N
-    else:
-        raw_all = torch.empty(world * n_loc, dtype=lab_dev.dtype, device=dev)
-        dist.all_gather_into_tensor(raw_all, lab_dev)
-        labels = cyd.rank_major_labels(raw_all, world, lambda r, m: _canonical_labels(r, m, dev))
-        rb, re = cyd.row_range(n_loc)
-    # same row order as the module uses: each rank's row block sorted by label (losses/contrastive.py sort_rows_by_label)
+    # same row order as the modules use: each rank's row block sorted by label
     with torch.no_grad():
-        for r in range(world):
-            z_all, labels = sort_rows_by_label(z_all, labels, r * 2 * n_loc, (r + 1) * 2 * n_loc)
-        z_all = z_all.contiguous()
+        if world == 1:
+            labels = _canonical_labels(lab_dev, n, dev)
+            z_all, labels = sort_rows_by_label(torch.cat([f1_dev, f2_dev]), labels)
+            z_all = z_all.contiguous()
+            rb, re = 0, N
+        else:
+            lab_loc = _canonical_labels(lab_dev, n_loc, dev)
+            order = torch.argsort(lab_loc)
+            z_all = cyd.gather_rank_major(torch.cat([f1_dev, f2_dev]).index_select(0, order).contiguous())
+            labels = cyd.gather_rank_major(lab_loc.index_select(0, order).contiguous())
+            rb, re = cyd.row_range(n_loc)
     path = {"auto": 0, "simt": 1, "tcgen05": 2}[args.path]
     stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev)
+    xstat = torch.zeros(N, 4, dtype=torch.float32, device=dev)
     out4 = torch.zeros(4, device=dev)
     ws_b = lib.cy_infonce_workspace_bytes(N, d, L.CY_BF16, 0, path)
     ws = torch.empty(ws_b, dtype=torch.uint8, device=dev)
@@ -447,17 +447,17 @@ def main():
 
     def k_fwd():
         L.check(lib.cy_infonce_fwd(z_all.data_ptr(), L.CY_BF16, N, d, d, labels.data_ptr(), None, rb, re, 1 / 0.07, 0, path,
-                                   stats.data_ptr(), ws.data_ptr(), ws_b, st), "fwd")
+                                   stats.data_ptr(), xstat.data_ptr(), ws.data_ptr(), ws_b, st), "fwd")
 
     def k_fin():
-        L.check(lib.cy_infonce_finalize(N, rb, re, 1 / 0.07, 0, 1, stats.data_ptr(), out4.data_ptr(), st), "fin")
+        if world > 1:
+            cyd.gather_rows_(xstat)
+        L.check(lib.cy_infonce_loss(N, 0, xstat.data_ptr(), out4.data_ptr(), ws.data_ptr(), ws_b, st), "loss")
 
     def k_bwd():
         L.check(lib.cy_infonce_bwd(z_all.data_ptr(), L.CY_BF16, N, d, d, labels.data_ptr(), None, rb, re, 1 / 0.07, 0, 0.0, path,
-                                   stats.data_ptr(), one.data_ptr(), dz.data_ptr(), d, ws.data_ptr(), ws_b, st), "bwd")
+                                   xstat.data_ptr(), one.data_ptr(), dz.data_ptr(), d, ws.data_ptr(), ws_b, st), "bwd")
     k_fwd(); k_fin()
-    if world > 1:
-        cyd.make_stats_exchange(n_loc)(stats, out4)
     kreps = max(3, min(K_, 10))
     fwd_ms = timed_loop(k_fwd, 2, kreps) / kreps
     bwd_ms = timed_loop(k_bwd, 2, kreps) / kreps
@@ -526,7 +526,7 @@ def main():
         iic_e2e_ms = timed_loop(lambda: iic_step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True)).item(),
                                 2, max(3, K_ // 2)) / max(3, K_ // 2)
         # kernel level
-        joint = torch.empty(Kc, Kc, 3, 3, device=dev)
+        joint = torch.empty(Kc, Kc, 3, 3, device=dev, dtype=torch.float64)
         wsj_b = lib.cy_iic_workspace_bytes(B, Kc, H, Wd, pad)
         wsj = torch.empty(wsj_b, dtype=torch.uint8, device=dev)
         dj = torch.randn(Kc, Kc, 3, 3, device=dev) * 1e-6

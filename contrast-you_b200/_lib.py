@@ -17,6 +17,7 @@ CY_F32, CY_BF16, CY_F16 = 0, 1, 2
 CY_SUPCON, CY_SUPCON_EXCLUDE, CY_SELFPACED_HARD, CY_SELFPACED_SOFT = 0, 1, 2, 3
 CY_PATH_AUTO, CY_PATH_SIMT, CY_PATH_TCGEN05 = 0, 1, 2
 CY_NSTAT = 8
+CY_ABI_VERSION = 2
 CY_STAT_LOGDEN, CY_STAT_INVC, CY_STAT_COEF, CY_STAT_AUX = 0, 1, 2, 3
 
 _c = ctypes
@@ -29,14 +30,14 @@ SIGNATURES = {
     "cy_device_sm_count": (_i32, []),
     "cy_launch_count": (_c.c_ulonglong, []),
     "cy_infonce_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32]),
-    "cy_infonce_fwd": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _i32, _i32, _vp, _vp, _sz, _vp]),
-    "cy_infonce_fwd_pass2": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _i32, _f32, _i32, _vp, _vp,
+    "cy_infonce_fwd": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "cy_infonce_fwd_pass2": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _i32, _f32, _i32, _vp, _vp, _vp,
                                     _sz, _vp]),
-    "cy_infonce_finalize": (_i32, [_i64, _i64, _i64, _f32, _i32, _i32, _vp, _vp, _vp]),
+    "cy_infonce_loss": (_i32, [_i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "cy_infonce_bwd": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _i32, _f32, _i32, _vp, _vp, _vp,
                               _i64, _vp, _sz, _vp]),
     "cy_infonce_masks": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp]),
-    "cy_labels_canonicalize": (_i32, [_vp, _i32, _i64, _vp, _vp]),
+    "cy_labels_canonicalize": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp]),
     "cy_infonce_pack": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "cy_infonce_unpack": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cy_iic_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
@@ -61,7 +62,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)      # AttributeError here == header / library mismatch
             fn.restype, fn.argtypes = res, args
-        if handle.cy_abi_version() != 1:
+        if handle.cy_abi_version() != CY_ABI_VERSION:
             raise RuntimeError("libcontrastyou_b200.so: ABI version mismatch")
         _LIB = handle
     return _LIB

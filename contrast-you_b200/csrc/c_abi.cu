@@ -48,25 +48,29 @@ int device_sm_count() {
 // infonce_simt.cu
 int infonce_fwd_simt(const void*, int, int64_t, int64_t, int64_t, const int32_t*, const uint8_t*, int64_t, int64_t, float, int,
                      int, float, float*, cudaStream_t);
-int infonce_finalize(int64_t, int64_t, int64_t, int, int, float*, float*, cudaStream_t);
 int infonce_bwd_simt(const void*, int, int64_t, int64_t, int64_t, const int32_t*, const uint8_t*, int64_t, int64_t, float, int,
                      float, const float*, const float*, void*, int64_t, cudaStream_t);
 int infonce_masks(int64_t, const int32_t*, const uint8_t*, float*, float*, cudaStream_t);
-int labels_canonicalize(const void*, int, int64_t, int32_t*, cudaStream_t);
+int labels_canonicalize(const void*, int, int64_t, int32_t*, int32_t*, cudaStream_t);
 int infonce_pack(const void*, const void*, int, int64_t, int64_t, int64_t, int64_t, const int64_t*, void*, int*, float*, cudaStream_t);
 int infonce_unpack(const void*, int, int64_t, int64_t, int64_t, const int64_t*, void*, void*, const void*, const float*, cudaStream_t);
 // infonce_tc.cu
 bool infonce_tc_supported(int dtype, int64_t N, int64_t d, int64_t ldz, const uint8_t* codes, int variant);
 size_t infonce_tc_workspace_bytes(int64_t N, int64_t d);
-int infonce_fwd_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, float*, void*, size_t,
+size_t infonce_loss_workspace_bytes(int64_t N);
+int infonce_fwd_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, int, float*, float*, void*, size_t,
                    cudaStream_t);
-int infonce_bwd_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, const float*, const float*,
-                   void*, int64_t, void*, size_t, cudaStream_t);
+int infonce_fwd2_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, int, float, float*, float*, void*,
+                    size_t, cudaStream_t);
+int infonce_rowstats(int64_t, int64_t, int64_t, float, int, int, float*, float*, cudaStream_t);
+int infonce_loss(int64_t, int, const float*, float*, void*, size_t, cudaStream_t);
+int infonce_bwd_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, int, float, const float*,
+                   const float*, void*, int64_t, void*, size_t, cudaStream_t);
 // iic.cu
 size_t iic_workspace_bytes(int, int, int, int, int);
-int iic_joint(const void*, const void*, int, int, int, int, int, int, float*, void*, size_t, cudaStream_t);
+int iic_joint(const void*, const void*, int, int, int, int, int, int, double*, void*, size_t, cudaStream_t);
 size_t iic_epilogue_workspace_bytes(int, int);
-int iic_epilogue(const float*, int, int, int, float, float, double, float*, float*, float*, float*, void*, size_t, cudaStream_t);
+int iic_epilogue(const double*, int, int, int, float, float, double, float*, float*, float*, float*, void*, size_t, cudaStream_t);
 int iic_bwd(const void*, const void*, int, int, int, int, int, int, const float*, const float*, void*, void*, cudaStream_t);
 
 static int check_infonce_args(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
@@ -85,16 +89,16 @@ static int check_infonce_args(const void* z, int dtype, int64_t N, int64_t d, in
 // 0 = simt, 1 = tcgen05; negative = error
 static int resolve_path(int path, int dtype, int64_t N, int64_t d, int64_t ldz, const uint8_t* codes, int variant,
                         int64_t row_begin, int64_t row_end) {
-    // the tensor kernels work on 128-row blocks: a row range that is not 128-aligned (row-sharded ranks with an odd local
-    // batch) takes the CUDA-core kernels under CY_PATH_AUTO instead of failing; forward and backward see the same
-    // arguments and therefore take the same path
-    const bool rows_ok = (row_begin % 128) == 0 && ((row_end - row_begin) % 128) == 0;
+    // the tensor kernels work on 128-row blocks: a row range that does not start on a multiple of 128 and end on one (or at
+    // N) — row-sharded ranks with an odd local batch — takes the CUDA-core kernels under CY_PATH_AUTO instead of failing;
+    // forward, pass 2 and backward see the same arguments and therefore take the same path
+    const bool rows_ok = (row_begin % 128) == 0 && ((row_end % 128) == 0 || row_end == N);
     const bool tc_ok = rows_ok && infonce_tc_supported(dtype, N, d, ldz, codes, variant);
     if (path == CY_PATH_TCGEN05) {
         if (!tc_ok) {
-            set_error("tcgen05 path needs bf16 / fp16, d == 256, N %% 128 == 0, a 128-aligned row range, labels, variant SUPCON "
-                      "(got dtype=%d N=%lld d=%lld variant=%d rows=[%lld,%lld))",
-                      dtype, (long long)N, (long long)d, variant, (long long)row_begin, (long long)row_end);
+            set_error("tcgen05 path needs bf16 / fp16, d in {128, 256}, N >= 256, a 128-aligned row range and label masks "
+                      "(got dtype=%d N=%lld d=%lld variant=%d rows=[%lld,%lld) codes=%d)",
+                      dtype, (long long)N, (long long)d, variant, (long long)row_begin, (long long)row_end, codes != nullptr);
             return CY_ERR_UNSUPPORTED;
         }
         return 1;
@@ -128,61 +132,69 @@ unsigned long long cy_launch_count(void) { return __atomic_load_n(&g_launches, _
 
 size_t cy_infonce_workspace_bytes(int64_t N, int64_t d, int dtype, int variant, int path) {
     (void)variant;
-    if (path == CY_PATH_SIMT || dtype == CY_F32) return 16;
-    return infonce_tc_workspace_bytes(N, d) + 16;
+    const size_t loss = infonce_loss_workspace_bytes(N);
+    if (path == CY_PATH_SIMT || dtype == CY_F32) return loss;
+    const size_t tc = infonce_tc_workspace_bytes(N, d);
+    return (tc > loss ? tc : loss) + 16;
 }
 
 int cy_infonce_fwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, const uint8_t* codes,
-                   int64_t row_begin, int64_t row_end, float inv_t, int variant, int path, float* stats, void* workspace,
-                   size_t workspace_bytes, void* stream) {
+                   int64_t row_begin, int64_t row_end, float inv_t, int variant, int path, float* stats, float* xstat,
+                   void* workspace, size_t workspace_bytes, void* stream) {
     CY_NVTX("cy_infonce_fwd");
     int rc = check_infonce_args(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, variant);
     if (rc) return rc;
-    CY_CHECK_ARG(stats != nullptr, "stats is null");
-    const int p = resolve_path(path, dtype, N, d, ldz, codes, variant, row_begin, row_end);
-    if (p < 0) return p;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (p == 1) return infonce_fwd_tc(z, dtype, N, d, ldz, labels, row_begin, row_end, inv_t, stats, workspace, workspace_bytes, st);
-    return infonce_fwd_simt(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, inv_t, variant, 1, 0.f, stats, st);
-}
-
-int cy_infonce_fwd_pass2(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
-                         const uint8_t* codes, int64_t row_begin, int64_t row_end, float inv_t, int variant, float gamma,
-                         int path, float* stats, void* workspace, size_t workspace_bytes, void* stream) {
-    CY_NVTX("cy_infonce_fwd_pass2");
-    (void)workspace; (void)workspace_bytes;
-    int rc = check_infonce_args(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, variant);
-    if (rc) return rc;
-    CY_CHECK_ARG(variant != CY_SUPCON, "CY_SUPCON has no second pass");
-    if (path == CY_PATH_TCGEN05) { set_error("pass 2 runs on the SIMT path only"); return CY_ERR_UNSUPPORTED; }
-    if (d > 256) { set_error("SIMT path supports d <= 256 (got %lld)", (long long)d); return CY_ERR_UNSUPPORTED; }
-    return infonce_fwd_simt(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, inv_t, variant, 2, gamma, stats,
-                            reinterpret_cast<cudaStream_t>(stream));
-}
-
-int cy_infonce_finalize(int64_t N, int64_t row_begin, int64_t row_end, float inv_t, int variant, int pass, float* stats,
-                        float* out4, void* stream) {
-    CY_NVTX("cy_infonce_finalize");
-    (void)inv_t;
-    CY_CHECK_ARG(stats && out4, "null pointer");
-    CY_CHECK_ARG(pass == 1 || pass == 2, "pass must be 1 or 2");
-    return infonce_finalize(N, row_begin, row_end, variant, pass, stats, out4, reinterpret_cast<cudaStream_t>(stream));
-}
-
-int cy_infonce_bwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, const uint8_t* codes,
-                   int64_t row_begin, int64_t row_end, float inv_t, int variant, float gamma, int path, const float* stats,
-                   const float* gscale, void* dz, int64_t lddz, void* workspace, size_t workspace_bytes, void* stream) {
-    CY_NVTX("cy_infonce_bwd");
-    int rc = check_infonce_args(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, variant);
-    if (rc) return rc;
-    CY_CHECK_ARG(stats && gscale && dz && lddz >= d, "null pointer or lddz < d");
+    CY_CHECK_ARG(stats != nullptr && xstat != nullptr, "stats / xstat is null");
     const int p = resolve_path(path, dtype, N, d, ldz, codes, variant, row_begin, row_end);
     if (p < 0) return p;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (p == 1)
-        return infonce_bwd_tc(z, dtype, N, d, ldz, labels, row_begin, row_end, inv_t, stats, gscale, dz, lddz, workspace,
+        return infonce_fwd_tc(z, dtype, N, d, ldz, labels, row_begin, row_end, inv_t, variant, stats, xstat, workspace, workspace_bytes, st);
+    rc = infonce_fwd_simt(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, inv_t, variant, 1, 0.f, stats, st);
+    if (rc) return rc;
+    return infonce_rowstats(N, row_begin, row_end, inv_t, variant, 1, stats, xstat, st);
+}
+
+int cy_infonce_fwd_pass2(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
+                         const uint8_t* codes, int64_t row_begin, int64_t row_end, float inv_t, int variant, float gamma,
+                         int path, float* stats, float* xstat, void* workspace, size_t workspace_bytes, void* stream) {
+    CY_NVTX("cy_infonce_fwd_pass2");
+    int rc = check_infonce_args(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, variant);
+    if (rc) return rc;
+    CY_CHECK_ARG(variant != CY_SUPCON, "CY_SUPCON has no second pass");
+    CY_CHECK_ARG(stats != nullptr && xstat != nullptr, "stats / xstat is null");
+    const int p = resolve_path(path, dtype, N, d, ldz, codes, variant, row_begin, row_end);
+    if (p < 0) return p;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (p == 1)
+        return infonce_fwd2_tc(z, dtype, N, d, ldz, labels, row_begin, row_end, inv_t, variant, gamma, stats, xstat, workspace,
+                               workspace_bytes, st);
+    rc = infonce_fwd_simt(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, inv_t, variant, 2, gamma, stats, st);
+    if (rc) return rc;
+    return infonce_rowstats(N, row_begin, row_end, inv_t, variant, 2, stats, xstat, st);
+}
+
+int cy_infonce_loss(int64_t N, int variant, const float* xstat, float* out4, void* workspace, size_t workspace_bytes, void* stream) {
+    CY_NVTX("cy_infonce_loss");
+    CY_CHECK_ARG(xstat && out4 && N >= 2, "null pointer");
+    CY_CHECK_ARG(variant >= CY_SUPCON && variant <= CY_SELFPACED_SOFT, "unknown variant %d", variant);
+    return infonce_loss(N, variant, xstat, out4, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_infonce_bwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, const uint8_t* codes,
+                   int64_t row_begin, int64_t row_end, float inv_t, int variant, float gamma, int path, const float* xstat,
+                   const float* gscale, void* dz, int64_t lddz, void* workspace, size_t workspace_bytes, void* stream) {
+    CY_NVTX("cy_infonce_bwd");
+    int rc = check_infonce_args(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, variant);
+    if (rc) return rc;
+    CY_CHECK_ARG(xstat && gscale && dz && lddz >= d, "null pointer or lddz < d");
+    const int p = resolve_path(path, dtype, N, d, ldz, codes, variant, row_begin, row_end);
+    if (p < 0) return p;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (p == 1)
+        return infonce_bwd_tc(z, dtype, N, d, ldz, labels, row_begin, row_end, inv_t, variant, gamma, xstat, gscale, dz, lddz, workspace,
                               workspace_bytes, st);
-    return infonce_bwd_simt(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, inv_t, variant, gamma, stats, gscale, dz,
+    return infonce_bwd_simt(z, dtype, N, d, ldz, labels, codes, row_begin, row_end, inv_t, variant, gamma, xstat, gscale, dz,
                             lddz, st);
 }
 
@@ -192,10 +204,11 @@ int cy_infonce_masks(int64_t N, const int32_t* labels, const uint8_t* codes, flo
     return infonce_masks(N, labels, codes, pos_mask, neg_mask, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int cy_labels_canonicalize(const void* src, int src_kind, int64_t n, int32_t* dst, void* stream) {
+int cy_labels_canonicalize(const void* src, int src_kind, int64_t n, int32_t* dst, int32_t* overflow, void* stream) {
     CY_NVTX("cy_labels_canonicalize");
-    CY_CHECK_ARG(src && dst && n >= 1 && (src_kind == 0 || src_kind == 1), "bad arguments");
-    return labels_canonicalize(src, src_kind, n, dst, reinterpret_cast<cudaStream_t>(stream));
+    CY_CHECK_ARG(src && dst && n >= 1 && src_kind >= 0 && src_kind <= 2, "bad arguments");
+    CY_CHECK_ARG(src_kind != 2 || overflow != nullptr, "int64 labels need the overflow counter");
+    return labels_canonicalize(src, src_kind, n, dst, overflow, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int cy_infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_t d, int64_t ld1, int64_t ld2,
@@ -228,7 +241,7 @@ static int check_iic(const void* x, const void* y, int dtype, int B, int K, int 
     return CY_OK;
 }
 
-int cy_iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, float* joint, void* workspace,
+int cy_iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, double* joint, void* workspace,
                  size_t workspace_bytes, void* stream) {
     CY_NVTX("cy_iic_joint");
     int rc = check_iic(x, y, dtype, B, K, H, W, pad);
@@ -242,7 +255,7 @@ size_t cy_iic_epilogue_workspace_bytes(int K, int pad) {
     return iic_epilogue_workspace_bytes(K, pad);
 }
 
-int cy_iic_epilogue(const float* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
+int cy_iic_epilogue(const double* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
                     float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes, void* stream) {
     CY_NVTX("cy_iic_epilogue");
     CY_CHECK_ARG(joint && loss && p00 && K >= 1 && pad >= 0, "bad arguments");

@@ -179,7 +179,7 @@ iic_joint_generic_kernel(const void* __restrict__ x, const void* __restrict__ y,
 // block = 32 joint entries (lanes) x 32 warps striding over the partials; fixed summation order: deterministic
 constexpr int RED_WARPS = 32;
 __global__ void __launch_bounds__(32 * RED_WARPS)
-iic_reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int nj, float* __restrict__ joint) {
+iic_reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int nj, double* __restrict__ joint) {
     __shared__ double acc[RED_WARPS][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + lane;
@@ -192,7 +192,7 @@ iic_reduce_partials_kernel(const float* __restrict__ partials, int n_partials, i
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k < RED_WARPS; ++k) t += acc[k][lane];
-        joint[i] = (float)t;
+        joint[i] = t;      // kept in double: the min-shift of the epilogue amplifies a float32 rounding of J ~sqrt(pixels)-fold
     }
 }
 static inline int reduce_grid(int nj) { return (nj + 31) / 32; }
@@ -233,7 +233,7 @@ __device__ double block_reduce_min(double v, double* red) {
 // dynamic smem: double A[nj] (B matrix, [dd][k1][k2]), P[nj], G[nj], sdisp[TT], colsum[TT*K], rowsum[TT*K]
 constexpr int EPI_THREADS = 1024;
 __global__ void __launch_bounds__(EPI_THREADS)
-iic_epilogue_kernel(const float* __restrict__ joint, int K, int pad, int symmetric, double lamda, double eps,
+iic_epilogue_kernel(const double* __restrict__ joint, int K, int pad, int symmetric, double lamda, double eps,
                     double n_pixels, float* __restrict__ loss, float* __restrict__ p00, float* __restrict__ p_ij,
                     float* __restrict__ djoint, double* __restrict__ gscratch) {
     extern __shared__ __align__(16) double sm[];
@@ -641,7 +641,7 @@ static int dispatch_joint(int pad, int kc, const void* x, const void* y, int dty
     return CY_ERR_UNSUPPORTED;
 }
 
-int iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, float* joint, void* workspace,
+int iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, double* joint, void* workspace,
               size_t workspace_bytes, cudaStream_t st) {
     const JointPlan p = plan_joint(B, K, H, W, pad);
     const int T = 2 * pad + 1, nj = K * K * T * T;
@@ -694,7 +694,7 @@ size_t iic_epilogue_workspace_bytes(int K, int pad) {
     return b > 160 * 1024 ? b : 0;      // small problems keep everything in shared memory
 }
 
-int iic_epilogue(const float* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
+int iic_epilogue(const double* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
                  float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     size_t smem = epilogue_scratch_doubles(K, pad) * sizeof(double);
     double* gscratch = nullptr;

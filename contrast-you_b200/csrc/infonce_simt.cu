@@ -151,94 +151,6 @@ infonce_fwd_simt_kernel(const void* __restrict__ z, int dtype, int64_t N, int d,
     }
 }
 
-// ------------------------------------------------------------------------------------------------- finalize
-// single block: deterministic reduction of the per-row loss terms
-__global__ void __launch_bounds__(1024)
-infonce_finalize_kernel(int64_t N, int64_t row_begin, int64_t row_end, int variant, int pass, float* __restrict__ stats,
-                        float* __restrict__ out4) {
-    float term_sum = 0.f, sw_sum = 0.f, c_sum = 0.f, bad = 0.f;
-    const bool last = (variant == CY_SUPCON) ? (pass == 1) : (pass == 2);
-    // one block walks all rows (fixed summation order); U rows per thread are loaded before any of them is stored so that the
-    // loads of a trip overlap (the stores go to the array the loads come from, which otherwise serialises the trips)
-    constexpr int U = 4;
-    for (int64_t i0 = row_begin + threadIdx.x; i0 < row_end; i0 += (int64_t)U * blockDim.x) {
-        float a0[U], a1[U], a2[U], a3[U], a4[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t i = i0 + (int64_t)u * blockDim.x;
-            const bool ok = i < row_end;
-            if (pass == 1) {
-                a0[u] = ok ? stats[CY_STAT_POSE * N + i] : 0.f;
-                a1[u] = ok ? stats[CY_STAT_AUX * N + i] : 0.f;
-                a2[u] = ok ? stats[CY_STAT_INVC * N + i] : 1.f;
-                a3[u] = ok ? stats[CY_STAT_NEGC * N + i] : 0.f;
-                a4[u] = ok ? stats[CY_STAT_POSL * N + i] : 0.f;
-            } else {
-                a0[u] = ok ? stats[CY_STAT_POSL * N + i] : 0.f;
-                a1[u] = ok ? stats[CY_STAT_SW * N + i] : 0.f;
-                a2[u] = ok ? stats[CY_STAT_INVC * N + i] : 0.f;
-                a3[u] = ok ? stats[CY_STAT_POSE * N + i] : 0.f;
-                a4[u] = ok ? (variant == CY_SUPCON_EXCLUDE ? stats[CY_STAT_NEGC * N + i] : stats[CY_STAT_LOGDEN * N + i]) : 0.f;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t i = i0 + (int64_t)u * blockDim.x;
-            if (i >= row_end) break;
-            float term = 0.f;
-            if (pass == 1) {
-                const float posE = a0[u], negE = a1[u], c = a2[u], nc = a3[u], posL = a4[u];
-                const float den = posE + negE + 1e-16f;
-                const float logden = logf(den);
-                const float invc = 1.f / c;
-                stats[CY_STAT_LOGDEN * N + i] = logden;
-                stats[CY_STAT_INVC * N + i] = invc;
-                stats[CY_STAT_POSE * N + i] = c;  // slot reused: positive count (needed by pass-2 finalize)
-                if (variant == CY_SUPCON) {
-                    stats[CY_STAT_COEF * N + i] = 1.f / den;
-                    term = -(posL * invc - logden);
-                    // c == 0: the reference computes 0/0 = NaN (contrastive.py:95) -> posL*invc = 0*inf = NaN as well
-                } else if (variant == CY_SUPCON_EXCLUDE) {
-                    const float ratio = nc / (c + nc);                       // contrastive.py:88 (float32)
-                    stats[CY_STAT_AUX * N + i] = negE / (ratio + 1e-4f);     // A_i
-                }
-            } else {
-                const float posl2 = a0[u], sw = a1[u], invc = a2[u], c = a3[u];
-                term = -posl2 * invc;
-                if (variant == CY_SUPCON_EXCLUDE) {
-                    const float nc = a4[u];
-                    const float ratio = nc / (c + nc);
-                    stats[CY_STAT_COEF * N + i] = sw * invc / (ratio + 1e-4f);
-                } else {
-                    stats[CY_STAT_COEF * N + i] = sw * invc * expf(-a4[u]);
-                    sw_sum += sw;
-                    c_sum += c;
-                }
-            }
-            if (last) {
-                if (!isfinite(term)) bad += 1.f;
-                term_sum += term;
-            }
-        }
-    }
-    __shared__ float red[4][32];
-    float v[4] = {term_sum, sw_sum, c_sum, bad};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = warp_sum(v[q]);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0)
-        for (int q = 0; q < 4; ++q) red[q][w] = v[q];
-    __syncthreads();
-    if (w == 0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float x = lane < (blockDim.x >> 5) ? red[q][lane] : 0.f;
-            x = warp_sum(x);
-            if (lane == 0 && last) out4[q] = (q == 0) ? x / (float)N : x;
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------- backward
 struct BwdSmem {
     float zi[BM][DMAX + 1];
@@ -253,7 +165,7 @@ template <int VARIANT, bool CODES>
 __global__ void __launch_bounds__(NT)
 infonce_bwd_simt_kernel(const void* __restrict__ z, int dtype, int64_t N, int d, int64_t ldz,
                         const int32_t* __restrict__ labels, const uint8_t* __restrict__ codes, int64_t n,
-                        int64_t row_begin, int64_t row_end, float inv_t, float gamma, const float* __restrict__ stats,
+                        int64_t row_begin, int64_t row_end, float inv_t, float gamma, const float4* __restrict__ xstat,
                         const float* __restrict__ gscale, void* __restrict__ dz, int64_t lddz) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdSmem& s = *reinterpret_cast<BwdSmem*>(smem_raw);
@@ -269,10 +181,12 @@ infonce_bwd_simt_kernel(const void* __restrict__ z, int dtype, int64_t N, int d,
         const int64_t i = i0 + tid;
         const bool ok = i < row_end;
         s.lab_i[tid] = (!CODES && ok) ? labels[i] : 0;
-        s.st_i[0][tid] = ok ? stats[CY_STAT_LOGDEN * N + i] : 0.f;
-        s.st_i[1][tid] = ok ? stats[CY_STAT_INVC * N + i] : 0.f;
-        s.st_i[2][tid] = ok ? stats[CY_STAT_COEF * N + i] : 0.f;
-        s.st_i[3][tid] = ok ? stats[CY_STAT_AUX * N + i] : 0.f;
+        // xstat row (contrastyou_b200.h CY_XS_*): x = log-denominator (self-paced), y = 1/c, z = coefficient, w = A_i (exclude)
+        const float4 xs = ok ? xstat[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s.st_i[0][tid] = xs.x;
+        s.st_i[1][tid] = xs.y;
+        s.st_i[2][tid] = xs.z;
+        s.st_i[3][tid] = xs.w;
     }
 
     float dacc[4][DMAX / 16];
@@ -292,10 +206,11 @@ infonce_bwd_simt_kernel(const void* __restrict__ z, int dtype, int64_t N, int d,
             const int64_t j = j0 + tid;
             const bool ok = j < N;
             s.lab_j[tid] = (!CODES && ok) ? labels[j] : 0;
-            s.st_j[0][tid] = ok ? stats[CY_STAT_LOGDEN * N + j] : 0.f;
-            s.st_j[1][tid] = ok ? stats[CY_STAT_INVC * N + j] : 0.f;
-            s.st_j[2][tid] = ok ? stats[CY_STAT_COEF * N + j] : 0.f;
-            s.st_j[3][tid] = ok ? stats[CY_STAT_AUX * N + j] : 0.f;
+            const float4 xs = ok ? xstat[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            s.st_j[0][tid] = xs.x;
+            s.st_j[1][tid] = xs.y;
+            s.st_j[2][tid] = xs.z;
+            s.st_j[3][tid] = xs.w;
         }
         __syncthreads();
 
@@ -402,11 +317,16 @@ __global__ void infonce_masks_kernel(int64_t N, int64_t n, const int32_t* __rest
     if (neg) neg[idx] = (bits & 2) ? 1.f : 0.f;
 }
 
-__global__ void labels_canonicalize_kernel(const void* __restrict__ src, int kind, int64_t n, int32_t* __restrict__ dst) {
+__global__ void labels_canonicalize_kernel(const void* __restrict__ src, int kind, int64_t n, int32_t* __restrict__ dst,
+                                           int32_t* __restrict__ overflow) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int32_t a, b;
-    if (kind == 0) {
+    if (kind == 2) {        // int64 labels (torch's default integer dtype): exact when they fit 32 bits, counted otherwise
+        const int64_t v = reinterpret_cast<const int64_t*>(src)[i];
+        if (v < (int64_t)INT32_MIN || v > (int64_t)INT32_MAX) atomicAdd(overflow, 1);
+        a = b = (int32_t)v;
+    } else if (kind == 0) {
         const float v = reinterpret_cast<const float*>(src)[i] + 0.0f;  // -0.0 -> +0.0
         if (v != v) {  // NaN never equals anything, not even its twin in the other view
             a = 0x7FC00000 | (int32_t)(i & 0x1FFFFF);
@@ -458,17 +378,11 @@ int infonce_fwd_simt(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz
     }
 }
 
-int infonce_finalize(int64_t N, int64_t row_begin, int64_t row_end, int variant, int pass, float* stats, float* out4,
-                     cudaStream_t st) {
-    infonce_finalize_kernel<<<1, 1024, 0, st>>>(N, row_begin, row_end, variant, pass, stats, out4);
-    CY_CHECK_LAUNCH("infonce_finalize");
-    return CY_OK;
-}
-
 template <int VARIANT>
 static int launch_bwd(const void* z, int dtype, int64_t N, int d, int64_t ldz, const int32_t* labels, const uint8_t* codes,
-                      int64_t row_begin, int64_t row_end, float inv_t, float gamma, const float* stats,
+                      int64_t row_begin, int64_t row_end, float inv_t, float gamma, const float* stats_,
                       const float* gscale, void* dz, int64_t lddz, cudaStream_t st) {
+    const float4* stats = reinterpret_cast<const float4*>(stats_);      // xstat [N][4]
     const int64_t rows = row_end - row_begin;
     const unsigned grid = (unsigned)((rows + BM - 1) / BM);
     const size_t smem = sizeof(BwdSmem);
@@ -513,8 +427,8 @@ int infonce_masks(int64_t N, const int32_t* labels, const uint8_t* codes, float*
     return CY_OK;
 }
 
-int labels_canonicalize(const void* src, int kind, int64_t n, int32_t* dst, cudaStream_t st) {
-    labels_canonicalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, kind, n, dst);
+int labels_canonicalize(const void* src, int kind, int64_t n, int32_t* dst, int32_t* overflow, cudaStream_t st) {
+    labels_canonicalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, kind, n, dst, overflow);
     CY_CHECK_LAUNCH("labels_canonicalize");
     return CY_OK;
 }

@@ -1,22 +1,33 @@
-// InfoNCE / SupCon on the 5th-gen tensor cores: TMA -> shared memory -> tcgen05.mma -> TMEM, flash-style.
+// InfoNCE / SupCon family on the 5th-gen tensor cores: TMA -> shared memory -> tcgen05.mma -> TMEM, flash-style.
 //
-// Scope: CY_SUPCON with label-derived masks, bf16 embeddings, d == 256, rows / N multiples of 128 (everything else
-// runs on the SIMT path).  The N x N similarity never exists in HBM: each CTA owns a 128-row block of Z (TMA-loaded
-// once, the MMA "A" operand), streams 128- or 64-row column tiles of Z through a TMA ring ("B" operand, K-major,
-// 128-byte swizzle), accumulates S = Zi Zj^T in TMEM and lets eight epilogue warps read it back with tcgen05.ld.
+// Scope: every variant of the family (SupConLoss1 with / without exclude_other_pos, SelfPacedSupConLoss hard / soft) with
+// label-derived masks, bf16 / fp16 embeddings, d in {128, 256}, any N >= 256 (a ragged last tile is masked in the
+// epilogue; TMA zero-fills the rows past N).  Explicit mask= codes, fp32 inputs and other d run on the SIMT path.
+// The N x N similarity never exists in HBM: each CTA owns a 128-row block of Z (held in TENSOR MEMORY as the MMA "A"
+// operand), streams column tiles of Z through a TMA ring ("B" operand, K-major, 128-byte swizzle), accumulates
+// S = Zi Zj^T in TMEM and lets eight epilogue warps read it back with tcgen05.ld.
 //
-//   forward  (infonce_fwd_tc_kernel):  per element E = 2^(s*c1 - c1), c1 = log2(e)/t; row sums D_i += E, positives
-//            c_i += [lab_i == lab_j], posS_i += [lab_i == lab_j] s; diagonal excluded on diagonal tiles only.
-//            Column range split over blockIdx.y; partial row sums go to a [slot][3][N] scratch, summed in a fixed
-//            order by infonce_tc_reduce_kernel (deterministic) into the CY_STAT_* rows cy_infonce_finalize reads.
-//   backward (infonce_bwd_tc_kernel):  S tile recomputed, W_ij = E_ij (coef_i + coef_j) - P_ij (invc_i + invc_j)
-//            written as bf16 into a swizzled K-major shared tile, second MMA dZ_i[128x256] += W[128x64] Zj[64x256]
-//            with the SAME Zj bytes read MN-major; dZ accumulates in TMEM across all column tiles of the row block
-//            and is scaled by gscale/(t N) on the way out (dZ = (1/t) W Z, W = G + G^T).
+//   pass 1   (infonce_fwd_tc_kernel<D,1,*>):  per element E = 2^(s*c1 - c1), c1 = log2(e)/t; row sums D_i += E, positives
+//            c_i += [lab_i == lab_j], posS_i += [..] s, posE_i += [..] E; diagonal / ragged columns excluded on the tiles
+//            that hold them only.  Column range split over blockIdx.y; partial row sums go to a [slot][4][N] scratch and
+//            are summed in a fixed order by infonce_rowstats_kernel (deterministic), which also forms the per-row
+//            statistics (log-denominator, 1/c, coefficient, loss term) the backward and the loss reduction read.
+//   pass 2   (infonce_fwd_tc_kernel<D,2,VARIANT>): exclude_other_pos / self-paced need per-element denominators / weights
+//            that depend on the pass-1 row sums — but only for POSITIVE pairs.  A CTA therefore visits only the column
+//            tiles whose label range intersects the label range of its rows (list built in shared memory from a per-tile
+//            [min,max] table): with rows sorted by label (the modules do that) this is a handful of tiles per row block
+//            instead of N/128, so the second sweep costs O(N), not O(N^2).  Unsorted callers get every tile: still exact.
+//   backward (infonce_bwd_tc_kernel<D,F16,VARIANT>):  S tile recomputed, W_ij = G_ij + G_ji written as bf16 straight back
+//            into the TMEM columns S was read from, second MMA dZ_i[128 x D] += W[128x64] Zj[64 x D] with the SAME Zj
+//            bytes read MN-major; dZ accumulates in TMEM across all column tiles of the row block and is scaled by
+//            gscale/(t N) on the way out (dZ = (1/t) W Z).  The variant only changes the
+//            positive-pair branch of the epilogue.  Column splits write fp32 slabs that one conversion kernel sums in a
+//            fixed order: bitwise reproducible gradients (the reference runs under use_deterministic_algorithms).
 //
 // Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane each), warp 2 TMEM allocator,
-// warps 4..11 epilogue (warp w reads TMEM lanes 32*(w%4).., column half (w-4)/4).
+// warp 3 tile-list builder (pass 2), warps 4..11 epilogue (warp w reads TMEM lanes 32*(w%4).., column half (w-4)/4).
 #include <cuda.h>
+#include <limits.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -25,55 +36,49 @@ namespace cy {
 
 using namespace tc;
 
-constexpr int TC_D = 256;            // embedding dim handled by this path
 constexpr int TC_BM = 128;           // rows per CTA (UMMA M)
 constexpr int TC_THREADS = 384;
-constexpr int TC_KBLK = TC_D / 64;   // 64-element (128-byte) K blocks per row
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr int FWD_BN = 128;          // column tile of the forward sweeps
+constexpr int BWD_BN = 64;           // column tile of the backward
+constexpr int P2_LISTCAP = 4096;     // pass-2 tile list capacity (uint16 entries) -> N <= 4096 * 128
+
+// contrastive.py:197-204 (evaluated for positive pairs only; elsewhere max(w, 1-P) = 1 and is unused)
+__device__ __forceinline__ float sp_weight_tc(int variant, float logp, float gamma) {
+    if (variant == CY_SELFPACED_HARD) return (-logp <= gamma) ? 1.f : 0.f;
+    return fmaxf(1.f + logp / gamma, 0.f);
+}
 
 // ------------------------------------------------------------------------------------------------------------ forward
-// -DCY_FWD_EX2_POLY=1 sends every other exponential of the forward epilogue to the FMA-pipe polynomial (tc_common.cuh:
-// ex2_poly).  Measured on B200 at N = 65536: 1.757 ms vs 1.646 ms with all of them on MUFU — the epilogue is issue-bound,
-// not MUFU-bound, so the default keeps MUFU.
-#ifndef CY_FWD_EX2_POLY
-#define CY_FWD_EX2_POLY 0
-#endif
-#if CY_FWD_EX2_POLY
-#define EX2_ALT ex2_poly
-#else
-#define EX2_ALT ex2_approx
-#endif
-#ifndef CY_FWD_A_TMEM
-#define CY_FWD_A_TMEM 1
-#endif
-// CY_FWD_A_TMEM: Zi in tensor memory (columns [384, 512)), three S accumulators instead of four, three Zj stages instead
-// of two.  With both operands in shared memory an M128 N128 K16 MMA fetches 8 KB per 64 clk — the whole 128 B/clk port —
-// while TMA refills the ring through the same port (64 KB per 1024-clk tile): the forward was shared-memory bound at
-// ~2/3 tensor utilisation.  A in TMEM halves the operand fetch.
-template <int BN>
-struct FwdSmem {
-    static constexpr bool A_TMEM = CY_FWD_A_TMEM != 0 && BN == 128;
-    static constexpr int NSTAGE = A_TMEM ? 3 : 2;
-    static constexpr int NACC = A_TMEM ? 3 : (512 / BN >= 4 ? 4 : 2);
-    static constexpr uint32_t A_BYTES = A_TMEM ? 0 : TC_BM * TC_D * 2;
-    static constexpr uint32_t B_BYTES = BN * TC_D * 2;
-    static constexpr uint32_t OFF_B = A_BYTES;
-    static constexpr uint32_t OFF_LAB = OFF_B + NSTAGE * B_BYTES;
-    static constexpr uint32_t OFF_BAR = OFF_LAB + 8 * (BN / 2) * 4;
-    static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024;   // + barriers + 1024-alignment slack
+// Zi lives in tensor memory (columns [384, 384 + D/2): two 16-bit elements per column), three S accumulators of 128 columns,
+// three Zj stages.  With both operands in shared memory an M128 N128 K16 MMA fetches 8 KB per 64 clk — the whole 128 B/clk
+// port, which TMA needs as well (round-1 profiles: 72 % tensor-active); with A in TMEM it is at 79 %.
+template <int D>
+struct FwdCfg {
+    static constexpr int BN = FWD_BN;
+    static constexpr int KBLK = D / 64;                         // 64-element (128-byte) K blocks per row
+    static constexpr int NSTAGE = 3;
+    static constexpr int NACC = 3;
+    static constexpr uint32_t B_BYTES = BN * D * 2;
+    static constexpr uint32_t OFF_LAB = NSTAGE * B_BYTES;
+    static constexpr uint32_t OFF_LIST = OFF_LAB + 8 * (BN / 2) * 4;
+    static constexpr uint32_t OFF_BAR = OFF_LIST + P2_LISTCAP * 2;
+    static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024;   // + barriers / scalars + 1024-alignment slack
 };
 
-template <int BN>
+template <int D, int PASS, int VARIANT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict__ labels, int N, int row_begin,
-                      int tiles_per_split, float c1, float* __restrict__ part, uint32_t idesc, const uint16_t* __restrict__ zrows,
-                      int64_t ldz) {
-    using S = FwdSmem<BN>;
+                      int ct_begin, int ct_end, int tiles_per_split, float c1, float inv_t, float gamma,
+                      float* __restrict__ part, int slot_base, uint32_t idesc, const uint16_t* __restrict__ zrows, int64_t ldz,
+                      const int2* __restrict__ tile_range, const float4* __restrict__ xstat) {
+    using S = FwdCfg<D>;
+    constexpr int BN = S::BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);    // 1024-aligned, still a shared pointer
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + S::OFF_B;
+    uint8_t* sB = smem;
     int32_t* sLab = reinterpret_cast<int32_t*>(smem + S::OFF_LAB);
+    uint16_t* sList = reinterpret_cast<uint16_t*>(smem + S::OFF_LIST);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
     uint64_t* a_full = bars;
     uint64_t* b_full = bars + 1;
@@ -81,69 +86,92 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
     uint64_t* acc_full = b_empty + S::NSTAGE;
     uint64_t* acc_empty = acc_full + S::NACC;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + S::NACC);
+    int32_t* sMisc = reinterpret_cast<int32_t*>(tmem_slot + 1);      // [0..7] row label min / max per warp, [8] list length
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = row_begin + blockIdx.x * TC_BM;              // first global row of this CTA
-    const int n_ctiles = N / BN;
-    const int ct0 = blockIdx.y * tiles_per_split;
-    const int ct1 = min(n_ctiles, ct0 + tiles_per_split);
 
     if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
     if (warp == 1 && lane == 0) {
-        mbar_init(a_full, S::A_TMEM ? 8 : 1);
+        mbar_init(a_full, 8);
         for (int i = 0; i < S::NSTAGE; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         for (int i = 0; i < S::NACC; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 8); }
         fence_barrier_init();
     }
     if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    if constexpr (PASS == 2) {
+        if (threadIdx.x < TC_BM) {                                // label range of this CTA's rows
+            const int gi = row0 + (int)threadIdx.x;
+            const int32_t lab = labels[min(gi, N - 1)];
+            const int32_t lo = __reduce_min_sync(0xffffffffu, gi < N ? lab : INT_MAX);
+            const int32_t hi = __reduce_max_sync(0xffffffffu, gi < N ? lab : INT_MIN);
+            if (lane == 0) { sMisc[2 * warp] = lo; sMisc[2 * warp + 1] = hi; }
+        }
+        __syncthreads();
+        if (warp == 3) {                                          // column tiles that can hold a positive pair of these rows
+            const int32_t rlo = min(min(sMisc[0], sMisc[2]), min(sMisc[4], sMisc[6]));
+            const int32_t rhi = max(max(sMisc[1], sMisc[3]), max(sMisc[5], sMisc[7]));
+            int count = 0;
+            for (int base = ct_begin; base < ct_end; base += 32) {
+                const int ct = base + lane;
+                bool hit = false;
+                if (ct < ct_end) {
+                    const int2 r = tile_range[ct];
+                    hit = r.y >= rlo && r.x <= rhi;
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                if (hit) sList[count + __popc(m & ((1u << lane) - 1u))] = (uint16_t)ct;
+                count += __popc(m);
+            }
+            if (lane == 0) sMisc[8] = count;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_a = tmem_base + 384;        // A_TMEM: Zi, columns [384, 512)
+    const uint32_t tmem_a = tmem_base + 384;        // Zi, columns [384, 384 + D/2)
+
+    int ct0 = 0, ntile;
+    if constexpr (PASS == 1) {
+        ct0 = ct_begin + (int)blockIdx.y * tiles_per_split;
+        ntile = max(0, min(ct_end, ct0 + tiles_per_split) - ct0);
+    } else {
+        ntile = sMisc[8];
+    }
+    auto tile_at = [&](int k) -> int { return PASS == 1 ? ct0 + k : (int)sList[k]; };
 
     if (warp == 0) {
         if (elect_one()) {
-            if constexpr (!S::A_TMEM) {
-                mbar_arrive_expect_tx(a_full, S::A_BYTES);
-                for (int kb = 0; kb < TC_KBLK; ++kb)
-                    for (int hb = 0; hb < TC_BM / 64; ++hb)
-                        tma_load_2d(sA + kb * (TC_BM * 128) + hb * 8192, &tmap, a_full, kb * 64, row0 + hb * 64);
-            }
             Ring<S::NSTAGE> ring;
-            for (int ct = ct0; ct < ct1; ++ct, ring.next()) {
+            for (int k = 0; k < ntile; ++k, ring.next()) {
+                const int ct = tile_at(k);
                 const uint32_t s = ring.stage();
                 mbar_wait(b_empty + s, ring.phase() ^ 1u);
                 mbar_arrive_expect_tx(b_full + s, S::B_BYTES);
                 uint8_t* dst = sB + s * S::B_BYTES;
-                for (int kb = 0; kb < TC_KBLK; ++kb)
+                for (int kb = 0; kb < S::KBLK; ++kb)
                     for (int hb = 0; hb < BN / 64; ++hb)
                         tma_load_2d(dst + kb * (BN * 128) + hb * 8192, &tmap, b_full + s, kb * 64, ct * BN + hb * 64);
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            const uint32_t a_addr = smem_u32(sA);        // idesc: M128 x N(BN) x K16, both operands K-major, bf16 or fp16
-            mbar_wait(a_full, 0);
+            mbar_wait(a_full, 0);                   // idesc: M128 x N(BN) x K16, A from TMEM, B K-major, bf16 or fp16
             Ring<S::NSTAGE> ring;
             Ring<S::NACC> acc;
-            for (int ct = ct0; ct < ct1; ++ct, ring.next(), acc.next()) {
+            for (int k = 0; k < ntile; ++k, ring.next(), acc.next()) {
                 const uint32_t s = ring.stage(), a = acc.stage();
                 mbar_wait(b_full + s, ring.phase());
                 mbar_wait(acc_empty + a, acc.phase() ^ 1u);
                 tc_fence_after();
                 const uint32_t b_addr = smem_u32(sB + s * S::B_BYTES);
 #pragma unroll
-                for (int kb = 0; kb < TC_KBLK; ++kb)
+                for (int kb = 0; kb < S::KBLK; ++kb)
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        if constexpr (S::A_TMEM)
-                            umma_bf16_ts(tmem_base + a * BN, tmem_a + (kb * 4 + ks) * 8,
-                                         smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc, (kb | ks) != 0);
-                        else
-                            umma_bf16(tmem_base + a * BN, smem_desc(a_addr + kb * (TC_BM * 128) + ks * 32, 16, 1024),
-                                      smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc, (kb | ks) != 0);
-                    }
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_bf16_ts(tmem_base + a * BN, tmem_a + (kb * 4 + ks) * 8,
+                                     smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc, (kb | ks) != 0);
                 umma_commit(b_empty + s);
                 umma_commit(acc_full + a);
             }
@@ -152,19 +180,20 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
         const int q = warp & 3, h = (warp - 4) >> 2, ew = warp - 4;
         const int row = q * 32 + lane;
         const int gi = row0 + row;
-        const int32_t my_lab = labels[gi];
-        if constexpr (S::A_TMEM) {
-            // this thread's half row of Zi (128 elements = 64 packed columns) -> tensor memory lanes q*32.., columns h*64..
-            const uint4* src = reinterpret_cast<const uint4*>(zrows + (size_t)gi * ldz + h * 128);
+        const int gic = min(gi, N - 1);                        // rows past N (ragged last block) compute on row N-1, store nothing
+        const int32_t my_lab = labels[gic];
+        {
+            // this thread's half row of Zi (D/2 elements = D/4 packed columns) -> tensor memory lanes q*32.., columns h*D/4..
+            const uint4* src = reinterpret_cast<const uint4*>(zrows + (size_t)gic * ldz + h * (D / 2));
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < D / 128; ++c) {
                 uint32_t r[32];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const uint4 v = __ldg(src + c * 8 + e);
                     r[4 * e] = v.x; r[4 * e + 1] = v.y; r[4 * e + 2] = v.z; r[4 * e + 3] = v.w;
                 }
-                tmem_st_32x32(tmem_a + (uint32_t(q * 32) << 16) + h * 64 + c * 32, r);
+                tmem_st_32x32(tmem_a + (uint32_t(q * 32) << 16) + h * (D / 4) + c * 32, r);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -172,20 +201,31 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
             if (lane == 0) mbar_arrive(a_full);
         }
         int32_t* wlab = sLab + ew * (BN / 2);
-        float D0 = 0.f, D1 = 0.f, D2 = 0.f, D3 = 0.f, posS = 0.f;
-        int cnt = 0;
         constexpr int NCH = BN / 64;                       // 32-column chunks per warp and tile
         // label range of this warp's 32 rows: a column chunk whose label range does not intersect it holds no positive
         // pair, whatever the order of the rows (callers that sort rows by label make this the common case)
         const int32_t row_lo = __reduce_min_sync(0xffffffffu, my_lab), row_hi = __reduce_max_sync(0xffffffffu, my_lab);
         int32_t lab_next[NCH];
-        if (ct0 < ct1) {
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) lab_next[c] = labels[ct0 * BN + h * (BN / 2) + c * 32 + lane];
+        for (int c = 0; c < NCH; ++c) lab_next[c] = 0;
+        if (ntile > 0) {
+            const int j0 = tile_at(0) * BN + h * (BN / 2);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) lab_next[c] = labels[min(j0 + c * 32 + lane, N - 1)];
+        }
+        // pass 1 accumulators
+        float D0 = 0.f, D1 = 0.f, D2 = 0.f, D3 = 0.f, posS = 0.f, posE = 0.f;
+        int cnt = 0;
+        // pass 2 accumulators and the row statistic they need (exclude: A_i; self-paced: log-denominator)
+        float r0 = 0.f, r1 = 0.f, rstat = 0.f;
+        if constexpr (PASS == 2) {
+            const float4 xs = xstat[gic];
+            rstat = (VARIANT == CY_SUPCON_EXCLUDE) ? xs.w : xs.x;
         }
         Ring<S::NACC> acc;
-        for (int ct = ct0; ct < ct1; ++ct, acc.next()) {
+        for (int k = 0; k < ntile; ++k, acc.next()) {
             const uint32_t a = acc.stage();
+            const int ct = tile_at(k);
             const int jbase = ct * BN + h * (BN / 2);          // first global column of this warp's half
             __syncwarp();
             int32_t cmin = lab_next[0], cmax = lab_next[0];
@@ -197,9 +237,10 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
             }
             const bool may_have_pos = __reduce_max_sync(0xffffffffu, cmax) >= row_lo && __reduce_min_sync(0xffffffffu, cmin) <= row_hi;
             __syncwarp();
-            if (ct + 1 < ct1) {                                // next tile's labels travel while this tile is processed
+            if (k + 1 < ntile) {                               // next tile's labels travel while this tile is processed
+                const int jn = tile_at(k + 1) * BN + h * (BN / 2);
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) lab_next[c] = labels[jbase + BN + c * 32 + lane];
+                for (int c = 0; c < NCH; ++c) lab_next[c] = labels[min(jn + c * 32 + lane, N - 1)];
             }
             mbar_wait(acc_full + a, acc.phase());
             tc_fence_after();
@@ -211,112 +252,255 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + a);         // values are in registers: hand the accumulator back now
-            const bool diag_tile = (gi >= jbase) && (gi < jbase + BN / 2);   // uniform per warp (32-row groups)
-            if (!may_have_pos) {                              // (a diagonal chunk always intersects: i is its own label)
+            const bool ragged = (ct + 1) * BN > N;             // uniform per CTA: columns past N are TMA zero fill
+            const bool diag_tile = __any_sync(0xffffffffu, (gi >= jbase) && (gi < jbase + BN / 2));
+            if constexpr (PASS == 1) {
+                if (!may_have_pos && !ragged) {               // (a diagonal chunk always intersects: i is its own label)
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
+                    for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-                    for (int e4 = 0; e4 < 8; ++e4) {
-                        D0 += ex2_approx(fmaf(__uint_as_float(r[c][e4 * 4 + 0]), c1, -c1));
-                        D1 += EX2_ALT(fmaf(__uint_as_float(r[c][e4 * 4 + 1]), c1, -c1));
-                        D2 += ex2_approx(fmaf(__uint_as_float(r[c][e4 * 4 + 2]), c1, -c1));
-                        D3 += EX2_ALT(fmaf(__uint_as_float(r[c][e4 * 4 + 3]), c1, -c1));
+                        for (int e4 = 0; e4 < 8; ++e4) {
+                            D0 += ex2_approx(fmaf(__uint_as_float(r[c][e4 * 4 + 0]), c1, -c1));
+                            D1 += ex2_approx(fmaf(__uint_as_float(r[c][e4 * 4 + 1]), c1, -c1));
+                            D2 += ex2_approx(fmaf(__uint_as_float(r[c][e4 * 4 + 2]), c1, -c1));
+                            D3 += ex2_approx(fmaf(__uint_as_float(r[c][e4 * 4 + 3]), c1, -c1));
+                        }
                     }
-                }
-            } else if (!__any_sync(0xffffffffu, diag_tile)) {
+                } else if (!diag_tile && !ragged) {
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
+                    for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-                    for (int e4 = 0; e4 < 8; ++e4) {
-                        const int4 lj = *reinterpret_cast<const int4*>(wlab + c * 32 + e4 * 4);
-                        const float s0 = __uint_as_float(r[c][e4 * 4 + 0]), s1 = __uint_as_float(r[c][e4 * 4 + 1]);
-                        const float s2 = __uint_as_float(r[c][e4 * 4 + 2]), s3 = __uint_as_float(r[c][e4 * 4 + 3]);
-                        D0 += ex2_approx(fmaf(s0, c1, -c1));
-                        D1 += EX2_ALT(fmaf(s1, c1, -c1));
-                        D2 += ex2_approx(fmaf(s2, c1, -c1));
-                        D3 += EX2_ALT(fmaf(s3, c1, -c1));
-                        if (lj.x == my_lab) { cnt += 1; posS += s0; }
-                        if (lj.y == my_lab) { cnt += 1; posS += s1; }
-                        if (lj.z == my_lab) { cnt += 1; posS += s2; }
-                        if (lj.w == my_lab) { cnt += 1; posS += s3; }
+                        for (int e4 = 0; e4 < 8; ++e4) {
+                            const int4 lj = *reinterpret_cast<const int4*>(wlab + c * 32 + e4 * 4);
+                            const float s0 = __uint_as_float(r[c][e4 * 4 + 0]), s1 = __uint_as_float(r[c][e4 * 4 + 1]);
+                            const float s2 = __uint_as_float(r[c][e4 * 4 + 2]), s3 = __uint_as_float(r[c][e4 * 4 + 3]);
+                            const float e0 = ex2_approx(fmaf(s0, c1, -c1)), e1 = ex2_approx(fmaf(s1, c1, -c1));
+                            const float e2 = ex2_approx(fmaf(s2, c1, -c1)), e3 = ex2_approx(fmaf(s3, c1, -c1));
+                            D0 += e0; D1 += e1; D2 += e2; D3 += e3;
+                            if (lj.x == my_lab) { cnt += 1; posS += s0; posE += e0; }
+                            if (lj.y == my_lab) { cnt += 1; posS += s1; posE += e1; }
+                            if (lj.z == my_lab) { cnt += 1; posS += s2; posE += e2; }
+                            if (lj.w == my_lab) { cnt += 1; posS += s3; posE += e3; }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            const int j = jbase + c * 32 + e;
+                            const float sv = __uint_as_float(r[c][e]);
+                            if (j != gi && j < N) {
+                                const float ev = ex2_approx(fmaf(sv, c1, -c1));
+                                D0 += ev;
+                                if (wlab[c * 32 + e] == my_lab) { cnt += 1; posS += sv; posE += ev; }
+                            }
+                        }
                     }
                 }
             } else {
+                if (may_have_pos) {
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
+                    for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int j = jbase + c * 32 + e;
-                        const float sv = __uint_as_float(r[c][e]);
-                        if (j != gi) {
-                            D0 += ex2_approx(fmaf(sv, c1, -c1));
-                            if (wlab[c * 32 + e] == my_lab) { cnt += 1; posS += sv; }
+                        for (int e = 0; e < 32; ++e) {
+                            const int j = jbase + c * 32 + e;
+                            if (j != gi && j < N && wlab[c * 32 + e] == my_lab) {
+                                const float L = fmaf(__uint_as_float(r[c][e]), inv_t, -inv_t);
+                                if (VARIANT == CY_SUPCON_EXCLUDE) {
+                                    const float den = __expf(L) + rstat + 1e-16f;
+                                    r0 += L - __logf(den);
+                                    r1 += 1.f / den;
+                                } else {
+                                    const float logp = L - rstat;
+                                    const float w = sp_weight_tc(VARIANT, logp, gamma);
+                                    r0 += w * logp;
+                                    r1 += w;
+                                }
+                            }
                         }
                     }
                 }
             }
         }
-        const float D = (D0 + D1) + (D2 + D3);
-        const int slot = blockIdx.y * 2 + h;
-        float* p = part + (size_t)slot * 3 * N;
-        p[gi] = D;
-        p[(size_t)N + gi] = (float)cnt;
-        p[2 * (size_t)N + gi] = posS;
+        if (gi < N) {
+            if constexpr (PASS == 1) {
+                float* p = part + (size_t)(slot_base + (int)blockIdx.y * 2 + h) * 4 * N;
+                p[gi] = (D0 + D1) + (D2 + D3);
+                p[(size_t)N + gi] = (float)cnt;
+                p[2 * (size_t)N + gi] = posS;
+                p[3 * (size_t)N + gi] = posE;
+            } else {
+                float* p = part + (size_t)h * 2 * N;
+                p[gi] = r0;
+                p[(size_t)N + gi] = r1;
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-// partial row sums -> the pass-1 raw statistics cy_infonce_finalize expects (fixed summation order)
-__global__ void infonce_tc_reduce_kernel(const float* __restrict__ part, int nslot, int N, int row_begin, int row_end,
-                                         float inv_t, float* __restrict__ stats) {
+// [min, max] label of every 128-column tile (pass-2 tile selection)
+__global__ void infonce_tile_range_kernel(const int32_t* __restrict__ labels, int N, int2* __restrict__ tile_range) {
+    const int ct = blockIdx.x, lane = threadIdx.x;          // one warp per tile
+    int32_t lo = INT_MAX, hi = INT_MIN;
+    for (int j = ct * FWD_BN + lane; j < min(N, (ct + 1) * FWD_BN); j += 32) {
+        const int32_t l = labels[j];
+        lo = min(lo, l);
+        hi = max(hi, l);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane == 0) tile_range[ct] = make_int2(lo, hi);
+}
+
+// ------------------------------------------------------------------------------------------------------------ row statistics
+// Per-row epilogue of a forward sweep, for the rows [row_begin, row_end) this process owns.  Source of the raw sums: the
+// tensor path's partial slots (`part` != nullptr: summed here in a fixed order) or the CY_STAT_* rows the SIMT sweep wrote.
+// Output: `xstat` [N][4] — what the backward needs for every row it meets as a row OR as a column, plus the row's loss
+// term, so that ONE all-gather of the owned rows of this array is the whole exchange of the row-sharded multi-GPU form
+// (include/contrastyou_b200.h: CY_XS_*).
+template <int PASS>
+__global__ void infonce_rowstats_kernel(int variant, int N, int row_begin, int row_end, float inv_t, const float* __restrict__ part,
+                                        int nslot, float* __restrict__ stats, float4* __restrict__ xstat) {
     const int i = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= row_end) return;
-    float D = 0.f, c = 0.f, ps = 0.f;
-    for (int s = 0; s < nslot; ++s) {
-        const float* p = part + (size_t)s * 3 * N;
-        D += p[i];
-        c += p[(size_t)N + i];
-        ps += p[2 * (size_t)N + i];
+    const size_t Ns = (size_t)N;
+    if (PASS == 1) {
+        float posE, negE, c, nc, posL;
+        if (part) {
+            float Dt = 0.f, ct = 0.f, ps = 0.f, pe = 0.f;
+            for (int s = 0; s < nslot; ++s) {
+                const float* p = part + (size_t)s * 4 * Ns;
+                Dt += p[i];
+                ct += p[Ns + i];
+                ps += p[2 * Ns + i];
+                pe += p[3 * Ns + i];
+            }
+            posE = pe;
+            negE = Dt - pe;                                     // every off-diagonal pair is positive or negative (label masks)
+            c = ct;
+            nc = (float)(N - 1) - ct;
+            posL = inv_t * ps - inv_t * ct;                     // sum_j P_ij (s_ij - 1)/t
+            stats[CY_STAT_AUX * Ns + i] = negE;
+            stats[CY_STAT_NEGC * Ns + i] = nc;
+            stats[CY_STAT_POSL * Ns + i] = posL;
+        } else {
+            posE = stats[CY_STAT_POSE * Ns + i];
+            negE = stats[CY_STAT_AUX * Ns + i];
+            c = stats[CY_STAT_INVC * Ns + i];
+            nc = stats[CY_STAT_NEGC * Ns + i];
+            posL = stats[CY_STAT_POSL * Ns + i];
+        }
+        const float den = posE + negE + 1e-16f;
+        const float logden = logf(den);
+        const float invc = 1.f / c;
+        stats[CY_STAT_LOGDEN * Ns + i] = logden;
+        stats[CY_STAT_INVC * Ns + i] = invc;
+        stats[CY_STAT_POSE * Ns + i] = c;                       // slot reused: positive count (read by pass 2)
+        float4 xs = make_float4(logden, invc, 0.f, 0.f);
+        if (variant == CY_SUPCON) {
+            xs.z = 1.f / den;
+            xs.w = -(posL * invc - logden);                     // c == 0: 0 * inf = NaN, like the reference's 0/0 (contrastive.py:95)
+            stats[CY_STAT_COEF * Ns + i] = xs.z;
+        } else if (variant == CY_SUPCON_EXCLUDE) {
+            const float ratio = nc / (c + nc);                  // contrastive.py:88 (float32)
+            xs.w = negE / (ratio + 1e-4f);                      // A_i
+            stats[CY_STAT_AUX * Ns + i] = xs.w;
+        }
+        xstat[i] = xs;
+    } else {
+        float r0, r1;
+        if (part) {
+            r0 = part[i] + part[2 * Ns + i];
+            r1 = part[Ns + i] + part[3 * Ns + i];
+            stats[CY_STAT_POSL * Ns + i] = r0;
+            stats[CY_STAT_SW * Ns + i] = r1;
+        } else {
+            r0 = stats[CY_STAT_POSL * Ns + i];
+            r1 = stats[CY_STAT_SW * Ns + i];
+        }
+        const float invc = stats[CY_STAT_INVC * Ns + i], c = stats[CY_STAT_POSE * Ns + i];
+        const float term = -r0 * invc;
+        float4 xs = xstat[i];
+        if (variant == CY_SUPCON_EXCLUDE) {
+            const float nc = stats[CY_STAT_NEGC * Ns + i];
+            const float ratio = nc / (c + nc);
+            xs.z = r1 * invc / (ratio + 1e-4f);
+            xs.x = term;                                        // the log-denominator is not needed by this variant's backward
+        } else {
+            xs.z = r1 * invc * expf(-xs.x);
+            xs.w = term;
+        }
+        stats[CY_STAT_COEF * Ns + i] = xs.z;
+        xstat[i] = xs;
     }
-    stats[(size_t)CY_STAT_POSE * N + i] = D;                       // total sum_j E_ij (positives and negatives together)
-    stats[(size_t)CY_STAT_AUX * N + i] = 0.f;
-    stats[(size_t)CY_STAT_INVC * N + i] = c;
-    stats[(size_t)CY_STAT_NEGC * N + i] = (float)(N - 1) - c;
-    stats[(size_t)CY_STAT_POSL * N + i] = inv_t * ps - inv_t * c;  // sum_j P_ij (s_ij - 1)/t
+}
+
+// ------------------------------------------------------------------------------------------------------------ loss reduction
+// out4 = { sum_i term_i / N, sum_i sw_i, sum_i c_i, #non-finite terms } over ALL N rows of xstat, in a fixed order (block
+// partials in index order): every rank of a sharded run computes the identical bits from the gathered array, so no
+// scalar collective is needed.
+constexpr int LOSS_THREADS = 1024;
+__global__ void __launch_bounds__(LOSS_THREADS)
+infonce_loss_partial_kernel(int variant, int N, const float4* __restrict__ xstat, float* __restrict__ partials) {
+    const int i = blockIdx.x * LOSS_THREADS + threadIdx.x;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (i < N) {
+        const float4 xs = xstat[i];
+        const float term = (variant == CY_SUPCON_EXCLUDE) ? xs.x : xs.w;
+        v[0] = term;
+        v[3] = isfinite(term) ? 0.f : 1.f;
+        if (variant == CY_SELFPACED_HARD || variant == CY_SELFPACED_SOFT) {
+            // coef = sw * invc * exp(-logden)  ->  sw = coef * exp(logden) / invc ;  c = 1 / invc
+            const bool ok = isfinite(xs.y) && xs.y > 0.f;
+            v[1] = ok ? xs.z * expf(xs.x) / xs.y : 0.f;
+            v[2] = ok ? 1.f / xs.y : 0.f;
+        }
+    }
+    __shared__ float red[4][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = warp_sum(v[q]);
+    if (lane == 0)
+        for (int q = 0; q < 4; ++q) red[q][w] = v[q];
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float x = warp_sum(red[q][lane]);
+            if (lane == 0) partials[blockIdx.x * 4 + q] = x;
+        }
+    }
+}
+
+__global__ void infonce_loss_final_kernel(int nblk, int N, const float* __restrict__ partials, float* __restrict__ out4) {
+    const int q = threadIdx.x;       // 4 threads, each walks its component in block order
+    if (q >= 4) return;
+    float s = 0.f;
+    for (int b = 0; b < nblk; ++b) s += partials[b * 4 + q];
+    out4[q] = (q == 0) ? s / (float)N : s;
 }
 
 // ------------------------------------------------------------------------------------------------------------ backward
-#ifndef CY_BWD_A_TMEM
-#define CY_BWD_A_TMEM 1
-#endif
-// CY_BWD_A_TMEM: the row block Zi (the A operand of S = Zi Zj^T) lives in TENSOR MEMORY (128 columns: two bf16 per column)
-// instead of shared memory.  An M128 N64 K16 MMA with both operands in shared memory fetches 6 KB and is bound by the
-// 128 B/clk shared-memory port (48 clk, profiles/probes/probe_umma_small.cu) instead of its 32 clk of math; with A in TMEM
-// it fetches 2 KB.  The 64 KB of shared memory this frees deepen the Zj ring.
-#ifndef CY_BWD_W_TMEM
-#define CY_BWD_W_TMEM 1
-#endif
-// CY_BWD_W_TMEM (needs A_TMEM): the weight tile W (A operand of dZ += W Zj) is written by the epilogue straight back into
-// the tensor-memory columns of the S accumulator it was computed from (bf16 pairs: 16 columns per 32-column half) and
-// read from there by the second MMA — no shared-memory W tile, no swizzled stores, no proxy fence, 32 KB less
-// shared-memory traffic per 128 x 64 tile.  The S slot is recycled by the in-order tensor pipe: MMA1(t+2) is issued
-// after MMA2(t), which is the last reader of slot t % 2.
+// The row block Zi (the A operand of S = Zi Zj^T) lives in TENSOR MEMORY (D/2 columns: two bf16 per column): an M128 N64
+// K16 MMA with both operands in shared memory fetches 6 KB and is bound by the 128 B/clk shared-memory port (48 clk,
+// profiles/probes/probe_umma_small.cu) instead of its 32 clk of math; with A in TMEM it fetches 2 KB.  The weight tile W
+// (A operand of dZ += W Zj) is written by the epilogue straight back into the tensor-memory columns of the S accumulator
+// it was computed from (bf16 pairs: 16 columns per 32-column half) and read from there by the second MMA — no
+// shared-memory W tile, no swizzled stores, no proxy fence.  The S slot is recycled by the in-order tensor pipe: MMA1(t+2)
+// is issued after MMA2(t), which is the last reader of slot t % 2.
+template <int D>
 struct BwdCfg {
-    static constexpr int BN = 64;
-    static constexpr bool A_TMEM = CY_BWD_A_TMEM != 0;
-    static constexpr bool W_TMEM = A_TMEM && CY_BWD_W_TMEM != 0;
-    static constexpr int NSTAGE = W_TMEM ? 6 : (A_TMEM ? 5 : 3);     // Zj ring (a stage lives from its MMA1 until its MMA2 retires)
-    static constexpr int NS = A_TMEM ? 2 : 4;         // S accumulators in TMEM (64 columns each), the last NS*64 columns
-    static constexpr int NW = 2;         // W tiles in shared memory
-    static constexpr uint32_t A_BYTES = A_TMEM ? 0 : TC_BM * TC_D * 2;       // 64 KB
-    static constexpr uint32_t B_BYTES = BN * TC_D * 2;          // 32 KB
-    static constexpr uint32_t W_BYTES = W_TMEM ? 0 : TC_BM * BN * 2;         // 16 KB
-    static constexpr uint32_t OFF_B = A_BYTES;
-    static constexpr uint32_t OFF_W = OFF_B + NSTAGE * B_BYTES;
-    static constexpr uint32_t OFF_COL = OFF_W + NW * W_BYTES;   // per epilogue warp: lab[32], coef[32], invc[32]
-    static constexpr uint32_t OFF_BAR = OFF_COL + 8 * 3 * 32 * 4;
+    static constexpr int BN = BWD_BN;
+    static constexpr int KBLK = D / 64;
+    static constexpr int NSTAGE = 6;     // Zj ring (a stage lives from its MMA1 until its MMA2 retires)
+    static constexpr int NS = 2;         // S accumulators in TMEM (64 columns each), the last NS*64 columns
+    static constexpr uint32_t B_BYTES = BN * D * 2;
+    static constexpr uint32_t OFF_COL = NSTAGE * B_BYTES;       // per epilogue warp: lab[32], coef[32], invc[32], aux[32]
+    static constexpr uint32_t OFF_BAR = OFF_COL + 8 * 4 * 32 * 4;
     static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024;
 };
 
@@ -336,47 +520,44 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // F16: fp16 embeddings.  W is then stored as fp16 scaled by 2^10 (softmax-sized weights below 6e-8 would flush to zero in
 // fp16; scaled, the flush threshold drops to 6e-11 while the largest weight, ~2, stays far from 65504); the scale is
 // undone in out_scale by the host.
-template <bool F16>
+template <int D, bool F16, int VARIANT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict__ labels,
-                      const float* __restrict__ stats, int N, int row_begin, int tiles_per_split, float c1,
-                      const float* __restrict__ gscale, float out_scale, void* __restrict__ dz_v, int64_t lddz,
-                      float* __restrict__ dz32, uint32_t idesc1, uint32_t idesc2, const uint16_t* __restrict__ zrows, int64_t ldz) {
+                      const float4* __restrict__ xstat, int N, int row_begin, int row_end, int tiles_per_split, float c1,
+                      float inv_t, float gamma, const float* __restrict__ gscale, float out_scale, void* __restrict__ dz_v,
+                      int64_t lddz, float* __restrict__ dz32, int rows_total, uint32_t idesc1, uint32_t idesc2,
+                      const uint16_t* __restrict__ zrows, int64_t ldz) {
     uint16_t* dz = reinterpret_cast<uint16_t*>(dz_v);
     constexpr float WS = F16 ? 1024.f : 1.f;
-    using C = BwdCfg;
+    using C = BwdCfg<D>;
     constexpr int BN = C::BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);    // 1024-aligned, still a shared pointer
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + C::OFF_B;
-    uint8_t* sW = smem + C::OFF_W;
+    uint8_t* sB = smem;
     float* sCol = reinterpret_cast<float*>(smem + C::OFF_COL);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* a_full = bars;
     uint64_t* b_full = bars + 1;
     uint64_t* b_empty = b_full + C::NSTAGE;
     uint64_t* s_full = b_empty + C::NSTAGE;
-    uint64_t* s_empty = s_full + C::NS;
-    uint64_t* w_full = s_empty + C::NS;
-    uint64_t* w_empty = w_full + C::NW;
-    uint64_t* dz_full = w_empty + C::NW;
+    uint64_t* w_full = s_full + C::NS;
+    uint64_t* dz_full = w_full + C::NS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dz_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = row_begin + blockIdx.x * TC_BM;
     // column tiles [t0, t1) of this CTA (blockIdx.y splits the columns so that small row ranges still fill the chip)
+    const int n_tiles = (N + BN - 1) / BN;
     const int t0 = blockIdx.y * tiles_per_split;
-    const int t1 = min(N / BN, t0 + tiles_per_split);
+    const int t1 = min(n_tiles, t0 + tiles_per_split);
     const int nt = t1 - t0;
-    if (nt <= 0) return;
+    if (nt <= 0) return;          // (the host sizes the splits so that this never happens; slabs would stay unwritten)
 
     if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
     if (warp == 1 && lane == 0) {
-        mbar_init(a_full, C::A_TMEM ? 8 : 1);
+        mbar_init(a_full, 8);
         for (int i = 0; i < C::NSTAGE; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-        for (int i = 0; i < C::NS; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 8); }
-        for (int i = 0; i < C::NW; ++i) { mbar_init(w_full + i, 8); mbar_init(w_empty + i, 1); }
+        for (int i = 0; i < C::NS; ++i) { mbar_init(s_full + i, 1); mbar_init(w_full + i, 8); }
         mbar_init(dz_full, 1);
         fence_barrier_init();
     }
@@ -385,77 +566,58 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_dz = tmem_base;             // columns [0, 256)
-    const uint32_t tmem_a = tmem_base + 256;        // A_TMEM: Zi, columns [256, 384)
+    const uint32_t tmem_dz = tmem_base;             // columns [0, D)
+    const uint32_t tmem_a = tmem_base + 256;        // Zi, columns [256, 256 + D/2)
     const uint32_t tmem_s = tmem_base + 512 - C::NS * BN;        // NS x 64 columns
 
     if (warp == 0) {
         if (elect_one()) {
-            if constexpr (!C::A_TMEM) {
-                mbar_arrive_expect_tx(a_full, C::A_BYTES);
-                for (int kb = 0; kb < TC_KBLK; ++kb)
-                    for (int hb = 0; hb < TC_BM / 64; ++hb)
-                        tma_load_2d(sA + kb * (TC_BM * 128) + hb * 8192, &tmap, a_full, kb * 64, row0 + hb * 64);
-            }
             Ring<C::NSTAGE> ring;
             for (int t = 0; t < nt; ++t, ring.next()) {
                 const uint32_t s = ring.stage();
                 mbar_wait(b_empty + s, ring.phase() ^ 1u);
                 mbar_arrive_expect_tx(b_full + s, C::B_BYTES);
                 uint8_t* dst = sB + s * C::B_BYTES;
-                for (int kb = 0; kb < TC_KBLK; ++kb) tma_load_2d(dst + kb * (BN * 128), &tmap, b_full + s, kb * 64, (t0 + t) * BN);
+                for (int kb = 0; kb < C::KBLK; ++kb) tma_load_2d(dst + kb * (BN * 128), &tmap, b_full + s, kb * 64, (t0 + t) * BN);
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            // idesc1: S = Zi (K-major) x Zj (K-major), M128 N64;  idesc2: dZ += W (K-major) x Zj (MN-major), M128 N256
-            const uint32_t a_addr = smem_u32(sA);
+            // idesc1: S = Zi (TMEM) x Zj (K-major), M128 N64;  idesc2: dZ += W (TMEM) x Zj (MN-major), M128 N(D)
             mbar_wait(a_full, 0);
             Ring<C::NSTAGE> ring1;      // stage / phase of the tile whose MMA1 is issued next
             Ring<C::NS> sacc;
             auto issue_mma1 = [&]() {
                 const uint32_t s = ring1.stage(), a = sacc.stage();
                 mbar_wait(b_full + s, ring1.phase());
-                if constexpr (!C::W_TMEM) mbar_wait(s_empty + a, sacc.phase() ^ 1u);
                 tc_fence_after();
                 const uint32_t b_addr = smem_u32(sB + s * C::B_BYTES);
 #pragma unroll
-                for (int kb = 0; kb < TC_KBLK; ++kb)
+                for (int kb = 0; kb < C::KBLK; ++kb)
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        if constexpr (C::A_TMEM)      // k-step (kb, ks) = elements 64*kb + 16*ks ..: 8 columns of Zi in TMEM
-                            umma_bf16_ts(tmem_s + a * BN, tmem_a + (kb * 4 + ks) * 8,
-                                         smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc1, (kb | ks) != 0);
-                        else
-                            umma_bf16(tmem_s + a * BN, smem_desc(a_addr + kb * (TC_BM * 128) + ks * 32, 16, 1024),
-                                      smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc1, (kb | ks) != 0);
-                    }
+                    for (int ks = 0; ks < 4; ++ks)      // k-step (kb, ks) = elements 64*kb + 16*ks ..: 8 columns of Zi in TMEM
+                        umma_bf16_ts(tmem_s + a * BN, tmem_a + (kb * 4 + ks) * 8,
+                                     smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc1, (kb | ks) != 0);
                 umma_commit(s_full + a);
                 ring1.next();
                 sacc.next();
             };
             issue_mma1();
             Ring<C::NSTAGE> ring2;
-            Ring<C::NW> wr;
+            Ring<C::NS> wr;
             for (int t = 0; t < nt; ++t, ring2.next(), wr.next()) {
                 if (t + 1 < nt) issue_mma1();                       // keep the tensor pipe busy while the epilogue works
                 const uint32_t s = ring2.stage(), w = wr.stage();
                 mbar_wait(w_full + w, wr.phase());
                 tc_fence_after();
-                const uint32_t w_addr = smem_u32(sW + w * C::W_BYTES);
                 const uint32_t b_addr = smem_u32(sB + s * C::B_BYTES);
 #pragma unroll
-                for (int ks = 0; ks < BN / 16; ++ks) {
-                    // A: W [128 x 64] K-major, 32 B per k-step.  B: Zj read MN-major: N = d (4 groups of 64, LBO = BN*128),
-                    // K = j (8-row groups, SBO = 1024); one k-step = 16 rows of j = 2048 B.
-                    if constexpr (C::W_TMEM)      // W of tile t sits in S slot t % NS: half h at columns h*32 .. h*32+15, 8 per k-step
-                        umma_bf16_ts(tmem_dz, tmem_s + (uint32_t)(t % C::NS) * BN + (ks >> 1) * 32 + (ks & 1) * 8,
-                                     smem_desc(b_addr + ks * 2048, BN * 128, 1024), idesc2, (t | ks) != 0);
-                    else
-                        umma_bf16(tmem_dz, smem_desc(w_addr + ks * 32, 16, 1024), smem_desc(b_addr + ks * 2048, BN * 128, 1024),
-                                  idesc2, (t | ks) != 0);      // t counts from this CTA's first tile
-                }
-                umma_commit(w_empty + w);
+                for (int ks = 0; ks < BN / 16; ++ks)
+                    // A: W of tile t sits in S slot t % NS: half h at columns h*32 .. h*32+15, 8 columns per k-step.
+                    // B: Zj read MN-major: N = d (D/64 groups of 64, LBO = BN*128), K = j (8-row groups, SBO = 1024); one
+                    // k-step = 16 rows of j = 2048 B.
+                    umma_bf16_ts(tmem_dz, tmem_s + (uint32_t)(t % C::NS) * BN + (ks >> 1) * 32 + (ks & 1) * 8,
+                                 smem_desc(b_addr + ks * 2048, BN * 128, 1024), idesc2, (t | ks) != 0);
                 umma_commit(b_empty + s);
             }
             umma_commit(dz_full);
@@ -464,48 +626,51 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
         const int q = warp & 3, h = (warp - 4) >> 2, ew = warp - 4;
         const int row = q * 32 + lane;
         const int gi = row0 + row;
-        const int32_t my_lab = labels[gi];
-        const float coef_i = stats[(size_t)CY_STAT_COEF * N + gi] * WS;
-        const float invc_i = stats[(size_t)CY_STAT_INVC * N + gi] * WS;
-        if constexpr (C::A_TMEM) {
-            // this thread's half row of Zi (128 elements = 64 packed columns) -> tensor memory lanes q*32.., columns h*64..
-            const uint4* src = reinterpret_cast<const uint4*>(zrows + (size_t)gi * ldz + h * 128);
+        const int gic = min(gi, N - 1);
+        const int32_t my_lab = labels[gic];
+        const float4 xi = xstat[gic];
+        const float coef_i = xi.z * WS, invc_i = xi.y * WS;
+        const float aux_i = (VARIANT == CY_SUPCON_EXCLUDE) ? xi.w : xi.x;      // exclude: A_i;  self-paced: log-denominator
+        {
+            // this thread's half row of Zi (D/2 elements = D/4 packed columns) -> tensor memory lanes q*32.., columns h*D/4..
+            const uint4* src = reinterpret_cast<const uint4*>(zrows + (size_t)gic * ldz + h * (D / 2));
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < D / 128; ++c) {
                 uint32_t r[32];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const uint4 v = __ldg(src + c * 8 + e);
                     r[4 * e] = v.x; r[4 * e + 1] = v.y; r[4 * e + 2] = v.z; r[4 * e + 3] = v.w;
                 }
-                tmem_st_32x32(tmem_a + (uint32_t(q * 32) << 16) + h * 64 + c * 32, r);
+                tmem_st_32x32(tmem_a + (uint32_t(q * 32) << 16) + h * (D / 4) + c * 32, r);
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full);
         }
-        float* wcol = sCol + ew * 96;                 // [0,32) labels (as int bits), [32,64) coef_j, [64,96) invc_j
+        float* wcol = sCol + ew * 128;                // [0,32) labels (as int bits), [32,64) coef_j, [64,96) invc_j, [96,128) aux_j
         const int32_t row_lo = __reduce_min_sync(0xffffffffu, my_lab), row_hi = __reduce_max_sync(0xffffffffu, my_lab);
-        float nx_lab = __int_as_float(labels[t0 * BN + h * 32 + lane]);
-        float nx_coef = stats[(size_t)CY_STAT_COEF * N + t0 * BN + h * 32 + lane] * WS;
-        float nx_invc = stats[(size_t)CY_STAT_INVC * N + t0 * BN + h * 32 + lane] * WS;
+        int jn = min(t0 * BN + h * 32 + lane, N - 1);
+        float nx_lab = __int_as_float(labels[jn]);
+        float4 nx = xstat[jn];
         Ring<C::NS> sacc;
-        Ring<C::NW> wr;
-        for (int t = 0; t < nt; ++t, sacc.next(), wr.next()) {
-            const uint32_t a = sacc.stage(), w = wr.stage();
+        for (int t = 0; t < nt; ++t, sacc.next()) {
+            const uint32_t a = sacc.stage();
             const int jbase = (t0 + t) * BN + h * 32;
             __syncwarp();
             wcol[lane] = nx_lab;
-            wcol[32 + lane] = nx_coef;
-            wcol[64 + lane] = nx_invc;
-            const bool may_have_pos = __reduce_max_sync(0xffffffffu, __float_as_int(nx_lab)) >= row_lo &&
-                                      __reduce_min_sync(0xffffffffu, __float_as_int(nx_lab)) <= row_hi;
+            wcol[32 + lane] = nx.z * WS;
+            wcol[64 + lane] = nx.y * WS;
+            wcol[96 + lane] = (VARIANT == CY_SUPCON_EXCLUDE) ? nx.w : nx.x;
+            const bool ragged = (t0 + t + 1) * BN > N;            // uniform per CTA: columns past N are TMA zero fill
+            const bool may_have_pos = ragged || (__reduce_max_sync(0xffffffffu, __float_as_int(nx_lab)) >= row_lo &&
+                                                 __reduce_min_sync(0xffffffffu, __float_as_int(nx_lab)) <= row_hi);
             __syncwarp();
             if (t + 1 < nt) {                             // next tile's column statistics travel during this tile
-                nx_lab = __int_as_float(labels[jbase + BN + lane]);
-                nx_coef = stats[(size_t)CY_STAT_COEF * N + jbase + BN + lane] * WS;
-                nx_invc = stats[(size_t)CY_STAT_INVC * N + jbase + BN + lane] * WS;
+                jn = min(jbase + BN + lane, N - 1);
+                nx_lab = __int_as_float(labels[jn]);
+                nx = xstat[jn];
             }
             mbar_wait(s_full + a, sacc.phase());
             tc_fence_after();
@@ -514,8 +679,6 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            // S values are in registers: the accumulator can be reused (W_TMEM: the slot is handed back by MMA2 instead)
-            if (!C::W_TMEM && lane == 0) mbar_arrive(s_empty + a);
             uint32_t packed[16];
             if (!may_have_pos) {                          // no positive pair in this 32 x 32 block: W = E (coef_i + coef_j)
 #pragma unroll
@@ -535,82 +698,85 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                     const int4 lj = *reinterpret_cast<const int4*>(wcol + e4 * 4);
                     const float4 cj = *reinterpret_cast<const float4*>(wcol + 32 + e4 * 4);
                     const float4 ij = *reinterpret_cast<const float4*>(wcol + 64 + e4 * 4);
+                    const float4 aj = *reinterpret_cast<const float4*>(wcol + 96 + e4 * 4);
                     const int lv[4] = {lj.x, lj.y, lj.z, lj.w};
                     const float cv[4] = {cj.x, cj.y, cj.z, cj.w};
                     const float iv[4] = {ij.x, ij.y, ij.z, ij.w};
+                    const float av[4] = {aj.x, aj.y, aj.z, aj.w};
                     float wv[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const float sv = __uint_as_float(r[e4 * 4 + u]);
                         const float E = ex2_approx(fmaf(sv, c1, -c1));
+                        const bool pos = lv[u] == my_lab;
                         float v = E * (coef_i + cv[u]);
-                        if (lv[u] == my_lab) v -= invc_i + iv[u];
+                        if (VARIANT == CY_SUPCON) {
+                            if (pos) v -= invc_i + iv[u];
+                        } else if (VARIANT == CY_SUPCON_EXCLUDE) {
+                            // positive pair: G_ij = (1/c_i)(E/(E + A_i + 1e-16) - 1); negative pair: coef_i E (contrastive.py:87-90)
+                            if (pos) v = invc_i * (E / (E + aux_i + 1e-16f) - 1.f) + iv[u] * (E / (E + av[u] + 1e-16f) - 1.f);
+                        } else {
+                            if (pos) {                    // self-paced: the positive term carries the no-grad weights w_ij, w_ji
+                                const float L = fmaf(sv, inv_t, -inv_t);
+                                v -= sp_weight_tc(VARIANT, L - aux_i, gamma) * invc_i + sp_weight_tc(VARIANT, L - av[u], gamma) * iv[u];
+                            }
+                        }
                         wv[u] = v;
                     }
-                    if (diag_tile) {
+                    if (diag_tile || ragged) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (jbase + e4 * 4 + u == gi) wv[u] = 0.f;
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = jbase + e4 * 4 + u;
+                            if (j == gi || j >= N) wv[u] = 0.f;
+                        }
                     }
                     packed[e4 * 2] = pack2<F16>(wv[0], wv[1]);
                     packed[e4 * 2 + 1] = pack2<F16>(wv[2], wv[3]);
                 }
             }
-            if constexpr (C::W_TMEM) {
-                // in place: this warp's 32 x 32 block of S (columns h*32 ..) becomes 32 x 32 bf16 weights in columns h*32 .. +15
-                tc_fence_after();
-                tmem_st_32x16(tmem_s + (uint32_t(q * 32) << 16) + a * BN + h * 32, packed);
-                tmem_st_wait();
-                tc_fence_before();
-            } else {
-                mbar_wait(w_empty + w, wr.phase() ^ 1u);
-                // row `row` of the [128 x 64] bf16 tile: 128 B, this warp's half = 16-byte chunks 4h..4h+3, swizzled by row % 8
-                uint8_t* wrow = sW + w * C::W_BYTES + row * 128;
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    const int phys = ((4 * h + ch) ^ (row & 7)) << 4;
-                    *reinterpret_cast<uint4*>(wrow + phys) =
-                        make_uint4(packed[4 * ch], packed[4 * ch + 1], packed[4 * ch + 2], packed[4 * ch + 3]);
-                }
-                fence_proxy_async_smem();
-            }
+            // in place: this warp's 32 x 32 block of S (columns h*32 ..) becomes 32 x 32 bf16 weights in columns h*32 .. +15
+            tc_fence_after();
+            tmem_st_32x16(tmem_s + (uint32_t(q * 32) << 16) + a * BN + h * 32, packed);
+            tmem_st_wait();
+            tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(w_full + w);
+            if (lane == 0) mbar_arrive(w_full + a);
         }
         // dZ rows of this CTA: TMEM -> registers -> bf16 -> global
         mbar_wait(dz_full, 0);
         tc_fence_after();
+        const bool store_row = gi < row_end;
         if (dz32 == nullptr) {
             const float scale = gscale[0] * out_scale;
-            uint16_t* out = dz + (size_t)gi * lddz + h * 128;
+            uint16_t* out = dz + (size_t)gi * lddz + h * (D / 2);
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < D / 64; ++c) {
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_dz + (uint32_t(q * 32) << 16) + h * 128 + c * 32, r);
+                tmem_ld_32x32(tmem_dz + (uint32_t(q * 32) << 16) + h * (D / 2) + c * 32, r);
                 tmem_ld_wait();
+                if (store_row) {
 #pragma unroll
-                for (int e = 0; e < 32; e += 8) {
-                    uint32_t pk[4];
+                    for (int e = 0; e < 32; e += 8) {
+                        uint32_t pk[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        pk[u] = pack2<F16>(__uint_as_float(r[e + 2 * u]) * scale, __uint_as_float(r[e + 2 * u + 1]) * scale);
-                    *reinterpret_cast<uint4*>(out + c * 32 + e) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        for (int u = 0; u < 4; ++u)
+                            pk[u] = pack2<F16>(__uint_as_float(r[e + 2 * u]) * scale, __uint_as_float(r[e + 2 * u + 1]) * scale);
+                        *reinterpret_cast<uint4*>(out + c * 32 + e) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
                 }
             }
         } else {
-            // column-split launch: partial row-block gradients meet in an fp32 accumulator (vector reductions at L2)
-            float* out = dz32 + (size_t)(gi - row_begin) * TC_D + h * 128;
+            // column-split launch: every split owns an fp32 slab [rows_total][D]; infonce_tc_convert_kernel sums the slabs
+            // in split order (no atomics: bitwise reproducible)
+            float* out = dz32 + ((size_t)blockIdx.y * rows_total + (size_t)(gi - row_begin)) * D + h * (D / 2);
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < D / 64; ++c) {
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_dz + (uint32_t(q * 32) << 16) + h * 128 + c * 32, r);
+                tmem_ld_32x32(tmem_dz + (uint32_t(q * 32) << 16) + h * (D / 2) + c * 32, r);
                 tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; e += 4)
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c * 32 + e),
-                                 "f"(__uint_as_float(r[e])), "f"(__uint_as_float(r[e + 1])), "f"(__uint_as_float(r[e + 2])),
-                                 "f"(__uint_as_float(r[e + 3]))
-                                 : "memory");
+                for (int e = 0; e < 32; e += 4)      // (rows past row_end land in the slab's own padding rows)
+                    *reinterpret_cast<uint4*>(out + c * 32 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
             }
         }
     }
@@ -619,18 +785,23 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-// fp32 split accumulator -> bf16 gradient rows (scaled by gscale / (t N))
-template <bool F16>
-__global__ void infonce_tc_convert_kernel(const float* __restrict__ dz32, int64_t rows, int64_t row_begin,
+// fp32 split slabs -> bf16 gradient rows (scaled by gscale / (t N)); slabs summed in split order
+template <int D, bool F16>
+__global__ void infonce_tc_convert_kernel(const float* __restrict__ dz32, int nsplit, int64_t rows, int64_t rows_pad, int64_t row_begin,
                                           const float* __restrict__ gscale, float out_scale, uint16_t* __restrict__ dz,
                                           int64_t lddz) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread = 8 consecutive columns
-    if (idx >= rows * (TC_D / 8)) return;
-    const int64_t r = idx / (TC_D / 8);
-    const int c = (int)(idx % (TC_D / 8)) * 8;
+    if (idx >= rows * (D / 8)) return;
+    const int64_t r = idx / (D / 8);
+    const int c = (int)(idx % (D / 8)) * 8;
     const float scale = gscale[0] * out_scale;
-    const float4 a = *reinterpret_cast<const float4*>(dz32 + r * TC_D + c);
-    const float4 b = *reinterpret_cast<const float4*>(dz32 + r * TC_D + c + 4);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    for (int s = 0; s < nsplit; ++s) {
+        const float* p = dz32 + ((size_t)s * rows_pad + r) * D + c;
+        const float4 pa = *reinterpret_cast<const float4*>(p), pb = *reinterpret_cast<const float4*>(p + 4);
+        a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
+        b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+    }
     *reinterpret_cast<uint4*>(dz + (row_begin + r) * lddz + c) =
         make_uint4(pack2<F16>(a.x * scale, a.y * scale), pack2<F16>(a.z * scale, a.w * scale),
                    pack2<F16>(b.x * scale, b.y * scale), pack2<F16>(b.z * scale, b.w * scale));
@@ -653,11 +824,11 @@ EncodeTiledFn tensor_map_encode_fn() {
     return fn;
 }
 
-// [N, 256] bf16, row pitch ldz elements; box = 64 columns (128 B, the swizzle span) x 64 rows
-static int make_tmap(CUtensorMap* m, const void* z, int64_t N, int64_t ldz, int dtype) {
+// [N, d] bf16 / fp16, row pitch ldz elements; box = 64 columns (128 B, the swizzle span) x 64 rows; rows past N read as zero
+static int make_tmap(CUtensorMap* m, const void* z, int64_t N, int64_t d, int64_t ldz, int dtype) {
     EncodeTiledFn fn = tensor_map_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CY_ERR_DEVICE; }
-    cuuint64_t gdim[2] = {(cuuint64_t)TC_D, (cuuint64_t)N};
+    cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)N};
     cuuint64_t gstride[1] = {(cuuint64_t)ldz * 2};
     cuuint32_t box[2] = {64, 64};
     cuuint32_t estr[2] = {1, 1};
@@ -670,22 +841,24 @@ static int make_tmap(CUtensorMap* m, const void* z, int64_t N, int64_t ldz, int 
 }
 
 bool infonce_tc_supported(int dtype, int64_t N, int64_t d, int64_t ldz, const uint8_t* codes, int variant) {
-    return (dtype == CY_BF16 || dtype == CY_F16) && d == TC_D && (N % 128) == 0 && N >= 256 && (ldz % 8) == 0 && codes == nullptr &&
-           variant == CY_SUPCON && N < (int64_t(1) << 30);
+    if (!((dtype == CY_BF16 || dtype == CY_F16) && (d == 256 || d == 128) && N >= 256 && (ldz % 8) == 0 && codes == nullptr &&
+          N < (int64_t(1) << 30)))
+        return false;
+    if (variant != CY_SUPCON && N > (int64_t)P2_LISTCAP * FWD_BN) return false;      // pass-2 tile list capacity
+    return true;
 }
-
-constexpr int FWD_BN = 128;
 
 static int sm_count() { return device_sm_count(); }
 
 // column splits of the backward: minimise waves x tiles-per-CTA (one CTA per SM), at least 16 tiles per CTA
-static int bwd_splits(int64_t N, int64_t rows) {
-    const int64_t sms = sm_count(), rb = rows / TC_BM, nt = N / BwdCfg::BN;
+static int bwd_splits(int64_t N, int64_t row_blocks) {
+    const int64_t sms = sm_count(), rb = row_blocks, nt = (N + BWD_BN - 1) / BWD_BN;
     int best = 1;
     double best_cost = 1e30;
     for (int s = 1; s <= 16; ++s) {
         if (s > 1 && nt / s < 16) break;
         const int64_t tps = (nt + s - 1) / s;
+        if ((int64_t)(s - 1) * tps >= nt) continue;                  // the last split would be empty
         const int64_t waves = (rb * s + sms - 1) / sms;
         const double cost = (double)waves * (double)(tps + 6);      // + fixed per-CTA cost (A load, drain) in tile units
         if (cost < best_cost * 0.97) { best_cost = cost; best = s; }
@@ -693,9 +866,9 @@ static int bwd_splits(int64_t N, int64_t rows) {
     return best;
 }
 
-static int fwd_splits(int64_t N, int64_t rows) {
+static int fwd_splits(int64_t N, int64_t row_blocks) {
     const int sms = sm_count();
-    const int64_t rb = rows / TC_BM, ctiles = N / FWD_BN;
+    const int64_t rb = row_blocks, ctiles = (N + FWD_BN - 1) / FWD_BN;
     // enough CTAs for ~8 waves, but at least 8 column tiles per CTA so the A load and the prologue amortise
     int64_t want = (8LL * sms + rb - 1) / rb;
     int64_t maxs = ctiles / 8 > 0 ? ctiles / 8 : 1;
@@ -704,88 +877,227 @@ static int fwd_splits(int64_t N, int64_t rows) {
     return (int)s;
 }
 
+constexpr size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
 size_t infonce_tc_workspace_bytes(int64_t N, int64_t d) {
-    if (d != TC_D || (N % 128) != 0) return 0;
-    // worst case over row ranges: a single 128-row block -> the most column splits
-    const int smax = fwd_splits(N, TC_BM);
-    const size_t fwd = (size_t)smax * 2 * 3 * (size_t)N * sizeof(float);
-    const size_t bwd = (size_t)N * TC_D * sizeof(float);            // fp32 split accumulator, worst case rows == N
-    return fwd > bwd ? fwd : bwd;
+    if (d != 256 && d != 128) return 0;
+    // forward: worst case over row ranges is a single 128-row block -> the most column splits
+    const int smax = fwd_splits(N, 1);
+    const size_t fwd = (size_t)smax * 2 * 4 * (size_t)N * sizeof(float);
+    // pass 2: [tile ranges | 2 slots x 2 values x N]
+    const size_t p2 = align256((size_t)((N + FWD_BN - 1) / FWD_BN) * sizeof(int2)) + (size_t)4 * N * sizeof(float);
+    // backward: fp32 slabs, splits x row blocks x 128 x d — worst case over the row-block count
+    const int64_t rb_all = (N + TC_BM - 1) / TC_BM;
+    size_t bwd = 0;
+    for (int64_t rb = 1; rb <= rb_all; ++rb) {
+        const int s = bwd_splits(N, rb);
+        if (s > 1) {
+            const size_t b = (size_t)s * rb * TC_BM * d * sizeof(float);
+            if (b > bwd) bwd = b;
+        }
+    }
+    size_t m = fwd > bwd ? fwd : bwd;
+    if (p2 > m) m = p2;
+    return m;
 }
 
+template <int D, int PASS, int VARIANT>
+static int launch_fwd_tc(const CUtensorMap& tmap, const int32_t* labels, int N, int row_begin, int ct_begin, int ct_end, int tps,
+                         float inv_t, float gamma, float* part, int slot_base, int fmt, const void* z, int64_t ldz,
+                         const int2* tile_range, const float4* xstat, dim3 grid, cudaStream_t st) {
+    using S = FwdCfg<D>;
+    auto k = infonce_fwd_tc_kernel<D, PASS, VARIANT>;
+    static SmemAttrCache attr;
+    if (attr.need(S::TOTAL)) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
+        if (e != cudaSuccess) { set_error("fwd_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr.set(S::TOTAL);
+    }
+    k<<<grid, TC_THREADS, S::TOTAL, st>>>(tmap, labels, N, row_begin, ct_begin, ct_end, tps, inv_t * LOG2E, inv_t, gamma, part, slot_base,
+                                          idesc_f16kind_f32(TC_BM, FWD_BN, 0, 0, fmt), reinterpret_cast<const uint16_t*>(z), ldz,
+                                          tile_range, xstat);
+    CY_CHECK_LAUNCH("infonce_fwd_tc");
+    return CY_OK;
+}
+
+static int check_tc_rows(int64_t N, int64_t row_begin, int64_t row_end) {
+    CY_CHECK_ARG((row_begin % TC_BM) == 0 && ((row_end % TC_BM) == 0 || row_end == N),
+                 "tcgen05 path: row range must start on a multiple of 128 and end on one (or at N)");
+    return CY_OK;
+}
+
+// pass 1: raw row sums of rows [row_begin, row_end) against all N columns, then the per-row statistics (xstat)
 int infonce_fwd_tc(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, int64_t row_begin, int64_t row_end,
-                   float inv_t, float* stats, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                   float inv_t, int variant, float* stats, float* xstat, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     const int64_t rows = row_end - row_begin;
     if (rows <= 0) return CY_OK;
-    CY_CHECK_ARG((rows % TC_BM) == 0 && (row_begin % TC_BM) == 0, "tcgen05 path: row range must be 128-aligned");
+    int rc = check_tc_rows(N, row_begin, row_end);
+    if (rc) return rc;
     CY_CHECK_ARG((reinterpret_cast<uintptr_t>(z) & 15) == 0, "tcgen05 path: z must be 16-byte aligned");
-    const int splits = fwd_splits(N, rows);
+    const int64_t rb = (rows + TC_BM - 1) / TC_BM;
+    const int splits = fwd_splits(N, rb);
     const int nslot = splits * 2;
-    const size_t need = (size_t)nslot * 3 * (size_t)N * sizeof(float);
+    const size_t need = (size_t)nslot * 4 * (size_t)N * sizeof(float);
     CY_CHECK_ARG(workspace && workspace_bytes >= need, "infonce_fwd_tc: workspace %zu < %zu", workspace_bytes, need);
     CUtensorMap tmap;
-    int rc = make_tmap(&tmap, z, N, ldz, dtype);
+    rc = make_tmap(&tmap, z, N, d, ldz, dtype);
     if (rc) return rc;
     const int fmt = dtype == CY_F16 ? 0 : 1;
-    using S = FwdSmem<FWD_BN>;
-    auto k = infonce_fwd_tc_kernel<FWD_BN>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
-    if (e != cudaSuccess) { set_error("fwd_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    const int ctiles = (int)(N / FWD_BN);
+    const int ctiles = (int)((N + FWD_BN - 1) / FWD_BN);
     const int tps = (ctiles + splits - 1) / splits;
-    dim3 grid((unsigned)(rows / TC_BM), (unsigned)splits);
-    k<<<grid, TC_THREADS, S::TOTAL, st>>>(tmap, labels, (int)N, (int)row_begin, tps, inv_t * LOG2E,
-                                          reinterpret_cast<float*>(workspace), idesc_f16kind_f32(TC_BM, FWD_BN, 0, 0, fmt),
-                                          reinterpret_cast<const uint16_t*>(z), ldz);
-    CY_CHECK_LAUNCH("infonce_fwd_tc");
-    infonce_tc_reduce_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(reinterpret_cast<float*>(workspace), nslot, (int)N,
-                                                                            (int)row_begin, (int)row_end, inv_t, stats);
-    CY_CHECK_LAUNCH("infonce_tc_reduce");
+    dim3 grid((unsigned)rb, (unsigned)splits);
+    float* part = reinterpret_cast<float*>(workspace);
+    if (d == 256)
+        rc = launch_fwd_tc<256, 1, CY_SUPCON>(tmap, labels, (int)N, (int)row_begin, 0, ctiles, tps, inv_t, 0.f, part, 0, fmt, z, ldz, nullptr,
+                                              nullptr, grid, st);
+    else
+        rc = launch_fwd_tc<128, 1, CY_SUPCON>(tmap, labels, (int)N, (int)row_begin, 0, ctiles, tps, inv_t, 0.f, part, 0, fmt, z, ldz, nullptr,
+                                              nullptr, grid, st);
+    if (rc) return rc;
+    infonce_rowstats_kernel<1><<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(variant, (int)N, (int)row_begin, (int)row_end, inv_t, part,
+                                                                              nslot, stats, reinterpret_cast<float4*>(xstat));
+    CY_CHECK_LAUNCH("infonce_rowstats<1>");
+    return CY_OK;
+}
+
+// pass 2 (exclude / self-paced): positive-pair sums that depend on the pass-1 row statistics
+int infonce_fwd2_tc(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, int64_t row_begin, int64_t row_end,
+                    float inv_t, int variant, float gamma, float* stats, float* xstat, void* workspace, size_t workspace_bytes,
+                    cudaStream_t st) {
+    const int64_t rows = row_end - row_begin;
+    if (rows <= 0) return CY_OK;
+    int rc = check_tc_rows(N, row_begin, row_end);
+    if (rc) return rc;
+    const int ctiles = (int)((N + FWD_BN - 1) / FWD_BN);
+    const size_t range_bytes = align256((size_t)ctiles * sizeof(int2));
+    const size_t need = range_bytes + (size_t)4 * N * sizeof(float);
+    CY_CHECK_ARG(workspace && workspace_bytes >= need, "infonce_fwd2_tc: workspace %zu < %zu", workspace_bytes, need);
+    CY_CHECK_ARG(ctiles <= P2_LISTCAP, "infonce_fwd2_tc: N too large for the tile list");
+    int2* tile_range = reinterpret_cast<int2*>(workspace);
+    float* part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + range_bytes);
+    CUtensorMap tmap;
+    rc = make_tmap(&tmap, z, N, d, ldz, dtype);
+    if (rc) return rc;
+    infonce_tile_range_kernel<<<ctiles, 32, 0, st>>>(labels, (int)N, tile_range);
+    CY_CHECK_LAUNCH("infonce_tile_range");
+    const int fmt = dtype == CY_F16 ? 0 : 1;
+    const int64_t rb = (rows + TC_BM - 1) / TC_BM;
+    dim3 grid((unsigned)rb, 1);
+    const float4* xs = reinterpret_cast<const float4*>(xstat);
+    rc = CY_ERR_UNSUPPORTED;
+#define CY_P2(DV, VAR)                                                                                                          \
+    if (d == DV && variant == VAR)                                                                                              \
+        rc = launch_fwd_tc<DV, 2, VAR>(tmap, labels, (int)N, (int)row_begin, 0, ctiles, ctiles, inv_t, gamma, part, 0, fmt, z, ldz, \
+                                       tile_range, xs, grid, st);
+    CY_P2(256, CY_SUPCON_EXCLUDE) CY_P2(256, CY_SELFPACED_HARD) CY_P2(256, CY_SELFPACED_SOFT)
+    CY_P2(128, CY_SUPCON_EXCLUDE) CY_P2(128, CY_SELFPACED_HARD) CY_P2(128, CY_SELFPACED_SOFT)
+#undef CY_P2
+    if (rc) {
+        if (rc == CY_ERR_UNSUPPORTED) set_error("infonce_fwd2_tc: no instantiation for d=%lld variant=%d", (long long)d, variant);
+        return rc;
+    }
+    infonce_rowstats_kernel<2><<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(variant, (int)N, (int)row_begin, (int)row_end, inv_t, part, 2,
+                                                                              stats, reinterpret_cast<float4*>(xstat));
+    CY_CHECK_LAUNCH("infonce_rowstats<2>");
+    return CY_OK;
+}
+
+// row statistics from the SoA sums a SIMT sweep left in `stats` (same kernel, part == nullptr)
+int infonce_rowstats(int64_t N, int64_t row_begin, int64_t row_end, float inv_t, int variant, int pass, float* stats, float* xstat,
+                     cudaStream_t st) {
+    const int64_t rows = row_end - row_begin;
+    if (rows <= 0) return CY_OK;
+    if (pass == 1)
+        infonce_rowstats_kernel<1><<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(variant, (int)N, (int)row_begin, (int)row_end, inv_t,
+                                                                                  nullptr, 0, stats, reinterpret_cast<float4*>(xstat));
+    else
+        infonce_rowstats_kernel<2><<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(variant, (int)N, (int)row_begin, (int)row_end, inv_t,
+                                                                                  nullptr, 0, stats, reinterpret_cast<float4*>(xstat));
+    CY_CHECK_LAUNCH("infonce_rowstats");
+    return CY_OK;
+}
+
+size_t infonce_loss_workspace_bytes(int64_t N) { return (size_t)((N + LOSS_THREADS - 1) / LOSS_THREADS) * 4 * sizeof(float) + 256; }
+
+int infonce_loss(int64_t N, int variant, const float* xstat, float* out4, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    const int nblk = (int)((N + LOSS_THREADS - 1) / LOSS_THREADS);
+    CY_CHECK_ARG(workspace && workspace_bytes >= (size_t)nblk * 4 * sizeof(float), "infonce_loss: workspace %zu too small", workspace_bytes);
+    float* partials = reinterpret_cast<float*>(workspace);
+    infonce_loss_partial_kernel<<<nblk, LOSS_THREADS, 0, st>>>(variant, (int)N, reinterpret_cast<const float4*>(xstat), partials);
+    CY_CHECK_LAUNCH("infonce_loss_partial");
+    infonce_loss_final_kernel<<<1, 32, 0, st>>>(nblk, (int)N, partials, out4);
+    CY_CHECK_LAUNCH("infonce_loss_final");
+    return CY_OK;
+}
+
+template <int D, bool F16, int VARIANT>
+static int launch_bwd_tc(const CUtensorMap& tmap, const int32_t* labels, const float4* xstat, int N, int row_begin, int row_end, int tps,
+                         float inv_t, float gamma, const float* gscale, float out_scale, void* dz, int64_t lddz, float* dz32,
+                         int rows_total, const void* z, int64_t ldz, dim3 grid, cudaStream_t st) {
+    using C = BwdCfg<D>;
+    auto k = infonce_bwd_tc_kernel<D, F16, VARIANT>;
+    static SmemAttrCache attr;
+    if (attr.need(C::TOTAL)) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TOTAL);
+        if (e != cudaSuccess) { set_error("bwd_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr.set(C::TOTAL);
+    }
+    const int fmt = F16 ? 0 : 1;
+    k<<<grid, TC_THREADS, C::TOTAL, st>>>(tmap, labels, xstat, N, row_begin, row_end, tps, inv_t * LOG2E, inv_t, gamma, gscale, out_scale, dz,
+                                          lddz, dz32, rows_total, idesc_f16kind_f32(TC_BM, BWD_BN, 0, 0, fmt),
+                                          idesc_f16kind_f32(TC_BM, D, 0, 1, fmt), reinterpret_cast<const uint16_t*>(z), ldz);
+    CY_CHECK_LAUNCH("infonce_bwd_tc");
     return CY_OK;
 }
 
 int infonce_bwd_tc(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, int64_t row_begin, int64_t row_end,
-                   float inv_t, const float* stats, const float* gscale, void* dz, int64_t lddz, void* workspace,
+                   float inv_t, int variant, float gamma, const float* xstat, const float* gscale, void* dz, int64_t lddz, void* workspace,
                    size_t workspace_bytes, cudaStream_t st) {
-    (void)d;
     const int64_t rows = row_end - row_begin;
     if (rows <= 0) return CY_OK;
-    CY_CHECK_ARG((rows % TC_BM) == 0 && (row_begin % TC_BM) == 0, "tcgen05 path: row range must be 128-aligned");
+    int rc = check_tc_rows(N, row_begin, row_end);
+    if (rc) return rc;
     CY_CHECK_ARG((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(dz) & 15) == 0 && (lddz % 8) == 0,
                  "tcgen05 path: z / dz must be 16-byte aligned");
     CUtensorMap tmap;
-    int rc = make_tmap(&tmap, z, N, ldz, dtype);
+    rc = make_tmap(&tmap, z, N, d, ldz, dtype);
     if (rc) return rc;
     const bool f16 = dtype == CY_F16;
-    const int fmt = f16 ? 0 : 1;
-    auto kern = f16 ? infonce_bwd_tc_kernel<true> : infonce_bwd_tc_kernel<false>;
     const float out_scale = (inv_t / (float)N) * (f16 ? (1.f / 1024.f) : 1.f);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdCfg::TOTAL);
-    if (e != cudaSuccess) { set_error("bwd_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    const int splits = bwd_splits(N, rows);
-    const int nt = (int)(N / BwdCfg::BN);
+    const int64_t rb = (rows + TC_BM - 1) / TC_BM;
+    const int splits = bwd_splits(N, rb);
+    const int nt = (int)((N + BWD_BN - 1) / BWD_BN);
     const int tps = (nt + splits - 1) / splits;
     float* dz32 = nullptr;
+    const int64_t rows_pad = rb * TC_BM;
     if (splits > 1) {
-        const size_t need = (size_t)rows * TC_D * sizeof(float);
+        const size_t need = (size_t)splits * rows_pad * d * sizeof(float);
         CY_CHECK_ARG(workspace && workspace_bytes >= need, "infonce_bwd_tc: workspace %zu < %zu", workspace_bytes, need);
         dz32 = reinterpret_cast<float*>(workspace);
-        e = cudaMemsetAsync(dz32, 0, need, st);
-        if (e != cudaSuccess) { set_error("bwd_tc memset: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    dim3 grid((unsigned)(rows / TC_BM), (unsigned)splits);
-    kern<<<grid, TC_THREADS, BwdCfg::TOTAL, st>>>(tmap, labels, stats, (int)N, (int)row_begin, tps, inv_t * LOG2E, gscale, out_scale,
-                                                  dz, lddz, dz32, idesc_f16kind_f32(TC_BM, BwdCfg::BN, 0, 0, fmt),
-                                                  idesc_f16kind_f32(TC_BM, TC_D, 0, 1, fmt), reinterpret_cast<const uint16_t*>(z), ldz);
-    CY_CHECK_LAUNCH("infonce_bwd_tc");
+    dim3 grid((unsigned)rb, (unsigned)splits);
+    const float4* xs = reinterpret_cast<const float4*>(xstat);
+    rc = CY_ERR_UNSUPPORTED;
+#define CY_BW(DV, F, VAR)                                                                                                       \
+    if (d == DV && f16 == F && variant == VAR)                                                                                  \
+        rc = launch_bwd_tc<DV, F, VAR>(tmap, labels, xs, (int)N, (int)row_begin, (int)row_end, tps, inv_t, gamma, gscale, out_scale, dz, \
+                                       lddz, dz32, (int)rows_pad, z, ldz, grid, st);
+#define CY_BW4(DV, F) CY_BW(DV, F, CY_SUPCON) CY_BW(DV, F, CY_SUPCON_EXCLUDE) CY_BW(DV, F, CY_SELFPACED_HARD) CY_BW(DV, F, CY_SELFPACED_SOFT)
+    CY_BW4(256, false) CY_BW4(256, true) CY_BW4(128, false) CY_BW4(128, true)
+#undef CY_BW4
+#undef CY_BW
+    if (rc) {
+        if (rc == CY_ERR_UNSUPPORTED) set_error("infonce_bwd_tc: no instantiation for d=%lld variant=%d", (long long)d, variant);
+        return rc;
+    }
     if (dz32) {
-        const int64_t n8 = rows * (TC_D / 8);
-        if (f16)
-            infonce_tc_convert_kernel<true><<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dz32, rows, row_begin, gscale, out_scale,
-                                                                                        reinterpret_cast<uint16_t*>(dz), lddz);
-        else
-            infonce_tc_convert_kernel<false><<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dz32, rows, row_begin, gscale, out_scale,
-                                                                                         reinterpret_cast<uint16_t*>(dz), lddz);
+        const int64_t n8 = rows * (d / 8);
+        const unsigned g = (unsigned)((n8 + 255) / 256);
+        uint16_t* out = reinterpret_cast<uint16_t*>(dz);
+        if (d == 256 && f16) infonce_tc_convert_kernel<256, true><<<g, 256, 0, st>>>(dz32, splits, rows, rows_pad, row_begin, gscale, out_scale, out, lddz);
+        else if (d == 256) infonce_tc_convert_kernel<256, false><<<g, 256, 0, st>>>(dz32, splits, rows, rows_pad, row_begin, gscale, out_scale, out, lddz);
+        else if (f16) infonce_tc_convert_kernel<128, true><<<g, 256, 0, st>>>(dz32, splits, rows, rows_pad, row_begin, gscale, out_scale, out, lddz);
+        else infonce_tc_convert_kernel<128, false><<<g, 256, 0, st>>>(dz32, splits, rows, rows_pad, row_begin, gscale, out_scale, out, lddz);
         CY_CHECK_LAUNCH("infonce_tc_convert");
     }
     return CY_OK;

@@ -4,20 +4,23 @@ The reference has no distributed path at all (it never calls ``in
 each rank would contrast its local batch only.  What is built here is the row-sharded global-batch form of
 BASELINE.json's config 4:
 
-InfoNCE — rank r owns the rows of its local samples.
-  1. all-gather the embeddings (bf16: N*d*2 bytes, 32 MiB at N=65536) and the raw labels;
-  2. every rank runs the forward sweep for its row block against all N columns -> per-row statistics, partial loss;
-  3. all-gather three N-float row-statistic vectors, all-reduce the 4-float scalar block;
-  4. backward: every rank computes the COMPLETE gradient of its own rows with one more strip sweep
+InfoNCE — rank r owns the rows of its local samples (rank-major order of the gathered problem:
+  [r0 view1; r0 view2; r1 view1; ...]; for label-derived masks the order of rows is immaterial).  Per step:
+  1. local: canonical labels, local sort by label, one pack kernel (cat + permutation + is_normalized) that writes the
+     rank's rows straight into its slice of the [N, d] buffer;
+  2. all-gather (in place) of the embeddings (bf16: N*d*2 bytes, 32 MiB at N=65536) and of the sorted labels;
+  3. forward sweep(s) of the owned row block against all N columns -> the owned rows of ``xstat`` [N, 4];
+  4. all-gather (in place) of ``xstat`` (16 B per row: 1 MiB at N=65536) — the ONLY exchange of statistics; every rank
+     then reduces the loss from the gathered array in the same fixed order (identical bits, no scalar collective);
+  5. backward: every rank computes the COMPLETE gradient of its own rows with one more strip sweep
      (dZ_i = (1/t) sum_k (G_ik + G_ki) z_k needs only the statistics of rows i and k, SURVEY.md §8e design (ii)),
-     so no gradient collective is needed; the north_star's reduce-scatter of dZ (design (i)) would move 64 MiB to
-     produce the identical numbers.
-  Row order of the gathered problem is rank-major ([r0 view1; r0 view2; r1 view1; ...]): for label-derived masks the
-  order of rows is immaterial (P_ij depends on the labels only, the diagonal on i == j).
+     so no gradient collective is needed.  ``variant="reduce_scatter"`` runs the north_star's design (i) instead — each
+     rank produces its strip's contribution to ALL N rows and the [N, d] gradient is reduce-scattered — for comparison;
+     it moves N*d*4 bytes per rank to produce the same numbers.
 
-IIC — images are independent summands of the raw joint: every rank accumulates its images, the [K,K,T,T] joint is
-  all-reduced (900 floats) BEFORE the non-linear epilogue, which every rank then evaluates redundantly; the
-  backward is purely local.
+IIC — images are independent summands of the raw joint: every rank accumulates its images, the [K,K,T,T] joint (double) is
+  all-reduced (900 values) BEFORE the non-linear epilogue, which every rank then evaluates redundantly; the backward
+  is purely local.
 
 The returned loss is the global-batch loss on every rank and each rank's backward yields d(global loss)/d(its own
 samples).  Under DDP (which averages parameter gradients over ranks) pass ``grad_scale=world_size`` to recover exactly
@@ -31,8 +34,8 @@ from torch import Tensor
 
 from . import _lib as L
 
-__all__ = ["row_range", "rank_major_labels", "gather_rank_major", "make_stats_exchange", "exchange_strip_stats", "make_joint_reduce",
-           "ShardedSupConLoss", "shard_iic_loss"]
+__all__ = ["row_range", "gather_rank_major", "gather_rows_", "local_view_major", "make_joint_reduce", "ShardedSupConLoss",
+           "shard_iic_loss"]
 
 
 def _ws(group):
@@ -67,26 +70,20 @@ def gather_rank_major(local: Tensor, group=None) -> Tensor:
     return _GatherRows.apply(local, group)
 
 
-def rank_major_labels(raw_all: Tensor, world: int, canonicalize) -> Tensor:
-    """raw labels of all ranks [G * n_local] -> canonical int32 labels of the rank-major stacked problem
-    [G * 2 * n_local].  ``canonicalize(raw, n)`` returns the view-major tiling [raw; raw] as int32 (cy_labels_canonicalize)."""
-    n_all = raw_all.shape[0]
-    n_local = n_all // world
-    view_major = canonicalize(raw_all, n_all)                      # [2, G, n_local]
-    return view_major.view(2, world, n_local).permute(1, 0, 2).reshape(-1).contiguous()
+def gather_rows_(full: Tensor, group=None) -> Tensor:
+    """IN-PLACE all-gather of a rank-major array: ``full`` [G * m, ...] holds this rank's block at rows [rank*m, (rank+1)*m)
+    on entry and every rank's block on return (the collective reads the own block where it already lies)."""
+    world, rank = _ws(group)
+    m = full.shape[0] // world
+    dist.all_gather_into_tensor(full, full[rank * m:(rank + 1) * m], group=group)
+    return full
 
 
-def make_stats_exchange(n_local: int, group=None, stat_rows=(L.CY_STAT_LOGDEN, L.CY_STAT_INVC, L.CY_STAT_COEF, L.CY_STAT_AUX)):
-    """callback for losses.contrastive.info_nce(gather_stats=...): all-gather the row statistics the backward needs
-    for foreign columns, all-reduce the scalar block (partial loss, self-paced sums, NaN count)."""
-    rb, re = row_range(n_local, group)
-
-    def exchange(stats: Tensor, out4: Tensor):
-        for s in stat_rows:
-            dist.all_gather_into_tensor(stats[s], stats[s, rb:re].clone(), group=group)
-        dist.all_reduce(out4, group=group)
-
-    return exchange
+def local_view_major(raw_local: Tensor, canonicalize) -> Tensor:
+    """raw labels of this rank [n_local] -> canonical int32 labels of its row block [2 * n_local] (view-major tiling,
+    ``canonicalize(raw, n)`` = cy_labels_canonicalize).  Canonicalisation is element-wise, so doing it per rank gives the
+    same integers as doing it on the gathered vector."""
+    return canonicalize(raw_local, raw_local.shape[0])
 
 
 def make_joint_reduce(group=None):
@@ -102,98 +99,168 @@ def make_joint_reduce(group=None):
 
 
 class _ShardedInfoNCE(torch.autograd.Function):
-    """z_loc [2*n_loc, d] (this rank's stacked views, rows already in their final order) -> (loss, out4).
-
-    forward : all-gather z (rank-major), forward strip of the owned rows, ONE all-gather that carries the four row-statistic
-              vectors of the strip plus the four partial scalars of every rank.
-    backward: one backward strip -> the complete gradient of the owned rows, written straight into a [2*n_loc, d]
-              buffer (no N x d zero fill, no gradient collective)."""
+    """(f1, f2) [n_loc, d] local views -> (loss, out4, bad).  One autograd node per step: pack + the three in-place
+    all-gathers + forward sweep(s) + loss reduction in forward, strip backward + unpack in backward."""
 
     @staticmethod
-    def forward(ctx, z_loc, labels_all, inv_t, path, group):
+    def forward(ctx, f1, f2, labels_loc, order, inv_t, variant, gamma, path, group, check, design):
         lib = L.lib()
         world, rank = _ws(group)
-        rows_loc, d = z_loc.shape
+        n_loc, d = f1.shape
+        rows_loc = 2 * n_loc
         N = world * rows_loc
         rb, re = rank * rows_loc, (rank + 1) * rows_loc
-        dev = z_loc.device
-        dt = L.dtype_code(z_loc)
-        st = L.stream_ptr(dev)
-        z_all = torch.empty(N, d, dtype=z_loc.dtype, device=dev)
-        dist.all_gather_into_tensor(z_all, z_loc.contiguous(), group=group)
-        stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev)
-        out4 = torch.zeros(4, dtype=torch.float32, device=dev)
-        ws_bytes = lib.cy_infonce_workspace_bytes(N, d, dt, L.CY_SUPCON, path)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        L.check(lib.cy_infonce_fwd(z_all.data_ptr(), dt, N, d, d, labels_all.data_ptr(), None, rb, re, inv_t, L.CY_SUPCON, path,
-                                   stats.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd")
-        L.check(lib.cy_infonce_finalize(N, rb, re, inv_t, L.CY_SUPCON, 1, stats.data_ptr(), out4.data_ptr(), st),
-                "cy_infonce_finalize")
-        out4 = exchange_strip_stats(stats, out4, rb, re, group)
-        ctx.save_for_backward(z_all, labels_all, stats, ws)
-        ctx.cfg = (inv_t, path, rb, re)
-        ctx.mark_non_differentiable(out4)
-        return out4[0].clone(), out4
+        dev = f1.device
+        dt = L.dtype_code(f1)
+        with L.guard(f1):
+            st = L.stream_ptr(dev)
+            z_all = torch.empty(N, d, dtype=f1.dtype, device=dev)
+            labels_all = torch.empty(N, dtype=torch.int32, device=dev)
+            xstat = torch.empty(N, 4, dtype=torch.float32, device=dev)
+            stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev)
+            out4 = torch.empty(4, dtype=torch.float32, device=dev)
+            bad = torch.zeros(1, dtype=torch.int32, device=dev)
+            esz = f1.element_size()
+            L.check(lib.cy_infonce_pack(f1.data_ptr(), f2.data_ptr(), dt, n_loc, d, f1.stride(0), f2.stride(0), L.ptr(order),
+                                        z_all.data_ptr() + rb * d * esz, bad.data_ptr() if check else None, None, st),
+                    "cy_infonce_pack")
+            labels_all[rb:re].copy_(labels_loc)
+            gather_rows_(z_all, group)
+            gather_rows_(labels_all, group)
+            ws_bytes = lib.cy_infonce_workspace_bytes(N, d, dt, variant, path)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            zp, lp = z_all.data_ptr(), labels_all.data_ptr()
+            L.check(lib.cy_infonce_fwd(zp, dt, N, d, d, lp, None, rb, re, inv_t, variant, path, stats.data_ptr(), xstat.data_ptr(),
+                                       ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd")
+            if variant != L.CY_SUPCON:
+                L.check(lib.cy_infonce_fwd_pass2(zp, dt, N, d, d, lp, None, rb, re, inv_t, variant, gamma, path, stats.data_ptr(),
+                                                 xstat.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd_pass2")
+            gather_rows_(xstat, group)
+            L.check(lib.cy_infonce_loss(N, variant, xstat.data_ptr(), out4.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_loss")
+        ctx.save_for_backward(z_all, labels_all, xstat, ws, *([order] if order is not None else []))
+        ctx.cfg = (inv_t, variant, gamma, path, rb, re, n_loc, group, design)
+        ctx.mark_non_differentiable(out4, bad)
+        return out4[0].clone(), out4, bad
 
     @staticmethod
-    def backward(ctx, grad_loss, _grad_out4):
+    def backward(ctx, grad_loss, _g4, _gb):
         lib = L.lib()
-        z_all, labels_all, stats, ws = ctx.saved_tensors
-        inv_t, path, rb, re = ctx.cfg
+        z_all, labels_all, xstat, ws, *rest = ctx.saved_tensors
+        order = rest[0] if rest else None
+        inv_t, variant, gamma, path, rb, re, n_loc, group, design = ctx.cfg
         N, d = z_all.shape
-        gscale = grad_loss
-        if gscale.dtype != torch.float32 or gscale.numel() != 1 or not gscale.is_contiguous():
-            gscale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
-        dz_loc = torch.empty(re - rb, d, dtype=z_all.dtype, device=z_all.device)
-        # the kernels index dz by GLOBAL row: hand them the address row rb would have in a full [N, d] gradient
-        dz_base = dz_loc.data_ptr() - rb * d * dz_loc.element_size()
-        L.check(lib.cy_infonce_bwd(z_all.data_ptr(), L.dtype_code(z_all), N, d, d, labels_all.data_ptr(), None, rb, re, inv_t,
-                                   L.CY_SUPCON, 0.0, path, stats.data_ptr(), gscale.data_ptr(), dz_base, d, ws.data_ptr(),
-                                   ws.numel(), L.stream_ptr(z_all.device)), "cy_infonce_bwd")
-        return dz_loc, None, None, None, None
+        dev = z_all.device
+        dt = L.dtype_code(z_all)
+        with L.guard(z_all):
+            st = L.stream_ptr(dev)
+            gscale = grad_loss
+            if gscale.dtype != torch.float32 or gscale.numel() != 1 or not gscale.is_contiguous():
+                gscale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+            if design == "reduce_scatter":
+                dz_loc = _strip_contribution_reduce_scatter(z_all, labels_all, xstat, gscale, inv_t, variant, gamma, rb, re, group)
+            else:
+                dz_loc = torch.empty(re - rb, d, dtype=z_all.dtype, device=dev)
+                # the kernels index dz by GLOBAL row: hand them the address row rb would have in a full [N, d] gradient
+                dz_base = dz_loc.data_ptr() - rb * d * dz_loc.element_size()
+                L.check(lib.cy_infonce_bwd(z_all.data_ptr(), dt, N, d, d, labels_all.data_ptr(), None, rb, re, inv_t, variant, gamma,
+                                           path, xstat.data_ptr(), gscale.data_ptr(), dz_base, d, ws.data_ptr(), ws.numel(), st),
+                        "cy_infonce_bwd")
+            g1 = torch.empty(n_loc, d, dtype=dz_loc.dtype, device=dev)
+            g2 = torch.empty(n_loc, d, dtype=dz_loc.dtype, device=dev)
+            L.check(lib.cy_infonce_unpack(dz_loc.data_ptr(), dt, n_loc, d, d, L.ptr(order), g1.data_ptr(), g2.data_ptr(), None, None,
+                                          st), "cy_infonce_unpack")
+        return g1, g2, None, None, None, None, None, None, None, None, None
 
 
-_STAT_ROWS = (L.CY_STAT_LOGDEN, L.CY_STAT_INVC, L.CY_STAT_COEF, L.CY_STAT_AUX)
-
-
-def exchange_strip_stats(stats: Tensor, out4: Tensor, rb: int, re: int, group=None) -> Tensor:
-    """ONE all-gather for what ``make_stats_exchange`` does with five collectives: every rank sends
-    [4 statistic rows of its strip | its 4 partial scalars]; on return ``stats`` holds the four rows for all N columns
-    (rank-major strips) and the summed scalar block is returned."""
-    world, _ = _ws(group)
-    rows_loc = re - rb
-    N = stats.shape[1]
-    assert _STAT_ROWS == (0, 1, 2, 3)      # the four rows are the leading rows of `stats`: plain slices, no index tensors
-    send = torch.cat([stats[:4, rb:re].reshape(-1), out4])          # (a python index list would cost a pageable H2D + sync)
-    recv = torch.empty(world * send.numel(), dtype=stats.dtype, device=stats.device)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    recv = recv.view(world, send.numel())
-    stats[:4].view(4, world, rows_loc).copy_(recv[:, :4 * rows_loc].view(world, 4, rows_loc).permute(1, 0, 2))
-    return recv[:, 4 * rows_loc:].sum(dim=0)
+def _strip_contribution_reduce_scatter(z_all, labels_all, xstat, gscale, inv_t, variant, gamma, rb, re, group):
+    """north_star design (i), kept for the side-by-side timing: this rank evaluates dL/dS for ITS strip of
+    rows only (G_ij for i owned, every j) and scatters both factors of dZ = (1/t)(G Z + G^T Z) — the owned rows get G Z,
+    every column j gets its G^T Z share — into a full [N, d] fp32 gradient, which is then reduce-scattered over the
+    ranks.  Evaluated with stock torch ops on the strip (tile by tile, fp32): it is the contract-named data flow, not the
+    optimised path; numbers are identical to design (ii) up to summation order."""
+    world, rank = _ws(group)
+    N, d = z_all.shape
+    rows = re - rb
+    lab_i = labels_all[rb:re]
+    xs_i = xstat[rb:re]
+    zf = z_all.float()
+    zi = zf[rb:re]
+    dz = torch.zeros(N, d, dtype=torch.float32, device=z_all.device)
+    if variant != L.CY_SUPCON:
+        raise NotImplementedError("the reduce-scatter comparison design covers SupConLoss1's default variant")
+    step = 4096
+    for j0 in range(0, N, step):
+        j1 = min(N, j0 + step)
+        s = zi @ zf[j0:j1].t()
+        e = torch.exp((s - 1.0) * inv_t)
+        pos = (lab_i[:, None] == labels_all[None, j0:j1])
+        g = e * xs_i[:, 2:3] - pos.to(torch.float32) * xs_i[:, 1:2]            # G_ij = coef_i E_ij - P_ij / c_i
+        if rb < j1 and re > j0:                                                 # clear the diagonal of this block
+            lo, hi = max(rb, j0), min(re, j1)
+            idx = torch.arange(lo, hi, device=z_all.device)
+            g[idx - rb, idx - j0] = 0.0
+        dz[rb:re] += g @ zf[j0:j1]
+        dz[j0:j1] += g.t() @ zi
+    dz *= gscale * (inv_t / N)
+    out = torch.empty(rows, d, dtype=torch.float32, device=z_all.device)
+    dist.reduce_scatter_tensor(out, dz, group=group)
+    return out.to(z_all.dtype)
 
 
 class ShardedSupConLoss(torch.nn.Module):
-    """Global-batch SupConLoss1 over all ranks of ``group`` (label / SimCLR masks).  Same forward signature as the
-    single-process module; every rank passes its local views and labels.
+    """Global-batch SupConLoss1 over all ranks of ``group`` (label / SimCLR masks, every variant of the family through
+    ``exclude_other_pos`` / ``self_paced``).  Same forward signature as the single-process module; every rank passes its
+    local views and labels.
 
-    Per step and rank: canonical labels of all ranks (one tiny all-gather), a LOCAL sort of the owned rows by label
-    (the loss is invariant under row permutations inside a rank's block; the other ranks' blocks arrive sorted), one
-    pack kernel (cat + permutation + is_normalized), then ``_ShardedInfoNCE`` (two more collectives)."""
+    ``backward_design``: "local" (default; complete gradient of the owned rows from the gathered row statistics, no gradient
+    collective — SURVEY.md §8e (ii)) or "reduce_scatter" (north_star's design (i), for comparison)."""
 
-    def __init__(self, temperature=0.07, *, group=None, grad_scale: float = 1.0, path: str = "auto",
-                 deferred_checks: bool = False):
+    def __init__(self, temperature=0.07, exclude_other_pos=False, *, group=None, grad_scale: float = 1.0, path: str = "auto",
+                 deferred_checks: bool = False, backward_design: str = "local"):
         super().__init__()
         self._t = temperature
         self._group = group
         self._grad_scale = float(grad_scale)
+        self._variant = L.CY_SUPCON_EXCLUDE if exclude_other_pos else L.CY_SUPCON
+        self._gamma = 1e6
         # deferred_checks: as in SupConLoss1 — device-side counters instead of the per-step host read, which makes the step
         # (collectives included) capturable in a CUDA graph when the labels are a tensor
         self._deferred_checks = deferred_checks
         self._flags = None
+        assert backward_design in ("local", "reduce_scatter")
+        self._design = backward_design
         self._path = {"auto": L.CY_PATH_AUTO, "simt": L.CY_PATH_SIMT, "tcgen05": L.CY_PATH_TCGEN05}[path]
+        self._cache = None
+
+    def _local_labels(self, target, n_local, rank, device, sort):
+        """canonical labels of the owned row block (+ the local sort), cached while the same label tensor comes back"""
+        from .losses.contrastive import _canonical_labels, _TensorLabelCache
+        overflow = None
+        if target is None:      # SimCLR: globally unique ids
+            raw = torch.arange(rank * n_local, (rank + 1) * n_local, dtype=torch.int32, device=device)
+        elif isinstance(target, list):
+            raw = torch.tensor(target, dtype=torch.float32, device=device)      # contrastive.py:39-40
+        else:
+            raw = target
+        cacheable = isinstance(target, Tensor)
+        if cacheable:
+            if self._cache is None:
+                self._cache = _TensorLabelCache()
+            hit = self._cache.get(target, n_local, device, sort)
+            if hit is not None:
+                return hit[0], hit[1], None
+        if isinstance(raw, Tensor) and raw.dtype == torch.int64:
+            overflow = torch.zeros(1, dtype=torch.int32, device=device)
+        labels = _canonical_labels(raw, n_local, device, overflow)
+        order = None
+        if sort:
+            order = torch.argsort(labels)
+            labels = labels.index_select(0, order)
+        if cacheable and overflow is None:
+            self._cache.put(target, n_local, device, sort, (labels, order))
+        return labels, order, overflow
 
     def forward(self, proj_feat1: Tensor, proj_feat2: Tensor, target=None, mask: Optional[Tensor] = None, **kwargs):
-        from .losses.contrastive import _canonical_labels, _PackViews
         if mask is not None:
             raise NotImplementedError("the sharded loss derives masks from labels (explicit [n,n] masks are per-process)")
         L.require_cuda(proj_feat1, proj_feat2)
@@ -204,39 +271,29 @@ class ShardedSupConLoss(torch.nn.Module):
         rows_loc = 2 * n_local
         N = world * rows_loc
         device = proj_feat1.device
-        if target is None:      # SimCLR: globally unique ids
-            raw = torch.arange(rank * n_local, (rank + 1) * n_local, dtype=torch.int32, device=device)
-        elif isinstance(target, list):
-            raw = torch.tensor(target, dtype=torch.float32, device=device)      # contrastive.py:39-40
-        else:
-            raw = target.to(device)
-        raw_all = torch.empty(world * n_local, dtype=raw.dtype, device=device)
-        dist.all_gather_into_tensor(raw_all, raw.contiguous(), group=self._group)
-        labels_all = rank_major_labels(raw_all, world, lambda r, n: _canonical_labels(r, n, device))      # [N]
-        order = None
-        tc = (proj_feat1.dtype in (torch.bfloat16, torch.float16) and d == 256 and rows_loc % 128 == 0 and N >= 256
+        # sort every rank's block by label when the tensor kernels will run (every rank decides the same way)
+        tc = (proj_feat1.dtype in (torch.bfloat16, torch.float16) and d in (128, 256) and rows_loc % 128 == 0 and N >= 256
+              and (self._variant == L.CY_SUPCON or N <= 4096 * 128)
               and (self._path == L.CY_PATH_TCGEN05 or (self._path == L.CY_PATH_AUTO and N >= 1024)))
-        if tc:      # sort every rank's block by label; the permutation is needed for the owned block only
-            sorted_blocks, perm = labels_all.view(world, rows_loc).sort(dim=1)
-            order = perm[rank]
-            labels_all = sorted_blocks.reshape(-1)
+        labels_loc, order, overflow = self._local_labels(target, n_local, rank, device, tc)
         f1 = proj_feat1 if proj_feat1.stride(1) == 1 else proj_feat1.contiguous()
         f2 = proj_feat2 if proj_feat2.stride(1) == 1 else proj_feat2.contiguous()
-        z_loc, bad = _PackViews.apply(f1, f2, order, __debug__, False)
-        loss, _ = _ShardedInfoNCE.apply(z_loc, labels_all, float(1.0 / self._t), self._path, self._group)
+        loss, _, bad = _ShardedInfoNCE.apply(f1, f2, labels_loc, order, float(1.0 / self._t), self._variant, float(self._gamma),
+                                             self._path, self._group, __debug__, self._design)
         if self._deferred_checks:
             nan = torch.isnan(loss.detach()).to(torch.int32).reshape(1)
-            cur = torch.cat((bad.to(torch.int32).reshape(1) if bad.numel() else torch.zeros_like(nan), nan))
+            cur = torch.cat((bad, nan, overflow if overflow is not None else torch.zeros_like(nan)))
             if self._flags is None or self._flags.device != cur.device:
                 self._flags = cur.clone()
             else:
                 self._flags.add_(cur)       # in place: the counters keep their address across CUDA-graph replays
             return loss * self._grad_scale if self._grad_scale != 1.0 else loss
-        if __debug__:
-            nbad, val = torch.stack((bad[0].to(torch.float32), loss.detach())).tolist()
-            assert nbad == 0, f"features need to be normalized first"
-        else:
-            val = loss.item()
+        zero = loss.detach().new_zeros(())
+        nbad, over, val = torch.stack((bad[0].to(torch.float32), overflow[0].to(torch.float32) if overflow is not None else zero,
+                                       loss.detach())).tolist()
+        assert nbad == 0, f"features need to be normalized first"
+        if over:
+            raise ValueError("int64 labels outside the int32 range are not supported (pass int32 labels or a python list)")
         if val != val:
             raise RuntimeError(loss)
         return loss * self._grad_scale if self._grad_scale != 1.0 else loss
@@ -245,9 +302,11 @@ class ShardedSupConLoss(torch.nn.Module):
         """deferred_checks mode: one host read of this rank's accumulated (un-normalised rows, NaN losses) counters"""
         if self._flags is None:
             return
-        nbad, nan = self._flags.tolist()
+        nbad, nan, over = self._flags.tolist()
         self._flags.zero_()
         assert nbad == 0, f"features need to be normalized first"
+        if over:
+            raise ValueError("int64 labels outside the int32 range are not supported (pass int32 labels or a python list)")
         if nan:
             raise RuntimeError(f"loss was NaN in {nan} forward call(s)")
 

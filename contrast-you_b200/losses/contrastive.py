@@ -30,11 +30,13 @@ def is_normalized(feature: Tensor, dim=1):
 _LABEL_CACHE = {}
 
 
-def _canonical_labels(target, n: int, device) -> Tensor:
+def _canonical_labels(target, n: int, device, overflow: Optional[Tensor] = None) -> Tensor:
     """[2n] int32 labels whose integer equality reproduces the reference comparison (contrastive.py:38-44).
 
     python lists go through ``torch.Tensor(list)`` in the reference, i.e. float32 (labels >= 2**24 collide, -0.0 == 0.0,
-    NaN equals nothing); tensors are compared in their own dtype."""
+    NaN equals nothing); tensors are compared in their own dtype.  int64 tensors (torch's default integer dtype) are
+    narrowed on the device; values outside the int32 range bump ``overflow`` (an int32 [1] device counter the modules read
+    together with their NaN check and turn into a ValueError) instead of costing a sort + host sync per step."""
     lib = L.lib()
     if isinstance(target, list):
         # cached by content (SURVEY.md §8f rank 4): a python list costs a pageable H2D copy + stream sync on every call
@@ -56,8 +58,10 @@ def _canonical_labels(target, n: int, device) -> Tensor:
         src, kind = target.to(torch.float32).contiguous(), 0      # exact widening
     elif target.dtype in (torch.int32, torch.int16, torch.int8, torch.uint8, torch.bool):
         src, kind = target.to(torch.int32).contiguous(), 1
+    elif target.dtype == torch.int64 and overflow is not None:
+        src, kind = target.contiguous(), 2
     else:
-        # 64-bit types: rank the distinct values (exact for any value range; costs one sort)
+        # float64 (and int64 without a counter): rank the distinct values (exact for any value range; costs one sort)
         if target.dtype.is_floating_point:
             target = torch.where(target == 0, torch.zeros_like(target), target)     # -0.0 == +0.0
             nan = target != target
@@ -65,9 +69,30 @@ def _canonical_labels(target, n: int, device) -> Tensor:
                 raise ValueError("NaN labels are not supported for float64 targets")
         src, kind = torch.unique(target, return_inverse=True)[1].to(torch.int32).contiguous(), 1
     with L.guard(out):
-        L.check(lib.cy_labels_canonicalize(src.data_ptr(), kind, n, out.data_ptr(), L.stream_ptr(out.device)),
-                "cy_labels_canonicalize")
+        L.check(lib.cy_labels_canonicalize(src.data_ptr(), kind, n, out.data_ptr(), L.ptr(overflow) if kind == 2 else None,
+                                           L.stream_ptr(out.device)), "cy_labels_canonicalize")
     return out
+
+
+class _TensorLabelCache:
+    """canonical (and sorted) labels of a label TENSOR that is passed again unchanged (same object, same autograd version
+    counter): fixed meta-labels, a partition list kept on the device, the bench's resident batch.  The entry holds a strong
+    reference to the tensor, so its storage cannot be recycled for different labels while the entry lives; any in-place
+    write bumps ``_version`` and invalidates it."""
+
+    def __init__(self, capacity=4):
+        self._entries, self._cap = [], capacity
+
+    def get(self, target, n, device, sort):
+        for e in self._entries:
+            if e[0] is target and e[1] == target._version and e[2] == (n, str(device), sort):
+                return e[3]
+        return None
+
+    def put(self, target, n, device, sort, value):
+        self._entries.append((target, target._version, (n, str(device), sort), value))
+        if len(self._entries) > self._cap:
+            self._entries.pop(0)
 
 
 def _mask_codes(mask: Tensor, n: int, device) -> Tensor:
@@ -82,33 +107,39 @@ def _mask_codes(mask: Tensor, n: int, device) -> Tensor:
 
 # ----------------------------------------------------------------------------------------------------- autograd glue
 class _InfoNCEFunction(torch.autograd.Function):
-    """z [N, d] (both views stacked) -> (loss, out4).  Rows [row_begin, row_end) are the ones this process owns."""
+    """z [N, d] (both views stacked) -> (loss, out4).  Rows [row_begin, row_end) are the ones this process owns.
+
+    forward : cy_infonce_fwd (+ cy_infonce_fwd_pass2 for exclude / self-paced) fill the owned rows of ``xstat`` [N, 4];
+              ``gather_xstat`` (row-sharded multi-GPU) all-gathers the other ranks' rows in place; cy_infonce_loss reduces
+              the loss from all N rows.
+    backward: one sweep, complete gradient of the owned rows (no gradient collective)."""
 
     @staticmethod
-    def forward(ctx, z, labels, codes, inv_t, variant, gamma, path, row_begin, row_end, gather_stats):
+    def forward(ctx, z, labels, codes, inv_t, variant, gamma, path, row_begin, row_end, gather_xstat):
         lib = L.lib()
         N, d = z.shape
         dt = L.dtype_code(z)
         with L.guard(z):
             st = L.stream_ptr(z.device)
             stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=z.device)
-            out4 = torch.zeros(4, dtype=torch.float32, device=z.device)
+            whole = (row_begin, row_end) == (0, N)
+            # rows nobody fills (a bare row range without an exchange) must read as "no contribution"
+            xstat = (torch.empty if whole or gather_xstat is not None else torch.zeros)(N, 4, dtype=torch.float32, device=z.device)
+            out4 = torch.empty(4, dtype=torch.float32, device=z.device)
             ws_bytes = lib.cy_infonce_workspace_bytes(N, d, dt, variant, path)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
             lp, cp = L.ptr(labels), L.ptr(codes)
             L.check(lib.cy_infonce_fwd(z.data_ptr(), dt, N, d, z.stride(0), lp, cp, row_begin, row_end, inv_t, variant, path,
-                                       stats.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd")
-            L.check(lib.cy_infonce_finalize(N, row_begin, row_end, inv_t, variant, 1, stats.data_ptr(), out4.data_ptr(), st),
-                    "cy_infonce_finalize")
+                                       stats.data_ptr(), xstat.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd")
             if variant != L.CY_SUPCON:
                 L.check(lib.cy_infonce_fwd_pass2(z.data_ptr(), dt, N, d, z.stride(0), lp, cp, row_begin, row_end, inv_t, variant,
-                                                 gamma, L.CY_PATH_SIMT, stats.data_ptr(), ws.data_ptr(), ws_bytes, st),
+                                                 gamma, path, stats.data_ptr(), xstat.data_ptr(), ws.data_ptr(), ws_bytes, st),
                         "cy_infonce_fwd_pass2")
-                L.check(lib.cy_infonce_finalize(N, row_begin, row_end, inv_t, variant, 2, stats.data_ptr(), out4.data_ptr(), st),
-                        "cy_infonce_finalize")
-            if gather_stats is not None:
-                gather_stats(stats, out4)       # sharded: all-gather the row statistics, all-reduce the scalars
-        ctx.save_for_backward(z, labels, codes, stats, ws)
+            if gather_xstat is not None:
+                gather_xstat(xstat)             # sharded: in-place all-gather of the owned rows
+            L.check(lib.cy_infonce_loss(N, variant, xstat.data_ptr(), out4.data_ptr(), ws.data_ptr(), ws_bytes, st),
+                    "cy_infonce_loss")
+        ctx.save_for_backward(z, labels, codes, xstat, ws)
         ctx.cfg = (inv_t, variant, gamma, path, row_begin, row_end)
         ctx.mark_non_differentiable(out4)
         return out4[0].clone(), out4
@@ -116,14 +147,14 @@ class _InfoNCEFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss, _grad_out4):
         lib = L.lib()
-        z, labels, codes, stats, ws = ctx.saved_tensors
+        z, labels, codes, xstat, ws = ctx.saved_tensors
         inv_t, variant, gamma, path, row_begin, row_end = ctx.cfg
         N, d = z.shape
         with L.guard(z):
             gscale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
             dz = torch.zeros_like(z) if (row_begin, row_end) != (0, N) else torch.empty_like(z)
             L.check(lib.cy_infonce_bwd(z.data_ptr(), L.dtype_code(z), N, d, z.stride(0), L.ptr(labels), L.ptr(codes), row_begin,
-                                       row_end, inv_t, variant, gamma, path, stats.data_ptr(), gscale.data_ptr(), dz.data_ptr(),
+                                       row_end, inv_t, variant, gamma, path, xstat.data_ptr(), gscale.data_ptr(), dz.data_ptr(),
                                        dz.stride(0), ws.data_ptr(), ws.numel(), L.stream_ptr(z.device)), "cy_infonce_bwd")
         return dz, None, None, None, None, None, None, None, None, None
 
@@ -174,10 +205,10 @@ class _PackViews(torch.autograd.Function):
 
 
 def tensor_core_eligible(z: Tensor, labels, codes, variant: int, path: int) -> bool:
-    """mirror of the C-side dispatch (c_abi.cu resolve_path): does this call run on the tcgen05 kernels?"""
+    """mirror of the C-side dispatch (c_abi.cu resolve_path): does this whole-range call run on the tcgen05 kernels?"""
     N, d = z.shape
-    ok = (z.dtype in (torch.bfloat16, torch.float16) and d == 256 and N % 128 == 0 and N >= 256 and codes is None and labels is not None
-          and variant == L.CY_SUPCON)
+    ok = (z.dtype in (torch.bfloat16, torch.float16) and d in (128, 256) and N >= 256 and codes is None and labels is not None
+          and (variant == L.CY_SUPCON or N <= 4096 * 128))
     return ok and (path == L.CY_PATH_TCGEN05 or (path == L.CY_PATH_AUTO and N >= 1024))
 
 
@@ -196,7 +227,7 @@ def sort_rows_by_label(z: Tensor, labels: Tensor, lo: int = 0, hi: Optional[int]
 
 
 def info_nce(z: Tensor, labels: Optional[Tensor], codes: Optional[Tensor], temperature: float, variant: int = L.CY_SUPCON,
-             gamma: float = 1e6, path: int = L.CY_PATH_AUTO, rows=None, gather_stats=None, sort_rows: bool = False):
+             gamma: float = 1e6, path: int = L.CY_PATH_AUTO, rows=None, gather_xstat=None, sort_rows: bool = False):
     """Functional entry: z [N, d] stacked views, int32 labels [N] (tiled) or uint8 codes [n, n] -> (loss, out4)."""
     L.require_cuda(z, labels, codes)
     if z.dim() != 2:
@@ -208,30 +239,55 @@ def info_nce(z: Tensor, labels: Optional[Tensor], codes: Optional[Tensor], tempe
         z, labels = sort_rows_by_label(z, labels)
     rb, re = (0, N) if rows is None else rows
     return _InfoNCEFunction.apply(z, labels, codes, float(1.0 / temperature), int(variant), float(gamma), int(path),
-                                  int(rb), int(re), gather_stats)
+                                  int(rb), int(re), gather_xstat)
 
 
 # ----------------------------------------------------------------------------------------------------- modules
 class _ContrastBase(nn.Module):
     _variant = L.CY_SUPCON
+    _path = L.CY_PATH_AUTO
+
+    def _kernel_variant(self) -> int:
+        return self._variant
 
     def _prepare(self, proj_feat1, proj_feat2, target, mask, sort=False):
         L.require_cuda(proj_feat1, proj_feat2)
         batch_size = proj_feat1.size(0)
         device = proj_feat2.device
         labels = codes = None
+        self._overflow = None
+        cacheable = False
         if mask is not None:
             assert mask.shape == torch.Size([batch_size, batch_size])
             codes = _mask_codes(mask, batch_size, device)
         elif target is not None:
-            labels = _canonical_labels(target, batch_size, device)
+            cacheable = isinstance(target, Tensor)
         else:  # SimCLR: only the twin view is positive
             labels = torch.arange(batch_size, dtype=torch.int32, device=device).repeat(2)
         assert proj_feat1.shape == proj_feat2.shape, (proj_feat1.shape, proj_feat2.shape)
-        self._views = (proj_feat1.detach(), proj_feat2.detach(), labels, codes)      # lazy side channels (original row order)
-        self._dbg_cache = {}
         fused = (proj_feat1.dim() == 2 and proj_feat1.dtype == proj_feat2.dtype and proj_feat1.device == proj_feat2.device
                  and proj_feat1.dtype in (torch.float32, torch.bfloat16, torch.float16))
+        do_sort = bool(sort and fused and codes is None and self._sorts_rows(proj_feat1))
+        order = None
+        hit = None
+        if cacheable:
+            cache = self.__dict__.setdefault("_label_cache", _TensorLabelCache())
+            hit = cache.get(target, batch_size, device, do_sort)
+        if hit is not None:
+            labels, order, sorted_labels = hit
+        elif codes is None:
+            if labels is None:
+                if isinstance(target, Tensor) and target.dtype == torch.int64:
+                    self._overflow = torch.zeros(1, dtype=torch.int32, device=device)
+                labels = _canonical_labels(target, batch_size, device, self._overflow)
+            sorted_labels = labels
+            if do_sort:
+                order = torch.argsort(labels)          # equal labels adjacent: the loss is invariant under row permutations
+                sorted_labels = labels.index_select(0, order)
+            if cacheable and self._overflow is None:   # (an entry made under an overflow counter would skip the check on a hit)
+                cache.put(target, batch_size, device, do_sort, (labels, order, sorted_labels))
+        self._views = (proj_feat1.detach(), proj_feat2.detach(), labels, codes)      # lazy side channels (original row order)
+        self._dbg_cache = {}
         normalize = bool(getattr(self, "_normalize_input", False))
         if not fused:
             if normalize:
@@ -242,16 +298,18 @@ class _ContrastBase(nn.Module):
             return torch.cat([proj_feat1, proj_feat2], dim=0), labels, codes
         f1 = proj_feat1 if proj_feat1.stride(1) == 1 else proj_feat1.contiguous()
         f2 = proj_feat2 if proj_feat2.stride(1) == 1 else proj_feat2.contiguous()
-        order = None
-        if sort and codes is None and self._sorts_rows(f1, labels):
-            order = torch.argsort(labels)          # equal labels adjacent: the loss is invariant under row permutations
-            labels = labels.index_select(0, order)
         z, bad = _PackViews.apply(f1, f2, order, __debug__, normalize)
         self._bad = bad if (__debug__ and not normalize) else None
-        return z, labels, codes
+        return z, (sorted_labels if codes is None else None), codes
 
-    def _sorts_rows(self, f1, labels) -> bool:
-        return False
+    def _sorts_rows(self, f1) -> bool:
+        """rows are sorted by label when the call runs on the tensor kernels: positives then sit in a few column tiles, the
+        mask-free epilogue runs everywhere else and the second sweep of exclude / self-paced visits O(1) tiles per row block"""
+        n, d = f1.shape
+        variant = self._kernel_variant()
+        ok = (f1.dtype in (torch.bfloat16, torch.float16) and d in (128, 256) and 2 * n >= 256
+              and (variant == L.CY_SUPCON or 2 * n <= 4096 * 128))
+        return ok and (self._path == L.CY_PATH_TCGEN05 or (self._path == L.CY_PATH_AUTO and 2 * n >= 1024))
 
     def _host_checks(self, loss: Tensor):
         """the reference's two assertions / errors in ONE device->host read: un-normalised rows (contrastive.py:58,
@@ -261,19 +319,25 @@ class _ContrastBase(nn.Module):
         ``raise_if_flagged()`` inspects whenever the caller chooses (e.g. once per epoch): the forward then has no host
         synchronisation at all and — with tensor labels — can be captured in a CUDA graph
         (``torch.cuda.make_graphed_callables``)."""
+        ovf = getattr(self, "_overflow", None)
         if getattr(self, "_deferred_checks", False):
             nan = torch.isnan(loss.detach()).to(torch.int32).reshape(1)
             bad = self._bad if self._bad is not None else torch.zeros_like(nan)
-            cur = torch.cat((bad.to(torch.int32), nan))
+            cur = torch.cat((bad.to(torch.int32), nan, ovf if ovf is not None else torch.zeros_like(nan)))
             flags = getattr(self, "_flags", None)
             if flags is None or flags.device != cur.device:
                 self._flags = cur.clone()
             else:
                 flags.add_(cur)         # in place: the counter tensor keeps its address across CUDA-graph replays
             return
-        if self._bad is not None:
-            bad, val = torch.stack((self._bad[0].to(torch.float32), loss.detach().to(torch.float32))).tolist()
+        if self._bad is not None or ovf is not None:
+            zero = loss.detach().new_zeros(())
+            bad, over, val = torch.stack((self._bad[0].to(torch.float32) if self._bad is not None else zero,
+                                          ovf[0].to(torch.float32) if ovf is not None else zero,
+                                          loss.detach().to(torch.float32))).tolist()
             assert bad == 0, f"features need to be normalized first"
+            if over:
+                raise ValueError("int64 labels outside the int32 range are not supported (pass int32 labels or a python list)")
         else:
             val = loss.item()
         if val != val:
@@ -285,9 +349,11 @@ class _ContrastBase(nn.Module):
         flags = getattr(self, "_flags", None)
         if flags is None:
             return
-        bad, nan = flags.tolist()
+        bad, nan, over = flags.tolist()
         flags.zero_()
         assert bad == 0, f"features need to be normalized first"
+        if over:
+            raise ValueError("int64 labels outside the int32 range are not supported (pass int32 labels or a python list)")
         if nan:
             raise RuntimeError(f"loss was NaN in {nan} forward call(s)")
 
@@ -336,19 +402,14 @@ class SupConLoss1(_ContrastBase):
         self._normalize_input = normalize_input
         self._path = {"auto": L.CY_PATH_AUTO, "simt": L.CY_PATH_SIMT, "tcgen05": L.CY_PATH_TCGEN05}[path]
 
+    def _kernel_variant(self) -> int:
+        return L.CY_SUPCON_EXCLUDE if self._exclude_pos else L.CY_SUPCON
+
     def forward(self, proj_feat1, proj_feat2, target=None, mask: Tensor = None, **kwargs):
         z, labels, codes = self._prepare(proj_feat1, proj_feat2, target, mask, sort=True)
-        variant = L.CY_SUPCON_EXCLUDE if self._exclude_pos else L.CY_SUPCON
-        loss, _ = info_nce(z, labels, codes, self._t, variant, path=self._path, sort_rows=False)
+        loss, _ = info_nce(z, labels, codes, self._t, self._kernel_variant(), path=self._path, sort_rows=False)
         self._host_checks(loss)
         return loss
-
-    def _sorts_rows(self, f1, labels) -> bool:
-        n, d = f1.shape
-        variant = L.CY_SUPCON_EXCLUDE if self._exclude_pos else L.CY_SUPCON
-        ok = (f1.dtype in (torch.bfloat16, torch.float16) and d == 256 and (2 * n) % 128 == 0 and 2 * n >= 256
-              and variant == L.CY_SUPCON)
-        return ok and (self._path == L.CY_PATH_TCGEN05 or (self._path == L.CY_PATH_AUTO and 2 * n >= 1024))
 
 
 class SelfPacedSupConLoss(_ContrastBase):
@@ -363,11 +424,15 @@ class SelfPacedSupConLoss(_ContrastBase):
         self._weight_update = weight_update
         self.__gamma = 1e6
         self._correct_grad = correct_grad
+        path = kwargs.get("path", "auto")      # keyword-only extra, like SupConLoss1: "auto" | "simt" | "tcgen05"
+        self._path = {"auto": L.CY_PATH_AUTO, "simt": L.CY_PATH_SIMT, "tcgen05": L.CY_PATH_TCGEN05}[path]
+
+    def _kernel_variant(self) -> int:
+        return L.CY_SELFPACED_HARD if self._weight_update == "hard" else L.CY_SELFPACED_SOFT
 
     def forward(self, proj_feat1, proj_feat2, target=None, mask: Tensor = None, **kwargs):
-        z, labels, codes = self._prepare(proj_feat1, proj_feat2, target, mask)
-        variant = L.CY_SELFPACED_HARD if self._weight_update == "hard" else L.CY_SELFPACED_SOFT
-        loss, out4 = info_nce(z, labels, codes, self._t, variant, gamma=self.__gamma, path=L.CY_PATH_SIMT)
+        z, labels, codes = self._prepare(proj_feat1, proj_feat2, target, mask, sort=True)
+        loss, out4 = info_nce(z, labels, codes, self._t, self._kernel_variant(), gamma=self.__gamma, path=self._path)
         # contrastive.py:179-181 — a python float (host sync, as in the reference)
         self.downgrade_ratio = (out4[1] / out4[2]).item()
         if self._correct_grad:

@@ -60,8 +60,8 @@ def _joint_forward(x, y, padding, joint=None):
     B, K, H, W = x.shape
     T = 2 * padding + 1
     with L.guard(x):
-        if joint is None:
-            joint = torch.empty(K, K, T, T, dtype=torch.float32, device=x.device)
+        if joint is None:      # double: see include/contrastyou_b200.h (the epilogue's min-shift amplifies a float32 rounding of J)
+            joint = torch.empty(K, K, T, T, dtype=torch.float64, device=x.device)
         st = L.stream_ptr(x.device)
         ws_bytes = lib.cy_iic_workspace_bytes(B, K, H, W, padding)
         ws = _workspace(ws_bytes, x.device, st)
@@ -88,7 +88,7 @@ class _RawJoint(torch.autograd.Function):
     def forward(ctx, x, y, padding):
         ctx.save_for_backward(x, y)
         ctx.padding = padding
-        return _joint_forward(x, y, padding)
+        return _joint_forward(x, y, padding).to(torch.float32)      # what F.conv2d hands back in the reference
 
     @staticmethod
     def backward(ctx, gJ):
@@ -148,10 +148,10 @@ class _IIDSegFunction(torch.autograd.Function):
         B, K, H, W = x.shape
         T = 2 * padding + 1
         nj = K * K * T * T
-        buf = torch.empty(1 + K * K + 2 * nj, dtype=torch.float32, device=x.device)      # one allocation for the small outputs
+        buf = torch.empty(1 + K * K + nj, dtype=torch.float32, device=x.device)      # one allocation for the small outputs
         loss, p00 = buf[:1], buf[1:1 + K * K].view(K, K)
-        djoint, joint = buf[1 + K * K:1 + K * K + nj].view(K, K, T, T), buf[1 + K * K + nj:].view(K, K, T, T)
-        _joint_forward(x, y, padding, joint)
+        djoint = buf[1 + K * K:].view(K, K, T, T)
+        joint = _joint_forward(x, y, padding)                                        # [K, K, T, T] float64
         n_pixels = float(B * H * W)
         if reduce_joint is not None:
             n_pixels = reduce_joint(joint, n_pixels)
@@ -208,7 +208,7 @@ class _IIDSegMultiFunction(torch.autograd.Function):
         for s in range(S):
             x, y = maps[2 * s], maps[2 * s + 1]
             o = base + s * per * 4
-            loss_p, p00_p, dj_p, j_p = o, o + 4, o + 4 * (1 + K * K), o + 4 * (1 + K * K + nj)
+            loss_p, p00_p, dj_p, j_p = o, o + 4, o + 4 * (1 + K * K), joints.data_ptr() + 8 * s * nj
             L.check(lib.cy_iic_joint(x.data_ptr(), y.data_ptr(), dt, B, K, H, W, padding, j_p, ws.data_ptr(), ws_bytes, st),
                     "cy_iic_joint")
             L.check(lib.cy_iic_epilogue(j_p, K, padding, int(bool(symmetric)), float(lamda), float(eps), float(B * H * W),

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CY_ABI_VERSION 1
+#define CY_ABI_VERSION 2
 
 /* element types of embeddings / probability maps */
 #define CY_F32 0
@@ -39,8 +39,9 @@ extern "C" {
 
 /* kernel family selection (cy_infonce_*: `path`) */
 #define CY_PATH_AUTO 0
-#define CY_PATH_SIMT 1    /* fp32 CUDA-core tiles: every variant, every mask source, d <= 256          */
-#define CY_PATH_TCGEN05 2 /* TMA -> smem -> tcgen05.mma -> TMEM; bf16 operands; label masks; d == 256  */
+#define CY_PATH_SIMT 1    /* fp32 CUDA-core tiles: every variant, every mask source, any dtype, d <= 256               */
+#define CY_PATH_TCGEN05 2 /* TMA -> smem -> tcgen05.mma -> TMEM: every variant, label masks, bf16 / fp16, d in {128,256}, */
+                          /* N >= 256 (ragged N allowed), row range starting on a multiple of 128 and ending on one or at N */
 
 /* error codes */
 #define CY_OK 0
@@ -70,48 +71,61 @@ unsigned long long cy_launch_count(void);
  *   rows     the call covers rows [row_begin, row_end) of the N x N problem against all N columns (single GPU:
  *            0..N; row-sharded multi-GPU: the rank's block).
  *
- * Forward = cy_infonce_fwd (+ cy_infonce_fwd_pass2 for the variants that need the row sums first) and then
- * cy_infonce_finalize.  All row statistics live in `stats`, a caller-owned float array of CY_NSTAT * N entries laid
- * out [CY_NSTAT][N]; after finalize it holds what the backward needs for EVERY row it will meet as a column, so in
- * the sharded case the caller all-gathers the stats rows (CY_STAT_LOGDEN, CY_STAT_INVC, CY_STAT_COEF) first.
+ * Forward = cy_infonce_fwd (+ cy_infonce_fwd_pass2 for the variants that need the row sums first), then cy_infonce_loss.
+ * Two caller-owned arrays carry the row statistics:
+ *   stats  [CY_NSTAT][N] float — raw per-row sums of the sweeps (scratch of the forward; owned rows only);
+ *   xstat  [N][4] float (16-byte aligned) — per row, everything the BACKWARD needs when it meets the row as a row or as a
+ *          column, plus the row's loss term.  cy_infonce_fwd / _pass2 fill the owned rows; in the row-sharded multi-GPU form
+ *          ONE all-gather of the owned rows of xstat is the whole exchange (the loss is then reduced from the gathered array
+ *          by every rank, identically: no scalar collective).  Slots (CY_XS_*):
+ *            variant            [0]                 [1]     [2]                          [3]
+ *            SUPCON             log-denominator     1/c_i   1/den_i                      loss term of row i
+ *            SELFPACED_*        log-denominator     1/c_i   sw_i/(c_i den_i)             loss term of row i
+ *            SUPCON_EXCLUDE     loss term of row i  1/c_i   u_i/(c_i (ratio_i+1e-4))     A_i = neg_sum_i/(ratio_i+1e-4)
  * ---------------------------------------------------------------------------------------------------------------- */
 #define CY_NSTAT 8
 #define CY_STAT_LOGDEN 0 /* log(sum_j M_ij E_ij + 1e-16), E = exp(S - 1/t), M = P + Neg                      */
 #define CY_STAT_INVC 1   /* 1 / c_i,  c_i = sum_j P_ij                                                       */
 #define CY_STAT_COEF 2   /* coefficient of E_ij in dL/dS_ij for row i (1/den_i, sw_i/(c_i den_i), ...)       */
-#define CY_STAT_AUX 3    /* variant specific: exclude -> A_i = neg_sum_i/(ratio_i+1e-4)                      */
+#define CY_STAT_AUX 3    /* pass 1: sum_j Neg_ij E_ij; exclude -> A_i = neg_sum_i/(ratio_i+1e-4)             */
 #define CY_STAT_POSL 4   /* sum_j P_ij (S_ij - 1/t)   (pass 1)  /  sum_j P_ij w_ij logp_ij (pass 2)          */
 #define CY_STAT_NEGC 5   /* sum_j Neg_ij                                                                     */
-#define CY_STAT_POSE 6   /* sum_j P_ij E_ij                                                                  */
+#define CY_STAT_POSE 6   /* sum_j P_ij E_ij, then c_i                                                        */
 #define CY_STAT_SW 7     /* pass 2: sum_j P_ij w_ij (self-paced)  /  sum_j u_ij (exclude)                    */
 
-/* bytes of scratch the forward / backward need for this problem (split-column partial sums etc.) */
+/* bytes of scratch the forward / loss / backward need for this problem (split-column partial sums, fp32 gradient slabs
+ * of a column-split backward, block partials of the loss reduction): one buffer of this size serves every call */
 size_t cy_infonce_workspace_bytes(int64_t N, int64_t d, int dtype, int variant, int path);
 
+/* pass 1: raw row sums of rows [row_begin, row_end) against all N columns, then their row statistics (xstat complete for
+ * CY_SUPCON) */
 int cy_infonce_fwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
                    const uint8_t* codes, int64_t row_begin, int64_t row_end, float inv_t, int variant, int path,
-                   float* stats, void* workspace, size_t workspace_bytes, void* stream);
+                   float* stats, float* xstat, void* workspace, size_t workspace_bytes, void* stream);
 
-/* second forward sweep for CY_SUPCON_EXCLUDE / CY_SELFPACED_*: needs stats of the owned rows from pass 1 (finalized
- * with pass = 1).  gamma = self-paced age parameter (contrastive.py:206-212). */
+/* second forward sweep for CY_SUPCON_EXCLUDE / CY_SELFPACED_*: positive-pair sums that depend on the pass-1 statistics of
+ * the owned rows; completes their xstat rows.  gamma = self-paced age parameter (contrastive.py:206-212).  On the tensor
+ * path a row block visits only the column tiles whose label range intersects its own: O(N) work when rows are sorted by
+ * label. */
 int cy_infonce_fwd_pass2(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
                          const uint8_t* codes, int64_t row_begin, int64_t row_end, float inv_t, int variant,
-                         float gamma, int path, float* stats, void* workspace, size_t workspace_bytes, void* stream);
+                         float gamma, int path, float* stats, float* xstat, void* workspace, size_t workspace_bytes,
+                         void* stream);
 
-/* Row-level epilogue.  pass = 1 after cy_infonce_fwd, pass = 2 after cy_infonce_fwd_pass2.  When this is the last
- * pass of the variant it writes out[0] = sum over owned rows of the per-row loss term / N  (the caller all-reduces
- * it in the sharded case), out[1] = sum_ij P_ij w_ij, out[2] = sum_ij P_ij (self-paced downgrade ratio =
- * out[1]/out[2], contrastive.py:179-181), out[3] = number of non-finite row terms (NaN check, :98-99). */
-int cy_infonce_finalize(int64_t N, int64_t row_begin, int64_t row_end, float inv_t, int variant, int pass,
-                        float* stats, float* out4, void* stream);
+/* Loss reduction over ALL N rows of xstat (the caller has all-gathered them in the sharded case), fixed summation order:
+ * out[0] = loss = sum_i term_i / N, out[1] = sum_ij P_ij w_ij, out[2] = sum_ij P_ij (self-paced downgrade ratio =
+ * out[1]/out[2], contrastive.py:179-181; 0 for the other variants), out[3] = number of non-finite row terms (NaN check,
+ * :98-99). */
+int cy_infonce_loss(int64_t N, int variant, const float* xstat, float* out4, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 /* Backward: dz[row_begin:row_end, :] = gscale[0] * (1/t) * sum_j (G_ij + G_ji) z_j  with G = dLoss/dS built on the
- * fly from `stats` of rows i and j.  gscale is a DEVICE scalar: the upstream gradient
+ * fly from the xstat rows of i and j.  gscale is a DEVICE scalar: the upstream gradient
  * of the loss (carries hook weight and GradScaler scale; for correct_grad also 1/downgrade_ratio).  dz has the dtype
- * of z and row stride lddz; only the owned rows are written. */
+ * of z and row stride lddz; only the owned rows are written.  Bitwise reproducible (no atomics). */
 int cy_infonce_bwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
                    const uint8_t* codes, int64_t row_begin, int64_t row_end, float inv_t, int variant, float gamma,
-                   int path, const float* stats, const float* gscale, void* dz, int64_t lddz, void* workspace,
+                   int path, const float* xstat, const float* gscale, void* dz, int64_t lddz, void* workspace,
                    size_t workspace_bytes, void* stream);
 
 /* Materialise the [N, N] fp32 positive / negative masks with the SAME device predicate the loss kernels evaluate
@@ -123,8 +137,10 @@ int cy_infonce_masks(int64_t N, const int32_t* labels, const uint8_t* codes, flo
 
 /* Canonicalise a label vector to int32 so that integer equality == the reference's comparison.
  * src_kind: 0 = float32 values (python lists go through torch.Tensor(list), contrastive.py:40: -0.0 == +0.0, NaN
- * never equal), 1 = int32 (copied).  Writes dst[0:n] and dst[n:2n] (tiling over the two views). */
-int cy_labels_canonicalize(const void* src, int src_kind, int64_t n, int32_t* dst, void* stream);
+ * never equal), 1 = int32 (copied), 2 = int64 (torch's default integer dtype: narrowed; *overflow is incremented for
+ * every value outside the int32 range so that the caller can raise instead of comparing truncated labels).
+ * Writes dst[0:n] and dst[n:2n] (tiling over the two views).  overflow may be NULL for kinds 0 and 1. */
+int cy_labels_canonicalize(const void* src, int src_kind, int64_t n, int32_t* dst, int32_t* overflow, void* stream);
 
 /* Feeder of cy_infonce_fwd: stacks the two views into z [2n, d] (contiguous), z[i] = source row order[i] of
  * cat(f1, f2) (contrastive.py:15; `order` = a permutation of 0..2n-1 as int64, or NULL for the identity — the modules
@@ -149,13 +165,16 @@ int cy_infonce_unpack(const void* dz, int dtype, int64_t n, int64_t d, int64_t l
  * (contrastyou/losses/discreteMI.py:225-261), IIDSegmentationLoss.forward (:139-165) and their autograd backward.
  *
  *   x, y     [B, K, H, W] contiguous probability maps (x_out, x_tf_out)
- *   joint    raw joint [K, K, T, T] fp32, T = 2*pad+1:  J[k1,k2,dy,dx] = sum_{b,h,w} x[b,k1,h+dy-pad,w+dx-pad] *
- *            y[b,k2,h,w]  — exactly what the F.conv2d call at discreteMI.py:229-232 returns.  Multi-GPU: every rank
- *            accumulates its images, the caller all-reduces `joint`, then every rank runs the epilogue.
+ *   joint    raw joint [K, K, T, T] in DOUBLE, T = 2*pad+1:  J[k1,k2,dy,dx] = sum_{b,h,w} x[b,k1,h+dy-pad,w+dx-pad] *
+ *            y[b,k2,h,w]  — what the F.conv2d call at discreteMI.py:229-232 returns.  It stays in double between the two
+ *            calls because the epilogue's global min-shift (:233) turns a relative error e of J into ~e * J / (J - min J)
+ *            of the normalised joint — a factor ~sqrt(pixels), 300-1000x at config 3 — and a float32 rounding of J
+ *            (6e-8) alone then costs 1e-4 of gradient accuracy.  Multi-GPU: every rank accumulates its images, the
+ *            caller all-reduces `joint` (900 doubles), then every rank runs the epilogue.
  * ---------------------------------------------------------------------------------------------------------------- */
 size_t cy_iic_workspace_bytes(int B, int K, int H, int W, int pad);
 
-int cy_iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, float* joint,
+int cy_iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, double* joint,
                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* Epilogue on the (global) raw joint: min-shift + 1e-8, per-displacement and global normalisation, optional
@@ -165,7 +184,7 @@ int cy_iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, i
  * shared memory unless K*K*T*T is large, in which case cy_iic_epilogue_workspace_bytes() is non-zero and the caller
  * passes that much device scratch. */
 size_t cy_iic_epilogue_workspace_bytes(int K, int pad);
-int cy_iic_epilogue(const float* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels,
+int cy_iic_epilogue(const double* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels,
                     float* loss, float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes,
                     void* stream);
 

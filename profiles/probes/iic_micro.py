@@ -27,7 +27,7 @@ def main():
     x = (2 * torch.randn(a.B, a.K, a.H, a.W, generator=g)).softmax(1).to(dev)
     y = (2 * torch.randn(a.B, a.K, a.H, a.W, generator=g)).softmax(1).to(dev)
     T = 2 * a.pad + 1
-    joint = torch.empty(a.K, a.K, T, T, device=dev)
+    joint = torch.empty(a.K, a.K, T, T, device=dev, dtype=torch.float64)
     wsb = lib.cy_iic_workspace_bytes(a.B, a.K, a.H, a.W, a.pad)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     dj = torch.randn(a.K, a.K, T, T, generator=g).to(dev)

@@ -1,8 +1,8 @@
 """World-size-2 `gloo` tests (CPU) of the multi-GPU plumbing in contrast_you_b200/distributed.py.
 
 The CUDA kernels cannot run here, so each rank evaluates ITS shard with the CPU oracle (test infrastructure) and the
-product's exchange code (gather_rank_major / rank_major_labels / make_stats_exchange / make_joint_reduce) has to turn
-the per-rank pieces into exactly the single-process result."""
+product's exchange code (gather_rank_major / local_view_major / gather_rows_ / make_joint_reduce) has to turn the
+per-rank pieces into exactly the single-process result."""
 import os
 import socket
 import sys
@@ -47,14 +47,21 @@ def _worker(rank, port, results):
         lab = torch.randint(0, 4, (n,), generator=g)
         sl = slice(rank * n_loc, (rank + 1) * n_loc)
         local = torch.cat([f1[sl], f2[sl]]).requires_grad_()
-        z_all = cyd.gather_rank_major(local)                                   # [G * 2 n_loc, d], rank-major
-        raw_all = torch.empty(n, dtype=torch.float32)
-        dist.all_gather_into_tensor(raw_all, lab[sl].to(torch.float32))
-        labels = cyd.rank_major_labels(raw_all, WORLD, _canon_cpu)
+        # what ShardedSupConLoss does: canonical labels and sort order are LOCAL, then three in-place all-gathers
+        lab_loc = cyd.local_view_major(lab[sl].to(torch.float32), _canon_cpu)  # [2 n_loc] canonical, view-major
+        order = torch.argsort(lab_loc)
+        z_all = cyd.gather_rank_major(local[order])                            # [G * 2 n_loc, d], rank-major, blocks sorted
         rb, re = cyd.row_range(n_loc)
         assert (rb, re) == (rank * 2 * n_loc, (rank + 1) * 2 * n_loc)
         N = 2 * n
-        # this rank's strip with the oracle's closed form: statistics of the owned rows only
+        labels = torch.zeros(N, dtype=torch.int32)
+        labels[rb:re] = lab_loc[order]
+        cyd.gather_rows_(labels)
+        # every rank's block holds ITS samples' labels, sorted: compare with a single-process construction
+        for r in range(WORLD):
+            want = _canon_cpu(lab[r * n_loc:(r + 1) * n_loc].to(torch.float32), n_loc).sort().values
+            assert torch.equal(labels[r * 2 * n_loc:(r + 1) * 2 * n_loc], want)
+        # this rank's strip with the oracle's closed form: xstat rows of the owned rows only
         Z = z_all.detach().numpy()
         lb = labels.numpy()
         S = Z[rb:re] @ Z.T / t
@@ -63,28 +70,21 @@ def _worker(rank, port, results):
         P = (lb[rb:re, None] == lb[None, :]).astype(np.float64); P[rows - rb, rows] = 0
         E = np.exp(S - m); E[rows - rb, rows] = 0
         D, c = E.sum(1), P.sum(1)
-        stats = torch.zeros(L.CY_NSTAT, N, dtype=torch.float64)
-        stats[L.CY_STAT_LOGDEN, rb:re] = torch.from_numpy(np.log(D + 1e-16))
-        stats[L.CY_STAT_INVC, rb:re] = torch.from_numpy(1 / c)
-        stats[L.CY_STAT_COEF, rb:re] = torch.from_numpy(1 / (D + 1e-16))
-        out4 = torch.zeros(4, dtype=torch.float64)
-        out4[0] = float(-((P * (S - m)).sum(1) / c - np.log(D + 1e-16)).sum() / N)
-        stats_b, out4_b = stats.clone(), out4.clone()
-        cyd.make_stats_exchange(n_loc)(stats, out4)                            # the product's exchange step (5 collectives)
-        out4_b = cyd.exchange_strip_stats(stats_b, out4_b, rb, re)             # ... and its one-collective form
-        assert torch.equal(stats_b, stats) and torch.allclose(out4_b, out4, rtol=1e-15, atol=0)
-        # local label sort used by ShardedSupConLoss: sorting every rank's block leaves the loss unchanged and the owned
-        # block's permutation maps sorted rows back to the original ones
-        sorted_blocks, perm = labels.view(WORLD, 2 * n_loc).sort(dim=1)
-        assert torch.equal(labels.view(WORLD, 2 * n_loc)[rank][perm[rank]], sorted_blocks[rank])
-        coef, invc = stats[L.CY_STAT_COEF].numpy(), stats[L.CY_STAT_INVC].numpy()
+        xstat = torch.zeros(N, 4, dtype=torch.float64)                          # CY_XS_*: logden, 1/c, coef, loss term
+        xstat[rb:re, 0] = torch.from_numpy(np.log(D + 1e-16))
+        xstat[rb:re, 1] = torch.from_numpy(1 / c)
+        xstat[rb:re, 2] = torch.from_numpy(1 / (D + 1e-16))
+        xstat[rb:re, 3] = torch.from_numpy(-((P * (S - m)).sum(1) / c - np.log(D + 1e-16)))
+        cyd.gather_rows_(xstat)                                                # the product's ONE statistics exchange
+        loss = xstat[:, 3].sum().item() / N                                    # what cy_infonce_loss reduces on every rank
+        coef, invc = xstat[:, 2].numpy(), xstat[:, 1].numpy()
         W = E * (coef[rb:re, None] + coef[None, :]) - P * (invc[rb:re, None] + invc[None, :])
         dz_all = torch.zeros(N, d, dtype=torch.float64)
         dz_all[rb:re] = torch.from_numpy(W @ Z / (t * N))
-        z_all.backward(dz_all)                                                 # through _GatherRows.backward
+        z_all.backward(dz_all)                                                 # through _GatherRows.backward + the local un-sort
         # single-process truth: the literal oracle on the concatenated batch
         ref = OC.supcon(f1.numpy(), f2.numpy(), target=lab.tolist(), t=t)
-        assert abs(out4[0].item() - ref["loss"]) < 1e-12 * abs(ref["loss"]), (out4[0].item(), ref["loss"])
+        assert abs(loss - ref["loss"]) < 1e-12 * abs(ref["loss"]), (loss, ref["loss"])
         got = local.grad.numpy()
         want = np.concatenate([ref["grad_f1"][sl], ref["grad_f2"][sl]])
         assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()

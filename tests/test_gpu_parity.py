@@ -429,7 +429,8 @@ def test_tcgen05_sharded_rows_not_128_aligned_fall_back():
 
 
 def test_tcgen05_row_stats_match_simt():
-    """the per-row statistics (log-denominator, 1/c, coefficient) of both kernel families agree row by row"""
+    """the per-row statistics both kernel families hand to the backward (xstat: log-denominator, 1/c, coefficient, loss
+    term) agree row by row, straight through the C ABI"""
     from contrast_you_b200.losses.contrastive import _canonical_labels
     z, lab, n = _tc_case(2048, 32, 5)
     N = 2 * n
@@ -438,20 +439,22 @@ def test_tcgen05_row_stats_match_simt():
     res = {}
     for name, path in (("tc", L.CY_PATH_TCGEN05), ("simt", L.CY_PATH_SIMT)):
         stats = torch.zeros(L.CY_NSTAT, N, device=DEV)
+        xstat = torch.zeros(N, 4, device=DEV)
         out4 = torch.zeros(4, device=DEV)
         wsb = lib.cy_infonce_workspace_bytes(N, 256, L.CY_BF16, 0, path)
         ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
         L.check(lib.cy_infonce_fwd(z.data_ptr(), L.CY_BF16, N, 256, 256, labels.data_ptr(), None, 0, N, 1 / 0.07, 0, path,
-                                   stats.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr()), "fwd")
-        L.check(lib.cy_infonce_finalize(N, 0, N, 1 / 0.07, 0, 1, stats.data_ptr(), out4.data_ptr(), L.stream_ptr()), "fin")
-        res[name] = (stats.cpu().numpy(), out4.cpu().numpy())
-    for row in (L.CY_STAT_LOGDEN, L.CY_STAT_INVC, L.CY_STAT_COEF):
-        np.testing.assert_allclose(res["tc"][0][row], res["simt"][0][row], rtol=2e-4, atol=1e-6)
+                                   stats.data_ptr(), xstat.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr()), "fwd")
+        L.check(lib.cy_infonce_loss(N, 0, xstat.data_ptr(), out4.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr()), "loss")
+        res[name] = (xstat.cpu().numpy(), out4.cpu().numpy())
+    np.testing.assert_allclose(res["tc"][0], res["simt"][0], rtol=2e-4, atol=1e-6)
     assert res["tc"][1][3] == 0 and res["simt"][1][3] == 0
+    assert res["tc"][1][0] == pytest.approx(res["simt"][1][0], rel=1e-5)
 
 
 def test_tcgen05_row_sharded_equals_whole():
-    """row ranges (the multi-GPU sharding unit): two half-range launches reproduce the full-range loss and gradient"""
+    """row ranges (the multi-GPU sharding unit): two half-range launches, each completed by an emulated all-gather of the
+    other half's xstat rows, reproduce the full-range loss and gradient"""
     from contrast_you_b200.losses.contrastive import info_nce, _canonical_labels
     z, lab, n = _tc_case(1024, 8, 9)
     N = 2 * n
@@ -459,31 +462,112 @@ def test_tcgen05_row_sharded_equals_whole():
     zf = z.clone().requires_grad_()
     loss, _ = info_nce(zf, labels, None, 0.07, path=L.CY_PATH_TCGEN05)
     loss.backward()
-    parts, grads = [], torch.zeros_like(z)
+    grads = torch.zeros_like(z)
     for rb, re in ((0, N // 2), (N // 2, N)):
         zs = z.clone().requires_grad_()
-        stats_all = {}
 
-        def exchange(stats, out4, rb=rb, re=re):
-            # emulate the all-gather of row statistics with a second (full-range) evaluation
-            full = torch.zeros_like(stats)
-            o4 = torch.zeros(4, device=DEV)
+        def exchange(xstat, rb=rb, re=re):
+            # emulate the all-gather of the other rank's rows with a second (full-range) evaluation
             lib = L.lib()
+            full_s = torch.zeros(L.CY_NSTAT, N, device=DEV)
+            full_x = torch.zeros(N, 4, device=DEV)
             wsb = lib.cy_infonce_workspace_bytes(N, 256, L.CY_BF16, 0, L.CY_PATH_TCGEN05)
             ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
             L.check(lib.cy_infonce_fwd(z.data_ptr(), L.CY_BF16, N, 256, 256, labels.data_ptr(), None, 0, N, 1 / 0.07, 0,
-                                       L.CY_PATH_TCGEN05, full.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr()), "fwd")
-            L.check(lib.cy_infonce_finalize(N, 0, N, 1 / 0.07, 0, 1, full.data_ptr(), o4.data_ptr(), L.stream_ptr()), "fin")
-            own = stats[:, rb:re].clone()
-            stats.copy_(full)
-            assert torch.allclose(stats[:3, rb:re], own[:3], rtol=1e-5)
-        l, _ = info_nce(zs, labels, None, 0.07, path=L.CY_PATH_TCGEN05, rows=(rb, re), gather_stats=exchange)
+                                       L.CY_PATH_TCGEN05, full_s.data_ptr(), full_x.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr()),
+                    "fwd")
+            own = xstat[rb:re].clone()
+            assert torch.allclose(full_x[rb:re], own, rtol=1e-5)               # the strip launch == the same rows of the full one
+            xstat.copy_(full_x)
+            xstat[rb:re] = own
+        l, _ = info_nce(zs, labels, None, 0.07, path=L.CY_PATH_TCGEN05, rows=(rb, re), gather_xstat=exchange)
         l.backward()
-        parts.append(l.item())
+        assert l.item() == pytest.approx(loss.item(), rel=1e-6)                 # every "rank" reduces the global loss
         grads[rb:re] = zs.grad[rb:re]
         assert float(zs.grad[:rb].abs().sum() + zs.grad[re:].abs().sum()) == 0.0
-    assert sum(parts) == pytest.approx(loss.item(), rel=1e-5)
     assert _relerr(grads.float().cpu().numpy(), zf.grad.float().cpu().numpy()) <= 1e-6
+
+
+@pytest.mark.parametrize("kind", ["exclude", "hard", "soft", "soft_cg"])
+@pytest.mark.parametrize("N,classes,d", [(512, 8, 256), (4096, 64, 256), (1000, 16, 256), (2048, 0, 128)])
+def test_tcgen05_family_variants(kind, N, classes, d):
+    """exclude_other_pos and the self-paced variants on the tensor path (second forward sweep over the positive tiles only,
+    variant-specific positive branch in the backward): vs the CUDA-core path on the same bf16 inputs (itself pinned to the
+    reference fixtures) and, where the literal oracle fits, vs the float64 numpy restatement.  N = 1000 has a ragged last
+    tile; classes = 0 is the SimCLR / self-label case (one positive per row); d = 128 is the second supported width."""
+    torch.manual_seed(N + len(kind))
+    n = N // 2
+    z = torch.nn.functional.normalize(torch.randn(N, d, device=DEV), dim=1).to(torch.bfloat16)
+    lab = torch.randint(0, classes, (n,)) if classes else torch.arange(n)
+
+    def make(path):
+        if kind == "exclude":
+            return SupConLoss1(exclude_other_pos=True, path=path)
+        crit = SelfPacedSupConLoss(weight_update="hard" if kind == "hard" else "soft", correct_grad=kind == "soft_cg", path=path)
+        crit.set_gamma(6.0 if kind == "hard" else 8.0)      # inside the range of -log p: some positives are down-weighted
+        return crit
+    out = {}
+    for path in ("tcgen05", "simt"):
+        f1, f2 = z[:n].clone().requires_grad_(), z[n:].clone().requires_grad_()
+        crit = make(path)
+        loss = crit(f1, f2, target=lab.tolist())
+        loss.backward()
+        out[path] = (loss.item(), torch.cat([f1.grad, f2.grad]).float().cpu().numpy(), getattr(crit, "downgrade_ratio", None))
+    assert out["tcgen05"][0] == pytest.approx(out["simt"][0], rel=1e-4)
+    assert _relerr(out["tcgen05"][1], out["simt"][1]) <= BF16_TOL
+    if kind != "exclude":
+        assert 0.0 < out["tcgen05"][2] < 1.0 or kind == "soft_cg"
+        assert out["tcgen05"][2] == pytest.approx(out["simt"][2], rel=1e-4)
+    if N <= 1000:
+        zn = z.float().cpu().double().numpy()
+        if kind == "exclude":
+            o = OC.supcon(zn[:n], zn[n:], target=lab.tolist(), exclude_other_pos=True)
+        else:
+            o = OC.selfpaced_supcon(zn[:n], zn[n:], target=lab.tolist(), weight_update="hard" if kind == "hard" else "soft",
+                                    gamma=6.0 if kind == "hard" else 8.0, correct_grad=kind == "soft_cg")
+        assert out["tcgen05"][0] == pytest.approx(o["loss"], rel=1e-4)
+        assert _relerr(out["tcgen05"][1], np.concatenate([o["grad_f1"], o["grad_f2"]])) <= BF16_TOL
+
+
+@pytest.mark.parametrize("N,d", [(1000, 256), (3334, 256), (2048, 128), (1406, 128)])
+def test_tcgen05_ragged_n_and_d128(N, d):
+    """SupConLoss1 default variant: N not a multiple of 128 (masked last tile, TMA zero fill) and d = 128, vs the C oracle"""
+    torch.manual_seed(N + d)
+    n = N // 2
+    z = torch.nn.functional.normalize(torch.randn(N, d, device=DEV), dim=1).to(torch.bfloat16)
+    lab = torch.randint(0, 24, (n,))
+    f1, f2 = z[:n].clone().requires_grad_(), z[n:].clone().requires_grad_()
+    loss = SupConLoss1(path="tcgen05")(f1, f2, target=lab.to(DEV))           # int64 device labels: narrowed on the device
+    loss.backward()
+    o = c_oracle.supcon_fwd_bwd(z.float().cpu().numpy(), np.tile(lab.numpy().astype(np.int32), 2), t=0.07, prec=1)
+    assert loss.item() == pytest.approx(o["loss"], rel=1e-4)
+    assert _relerr(torch.cat([f1.grad, f2.grad]).float().cpu().numpy(), o["grad"]) <= BF16_TOL
+
+
+def test_tcgen05_gradients_are_bitwise_reproducible():
+    """the column-split backward sums fp32 slabs in a fixed order (no atomics): two runs give identical bits"""
+    from contrast_you_b200.losses.contrastive import info_nce, _canonical_labels
+    z, lab, n = _tc_case(4096, 64, 21)
+    labels = _canonical_labels(lab.tolist(), n, z.device)
+    grads = []
+    for _ in range(2):
+        zs = z.clone().requires_grad_()
+        # a 256-row strip of a 4096-column problem: the backward splits the columns over many CTAs
+        l, _ = info_nce(zs, labels, None, 0.07, path=L.CY_PATH_TCGEN05, rows=(256, 512))
+        l.backward()
+        grads.append(zs.grad[256:512].clone())
+    assert torch.equal(grads[0], grads[1])
+    assert float(grads[0].float().abs().sum()) > 0
+
+
+def test_int64_labels_out_of_range_raise():
+    f = torch.nn.functional.normalize(torch.randn(8, 16, device=DEV), dim=1)
+    lab = torch.tensor([0, 1, 2, 3, 0, 1, 2, 2 ** 40], device=DEV)
+    with pytest.raises(ValueError, match="int32"):
+        SupConLoss1()(f, f, target=lab)
+    ok = torch.tensor([5, 5, 2 ** 31 - 1, 7, -2 ** 31, 1, 2, 7], device=DEV)
+    ref = OC.supcon(f.cpu().double().numpy(), f.cpu().double().numpy(), target=[0, 0, 1, 2, 3, 4, 5, 2])
+    assert SupConLoss1()(f, f, target=ok).item() == pytest.approx(ref["loss"], rel=FP32_TOL)
 
 
 # ------------------------------------------------------------------------------------------------ sibling losses

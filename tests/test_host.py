@@ -30,13 +30,13 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(handle, n), f"{n} declared in contrastyou_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
-    assert handle.cy_abi_version() == 1
+    assert handle.cy_abi_version() == _lib.CY_ABI_VERSION
 
 
 def test_argument_validation_needs_no_gpu():
     handle = _lib.load()
     # null pointers / bad sizes are rejected before anything touches the device
-    assert handle.cy_infonce_fwd(None, 0, 4, 8, 8, None, None, 0, 4, 1.0, 0, 0, None, None, 0, None) == -1
+    assert handle.cy_infonce_fwd(None, 0, 4, 8, 8, None, None, 0, 4, 1.0, 0, 0, None, None, None, 0, None) == -1
     assert b"null" in handle.cy_last_error()
     assert handle.cy_iic_joint(None, None, 0, 1, 2, 3, 3, 1, None, None, 0, None) == -1
     assert handle.cy_iic_workspace_bytes(0, 1, 1, 1, 0) == 0
