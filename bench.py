@@ -31,6 +31,18 @@ if ROOT not in sys.path:
 WORKLOADS = {
     "cfg4": dict(N=65536, d=256, classes=4096, name="cfg4 global InfoNCE N=65536 d=256 bf16 meta-labels(4096)"),
     "cfg2": dict(N=32768, d=256, classes=0, name="cfg2 dense InfoNCE N=32768 (16 img x 1024 px x 2 views) d=256 bf16 self-labels"),
+    # the rest of the family on cfg4's shape: SelfPacedSupConLoss / exclude_other_pos on the tensor path
+    "selfpaced": dict(N=65536, d=256, classes=4096, variant=3, gamma=12.0,
+                      name="cfg4 shape, SelfPacedSupConLoss(weight_update='soft', gamma=12) N=65536 d=256 bf16 meta-labels(4096)"),
+    "selfpaced_hard": dict(N=65536, d=256, classes=4096, variant=2, gamma=11.0,
+                           name="cfg4 shape, SelfPacedSupConLoss(weight_update='hard', gamma=11) N=65536 d=256 bf16 meta-labels(4096)"),
+    "exclude": dict(N=65536, d=256, classes=4096, variant=1,
+                    name="cfg4 shape, SupConLoss1(exclude_other_pos=True) N=65536 d=256 bf16 meta-labels(4096)"),
+    "d128": dict(N=65536, d=128, classes=4096, name="cfg4 shape with d=128: N=65536 bf16 meta-labels(4096)"),
+    # fp32 embeddings under torch.autocast (the reference's default AMP config hands fp32 to the criterion and runs the GEMM in
+    # half precision): the module follows autocast and takes the tensor kernels
+    "amp": dict(N=65536, d=256, classes=4096, dtype="f32", autocast=True,
+                name="cfg4 shape, fp32 inputs under torch.autocast(bf16): N=65536 d=256 meta-labels(4096)"),
 }
 IIC_CFG = dict(B=32, K=10, H=224, W=224, pad=1)
 CPU_SAMPLE_N = 8192          # the reference materialises ~13 N x N fp32 tensors: 8192 is what fits / finishes in seconds
@@ -261,7 +273,7 @@ def main():
     import torch
     import torch.distributed as dist
     from contrast_you_b200 import _lib as L
-    from contrast_you_b200.losses import SupConLoss1, IIDSegmentationLoss
+    from contrast_you_b200.losses import SupConLoss1, SelfPacedSupConLoss, IIDSegmentationLoss
     from contrast_you_b200.losses.contrastive import _canonical_labels, sort_rows_by_label
     from contrast_you_b200 import distributed as cyd
 
@@ -285,7 +297,9 @@ def main():
 
     # ---- synthetic inputs (seeded; identical on every rank, each rank keeps its slice) in PINNED HOST memory
     gen = torch.Generator().manual_seed(0)
-    z_host = torch.nn.functional.normalize(torch.randn(N, d, generator=gen), dim=1).to(torch.bfloat16)
+    in_dtype = torch.float32 if wl.get("dtype") == "f32" else torch.bfloat16
+    z_host = torch.nn.functional.normalize(torch.randn(N, d, generator=gen), dim=1).to(in_dtype)
+    variant, gamma = int(wl.get("variant", 0)), float(wl.get("gamma", 1e6))
     lab_host = (torch.randint(0, wl["classes"], (n,), generator=gen) if wl["classes"] else torch.arange(n)).to(torch.int32)
     sl = slice(rank * n_loc, (rank + 1) * n_loc)
     f1_host = z_host[:n][sl].contiguous().pin_memory()
@@ -294,12 +308,23 @@ def main():
     f1_dev, f2_dev, lab_dev = f1_host.to(dev), f2_host.to(dev), lab_loc_host.to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    crit = SupConLoss1(path=args.path) if world == 1 else cyd.ShardedSupConLoss(group=None, path=args.path)
+    def make_criterion(path, sharded):
+        if variant in (2, 3):
+            assert not sharded, "the self-paced workloads are single-GPU bench lines"
+            c = SelfPacedSupConLoss(weight_update="hard" if variant == 2 else "soft", path=path)
+            c.set_gamma(gamma)
+            return c
+        if sharded:
+            return cyd.ShardedSupConLoss(exclude_other_pos=variant == 1, group=None, path=path)
+        return SupConLoss1(exclude_other_pos=variant == 1, path=path)
+    crit = make_criterion(args.path, world > 1)
+    use_autocast = bool(wl.get("autocast"))
 
-    def step(a, b, lab):
+    def step(a, b, lab, criterion=None):
         a = a.detach().requires_grad_()
         b = b.detach().requires_grad_()
-        loss = crit(a, b, target=lab)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=use_autocast):
+            loss = (criterion or crit)(a, b, target=lab)
         loss.backward()
         return loss, a.grad, b.grad
 
@@ -346,7 +371,14 @@ def main():
     def parity_block():
         loss, ga, gb = step(f1_dev, f2_dev, lab_dev)
         got_loss = float(loss.item())
-        if world == 1:
+        if world == 1 and (variant != 0 or use_autocast or d != 256):
+            # the C oracle restates SupConLoss1's default variant; the other members of the family are checked at full size
+            # against this library's fp32 CUDA-core path, which the -m gpu suite pins to the reference's fixtures
+            ref, ra, rb_ = step(f1_dev, f2_dev, lab_dev, make_criterion("simt", False))
+            ref_loss, ref_grad = float(ref.item()), torch.cat([ra, rb_]).float().cpu()
+            got = torch.cat([ga, gb]).float().cpu()
+            against = f"fp32 CUDA-core path of this library (pinned to the reference fixtures by the -m gpu suite) at the full N={N}"
+        elif world == 1:
             if args.no_cpu:
                 return None
             from oracle import c_oracle
@@ -390,7 +422,7 @@ def main():
         loss, _, _ = step(a, b, lab)
         return loss.item()                                   # D2H read of the step's result
     e2e_ms = timed_loop(e2e_step, 3, K_) / K_
-    h2d = f1_host.numel() * 2 * 2 + lab_loc_host.numel() * 4
+    h2d = f1_host.numel() * f1_host.element_size() * 2 + lab_loc_host.numel() * 4
     e2e = {"value": N * N / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
            "ms_per_step": e2e_ms}
 
@@ -439,27 +471,43 @@ def main():
     stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev)
     xstat = torch.zeros(N, 4, dtype=torch.float32, device=dev)
     out4 = torch.zeros(4, device=dev)
-    ws_b = lib.cy_infonce_workspace_bytes(N, d, L.CY_BF16, 0, path)
+    ws_b = lib.cy_infonce_workspace_bytes(N, d, L.CY_BF16, variant, path)
     ws = torch.empty(ws_b, dtype=torch.uint8, device=dev)
     one = torch.ones(1, device=dev)
     dz = torch.empty_like(z_all)
     st = L.stream_ptr()
 
+    kdt = L.CY_BF16        # the kernels see what the module hands them: bf16 (fp32 inputs under autocast are cast by the module)
+    if in_dtype != torch.bfloat16:
+        z_all = z_all.to(torch.bfloat16)
+        dz = torch.empty_like(z_all)
+
     def k_fwd():
-        L.check(lib.cy_infonce_fwd(z_all.data_ptr(), L.CY_BF16, N, d, d, labels.data_ptr(), None, rb, re, 1 / 0.07, 0, path,
+        L.check(lib.cy_infonce_fwd(z_all.data_ptr(), kdt, N, d, d, labels.data_ptr(), None, rb, re, 1 / 0.07, variant, path,
                                    stats.data_ptr(), xstat.data_ptr(), ws.data_ptr(), ws_b, st), "fwd")
 
+    def k_fwd2():
+        L.check(lib.cy_infonce_fwd_pass2(z_all.data_ptr(), kdt, N, d, d, labels.data_ptr(), None, rb, re, 1 / 0.07, variant, gamma,
+                                         path, stats.data_ptr(), xstat.data_ptr(), ws.data_ptr(), ws_b, st), "fwd2")
+
     def k_fin():
+        if variant != 0:
+            k_fwd2()
         if world > 1:
             cyd.gather_rows_(xstat)
-        L.check(lib.cy_infonce_loss(N, 0, xstat.data_ptr(), out4.data_ptr(), ws.data_ptr(), ws_b, st), "loss")
+        L.check(lib.cy_infonce_loss(N, variant, xstat.data_ptr(), out4.data_ptr(), ws.data_ptr(), ws_b, st), "loss")
 
     def k_bwd():
-        L.check(lib.cy_infonce_bwd(z_all.data_ptr(), L.CY_BF16, N, d, d, labels.data_ptr(), None, rb, re, 1 / 0.07, 0, 0.0, path,
+        L.check(lib.cy_infonce_bwd(z_all.data_ptr(), kdt, N, d, d, labels.data_ptr(), None, rb, re, 1 / 0.07, variant, gamma, path,
                                    xstat.data_ptr(), one.data_ptr(), dz.data_ptr(), d, ws.data_ptr(), ws_b, st), "bwd")
     k_fwd(); k_fin()
     kreps = max(3, min(K_, 10))
     fwd_ms = timed_loop(k_fwd, 2, kreps) / kreps
+    fwd2_ms = None
+    if variant != 0:        # second sweep of exclude / self-paced: only the column tiles that can hold positives
+        k_fwd()
+        fwd2_ms = timed_loop(k_fwd2, 2, kreps) / kreps
+        k_fwd(); k_fin()
     bwd_ms = timed_loop(k_bwd, 2, kreps) / kreps
     rows = re - rb
     fwd_tf = 2.0 * rows * N * d / (fwd_ms * 1e-3) / 1e12
@@ -473,12 +521,13 @@ def main():
                 if (world == 1 and N == 65536 and path != 1) else None,
                 "peak_source": peaks["source"] + " bf16 burst",
                 "fwd": {"kernel": "cy_infonce_fwd (2*rows*N*d FLOP)", "ms": fwd_ms, "achieved": fwd_tf, "frac": fwd_tf / peak_tf},
-                "bwd_ms": bwd_ms,
+                "bwd_ms": bwd_ms, "fwd_pass2_ms": fwd2_ms,
                 "fwd_bwd_frac": (6.0 * rows * N * d / ((fwd_ms + bwd_ms) * 1e-3) / 1e12) / peak_tf}
 
     line = {
         "metric": "InfoNCE fwd+bwd pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K_, "warmup": W_,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16" if not use_autocast else "bf16 (fp32 inputs under autocast)",
         "data": "synthetic",
         "config": {"workload": wl["name"], "N": N, "d": d, "temperature": 0.07, "path": args.path,
                    "parallelism": f"rows{world}" if world > 1 else "single",

@@ -265,6 +265,15 @@ class _ContrastBase(nn.Module):
         else:  # SimCLR: only the twin view is positive
             labels = torch.arange(batch_size, dtype=torch.int32, device=device).repeat(2)
         assert proj_feat1.shape == proj_feat2.shape, (proj_feat1.shape, proj_feat2.shape)
+        if (proj_feat1.dtype == torch.float32 and proj_feat2.dtype == torch.float32 and getattr(self, "_follow_autocast", True)
+                and torch.is_autocast_enabled("cuda")):
+            # Under torch.autocast the reference's similarity GEMM (torch.mm, contrastive.py:16) runs on half-precision
+            # copies of its fp32 inputs — the projector's F.normalize hands fp32 to the criterion under AMP, which is the
+            # reference's default (config/base.yaml:42).  Follow that: the half-precision copy takes the tensor kernels
+            # (products exact in fp32, fp32 accumulation and logits — the reference additionally rounds the logits to half),
+            # gradients come back in fp32 through the cast.  Outside autocast fp32 inputs keep full fp32 arithmetic.
+            half = torch.get_autocast_dtype("cuda")
+            proj_feat1, proj_feat2 = proj_feat1.to(half), proj_feat2.to(half)
         fused = (proj_feat1.dim() == 2 and proj_feat1.dtype == proj_feat2.dtype and proj_feat1.device == proj_feat2.device
                  and proj_feat1.dtype in (torch.float32, torch.bfloat16, torch.float16))
         do_sort = bool(sort and fused and codes is None and self._sorts_rows(proj_feat1))

@@ -194,10 +194,11 @@ class _IIDSegMultiFunction(torch.autograd.Function):
         B, K, H, W = x0.shape
         T = 2 * padding + 1
         nj = K * K * T * T
-        per = 1 + K * K + 2 * nj
+        per = 1 + K * K + nj
         if x0.device.index != torch.cuda.current_device():
             torch.cuda.set_device(x0.device)      # (rare) model on a non-current device: make it current for the launches
         buf = torch.empty(S, per, dtype=torch.float32, device=x0.device)
+        joints = torch.empty(S, nj, dtype=torch.float64, device=x0.device)      # raw joints stay in double (contrastyou_b200.h)
         st = L.stream_ptr(x0.device)
         ws_bytes = lib.cy_iic_workspace_bytes(B, K, H, W, padding)
         ws = _workspace(ws_bytes, x0.device, st)
