@@ -410,8 +410,11 @@ def main():
             t = torch.tensor([loss_rel, grad_rel], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             loss_rel, grad_rel = float(t[0]), float(t[1])
+        # hard self-paced weights are a step function of -log p: pairs within float rounding of gamma flip between the two
+        # evaluations, each flip moving one weight by 1/c_i — the gradient bar is looser there, the loss bar is not
+        gtol = 5e-2 if variant == 2 else 1e-2
         return {"loss": got_loss, "ref_loss": ref_loss, "loss_rel": loss_rel, "grad_rel": grad_rel, "against": against,
-                "tolerance": {"loss_rel": 1e-4, "grad_rel": 1e-2}, "ok": bool(loss_rel <= 1e-4 and grad_rel <= 1e-2)}
+                "tolerance": {"loss_rel": 1e-4, "grad_rel": gtol}, "ok": bool(loss_rel <= 1e-4 and grad_rel <= gtol)}
     parity = parity_block()
 
     # ---- end-to-end leg: host buffers -> module -> loss back on the host, every step
@@ -470,7 +473,7 @@ def main():
     path = {"auto": 0, "simt": 1, "tcgen05": 2}[args.path]
     stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev)
     xstat = torch.zeros(N, 4, dtype=torch.float32, device=dev)
-    out4 = torch.zeros(4, device=dev)
+    out4 = torch.zeros(8, device=dev)
     ws_b = lib.cy_infonce_workspace_bytes(N, d, L.CY_BF16, variant, path)
     ws = torch.empty(ws_b, dtype=torch.uint8, device=dev)
     one = torch.ones(1, device=dev)
@@ -495,7 +498,7 @@ def main():
             k_fwd2()
         if world > 1:
             cyd.gather_rows_(xstat)
-        L.check(lib.cy_infonce_loss(N, variant, xstat.data_ptr(), out4.data_ptr(), ws.data_ptr(), ws_b, st), "loss")
+        L.check(lib.cy_infonce_loss(N, variant, xstat.data_ptr(), out4.data_ptr(), None, None, ws.data_ptr(), ws_b, st), "loss")
 
     def k_bwd():
         L.check(lib.cy_infonce_bwd(z_all.data_ptr(), kdt, N, d, d, labels.data_ptr(), None, rb, re, 1 / 0.07, variant, gamma, path,

@@ -33,13 +33,13 @@ SIGNATURES = {
     "cy_infonce_fwd": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "cy_infonce_fwd_pass2": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _i32, _f32, _i32, _vp, _vp, _vp,
                                     _sz, _vp]),
-    "cy_infonce_loss": (_i32, [_i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "cy_infonce_loss": (_i32, [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cy_infonce_bwd": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _i32, _f32, _i32, _vp, _vp, _vp,
                               _i64, _vp, _sz, _vp]),
     "cy_infonce_masks": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "cy_labels_canonicalize": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp]),
     "cy_infonce_pack": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "cy_infonce_unpack": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cy_infonce_unpack": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cy_iic_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "cy_iic_joint": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "cy_iic_epilogue_workspace_bytes": (_sz, [_i32, _i32]),

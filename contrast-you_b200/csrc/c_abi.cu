@@ -53,7 +53,7 @@ int infonce_bwd_simt(const void*, int, int64_t, int64_t, int64_t, const int32_t*
 int infonce_masks(int64_t, const int32_t*, const uint8_t*, float*, float*, cudaStream_t);
 int labels_canonicalize(const void*, int, int64_t, int32_t*, int32_t*, cudaStream_t);
 int infonce_pack(const void*, const void*, int, int64_t, int64_t, int64_t, int64_t, const int64_t*, void*, int*, float*, cudaStream_t);
-int infonce_unpack(const void*, int, int64_t, int64_t, int64_t, const int64_t*, void*, void*, const void*, const float*, cudaStream_t);
+int infonce_unpack(const void*, int, int64_t, int64_t, int64_t, const int64_t*, void*, void*, const void*, const float*, const float*, cudaStream_t);
 // infonce_tc.cu
 bool infonce_tc_supported(int dtype, int64_t N, int64_t d, int64_t ldz, const uint8_t* codes, int variant);
 size_t infonce_tc_workspace_bytes(int64_t N, int64_t d);
@@ -63,7 +63,7 @@ int infonce_fwd_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, 
 int infonce_fwd2_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, int, float, float*, float*, void*,
                     size_t, cudaStream_t);
 int infonce_rowstats(int64_t, int64_t, int64_t, float, int, int, float*, float*, cudaStream_t);
-int infonce_loss(int64_t, int, const float*, float*, void*, size_t, cudaStream_t);
+int infonce_loss(int64_t, int, const float*, float*, const int32_t*, const int32_t*, void*, size_t, cudaStream_t);
 int infonce_bwd_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, int, float, const float*,
                    const float*, void*, int64_t, void*, size_t, cudaStream_t);
 // iic.cu
@@ -174,11 +174,12 @@ int cy_infonce_fwd_pass2(const void* z, int dtype, int64_t N, int64_t d, int64_t
     return infonce_rowstats(N, row_begin, row_end, inv_t, variant, 2, stats, xstat, st);
 }
 
-int cy_infonce_loss(int64_t N, int variant, const float* xstat, float* out4, void* workspace, size_t workspace_bytes, void* stream) {
+int cy_infonce_loss(int64_t N, int variant, const float* xstat, float* out8, const int32_t* bad_rows, const int32_t* overflow,
+                    void* workspace, size_t workspace_bytes, void* stream) {
     CY_NVTX("cy_infonce_loss");
-    CY_CHECK_ARG(xstat && out4 && N >= 2, "null pointer");
+    CY_CHECK_ARG(xstat && out8 && N >= 2, "null pointer");
     CY_CHECK_ARG(variant >= CY_SUPCON && variant <= CY_SELFPACED_SOFT, "unknown variant %d", variant);
-    return infonce_loss(N, variant, xstat, out4, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+    return infonce_loss(N, variant, xstat, out8, bad_rows, overflow, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int cy_infonce_bwd(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels, const uint8_t* codes,
@@ -220,12 +221,12 @@ int cy_infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_
 }
 
 int cy_infonce_unpack(const void* dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* order, void* g1,
-                      void* g2, const void* z, const float* inv_norm, void* stream) {
+                      void* g2, const void* z, const float* inv_norm, const float* gscale, void* stream) {
     CY_NVTX("cy_infonce_unpack");
     CY_CHECK_ARG(dz && g1 && g2 && n >= 1 && d >= 1 && lddz >= d, "bad arguments");
     CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
     CY_CHECK_ARG((z == nullptr) == (inv_norm == nullptr), "z and inv_norm go together");
-    return infonce_unpack(dz, dtype, n, d, lddz, order, g1, g2, z, inv_norm, reinterpret_cast<cudaStream_t>(stream));
+    return infonce_unpack(dz, dtype, n, d, lddz, order, g1, g2, z, inv_norm, gscale, reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t cy_iic_workspace_bytes(int B, int K, int H, int W, int pad) {

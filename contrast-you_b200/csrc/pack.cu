@@ -80,11 +80,35 @@ pack_rows_kernel(const uint8_t* __restrict__ f1, const uint8_t* __restrict__ f2,
     }
 }
 
+// 16 bytes of gradient (4 fp32 or 8 half-precision elements) times a scalar
+__device__ __forceinline__ uint4 scale16(uint4 v, int dtype, float g) {
+    if (dtype == CY_F32) {
+        return make_uint4(__float_as_uint(__uint_as_float(v.x) * g), __float_as_uint(__uint_as_float(v.y) * g),
+                          __float_as_uint(__uint_as_float(v.z) * g), __float_as_uint(__uint_as_float(v.w) * g));
+    }
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (dtype == CY_BF16) {
+            float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+            const __nv_bfloat162 r = __floats2bfloat162_rn(f.x * g, f.y * g);
+            w[k] = *reinterpret_cast<const uint32_t*>(&r);
+        } else {
+            float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+            const __half2 r = __floats2half2_rn(f.x * g, f.y * g);
+            w[k] = *reinterpret_cast<const uint32_t*>(&r);
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 template <int ESIZE>
 __global__ void __launch_bounds__(256)
 unpack_rows_kernel(const uint8_t* __restrict__ dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* __restrict__ order,
-                   uint8_t* __restrict__ g1, uint8_t* __restrict__ g2, const uint8_t* __restrict__ z, const float* __restrict__ inv_norm) {
+                   uint8_t* __restrict__ g1, uint8_t* __restrict__ g2, const uint8_t* __restrict__ z, const float* __restrict__ inv_norm,
+                   const float* __restrict__ gscale) {
     const int lane = threadIdx.x & 31;
+    const float gs = gscale ? gscale[0] : 1.f;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= 2 * n) return;
     const int64_t dst = order ? order[row] : row;
@@ -98,12 +122,19 @@ unpack_rows_kernel(const uint8_t* __restrict__ dz, int dtype, int64_t n, int64_t
         dot = warp_sum(dot);
         const float inv = inv_norm[row];
         for (int64_t c = lane; c < d; c += 32)
-            st_from_float(o, dtype, c, (ld_as_float(s, dtype, c) - ld_as_float(zr, dtype, c) * dot) * inv);
+            st_from_float(o, dtype, c, (ld_as_float(s, dtype, c) - ld_as_float(zr, dtype, c) * dot) * (inv * gs));
         return;
     }
     const bool vec = ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(o)) & 15) == 0 && (d * ESIZE) % 16 == 0;
     if (vec) {
-        for (int64_t c = lane; c < d * ESIZE / 16; c += 32) *reinterpret_cast<uint4*>(o + c * 16) = *reinterpret_cast<const uint4*>(s + c * 16);
+        if (gscale) {
+            for (int64_t c = lane; c < d * ESIZE / 16; c += 32)
+                *reinterpret_cast<uint4*>(o + c * 16) = scale16(*reinterpret_cast<const uint4*>(s + c * 16), dtype, gs);
+        } else {
+            for (int64_t c = lane; c < d * ESIZE / 16; c += 32) *reinterpret_cast<uint4*>(o + c * 16) = *reinterpret_cast<const uint4*>(s + c * 16);
+        }
+    } else if (gscale) {
+        for (int64_t c = lane; c < d; c += 32) st_from_float(o, dtype, c, ld_as_float(s, dtype, c) * gs);
     } else {
         for (int64_t c = lane; c < d * ESIZE; c += 32) o[c] = s[c];
     }
@@ -123,12 +154,12 @@ int infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_t d
 }
 
 int infonce_unpack(const void* dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* order, void* g1, void* g2,
-                   const void* z, const float* inv_norm, cudaStream_t st) {
+                   const void* z, const float* inv_norm, const float* gscale, cudaStream_t st) {
     const unsigned grid = (unsigned)((2 * n + 7) / 8);
     if (dtype == CY_F32)
-        unpack_rows_kernel<4><<<grid, 256, 0, st>>>((const uint8_t*)dz, dtype, n, d, lddz, order, (uint8_t*)g1, (uint8_t*)g2, (const uint8_t*)z, inv_norm);
+        unpack_rows_kernel<4><<<grid, 256, 0, st>>>((const uint8_t*)dz, dtype, n, d, lddz, order, (uint8_t*)g1, (uint8_t*)g2, (const uint8_t*)z, inv_norm, gscale);
     else
-        unpack_rows_kernel<2><<<grid, 256, 0, st>>>((const uint8_t*)dz, dtype, n, d, lddz, order, (uint8_t*)g1, (uint8_t*)g2, (const uint8_t*)z, inv_norm);
+        unpack_rows_kernel<2><<<grid, 256, 0, st>>>((const uint8_t*)dz, dtype, n, d, lddz, order, (uint8_t*)g1, (uint8_t*)g2, (const uint8_t*)z, inv_norm, gscale);
     CY_CHECK_LAUNCH("infonce_unpack");
     return CY_OK;
 }

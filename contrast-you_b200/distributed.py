@@ -99,11 +99,14 @@ def make_joint_reduce(group=None):
 
 
 class _ShardedInfoNCE(torch.autograd.Function):
-    """(f1, f2) [n_loc, d] local views -> (loss, out4, bad).  One autograd node per step: pack + the three in-place
-    all-gathers + forward sweep(s) + loss reduction in forward, strip backward + unpack in backward."""
+    """(f1, f2) [n_loc, d] local views -> (loss, out8).  One autograd node and one uninterrupted kernel / collective sequence
+    per step: pack, the three in-place all-gathers, forward sweep(s), loss reduction and — when a gradient will be asked
+    for — the strip backward with unit upstream gradient right behind it (losses/contrastive.py _FusedInfoNCE explains
+    why); ``backward`` only scatters the stored rows back to the two views, times the upstream gradient."""
 
     @staticmethod
-    def forward(ctx, f1, f2, labels_loc, order, inv_t, variant, gamma, path, group, check, design):
+    def forward(ctx, f1, f2, labels_loc, order, inv_t, variant, gamma, path, group, check, design, overflow, status):
+        from .losses.contrastive import _unit_scale
         lib = L.lib()
         world, rank = _ws(group)
         n_loc, d = f1.shape
@@ -112,18 +115,18 @@ class _ShardedInfoNCE(torch.autograd.Function):
         rb, re = rank * rows_loc, (rank + 1) * rows_loc
         dev = f1.device
         dt = L.dtype_code(f1)
+        need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         with L.guard(f1):
             st = L.stream_ptr(dev)
             z_all = torch.empty(N, d, dtype=f1.dtype, device=dev)
             labels_all = torch.empty(N, dtype=torch.int32, device=dev)
             xstat = torch.empty(N, 4, dtype=torch.float32, device=dev)
             stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev)
-            out4 = torch.empty(4, dtype=torch.float32, device=dev)
-            bad = torch.zeros(1, dtype=torch.int32, device=dev)
+            out8 = torch.empty(8, dtype=torch.float32, device=dev)
+            bad = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
             esz = f1.element_size()
             L.check(lib.cy_infonce_pack(f1.data_ptr(), f2.data_ptr(), dt, n_loc, d, f1.stride(0), f2.stride(0), L.ptr(order),
-                                        z_all.data_ptr() + rb * d * esz, bad.data_ptr() if check else None, None, st),
-                    "cy_infonce_pack")
+                                        z_all.data_ptr() + rb * d * esz, L.ptr(bad), None, st), "cy_infonce_pack")
             labels_all[rb:re].copy_(labels_loc)
             gather_rows_(z_all, group)
             gather_rows_(labels_all, group)
@@ -136,40 +139,44 @@ class _ShardedInfoNCE(torch.autograd.Function):
                 L.check(lib.cy_infonce_fwd_pass2(zp, dt, N, d, d, lp, None, rb, re, inv_t, variant, gamma, path, stats.data_ptr(),
                                                  xstat.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd_pass2")
             gather_rows_(xstat, group)
-            L.check(lib.cy_infonce_loss(N, variant, xstat.data_ptr(), out4.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_loss")
-        ctx.save_for_backward(z_all, labels_all, xstat, ws, *([order] if order is not None else []))
-        ctx.cfg = (inv_t, variant, gamma, path, rb, re, n_loc, group, design)
-        ctx.mark_non_differentiable(out4, bad)
-        return out4[0].clone(), out4, bad
+            L.check(lib.cy_infonce_loss(N, variant, xstat.data_ptr(), out8.data_ptr(), L.ptr(bad), L.ptr(overflow), ws.data_ptr(),
+                                        ws_bytes, st), "cy_infonce_loss")
+            loss = out8[0].clone()
+            if status is not None:
+                status.post(out8)
+            dz_loc = None
+            if need_grad:
+                one = _unit_scale(dev)
+                if design == "reduce_scatter":
+                    dz_loc = _strip_contribution_reduce_scatter(z_all, labels_all, xstat, one, inv_t, variant, gamma, rb, re, group)
+                else:
+                    dz_loc = torch.empty(re - rb, d, dtype=z_all.dtype, device=dev)
+                    # the kernels index dz by GLOBAL row: hand them the address row rb would have in a full [N, d] gradient
+                    dz_base = dz_loc.data_ptr() - rb * d * dz_loc.element_size()
+                    L.check(lib.cy_infonce_bwd(zp, dt, N, d, d, lp, None, rb, re, inv_t, variant, gamma, path, xstat.data_ptr(),
+                                               one.data_ptr(), dz_base, d, ws.data_ptr(), ws_bytes, st), "cy_infonce_bwd")
+        if need_grad:
+            ctx.save_for_backward(dz_loc, *([order] if order is not None else []))
+        ctx.n_loc = n_loc
+        ctx.mark_non_differentiable(out8)
+        return loss, out8
 
     @staticmethod
-    def backward(ctx, grad_loss, _g4, _gb):
+    def backward(ctx, grad_loss, _g8):
         lib = L.lib()
-        z_all, labels_all, xstat, ws, *rest = ctx.saved_tensors
+        dz_loc, *rest = ctx.saved_tensors
         order = rest[0] if rest else None
-        inv_t, variant, gamma, path, rb, re, n_loc, group, design = ctx.cfg
-        N, d = z_all.shape
-        dev = z_all.device
-        dt = L.dtype_code(z_all)
-        with L.guard(z_all):
-            st = L.stream_ptr(dev)
-            gscale = grad_loss
-            if gscale.dtype != torch.float32 or gscale.numel() != 1 or not gscale.is_contiguous():
-                gscale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
-            if design == "reduce_scatter":
-                dz_loc = _strip_contribution_reduce_scatter(z_all, labels_all, xstat, gscale, inv_t, variant, gamma, rb, re, group)
-            else:
-                dz_loc = torch.empty(re - rb, d, dtype=z_all.dtype, device=dev)
-                # the kernels index dz by GLOBAL row: hand them the address row rb would have in a full [N, d] gradient
-                dz_base = dz_loc.data_ptr() - rb * d * dz_loc.element_size()
-                L.check(lib.cy_infonce_bwd(z_all.data_ptr(), dt, N, d, d, labels_all.data_ptr(), None, rb, re, inv_t, variant, gamma,
-                                           path, xstat.data_ptr(), gscale.data_ptr(), dz_base, d, ws.data_ptr(), ws.numel(), st),
-                        "cy_infonce_bwd")
+        n_loc, d = ctx.n_loc, dz_loc.shape[1]
+        dev = dz_loc.device
+        gscale = grad_loss
+        if gscale.dtype != torch.float32 or gscale.numel() != 1 or not gscale.is_contiguous():
+            gscale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        with L.guard(dz_loc):
             g1 = torch.empty(n_loc, d, dtype=dz_loc.dtype, device=dev)
             g2 = torch.empty(n_loc, d, dtype=dz_loc.dtype, device=dev)
-            L.check(lib.cy_infonce_unpack(dz_loc.data_ptr(), dt, n_loc, d, d, L.ptr(order), g1.data_ptr(), g2.data_ptr(), None, None,
-                                          st), "cy_infonce_unpack")
-        return g1, g2, None, None, None, None, None, None, None, None, None
+            L.check(lib.cy_infonce_unpack(dz_loc.data_ptr(), L.dtype_code(dz_loc), n_loc, d, d, L.ptr(order), g1.data_ptr(),
+                                          g2.data_ptr(), None, None, gscale.data_ptr(), L.stream_ptr(dev)), "cy_infonce_unpack")
+        return g1, g2, None, None, None, None, None, None, None, None, None, None, None
 
 
 def _strip_contribution_reduce_scatter(z_all, labels_all, xstat, gscale, inv_t, variant, gamma, rb, re, group):
@@ -231,6 +238,7 @@ class ShardedSupConLoss(torch.nn.Module):
         self._design = backward_design
         self._path = {"auto": L.CY_PATH_AUTO, "simt": L.CY_PATH_SIMT, "tcgen05": L.CY_PATH_TCGEN05}[path]
         self._cache = None
+        self._status = None
 
     def _local_labels(self, target, n_local, rank, device, sort):
         """canonical labels of the owned row block (+ the local sort), cached while the same label tensor comes back"""
@@ -242,7 +250,7 @@ class ShardedSupConLoss(torch.nn.Module):
             raw = torch.tensor(target, dtype=torch.float32, device=device)      # contrastive.py:39-40
         else:
             raw = target
-        cacheable = isinstance(target, Tensor)
+        cacheable = isinstance(target, Tensor) and not torch.cuda.is_current_stream_capturing()      # see _ContrastBase._prepare
         if cacheable:
             if self._cache is None:
                 self._cache = _TensorLabelCache()
@@ -278,19 +286,24 @@ class ShardedSupConLoss(torch.nn.Module):
         labels_loc, order, overflow = self._local_labels(target, n_local, rank, device, tc)
         f1 = proj_feat1 if proj_feat1.stride(1) == 1 else proj_feat1.contiguous()
         f2 = proj_feat2 if proj_feat2.stride(1) == 1 else proj_feat2.contiguous()
-        loss, _, bad = _ShardedInfoNCE.apply(f1, f2, labels_loc, order, float(1.0 / self._t), self._variant, float(self._gamma),
-                                             self._path, self._group, __debug__, self._design)
-        if self._deferred_checks:
-            nan = torch.isnan(loss.detach()).to(torch.int32).reshape(1)
-            cur = torch.cat((bad, nan, overflow if overflow is not None else torch.zeros_like(nan)))
+        status = None
+        if not self._deferred_checks:
+            from .losses.contrastive import _HostStatus
+            if self._status is None:
+                self._status = _HostStatus()
+            status = self._status
+        loss, out8 = _ShardedInfoNCE.apply(f1, f2, labels_loc, order, float(1.0 / self._t), self._variant, float(self._gamma),
+                                           self._path, self._group, __debug__, self._design, overflow, status)
+        if status is None:
+            cur = out8[3:6].detach().clone()          # [non-finite terms, un-normalised rows, label overflows]
+            cur[0] = cur[0] + torch.isnan(loss.detach()).to(cur.dtype)
             if self._flags is None or self._flags.device != cur.device:
-                self._flags = cur.clone()
+                self._flags = cur
             else:
                 self._flags.add_(cur)       # in place: the counters keep their address across CUDA-graph replays
             return loss * self._grad_scale if self._grad_scale != 1.0 else loss
-        zero = loss.detach().new_zeros(())
-        nbad, over, val = torch.stack((bad[0].to(torch.float32), overflow[0].to(torch.float32) if overflow is not None else zero,
-                                       loss.detach())).tolist()
+        host = status.wait()                  # one 32-byte read, posted BEFORE the backward sweep was launched
+        val, nbad, over = host[0], host[4], host[5]
         assert nbad == 0, f"features need to be normalized first"
         if over:
             raise ValueError("int64 labels outside the int32 range are not supported (pass int32 labels or a python list)")
@@ -302,7 +315,7 @@ class ShardedSupConLoss(torch.nn.Module):
         """deferred_checks mode: one host read of this rank's accumulated (un-normalised rows, NaN losses) counters"""
         if self._flags is None:
             return
-        nbad, nan, over = self._flags.tolist()
+        nan, nbad, over = self._flags.tolist()
         self._flags.zero_()
         assert nbad == 0, f"features need to be normalized first"
         if over:

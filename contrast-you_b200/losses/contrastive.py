@@ -125,7 +125,7 @@ class _InfoNCEFunction(torch.autograd.Function):
             whole = (row_begin, row_end) == (0, N)
             # rows nobody fills (a bare row range without an exchange) must read as "no contribution"
             xstat = (torch.empty if whole or gather_xstat is not None else torch.zeros)(N, 4, dtype=torch.float32, device=z.device)
-            out4 = torch.empty(4, dtype=torch.float32, device=z.device)
+            out4 = torch.empty(8, dtype=torch.float32, device=z.device)
             ws_bytes = lib.cy_infonce_workspace_bytes(N, d, dt, variant, path)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
             lp, cp = L.ptr(labels), L.ptr(codes)
@@ -137,7 +137,7 @@ class _InfoNCEFunction(torch.autograd.Function):
                         "cy_infonce_fwd_pass2")
             if gather_xstat is not None:
                 gather_xstat(xstat)             # sharded: in-place all-gather of the owned rows
-            L.check(lib.cy_infonce_loss(N, variant, xstat.data_ptr(), out4.data_ptr(), ws.data_ptr(), ws_bytes, st),
+            L.check(lib.cy_infonce_loss(N, variant, xstat.data_ptr(), out4.data_ptr(), None, None, ws.data_ptr(), ws_bytes, st),
                     "cy_infonce_loss")
         ctx.save_for_backward(z, labels, codes, xstat, ws)
         ctx.cfg = (inv_t, variant, gamma, path, row_begin, row_end)
@@ -159,49 +159,111 @@ class _InfoNCEFunction(torch.autograd.Function):
         return dz, None, None, None, None, None, None, None, None, None
 
 
-class _PackViews(torch.autograd.Function):
-    """(proj_feat1, proj_feat2) -> z [2n, d]: ``torch.cat`` of the two views (contrastive.py:15) with the rows taken in
-    ``order`` (a permutation of 0..2n-1 or None) and the ``is_normalized`` assertion (:9-11, :58) evaluated on the device
-    in the same pass (``bad`` counts the offending rows; the module reads it together with the NaN check, one host sync
-    per forward instead of three).  Backward scatters dz to the two views."""
+_ONES = {}
+
+
+def _unit_scale(device) -> Tensor:
+    """a resident fp32 1.0 per device: the upstream gradient of the eagerly launched backward sweep"""
+    t = _ONES.get(device)
+    if t is None:
+        t = torch.ones(1, dtype=torch.float32, device=device)
+        if not torch.cuda.is_current_stream_capturing():      # a tensor born inside a capture lives in the graph's private pool
+            _ONES[device] = t
+    return t
+
+
+class _HostStatus:
+    """pinned 8-float landing buffer + event for the per-step status read (loss, self-paced sums, NaN / un-normalised /
+    label-overflow counters).  The copy is enqueued right behind the loss reduction and BEFORE the backward sweep is launched,
+    so waiting for it does not wait for the backward."""
+
+    def __init__(self):
+        self.buf = torch.empty(8, dtype=torch.float32).pin_memory()
+        self.event = torch.cuda.Event()
+
+    def post(self, out8: Tensor):
+        self.buf.copy_(out8, non_blocking=True)
+        self.event.record()
+
+    def wait(self):
+        self.event.synchronize()
+        return self.buf.tolist()
+
+
+class _FusedInfoNCE(torch.autograd.Function):
+    """(proj_feat1, proj_feat2) -> (loss, out8) as ONE autograd node and one uninterrupted kernel sequence:
+
+        cy_infonce_pack     torch.cat of the two views (contrastive.py:15) with the rows taken in ``order`` (the label sort)
+                            and the ``is_normalized`` assertion (:9-11, :58) counted on the device in the same pass
+        cy_infonce_fwd      (+ cy_infonce_fwd_pass2 for exclude / self-paced)
+        cy_infonce_loss     loss + the counters of the reference's per-step assertions -> out8; ``status.post`` copies it
+                            to pinned host memory asynchronously
+        cy_infonce_bwd      launched right here, with unit upstream gradient, whenever an input needs a gradient: the
+                            gradient of this loss is linear in the upstream scalar, so the sweep does not have to wait for
+                            ``loss.backward()`` — the host round trip of the strict per-step check (and autograd's own launch
+                            latency) then overlaps the sweep instead of idling the GPU between the two GEMM kernels.
+    backward = cy_infonce_unpack: scatter dz back to the two views, times the actual upstream gradient."""
 
     @staticmethod
-    def forward(ctx, f1, f2, order, check, normalize):
+    def forward(ctx, f1, f2, labels, order, inv_t, variant, gamma, path, check_norm, normalize, overflow, status):
         lib = L.lib()
         n, d = f1.shape
+        N = 2 * n
+        dev = f1.device
+        dt = L.dtype_code(f1)
+        need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         with L.guard(f1):
-            z = torch.empty(2 * n, d, dtype=f1.dtype, device=f1.device)
-            bad = torch.zeros(1, dtype=torch.int32, device=f1.device) if (check and not normalize) else None
-            inv_norm = torch.empty(2 * n, dtype=torch.float32, device=f1.device) if normalize else None
-            L.check(lib.cy_infonce_pack(f1.data_ptr(), f2.data_ptr(), L.dtype_code(f1), n, d, f1.stride(0), f2.stride(0),
-                                        L.ptr(order), z.data_ptr(), L.ptr(bad), L.ptr(inv_norm), L.stream_ptr(f1.device)),
-                    "cy_infonce_pack")
+            st = L.stream_ptr(dev)
+            z = torch.empty(N, d, dtype=f1.dtype, device=dev)
+            bad = torch.zeros(1, dtype=torch.int32, device=dev) if (check_norm and not normalize) else None
+            inv_norm = torch.empty(N, dtype=torch.float32, device=dev) if normalize else None
+            L.check(lib.cy_infonce_pack(f1.data_ptr(), f2.data_ptr(), dt, n, d, f1.stride(0), f2.stride(0), L.ptr(order), z.data_ptr(),
+                                        L.ptr(bad), L.ptr(inv_norm), st), "cy_infonce_pack")
+            stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev)
+            xstat = torch.empty(N, 4, dtype=torch.float32, device=dev)
+            out8 = torch.empty(8, dtype=torch.float32, device=dev)
+            ws_bytes = lib.cy_infonce_workspace_bytes(N, d, dt, variant, path)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            zp, lp = z.data_ptr(), labels.data_ptr()
+            L.check(lib.cy_infonce_fwd(zp, dt, N, d, d, lp, None, 0, N, inv_t, variant, path, stats.data_ptr(), xstat.data_ptr(),
+                                       ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd")
+            if variant != L.CY_SUPCON:
+                L.check(lib.cy_infonce_fwd_pass2(zp, dt, N, d, d, lp, None, 0, N, inv_t, variant, gamma, path, stats.data_ptr(),
+                                                 xstat.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd_pass2")
+            L.check(lib.cy_infonce_loss(N, variant, xstat.data_ptr(), out8.data_ptr(), L.ptr(bad), L.ptr(overflow), ws.data_ptr(),
+                                        ws_bytes, st), "cy_infonce_loss")
+            loss = out8[0].clone()
+            if status is not None:
+                status.post(out8)
+            dz = None
+            if need_grad:
+                dz = torch.empty_like(z)
+                L.check(lib.cy_infonce_bwd(zp, dt, N, d, d, lp, None, 0, N, inv_t, variant, gamma, path, xstat.data_ptr(),
+                                           _unit_scale(dev).data_ptr(), dz.data_ptr(), d, ws.data_ptr(), ws_bytes, st),
+                        "cy_infonce_bwd")
         ctx.shape = (n, d)
         ctx.has_order, ctx.normalize = order is not None, normalize
-        # saved through autograd (not as plain attributes): an output stored on ctx would keep the graph alive in a
-        # reference cycle that only the garbage collector frees
-        saved = ([order] if order is not None else []) + ([z, inv_norm] if normalize else [])
-        ctx.save_for_backward(*saved)
-        if bad is None:
-            bad = torch.zeros(0, dtype=torch.int32, device=f1.device)
-        ctx.mark_non_differentiable(bad)
-        return z, bad
+        if need_grad:
+            ctx.save_for_backward(dz, *([order] if order is not None else []), *([z, inv_norm] if normalize else []))
+        ctx.mark_non_differentiable(out8)
+        return loss, out8
 
     @staticmethod
-    def backward(ctx, dz, _grad_bad):
+    def backward(ctx, grad_loss, _grad_out8):
         lib = L.lib()
         n, d = ctx.shape
-        saved = list(ctx.saved_tensors)
+        dz, *saved = ctx.saved_tensors
         order = saved.pop(0) if ctx.has_order else None
         z, inv_norm = (saved[0], saved[1]) if ctx.normalize else (None, None)
-        if dz.stride(1) != 1:
-            dz = dz.contiguous()
+        gscale = grad_loss
+        if gscale.dtype != torch.float32 or gscale.numel() != 1 or not gscale.is_contiguous():
+            gscale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         with L.guard(dz):
             g1 = torch.empty(n, d, dtype=dz.dtype, device=dz.device)
             g2 = torch.empty(n, d, dtype=dz.dtype, device=dz.device)
-            L.check(lib.cy_infonce_unpack(dz.data_ptr(), L.dtype_code(dz), n, d, dz.stride(0), L.ptr(order), g1.data_ptr(),
-                                          g2.data_ptr(), L.ptr(z), L.ptr(inv_norm), L.stream_ptr(dz.device)), "cy_infonce_unpack")
-        return g1, g2, None, None, None
+            L.check(lib.cy_infonce_unpack(dz.data_ptr(), L.dtype_code(dz), n, d, d, L.ptr(order), g1.data_ptr(), g2.data_ptr(),
+                                          L.ptr(z), L.ptr(inv_norm), gscale.data_ptr(), L.stream_ptr(dz.device)), "cy_infonce_unpack")
+        return g1, g2, None, None, None, None, None, None, None, None, None, None
 
 
 def tensor_core_eligible(z: Tensor, labels, codes, variant: int, path: int) -> bool:
@@ -261,7 +323,9 @@ class _ContrastBase(nn.Module):
             assert mask.shape == torch.Size([batch_size, batch_size])
             codes = _mask_codes(mask, batch_size, device)
         elif target is not None:
-            cacheable = isinstance(target, Tensor)
+            # (never while a CUDA graph is being captured: a hit would leave the label kernels out of the graph, and replays
+            # with new label contents in the same buffer would silently reuse the captured labels)
+            cacheable = isinstance(target, Tensor) and not torch.cuda.is_current_stream_capturing()
         else:  # SimCLR: only the twin view is positive
             labels = torch.arange(batch_size, dtype=torch.int32, device=device).repeat(2)
         assert proj_feat1.shape == proj_feat2.shape, (proj_feat1.shape, proj_feat2.shape)
@@ -298,18 +362,40 @@ class _ContrastBase(nn.Module):
         self._views = (proj_feat1.detach(), proj_feat2.detach(), labels, codes)      # lazy side channels (original row order)
         self._dbg_cache = {}
         normalize = bool(getattr(self, "_normalize_input", False))
-        if not fused:
+        if not fused or codes is not None:
+            # general route (explicit mask= codes, mixed dtypes / devices, > 2-D inputs): stock torch glue around the sweeps
             if normalize:
                 proj_feat1 = torch.nn.functional.normalize(proj_feat1, dim=1)
                 proj_feat2 = torch.nn.functional.normalize(proj_feat2, dim=1)
             assert is_normalized(proj_feat1) and is_normalized(proj_feat2), f"features need to be normalized first"
-            self._bad = None
-            return torch.cat([proj_feat1, proj_feat2], dim=0), labels, codes
+            z = torch.cat([proj_feat1, proj_feat2], dim=0)
+            return None, (z, labels, codes)
         f1 = proj_feat1 if proj_feat1.stride(1) == 1 else proj_feat1.contiguous()
         f2 = proj_feat2 if proj_feat2.stride(1) == 1 else proj_feat2.contiguous()
-        z, bad = _PackViews.apply(f1, f2, order, __debug__, normalize)
-        self._bad = bad if (__debug__ and not normalize) else None
-        return z, (sorted_labels if codes is None else None), codes
+        return (f1, f2, sorted_labels, order, normalize), None
+
+    def _evaluate(self, proj_feat1, proj_feat2, target, mask, gamma=1e6):
+        """-> (loss, status): status = the 8 host floats of cy_infonce_loss (None with deferred_checks)"""
+        fused_args, general = self._prepare(proj_feat1, proj_feat2, target, mask, sort=True)
+        variant = self._kernel_variant()
+        deferred = bool(getattr(self, "_deferred_checks", False))
+        if general is not None:
+            z, labels, codes = general
+            loss, out8 = info_nce(z, labels, codes, self._t, variant, gamma=gamma, path=self._path)
+            if self._overflow is not None:
+                out8[5:6].copy_(self._overflow)
+            self._out8 = out8
+            return loss, (None if deferred else out8.tolist())
+        f1, f2, labels, order, normalize = fused_args
+        status = None
+        if not deferred:
+            status = self.__dict__.get("_status")
+            if status is None:
+                status = self.__dict__["_status"] = _HostStatus()
+        loss, out8 = _FusedInfoNCE.apply(f1, f2, labels, order, float(1.0 / self._t), int(variant), float(gamma), int(self._path),
+                                         __debug__, normalize, self._overflow, status)
+        self._out8 = out8
+        return loss, (status.wait() if status is not None else None)
 
     def _sorts_rows(self, f1) -> bool:
         """rows are sorted by label when the call runs on the tensor kernels: positives then sit in a few column tiles, the
@@ -320,35 +406,27 @@ class _ContrastBase(nn.Module):
               and (variant == L.CY_SUPCON or 2 * n <= 4096 * 128))
         return ok and (self._path == L.CY_PATH_TCGEN05 or (self._path == L.CY_PATH_AUTO and 2 * n >= 1024))
 
-    def _host_checks(self, loss: Tensor):
-        """the reference's two assertions / errors in ONE device->host read: un-normalised rows (contrastive.py:58,
-        AssertionError) and a NaN loss (:98-99, RuntimeError(loss)).
+    def _host_checks(self, loss: Tensor, status):
+        """the reference's assertions / errors from ONE device->host read: un-normalised rows (contrastive.py:58,
+        AssertionError), a NaN loss (:98-99, RuntimeError(loss)) and, for int64 label tensors, values outside int32.
 
-        ``deferred_checks=True`` (extension) replaces the read by two device-side counters that
+        ``deferred_checks=True`` (extension) replaces the read by device-side counters that
         ``raise_if_flagged()`` inspects whenever the caller chooses (e.g. once per epoch): the forward then has no host
         synchronisation at all and — with tensor labels — can be captured in a CUDA graph
         (``torch.cuda.make_graphed_callables``)."""
-        ovf = getattr(self, "_overflow", None)
-        if getattr(self, "_deferred_checks", False):
-            nan = torch.isnan(loss.detach()).to(torch.int32).reshape(1)
-            bad = self._bad if self._bad is not None else torch.zeros_like(nan)
-            cur = torch.cat((bad.to(torch.int32), nan, ovf if ovf is not None else torch.zeros_like(nan)))
+        if status is None:
+            cur = self._out8[3:6].detach().clone()      # [non-finite terms, un-normalised rows, label overflows]
+            cur[0] = cur[0] + torch.isnan(loss.detach()).to(cur.dtype)
             flags = getattr(self, "_flags", None)
             if flags is None or flags.device != cur.device:
-                self._flags = cur.clone()
+                self._flags = cur
             else:
                 flags.add_(cur)         # in place: the counter tensor keeps its address across CUDA-graph replays
             return
-        if self._bad is not None or ovf is not None:
-            zero = loss.detach().new_zeros(())
-            bad, over, val = torch.stack((self._bad[0].to(torch.float32) if self._bad is not None else zero,
-                                          ovf[0].to(torch.float32) if ovf is not None else zero,
-                                          loss.detach().to(torch.float32))).tolist()
-            assert bad == 0, f"features need to be normalized first"
-            if over:
-                raise ValueError("int64 labels outside the int32 range are not supported (pass int32 labels or a python list)")
-        else:
-            val = loss.item()
+        val, bad, over = status[0], status[4], status[5]
+        assert bad == 0, f"features need to be normalized first"
+        if over:
+            raise ValueError("int64 labels outside the int32 range are not supported (pass int32 labels or a python list)")
         if val != val:
             raise RuntimeError(loss)
 
@@ -358,7 +436,7 @@ class _ContrastBase(nn.Module):
         flags = getattr(self, "_flags", None)
         if flags is None:
             return
-        bad, nan, over = flags.tolist()
+        nan, bad, over = flags.tolist()
         flags.zero_()
         assert bad == 0, f"features need to be normalized first"
         if over:
@@ -415,9 +493,8 @@ class SupConLoss1(_ContrastBase):
         return L.CY_SUPCON_EXCLUDE if self._exclude_pos else L.CY_SUPCON
 
     def forward(self, proj_feat1, proj_feat2, target=None, mask: Tensor = None, **kwargs):
-        z, labels, codes = self._prepare(proj_feat1, proj_feat2, target, mask, sort=True)
-        loss, _ = info_nce(z, labels, codes, self._t, self._kernel_variant(), path=self._path, sort_rows=False)
-        self._host_checks(loss)
+        loss, status = self._evaluate(proj_feat1, proj_feat2, target, mask)
+        self._host_checks(loss, status)
         return loss
 
 
@@ -440,14 +517,15 @@ class SelfPacedSupConLoss(_ContrastBase):
         return L.CY_SELFPACED_HARD if self._weight_update == "hard" else L.CY_SELFPACED_SOFT
 
     def forward(self, proj_feat1, proj_feat2, target=None, mask: Tensor = None, **kwargs):
-        z, labels, codes = self._prepare(proj_feat1, proj_feat2, target, mask, sort=True)
-        loss, out4 = info_nce(z, labels, codes, self._t, self._kernel_variant(), gamma=self.__gamma, path=self._path)
-        # contrastive.py:179-181 — a python float (host sync, as in the reference)
-        self.downgrade_ratio = (out4[1] / out4[2]).item()
+        loss, status = self._evaluate(proj_feat1, proj_feat2, target, mask, gamma=self.__gamma)
+        # contrastive.py:179-181 — a python float (the reference syncs for it too); it rides on the status read
+        if status is None:
+            status = self._out8.tolist()
+        self.downgrade_ratio = status[1] / status[2] if status[2] else float("nan")
         if self._correct_grad:
             if self.downgrade_ratio > 0:
                 loss = loss / self.downgrade_ratio
-        self._host_checks(loss)
+        self._host_checks(loss, status)
         return loss
 
     @property

@@ -13,6 +13,13 @@ The network is a plain torch U-Net with the reference's layer widths (``arch/une
     python examples/pretrain_step.py --steps 10                       # one GPU
     torchrun --nproc-per-node 8 examples/pretrain_step.py --steps 10  # DDP, 18 scans x 2 views per rank
 Prints one JSON line (rank 0): images/s over all ranks, ms/step, and the share of the step spent in the two criteria.
+
+Under DDP the two criteria are the GLOBAL-BATCH forms (``--local-criteria`` restores what the reference would do under a
+DDP launch: every rank contrasts its own 18 images): ``ShardedSupConLoss(grad_scale=world)`` and a batch-sharded
+``IIDSegmentationLoss`` whose loss is scaled by ``world`` the same way, so that DDP's gradient AVERAGE over ranks equals the
+single-process gradient of the global-batch loss.  ``--check`` verifies exactly that on the GPU box: after one backward the
+DDP-averaged parameter gradients are compared with a single-process evaluation of the concatenated batch of all ranks on
+the same weights (BatchNorm in eval mode for the check: batch statistics are per-rank under DDP by design).
 """
 import argparse
 import json
@@ -75,6 +82,45 @@ class PretrainModel(nn.Module):
         return self.infonce_head(conv5), self.mi_head(up2)
 
 
+def ddp_gradient_check(model, fwd, infonce, mi, mi_scale, img, img_tf, labels, dev, rank, world):
+    """one fp32 backward through DDP with the global-batch criteria vs a single-process backward on the concatenated batch
+    of all ranks, same weights, BatchNorm in eval mode.  Returns the max relative parameter-gradient error (over ranks)."""
+    model.eval()
+    x = torch.cat((img.to(dev), img_tf.to(dev)))
+    model.zero_grad(set_to_none=True)
+    z, probs = fwd(x)
+    z1, z2 = torch.chunk(z, 2, dim=0)
+    pairs = [torch.chunk(p.float(), 2, 0) for p in probs]
+    loss = infonce(z1, z2, target=labels) + (0.1 * mi_scale) * sum(mi(a, b) for a, b in pairs) / len(pairs)
+    loss.backward()                                                       # DDP averages the parameter gradients over ranks
+    got = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    # single process: gather every rank's images, evaluate the plain modules on the whole batch with the same weights
+    def gather(t):
+        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=dev)
+        dist.all_gather_into_tensor(out, t.to(dev).contiguous())
+        return out.flatten(0, 1)
+    xa, xb = gather(img), gather(img_tf)
+    all_labels = labels * world                                            # every rank holds the same partition list
+    model.zero_grad(set_to_none=True)
+    z, probs = model(torch.cat((xa, xb)))
+    z1, z2 = torch.chunk(z, 2, dim=0)
+    pairs = [torch.chunk(p.float(), 2, 0) for p in probs]
+    ref = SupConLoss1()(z1, z2, target=all_labels) + 0.1 * sum(IIDSegmentationLoss(padding=1)(a, b) for a, b in pairs) / len(pairs)
+    ref.backward()
+    worst = 0.0
+    for n, p in model.named_parameters():
+        if p.grad is None or n not in got:
+            continue
+        denom = float(p.grad.abs().max())
+        if denom > 0:
+            worst = max(worst, float((got[n] - p.grad).abs().max()) / denom)
+    t = torch.tensor([worst, abs(float(loss.item()) / world - float(ref.item()))], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    model.zero_grad(set_to_none=True)
+    model.train()
+    return {"max_param_grad_rel_err": float(t[0]), "loss_abs_diff": float(t[1]), "ok": bool(t[0] < 2e-3)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
@@ -86,6 +132,8 @@ def main():
     ap.add_argument("--subheads", type=int, default=5)
     ap.add_argument("--no-amp", action="store_true")
     ap.add_argument("--batched-heads", action="store_true", help="IIDSegmentationLoss.forward_heads instead of the python sum")
+    ap.add_argument("--local-criteria", action="store_true", help="under DDP: per-rank criteria (no exchange), as the reference would run")
+    ap.add_argument("--check", action="store_true", help="DDP global-batch gradients == single-process gradients on the concatenated batch")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -99,7 +147,14 @@ def main():
 
     model = PretrainModel(args.max_channel, args.clusters, args.subheads).to(dev)
     fwd = nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if world > 1 else model
-    infonce, mi = SupConLoss1(), IIDSegmentationLoss(padding=1)          # the drop-in criteria (no parameters)
+    global_batch = world > 1 and not args.local_criteria
+    if global_batch:
+        from contrast_you_b200 import distributed as cyd
+        infonce = cyd.ShardedSupConLoss(grad_scale=world)
+        mi = cyd.shard_iic_loss(IIDSegmentationLoss(padding=1))
+    else:
+        infonce, mi = SupConLoss1(), IIDSegmentationLoss(padding=1)          # the drop-in criteria (no parameters)
+    mi_scale = float(world) if global_batch else 1.0
     opt = torch.optim.Adam(model.parameters(), lr=1e-6)
     amp = not args.no_amp
     scaler = torch.amp.GradScaler("cuda", enabled=amp)
@@ -129,13 +184,17 @@ def main():
             else:
                 loss_mi = sum(mi(a, b) for a, b in pairs) / len(pairs)
             c1.record()
-            loss = loss_nce + 0.1 * loss_mi
+            loss = loss_nce + (0.1 * mi_scale) * loss_mi
         scaler.scale(loss).backward()
         scaler.step(opt)
         scaler.update()
         meters = (loss_nce.item(), loss_mi.item())                       # hooks meter with .item() every batch
         t_crit[0] += c0.elapsed_time(c1)
         return meters
+
+    check = None
+    if args.check and world > 1:
+        check = ddp_gradient_check(model, fwd, infonce, mi, mi_scale, img, img_tf, labels, dev, rank, world)
 
     for _ in range(args.warmup):
         step()
@@ -162,6 +221,8 @@ def main():
             "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / args.steps, "amp": amp,
             "config": {"images_per_rank": 2 * n_img, "size": args.size, "max_channel": args.max_channel,
                        "clusters": args.clusters, "subheads": args.subheads, "padding": 1},
+            "criteria": "global-batch (row-sharded InfoNCE + batch-sharded IIC)" if global_batch else "per-rank",
+            "ddp_gradient_check": check,
             "last_losses": {"infonce": meters[0], "discrete_mi": meters[1]}, "data": "synthetic"}))
     if world > 1:
         dist.destroy_process_group()

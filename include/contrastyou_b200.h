@@ -112,12 +112,13 @@ int cy_infonce_fwd_pass2(const void* z, int dtype, int64_t N, int64_t d, int64_t
                          float gamma, int path, float* stats, float* xstat, void* workspace, size_t workspace_bytes,
                          void* stream);
 
-/* Loss reduction over ALL N rows of xstat (the caller has all-gathered them in the sharded case), fixed summation order:
- * out[0] = loss = sum_i term_i / N, out[1] = sum_ij P_ij w_ij, out[2] = sum_ij P_ij (self-paced downgrade ratio =
- * out[1]/out[2], contrastive.py:179-181; 0 for the other variants), out[3] = number of non-finite row terms (NaN check,
- * :98-99). */
-int cy_infonce_loss(int64_t N, int variant, const float* xstat, float* out4, void* workspace, size_t workspace_bytes,
-                    void* stream);
+/* Loss reduction over ALL N rows of xstat (the caller has all-gathered them in the sharded case), fixed summation order.
+ * out8 [8] float: [0] = loss = sum_i term_i / N, [1] = sum_ij P_ij w_ij, [2] = sum_ij P_ij (self-paced downgrade ratio =
+ * [1]/[2], contrastive.py:179-181; 0 for the other variants), [3] = number of non-finite row terms (NaN check, :98-99),
+ * [4] = *bad_rows (un-normalised rows counted by cy_infonce_pack, :58), [5] = *overflow (cy_labels_canonicalize), [6..7] = 0:
+ * everything the reference's per-step assertions need, in one 32-byte device->host read.  bad_rows / overflow may be NULL. */
+int cy_infonce_loss(int64_t N, int variant, const float* xstat, float* out8, const int32_t* bad_rows, const int32_t* overflow,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward: dz[row_begin:row_end, :] = gscale[0] * (1/t) * sum_j (G_ij + G_ji) z_j  with G = dLoss/dS built on the
  * fly from the xstat rows of i and j.  gscale is a DEVICE scalar: the upstream gradient
@@ -156,9 +157,11 @@ int cy_infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_
 
 /* Adjoint of cy_infonce_pack: scatters dz [2n, d] (row pitch lddz) back to the two views, g(order[i]) = dz[i];
  * g1, g2 are contiguous [n, d].  With (z, inv_norm) from a normalising pack it also applies the Jacobian of the
- * normalisation, g = (dz - z (z . dz)) * inv_norm; pass NULL, NULL otherwise. */
+ * normalisation, g = (dz - z (z . dz)) * inv_norm; pass NULL, NULL otherwise.  gscale (device scalar, may be NULL)
+ * multiplies the result: the modules run cy_infonce_bwd with unit upstream gradient right behind the forward sweep (no
+ * host round trip between the two) and apply the actual upstream gradient here. */
 int cy_infonce_unpack(const void* dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* order, void* g1,
-                      void* g2, const void* z, const float* inv_norm, void* stream);
+                      void* g2, const void* z, const float* inv_norm, const float* gscale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * IIC discrete-MI segmentation loss.  Replaces compute_joint_2D / compute_joint_2D_with_padding_zeros

@@ -22,8 +22,13 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for (n_loc, dtype, path, tol) in [(64, torch.float32, "simt", 1e-4), (512, torch.bfloat16, "tcgen05", 2e-2),
-                                      (2048, torch.bfloat16, "auto", 2e-2)]:
+    cases = [(64, torch.float32, "simt", 1e-4, {}), (512, torch.bfloat16, "tcgen05", 2e-2, {}), (2048, torch.bfloat16, "auto", 2e-2, {}),
+             # a local batch whose row block is not 128-aligned (2 x 96 = 192 rows) must fall back, not raise
+             (96, torch.bfloat16, "auto", 2e-2, {}),
+             # the rest of the family, sharded; and the north_star's reduce-scatter design (i) next to the default (ii)
+             (1024, torch.bfloat16, "auto", 2e-2, {"exclude_other_pos": True}),
+             (512, torch.bfloat16, "auto", 2e-2, {"backward_design": "reduce_scatter"})]
+    for (n_loc, dtype, path, tol, extra) in cases:
         g = torch.Generator().manual_seed(1234)
         n = n_loc * world
         f1 = torch.nn.functional.normalize(torch.randn(n, 256, generator=g), dim=1).to(dtype)
@@ -32,20 +37,29 @@ def main():
         sl = slice(rank * n_loc, (rank + 1) * n_loc)
         a = f1[sl].to(dev).requires_grad_()
         b = f2[sl].to(dev).requires_grad_()
-        loss = cyd.ShardedSupConLoss(path=path)(a, b, target=lab[sl].tolist())
+        crit = cyd.ShardedSupConLoss(path=path, **extra)
+        loss = crit(a, b, target=lab[sl].tolist())
         loss.backward()
+        # second call with DEVICE int64 labels (the cached-tensor route): must give the same numbers
+        a2, b2 = a.detach().clone().requires_grad_(), b.detach().clone().requires_grad_()
+        lab_dev = lab[sl].to(dev)
+        for _ in range(2):
+            a2.grad = None
+            loss2 = crit(a2, b2, target=lab_dev)
+            loss2.backward()
         # single-process reference on the whole batch (every rank recomputes it; SIMT fp32 path for the bf16 cases too)
         A = f1.to(dev).requires_grad_()
         B = f2.to(dev).requires_grad_()
-        ref = SupConLoss1(path="simt")(A, B, target=lab.tolist())
+        ref = SupConLoss1(path="simt", exclude_other_pos=bool(extra.get("exclude_other_pos")))(A, B, target=lab.tolist())
         ref.backward()
         e_loss = abs(loss.item() - ref.item()) / abs(ref.item())
         ga, gA = a.grad.float(), A.grad[sl].float()
         e_grad = ((ga - gA).abs().max() / gA.abs().max()).item()
-        good = e_loss < tol and e_grad < tol
+        same = abs(loss2.item() - loss.item()) <= 1e-6 * abs(loss.item()) and torch.equal(a2.grad, a.grad)
+        good = e_loss < tol and e_grad < tol and same
         ok &= good
-        print(f"[rank {rank}] infonce n_loc={n_loc} {dtype} {path}: loss {loss.item():.6f} ref {ref.item():.6f} "
-              f"rel {e_loss:.2e} grad rel {e_grad:.2e} {'OK' if good else 'FAIL'}", flush=True)
+        print(f"[rank {rank}] infonce n_loc={n_loc} {dtype} {path} {extra}: loss {loss.item():.6f} ref {ref.item():.6f} "
+              f"rel {e_loss:.2e} grad rel {e_grad:.2e} repeat-identical {same} {'OK' if good else 'FAIL'}", flush=True)
 
     g = torch.Generator().manual_seed(99)
     Bt, K, H, W = 2 * world, 10, 48, 40

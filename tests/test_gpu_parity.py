@@ -440,12 +440,12 @@ def test_tcgen05_row_stats_match_simt():
     for name, path in (("tc", L.CY_PATH_TCGEN05), ("simt", L.CY_PATH_SIMT)):
         stats = torch.zeros(L.CY_NSTAT, N, device=DEV)
         xstat = torch.zeros(N, 4, device=DEV)
-        out4 = torch.zeros(4, device=DEV)
+        out4 = torch.zeros(8, device=DEV)
         wsb = lib.cy_infonce_workspace_bytes(N, 256, L.CY_BF16, 0, path)
         ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
         L.check(lib.cy_infonce_fwd(z.data_ptr(), L.CY_BF16, N, 256, 256, labels.data_ptr(), None, 0, N, 1 / 0.07, 0, path,
                                    stats.data_ptr(), xstat.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr()), "fwd")
-        L.check(lib.cy_infonce_loss(N, 0, xstat.data_ptr(), out4.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr()), "loss")
+        L.check(lib.cy_infonce_loss(N, 0, xstat.data_ptr(), out4.data_ptr(), None, None, ws.data_ptr(), wsb, L.stream_ptr()), "loss")
         res[name] = (xstat.cpu().numpy(), out4.cpu().numpy())
     np.testing.assert_allclose(res["tc"][0], res["simt"][0], rtol=2e-4, atol=1e-6)
     assert res["tc"][1][3] == 0 and res["simt"][1][3] == 0
