@@ -43,8 +43,9 @@ SIGNATURES = {
     "cy_iic_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "cy_iic_joint": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "cy_iic_epilogue_workspace_bytes": (_sz, [_i32, _i32]),
-    "cy_iic_epilogue": (_i32, [_vp, _i32, _i32, _i32, _f32, _f32, _f64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cy_iic_epilogue": (_i32, [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _f64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cy_iic_bwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "cy_p2p_push": (_i32, [_vp, _i32, _i32, _vp, _i32, _vp]),
 }
 
 _LIB = None

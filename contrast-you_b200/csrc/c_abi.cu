@@ -70,7 +70,9 @@ int infonce_bwd_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, 
 size_t iic_workspace_bytes(int, int, int, int, int);
 int iic_joint(const void*, const void*, int, int, int, int, int, int, double*, void*, size_t, cudaStream_t);
 size_t iic_epilogue_workspace_bytes(int, int);
-int iic_epilogue(const double*, int, int, int, float, float, double, float*, float*, float*, float*, void*, size_t, cudaStream_t);
+int iic_epilogue(const double*, int, int, int, int, float, float, double, float*, float*, float*, float*, void*, size_t, cudaStream_t);
+// p2p.cu
+int p2p_push(void* const*, int, int, const unsigned long long*, int, cudaStream_t);
 int iic_bwd(const void*, const void*, int, int, int, int, int, int, const float*, const float*, void*, void*, cudaStream_t);
 
 static int check_infonce_args(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
@@ -256,12 +258,18 @@ size_t cy_iic_epilogue_workspace_bytes(int K, int pad) {
     return iic_epilogue_workspace_bytes(K, pad);
 }
 
-int cy_iic_epilogue(const double* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
-                    float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes, void* stream) {
+int cy_iic_epilogue(const double* joint, int n_slots, int K, int pad, int symmetric, float lamda, float eps, double n_pixels,
+                    float* loss, float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes, void* stream) {
     CY_NVTX("cy_iic_epilogue");
-    CY_CHECK_ARG(joint && loss && p00 && K >= 1 && pad >= 0, "bad arguments");
-    return iic_epilogue(joint, K, pad, symmetric, lamda, eps, n_pixels, loss, p00, p_ij, djoint, workspace, workspace_bytes,
+    CY_CHECK_ARG(joint && loss && p00 && K >= 1 && pad >= 0 && n_slots >= 1, "bad arguments");
+    return iic_epilogue(joint, n_slots, K, pad, symmetric, lamda, eps, n_pixels, loss, p00, p_ij, djoint, workspace, workspace_bytes,
                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_p2p_push(void* const* peer_bufs, int world, int rank, const unsigned long long* ranges, int n_ranges, void* stream) {
+    CY_NVTX("cy_p2p_push");
+    CY_CHECK_ARG(peer_bufs && ranges && world >= 1 && rank >= 0 && rank < world && n_ranges >= 1 && n_ranges <= 4, "bad arguments");
+    return p2p_push(peer_bufs, world, rank, ranges, n_ranges, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int cy_iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,

@@ -233,7 +233,7 @@ __device__ double block_reduce_min(double v, double* red) {
 // dynamic smem: double A[nj] (B matrix, [dd][k1][k2]), P[nj], G[nj], sdisp[TT], colsum[TT*K], rowsum[TT*K]
 constexpr int EPI_THREADS = 1024;
 __global__ void __launch_bounds__(EPI_THREADS)
-iic_epilogue_kernel(const double* __restrict__ joint, int K, int pad, int symmetric, double lamda, double eps,
+iic_epilogue_kernel(const double* __restrict__ joint, int n_slots, int K, int pad, int symmetric, double lamda, double eps,
                     double n_pixels, float* __restrict__ loss, float* __restrict__ p00, float* __restrict__ p_ij,
                     float* __restrict__ djoint, double* __restrict__ gscratch) {
     extern __shared__ __align__(16) double sm[];
@@ -251,14 +251,21 @@ iic_epilogue_kernel(const double* __restrict__ joint, int K, int pad, int symmet
     auto JIDX = [&](int k1, int k2, int dd) { return (k1 * K + k2) * TT + dd; };
     auto PIDX = [&](int dd, int k1, int k2) { return (dd * K + k1) * K + k2; };
 
+    // batch-sharded multi-GPU form: `joint` holds one partial joint per rank ([n_slots][nj], written by the ranks themselves
+    // through peer memory); they are summed here in slot order, so every rank forms the identical global joint
+    auto JV = [&](int i) {
+        double t = joint[i];
+        for (int sl = 1; sl < n_slots; ++sl) t += joint[(size_t)sl * nj + i];
+        return t;
+    };
     double total = 1.0;
     if (pad > 0) {
         double mn = 1e300;
-        for (int i = tid; i < nj; i += nt) mn = fmin(mn, (double)joint[i]);
+        for (int i = tid; i < nj; i += nt) mn = fmin(mn, JV(i));
         mn = block_reduce_min(mn, red);
         for (int i = tid; i < nj; i += nt) {
             const int dd = i % TT, k2 = (i / TT) % K, k1 = i / (TT * K);
-            Bm[PIDX(dd, k1, k2)] = (double)joint[i] - mn + 1e-8;
+            Bm[PIDX(dd, k1, k2)] = JV(i) - mn + 1e-8;
         }
         __syncthreads();
         for (int dd = warp; dd < TT; dd += nwarp) {          // one warp per displacement
@@ -278,7 +285,7 @@ iic_epilogue_kernel(const double* __restrict__ joint, int K, int pad, int symmet
         total = block_reduce_sum(part, red);
         for (int i = tid; i < nj; i += nt) P[i] /= total;
     } else {
-        for (int i = tid; i < nj; i += nt) Bm[i] = (double)joint[i] / n_pixels;   // TT == 1: layouts coincide
+        for (int i = tid; i < nj; i += nt) Bm[i] = JV(i) / n_pixels;   // TT == 1: layouts coincide
         __syncthreads();
         for (int i = tid; i < nj; i += nt) {
             const int k2 = i % K, k1 = i / K;
@@ -694,7 +701,7 @@ size_t iic_epilogue_workspace_bytes(int K, int pad) {
     return b > 160 * 1024 ? b : 0;      // small problems keep everything in shared memory
 }
 
-int iic_epilogue(const double* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
+int iic_epilogue(const double* joint, int n_slots, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
                  float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     size_t smem = epilogue_scratch_doubles(K, pad) * sizeof(double);
     double* gscratch = nullptr;
@@ -709,8 +716,8 @@ int iic_epilogue(const double* joint, int K, int pad, int symmetric, float lamda
         if (e != cudaSuccess) { set_error("iic_epilogue smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr.set(smem);
     }
-    iic_epilogue_kernel<<<1, EPI_THREADS, smem, st>>>(joint, K, pad, symmetric, (double)lamda, (double)eps, n_pixels, loss, p00, p_ij,
-                                              djoint, gscratch);
+    iic_epilogue_kernel<<<1, EPI_THREADS, smem, st>>>(joint, n_slots, K, pad, symmetric, (double)lamda, (double)eps, n_pixels, loss, p00,
+                                                      p_ij, djoint, gscratch);
     CY_CHECK_LAUNCH("iic_epilogue");
     return CY_OK;
 }

@@ -34,8 +34,8 @@ from torch import Tensor
 
 from . import _lib as L
 
-__all__ = ["row_range", "gather_rank_major", "gather_rows_", "local_view_major", "make_joint_reduce", "ShardedSupConLoss",
-           "shard_iic_loss"]
+__all__ = ["row_range", "gather_rank_major", "gather_rows_", "local_view_major", "make_joint_reduce", "PeerExchange",
+           "ShardedSupConLoss", "shard_iic_loss"]
 
 
 def _ws(group):
@@ -86,14 +86,103 @@ def local_view_major(raw_local: Tensor, canonicalize) -> Tensor:
     return canonicalize(raw_local, raw_local.shape[0])
 
 
-def make_joint_reduce(group=None):
-    """callback for IIDSegmentationLoss: sum the raw joint over ranks; the pixel count scales with the world size
-    (equal per-rank batches, as under a DistributedSampler)."""
-    world, _ = _ws(group)
+class PeerExchange:
+    """Symmetric (peer-mapped) scratch of one process group: the ranks write into each other's buffers over NVLink with their
+    own kernels (cy_p2p_push) and meet at signal-pad barriers — no NCCL collective on the data path.
 
-    def reduce(joint: Tensor, n_pixels: float) -> float:
-        dist.all_reduce(joint, group=group)
-        return n_pixels * world
+    Built on ``torch.distributed._symmetric_memory`` (cuMem allocation + peer mapping + signal pads); the rendezvous is a
+    collective, so every rank must create / grow the exchange at the same call.  ``acquire(nbytes)`` returns the local view of
+    one of TWO alternating halves: rank A may already be writing step k+1's blocks into rank B's memory while B still reads
+    step k's — a half is reused only two steps later, after a barrier that every rank reaches behind its own readers."""
+
+    def __init__(self, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = _ws(group)
+        self.buf = None
+        self.hdl = None
+        self.half_bytes = 0
+        self.step = 0
+
+    @staticmethod
+    def available() -> bool:
+        try:
+            import torch.distributed._symmetric_memory  # noqa: F401
+            return True
+        except Exception:  # noqa
+            return False
+
+    def _grow(self, nbytes: int, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.half_bytes = (nbytes + (1 << 20) - 1) >> 20 << 20
+        self.buf = symm_mem.empty(2 * self.half_bytes, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.ptrs_dev = int(self.hdl.buffer_ptrs_dev)
+        self.step = 0
+
+    def acquire(self, nbytes: int, device):
+        """-> (local uint8 view of this step's half, its byte offset inside the symmetric buffer)"""
+        if self.buf is None or nbytes > self.half_bytes:
+            self._grow(nbytes, device)
+        off = (self.step & 1) * self.half_bytes
+        self.step += 1
+        return self.buf[off:off + self.half_bytes], off
+
+    def push(self, ranges):
+        """copy the (offset, bytes) ranges of the local buffer into every peer's buffer (offsets relative to the whole
+        symmetric buffer), then barrier: on return (in stream order) every rank's ranges are visible here"""
+        import ctypes
+        lib = L.lib()
+        flat = []
+        for off, nb in ranges:
+            assert off % 16 == 0 and nb % 16 == 0, (off, nb)
+            flat += [off, nb]
+        arr = (ctypes.c_ulonglong * len(flat))(*flat)
+        L.check(lib.cy_p2p_push(self.ptrs_dev, self.world, self.rank, arr, len(ranges), L.stream_ptr(self.buf.device)), "cy_p2p_push")
+        self.hdl.barrier(channel=0)
+
+
+def make_joint_reduce(group=None, exchange: str = "auto"):
+    """callback for IIDSegmentationLoss: make the raw joint global; the pixel count scales with the world size (equal per-rank
+    batches, as under a DistributedSampler).  Protocol: ``reduce(compute_into, shape, n_pixels, device) -> (joint, n_slots,
+    n_pixels)`` where ``compute_into(out)`` runs cy_iic_joint into ``out``.
+
+    exchange "p2p" (default when symmetric memory is available): every rank computes its partial joint straight into ITS
+    slot of a peer-mapped [world, K,K,T,T] array, pushes the slot to all peers (cy_p2p_push + signal-pad barrier) and
+    cy_iic_epilogue sums the slots in rank order — identical bits on every rank, no NCCL call.  "nccl": all-reduce in place."""
+    world, rank = _ws(group)
+    state = {"px": None, "failed": exchange == "nccl"}
+
+    def reduce(compute_into, shape, n_pixels: float, device):
+        nj = 1
+        for v in shape:
+            nj *= v
+        # (a captured graph would replay ONE half of the alternating buffer every step: captures take the collective form)
+        if not state["failed"] and world > 1 and not torch.cuda.is_current_stream_capturing():
+            try:
+                if state["px"] is None:
+                    if not PeerExchange.available():
+                        raise RuntimeError("torch.distributed._symmetric_memory is not available")
+                    state["px"] = PeerExchange(group)
+                px = state["px"]
+                slot_bytes = (nj * 8 + 15) // 16 * 16
+                view, base = px.acquire(world * slot_bytes, device)
+                slots = view[:world * slot_bytes].view(torch.float64).view(world, slot_bytes // 8)
+                compute_into(slots[rank, :nj].view(shape))
+                px.push([(base + rank * slot_bytes, slot_bytes)])
+                if slot_bytes == nj * 8:
+                    return slots.view(world, *shape), world, n_pixels * world
+                return slots[:, :nj].contiguous().view(world, *shape), world, n_pixels * world
+            except Exception as e:  # noqa  (rendezvous refused on this box: fall back for good, every rank alike)
+                if exchange == "p2p":
+                    raise
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable ({e}); using NCCL all-reduce for the IIC joint")
+                state["failed"] = True
+        joint = torch.empty(shape, dtype=torch.float64, device=device)
+        compute_into(joint)
+        if world > 1:
+            dist.all_reduce(joint, group=group)
+        return joint, 1, n_pixels * world
 
     return reduce
 
@@ -105,7 +194,7 @@ class _ShardedInfoNCE(torch.autograd.Function):
     why); ``backward`` only scatters the stored rows back to the two views, times the upstream gradient."""
 
     @staticmethod
-    def forward(ctx, f1, f2, labels_loc, order, inv_t, variant, gamma, path, group, check, design, overflow, status):
+    def forward(ctx, f1, f2, labels_loc, order, inv_t, variant, gamma, path, group, check, design, overflow, status, px):
         from .losses.contrastive import _unit_scale
         lib = L.lib()
         world, rank = _ws(group)
@@ -118,18 +207,29 @@ class _ShardedInfoNCE(torch.autograd.Function):
         need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         with L.guard(f1):
             st = L.stream_ptr(dev)
-            z_all = torch.empty(N, d, dtype=f1.dtype, device=dev)
-            labels_all = torch.empty(N, dtype=torch.int32, device=dev)
-            xstat = torch.empty(N, 4, dtype=torch.float32, device=dev)
+            esz = f1.element_size()
+            if px is not None:
+                # peer-memory exchange: the three gathered arrays live in this step's half of the symmetric buffer
+                zb, lb, xb = N * d * esz, N * 4, N * 16
+                view, base = px.acquire(zb + lb + xb, dev)
+                z_all = view[:zb].view(f1.dtype).view(N, d)
+                labels_all = view[zb:zb + lb].view(torch.int32)
+                xstat = view[zb + lb:zb + lb + xb].view(torch.float32).view(N, 4)
+            else:
+                z_all = torch.empty(N, d, dtype=f1.dtype, device=dev)
+                labels_all = torch.empty(N, dtype=torch.int32, device=dev)
+                xstat = torch.empty(N, 4, dtype=torch.float32, device=dev)
             stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev)
             out8 = torch.empty(8, dtype=torch.float32, device=dev)
             bad = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
-            esz = f1.element_size()
             L.check(lib.cy_infonce_pack(f1.data_ptr(), f2.data_ptr(), dt, n_loc, d, f1.stride(0), f2.stride(0), L.ptr(order),
                                         z_all.data_ptr() + rb * d * esz, L.ptr(bad), None, st), "cy_infonce_pack")
             labels_all[rb:re].copy_(labels_loc)
-            gather_rows_(z_all, group)
-            gather_rows_(labels_all, group)
+            if px is not None:      # ONE launch pushes this rank's embedding rows and labels to every peer; then the barrier
+                px.push([(base + rb * d * esz, rows_loc * d * esz), (base + zb + rb * 4, rows_loc * 4)])
+            else:
+                gather_rows_(z_all, group)
+                gather_rows_(labels_all, group)
             ws_bytes = lib.cy_infonce_workspace_bytes(N, d, dt, variant, path)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             zp, lp = z_all.data_ptr(), labels_all.data_ptr()
@@ -138,7 +238,10 @@ class _ShardedInfoNCE(torch.autograd.Function):
             if variant != L.CY_SUPCON:
                 L.check(lib.cy_infonce_fwd_pass2(zp, dt, N, d, d, lp, None, rb, re, inv_t, variant, gamma, path, stats.data_ptr(),
                                                  xstat.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd_pass2")
-            gather_rows_(xstat, group)
+            if px is not None:
+                px.push([(base + zb + lb + rb * 16, rows_loc * 16)])
+            else:
+                gather_rows_(xstat, group)
             L.check(lib.cy_infonce_loss(N, variant, xstat.data_ptr(), out8.data_ptr(), L.ptr(bad), L.ptr(overflow), ws.data_ptr(),
                                         ws_bytes, st), "cy_infonce_loss")
             loss = out8[0].clone()
@@ -176,7 +279,7 @@ class _ShardedInfoNCE(torch.autograd.Function):
             g2 = torch.empty(n_loc, d, dtype=dz_loc.dtype, device=dev)
             L.check(lib.cy_infonce_unpack(dz_loc.data_ptr(), L.dtype_code(dz_loc), n_loc, d, d, L.ptr(order), g1.data_ptr(),
                                           g2.data_ptr(), None, None, gscale.data_ptr(), L.stream_ptr(dev)), "cy_infonce_unpack")
-        return g1, g2, None, None, None, None, None, None, None, None, None, None, None
+        return g1, g2, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 def _strip_contribution_reduce_scatter(z_all, labels_all, xstat, gscale, inv_t, variant, gamma, rb, re, group):
@@ -223,7 +326,7 @@ class ShardedSupConLoss(torch.nn.Module):
     collective — SURVEY.md §8e (ii)) or "reduce_scatter" (north_star's design (i), for comparison)."""
 
     def __init__(self, temperature=0.07, exclude_other_pos=False, *, group=None, grad_scale: float = 1.0, path: str = "auto",
-                 deferred_checks: bool = False, backward_design: str = "local"):
+                 deferred_checks: bool = False, backward_design: str = "local", exchange: str = "auto"):
         super().__init__()
         self._t = temperature
         self._group = group
@@ -239,6 +342,11 @@ class ShardedSupConLoss(torch.nn.Module):
         self._path = {"auto": L.CY_PATH_AUTO, "simt": L.CY_PATH_SIMT, "tcgen05": L.CY_PATH_TCGEN05}[path]
         self._cache = None
         self._status = None
+        # exchange: "p2p" = the ranks' own stores over NVLink peer memory + signal-pad barriers (PeerExchange), "nccl" = three
+        # in-place all-gathers, "auto" = p2p when torch's symmetric memory rendezvous works on this box, else nccl
+        assert exchange in ("auto", "p2p", "nccl")
+        self._exchange = exchange
+        self._px = None
 
     def _local_labels(self, target, n_local, rank, device, sort):
         """canonical labels of the owned row block (+ the local sort), cached while the same label tensor comes back"""
@@ -292,8 +400,9 @@ class ShardedSupConLoss(torch.nn.Module):
             if self._status is None:
                 self._status = _HostStatus()
             status = self._status
+        px = self._peer_exchange(rows_loc % 4 == 0 and (rows_loc * d * proj_feat1.element_size()) % 16 == 0)
         loss, out8 = _ShardedInfoNCE.apply(f1, f2, labels_loc, order, float(1.0 / self._t), self._variant, float(self._gamma),
-                                           self._path, self._group, __debug__, self._design, overflow, status)
+                                           self._path, self._group, __debug__, self._design, overflow, status, px)
         if status is None:
             cur = out8[3:6].detach().clone()          # [non-finite terms, un-normalised rows, label overflows]
             cur[0] = cur[0] + torch.isnan(loss.detach()).to(cur.dtype)
@@ -311,6 +420,26 @@ class ShardedSupConLoss(torch.nn.Module):
             raise RuntimeError(loss)
         return loss * self._grad_scale if self._grad_scale != 1.0 else loss
 
+    def _peer_exchange(self, aligned: bool):
+        # (a captured graph would replay ONE half of the alternating buffer every step: captures take the collective form)
+        if self._exchange == "nccl" or not aligned or _ws(self._group)[0] == 1 or torch.cuda.is_current_stream_capturing():
+            return None
+        if self._px is None:
+            try:
+                if not PeerExchange.available():
+                    raise RuntimeError("torch.distributed._symmetric_memory is not available")
+                px = PeerExchange(self._group)
+                px._grow(1 << 20, torch.device("cuda", torch.cuda.current_device()))      # rendezvous now: fail here, not mid-step
+                self._px = px
+            except Exception as e:  # noqa  (same outcome on every rank of one box)
+                if self._exchange == "p2p":
+                    raise
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable ({e}); ShardedSupConLoss uses NCCL all-gathers")
+                self._exchange = "nccl"
+                return None
+        return self._px
+
     def raise_if_flagged(self):
         """deferred_checks mode: one host read of this rank's accumulated (un-normalised rows, NaN losses) counters"""
         if self._flags is None:
@@ -324,7 +453,8 @@ class ShardedSupConLoss(torch.nn.Module):
             raise RuntimeError(f"loss was NaN in {nan} forward call(s)")
 
 
-def shard_iic_loss(criterion, group=None):
-    """Make an ``IIDSegmentationLoss`` batch-sharded: its raw joint is all-reduced over ``group`` before the epilogue."""
-    criterion._reduce_joint = make_joint_reduce(group)
+def shard_iic_loss(criterion, group=None, exchange: str = "auto"):
+    """Make an ``IIDSegmentationLoss`` batch-sharded: its raw joint is summed over ``group`` before the epilogue
+    (``exchange``: "auto" | "p2p" | "nccl", see make_joint_reduce)."""
+    criterion._reduce_joint = make_joint_reduce(group, exchange)
     return criterion

@@ -151,15 +151,19 @@ class _IIDSegFunction(torch.autograd.Function):
         buf = torch.empty(1 + K * K + nj, dtype=torch.float32, device=x.device)      # one allocation for the small outputs
         loss, p00 = buf[:1], buf[1:1 + K * K].view(K, K)
         djoint = buf[1 + K * K:].view(K, K, T, T)
-        joint = _joint_forward(x, y, padding)                                        # [K, K, T, T] float64
         n_pixels = float(B * H * W)
-        if reduce_joint is not None:
-            n_pixels = reduce_joint(joint, n_pixels)
+        n_slots = 1
+        if reduce_joint is None:
+            joint = _joint_forward(x, y, padding)                                    # [K, K, T, T] float64
+        else:
+            # batch-sharded: the callback supplies where the partial joint is written and makes the other ranks' partials
+            # visible — an NCCL all-reduce in place (1 slot) or peer-memory stores into per-rank slots that the epilogue sums
+            joint, n_slots, n_pixels = reduce_joint(lambda out: _joint_forward(x, y, padding, out), (K, K, T, T), n_pixels, x.device)
         with L.guard(x):
             ws_bytes = lib.cy_iic_epilogue_workspace_bytes(K, padding)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
-            L.check(lib.cy_iic_epilogue(joint.data_ptr(), K, padding, int(bool(symmetric)), float(lamda), float(eps), n_pixels,
-                                        loss.data_ptr(), p00.data_ptr(), None, djoint.data_ptr(), L.ptr(ws), ws_bytes,
+            L.check(lib.cy_iic_epilogue(joint.data_ptr(), n_slots, K, padding, int(bool(symmetric)), float(lamda), float(eps),
+                                        n_pixels, loss.data_ptr(), p00.data_ptr(), None, djoint.data_ptr(), L.ptr(ws), ws_bytes,
                                         L.stream_ptr(x.device)), "cy_iic_epilogue")
         ctx.save_for_backward(x, y, djoint)
         ctx.padding = padding
@@ -212,7 +216,7 @@ class _IIDSegMultiFunction(torch.autograd.Function):
             loss_p, p00_p, dj_p, j_p = o, o + 4, o + 4 * (1 + K * K), joints.data_ptr() + 8 * s * nj
             L.check(lib.cy_iic_joint(x.data_ptr(), y.data_ptr(), dt, B, K, H, W, padding, j_p, ws.data_ptr(), ws_bytes, st),
                     "cy_iic_joint")
-            L.check(lib.cy_iic_epilogue(j_p, K, padding, int(bool(symmetric)), float(lamda), float(eps), float(B * H * W),
+            L.check(lib.cy_iic_epilogue(j_p, 1, K, padding, int(bool(symmetric)), float(lamda), float(eps), float(B * H * W),
                                         loss_p, p00_p, None, dj_p, L.ptr(ews), ews_bytes, st), "cy_iic_epilogue")
         ctx.save_for_backward(buf, *maps)
         ctx.cfg = (padding, S, K, T, per)

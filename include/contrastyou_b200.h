@@ -185,15 +185,29 @@ int cy_iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, i
  * Outputs: loss[1]; p00 [K,K] = p_i_j[0][0] (:152, get_joint_matrix); p_ij [T,T,K,K] (may be NULL);
  * djoint [K,K,T,T] = dLoss/dJoint (may be NULL).  n_pixels = global B*H*W.  One CTA, fp64; its few arrays live in
  * shared memory unless K*K*T*T is large, in which case cy_iic_epilogue_workspace_bytes() is non-zero and the caller
- * passes that much device scratch. */
+ * passes that much device scratch.  n_slots >= 1: `joint` is [n_slots][K,K,T,T] and the slots are summed first, in slot
+ * order — the peer-memory form of the multi-GPU all-reduce: every rank pushes its partial joint into slot `rank` of every
+ * peer (cy_p2p_push), and each rank then forms the identical global joint inside this kernel. */
 size_t cy_iic_epilogue_workspace_bytes(int K, int pad);
-int cy_iic_epilogue(const double* joint, int K, int pad, int symmetric, float lamda, float eps, double n_pixels,
-                    float* loss, float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes,
-                    void* stream);
+int cy_iic_epilogue(const double* joint, int n_slots, int K, int pad, int symmetric, float lamda, float eps,
+                    double n_pixels, float* loss, float* p00, float* p_ij, float* djoint, void* workspace,
+                    size_t workspace_bytes, void* stream);
 
 /* Backward: dx, dy [B,K,H,W] (dtype of x) = gscale[0] * adjoint of cy_iic_joint applied to djoint. */
 int cy_iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
                const float* gscale, void* dx, void* dy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Exchange over NVLink peer memory (row-sharded InfoNCE, batch-sharded IIC).  The reference has no distributed path; the
+ * north_star's all-gather of embeddings / statistics and all-reduce of the joint are done here by the ranks' own stores
+ * into each other's buffers instead of NCCL collectives.
+ *
+ *   peer_bufs  DEVICE array [world] of base pointers: the same symmetric allocation as mapped on every rank
+ *              (torch.distributed._symmetric_memory: buffer_ptrs_dev); peer_bufs[rank] is the local buffer
+ *   ranges     HOST array of n_ranges (<= 4) pairs (byte offset, byte count), both multiples of 16
+ * Copies every range from the local buffer to the same offsets of all OTHER ranks' buffers (push all-gather: each rank
+ * owns the ranges it pushes).  Completion on the peers is established by the caller's signal-pad barrier after the call. */
+int cy_p2p_push(void* const* peer_bufs, int world, int rank, const unsigned long long* ranges, int n_ranges, void* stream);
 
 #ifdef __cplusplus
 }

@@ -94,9 +94,11 @@ def _worker(rank, port, results):
         x = torch.randn(2 * WORLD, 5, 9, 11, generator=g, dtype=torch.float64).softmax(1).numpy()
         y = torch.randn(2 * WORLD, 5, 9, 11, generator=g, dtype=torch.float64).softmax(1).numpy()
         bs = slice(2 * rank, 2 * rank + 2)
-        J = torch.from_numpy(OM.raw_joint_2d(x[bs], y[bs], 1))
-        npx = cyd.make_joint_reduce()(J, float(2 * 9 * 11))
-        assert npx == 2 * WORLD * 9 * 11
+        J_loc = torch.from_numpy(OM.raw_joint_2d(x[bs], y[bs], 1))
+        # the callback protocol of IIDSegmentationLoss (collective form; the peer-memory form needs CUDA)
+        J, n_slots, npx = cyd.make_joint_reduce(exchange="nccl")(lambda out: out.copy_(J_loc), tuple(J_loc.shape), float(2 * 9 * 11),
+                                                                   torch.device("cpu"))
+        assert npx == 2 * WORLD * 9 * 11 and n_slots == 1 and J.dtype == torch.float64
         np.testing.assert_allclose(J.numpy(), OM.raw_joint_2d(x, y, 1), rtol=1e-13)
         results[rank] = "ok"
     except Exception as e:  # noqa
