@@ -40,11 +40,16 @@ SIGNATURES = {
     "cy_labels_canonicalize": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp]),
     "cy_infonce_pack": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "cy_infonce_unpack": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cy_infonce_pack_gather": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "cy_infonce_unpack_scatter": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "cy_iic_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "cy_iic_joint": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "cy_iic_epilogue_workspace_bytes": (_sz, [_i32, _i32]),
     "cy_iic_epilogue": (_i32, [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _f64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cy_iic_bwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "cy_imsat_workspace_bytes": (_sz, [_i32]),
+    "cy_imsat_fwd": (_i32, [_vp, _i32, _i64, _i32, _i64, _f32, _vp, _vp, _vp, _sz, _vp]),
+    "cy_imsat_bwd": (_i32, [_vp, _i32, _i64, _i32, _i64, _f32, _vp, _vp, _vp, _vp]),
     "cy_p2p_push": (_i32, [_vp, _i32, _i32, _vp, _i32, _vp]),
 }
 

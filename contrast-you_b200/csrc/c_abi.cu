@@ -52,8 +52,10 @@ int infonce_bwd_simt(const void*, int, int64_t, int64_t, int64_t, const int32_t*
                      float, const float*, const float*, void*, int64_t, cudaStream_t);
 int infonce_masks(int64_t, const int32_t*, const uint8_t*, float*, float*, cudaStream_t);
 int labels_canonicalize(const void*, int, int64_t, int32_t*, int32_t*, cudaStream_t);
-int infonce_pack(const void*, const void*, int, int64_t, int64_t, int64_t, int64_t, const int64_t*, void*, int*, float*, cudaStream_t);
-int infonce_unpack(const void*, int, int64_t, int64_t, int64_t, const int64_t*, void*, void*, const void*, const float*, const float*, cudaStream_t);
+int infonce_pack(const void*, const void*, int, int64_t, int64_t, int64_t, int64_t, const int64_t*, void*, int*, float*, const int64_t*, int64_t,
+                 cudaStream_t);
+int infonce_unpack(const void*, int, int64_t, int64_t, int64_t, const int64_t*, void*, void*, const void*, const float*, const float*,
+                   const int64_t*, int64_t, cudaStream_t);
 // infonce_tc.cu
 bool infonce_tc_supported(int dtype, int64_t N, int64_t d, int64_t ldz, const uint8_t* codes, int variant);
 size_t infonce_tc_workspace_bytes(int64_t N, int64_t d);
@@ -71,6 +73,10 @@ size_t iic_workspace_bytes(int, int, int, int, int);
 int iic_joint(const void*, const void*, int, int, int, int, int, int, double*, void*, size_t, cudaStream_t);
 size_t iic_epilogue_workspace_bytes(int, int);
 int iic_epilogue(const double*, int, int, int, int, float, float, double, float*, float*, float*, float*, void*, size_t, cudaStream_t);
+// imsat.cu
+size_t imsat_workspace_bytes(int);
+int imsat_fwd(const void*, int, int64_t, int, int64_t, float, float*, float*, void*, size_t, cudaStream_t);
+int imsat_bwd(const void*, int, int64_t, int, int64_t, float, const float*, const float*, void*, cudaStream_t);
 // p2p.cu
 int p2p_push(void* const*, int, int, const unsigned long long*, int, cudaStream_t);
 int iic_bwd(const void*, const void*, int, int, int, int, int, int, const float*, const float*, void*, void*, cudaStream_t);
@@ -219,7 +225,16 @@ int cy_infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_
     CY_NVTX("cy_infonce_pack");
     CY_CHECK_ARG(f1 && f2 && z && n >= 1 && d >= 1 && ld1 >= d && ld2 >= d, "bad arguments");
     CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
-    return infonce_pack(f1, f2, dtype, n, d, ld1, ld2, order, z, bad_rows, inv_norm, reinterpret_cast<cudaStream_t>(stream));
+    return infonce_pack(f1, f2, dtype, n, d, ld1, ld2, order, z, bad_rows, inv_norm, nullptr, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_infonce_pack_gather(const void* map1, const void* map2, int dtype, int64_t n, int64_t d, const int64_t* pix_off,
+                           int64_t chan_stride, const int64_t* order, void* z, int32_t* bad_rows, void* stream) {
+    CY_NVTX("cy_infonce_pack_gather");
+    CY_CHECK_ARG(map1 && map2 && z && pix_off && n >= 1 && d >= 1 && chan_stride >= 1, "bad arguments");
+    CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
+    return infonce_pack(map1, map2, dtype, n, d, 0, 0, order, z, bad_rows, nullptr, pix_off, chan_stride,
+                        reinterpret_cast<cudaStream_t>(stream));
 }
 
 int cy_infonce_unpack(const void* dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* order, void* g1,
@@ -228,7 +243,16 @@ int cy_infonce_unpack(const void* dz, int dtype, int64_t n, int64_t d, int64_t l
     CY_CHECK_ARG(dz && g1 && g2 && n >= 1 && d >= 1 && lddz >= d, "bad arguments");
     CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
     CY_CHECK_ARG((z == nullptr) == (inv_norm == nullptr), "z and inv_norm go together");
-    return infonce_unpack(dz, dtype, n, d, lddz, order, g1, g2, z, inv_norm, gscale, reinterpret_cast<cudaStream_t>(stream));
+    return infonce_unpack(dz, dtype, n, d, lddz, order, g1, g2, z, inv_norm, gscale, nullptr, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_infonce_unpack_scatter(const void* dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* order, void* gmap1,
+                              void* gmap2, const int64_t* pix_off, int64_t chan_stride, const float* gscale, void* stream) {
+    CY_NVTX("cy_infonce_unpack_scatter");
+    CY_CHECK_ARG(dz && gmap1 && gmap2 && pix_off && n >= 1 && d >= 1 && lddz >= d && chan_stride >= 1, "bad arguments");
+    CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
+    return infonce_unpack(dz, dtype, n, d, lddz, order, gmap1, gmap2, nullptr, nullptr, gscale, pix_off, chan_stride,
+                          reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t cy_iic_workspace_bytes(int B, int K, int H, int W, int pad) {
@@ -264,6 +288,24 @@ int cy_iic_epilogue(const double* joint, int n_slots, int K, int pad, int symmet
     CY_CHECK_ARG(joint && loss && p00 && K >= 1 && pad >= 0 && n_slots >= 1, "bad arguments");
     return iic_epilogue(joint, n_slots, K, pad, symmetric, lamda, eps, n_pixels, loss, p00, p_ij, djoint, workspace, workspace_bytes,
                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t cy_imsat_workspace_bytes(int K) { return K >= 1 ? imsat_workspace_bytes(K) : 0; }
+
+int cy_imsat_fwd(const void* pred, int dtype, int64_t N, int K, int64_t S, float eps, float* out2, float* q, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+    CY_NVTX("cy_imsat_fwd");
+    CY_CHECK_ARG(pred && out2 && q && N >= 1 && S >= 1, "bad arguments");
+    CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
+    return imsat_fwd(pred, dtype, N, K, S, eps, out2, q, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_imsat_bwd(const void* pred, int dtype, int64_t N, int K, int64_t S, float eps, const float* q, const float* g2, void* grad,
+                 void* stream) {
+    CY_NVTX("cy_imsat_bwd");
+    CY_CHECK_ARG(pred && q && g2 && grad && N >= 1 && S >= 1, "bad arguments");
+    CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
+    return imsat_bwd(pred, dtype, N, K, S, eps, q, g2, grad, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int cy_p2p_push(void* const* peer_bufs, int world, int rank, const unsigned long long* ranges, int n_ranges, void* stream) {

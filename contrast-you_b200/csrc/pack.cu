@@ -20,15 +20,32 @@ template <int ESIZE>
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const uint8_t* __restrict__ f1, const uint8_t* __restrict__ f2, int dtype, int64_t n, int64_t d,
                  int64_t ld1, int64_t ld2, const int64_t* __restrict__ order, uint8_t* __restrict__ z, int* __restrict__ bad_rows,
-                 float* __restrict__ inv_norm) {
+                 float* __restrict__ inv_norm, const int64_t* __restrict__ pix_off, int64_t chan_stride) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= 2 * n) return;
     const int64_t src = order ? order[row] : row;
-    const uint8_t* s = src < n ? f1 + src * ld1 * ESIZE : f2 + (src - n) * ld2 * ESIZE;
     uint8_t* o = z + row * d * ESIZE;
-    const bool vec = ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(o)) & 15) == 0 && (d * ESIZE) % 16 == 0;
     float ss = 0.f;
+    if (pix_off) {
+        // dense-feature gather fused into the pack (semi_seg/hooks/infonce.py:31-46): row = the C-vector of one sampled pixel of
+        // a [B, C, h, w] map, element c at pix_off[i] + c * chan_stride (the same pixel list serves both views)
+        const int64_t i = src < n ? src : src - n;
+        const uint8_t* base = (src < n ? f1 : f2) + pix_off[i] * ESIZE;
+        for (int64_t c = lane; c < d; c += 32) {
+            const float a = ld_as_float(base, dtype, c * chan_stride);
+            st_from_float(o, dtype, c, a);
+            ss = fmaf(a, a, ss);
+        }
+        ss = warp_sum(ss);
+        if (lane == 0 && bad_rows) {
+            const float nrm = round_to_dtype(sqrtf(ss), dtype);
+            if (!(fabsf(nrm - 1.f) <= 1e-8f + 1e-5f)) atomicAdd(bad_rows, 1);
+        }
+        return;
+    }
+    const uint8_t* s = src < n ? f1 + src * ld1 * ESIZE : f2 + (src - n) * ld2 * ESIZE;
+    const bool vec = ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(o)) & 15) == 0 && (d * ESIZE) % 16 == 0;
     if (inv_norm) {
         // fused F.normalize (contrastyou/projectors/nn.py:47-54, heads.py:20): z = f / max(||f||_2, 1e-12).  Two sweeps over
         // the row (the second one hits L1); the reciprocal norm is kept for the adjoint.
@@ -106,13 +123,19 @@ template <int ESIZE>
 __global__ void __launch_bounds__(256)
 unpack_rows_kernel(const uint8_t* __restrict__ dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* __restrict__ order,
                    uint8_t* __restrict__ g1, uint8_t* __restrict__ g2, const uint8_t* __restrict__ z, const float* __restrict__ inv_norm,
-                   const float* __restrict__ gscale) {
+                   const float* __restrict__ gscale, const int64_t* __restrict__ pix_off, int64_t chan_stride) {
     const int lane = threadIdx.x & 31;
     const float gs = gscale ? gscale[0] : 1.f;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= 2 * n) return;
     const int64_t dst = order ? order[row] : row;
     const uint8_t* s = dz + row * lddz * ESIZE;
+    if (pix_off) {      // adjoint of the fused gather: the sampled pixels of one image are distinct, so plain stores into zeroed maps
+        const int64_t i = dst < n ? dst : dst - n;
+        uint8_t* base = (dst < n ? g1 : g2) + pix_off[i] * ESIZE;
+        for (int64_t c = lane; c < d; c += 32) st_from_float(base, dtype, c * chan_stride, ld_as_float(s, dtype, c) * gs);
+        return;
+    }
     uint8_t* o = dst < n ? g1 + dst * d * ESIZE : g2 + (dst - n) * d * ESIZE;
     if (inv_norm) {
         // adjoint of z = f / ||f||:  g = (dz - z (z . dz)) / ||f||
@@ -143,23 +166,23 @@ unpack_rows_kernel(const uint8_t* __restrict__ dz, int dtype, int64_t n, int64_t
 }  // namespace
 
 int infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_t d, int64_t ld1, int64_t ld2, const int64_t* order,
-                 void* z, int* bad_rows, float* inv_norm, cudaStream_t st) {
+                 void* z, int* bad_rows, float* inv_norm, const int64_t* pix_off, int64_t chan_stride, cudaStream_t st) {
     const unsigned grid = (unsigned)((2 * n + 7) / 8);
     if (dtype == CY_F32)
-        pack_rows_kernel<4><<<grid, 256, 0, st>>>((const uint8_t*)f1, (const uint8_t*)f2, dtype, n, d, ld1, ld2, order, (uint8_t*)z, bad_rows, inv_norm);
+        pack_rows_kernel<4><<<grid, 256, 0, st>>>((const uint8_t*)f1, (const uint8_t*)f2, dtype, n, d, ld1, ld2, order, (uint8_t*)z, bad_rows, inv_norm, pix_off, chan_stride);
     else
-        pack_rows_kernel<2><<<grid, 256, 0, st>>>((const uint8_t*)f1, (const uint8_t*)f2, dtype, n, d, ld1, ld2, order, (uint8_t*)z, bad_rows, inv_norm);
+        pack_rows_kernel<2><<<grid, 256, 0, st>>>((const uint8_t*)f1, (const uint8_t*)f2, dtype, n, d, ld1, ld2, order, (uint8_t*)z, bad_rows, inv_norm, pix_off, chan_stride);
     CY_CHECK_LAUNCH("infonce_pack");
     return CY_OK;
 }
 
 int infonce_unpack(const void* dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* order, void* g1, void* g2,
-                   const void* z, const float* inv_norm, const float* gscale, cudaStream_t st) {
+                   const void* z, const float* inv_norm, const float* gscale, const int64_t* pix_off, int64_t chan_stride, cudaStream_t st) {
     const unsigned grid = (unsigned)((2 * n + 7) / 8);
     if (dtype == CY_F32)
-        unpack_rows_kernel<4><<<grid, 256, 0, st>>>((const uint8_t*)dz, dtype, n, d, lddz, order, (uint8_t*)g1, (uint8_t*)g2, (const uint8_t*)z, inv_norm, gscale);
+        unpack_rows_kernel<4><<<grid, 256, 0, st>>>((const uint8_t*)dz, dtype, n, d, lddz, order, (uint8_t*)g1, (uint8_t*)g2, (const uint8_t*)z, inv_norm, gscale, pix_off, chan_stride);
     else
-        unpack_rows_kernel<2><<<grid, 256, 0, st>>>((const uint8_t*)dz, dtype, n, d, lddz, order, (uint8_t*)g1, (uint8_t*)g2, (const uint8_t*)z, inv_norm, gscale);
+        unpack_rows_kernel<2><<<grid, 256, 0, st>>>((const uint8_t*)dz, dtype, n, d, lddz, order, (uint8_t*)g1, (uint8_t*)g2, (const uint8_t*)z, inv_norm, gscale, pix_off, chan_stride);
     CY_CHECK_LAUNCH("infonce_unpack");
     return CY_OK;
 }

@@ -205,9 +205,13 @@ class _FusedInfoNCE(torch.autograd.Function):
     backward = cy_infonce_unpack: scatter dz back to the two views, times the actual upstream gradient."""
 
     @staticmethod
-    def forward(ctx, f1, f2, labels, order, inv_t, variant, gamma, path, check_norm, normalize, overflow, status):
+    def forward(ctx, f1, f2, labels, order, inv_t, variant, gamma, path, check_norm, normalize, overflow, status, gather=None):
         lib = L.lib()
-        n, d = f1.shape
+        if gather is None:
+            n, d = f1.shape
+        else:       # dense maps [B, C, h, w] + the sampled pixels' element offsets: rows are gathered inside the pack kernel
+            pix_off, chan_stride = gather
+            n, d = pix_off.numel(), f1.shape[1]
         N = 2 * n
         dev = f1.device
         dt = L.dtype_code(f1)
@@ -217,8 +221,12 @@ class _FusedInfoNCE(torch.autograd.Function):
             z = torch.empty(N, d, dtype=f1.dtype, device=dev)
             bad = torch.zeros(1, dtype=torch.int32, device=dev) if (check_norm and not normalize) else None
             inv_norm = torch.empty(N, dtype=torch.float32, device=dev) if normalize else None
-            L.check(lib.cy_infonce_pack(f1.data_ptr(), f2.data_ptr(), dt, n, d, f1.stride(0), f2.stride(0), L.ptr(order), z.data_ptr(),
-                                        L.ptr(bad), L.ptr(inv_norm), st), "cy_infonce_pack")
+            if gather is None:
+                L.check(lib.cy_infonce_pack(f1.data_ptr(), f2.data_ptr(), dt, n, d, f1.stride(0), f2.stride(0), L.ptr(order), z.data_ptr(),
+                                            L.ptr(bad), L.ptr(inv_norm), st), "cy_infonce_pack")
+            else:
+                L.check(lib.cy_infonce_pack_gather(f1.data_ptr(), f2.data_ptr(), dt, n, d, pix_off.data_ptr(), chan_stride, L.ptr(order),
+                                                   z.data_ptr(), L.ptr(bad), st), "cy_infonce_pack_gather")
             stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev)
             xstat = torch.empty(N, 4, dtype=torch.float32, device=dev)
             out8 = torch.empty(8, dtype=torch.float32, device=dev)
@@ -243,8 +251,10 @@ class _FusedInfoNCE(torch.autograd.Function):
                         "cy_infonce_bwd")
         ctx.shape = (n, d)
         ctx.has_order, ctx.normalize = order is not None, normalize
+        ctx.gather = None if gather is None else (chan_stride, tuple(f1.shape))
         if need_grad:
-            ctx.save_for_backward(dz, *([order] if order is not None else []), *([z, inv_norm] if normalize else []))
+            ctx.save_for_backward(dz, *([order] if order is not None else []), *([z, inv_norm] if normalize else []),
+                                  *([pix_off] if gather is not None else []))
         ctx.mark_non_differentiable(out8)
         return loss, out8
 
@@ -259,11 +269,20 @@ class _FusedInfoNCE(torch.autograd.Function):
         if gscale.dtype != torch.float32 or gscale.numel() != 1 or not gscale.is_contiguous():
             gscale = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         with L.guard(dz):
-            g1 = torch.empty(n, d, dtype=dz.dtype, device=dz.device)
-            g2 = torch.empty(n, d, dtype=dz.dtype, device=dz.device)
-            L.check(lib.cy_infonce_unpack(dz.data_ptr(), L.dtype_code(dz), n, d, d, L.ptr(order), g1.data_ptr(), g2.data_ptr(),
-                                          L.ptr(z), L.ptr(inv_norm), gscale.data_ptr(), L.stream_ptr(dz.device)), "cy_infonce_unpack")
-        return g1, g2, None, None, None, None, None, None, None, None, None, None
+            if ctx.gather is not None:
+                chan_stride, map_shape = ctx.gather
+                pix_off = saved[-1]
+                g1 = torch.zeros(map_shape, dtype=dz.dtype, device=dz.device)
+                g2 = torch.zeros(map_shape, dtype=dz.dtype, device=dz.device)
+                L.check(lib.cy_infonce_unpack_scatter(dz.data_ptr(), L.dtype_code(dz), n, d, d, L.ptr(order), g1.data_ptr(),
+                                                      g2.data_ptr(), pix_off.data_ptr(), chan_stride, gscale.data_ptr(),
+                                                      L.stream_ptr(dz.device)), "cy_infonce_unpack_scatter")
+            else:
+                g1 = torch.empty(n, d, dtype=dz.dtype, device=dz.device)
+                g2 = torch.empty(n, d, dtype=dz.dtype, device=dz.device)
+                L.check(lib.cy_infonce_unpack(dz.data_ptr(), L.dtype_code(dz), n, d, d, L.ptr(order), g1.data_ptr(), g2.data_ptr(),
+                                              L.ptr(z), L.ptr(inv_norm), gscale.data_ptr(), L.stream_ptr(dz.device)), "cy_infonce_unpack")
+        return g1, g2, None, None, None, None, None, None, None, None, None, None, None
 
 
 def tensor_core_eligible(z: Tensor, labels, codes, variant: int, path: int) -> bool:
@@ -312,9 +331,9 @@ class _ContrastBase(nn.Module):
     def _kernel_variant(self) -> int:
         return self._variant
 
-    def _prepare(self, proj_feat1, proj_feat2, target, mask, sort=False):
+    def _prepare(self, proj_feat1, proj_feat2, target, mask, sort=False, gather=None):
         L.require_cuda(proj_feat1, proj_feat2)
-        batch_size = proj_feat1.size(0)
+        batch_size = proj_feat1.size(0) if gather is None else gather[0].numel()
         device = proj_feat2.device
         labels = codes = None
         self._overflow = None
@@ -338,9 +357,9 @@ class _ContrastBase(nn.Module):
             # gradients come back in fp32 through the cast.  Outside autocast fp32 inputs keep full fp32 arithmetic.
             half = torch.get_autocast_dtype("cuda")
             proj_feat1, proj_feat2 = proj_feat1.to(half), proj_feat2.to(half)
-        fused = (proj_feat1.dim() == 2 and proj_feat1.dtype == proj_feat2.dtype and proj_feat1.device == proj_feat2.device
-                 and proj_feat1.dtype in (torch.float32, torch.bfloat16, torch.float16))
-        do_sort = bool(sort and fused and codes is None and self._sorts_rows(proj_feat1))
+        fused = (proj_feat1.dim() == (2 if gather is None else 4) and proj_feat1.dtype == proj_feat2.dtype
+                 and proj_feat1.device == proj_feat2.device and proj_feat1.dtype in (torch.float32, torch.bfloat16, torch.float16))
+        do_sort = bool(sort and fused and codes is None and self._sorts_rows(proj_feat1, batch_size))
         order = None
         hit = None
         if cacheable:
@@ -360,6 +379,7 @@ class _ContrastBase(nn.Module):
             if cacheable and self._overflow is None:   # (an entry made under an overflow counter would skip the check on a hit)
                 cache.put(target, batch_size, device, do_sort, (labels, order, sorted_labels))
         self._views = (proj_feat1.detach(), proj_feat2.detach(), labels, codes)      # lazy side channels (original row order)
+        self._view_gather = gather
         self._dbg_cache = {}
         normalize = bool(getattr(self, "_normalize_input", False))
         if not fused or codes is not None:
@@ -370,13 +390,18 @@ class _ContrastBase(nn.Module):
             assert is_normalized(proj_feat1) and is_normalized(proj_feat2), f"features need to be normalized first"
             z = torch.cat([proj_feat1, proj_feat2], dim=0)
             return None, (z, labels, codes)
-        f1 = proj_feat1 if proj_feat1.stride(1) == 1 else proj_feat1.contiguous()
-        f2 = proj_feat2 if proj_feat2.stride(1) == 1 else proj_feat2.contiguous()
+        if gather is not None:
+            f1, f2 = proj_feat1.contiguous(), proj_feat2.contiguous()
+        else:
+            f1 = proj_feat1 if proj_feat1.stride(1) == 1 else proj_feat1.contiguous()
+            f2 = proj_feat2 if proj_feat2.stride(1) == 1 else proj_feat2.contiguous()
         return (f1, f2, sorted_labels, order, normalize), None
 
-    def _evaluate(self, proj_feat1, proj_feat2, target, mask, gamma=1e6):
+    def _evaluate(self, proj_feat1, proj_feat2, target, mask, gamma=1e6, gather=None):
         """-> (loss, status): status = the 8 host floats of cy_infonce_loss (None with deferred_checks)"""
-        fused_args, general = self._prepare(proj_feat1, proj_feat2, target, mask, sort=True)
+        fused_args, general = self._prepare(proj_feat1, proj_feat2, target, mask, sort=True, gather=gather)
+        if gather is not None and general is not None:
+            raise ValueError("forward_dense takes two [B, C, h, w] maps of one floating dtype on one device (and no mask=)")
         variant = self._kernel_variant()
         deferred = bool(getattr(self, "_deferred_checks", False))
         if general is not None:
@@ -393,14 +418,14 @@ class _ContrastBase(nn.Module):
             if status is None:
                 status = self.__dict__["_status"] = _HostStatus()
         loss, out8 = _FusedInfoNCE.apply(f1, f2, labels, order, float(1.0 / self._t), int(variant), float(gamma), int(self._path),
-                                         __debug__, normalize, self._overflow, status)
+                                         __debug__, normalize, self._overflow, status, gather)
         self._out8 = out8
         return loss, (status.wait() if status is not None else None)
 
-    def _sorts_rows(self, f1) -> bool:
+    def _sorts_rows(self, f1, n) -> bool:
         """rows are sorted by label when the call runs on the tensor kernels: positives then sit in a few column tiles, the
         mask-free epilogue runs everywhere else and the second sweep of exclude / self-paced visits O(1) tiles per row block"""
-        n, d = f1.shape
+        d = f1.shape[1]
         variant = self._kernel_variant()
         ok = (f1.dtype in (torch.bfloat16, torch.float16) and d in (128, 256) and 2 * n >= 256
               and (variant == L.CY_SUPCON or 2 * n <= 4096 * 128))
@@ -450,6 +475,10 @@ class _ContrastBase(nn.Module):
             raise AttributeError(name)
         if name not in self._dbg_cache:
             f1, f2, labels, codes = self._views
+            if getattr(self, "_view_gather", None) is not None:      # dense form: the sampled pixels' C-vectors
+                pix, stride = self._view_gather
+                idx = pix[:, None] + torch.arange(f1.shape[1], device=pix.device)[None, :] * stride
+                f1, f2 = f1.reshape(-1)[idx], f2.reshape(-1)[idx]
             z = torch.cat([f1, f2], dim=0)
             if getattr(self, "_normalize_input", False):
                 z = torch.nn.functional.normalize(z, dim=1)
@@ -494,6 +523,19 @@ class SupConLoss1(_ContrastBase):
 
     def forward(self, proj_feat1, proj_feat2, target=None, mask: Tensor = None, **kwargs):
         loss, status = self._evaluate(proj_feat1, proj_feat2, target, mask)
+        self._host_checks(loss, status)
+        return loss
+
+    def forward_dense(self, feature_map1, feature_map2, pixel_offsets: Tensor, target=None):
+        """Dense-hook form (extension): ``self(region_extractor(map1), region_extractor(map2), target)``
+        of ``semi_seg/hooks/infonce.py:262-266`` with the point gather fused into the pack kernel.  ``feature_map*``:
+        [B, C, h, w] normalised dense projections of the two views; ``pixel_offsets``: int64 [n] element offsets
+        b*C*h*w + y*w + x of the sampled pixels (``sampling.region_pixel_offsets`` reproduces the hook's coordinates); the
+        same pixels are taken from both views, as the shared seed does in the hook.  target=None: SimCLR / self labels."""
+        assert feature_map1.dim() == 4 and feature_map1.shape == feature_map2.shape, (feature_map1.shape, feature_map2.shape)
+        b, c, h, w = feature_map1.shape
+        pix = pixel_offsets.to(device=feature_map1.device, dtype=torch.int64).contiguous()
+        loss, status = self._evaluate(feature_map1, feature_map2, target, None, gather=(pix, h * w))
         self._host_checks(loss, status)
         return loss
 

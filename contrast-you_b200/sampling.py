@@ -9,7 +9,7 @@ B x point_nums slices and a ``torch.stack``.
 import numpy as np
 import torch
 
-__all__ = ["region_coordinates", "region_extractor"]
+__all__ = ["region_coordinates", "region_extractor", "region_pixel_offsets"]
 
 
 def region_coordinates(batch: int, h: int, w: int, point_nums: int, seed: int) -> np.ndarray:
@@ -28,3 +28,11 @@ def region_extractor(normalize_features: torch.Tensor, *, point_nums=5, seed: in
     bi = torch.arange(b, device=normalize_features.device)[:, None].expand(b, point_nums)
     picked = normalize_features[bi, :, coords[..., 0], coords[..., 1]]       # [B, P, C]
     return picked.reshape(b * point_nums, c)
+
+
+def region_pixel_offsets(batch: int, channels: int, h: int, w: int, point_nums: int, seed: int) -> torch.Tensor:
+    """element offsets b*C*h*w + y*w + x of the hook's sampled pixels inside a contiguous [B, C, h, w] map, image-major in the
+    reference's point order — the pixel list ``SupConLoss1.forward_dense`` gathers inside its pack kernel"""
+    coords = region_coordinates(batch, h, w, point_nums, seed)                  # [B, P, (y, x)]
+    base = np.arange(batch, dtype=np.int64)[:, None] * (channels * h * w)
+    return torch.from_numpy((base + coords[..., 0] * w + coords[..., 1]).reshape(-1))

@@ -163,6 +163,18 @@ int cy_infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_
 int cy_infonce_unpack(const void* dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* order, void* g1,
                       void* g2, const void* z, const float* inv_norm, const float* gscale, void* stream);
 
+/* Dense-feature variant of the feeder: the gather of `region_extractor`
+ * (semi_seg/hooks/infonce.py:31-46, call sites :262-263) fused into the pack.  map1 / map2: [B, C, h, w] feature maps of the
+ * two views (the dense projector's output); row i of a view = the C-vector of one sampled pixel: element c at
+ * map[pix_off[i] + c * chan_stride] (pix_off [n] int64 = b*C*h*w + y*w + x, chan_stride = h*w; the same pixel list serves
+ * both views, like the shared seed in the hook).  Everything else as cy_infonce_pack (d = C).  The adjoint scatters dz into
+ * the caller's ZEROED [B, C, h, w] gradient maps (the sampled pixels of an image are distinct: plain stores). */
+int cy_infonce_pack_gather(const void* map1, const void* map2, int dtype, int64_t n, int64_t d, const int64_t* pix_off,
+                           int64_t chan_stride, const int64_t* order, void* z, int32_t* bad_rows, void* stream);
+int cy_infonce_unpack_scatter(const void* dz, int dtype, int64_t n, int64_t d, int64_t lddz, const int64_t* order,
+                              void* gmap1, void* gmap2, const int64_t* pix_off, int64_t chan_stride, const float* gscale,
+                              void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * IIC discrete-MI segmentation loss.  Replaces compute_joint_2D / compute_joint_2D_with_padding_zeros
  * (contrastyou/losses/discreteMI.py:225-261), IIDSegmentationLoss.forward (:139-165) and their autograd backward.
@@ -196,6 +208,20 @@ int cy_iic_epilogue(const double* joint, int n_slots, int K, int pad, int symmet
 /* Backward: dx, dy [B,K,H,W] (dtype of x) = gscale[0] * adjoint of cy_iic_joint applied to djoint. */
 int cy_iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
                const float* gscale, void* dx, void* dy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * IMSAT entropies.  Replaces imsat_loss / the marginal + conditional entropy pair of
+ * contrastyou/losses/discreteMI.py:275-297 (used by IMSATLoss :20-52 and IMSATDynamicWeight :55-87) and their autograd.
+ *   pred   [N, K, S] contiguous simplex over K (S = product of trailing dims; 1 for [N, K] classification outputs), K <= 64
+ *   out2   {marginal = H(mean_{n,s} pred), conditional = mean_{n,s} H(pred[n,:,s])},  H(p) = -sum_k p log(p + eps)
+ *   q      [K] class means, kept for the backward
+ * One streaming pass each way; per-block partial sums reduced in a fixed order.  g2 = device {dL/dmarginal, dL/dconditional}.
+ * ---------------------------------------------------------------------------------------------------------------- */
+size_t cy_imsat_workspace_bytes(int K);
+int cy_imsat_fwd(const void* pred, int dtype, int64_t N, int K, int64_t S, float eps, float* out2, float* q, void* workspace,
+                 size_t workspace_bytes, void* stream);
+int cy_imsat_bwd(const void* pred, int dtype, int64_t N, int K, int64_t S, float eps, const float* q, const float* g2,
+                 void* grad, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Exchange over NVLink peer memory (row-sharded InfoNCE, batch-sharded IIC).  The reference has no distributed path; the

@@ -598,6 +598,36 @@ def test_puiseg_golden(name):
     assert _relerr(y.grad.cpu().numpy(), g["grad_y"]) <= FP32_TOL
 
 
+def test_imsat_streaming_kernels_match_fixture_and_host_mirror():
+    """IMSATLoss / IMSATDynamicWeight on the streaming kernels (cy_imsat_fwd / _bwd) vs the reference
+    fixture (fp32 inputs: 1e-4 bar) and, on a segmentation-shaped map, vs the float64 host-side mirror"""
+    from contrast_you_b200.losses import IMSATLoss, IMSATDynamicWeight
+    g = load_golden("imsat")
+    x, y = _t(g["x"], grad=True), _t(g["y"], grad=True)
+    loss = IMSATLoss(lamda=float(g["lamda"]))(x, y)
+    loss.backward()
+    assert loss.item() == pytest.approx(float(g["loss_pair"]), rel=FP32_TOL)
+    assert _relerr(x.grad.cpu().numpy(), g["grad_x_pair"]) <= FP32_TOL
+    assert _relerr(y.grad.cpu().numpy(), g["grad_y_pair"]) <= FP32_TOL
+    x.grad = None
+    dyn = IMSATDynamicWeight(lamda=float(g["lamda_dynamic"])).to(DEV)
+    loss = dyn(x)
+    loss.backward()
+    assert loss.item() == pytest.approx(float(g["loss_dynamic"]), rel=FP32_TOL)
+    assert _relerr(x.grad.cpu().numpy(), g["grad_x_dynamic"]) <= FP32_TOL
+    assert float(dyn.dynamic_weight) == pytest.approx(float(g["dynamic_weight_after"]), rel=1e-5)
+    from contrast_you_b200.losses.siblings import imsat_loss
+    torch.manual_seed(8)
+    p = (2 * torch.randn(6, 10, 40, 56, device=DEV)).softmax(1).requires_grad_()
+    out = imsat_loss(p, lamda=0.7)
+    (out * 3.0).backward()
+    p64 = p.detach().cpu().double().requires_grad_()
+    ref = imsat_loss(p64, lamda=0.7)
+    (ref * 3.0).backward()
+    assert out.item() == pytest.approx(ref.item(), rel=FP32_TOL)
+    assert _relerr(p.grad.cpu().numpy(), p64.grad.numpy()) <= FP32_TOL
+
+
 # ------------------------------------------------------------------------------------------------ tensor-pipe IIC shapes
 @pytest.mark.parametrize("B,K,H,W,pad", [(3, 13, 50, 72, 1), (2, 4, 33, 128, 1), (2, 16, 40, 64, 1), (1, 10, 9, 32, 1),
                                           (2, 10, 30, 44, 2), (2, 5, 23, 36, 3), (1, 20, 40, 40, 1),
@@ -643,6 +673,51 @@ def test_pack_feeder_strided_views_and_unnormalised_rows():
     SupConLoss1()(bf[:128], bf[128:], target=list(range(128)))          # bf16 unit rows pass, as in the reference
     with pytest.raises(AssertionError):
         SupConLoss1()(bf[:128] * 1.02, bf[128:], target=list(range(128)))
+
+
+def test_dense_gather_fused_into_pack_equals_hook_route():
+    """SupConLoss1.forward_dense(map1, map2, pixel_offsets) == the dense hook's route
+    (region_extractor on both maps, then the criterion; semi_seg/hooks/infonce.py:262-266): loss, gradients w.r.t. the maps,
+    and the sampled coordinates themselves (pinned by tests/golden/regions.json on the CPU side)"""
+    from contrast_you_b200 import sampling
+    torch.manual_seed(41)
+    B, C, h, w, P, seed = 6, 64, 20, 20, 5, 123
+    m = torch.nn.functional.normalize(torch.randn(2 * B, C, h, w, device=DEV), dim=1)
+    m1, m2 = torch.chunk(m, 2, dim=0)                                   # contiguous halves of one tensor, as in the hook
+    a1, a2 = m1.detach().clone().requires_grad_(), m2.detach().clone().requires_grad_()
+    s1 = sampling.region_extractor(a1, point_nums=P, seed=seed)
+    s2 = sampling.region_extractor(a2, point_nums=P, seed=seed)
+    labels = list(range(s1.shape[0]))
+    ref = SupConLoss1()(s1, s2, target=labels)
+    (ref * 2.5).backward()
+    b1, b2 = m1.detach().clone().requires_grad_(), m2.detach().clone().requires_grad_()
+    pix = sampling.region_pixel_offsets(B, C, h, w, P, seed)
+    crit = SupConLoss1()
+    loss = crit.forward_dense(b1, b2, pix, target=labels)
+    (loss * 2.5).backward()
+    assert loss.item() == pytest.approx(ref.item(), rel=1e-6)
+    np.testing.assert_allclose(b1.grad.cpu().numpy(), a1.grad.cpu().numpy(), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(b2.grad.cpu().numpy(), a2.grad.cpu().numpy(), rtol=1e-5, atol=1e-9)
+    assert crit.pos_mask.shape == (2 * B * P, 2 * B * P)
+    with pytest.raises(AssertionError):
+        SupConLoss1().forward_dense(b1.detach() * 1.1, b2.detach(), pix, target=labels)
+    # the large-batch shape of BASELINE config 2, scaled down: bf16 maps, many points per image, tensor path
+    B, C, h, w = 4, 256, 32, 32
+    m = torch.nn.functional.normalize(torch.randn(2 * B, C, h, w, device=DEV), dim=1).to(torch.bfloat16)
+    m1, m2 = torch.chunk(m, 2, dim=0)
+    g = torch.Generator().manual_seed(5)
+    pix = torch.cat([b * C * h * w + torch.randperm(h * w, generator=g)[:256] for b in range(B)])
+    idx = pix[:, None].to(DEV) + torch.arange(C, device=DEV)[None, :] * (h * w)
+    r1 = m1.reshape(-1)[idx].clone().requires_grad_()
+    r2 = m2.reshape(-1)[idx].clone().requires_grad_()
+    ref = SupConLoss1(path="tcgen05")(r1, r2)
+    ref.backward()
+    d1, d2 = m1.detach().clone().requires_grad_(), m2.detach().clone().requires_grad_()
+    loss = SupConLoss1(path="tcgen05").forward_dense(d1, d2, pix)
+    loss.backward()
+    assert loss.item() == pytest.approx(ref.item(), rel=1e-6)
+    assert torch.equal(d1.grad.reshape(-1)[idx], r1.grad)
+    assert float(d1.grad.float().abs().sum()) == pytest.approx(float(r1.grad.float().abs().sum()), rel=1e-6)
 
 
 # ------------------------------------------------------------------------------------------------ config 5 stand-in
