@@ -429,6 +429,18 @@ def main():
     e2e = {"value": N * N / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
            "ms_per_step": e2e_ms}
 
+    # ---- the north_star's contract-named backward, design (i): strip contribution to all N rows + reduce-scatter of dZ, timed
+    # beside the default design (ii) (complete gradient of the owned rows from the gathered row statistics)
+    rs_variant = None
+    if world > 1 and variant == 0:
+        rs_crit = cyd.ShardedSupConLoss(group=None, path=args.path, backward_design="reduce_scatter")
+        rs_ms = timed_loop(lambda: step(f1_dev, f2_dev, lab_dev, rs_crit), 1, 3) / 3
+        rs_variant = {"ms_per_step": rs_ms, "value": N * N / (rs_ms * 1e-3), "unit": "pairs/s",
+                      "bytes_reduce_scattered_per_rank": N * d * 4,
+                      "note": "design (i): every rank forms dL/dS for its row strip, contributes G Z to its rows and G^T Z to all N "
+                              "columns (fp32, stock torch ops on the strip) and the [N, d] gradient is reduce-scattered (NCCL); "
+                              "same numbers as the default design (ii), which needs no gradient collective"}
+
     # ---- optional: the same step replayed from CUDA graphs (forward and backward captured once, collectives included)
     graphed = None
     if args.graph:
@@ -611,6 +623,11 @@ def main():
             line["iic"]["cpu_baseline"] = cpu_iic_baseline(steps=3, warmup=1)
     if graphed is not None:
         line["graphed"] = graphed
+    if rs_variant is not None:
+        line["reduce_scatter_design"] = rs_variant
+    if world > 1:
+        line["config"]["exchange"] = ("peer memory (cy_p2p_push + symmetric-memory signal barriers)"
+                                      if getattr(crit, "_px", None) is not None else "NCCL all-gathers")
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
