@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcontrastyou_b200.so")
 
 # dtype / variant / path codes (contrastyou_b200.h)
-CY_F32, CY_BF16, CY_F16 = 0, 1, 2
+CY_F32, CY_BF16, CY_F16, CY_F32_SPLIT = 0, 1, 2, 3
 CY_SUPCON, CY_SUPCON_EXCLUDE, CY_SELFPACED_HARD, CY_SELFPACED_SOFT = 0, 1, 2, 3
 CY_PATH_AUTO, CY_PATH_SIMT, CY_PATH_TCGEN05 = 0, 1, 2
 CY_NSTAT = 8
@@ -40,6 +40,7 @@ SIGNATURES = {
     "cy_labels_canonicalize": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp]),
     "cy_infonce_pack": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "cy_infonce_unpack": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cy_infonce_pack_split": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "cy_infonce_pack_gather": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "cy_infonce_unpack_scatter": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "cy_iic_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),

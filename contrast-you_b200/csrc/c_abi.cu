@@ -54,6 +54,7 @@ int infonce_masks(int64_t, const int32_t*, const uint8_t*, float*, float*, cudaS
 int labels_canonicalize(const void*, int, int64_t, int32_t*, int32_t*, cudaStream_t);
 int infonce_pack(const void*, const void*, int, int64_t, int64_t, int64_t, int64_t, const int64_t*, void*, int*, float*, const int64_t*, int64_t,
                  cudaStream_t);
+int infonce_pack_split(const void*, const void*, int64_t, int64_t, int64_t, int64_t, const int64_t*, void*, int*, cudaStream_t);
 int infonce_unpack(const void*, int, int64_t, int64_t, int64_t, const int64_t*, void*, void*, const void*, const float*, const float*,
                    const int64_t*, int64_t, cudaStream_t);
 // infonce_tc.cu
@@ -84,7 +85,7 @@ int iic_bwd(const void*, const void*, int, int, int, int, int, int, const float*
 static int check_infonce_args(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
                               const uint8_t* codes, int64_t row_begin, int64_t row_end, int variant) {
     CY_CHECK_ARG(z != nullptr, "z is null");
-    CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
+    CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16 || dtype == CY_F32_SPLIT, "unknown dtype %d", dtype);
     CY_CHECK_ARG(N >= 2 && (N % 2) == 0, "N=%lld must be even (two stacked views)", (long long)N);
     CY_CHECK_ARG(d >= 1 && ldz >= d, "d=%lld ldz=%lld", (long long)d, (long long)ldz);
     CY_CHECK_ARG(labels != nullptr || codes != nullptr, "need labels or codes");
@@ -112,6 +113,10 @@ static int resolve_path(int path, int dtype, int64_t N, int64_t d, int64_t ldz, 
         return 1;
     }
     if (path == CY_PATH_AUTO && tc_ok && N >= 1024) return 1;
+    if (dtype == CY_F32_SPLIT) {
+        set_error("CY_F32_SPLIT rows are a tensor-path format (d in {128, 256}, N >= 256, 128-aligned row range, label masks)");
+        return CY_ERR_UNSUPPORTED;
+    }
     if (d > 256) {
         set_error("SIMT path supports d <= 256 (got %lld)", (long long)d);
         return CY_ERR_UNSUPPORTED;
@@ -226,6 +231,13 @@ int cy_infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_
     CY_CHECK_ARG(f1 && f2 && z && n >= 1 && d >= 1 && ld1 >= d && ld2 >= d, "bad arguments");
     CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
     return infonce_pack(f1, f2, dtype, n, d, ld1, ld2, order, z, bad_rows, inv_norm, nullptr, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_infonce_pack_split(const void* f1, const void* f2, int64_t n, int64_t d, int64_t ld1, int64_t ld2, const int64_t* order,
+                          void* zs, int32_t* bad_rows, void* stream) {
+    CY_NVTX("cy_infonce_pack_split");
+    CY_CHECK_ARG(f1 && f2 && zs && n >= 1 && d >= 1 && ld1 >= d && ld2 >= d, "bad arguments");
+    return infonce_pack_split(f1, f2, n, d, ld1, ld2, order, zs, bad_rows, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int cy_infonce_pack_gather(const void* map1, const void* map2, int dtype, int64_t n, int64_t d, const int64_t* pix_off,

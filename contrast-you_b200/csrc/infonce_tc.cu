@@ -53,26 +53,34 @@ __device__ __forceinline__ float sp_weight_tc(int variant, float logp, float gam
 // Zi lives in tensor memory (columns [384, 384 + D/2): two 16-bit elements per column), three S accumulators of 128 columns,
 // three Zj stages.  With both operands in shared memory an M128 N128 K16 MMA fetches 8 KB per 64 clk — the whole 128 B/clk
 // port, which TMA needs as well (round-1 profiles: 72 % tensor-active); with A in TMEM it is at 79 %.
-template <int D>
+// SPLIT (fp32 embeddings, CY_F32_SPLIT): every row arrives as [hi | lo] bf16 halves (z = hi + lo to 2^-17, cy_infonce_pack_split)
+// and S = hi_i hi_j + hi_i lo_j + lo_i hi_j — three MMA terms into the same accumulator, products good to 2^-16: fp32 parity
+// (1e-4) at a third of the bf16 rate instead of the CUDA-core path's 1 %.  Column tiles shrink to 64 so that three [hi | lo]
+// stages still fit; Zi hi AND lo live in tensor memory (D columns), four 64-column accumulators.
+template <int D, bool SPLIT>
 struct FwdCfg {
-    static constexpr int BN = FWD_BN;
-    static constexpr int KBLK = D / 64;                         // 64-element (128-byte) K blocks per row
+    static constexpr int BN = SPLIT ? 64 : FWD_BN;
+    static constexpr int KBLK = D / 64;                         // 64-element (128-byte) K blocks per term
+    static constexpr int KBLK_B = SPLIT ? 2 * KBLK : KBLK;      // K blocks staged per column tile
     static constexpr int NSTAGE = 3;
-    static constexpr int NACC = 3;
-    static constexpr uint32_t B_BYTES = BN * D * 2;
+    static constexpr int NACC = SPLIT ? 4 : 3;
+    static constexpr int A_COLS = SPLIT ? D : D / 2;            // tensor-memory columns of Zi
+    static constexpr int TMEM_A = 512 - A_COLS;
+    static_assert(NACC * BN <= TMEM_A, "accumulators and Zi overlap in tensor memory");
+    static constexpr uint32_t B_BYTES = BN * KBLK_B * 128;
     static constexpr uint32_t OFF_LAB = NSTAGE * B_BYTES;
-    static constexpr uint32_t OFF_LIST = OFF_LAB + 8 * (BN / 2) * 4;
+    static constexpr uint32_t OFF_LIST = OFF_LAB + 8 * (FWD_BN / 2) * 4;
     static constexpr uint32_t OFF_BAR = OFF_LIST + P2_LISTCAP * 2;
     static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024;   // + barriers / scalars + 1024-alignment slack
 };
 
-template <int D, int PASS, int VARIANT>
+template <int D, int PASS, int VARIANT, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict__ labels, int N, int row_begin,
                       int ct_begin, int ct_end, int tiles_per_split, float c1, float inv_t, float gamma,
                       float* __restrict__ part, int slot_base, uint32_t idesc, const uint16_t* __restrict__ zrows, int64_t ldz,
                       const int2* __restrict__ tile_range, const float4* __restrict__ xstat) {
-    using S = FwdCfg<D>;
+    using S = FwdCfg<D, SPLIT>;
     constexpr int BN = S::BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);    // 1024-aligned, still a shared pointer
@@ -130,7 +138,7 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_a = tmem_base + 384;        // Zi, columns [384, 384 + D/2)
+    const uint32_t tmem_a = tmem_base + S::TMEM_A;  // Zi: hi in columns [0, D/2) of this range, lo (SPLIT) in [D/2, D)
 
     int ct0 = 0, ntile;
     if constexpr (PASS == 1) {
@@ -150,7 +158,7 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                 mbar_wait(b_empty + s, ring.phase() ^ 1u);
                 mbar_arrive_expect_tx(b_full + s, S::B_BYTES);
                 uint8_t* dst = sB + s * S::B_BYTES;
-                for (int kb = 0; kb < S::KBLK; ++kb)
+                for (int kb = 0; kb < S::KBLK_B; ++kb)      // (SPLIT: K blocks KBLK.. are the lo halves, columns D.. of the row)
                     for (int hb = 0; hb < BN / 64; ++hb)
                         tma_load_2d(dst + kb * (BN * 128) + hb * 8192, &tmap, b_full + s, kb * 64, ct * BN + hb * 64);
             }
@@ -172,6 +180,20 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                     for (int ks = 0; ks < 4; ++ks)
                         umma_bf16_ts(tmem_base + a * BN, tmem_a + (kb * 4 + ks) * 8,
                                      smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc, (kb | ks) != 0);
+                if constexpr (SPLIT) {
+#pragma unroll
+                    for (int kb = 0; kb < S::KBLK; ++kb)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)      // hi_i . lo_j
+                            umma_bf16_ts(tmem_base + a * BN, tmem_a + (kb * 4 + ks) * 8,
+                                         smem_desc(b_addr + (S::KBLK + kb) * (BN * 128) + ks * 32, 16, 1024), idesc, 1u);
+#pragma unroll
+                    for (int kb = 0; kb < S::KBLK; ++kb)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)      // lo_i . hi_j
+                            umma_bf16_ts(tmem_base + a * BN, tmem_a + D / 2 + (kb * 4 + ks) * 8,
+                                         smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc, 1u);
+                }
                 umma_commit(b_empty + s);
                 umma_commit(acc_full + a);
             }
@@ -184,16 +206,20 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
         const int32_t my_lab = labels[gic];
         {
             // this thread's half row of Zi (D/2 elements = D/4 packed columns) -> tensor memory lanes q*32.., columns h*D/4..
-            const uint4* src = reinterpret_cast<const uint4*>(zrows + (size_t)gic * ldz + h * (D / 2));
+            // (SPLIT: the same for the lo half of the row, D elements further, into the columns D/2 further)
 #pragma unroll
-            for (int c = 0; c < D / 128; ++c) {
-                uint32_t r[32];
+            for (int part_ = 0; part_ < (SPLIT ? 2 : 1); ++part_) {
+                const uint4* src = reinterpret_cast<const uint4*>(zrows + (size_t)gic * ldz + part_ * D + h * (D / 2));
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const uint4 v = __ldg(src + c * 8 + e);
-                    r[4 * e] = v.x; r[4 * e + 1] = v.y; r[4 * e + 2] = v.z; r[4 * e + 3] = v.w;
+                for (int c = 0; c < D / 128; ++c) {
+                    uint32_t r[32];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const uint4 v = __ldg(src + c * 8 + e);
+                        r[4 * e] = v.x; r[4 * e + 1] = v.y; r[4 * e + 2] = v.z; r[4 * e + 3] = v.w;
+                    }
+                    tmem_st_32x32(tmem_a + (uint32_t(q * 32) << 16) + part_ * (D / 2) + h * (D / 4) + c * 32, r);
                 }
-                tmem_st_32x32(tmem_a + (uint32_t(q * 32) << 16) + h * (D / 4) + c * 32, r);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -201,7 +227,7 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
             if (lane == 0) mbar_arrive(a_full);
         }
         int32_t* wlab = sLab + ew * (BN / 2);
-        constexpr int NCH = BN / 64;                       // 32-column chunks per warp and tile
+        constexpr int NCH = BN / 64;                       // 32-column chunks per warp and tile (its half of the BN columns)
         // label range of this warp's 32 rows: a column chunk whose label range does not intersect it holds no positive
         // pair, whatever the order of the rows (callers that sort rows by label make this the common case)
         const int32_t row_lo = __reduce_min_sync(0xffffffffu, my_lab), row_hi = __reduce_max_sync(0xffffffffu, my_lab);
@@ -343,10 +369,10 @@ infonce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
 }
 
 // [min, max] label of every 128-column tile (pass-2 tile selection)
-__global__ void infonce_tile_range_kernel(const int32_t* __restrict__ labels, int N, int2* __restrict__ tile_range) {
-    const int ct = blockIdx.x, lane = threadIdx.x;          // one warp per tile
+__global__ void infonce_tile_range_kernel(const int32_t* __restrict__ labels, int N, int bn, int2* __restrict__ tile_range) {
+    const int ct = blockIdx.x, lane = threadIdx.x;          // one warp per tile of bn columns
     int32_t lo = INT_MAX, hi = INT_MIN;
-    for (int j = ct * FWD_BN + lane; j < min(N, (ct + 1) * FWD_BN); j += 32) {
+    for (int j = ct * bn + lane; j < min(N, (ct + 1) * bn); j += 32) {
         const int32_t l = labels[j];
         lo = min(lo, l);
         hi = max(hi, l);
@@ -502,14 +528,21 @@ __global__ void infonce_loss_final_kernel(int nblk, int N, const float* __restri
 // it was computed from (bf16 pairs: 16 columns per 32-column half) and read from there by the second MMA — no
 // shared-memory W tile, no swizzled stores, no proxy fence.  The S slot is recycled by the in-order tensor pipe: MMA1(t+2)
 // is issued after MMA2(t), which is the last reader of slot t % 2.
-template <int D>
+// SPLIT (fp32 embeddings as [hi | lo] bf16 halves): S = hi_i hi_j + hi_i lo_j + lo_i hi_j and dZ += W_hi Zj_hi + W_lo Zj_hi +
+// W_hi Zj_lo — six MMA groups per tile instead of two.  Tensor memory is full with dZ (D fp32 columns), Zi_hi and the two S
+// slots, so Zi_lo is a K-major shared-memory tile (the one SS-mode MMA of the kernel) and the Zj ring shrinks to two
+// [hi | lo] stages; the gradient leaves in fp32.
+template <int D, bool SPLIT>
 struct BwdCfg {
     static constexpr int BN = BWD_BN;
     static constexpr int KBLK = D / 64;
-    static constexpr int NSTAGE = 6;     // Zj ring (a stage lives from its MMA1 until its MMA2 retires)
+    static constexpr int KBLK_B = SPLIT ? 2 * KBLK : KBLK;
+    static constexpr int NSTAGE = SPLIT ? 2 : 6;     // Zj ring (a stage lives from its MMA1 until its MMA2 retires)
     static constexpr int NS = 2;         // S accumulators in TMEM (64 columns each), the last NS*64 columns
-    static constexpr uint32_t B_BYTES = BN * D * 2;
-    static constexpr uint32_t OFF_COL = NSTAGE * B_BYTES;       // per epilogue warp: lab[32], coef[32], invc[32], aux[32]
+    static constexpr uint32_t B_BYTES = BN * KBLK_B * 128;
+    static constexpr uint32_t ALO_BYTES = SPLIT ? TC_BM * D * 2 : 0;      // Zi_lo [KBLK][128 rows x 128 B]
+    static constexpr uint32_t OFF_ALO = NSTAGE * B_BYTES;
+    static constexpr uint32_t OFF_COL = OFF_ALO + ALO_BYTES;    // per epilogue warp: lab[32], coef[32], invc[32], aux[32]
     static constexpr uint32_t OFF_BAR = OFF_COL + 8 * 4 * 32 * 4;
     static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024;
 };
@@ -530,7 +563,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // F16: fp16 embeddings.  W is then stored as fp16 scaled by 2^10 (softmax-sized weights below 6e-8 would flush to zero in
 // fp16; scaled, the flush threshold drops to 6e-11 while the largest weight, ~2, stays far from 65504); the scale is
 // undone in out_scale by the host.
-template <int D, bool F16, int VARIANT>
+template <int D, bool F16, int VARIANT, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict__ labels,
                       const float4* __restrict__ xstat, int N, int row_begin, int row_end, int tiles_per_split, float c1,
@@ -539,11 +572,13 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                       const uint16_t* __restrict__ zrows, int64_t ldz) {
     uint16_t* dz = reinterpret_cast<uint16_t*>(dz_v);
     constexpr float WS = F16 ? 1024.f : 1.f;
-    using C = BwdCfg<D>;
+    using C = BwdCfg<D, SPLIT>;
     constexpr int BN = C::BN;
+    static_assert(!(SPLIT && F16), "the split path carries bf16 halves");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);    // 1024-aligned, still a shared pointer
     uint8_t* sB = smem;
+    uint8_t* sAlo = smem + C::OFF_ALO;
     float* sCol = reinterpret_cast<float*>(smem + C::OFF_COL);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* a_full = bars;
@@ -552,7 +587,8 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
     uint64_t* s_full = b_empty + C::NSTAGE;
     uint64_t* w_full = s_full + C::NS;
     uint64_t* dz_full = w_full + C::NS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dz_full + 1);
+    uint64_t* alo_full = dz_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(alo_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = row_begin + blockIdx.x * TC_BM;
@@ -569,6 +605,7 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
         for (int i = 0; i < C::NSTAGE; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         for (int i = 0; i < C::NS; ++i) { mbar_init(s_full + i, 1); mbar_init(w_full + i, 8); }
         mbar_init(dz_full, 1);
+        mbar_init(alo_full, 1);
         fence_barrier_init();
     }
     if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -582,19 +619,27 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
 
     if (warp == 0) {
         if (elect_one()) {
+            if constexpr (SPLIT) {          // Zi_lo: columns D.. of the row block, K-major tile (rows past N: TMA zero fill)
+                mbar_arrive_expect_tx(alo_full, C::ALO_BYTES);
+                for (int kb = 0; kb < C::KBLK; ++kb)
+                    for (int hb = 0; hb < TC_BM / 64; ++hb)
+                        tma_load_2d(sAlo + kb * (TC_BM * 128) + hb * 8192, &tmap, alo_full, D + kb * 64, row0 + hb * 64);
+            }
             Ring<C::NSTAGE> ring;
             for (int t = 0; t < nt; ++t, ring.next()) {
                 const uint32_t s = ring.stage();
                 mbar_wait(b_empty + s, ring.phase() ^ 1u);
                 mbar_arrive_expect_tx(b_full + s, C::B_BYTES);
                 uint8_t* dst = sB + s * C::B_BYTES;
-                for (int kb = 0; kb < C::KBLK; ++kb) tma_load_2d(dst + kb * (BN * 128), &tmap, b_full + s, kb * 64, (t0 + t) * BN);
+                for (int kb = 0; kb < C::KBLK_B; ++kb) tma_load_2d(dst + kb * (BN * 128), &tmap, b_full + s, kb * 64, (t0 + t) * BN);
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
             // idesc1: S = Zi (TMEM) x Zj (K-major), M128 N64;  idesc2: dZ += W (TMEM) x Zj (MN-major), M128 N(D)
             mbar_wait(a_full, 0);
+            if constexpr (SPLIT) mbar_wait(alo_full, 0);
+            const uint32_t alo_addr = smem_u32(sAlo);
             Ring<C::NSTAGE> ring1;      // stage / phase of the tile whose MMA1 is issued next
             Ring<C::NS> sacc;
             auto issue_mma1 = [&]() {
@@ -608,6 +653,20 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                     for (int ks = 0; ks < 4; ++ks)      // k-step (kb, ks) = elements 64*kb + 16*ks ..: 8 columns of Zi in TMEM
                         umma_bf16_ts(tmem_s + a * BN, tmem_a + (kb * 4 + ks) * 8,
                                      smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc1, (kb | ks) != 0);
+                if constexpr (SPLIT) {
+#pragma unroll
+                    for (int kb = 0; kb < C::KBLK; ++kb)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)      // hi_i . lo_j
+                            umma_bf16_ts(tmem_s + a * BN, tmem_a + (kb * 4 + ks) * 8,
+                                         smem_desc(b_addr + (C::KBLK + kb) * (BN * 128) + ks * 32, 16, 1024), idesc1, 1u);
+#pragma unroll
+                    for (int kb = 0; kb < C::KBLK; ++kb)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)      // lo_i (shared memory, K-major) . hi_j
+                            umma_bf16(tmem_s + a * BN, smem_desc(alo_addr + kb * (TC_BM * 128) + ks * 32, 16, 1024),
+                                      smem_desc(b_addr + kb * (BN * 128) + ks * 32, 16, 1024), idesc1, 1u);
+                }
                 umma_commit(s_full + a);
                 ring1.next();
                 sacc.next();
@@ -628,6 +687,16 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                     // k-step = 16 rows of j = 2048 B.
                     umma_bf16_ts(tmem_dz, tmem_s + (uint32_t)(t % C::NS) * BN + (ks >> 1) * 32 + (ks & 1) * 8,
                                  smem_desc(b_addr + ks * 2048, BN * 128, 1024), idesc2, (t | ks) != 0);
+                if constexpr (SPLIT) {
+#pragma unroll
+                    for (int ks = 0; ks < BN / 16; ++ks)      // W_lo (columns +16 of the half) . Zj_hi
+                        umma_bf16_ts(tmem_dz, tmem_s + (uint32_t)(t % C::NS) * BN + (ks >> 1) * 32 + 16 + (ks & 1) * 8,
+                                     smem_desc(b_addr + ks * 2048, BN * 128, 1024), idesc2, 1u);
+#pragma unroll
+                    for (int ks = 0; ks < BN / 16; ++ks)      // W_hi . Zj_lo (K blocks KBLK.. of the stage)
+                        umma_bf16_ts(tmem_dz, tmem_s + (uint32_t)(t % C::NS) * BN + (ks >> 1) * 32 + (ks & 1) * 8,
+                                     smem_desc(b_addr + C::KBLK * (BN * 128) + ks * 2048, BN * 128, 1024), idesc2, 1u);
+                }
                 umma_commit(b_empty + s);
             }
             umma_commit(dz_full);
@@ -689,7 +758,12 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            uint32_t packed[16];
+            uint32_t packed[SPLIT ? 32 : 16];            // [0,16): W (hi) pairs; SPLIT: [16,32): the bf16 remainders
+            auto put = [&](int idx, float a, float b) {
+                const uint32_t hi = pack2<F16>(a, b);
+                packed[idx] = hi;
+                if constexpr (SPLIT) packed[16 + idx] = pack2<false>(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+            };
             if (!may_have_pos) {                          // no positive pair in this 32 x 32 block: W = E (coef_i + coef_j)
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
@@ -698,8 +772,8 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                     const float w1 = ex2_approx(fmaf(__uint_as_float(r[e4 * 4 + 1]), c1, -c1)) * (coef_i + cj.y);
                     const float w2 = ex2_approx(fmaf(__uint_as_float(r[e4 * 4 + 2]), c1, -c1)) * (coef_i + cj.z);
                     const float w3 = ex2_approx(fmaf(__uint_as_float(r[e4 * 4 + 3]), c1, -c1)) * (coef_i + cj.w);
-                    packed[e4 * 2] = pack2<F16>(w0, w1);
-                    packed[e4 * 2 + 1] = pack2<F16>(w2, w3);
+                    put(e4 * 2, w0, w1);
+                    put(e4 * 2 + 1, w2, w3);
                 }
             } else {
                 const bool diag_tile = __any_sync(0xffffffffu, (gi >= jbase) && (gi < jbase + 32));
@@ -740,13 +814,15 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
                             if (j == gi || j >= N) wv[u] = 0.f;
                         }
                     }
-                    packed[e4 * 2] = pack2<F16>(wv[0], wv[1]);
-                    packed[e4 * 2 + 1] = pack2<F16>(wv[2], wv[3]);
+                    put(e4 * 2, wv[0], wv[1]);
+                    put(e4 * 2 + 1, wv[2], wv[3]);
                 }
             }
             // in place: this warp's 32 x 32 block of S (columns h*32 ..) becomes 32 x 32 bf16 weights in columns h*32 .. +15
+            // (SPLIT: and their bf16 remainders in columns h*32+16 .. +31)
             tc_fence_after();
-            tmem_st_32x16(tmem_s + (uint32_t(q * 32) << 16) + a * BN + h * 32, packed);
+            if constexpr (SPLIT) tmem_st_32x32(tmem_s + (uint32_t(q * 32) << 16) + a * BN + h * 32, packed);
+            else tmem_st_32x16(tmem_s + (uint32_t(q * 32) << 16) + a * BN + h * 32, packed);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -756,7 +832,23 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
         mbar_wait(dz_full, 0);
         tc_fence_after();
         const bool store_row = gi < row_end;
-        if (dz32 == nullptr) {
+        if (dz32 == nullptr && SPLIT) {
+            const float scale = gscale[0] * out_scale;
+            float* out = reinterpret_cast<float*>(dz_v) + (size_t)gi * lddz + h * (D / 2);
+#pragma unroll 1
+            for (int c = 0; c < D / 64; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_dz + (uint32_t(q * 32) << 16) + h * (D / 2) + c * 32, r);
+                tmem_ld_wait();
+                if (store_row) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        *reinterpret_cast<float4*>(out + c * 32 + e) =
+                            make_float4(__uint_as_float(r[e]) * scale, __uint_as_float(r[e + 1]) * scale,
+                                        __uint_as_float(r[e + 2]) * scale, __uint_as_float(r[e + 3]) * scale);
+                }
+            }
+        } else if (dz32 == nullptr) {
             const float scale = gscale[0] * out_scale;
             uint16_t* out = dz + (size_t)gi * lddz + h * (D / 2);
 #pragma unroll 1
@@ -796,7 +888,7 @@ infonce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* _
 }
 
 // fp32 split slabs -> bf16 gradient rows (scaled by gscale / (t N)); slabs summed in split order
-template <int D, bool F16>
+template <int D, bool F16, bool OUT32 = false>
 __global__ void infonce_tc_convert_kernel(const float* __restrict__ dz32, int nsplit, int64_t rows, int64_t rows_pad, int64_t row_begin,
                                           const float* __restrict__ gscale, float out_scale, uint16_t* __restrict__ dz,
                                           int64_t lddz) {
@@ -812,9 +904,15 @@ __global__ void infonce_tc_convert_kernel(const float* __restrict__ dz32, int ns
         a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
         b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
     }
-    *reinterpret_cast<uint4*>(dz + (row_begin + r) * lddz + c) =
-        make_uint4(pack2<F16>(a.x * scale, a.y * scale), pack2<F16>(a.z * scale, a.w * scale),
-                   pack2<F16>(b.x * scale, b.y * scale), pack2<F16>(b.z * scale, b.w * scale));
+    if constexpr (OUT32) {
+        float* o = reinterpret_cast<float*>(dz) + (row_begin + r) * lddz + c;
+        *reinterpret_cast<float4*>(o) = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(b.x * scale, b.y * scale, b.z * scale, b.w * scale);
+    } else {
+        *reinterpret_cast<uint4*>(dz + (row_begin + r) * lddz + c) =
+            make_uint4(pack2<F16>(a.x * scale, a.y * scale), pack2<F16>(a.z * scale, a.w * scale),
+                       pack2<F16>(b.x * scale, b.y * scale), pack2<F16>(b.z * scale, b.w * scale));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------ host
@@ -834,11 +932,12 @@ EncodeTiledFn tensor_map_encode_fn() {
     return fn;
 }
 
-// [N, d] bf16 / fp16, row pitch ldz elements; box = 64 columns (128 B, the swizzle span) x 64 rows; rows past N read as zero
-static int make_tmap(CUtensorMap* m, const void* z, int64_t N, int64_t d, int64_t ldz, int dtype) {
+// [N, cols] bf16 / fp16, row pitch ldz elements; box = 64 columns (128 B, the swizzle span) x 64 rows; rows past N read as zero.
+// cols = d, or 2 d for CY_F32_SPLIT rows ([hi | lo] bf16 halves)
+static int make_tmap(CUtensorMap* m, const void* z, int64_t N, int64_t cols, int64_t ldz, int dtype) {
     EncodeTiledFn fn = tensor_map_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CY_ERR_DEVICE; }
-    cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)N};
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)N};
     cuuint64_t gstride[1] = {(cuuint64_t)ldz * 2};
     cuuint32_t box[2] = {64, 64};
     cuuint32_t estr[2] = {1, 1};
@@ -850,11 +949,15 @@ static int make_tmap(CUtensorMap* m, const void* z, int64_t N, int64_t d, int64_
     return CY_OK;
 }
 
+static inline bool is_split(int dtype) { return dtype == CY_F32_SPLIT; }
+static inline int fwd_bn(int dtype) { return is_split(dtype) ? 64 : FWD_BN; }
+
 bool infonce_tc_supported(int dtype, int64_t N, int64_t d, int64_t ldz, const uint8_t* codes, int variant) {
-    if (!((dtype == CY_BF16 || dtype == CY_F16) && (d == 256 || d == 128) && N >= 256 && (ldz % 8) == 0 && codes == nullptr &&
-          N < (int64_t(1) << 30)))
+    if (!((dtype == CY_BF16 || dtype == CY_F16 || dtype == CY_F32_SPLIT) && (d == 256 || d == 128) && N >= 256 && (ldz % 8) == 0 &&
+          codes == nullptr && N < (int64_t(1) << 30)))
         return false;
-    if (variant != CY_SUPCON && N > (int64_t)P2_LISTCAP * FWD_BN) return false;      // pass-2 tile list capacity
+    if (is_split(dtype) && ldz < 2 * d) return false;
+    if (variant != CY_SUPCON && N > (int64_t)P2_LISTCAP * fwd_bn(dtype)) return false;      // pass-2 tile list capacity
     return true;
 }
 
@@ -876,9 +979,9 @@ static int bwd_splits(int64_t N, int64_t row_blocks) {
     return best;
 }
 
-static int fwd_splits(int64_t N, int64_t row_blocks) {
+static int fwd_splits(int64_t N, int64_t row_blocks, int bn) {
     const int sms = sm_count();
-    const int64_t rb = row_blocks, ctiles = (N + FWD_BN - 1) / FWD_BN;
+    const int64_t rb = row_blocks, ctiles = (N + bn - 1) / bn;
     // enough CTAs for ~8 waves, but at least 8 column tiles per CTA so the A load and the prologue amortise
     int64_t want = (8LL * sms + rb - 1) / rb;
     int64_t maxs = ctiles / 8 > 0 ? ctiles / 8 : 1;
@@ -892,10 +995,10 @@ constexpr size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 size_t infonce_tc_workspace_bytes(int64_t N, int64_t d) {
     if (d != 256 && d != 128) return 0;
     // forward: worst case over row ranges is a single 128-row block -> the most column splits
-    const int smax = fwd_splits(N, 1);
+    const int smax = fwd_splits(N, 1, 64);
     const size_t fwd = (size_t)smax * 2 * 4 * (size_t)N * sizeof(float);
     // pass 2: [tile ranges | 2 slots x 2 values x N]
-    const size_t p2 = align256((size_t)((N + FWD_BN - 1) / FWD_BN) * sizeof(int2)) + (size_t)4 * N * sizeof(float);
+    const size_t p2 = align256((size_t)((N + 63) / 64) * sizeof(int2)) + (size_t)4 * N * sizeof(float);
     // backward: fp32 slabs, splits x row blocks x 128 x d — worst case over the row-block count
     const int64_t rb_all = (N + TC_BM - 1) / TC_BM;
     size_t bwd = 0;
@@ -911,12 +1014,12 @@ size_t infonce_tc_workspace_bytes(int64_t N, int64_t d) {
     return m;
 }
 
-template <int D, int PASS, int VARIANT>
+template <int D, int PASS, int VARIANT, bool SPLIT>
 static int launch_fwd_tc(const CUtensorMap& tmap, const int32_t* labels, int N, int row_begin, int ct_begin, int ct_end, int tps,
                          float inv_t, float gamma, float* part, int slot_base, int fmt, const void* z, int64_t ldz,
                          const int2* tile_range, const float4* xstat, dim3 grid, cudaStream_t st) {
-    using S = FwdCfg<D>;
-    auto k = infonce_fwd_tc_kernel<D, PASS, VARIANT>;
+    using S = FwdCfg<D, SPLIT>;
+    auto k = infonce_fwd_tc_kernel<D, PASS, VARIANT, SPLIT>;
     static SmemAttrCache attr;
     if (attr.need(S::TOTAL)) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
@@ -924,7 +1027,7 @@ static int launch_fwd_tc(const CUtensorMap& tmap, const int32_t* labels, int N, 
         attr.set(S::TOTAL);
     }
     k<<<grid, TC_THREADS, S::TOTAL, st>>>(tmap, labels, N, row_begin, ct_begin, ct_end, tps, inv_t * LOG2E, inv_t, gamma, part, slot_base,
-                                          idesc_f16kind_f32(TC_BM, FWD_BN, 0, 0, fmt), reinterpret_cast<const uint16_t*>(z), ldz,
+                                          idesc_f16kind_f32(TC_BM, S::BN, 0, 0, fmt), reinterpret_cast<const uint16_t*>(z), ldz,
                                           tile_range, xstat);
     CY_CHECK_LAUNCH("infonce_fwd_tc");
     return CY_OK;
@@ -944,25 +1047,28 @@ int infonce_fwd_tc(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, 
     int rc = check_tc_rows(N, row_begin, row_end);
     if (rc) return rc;
     CY_CHECK_ARG((reinterpret_cast<uintptr_t>(z) & 15) == 0, "tcgen05 path: z must be 16-byte aligned");
+    const bool split = is_split(dtype);
+    const int bn = fwd_bn(dtype);
     const int64_t rb = (rows + TC_BM - 1) / TC_BM;
-    const int splits = fwd_splits(N, rb);
+    const int splits = fwd_splits(N, rb, bn);
     const int nslot = splits * 2;
     const size_t need = (size_t)nslot * 4 * (size_t)N * sizeof(float);
     CY_CHECK_ARG(workspace && workspace_bytes >= need, "infonce_fwd_tc: workspace %zu < %zu", workspace_bytes, need);
     CUtensorMap tmap;
-    rc = make_tmap(&tmap, z, N, d, ldz, dtype);
+    rc = make_tmap(&tmap, z, N, split ? 2 * d : d, ldz, dtype);
     if (rc) return rc;
     const int fmt = dtype == CY_F16 ? 0 : 1;
-    const int ctiles = (int)((N + FWD_BN - 1) / FWD_BN);
+    const int ctiles = (int)((N + bn - 1) / bn);
     const int tps = (ctiles + splits - 1) / splits;
     dim3 grid((unsigned)rb, (unsigned)splits);
     float* part = reinterpret_cast<float*>(workspace);
-    if (d == 256)
-        rc = launch_fwd_tc<256, 1, CY_SUPCON>(tmap, labels, (int)N, (int)row_begin, 0, ctiles, tps, inv_t, 0.f, part, 0, fmt, z, ldz, nullptr,
-                                              nullptr, grid, st);
-    else
-        rc = launch_fwd_tc<128, 1, CY_SUPCON>(tmap, labels, (int)N, (int)row_begin, 0, ctiles, tps, inv_t, 0.f, part, 0, fmt, z, ldz, nullptr,
-                                              nullptr, grid, st);
+#define CY_P1(DV, SP)                                                                                                              \
+    if (d == DV && split == SP)                                                                                                    \
+        rc = launch_fwd_tc<DV, 1, CY_SUPCON, SP>(tmap, labels, (int)N, (int)row_begin, 0, ctiles, tps, inv_t, 0.f, part, 0, fmt, z, ldz, \
+                                                 nullptr, nullptr, grid, st);
+    rc = CY_ERR_UNSUPPORTED;
+    CY_P1(256, false) CY_P1(128, false) CY_P1(256, true) CY_P1(128, true)
+#undef CY_P1
     if (rc) return rc;
     infonce_rowstats_kernel<1><<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(variant, (int)N, (int)row_begin, (int)row_end, inv_t, part,
                                                                               nslot, stats, reinterpret_cast<float4*>(xstat));
@@ -978,7 +1084,9 @@ int infonce_fwd2_tc(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz,
     if (rows <= 0) return CY_OK;
     int rc = check_tc_rows(N, row_begin, row_end);
     if (rc) return rc;
-    const int ctiles = (int)((N + FWD_BN - 1) / FWD_BN);
+    const bool split = is_split(dtype);
+    const int bn = fwd_bn(dtype);
+    const int ctiles = (int)((N + bn - 1) / bn);
     const size_t range_bytes = align256((size_t)ctiles * sizeof(int2));
     const size_t need = range_bytes + (size_t)4 * N * sizeof(float);
     CY_CHECK_ARG(workspace && workspace_bytes >= need, "infonce_fwd2_tc: workspace %zu < %zu", workspace_bytes, need);
@@ -986,21 +1094,22 @@ int infonce_fwd2_tc(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz,
     int2* tile_range = reinterpret_cast<int2*>(workspace);
     float* part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + range_bytes);
     CUtensorMap tmap;
-    rc = make_tmap(&tmap, z, N, d, ldz, dtype);
+    rc = make_tmap(&tmap, z, N, split ? 2 * d : d, ldz, dtype);
     if (rc) return rc;
-    infonce_tile_range_kernel<<<ctiles, 32, 0, st>>>(labels, (int)N, tile_range);
+    infonce_tile_range_kernel<<<ctiles, 32, 0, st>>>(labels, (int)N, bn, tile_range);
     CY_CHECK_LAUNCH("infonce_tile_range");
     const int fmt = dtype == CY_F16 ? 0 : 1;
     const int64_t rb = (rows + TC_BM - 1) / TC_BM;
     dim3 grid((unsigned)rb, 1);
     const float4* xs = reinterpret_cast<const float4*>(xstat);
     rc = CY_ERR_UNSUPPORTED;
-#define CY_P2(DV, VAR)                                                                                                          \
-    if (d == DV && variant == VAR)                                                                                              \
-        rc = launch_fwd_tc<DV, 2, VAR>(tmap, labels, (int)N, (int)row_begin, 0, ctiles, ctiles, inv_t, gamma, part, 0, fmt, z, ldz, \
-                                       tile_range, xs, grid, st);
-    CY_P2(256, CY_SUPCON_EXCLUDE) CY_P2(256, CY_SELFPACED_HARD) CY_P2(256, CY_SELFPACED_SOFT)
-    CY_P2(128, CY_SUPCON_EXCLUDE) CY_P2(128, CY_SELFPACED_HARD) CY_P2(128, CY_SELFPACED_SOFT)
+#define CY_P2(DV, VAR, SP)                                                                                                        \
+    if (d == DV && variant == VAR && split == SP)                                                                                 \
+        rc = launch_fwd_tc<DV, 2, VAR, SP>(tmap, labels, (int)N, (int)row_begin, 0, ctiles, ctiles, inv_t, gamma, part, 0, fmt, z, ldz, \
+                                           tile_range, xs, grid, st);
+#define CY_P2V(DV, SP) CY_P2(DV, CY_SUPCON_EXCLUDE, SP) CY_P2(DV, CY_SELFPACED_HARD, SP) CY_P2(DV, CY_SELFPACED_SOFT, SP)
+    CY_P2V(256, false) CY_P2V(128, false) CY_P2V(256, true) CY_P2V(128, true)
+#undef CY_P2V
 #undef CY_P2
     if (rc) {
         if (rc == CY_ERR_UNSUPPORTED) set_error("infonce_fwd2_tc: no instantiation for d=%lld variant=%d", (long long)d, variant);
@@ -1041,12 +1150,12 @@ int infonce_loss(int64_t N, int variant, const float* xstat, float* out8, const 
     return CY_OK;
 }
 
-template <int D, bool F16, int VARIANT>
+template <int D, bool F16, int VARIANT, bool SPLIT>
 static int launch_bwd_tc(const CUtensorMap& tmap, const int32_t* labels, const float4* xstat, int N, int row_begin, int row_end, int tps,
                          float inv_t, float gamma, const float* gscale, float out_scale, void* dz, int64_t lddz, float* dz32,
                          int rows_total, const void* z, int64_t ldz, dim3 grid, cudaStream_t st) {
-    using C = BwdCfg<D>;
-    auto k = infonce_bwd_tc_kernel<D, F16, VARIANT>;
+    using C = BwdCfg<D, SPLIT>;
+    auto k = infonce_bwd_tc_kernel<D, F16, VARIANT, SPLIT>;
     static SmemAttrCache attr;
     if (attr.need(C::TOTAL)) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TOTAL);
@@ -1068,10 +1177,11 @@ int infonce_bwd_tc(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, 
     if (rows <= 0) return CY_OK;
     int rc = check_tc_rows(N, row_begin, row_end);
     if (rc) return rc;
-    CY_CHECK_ARG((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(dz) & 15) == 0 && (lddz % 8) == 0,
+    const bool split = is_split(dtype);
+    CY_CHECK_ARG((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(dz) & 15) == 0 && (lddz % (split ? 4 : 8)) == 0,
                  "tcgen05 path: z / dz must be 16-byte aligned");
     CUtensorMap tmap;
-    rc = make_tmap(&tmap, z, N, d, ldz, dtype);
+    rc = make_tmap(&tmap, z, N, split ? 2 * d : d, ldz, dtype);
     if (rc) return rc;
     const bool f16 = dtype == CY_F16;
     const float out_scale = (inv_t / (float)N) * (f16 ? (1.f / 1024.f) : 1.f);
@@ -1089,12 +1199,14 @@ int infonce_bwd_tc(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, 
     dim3 grid((unsigned)rb, (unsigned)splits);
     const float4* xs = reinterpret_cast<const float4*>(xstat);
     rc = CY_ERR_UNSUPPORTED;
-#define CY_BW(DV, F, VAR)                                                                                                       \
-    if (d == DV && f16 == F && variant == VAR)                                                                                  \
-        rc = launch_bwd_tc<DV, F, VAR>(tmap, labels, xs, (int)N, (int)row_begin, (int)row_end, tps, inv_t, gamma, gscale, out_scale, dz, \
-                                       lddz, dz32, (int)rows_pad, z, ldz, grid, st);
-#define CY_BW4(DV, F) CY_BW(DV, F, CY_SUPCON) CY_BW(DV, F, CY_SUPCON_EXCLUDE) CY_BW(DV, F, CY_SELFPACED_HARD) CY_BW(DV, F, CY_SELFPACED_SOFT)
-    CY_BW4(256, false) CY_BW4(256, true) CY_BW4(128, false) CY_BW4(128, true)
+#define CY_BW(DV, F, VAR, SP)                                                                                                    \
+    if (d == DV && f16 == F && variant == VAR && split == SP)                                                                    \
+        rc = launch_bwd_tc<DV, F, VAR, SP>(tmap, labels, xs, (int)N, (int)row_begin, (int)row_end, tps, inv_t, gamma, gscale, out_scale, dz, \
+                                           lddz, dz32, (int)rows_pad, z, ldz, grid, st);
+#define CY_BW4(DV, F, SP) CY_BW(DV, F, CY_SUPCON, SP) CY_BW(DV, F, CY_SUPCON_EXCLUDE, SP) CY_BW(DV, F, CY_SELFPACED_HARD, SP) \
+    CY_BW(DV, F, CY_SELFPACED_SOFT, SP)
+    CY_BW4(256, false, false) CY_BW4(256, true, false) CY_BW4(128, false, false) CY_BW4(128, true, false)
+    CY_BW4(256, false, true) CY_BW4(128, false, true)
 #undef CY_BW4
 #undef CY_BW
     if (rc) {
@@ -1105,7 +1217,9 @@ int infonce_bwd_tc(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, 
         const int64_t n8 = rows * (d / 8);
         const unsigned g = (unsigned)((n8 + 255) / 256);
         uint16_t* out = reinterpret_cast<uint16_t*>(dz);
-        if (d == 256 && f16) infonce_tc_convert_kernel<256, true><<<g, 256, 0, st>>>(dz32, splits, rows, rows_pad, row_begin, gscale, out_scale, out, lddz);
+        if (split && d == 256) infonce_tc_convert_kernel<256, false, true><<<g, 256, 0, st>>>(dz32, splits, rows, rows_pad, row_begin, gscale, out_scale, out, lddz);
+        else if (split) infonce_tc_convert_kernel<128, false, true><<<g, 256, 0, st>>>(dz32, splits, rows, rows_pad, row_begin, gscale, out_scale, out, lddz);
+        else if (d == 256 && f16) infonce_tc_convert_kernel<256, true><<<g, 256, 0, st>>>(dz32, splits, rows, rows_pad, row_begin, gscale, out_scale, out, lddz);
         else if (d == 256) infonce_tc_convert_kernel<256, false><<<g, 256, 0, st>>>(dz32, splits, rows, rows_pad, row_begin, gscale, out_scale, out, lddz);
         else if (f16) infonce_tc_convert_kernel<128, true><<<g, 256, 0, st>>>(dz32, splits, rows, rows_pad, row_begin, gscale, out_scale, out, lddz);
         else infonce_tc_convert_kernel<128, false><<<g, 256, 0, st>>>(dz32, splits, rows, rows_pad, row_begin, gscale, out_scale, out, lddz);

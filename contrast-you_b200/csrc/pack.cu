@@ -163,7 +163,39 @@ unpack_rows_kernel(const uint8_t* __restrict__ dz, int dtype, int64_t n, int64_t
     }
 }
 
+// fp32 rows -> [hi | lo] bf16 halves (CY_F32_SPLIT): hi = bf16(v) (round to nearest), lo = bf16(v - hi); one warp per row
+__global__ void __launch_bounds__(256)
+pack_split_kernel(const float* __restrict__ f1, const float* __restrict__ f2, int64_t n, int64_t d, int64_t ld1, int64_t ld2,
+                  const int64_t* __restrict__ order, __nv_bfloat16* __restrict__ zs, int* __restrict__ bad_rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= 2 * n) return;
+    const int64_t src = order ? order[row] : row;
+    const float* s = src < n ? f1 + src * ld1 : f2 + (src - n) * ld2;
+    __nv_bfloat16* o = zs + row * 2 * d;
+    float ss = 0.f;
+    for (int64_t c = lane; c < d; c += 32) {
+        const float v = s[c];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        o[c] = hi;
+        o[d + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    if (lane == 0 && bad_rows) {
+        if (!(fabsf(sqrtf(ss) - 1.f) <= 1e-8f + 1e-5f)) atomicAdd(bad_rows, 1);      // is_normalized on the fp32 values
+    }
+}
+
 }  // namespace
+
+int infonce_pack_split(const void* f1, const void* f2, int64_t n, int64_t d, int64_t ld1, int64_t ld2, const int64_t* order, void* zs,
+                       int* bad_rows, cudaStream_t st) {
+    const unsigned grid = (unsigned)((2 * n + 7) / 8);
+    pack_split_kernel<<<grid, 256, 0, st>>>((const float*)f1, (const float*)f2, n, d, ld1, ld2, order, (__nv_bfloat16*)zs, bad_rows);
+    CY_CHECK_LAUNCH("infonce_pack_split");
+    return CY_OK;
+}
 
 int infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_t d, int64_t ld1, int64_t ld2, const int64_t* order,
                  void* z, int* bad_rows, float* inv_norm, const int64_t* pix_off, int64_t chan_stride, cudaStream_t st) {

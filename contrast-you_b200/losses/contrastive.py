@@ -216,12 +216,20 @@ class _FusedInfoNCE(torch.autograd.Function):
         dev = f1.device
         dt = L.dtype_code(f1)
         need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        # fp32 views that qualify for the tensor kernels travel as [hi | lo] bf16 halves (CY_F32_SPLIT): three MMA terms per
+        # product, fp32 parity, fp32 gradient
+        split = (f1.dtype == torch.float32 and gather is None and not normalize and fp32_split_eligible(N, d, variant, path))
+        ldz = 2 * d if split else d
         with L.guard(f1):
             st = L.stream_ptr(dev)
-            z = torch.empty(N, d, dtype=f1.dtype, device=dev)
+            z = torch.empty(N, ldz, dtype=torch.bfloat16 if split else f1.dtype, device=dev)
             bad = torch.zeros(1, dtype=torch.int32, device=dev) if (check_norm and not normalize) else None
             inv_norm = torch.empty(N, dtype=torch.float32, device=dev) if normalize else None
-            if gather is None:
+            if split:
+                dt = L.CY_F32_SPLIT
+                L.check(lib.cy_infonce_pack_split(f1.data_ptr(), f2.data_ptr(), n, d, f1.stride(0), f2.stride(0), L.ptr(order),
+                                                  z.data_ptr(), L.ptr(bad), st), "cy_infonce_pack_split")
+            elif gather is None:
                 L.check(lib.cy_infonce_pack(f1.data_ptr(), f2.data_ptr(), dt, n, d, f1.stride(0), f2.stride(0), L.ptr(order), z.data_ptr(),
                                             L.ptr(bad), L.ptr(inv_norm), st), "cy_infonce_pack")
             else:
@@ -233,10 +241,10 @@ class _FusedInfoNCE(torch.autograd.Function):
             ws_bytes = lib.cy_infonce_workspace_bytes(N, d, dt, variant, path)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             zp, lp = z.data_ptr(), labels.data_ptr()
-            L.check(lib.cy_infonce_fwd(zp, dt, N, d, d, lp, None, 0, N, inv_t, variant, path, stats.data_ptr(), xstat.data_ptr(),
+            L.check(lib.cy_infonce_fwd(zp, dt, N, d, ldz, lp, None, 0, N, inv_t, variant, path, stats.data_ptr(), xstat.data_ptr(),
                                        ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd")
             if variant != L.CY_SUPCON:
-                L.check(lib.cy_infonce_fwd_pass2(zp, dt, N, d, d, lp, None, 0, N, inv_t, variant, gamma, path, stats.data_ptr(),
+                L.check(lib.cy_infonce_fwd_pass2(zp, dt, N, d, ldz, lp, None, 0, N, inv_t, variant, gamma, path, stats.data_ptr(),
                                                  xstat.data_ptr(), ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd_pass2")
             L.check(lib.cy_infonce_loss(N, variant, xstat.data_ptr(), out8.data_ptr(), L.ptr(bad), L.ptr(overflow), ws.data_ptr(),
                                         ws_bytes, st), "cy_infonce_loss")
@@ -245,8 +253,8 @@ class _FusedInfoNCE(torch.autograd.Function):
                 status.post(out8)
             dz = None
             if need_grad:
-                dz = torch.empty_like(z)
-                L.check(lib.cy_infonce_bwd(zp, dt, N, d, d, lp, None, 0, N, inv_t, variant, gamma, path, xstat.data_ptr(),
+                dz = torch.empty(N, d, dtype=f1.dtype, device=dev)
+                L.check(lib.cy_infonce_bwd(zp, dt, N, d, ldz, lp, None, 0, N, inv_t, variant, gamma, path, xstat.data_ptr(),
                                            _unit_scale(dev).data_ptr(), dz.data_ptr(), d, ws.data_ptr(), ws_bytes, st),
                         "cy_infonce_bwd")
         ctx.shape = (n, d)
@@ -283,6 +291,12 @@ class _FusedInfoNCE(torch.autograd.Function):
                 L.check(lib.cy_infonce_unpack(dz.data_ptr(), L.dtype_code(dz), n, d, d, L.ptr(order), g1.data_ptr(), g2.data_ptr(),
                                               L.ptr(z), L.ptr(inv_norm), gscale.data_ptr(), L.stream_ptr(dz.device)), "cy_infonce_unpack")
         return g1, g2, None, None, None, None, None, None, None, None, None, None, None
+
+
+def fp32_split_eligible(N: int, d: int, variant: int, path: int) -> bool:
+    """fp32 views of this shape run on the tensor kernels as [hi | lo] bf16 halves (CY_F32_SPLIT; 64-column forward tiles)"""
+    ok = d in (128, 256) and N >= 256 and (variant == L.CY_SUPCON or N <= 4096 * 64)
+    return ok and (path == L.CY_PATH_TCGEN05 or (path == L.CY_PATH_AUTO and N >= 1024))
 
 
 def tensor_core_eligible(z: Tensor, labels, codes, variant: int, path: int) -> bool:
@@ -427,6 +441,8 @@ class _ContrastBase(nn.Module):
         mask-free epilogue runs everywhere else and the second sweep of exclude / self-paced visits O(1) tiles per row block"""
         d = f1.shape[1]
         variant = self._kernel_variant()
+        if f1.dtype == torch.float32:
+            return f1.dim() == 2 and not getattr(self, "_normalize_input", False) and fp32_split_eligible(2 * n, d, variant, self._path)
         ok = (f1.dtype in (torch.bfloat16, torch.float16) and d in (128, 256) and 2 * n >= 256
               and (variant == L.CY_SUPCON or 2 * n <= 4096 * 128))
         return ok and (self._path == L.CY_PATH_TCGEN05 or (self._path == L.CY_PATH_AUTO and 2 * n >= 1024))

@@ -30,6 +30,10 @@ extern "C" {
 #define CY_F32 0
 #define CY_BF16 1
 #define CY_F16 2
+/* fp32 embeddings split for the tensor kernels: z is [N, 2 d] bf16, row = [hi (d) | lo (d)] with fp32 value = hi + lo
+ * (cy_infonce_pack_split writes it); products hi.hi + hi.lo + lo.hi are good to 2^-16, the gradient dz is fp32 [N, d].
+ * Accepted by cy_infonce_fwd / _fwd_pass2 / _bwd on the tcgen05 path only (d in {128, 256}). */
+#define CY_F32_SPLIT 3
 
 /* InfoNCE variants (cy_infonce_*: `variant`) */
 #define CY_SUPCON 0         /* SupConLoss1, exclude_other_pos=False      contrastive.py:92            */
@@ -154,6 +158,11 @@ int cy_labels_canonicalize(const void* src, int src_kind, int64_t n, int32_t* ds
  * the is_normalized check is skipped in that mode. */
 int cy_infonce_pack(const void* f1, const void* f2, int dtype, int64_t n, int64_t d, int64_t ld1, int64_t ld2,
                     const int64_t* order, void* z, int32_t* bad_rows, float* inv_norm, void* stream);
+
+/* fp32 feeder of the tensor kernels: as cy_infonce_pack for float32 views (cat, permutation, is_normalized counted on the fp32
+ * values), but every row is written as [hi | lo] bf16 halves (CY_F32_SPLIT): zs [2n, 2 d] bf16. */
+int cy_infonce_pack_split(const void* f1, const void* f2, int64_t n, int64_t d, int64_t ld1, int64_t ld2, const int64_t* order,
+                          void* zs, int32_t* bad_rows, void* stream);
 
 /* Adjoint of cy_infonce_pack: scatters dz [2n, d] (row pitch lddz) back to the two views, g(order[i]) = dz[i];
  * g1, g2 are contiguous [n, d].  With (z, inv_norm) from a normalising pack it also applies the Jacobian of the

@@ -544,6 +544,40 @@ def test_tcgen05_ragged_n_and_d128(N, d):
     assert _relerr(torch.cat([f1.grad, f2.grad]).float().cpu().numpy(), o["grad"]) <= BF16_TOL
 
 
+@pytest.mark.parametrize("kind", ["supcon", "exclude", "soft"])
+@pytest.mark.parametrize("N,classes,d", [(1024, 16, 256), (3000, 40, 256), (4096, 0, 128), (8192, 512, 256)])
+def test_tcgen05_fp32_inputs_split_path(kind, N, classes, d):
+    """fp32 embeddings on the tensor kernels ([hi | lo] bf16 halves, three MMA terms per product, fp32 gradient): the fp32
+    parity bar of north_star — loss and gradients within 1e-4 of the float64 oracle (numpy at the small sizes, the chunked C
+    oracle for SupConLoss1 at the larger ones) and of this library's fp32 CUDA-core path"""
+    torch.manual_seed(7 * N + d)
+    n = N // 2
+    z = torch.nn.functional.normalize(torch.randn(N, d, device=DEV), dim=1)
+    lab = torch.randint(0, classes, (n,)) if classes else torch.arange(n)
+
+    def make(path):
+        if kind == "supcon":
+            return SupConLoss1(path=path)
+        if kind == "exclude":
+            return SupConLoss1(exclude_other_pos=True, path=path)
+        crit = SelfPacedSupConLoss(weight_update="soft", path=path)
+        crit.set_gamma(8.0)
+        return crit
+    out = {}
+    for path in ("tcgen05", "simt"):
+        f1, f2 = z[:n].clone().requires_grad_(), z[n:].clone().requires_grad_()
+        loss = make(path)(f1, f2, target=lab.tolist())
+        (loss * 1.7).backward()
+        assert f1.grad.dtype == torch.float32
+        out[path] = (loss.item(), torch.cat([f1.grad, f2.grad]).cpu().numpy())
+    assert out["tcgen05"][0] == pytest.approx(out["simt"][0], rel=FP32_TOL)
+    assert _relerr(out["tcgen05"][1], out["simt"][1]) <= FP32_TOL
+    if kind == "supcon":
+        o = c_oracle.supcon_fwd_bwd(z.cpu().numpy(), np.tile(lab.numpy().astype(np.int32), 2), t=0.07, prec=1)
+        assert out["tcgen05"][0] == pytest.approx(o["loss"], rel=FP32_TOL)
+        assert _relerr(out["tcgen05"][1], 1.7 * o["grad"]) <= FP32_TOL
+
+
 def test_tcgen05_gradients_are_bitwise_reproducible():
     """the column-split backward sums fp32 slabs in a fixed order (no atomics): two runs give identical bits"""
     from contrast_you_b200.losses.contrastive import info_nce, _canonical_labels
