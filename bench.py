@@ -489,7 +489,8 @@ def main():
     stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev)
     xstat = torch.zeros(N, 4, dtype=torch.float32, device=dev)
     out4 = torch.zeros(8, device=dev)
-    ws_b = lib.cy_infonce_workspace_bytes(N, d, L.CY_BF16, variant, path)      # (same size for the split format)
+    ws_b = lib.cy_infonce_workspace_bytes(N, d, L.CY_F32_SPLIT if (in_dtype == torch.float32 and not use_autocast) else L.CY_BF16,
+                                          variant, path)
     ws = torch.empty(ws_b, dtype=torch.uint8, device=dev)
     one = torch.ones(1, device=dev)
     dz = torch.empty_like(z_all)

@@ -59,7 +59,7 @@ int infonce_unpack(const void*, int, int64_t, int64_t, int64_t, const int64_t*, 
                    const int64_t*, int64_t, cudaStream_t);
 // infonce_tc.cu
 bool infonce_tc_supported(int dtype, int64_t N, int64_t d, int64_t ldz, const uint8_t* codes, int variant);
-size_t infonce_tc_workspace_bytes(int64_t N, int64_t d);
+size_t infonce_tc_workspace_bytes(int64_t N, int64_t d, bool split);
 size_t infonce_loss_workspace_bytes(int64_t N);
 int infonce_fwd_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, int, float*, float*, void*, size_t,
                    cudaStream_t);
@@ -147,7 +147,7 @@ size_t cy_infonce_workspace_bytes(int64_t N, int64_t d, int dtype, int variant, 
     (void)variant;
     const size_t loss = infonce_loss_workspace_bytes(N);
     if (path == CY_PATH_SIMT || dtype == CY_F32) return loss;
-    const size_t tc = infonce_tc_workspace_bytes(N, d);
+    const size_t tc = infonce_tc_workspace_bytes(N, d, dtype == CY_F32_SPLIT);
     return (tc > loss ? tc : loss) + 16;
 }
 

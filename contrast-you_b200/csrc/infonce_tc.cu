@@ -963,14 +963,20 @@ bool infonce_tc_supported(int dtype, int64_t N, int64_t d, int64_t ldz, const ui
 
 static int sm_count() { return device_sm_count(); }
 
-// column splits of the backward: minimise waves x tiles-per-CTA (one CTA per SM), at least 16 tiles per CTA
-static int bwd_splits(int64_t N, int64_t row_blocks) {
+// column splits of the backward: minimise waves x tiles-per-CTA (one CTA per SM), at least 16 tiles per CTA.
+// max_tps > 0 caps the tiles one CTA accumulates in tensor memory: the fp32 (split) path needs 1e-4 gradients, and the
+// tensor core's fp32 accumulator loses ~2^-26 of the running sum per accumulation step on average (measured: 1.2e-4 of the
+// gradient max-norm after 12288 steps at N = 65536 with 2 splits) — shorter chains, summed by the conversion kernel with
+// round-to-nearest adds, keep it at ~1e-5.
+static int bwd_splits(int64_t N, int64_t row_blocks, int64_t max_tps = 0) {
     const int64_t sms = sm_count(), rb = row_blocks, nt = (N + BWD_BN - 1) / BWD_BN;
     int best = 1;
     double best_cost = 1e30;
-    for (int s = 1; s <= 16; ++s) {
+    const int smax = max_tps > 0 ? 64 : 16;
+    for (int s = 1; s <= smax; ++s) {
         if (s > 1 && nt / s < 16) break;
         const int64_t tps = (nt + s - 1) / s;
+        if (max_tps > 0 && tps > max_tps && nt / (s + 1) >= 16 && s < smax) continue;      // chain too long: split further
         if ((int64_t)(s - 1) * tps >= nt) continue;                  // the last split would be empty
         const int64_t waves = (rb * s + sms - 1) / sms;
         const double cost = (double)waves * (double)(tps + 6);      // + fixed per-CTA cost (A load, drain) in tile units
@@ -992,7 +998,9 @@ static int fwd_splits(int64_t N, int64_t row_blocks, int bn) {
 
 constexpr size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-size_t infonce_tc_workspace_bytes(int64_t N, int64_t d) {
+constexpr int64_t SPLIT_MAX_TPS = 128;     // fp32 path: at most 128 column tiles (8192 columns) accumulated per CTA
+
+size_t infonce_tc_workspace_bytes(int64_t N, int64_t d, bool split) {
     if (d != 256 && d != 128) return 0;
     // forward: worst case over row ranges is a single 128-row block -> the most column splits
     const int smax = fwd_splits(N, 1, 64);
@@ -1003,7 +1011,7 @@ size_t infonce_tc_workspace_bytes(int64_t N, int64_t d) {
     const int64_t rb_all = (N + TC_BM - 1) / TC_BM;
     size_t bwd = 0;
     for (int64_t rb = 1; rb <= rb_all; ++rb) {
-        const int s = bwd_splits(N, rb);
+        const int s = bwd_splits(N, rb, split ? SPLIT_MAX_TPS : 0);
         if (s > 1) {
             const size_t b = (size_t)s * rb * TC_BM * d * sizeof(float);
             if (b > bwd) bwd = b;
@@ -1186,7 +1194,7 @@ int infonce_bwd_tc(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, 
     const bool f16 = dtype == CY_F16;
     const float out_scale = (inv_t / (float)N) * (f16 ? (1.f / 1024.f) : 1.f);
     const int64_t rb = (rows + TC_BM - 1) / TC_BM;
-    const int splits = bwd_splits(N, rb);
+    const int splits = bwd_splits(N, rb, split ? SPLIT_MAX_TPS : 0);
     const int nt = (int)((N + BWD_BN - 1) / BWD_BN);
     const int tps = (nt + splits - 1) / splits;
     float* dz32 = nullptr;
