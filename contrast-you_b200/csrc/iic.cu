@@ -570,24 +570,19 @@ int iic_joint_mma(const void* x, const void* y, int dtype, int B, int K, int H, 
 int iic_bwd_mma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
                 const float* gscale, void* dx, void* dy, cudaStream_t st);
 
-#ifdef CY_EXPERIMENTAL
-// iic_umma.cu (tcgen05 adjoint for padding = 1: TMA boxes -> bf16 hi/lo channels-last rows -> UMMA into TMEM).  Built
-// only with `make EXPERIMENTAL=1`: slower than the mma.sync adjoint and outside the test gate (profiles/README.md).
-int iic_bwd_umma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
-                 const float* gscale, void* dx, void* dy, cudaStream_t st);
+// iic_bwd_tc.cu (tcgen05 adjoint for padding = 1, K <= 16, fp32: pixels on the TMEM lanes, A slots written by converter warps,
+// 18 small MMAs per output row; CY_ERR_UNSUPPORTED for shapes it does not take).  The default adjoint.
+int iic_bwd_tc(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
+               const float* gscale, void* dx, void* dy, cudaStream_t st);
 
-static bool umma_enabled() {
+static bool tc_enabled() {
     static int on = -1;
     if (on < 0) {
-        // EXPERIMENTAL, off by default: CY_IIC_UMMA=1 routes the padding-1 adjoint through iic_umma.cu.  Parity holds, but at
-        // config 3 it runs at ~140 us against 90 us for the mma.sync kernel (per-row handshakes between its warp roles are
-        // latency-bound, profiles/README.md), so it is not part of the tested product path.
-        const char* e = getenv("CY_IIC_UMMA");
-        on = (e && e[0] == '1') ? 1 : 0;
+        const char* e = getenv("CY_IIC_TC");      // CY_IIC_TC=0 pins the mma.sync adjoint (A/B measurements)
+        on = (e && e[0] == '0') ? 0 : 1;
     }
-    return on != 0;
+    return on == 1;
 }
-#endif
 
 static bool mma_enabled() {
     static int on = -1;
@@ -750,12 +745,10 @@ static int dispatch_bwd(int pad, int kc, const void* x, const void* y, int dtype
 int iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
             const float* gscale, void* dx, void* dy, cudaStream_t st) {
     const int T = 2 * pad + 1;
-#ifdef CY_EXPERIMENTAL
-    if (mma_enabled() && umma_enabled()) {
-        const int rc = iic_bwd_umma(x, y, dtype, B, K, H, W, pad, djoint, gscale, dx, dy, st);
+    if (mma_enabled() && tc_enabled()) {
+        const int rc = iic_bwd_tc(x, y, dtype, B, K, H, W, pad, djoint, gscale, dx, dy, st);
         if (rc != CY_ERR_UNSUPPORTED) return rc;
     }
-#endif
     if (mma_enabled()) {
         const int rc = iic_bwd_mma(x, y, dtype, B, K, H, W, pad, djoint, gscale, dx, dy, st);
         if (rc != CY_ERR_UNSUPPORTED) return rc;

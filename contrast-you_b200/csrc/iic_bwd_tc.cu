@@ -1,0 +1,433 @@
+// IIC adjoint (padding = 1, K <= 16, fp32 maps) on the tcgen05 tensor cores — the default adjoint of cy_iic_bwd.
+//
+//   dL/dy[k2, h, w] = sum_{k1, dy, dx} G[k1, k2, dy, dx] * x[k1, h + dy - 1, w + dx - 1]      (and the mirrored sum for dL/dx)
+//
+// is a 3x3 convolution with K -> K channels: out[o, p] = sum_k A[p, k] * Wt[o, k], k = (dy, dx, c).  Pixels are the M
+// dimension of the MMA (one TMEM lane per pixel), the K output channels its N dimension (N = 16) and the 9 K taps its
+// reduction dimension.  The legacy mma.sync adjoint (iic_mma.cu) is bound by the warp schedulers (an HMMA holds the issue
+// port for its 8 pipe cycles on sm_100a, so tensor and CUDA-core instructions add up); tcgen05.mma is asynchronous and
+// issued by one thread, which leaves the schedulers to the conversion work.  One persistent CTA per SM, four warp roles:
+//
+//   converters (2 sets x 4 warps)  thread = input pixel = TMEM lane.  For input row r the thread loads its K channel values
+//                         straight from global memory (coalesced 128-byte rows, prefetched 3 rows ahead in registers — no
+//                         shared-memory staging), splits them into bf16 hi / lo parts (integer / FADD / PRMT only), takes
+//                         the copies shifted by one and two columns from the neighbour lanes by shuffle and writes ONE
+//                         A slot [lane = pixel][k = (dx, c)] x {hi, lo} to tensor memory (tcgen05.st).  A warp owns 28
+//                         output pixels + the halo of its shifts, so shuffles never cross a warp (224 = 8 x 28).
+//   issuers    (2 warps, rows alternate)  output row h takes its three dy taps from the A slots of input rows h-1, h, h+1:
+//                         per output row 3 x KS x 3 MMAs (M 128, N 16, K 16; A from TMEM, B = weights from shared memory),
+//                         hi*hi + lo*hi + hi*lo, accumulating into one 16-column D slot.  An A slot is written once and
+//                         read by three output rows; its "empty" barrier counts the three tcgen05.commit arrivals.
+//   epilogue   (2 sets x 4 warps)  thread = output pixel: tcgen05.ld of the K live columns of a finished D slot, K
+//                         coalesced 112-byte stores.  No state is carried between rows.
+//
+// Work split: the 2 (sides) x B x ceil(W / 112) column strips of H rows form one linear row space that is cut into equal
+// contiguous ranges, one per CTA; a range that starts or ends inside a strip converts two extra halo rows.
+// Measured on B200 (profiles/probes/probe_umma_issue2): N = 16 MMAs execute in 9 clk, one thread issues one every ~20 clk
+// (two issuers: pipe-bound), a 32-column tcgen05.st + wait costs ~58 clk per warp, a 16-column tcgen05.ld ~39 clk.
+//
+// Precision: v = hi + lo (hi = bf16 rounded, lo = bf16 of the exact remainder); products hi*hi + lo*hi + hi*lo are good to
+// 2^-16 relative, fp32 accumulation in TMEM: gradients agree with the float64 oracle to ~1e-5 of their max-norm.
+// Reference: the autograd adjoint of compute_joint_2D's F.conv2d (contrastyou/losses/discreteMI.py:225-243).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cy {
+
+using namespace tc;
+
+namespace {
+
+constexpr int T_QPX = 28;                        // output pixels per lane quarter (lanes 28..31: halo of the column shifts)
+constexpr int T_TWO = 4 * T_QPX;                 // output columns per strip
+constexpr int T_NA = 8;                          // A slots (input rows) in tensor memory
+constexpr int T_ND = 8;                          // D slots (output rows)
+constexpr int T_NISS = 2;                        // issuer warps: warps 0, 1
+constexpr int T_NCS = 2;                         // converter sets
+constexpr int T_NES = 2;                         // epilogue sets
+constexpr int T_WALLOC = 2;                      // warp 2 owns the TMEM allocation; warp 3 idles
+constexpr int T_CONV0 = 4;
+constexpr int T_EPI0 = T_CONV0 + 4 * T_NCS;
+constexpr int T_THREADS = 32 * (T_EPI0 + 4 * T_NES);
+constexpr int T_PF = 4;                          // converter prefetch depth (own rows): cp.async groups in flight per warp
+constexpr int T_WTILE = 512;                     // one weight tile: [n 16][k 16] bf16, no-swizzle K-major core matrices
+
+struct TcGeom {
+    int B, K, H, W;
+    int TW2;                                     // strips per image row
+    int rows_total;                              // 2 * B * TW2 * H
+};
+
+// The row-space range [R0, R1) of one CTA is walked as segments (a segment never crosses a strip).  Segment k starts at R0
+// (k = 0) or at the k-th strip boundary after it; it produces n_out output rows from n_out + 2 input rows.
+struct Seg {
+    int unit, hb, n_out;
+};
+__device__ __forceinline__ bool seg_at(int R0, int R1, int H, int k, Seg& s) {
+    const int start = k == 0 ? R0 : (R0 / H + k) * H;
+    if (start >= R1) return false;
+    s.unit = start / H;
+    const int ue = (s.unit + 1) * H, end = ue < R1 ? ue : R1;
+    s.hb = start - s.unit * H;
+    s.n_out = end - start;
+    return true;
+}
+
+// unit -> (side, image, strip).  Images run backwards and the two sides alternate: the joint kernel has just streamed x and y
+// front to back, so the tail of both tensors is what the 126 MB L2 still holds.
+__device__ __forceinline__ void unit_decode(const TcGeom& g, int unit, int& side, int& b, int& tw) {
+    tw = unit % g.TW2;
+    side = (unit / g.TW2) & 1;
+    b = g.B - 1 - unit / (2 * g.TW2);
+}
+
+// (v0, v1) -> packed bf16 pairs (v0 in the low half): hi = round-half-up bf16, lo = truncated bf16 of the exact remainder
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const uint32_t h0 = (__float_as_uint(v0) + 0x8000u) & 0xffff0000u;
+    const uint32_t h1 = (__float_as_uint(v1) + 0x8000u) & 0xffff0000u;
+    hi = __byte_perm(h0, h1, 0x7632);
+    lo = __byte_perm(__float_as_uint(v0 - __uint_as_float(h0)), __float_as_uint(v1 - __uint_as_float(h1)), 0x7632);
+}
+
+// 4-byte cp.async (LDGSTS) with zero fill: bytes = 0 writes zeros and reads nothing
+__device__ __forceinline__ void cp_async_4(uint32_t smem_dst, const float* src, uint32_t bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// mbarrier wait for roles that are expected to wait: try_wait with a suspend-time hint, so the warp sleeps in hardware until
+// the phase completes instead of re-issuing the probe (the spin loops were 20 % of all issued instructions in the first
+// profile of this kernel)
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity), "r"(4000u)
+        : "memory");
+}
+
+__device__ __forceinline__ float lds_f32_own(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+template <int NW>
+__device__ __forceinline__ void tmem_st_words(uint32_t taddr, const uint32_t* w) {
+    if constexpr (NW == 8) {
+        tmem_st_32x8(taddr, *reinterpret_cast<const uint32_t (*)[8]>(w));
+    } else if constexpr (NW == 16) {
+        tmem_st_32x16(taddr, *reinterpret_cast<const uint32_t (*)[16]>(w));
+    } else {
+        static_assert(NW == 24, "A slot plane: 8, 16 or 24 words");
+        tmem_st_32x16(taddr, *reinterpret_cast<const uint32_t (*)[16]>(w));
+        tmem_st_32x8(taddr + 16, *reinterpret_cast<const uint32_t (*)[8]>(w + 16));
+    }
+}
+
+template <int KH>                                // channel pairs: K <= 2 * KH
+__global__ void __launch_bounds__(T_THREADS, 1)
+iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGeom g, const float* __restrict__ djoint,
+                  const float* __restrict__ gscale, float* __restrict__ dx_out, float* __restrict__ dy_out) {
+    constexpr int KC = 2 * KH;                   // channels carried per pixel (zero past K)
+    constexpr int KS = (3 * KH + 7) / 8;         // K-steps of 16 per input row: k = dxx * KC + c
+    constexpr int PW = KS * 8;                   // 32-bit words per plane (hi or lo) of an A slot
+    constexpr int ACOLS = 2 * PW;
+    constexpr uint32_t A0 = T_ND * 16;           // TMEM columns: [0, 128) D slots, [128, 128 + 8 * ACOLS) A slots
+    static_assert(A0 + T_NA * ACOLS <= 512, "TMEM budget");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* wsm = smem;                         // weights [side 2][dy 3][ks KS][part 2] tiles of T_WTILE bytes
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + 2 * 3 * KS * 2 * T_WTILE);
+    uint64_t* a_full = bars;                     // [T_NA]  the four quarter warps have written the slot
+    uint64_t* a_empty = a_full + T_NA;           // [T_NA]  the MMAs of the three output rows that read the slot are complete
+    uint64_t* d_full = a_empty + T_NA;           // [T_ND]  the MMAs of the output row are complete
+    uint64_t* d_empty = d_full + T_ND;           // [T_ND]  the four epilogue warps have read the slot
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + T_ND);
+    float* ring0 = reinterpret_cast<float*>(tmem_slot + 4);   // converter staging: [warp 4 * T_NCS][stage T_PF][channel KC][lane 32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = g.K;
+
+    // ---- one-time setup: weights in UMMA layout (hi / lo), barriers, tensor memory
+    {
+        const float scale = gscale[0];
+        for (int i = threadIdx.x; i < 2 * 3 * KS * 16 * 16; i += T_THREADS) {
+            const int k = i % 16, n = (i / 16) % 16, ks = (i / 256) % KS, dyy = (i / (256 * KS)) % 3, side = i / (256 * KS * 3);
+            const int kk = ks * 16 + k, dxx = kk / KC, c = kk % KC, o = n;
+            float w = 0.f;
+            if (dxx < 3 && c < K && o < K) {
+                // side 0 (dL/dy from x): Wt[o = k2][c = k1][dy][dx] = G[k1, k2, dy, dx]
+                // side 1 (dL/dx from y): Wt[o = k1][c = k2][dy][dx] = G[k1, k2, 2 - dy, 2 - dx]
+                w = side == 0 ? djoint[((c * K + o) * 3 + dyy) * 3 + dxx] : djoint[((o * K + c) * 3 + (2 - dyy)) * 3 + (2 - dxx)];
+                w *= scale;
+            }
+            const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+            const uint32_t tile = (uint32_t)(((side * 3 + dyy) * KS + ks) * 2) * T_WTILE;
+            const uint32_t off = (n / 8) * 256 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2;
+            *reinterpret_cast<__nv_bfloat16*>(wsm + tile + off) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(wsm + tile + T_WTILE + off) = lo;
+        }
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < T_NA; ++i) { mbar_init(a_full + i, 4); mbar_init(a_empty + i, 3); }
+            for (int i = 0; i < T_ND; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
+            fence_barrier_init();
+        }
+        if (warp == T_WALLOC) {
+            tmem_alloc(tmem_slot, 512);
+            tmem_relinquish();
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    const uint32_t tmem = *tmem_slot;
+    // this CTA's range of the row space
+    const int R0 = (int)(((long long)g.rows_total * blockIdx.x) / gridDim.x);
+    const int R1 = (int)(((long long)g.rows_total * (blockIdx.x + 1)) / gridDim.x);
+    const int plane = g.H * g.W;                 // host checks K * H * W < 2^31
+
+    if (warp < T_NISS) {
+        // ------------------------------------------------------------------------------------------ MMA issuers
+        if (elect_one()) {
+            constexpr uint32_t idesc = idesc_bf16_f32(128, 16, 0, 0);
+            const uint64_t wdesc0 = smem_desc_noswz(smem_u32(wsm), 128, 256);
+            uint32_t ar0 = 0, orow = 0;
+            Seg sg;
+            for (int k = 0; seg_at(R0, R1, g.H, k, sg); ++k) {
+                int side, b, tw;
+                unit_decode(g, sg.unit, side, b, tw);
+                const int n_out = sg.n_out;
+                const uint64_t wside = wdesc0 + (uint64_t)((side * 3 * KS * 2 * T_WTILE) >> 4);
+                for (int i = 0; i < n_out; ++i, ++orow) {
+                    if ((int)(orow % T_NISS) != warp) continue;
+                    const uint32_t a = ar0 + (uint32_t)i;
+                    // this issuer's previous row (two rows back) has already observed A row a; rows a+1, a+2 are new to it
+                    if (i < T_NISS) mbar_wait(a_full + (a % T_NA), (a / T_NA) & 1u);
+                    mbar_wait(a_full + ((a + 1) % T_NA), ((a + 1) / T_NA) & 1u);
+                    mbar_wait(a_full + ((a + 2) % T_NA), ((a + 2) / T_NA) & 1u);
+                    mbar_wait(d_empty + (orow % T_ND), ((orow / T_ND) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d = tmem + (orow % T_ND) * 16;
+#pragma unroll
+                    for (int dyy = 0; dyy < 3; ++dyy) {
+                        const uint32_t ah = tmem + A0 + ((a + dyy) % T_NA) * ACOLS, al = ah + PW;
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            const uint64_t bh = wside + (uint64_t)(((dyy * KS + ks) * 2 * T_WTILE) >> 4);
+                            const uint64_t bl = bh + (uint64_t)(T_WTILE >> 4);
+                            if (dyy == 0 && ks == 0) umma_bf16_ts_c<0>(d, ah + ks * 8, bh, idesc);
+                            else umma_bf16_ts_c<1>(d, ah + ks * 8, bh, idesc);
+                            umma_bf16_ts_c<1>(d, al + ks * 8, bh, idesc);
+                            umma_bf16_ts_c<1>(d, ah + ks * 8, bl, idesc);
+                        }
+                    }
+                    umma_commit(d_full + (orow % T_ND));
+                    // every A slot expects three arrivals; at the ends of a segment a slot has fewer readers and the first /
+                    // last output row stands in for the missing ones
+#pragma unroll
+                    for (int dyy = 0; dyy < 3; ++dyy) {
+                        const int cnt = 1 + (i == 0 ? 2 - dyy : 0) + (i == n_out - 1 ? dyy : 0);
+                        for (int c = 0; c < cnt; ++c) umma_commit(a_empty + ((a + dyy) % T_NA));
+                    }
+                }
+                ar0 += (uint32_t)n_out + 2u;
+            }
+        }
+        __syncwarp();
+    } else if (warp >= T_CONV0 && warp < T_EPI0) {
+        // ------------------------------------------------------------------------------------------ converters
+        const int cset = (warp - T_CONV0) >> 2, quarter = warp & 3;
+        // A cursor over this warp's own input rows (global input-row index == cset mod T_NCS).  Everything that needs a
+        // division is done once per segment; a step is a pointer increment.
+        struct Cursor {
+            const float* p;      // &in[b, 0, h, col] of this lane (col clamped to 0 when the lane is outside the image)
+            int h, j, n_in, k;   // image row, index inside the segment, input rows of the segment, segment number
+            uint32_t ar0;        // global index of the segment's first input row
+            bool lane_ok, done;
+        };
+        auto enter = [&](Cursor& c) {                                  // position on the first own row of segment c.k
+            Seg sg;
+            c.done = !seg_at(R0, R1, g.H, c.k, sg);
+            if (c.done) return;
+            int side, b, tw;
+            unit_decode(g, sg.unit, side, b, tw);
+            const int col = tw * T_TWO + quarter * T_QPX - 1 + lane;
+            c.lane_ok = col >= 0 && col < g.W;
+            c.n_in = sg.n_out + 2;
+            c.j = (int)((cset - c.ar0) & (T_NCS - 1));
+            c.h = sg.hb - 1 + c.j;
+            c.p = (side ? y : x) + (size_t)b * K * plane + (c.lane_ok ? col : 0) + (long long)c.h * g.W;
+        };
+        auto step = [&](Cursor& c) {
+            c.j += T_NCS;
+            if (c.j < c.n_in) {
+                c.h += T_NCS;
+                c.p += T_NCS * g.W;
+            } else {
+                c.ar0 += (uint32_t)c.n_in;
+                ++c.k;
+                enter(c);
+            }
+        };
+        // Staging ring of this warp: each lane copies its own pixel's K channel values with 4-byte cp.async (zero fill outside
+        // the image) and reads them back itself, so completion is tracked per row by cp.async groups (no register
+        // scoreboards shared between the rows in flight, no cross-lane hand-off).
+        const uint32_t ring = smem_u32(ring0) + (uint32_t)(((warp - T_CONV0) * T_PF * KC) * 32 + lane) * 4u;
+        auto issue_row = [&](const Cursor& c, int stage) {
+            const bool ok = !c.done && c.lane_ok && (unsigned)c.h < (unsigned)g.H;
+            const float* src = ok ? c.p : x;
+            const uint32_t dst = ring + (uint32_t)(stage * KC) * 128u;
+#pragma unroll
+            for (int ch = 0; ch < KC; ++ch) {
+                cp_async_4(dst + ch * 128u, src, (ok && ch < K) ? 4u : 0u);
+                if (ok) src += plane;
+            }
+            cp_async_commit();
+        };
+        Cursor cur, pf;
+        cur.k = 0; cur.ar0 = 0;
+        enter(cur);
+        pf = cur;
+#pragma unroll
+        for (int u = 0; u < T_PF; ++u) {
+            issue_row(pf, u);
+            if (!pf.done) step(pf);
+        }
+        while (!cur.done) {
+#pragma unroll
+            for (int u = 0; u < T_PF; ++u) {
+                if (cur.done) break;
+                cp_async_wait<T_PF - 1>();                            // the oldest group (this stage) has landed
+                float v[KC];
+#pragma unroll
+                for (int c = 0; c < KC; ++c) v[c] = lds_f32_own(ring + (uint32_t)((u * KC + c) * 128));
+                uint32_t th[PW], tl[PW];
+#pragma unroll
+                for (int i = 3 * KH; i < PW; ++i) { th[i] = 0u; tl[i] = 0u; }
+#pragma unroll
+                for (int i = 0; i < KH; ++i) {
+                    uint32_t hw, lw;
+                    split2(v[2 * i], v[2 * i + 1], hw, lw);
+                    th[i] = hw;
+                    tl[i] = lw;
+                    th[KH + i] = __shfl_down_sync(0xffffffffu, hw, 1);
+                    tl[KH + i] = __shfl_down_sync(0xffffffffu, lw, 1);
+                    th[2 * KH + i] = __shfl_down_sync(0xffffffffu, hw, 2);
+                    tl[2 * KH + i] = __shfl_down_sync(0xffffffffu, lw, 2);
+                }
+                issue_row(pf, u);                                     // refill this stage: T_PF own rows ahead
+                if (!pf.done) step(pf);
+                const uint32_t ar = cur.ar0 + (uint32_t)cur.j, slot = ar % T_NA;
+                mbar_wait_sleepy(a_empty + slot, ((ar / T_NA) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t ta = tmem + ((uint32_t)(quarter * 32) << 16) + A0 + slot * ACOLS;
+                tmem_st_words<PW>(ta, th);
+                tmem_st_words<PW>(ta + PW, tl);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full + slot);
+                step(cur);
+            }
+        }
+        cp_async_wait<0>();
+    } else if (warp >= T_EPI0) {
+        // ------------------------------------------------------------------------------------------ epilogue
+        const int eset = (warp - T_EPI0) >> 2, quarter = warp & 3;
+        uint32_t orow = 0;
+        Seg sg;
+        for (int k = 0; seg_at(R0, R1, g.H, k, sg); ++k) {
+            int side, b, tw;
+            unit_decode(g, sg.unit, side, b, tw);
+            const int col = tw * T_TWO + quarter * T_QPX + lane;
+            const bool col_ok = lane < T_QPX && col < g.W;
+            int i = (int)((eset - orow) & (T_NES - 1));                // first own row of the segment
+            float* p = (side ? dx_out : dy_out) + (size_t)b * K * plane + (size_t)(sg.hb + i) * g.W + (col_ok ? col : 0);
+            for (; i < sg.n_out; i += T_NES, p += T_NES * g.W) {
+                const uint32_t r_ = orow + (uint32_t)i, slot = r_ % T_ND;
+                mbar_wait_sleepy(d_full + slot, (r_ / T_ND) & 1u);
+                tc_fence_after();
+                uint32_t r[16];
+                const uint32_t td = tmem + ((uint32_t)(quarter * 32) << 16) + slot * 16;
+                if constexpr (KC <= 8) {
+                    tmem_ld_32x8(td, *reinterpret_cast<uint32_t (*)[8]>(r));
+                } else if constexpr (KC <= 10) {
+                    tmem_ld_32x8(td, *reinterpret_cast<uint32_t (*)[8]>(r));
+                    tmem_ld_32x2(td + 8, r + 8);
+                } else {
+                    tmem_ld_32x16(td, r);
+                }
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d_empty + slot);
+                if (col_ok) {
+                    float* q = p;
+#pragma unroll
+                    for (int o = 0; o < KC; ++o) {
+                        if (o < K) *q = __uint_as_float(r[o]);
+                        q += plane;
+                    }
+                }
+            }
+            orow += (uint32_t)sg.n_out;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == T_WALLOC) tmem_dealloc(tmem, 512);
+}
+
+template <int KH>
+int launch_bwd_tc(const float* x, const float* y, const TcGeom& g, const float* djoint, const float* gscale, float* dx, float* dy,
+                  cudaStream_t st) {
+    // more than half of the SM's shared memory: at most one CTA (and one 512-column TMEM allocation) per SM
+    const size_t smem = 120 * 1024;
+    auto k = iic_bwd_tc_kernel<KH>;
+    static SmemAttrCache attr;
+    if (attr.need(smem)) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("iic_bwd_tc smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
+        attr.set(smem);
+    }
+    const int sms = device_sm_count();
+    const int grid = g.rows_total < sms ? g.rows_total : sms;
+    k<<<grid, T_THREADS, smem, st>>>(x, y, g, djoint, gscale, dx, dy);
+    CY_CHECK_LAUNCH("iic_bwd_tc");
+    return CY_OK;
+}
+
+}  // namespace
+
+// returns CY_ERR_UNSUPPORTED when the shape is not eligible (the caller then takes the mma.sync / CUDA-core kernels)
+int iic_bwd_tc(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
+               const float* gscale, void* dx, void* dy, cudaStream_t st) {
+    if (dtype != CY_F32 || pad != 1 || K > 16 || K < 1) return CY_ERR_UNSUPPORTED;
+    TcGeom g;
+    g.B = B; g.K = K; g.H = H; g.W = W;
+    g.TW2 = (W + T_TWO - 1) / T_TWO;
+    const long long rows = 2LL * B * g.TW2 * H;
+    if (rows <= 0 || rows > 0x7fffffffLL / 2 || (long long)K * H * W > 0x7fffffffLL / 8) return CY_ERR_UNSUPPORTED;
+    g.rows_total = (int)rows;
+    const float* xf = reinterpret_cast<const float*>(x);
+    const float* yf = reinterpret_cast<const float*>(y);
+    float* dxf = reinterpret_cast<float*>(dx);
+    float* dyf = reinterpret_cast<float*>(dy);
+    if (K <= 4) return launch_bwd_tc<2>(xf, yf, g, djoint, gscale, dxf, dyf, st);
+    if (K <= 8) return launch_bwd_tc<4>(xf, yf, g, djoint, gscale, dxf, dyf, st);
+    if (K <= 10) return launch_bwd_tc<5>(xf, yf, g, djoint, gscale, dxf, dyf, st);
+    if (K <= 12) return launch_bwd_tc<6>(xf, yf, g, djoint, gscale, dxf, dyf, st);
+    return launch_bwd_tc<8>(xf, yf, g, djoint, gscale, dxf, dyf, st);
+}
+
+}  // namespace cy
