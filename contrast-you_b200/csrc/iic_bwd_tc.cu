@@ -47,7 +47,7 @@ constexpr int T_NA = 8;                          // A slots (input rows) in tens
 constexpr int T_ND = 8;                          // D slots (output rows)
 constexpr int T_NISS = 2;                        // issuer warps: warps 0, 1
 constexpr int T_NCS = 2;                         // converter sets
-constexpr int T_NES = 2;                         // epilogue sets
+constexpr int T_NES = 1;                         // epilogue sets
 constexpr int T_WALLOC = 2;                      // warp 2 owns the TMEM allocation; warp 3 idles
 constexpr int T_CONV0 = 4;
 constexpr int T_EPI0 = T_CONV0 + 4 * T_NCS;
@@ -92,27 +92,18 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
     lo = __byte_perm(__float_as_uint(v0 - __uint_as_float(h0)), __float_as_uint(v1 - __uint_as_float(h1)), 0x7632);
 }
 
-// 4-byte cp.async (LDGSTS) with zero fill: bytes = 0 writes zeros and reads nothing
-__device__ __forceinline__ void cp_async_4(uint32_t smem_dst, const float* src, uint32_t bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(src), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// mbarrier wait for roles that are expected to wait: try_wait with a suspend-time hint, so the warp sleeps in hardware until
-// the phase completes instead of re-issuing the probe (the spin loops were 20 % of all issued instructions in the first
-// profile of this kernel)
-__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}"
-        ::"r"(smem_u32(bar)), "r"(parity), "r"(4000u)
-        : "memory");
+// mbarrier wait for a role that is expected to wait (the epilogue is faster than its producers): a failed probe backs off
+// for ~100 ns instead of re-issuing at once — in the first profile of this kernel the spin loops were 30 % of all issued
+// instructions of an issue-bound SM.  The D ring (8 slots) absorbs the added wake-up latency.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(100);
+}
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const float* src, uint32_t bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(src), "r"(bytes) : "memory");
 }
 
 __device__ __forceinline__ float lds_f32_own(uint32_t addr) {
@@ -250,23 +241,40 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
         // A cursor over this warp's own input rows (global input-row index == cset mod T_NCS).  Everything that needs a
         // division is done once per segment; a step is a pointer increment.
         struct Cursor {
-            const float* p;      // &in[b, 0, h, col] of this lane (col clamped to 0 when the lane is outside the image)
+            const float* p;      // &in[b, 0, h, w0q]: first output column of this quarter, channel 0, image row h
             int h, j, n_in, k;   // image row, index inside the segment, input rows of the segment, segment number
             uint32_t ar0;        // global index of the segment's first input row
-            bool lane_ok, done;
+            uint32_t cmask;      // bit i: this lane's i-th staging chunk lies inside the image row (and below channel K)
+            bool done;
         };
+        // Staging: one input row of a quarter is [KC channels][CW = 36 floats] = image columns w0q-4 .. w0q+31, copied as
+        // 16-byte chunks (9 per channel) by cp.async with zero fill outside the image; W % 4 == 0 makes every chunk lie
+        // entirely inside or outside a row.  Lane l copies chunks l, l + 32, l + 64; lane l reads float 3 + l of every channel.
+        constexpr int CW = 36, NCHUNK = KC * (CW / 4), NIT = (NCHUNK + 31) / 32, STAGE_BYTES = KC * CW * 4;
+        int coff[NIT], ccol[NIT];
+        bool clive[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int idx = lane + 32 * it, ch = idx / (CW / 4), jc = idx % (CW / 4);
+            clive[it] = idx < NCHUNK && ch < K;
+            ccol[it] = 4 * jc - 4;
+            coff[it] = ch * plane + ccol[it];
+        }
         auto enter = [&](Cursor& c) {                                  // position on the first own row of segment c.k
             Seg sg;
             c.done = !seg_at(R0, R1, g.H, c.k, sg);
             if (c.done) return;
             int side, b, tw;
             unit_decode(g, sg.unit, side, b, tw);
-            const int col = tw * T_TWO + quarter * T_QPX - 1 + lane;
-            c.lane_ok = col >= 0 && col < g.W;
+            const int w0q = tw * T_TWO + quarter * T_QPX;
+            c.cmask = 0u;
+#pragma unroll
+            for (int it = 0; it < NIT; ++it)
+                if (clive[it] && w0q + ccol[it] >= 0 && w0q + ccol[it] < g.W) c.cmask |= 1u << it;
             c.n_in = sg.n_out + 2;
             c.j = (int)((cset - c.ar0) & (T_NCS - 1));
             c.h = sg.hb - 1 + c.j;
-            c.p = (side ? y : x) + (size_t)b * K * plane + (c.lane_ok ? col : 0) + (long long)c.h * g.W;
+            c.p = (side ? y : x) + (size_t)b * K * plane + w0q + (long long)c.h * g.W;
         };
         auto step = [&](Cursor& c) {
             c.j += T_NCS;
@@ -279,23 +287,18 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
                 enter(c);
             }
         };
-        // Staging ring of this warp: each lane copies its own pixel's K channel values with 4-byte cp.async (zero fill outside
-        // the image) and reads them back itself, so completion is tracked per row by cp.async groups (no register
-        // scoreboards shared between the rows in flight, no cross-lane hand-off).
-        const uint32_t ring = smem_u32(ring0) + (uint32_t)(((warp - T_CONV0) * T_PF * KC) * 32 + lane) * 4u;
+        const uint32_t ring = smem_u32(ring0) + (uint32_t)((warp - T_CONV0) * T_PF * STAGE_BYTES);
+        const uint32_t ring_wr = ring + (uint32_t)lane * 16u, ring_rd = ring + (uint32_t)(3 + lane) * 4u;
         auto issue_row = [&](const Cursor& c, int stage) {
-            const bool ok = !c.done && c.lane_ok && (unsigned)c.h < (unsigned)g.H;
-            const float* src = ok ? c.p : x;
-            const uint32_t dst = ring + (uint32_t)(stage * KC) * 128u;
+            const uint32_t m = (!c.done && (unsigned)c.h < (unsigned)g.H) ? c.cmask : 0u;
 #pragma unroll
-            for (int ch = 0; ch < KC; ++ch) {
-                cp_async_4(dst + ch * 128u, src, (ok && ch < K) ? 4u : 0u);
-                if (ok) src += plane;
-            }
+            for (int it = 0; it < NIT; ++it)        // size 0: nothing is read (the address may lie outside the tensor), zeros are written
+                if (lane + 32 * it < NCHUNK)
+                    cp_async_16(ring_wr + (uint32_t)(stage * STAGE_BYTES + it * 512), c.p + coff[it], (m >> it) & 1u ? 16u : 0u);
             cp_async_commit();
         };
         Cursor cur, pf;
-        cur.k = 0; cur.ar0 = 0;
+        cur.k = 0; cur.ar0 = 0; cur.cmask = 0u;
         enter(cur);
         pf = cur;
 #pragma unroll
@@ -307,10 +310,11 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
 #pragma unroll
             for (int u = 0; u < T_PF; ++u) {
                 if (cur.done) break;
-                cp_async_wait<T_PF - 1>();                            // the oldest group (this stage) has landed
+                cp_async_wait<T_PF - 1>();                            // the oldest group (this stage) has landed ...
+                __syncwarp();                                         // ... for every lane of the warp
                 float v[KC];
 #pragma unroll
-                for (int c = 0; c < KC; ++c) v[c] = lds_f32_own(ring + (uint32_t)((u * KC + c) * 128));
+                for (int c = 0; c < KC; ++c) v[c] = lds_f32_own(ring_rd + (uint32_t)(u * STAGE_BYTES + c * CW * 4));
                 uint32_t th[PW], tl[PW];
 #pragma unroll
                 for (int i = 3 * KH; i < PW; ++i) { th[i] = 0u; tl[i] = 0u; }
@@ -325,10 +329,10 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
                     th[2 * KH + i] = __shfl_down_sync(0xffffffffu, hw, 2);
                     tl[2 * KH + i] = __shfl_down_sync(0xffffffffu, lw, 2);
                 }
-                issue_row(pf, u);                                     // refill this stage: T_PF own rows ahead
-                if (!pf.done) step(pf);
+                issue_row(pf, u);                                     // refill this stage (every lane is past its reads: the
+                if (!pf.done) step(pf);                               // shuffles above are warp-synchronous)
                 const uint32_t ar = cur.ar0 + (uint32_t)cur.j, slot = ar % T_NA;
-                mbar_wait_sleepy(a_empty + slot, ((ar / T_NA) & 1u) ^ 1u);
+                mbar_wait(a_empty + slot, ((ar / T_NA) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t ta = tmem + ((uint32_t)(quarter * 32) << 16) + A0 + slot * ACOLS;
                 tmem_st_words<PW>(ta, th);
@@ -355,7 +359,7 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
             float* p = (side ? dx_out : dy_out) + (size_t)b * K * plane + (size_t)(sg.hb + i) * g.W + (col_ok ? col : 0);
             for (; i < sg.n_out; i += T_NES, p += T_NES * g.W) {
                 const uint32_t r_ = orow + (uint32_t)i, slot = r_ % T_ND;
-                mbar_wait_sleepy(d_full + slot, (r_ / T_ND) & 1u);
+                mbar_wait_backoff(d_full + slot, (r_ / T_ND) & 1u);
                 tc_fence_after();
                 uint32_t r[16];
                 const uint32_t td = tmem + ((uint32_t)(quarter * 32) << 16) + slot * 16;
@@ -412,7 +416,8 @@ int launch_bwd_tc(const float* x, const float* y, const TcGeom& g, const float* 
 // returns CY_ERR_UNSUPPORTED when the shape is not eligible (the caller then takes the mma.sync / CUDA-core kernels)
 int iic_bwd_tc(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
                const float* gscale, void* dx, void* dy, cudaStream_t st) {
-    if (dtype != CY_F32 || pad != 1 || K > 16 || K < 1) return CY_ERR_UNSUPPORTED;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (dtype != CY_F32 || pad != 1 || K > 16 || K < 1 || (W % 4) != 0 || !al16(x) || !al16(y)) return CY_ERR_UNSUPPORTED;
     TcGeom g;
     g.B = B; g.K = K; g.H = H; g.W = W;
     g.TW2 = (W + T_TWO - 1) / T_TWO;
