@@ -18,6 +18,9 @@ def main():
     for k, v in (("B", 32), ("K", 10), ("H", 224), ("W", 224), ("pad", 1), ("reps", 20)):
         ap.add_argument("--" + k, type=int, default=v)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--flush", default="write", choices=["write", "read", "rotate", "none"],
+                    help="between timed launches: write a 256 MiB buffer (dirty L2 lines are written back DURING the timed kernel), "
+                         "read it (clean lines), rotate over 3 input/output sets (inputs larger than L2, no flush), or nothing")
     ap.add_argument("--ref", default=None, help="npz written by an earlier run: report max relative differences")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -34,11 +37,19 @@ def main():
     one = torch.ones(1, device=dev)
     dx, dy = torch.empty_like(x), torch.empty_like(y)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    nset = 3 if a.flush == "rotate" else 1
+    xs = [x] + [x.clone() for _ in range(nset - 1)]
+    ys = [y] + [y.clone() for _ in range(nset - 1)]
+    dxs = [dx] + [torch.empty_like(x) for _ in range(nset - 1)]
+    dys = [dy] + [torch.empty_like(y) for _ in range(nset - 1)]
+    cur = [0]
 
     def joint_call():
+        x, y = xs[cur[0]], ys[cur[0]]
         L.check(lib.cy_iic_joint(x.data_ptr(), y.data_ptr(), 0, a.B, a.K, a.H, a.W, a.pad, joint.data_ptr(), ws.data_ptr(), wsb, st), "joint")
 
     def bwd_call():
+        x, y, dx, dy = xs[cur[0]], ys[cur[0]], dxs[cur[0]], dys[cur[0]]
         L.check(lib.cy_iic_bwd(x.data_ptr(), y.data_ptr(), 0, a.B, a.K, a.H, a.W, a.pad, dj.data_ptr(), one.data_ptr(),
                                dx.data_ptr(), dy.data_ptr(), st), "bwd")
 
@@ -47,7 +58,11 @@ def main():
             fn()
         ts = []
         for _ in range(a.reps):
-            flush.zero_()
+            if a.flush == "write":
+                flush.zero_()
+            elif a.flush == "read":
+                flush.sum()
+            cur[0] = (cur[0] + 1) % nset
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record()
             torch.cuda.synchronize()
@@ -57,7 +72,8 @@ def main():
     jm, jmin = timeit(joint_call)
     bm, bmin = timeit(bwd_call)
     by = 2 * a.B * a.K * a.H * a.W * 4
-    print(f"env MMA={os.environ.get('CY_IIC_MMA', '1')} TMA={os.environ.get('CY_IIC_TMA', '1')}  "
+    cur[0] = 0
+    print(f"flush={a.flush} env MMA={os.environ.get('CY_IIC_MMA', '1')} TMA={os.environ.get('CY_IIC_TMA', '1')}  "
           f"joint {jm * 1e3:.1f} us (min {jmin * 1e3:.1f}; {by / jm / 1e6:.0f} GB/s)  "
           f"bwd {bm * 1e3:.1f} us (min {bmin * 1e3:.1f}; {2 * by / bm / 1e6:.0f} GB/s)  "
           f"fwd+bwd {3 * by / (jm + bm) / 1e6:.0f} GB/s")
