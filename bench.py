@@ -128,9 +128,9 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
 def ncu_traffic():
-    """DRAM bytes per launch measured by ncu (profiles/r1_traffic.json, exported from the committed --set full captures)."""
+    """DRAM bytes per launch measured by ncu (profiles/r2_traffic.json, exported from the committed --set full captures)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             return json.load(f)
     except (OSError, ValueError):
         return {}
@@ -621,7 +621,7 @@ def main():
                          "achieved": gbs(3 * bytes_map, j_ms + b_ms), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": gbs(3 * bytes_map, j_ms + b_ms) / peaks["hbm_gbs"],
                          "traffic": (traffic.get("iic_joint_mma_kernel<2,4,1,2> cfg3", {}).get("bytes", 0)
-                                     + traffic.get("iic_bwd_mma_kernel<32,2> cfg3", {}).get("bytes", 0)) or None,
+                                     + traffic.get("iic_bwd_tc_kernel<5> cfg3", {}).get("bytes", 0)) or None,
                          "joint": {"ms": j_ms, "achieved": gbs(bytes_map, j_ms), "frac": gbs(bytes_map, j_ms) / peaks["hbm_gbs"]},
                          "bwd": {"ms": b_ms, "achieved": gbs(2 * bytes_map, b_ms), "frac": gbs(2 * bytes_map, b_ms) / peaks["hbm_gbs"]},
                          "peak_source": peaks["source"] + " copy bandwidth"},

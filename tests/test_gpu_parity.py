@@ -684,6 +684,61 @@ def test_iic_tensor_pipe_shapes_vs_c_oracle(B, K, H, W, pad):
     assert _relerr(y.grad.cpu().numpy(), gy) <= 3e-5
 
 
+# ------------------------------------------------------------------------------------------------ tcgen05 IIC adjoint
+def _adjoint_direct(x, y, dj, pad=1):
+    """cy_iic_bwd through the C ABI (the path IIDSegmentationLoss.backward takes): dL/dx, dL/dy for a given dL/dJoint"""
+    B, K, H, W = x.shape
+    dx, dy = torch.empty_like(x), torch.empty_like(y)
+    one = torch.ones(1, device=x.device)
+    L.check(L.lib().cy_iic_bwd(x.data_ptr(), y.data_ptr(), 0, B, K, H, W, pad, dj.data_ptr(), one.data_ptr(), dx.data_ptr(),
+                               dy.data_ptr(), L.stream_ptr()), "cy_iic_bwd")
+    return dx, dy
+
+
+@pytest.mark.parametrize("B,K,H,W", [(1, 1, 5, 8), (2, 2, 1, 12), (1, 3, 2, 116), (3, 5, 17, 228), (2, 7, 40, 340), (1, 11, 64, 112),
+                                      (2, 12, 3, 60), (1, 14, 30, 32), (1, 15, 225, 224), (5, 10, 224, 224), (40, 10, 7, 16)])
+def test_iic_tcgen05_adjoint_shapes(B, K, H, W):
+    """csrc/iic_bwd_tc.cu (padding 1, fp32, W % 4 == 0, K <= 16): every channel-pair instantiation (K = 1..16), images
+    narrower than one 112-column strip and with 2 / 3 / 4 strips (ragged last strip), one- and two-row images (segments made
+    of halo rows only), more CTAs than rows and CTA ranges that cross several strips, vs the float64 oracle"""
+    torch.manual_seed(B * 1000 + K * 10 + H)
+    x = (2 * torch.randn(B, K, H, W, device=DEV)).softmax(1)
+    y = (2 * torch.randn(B, K, H, W, device=DEV)).softmax(1)
+    dj = torch.randn(K, K, 3, 3, device=DEV)
+    dx, dy = _adjoint_direct(x, y, dj)
+    gx, gy = OM.input_grads(x.cpu().double().numpy(), y.cpu().double().numpy(), dj.cpu().double().numpy(), 1)
+    assert _relerr(dx.cpu().numpy(), gx) <= 3e-5
+    assert _relerr(dy.cpu().numpy(), gy) <= 3e-5
+
+
+def test_iic_mma_sync_adjoint_still_agrees():
+    """CY_IIC_TC=0 pins the round-1 mma.sync adjoint (csrc/iic_mma.cu), kept for A/B timing: it must return what the tcgen05
+    adjoint returns (the switch is read once per process, hence the subprocess)"""
+    import subprocess, sys, tempfile
+    torch.manual_seed(11)
+    x = (2 * torch.randn(3, 10, 37, 72, device=DEV)).softmax(1)
+    y = (2 * torch.randn(3, 10, 37, 72, device=DEV)).softmax(1)
+    dj = torch.randn(10, 10, 3, 3, device=DEV)
+    dx, dy = _adjoint_direct(x, y, dj)
+    with tempfile.TemporaryDirectory() as td:
+        np.savez(os.path.join(td, "in.npz"), x=x.cpu().numpy(), y=y.cpu().numpy(), dj=dj.cpu().numpy())
+        code = (
+            "import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
+            "from contrast_you_b200 import _lib as L\n"
+            "d = np.load(%r); x, y, dj = (torch.from_numpy(d[k]).cuda() for k in ('x', 'y', 'dj'))\n"
+            "dx, dy = torch.empty_like(x), torch.empty_like(y); one = torch.ones(1, device='cuda')\n"
+            "B, K, H, W = x.shape\n"
+            "L.check(L.lib().cy_iic_bwd(x.data_ptr(), y.data_ptr(), 0, B, K, H, W, 1, dj.data_ptr(), one.data_ptr(), dx.data_ptr(),"
+            " dy.data_ptr(), L.stream_ptr()), 'bwd')\n"
+            "np.savez(%r, dx=dx.cpu().numpy(), dy=dy.cpu().numpy())\n"
+        ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(td, "in.npz"), os.path.join(td, "out.npz"))
+        env = dict(os.environ, CY_IIC_TC="0")
+        subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+        o = np.load(os.path.join(td, "out.npz"))
+    assert _relerr(dx.cpu().numpy(), o["dx"]) <= 2e-5
+    assert _relerr(dy.cpu().numpy(), o["dy"]) <= 2e-5
+
+
 # ------------------------------------------------------------------------------------------------ pack feeder
 def test_pack_feeder_strided_views_and_unnormalised_rows():
     """the modules take views produced by torch.chunk (row pitch > d) and must raise the reference's AssertionError
