@@ -17,7 +17,7 @@ CY_F32, CY_BF16, CY_F16, CY_F32_SPLIT = 0, 1, 2, 3
 CY_SUPCON, CY_SUPCON_EXCLUDE, CY_SELFPACED_HARD, CY_SELFPACED_SOFT = 0, 1, 2, 3
 CY_PATH_AUTO, CY_PATH_SIMT, CY_PATH_TCGEN05 = 0, 1, 2
 CY_NSTAT = 8
-CY_ABI_VERSION = 2
+CY_ABI_VERSION = 3
 CY_STAT_LOGDEN, CY_STAT_INVC, CY_STAT_COEF, CY_STAT_AUX = 0, 1, 2, 3
 
 _c = ctypes
@@ -52,6 +52,7 @@ SIGNATURES = {
     "cy_imsat_fwd": (_i32, [_vp, _i32, _i64, _i32, _i64, _f32, _vp, _vp, _vp, _sz, _vp]),
     "cy_imsat_bwd": (_i32, [_vp, _i32, _i64, _i32, _i64, _f32, _vp, _vp, _vp, _vp]),
     "cy_p2p_push": (_i32, [_vp, _i32, _i32, _vp, _i32, _vp]),
+    "cy_p2p_push_barrier": (_i32, [_vp, _i32, _i32, _vp, _i32, _c.c_ulonglong, _vp, _c.c_uint, _vp]),
 }
 
 _LIB = None

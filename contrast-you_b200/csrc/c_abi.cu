@@ -66,7 +66,7 @@ int infonce_fwd_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, 
 int infonce_fwd2_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, int, float, float*, float*, void*,
                     size_t, cudaStream_t);
 int infonce_rowstats(int64_t, int64_t, int64_t, float, int, int, float*, float*, cudaStream_t);
-int infonce_loss(int64_t, int, const float*, float*, const int32_t*, const int32_t*, void*, size_t, cudaStream_t);
+int infonce_loss(int64_t, int, const float*, float*, int32_t*, const int32_t*, void*, size_t, cudaStream_t);
 int infonce_bwd_tc(const void*, int, int64_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, float, int, float, const float*,
                    const float*, void*, int64_t, void*, size_t, cudaStream_t);
 // iic.cu
@@ -80,6 +80,7 @@ int imsat_fwd(const void*, int, int64_t, int, int64_t, float, float*, float*, vo
 int imsat_bwd(const void*, int, int64_t, int, int64_t, float, const float*, const float*, void*, cudaStream_t);
 // p2p.cu
 int p2p_push(void* const*, int, int, const unsigned long long*, int, cudaStream_t);
+int p2p_push_barrier(void* const*, int, int, const unsigned long long*, int, unsigned long long, unsigned int*, unsigned int, cudaStream_t);
 int iic_bwd(const void*, const void*, int, int, int, int, int, int, const float*, const float*, void*, void*, cudaStream_t);
 
 static int check_infonce_args(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
@@ -187,7 +188,7 @@ int cy_infonce_fwd_pass2(const void* z, int dtype, int64_t N, int64_t d, int64_t
     return infonce_rowstats(N, row_begin, row_end, inv_t, variant, 2, stats, xstat, st);
 }
 
-int cy_infonce_loss(int64_t N, int variant, const float* xstat, float* out8, const int32_t* bad_rows, const int32_t* overflow,
+int cy_infonce_loss(int64_t N, int variant, const float* xstat, float* out8, int32_t* bad_rows, const int32_t* overflow,
                     void* workspace, size_t workspace_bytes, void* stream) {
     CY_NVTX("cy_infonce_loss");
     CY_CHECK_ARG(xstat && out8 && N >= 2, "null pointer");
@@ -324,6 +325,13 @@ int cy_p2p_push(void* const* peer_bufs, int world, int rank, const unsigned long
     CY_NVTX("cy_p2p_push");
     CY_CHECK_ARG(peer_bufs && ranges && world >= 1 && rank >= 0 && rank < world && n_ranges >= 1 && n_ranges <= 4, "bad arguments");
     return p2p_push(peer_bufs, world, rank, ranges, n_ranges, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_p2p_push_barrier(void* const* peer_bufs, int world, int rank, const unsigned long long* ranges, int n_ranges,
+                        unsigned long long flag_off, unsigned int* counter, unsigned int epoch, void* stream) {
+    CY_NVTX("cy_p2p_push_barrier");
+    CY_CHECK_ARG(peer_bufs && ranges && world >= 1 && rank >= 0 && rank < world && n_ranges >= 1 && n_ranges <= 4, "bad arguments");
+    return p2p_push_barrier(peer_bufs, world, rank, ranges, n_ranges, flag_off, counter, epoch, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int cy_iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,

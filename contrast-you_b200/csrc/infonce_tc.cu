@@ -505,7 +505,7 @@ infonce_loss_partial_kernel(int variant, int N, const float4* __restrict__ xstat
 // out8[0..3] as above; out8[4] = *bad_rows (un-normalised rows counted by cy_infonce_pack), out8[5] = *overflow (int64 labels
 // outside int32, cy_labels_canonicalize), out8[6..7] = 0: everything the module's per-step host check needs in ONE 32-byte read
 __global__ void infonce_loss_final_kernel(int nblk, int N, const float* __restrict__ partials, float* __restrict__ out8,
-                                          const int32_t* __restrict__ bad_rows, const int32_t* __restrict__ overflow) {
+                                          int32_t* __restrict__ bad_rows, const int32_t* __restrict__ overflow) {
     const int q = threadIdx.x;       // 4 threads, each walks its component in block order
     if (q < 4) {
         float s = 0.f;
@@ -513,6 +513,7 @@ __global__ void infonce_loss_final_kernel(int nblk, int N, const float* __restri
         out8[q] = (q == 0) ? s / (float)N : s;
     } else if (q == 4) {
         out8[4] = bad_rows ? (float)bad_rows[0] : 0.f;
+        if (bad_rows) bad_rows[0] = 0;      // the counter is consumed: a persistent one is ready for the next step's pack
     } else if (q == 5) {
         out8[5] = overflow ? (float)overflow[0] : 0.f;
     } else if (q < 8) {
@@ -1146,7 +1147,7 @@ int infonce_rowstats(int64_t N, int64_t row_begin, int64_t row_end, float inv_t,
 
 size_t infonce_loss_workspace_bytes(int64_t N) { return (size_t)((N + LOSS_THREADS - 1) / LOSS_THREADS) * 4 * sizeof(float) + 256; }
 
-int infonce_loss(int64_t N, int variant, const float* xstat, float* out8, const int32_t* bad_rows, const int32_t* overflow,
+int infonce_loss(int64_t N, int variant, const float* xstat, float* out8, int32_t* bad_rows, const int32_t* overflow,
                  void* workspace, size_t workspace_bytes, cudaStream_t st) {
     const int nblk = (int)((N + LOSS_THREADS - 1) / LOSS_THREADS);
     CY_CHECK_ARG(workspace && workspace_bytes >= (size_t)nblk * 4 * sizeof(float), "infonce_loss: workspace %zu too small", workspace_bytes);

@@ -111,34 +111,51 @@ class PeerExchange:
         except Exception:  # noqa
             return False
 
+    FLAG_BYTES = 4096      # uint32 [world] epoch flags of cy_p2p_push_barrier, behind the two data halves
+
     def _grow(self, nbytes: int, device):
         import torch.distributed._symmetric_memory as symm_mem
         self.half_bytes = (nbytes + (1 << 20) - 1) >> 20 << 20
-        self.buf = symm_mem.empty(2 * self.half_bytes, dtype=torch.uint8, device=device)
+        self.buf = symm_mem.empty(2 * self.half_bytes + self.FLAG_BYTES, dtype=torch.uint8, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.ptrs_dev = int(self.hdl.buffer_ptrs_dev)
         self.step = 0
+        # the exchange's own barrier state: epoch flags inside the symmetric buffer (zeroed on every rank before anyone can
+        # publish into them), the last-block counter of the push kernel, the epoch of the next call, and what each half's
+        # label block currently holds (ShardedSupConLoss skips re-sending unchanged labels)
+        self.buf[2 * self.half_bytes:].zero_()
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.epoch = 0
+        self.labels_token = [None, None]
+        self.hdl.barrier(channel=0)
 
     def acquire(self, nbytes: int, device):
         """-> (local uint8 view of this step's half, its byte offset inside the symmetric buffer)"""
         if self.buf is None or nbytes > self.half_bytes:
             self._grow(nbytes, device)
-        off = (self.step & 1) * self.half_bytes
+        self.half = self.step & 1
+        off = self.half * self.half_bytes
         self.step += 1
         return self.buf[off:off + self.half_bytes], off
 
     def push(self, ranges):
         """copy the (offset, bytes) ranges of the local buffer into every peer's buffer (offsets relative to the whole
-        symmetric buffer), then barrier: on return (in stream order) every rank's ranges are visible here"""
+        symmetric buffer) and meet the peers — ONE launch (cy_p2p_push_barrier: the kernel's last block publishes this call's
+        epoch to every peer and waits for theirs): on return (in stream order) every rank's ranges are visible here.  An empty
+        range list is a plain barrier."""
         import ctypes
         lib = L.lib()
         flat = []
         for off, nb in ranges:
             assert off % 16 == 0 and nb % 16 == 0, (off, nb)
             flat += [off, nb]
+        if not flat:
+            flat = [0, 0]
         arr = (ctypes.c_ulonglong * len(flat))(*flat)
-        L.check(lib.cy_p2p_push(self.ptrs_dev, self.world, self.rank, arr, len(ranges), L.stream_ptr(self.buf.device)), "cy_p2p_push")
-        self.hdl.barrier(channel=0)
+        self.epoch += 1
+        L.check(lib.cy_p2p_push_barrier(self.ptrs_dev, self.world, self.rank, arr, len(flat) // 2, 2 * self.half_bytes,
+                                        self.counter.data_ptr(), self.epoch & 0xffffffff, L.stream_ptr(self.buf.device)),
+                "cy_p2p_push_barrier")
 
 
 def make_joint_reduce(group=None, exchange: str = "auto"):
@@ -194,7 +211,8 @@ class _ShardedInfoNCE(torch.autograd.Function):
     why); ``backward`` only scatters the stored rows back to the two views, times the upstream gradient."""
 
     @staticmethod
-    def forward(ctx, f1, f2, labels_loc, order, inv_t, variant, gamma, path, group, check, design, overflow, status, px):
+    def forward(ctx, f1, f2, labels_loc, order, inv_t, variant, gamma, path, group, check, design, overflow, status, px, scratch,
+                lab_cached):
         from .losses.contrastive import _unit_scale
         lib = L.lib()
         world, rank = _ws(group)
@@ -219,19 +237,33 @@ class _ShardedInfoNCE(torch.autograd.Function):
                 z_all = torch.empty(N, d, dtype=f1.dtype, device=dev)
                 labels_all = torch.empty(N, dtype=torch.int32, device=dev)
                 xstat = torch.empty(N, 4, dtype=torch.float32, device=dev)
-            stats = torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev)
+            # per-shape scratch of the module (row statistics, kernel workspace) and its persistent un-normalised-row counter
+            # (cy_infonce_loss resets it once read): no allocation / memset launches per step
+            key = (N, d, dt, variant, path, str(dev))
+            if scratch.get("key") != key:
+                ws_bytes = lib.cy_infonce_workspace_bytes(N, d, dt, variant, path)
+                scratch.clear()
+                scratch.update(key=key, stats=torch.empty(L.CY_NSTAT, N, dtype=torch.float32, device=dev), ws_bytes=ws_bytes,
+                               ws=torch.empty(ws_bytes, dtype=torch.uint8, device=dev),
+                               bad=torch.zeros(1, dtype=torch.int32, device=dev))
+            stats, ws, ws_bytes = scratch["stats"], scratch["ws"], scratch["ws_bytes"]
             out8 = torch.empty(8, dtype=torch.float32, device=dev)
-            bad = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
+            bad = scratch["bad"] if check else None
             L.check(lib.cy_infonce_pack(f1.data_ptr(), f2.data_ptr(), dt, n_loc, d, f1.stride(0), f2.stride(0), L.ptr(order),
                                         z_all.data_ptr() + rb * d * esz, L.ptr(bad), None, st), "cy_infonce_pack")
-            labels_all[rb:re].copy_(labels_loc)
-            if px is not None:      # ONE launch pushes this rank's embedding rows and labels to every peer; then the barrier
-                px.push([(base + rb * d * esz, rows_loc * d * esz), (base + zb + rb * 4, rows_loc * 4)])
+            # the owned label block: a block that this half of the exchange buffer already holds (same cached label tensor,
+            # unchanged since) is neither copied nor sent again — every rank decides that for ITS block only
+            held = px.labels_token[px.half] if px is not None else None      # (tensor, version, rb): the tensor is kept alive
+            send_labels = not (held is not None and held[0] is labels_loc and held[1] == labels_loc._version and held[2] == rb)
+            if send_labels:
+                labels_all[rb:re].copy_(labels_loc)
+                if px is not None:
+                    px.labels_token[px.half] = (labels_loc, labels_loc._version, rb) if lab_cached else None
+            if px is not None:      # ONE launch pushes this rank's embedding rows (and labels) to every peer and meets the peers
+                px.push([(base + rb * d * esz, rows_loc * d * esz)] + ([(base + zb + rb * 4, rows_loc * 4)] if send_labels else []))
             else:
                 gather_rows_(z_all, group)
                 gather_rows_(labels_all, group)
-            ws_bytes = lib.cy_infonce_workspace_bytes(N, d, dt, variant, path)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             zp, lp = z_all.data_ptr(), labels_all.data_ptr()
             L.check(lib.cy_infonce_fwd(zp, dt, N, d, d, lp, None, rb, re, inv_t, variant, path, stats.data_ptr(), xstat.data_ptr(),
                                        ws.data_ptr(), ws_bytes, st), "cy_infonce_fwd")
@@ -279,7 +311,7 @@ class _ShardedInfoNCE(torch.autograd.Function):
             g2 = torch.empty(n_loc, d, dtype=dz_loc.dtype, device=dev)
             L.check(lib.cy_infonce_unpack(dz_loc.data_ptr(), L.dtype_code(dz_loc), n_loc, d, d, L.ptr(order), g1.data_ptr(),
                                           g2.data_ptr(), None, None, gscale.data_ptr(), L.stream_ptr(dev)), "cy_infonce_unpack")
-        return g1, g2, None, None, None, None, None, None, None, None, None, None, None, None
+        return g1, g2, None, None, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 def _strip_contribution_reduce_scatter(z_all, labels_all, xstat, gscale, inv_t, variant, gamma, rb, re, group):
@@ -347,6 +379,7 @@ class ShardedSupConLoss(torch.nn.Module):
         assert exchange in ("auto", "p2p", "nccl")
         self._exchange = exchange
         self._px = None
+        self._scratch = {}
 
     def _local_labels(self, target, n_local, rank, device, sort):
         """canonical labels of the owned row block (+ the local sort), cached while the same label tensor comes back"""
@@ -364,7 +397,7 @@ class ShardedSupConLoss(torch.nn.Module):
                 self._cache = _TensorLabelCache()
             hit = self._cache.get(target, n_local, device, sort)
             if hit is not None:
-                return hit[0], hit[1], None
+                return hit[0], hit[1], None, True
         if isinstance(raw, Tensor) and raw.dtype == torch.int64:
             overflow = torch.zeros(1, dtype=torch.int32, device=device)
         labels = _canonical_labels(raw, n_local, device, overflow)
@@ -374,7 +407,8 @@ class ShardedSupConLoss(torch.nn.Module):
             labels = labels.index_select(0, order)
         if cacheable and overflow is None:
             self._cache.put(target, n_local, device, sort, (labels, order))
-        return labels, order, overflow
+            return labels, order, overflow, True
+        return labels, order, overflow, False
 
     def forward(self, proj_feat1: Tensor, proj_feat2: Tensor, target=None, mask: Optional[Tensor] = None, **kwargs):
         if mask is not None:
@@ -391,7 +425,7 @@ class ShardedSupConLoss(torch.nn.Module):
         tc = (proj_feat1.dtype in (torch.bfloat16, torch.float16) and d in (128, 256) and rows_loc % 128 == 0 and N >= 256
               and (self._variant == L.CY_SUPCON or N <= 4096 * 128)
               and (self._path == L.CY_PATH_TCGEN05 or (self._path == L.CY_PATH_AUTO and N >= 1024)))
-        labels_loc, order, overflow = self._local_labels(target, n_local, rank, device, tc)
+        labels_loc, order, overflow, lab_cached = self._local_labels(target, n_local, rank, device, tc)
         f1 = proj_feat1 if proj_feat1.stride(1) == 1 else proj_feat1.contiguous()
         f2 = proj_feat2 if proj_feat2.stride(1) == 1 else proj_feat2.contiguous()
         status = None
@@ -402,7 +436,8 @@ class ShardedSupConLoss(torch.nn.Module):
             status = self._status
         px = self._peer_exchange(rows_loc % 4 == 0 and (rows_loc * d * proj_feat1.element_size()) % 16 == 0)
         loss, out8 = _ShardedInfoNCE.apply(f1, f2, labels_loc, order, float(1.0 / self._t), self._variant, float(self._gamma),
-                                           self._path, self._group, __debug__, self._design, overflow, status, px)
+                                           self._path, self._group, __debug__, self._design, overflow, status, px, self._scratch,
+                                           lab_cached)
         if status is None:
             cur = out8[3:6].detach().clone()          # [non-finite terms, un-normalised rows, label overflows]
             cur[0] = cur[0] + torch.isnan(loss.detach()).to(cur.dtype)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CY_ABI_VERSION 2
+#define CY_ABI_VERSION 3
 
 /* element types of embeddings / probability maps */
 #define CY_F32 0
@@ -120,8 +120,9 @@ int cy_infonce_fwd_pass2(const void* z, int dtype, int64_t N, int64_t d, int64_t
  * out8 [8] float: [0] = loss = sum_i term_i / N, [1] = sum_ij P_ij w_ij, [2] = sum_ij P_ij (self-paced downgrade ratio =
  * [1]/[2], contrastive.py:179-181; 0 for the other variants), [3] = number of non-finite row terms (NaN check, :98-99),
  * [4] = *bad_rows (un-normalised rows counted by cy_infonce_pack, :58), [5] = *overflow (cy_labels_canonicalize), [6..7] = 0:
- * everything the reference's per-step assertions need, in one 32-byte device->host read.  bad_rows / overflow may be NULL. */
-int cy_infonce_loss(int64_t N, int variant, const float* xstat, float* out8, const int32_t* bad_rows, const int32_t* overflow,
+ * everything the reference's per-step assertions need, in one 32-byte device->host read.  bad_rows / overflow may be NULL;
+ * *bad_rows is reset to zero once it has been read (a persistent counter serves every step without a memset). */
+int cy_infonce_loss(int64_t N, int variant, const float* xstat, float* out8, int32_t* bad_rows, const int32_t* overflow,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward: dz[row_begin:row_end, :] = gscale[0] * (1/t) * sum_j (G_ij + G_ji) z_j  with G = dLoss/dS built on the
@@ -243,6 +244,16 @@ int cy_imsat_bwd(const void* pred, int dtype, int64_t N, int K, int64_t S, float
  * Copies every range from the local buffer to the same offsets of all OTHER ranks' buffers (push all-gather: each rank
  * owns the ranges it pushes).  Completion on the peers is established by the caller's signal-pad barrier after the call. */
 int cy_p2p_push(void* const* peer_bufs, int world, int rank, const unsigned long long* ranges, int n_ranges, void* stream);
+
+/* cy_p2p_push + the barrier in ONE launch: after its copies the kernel's last block publishes `epoch` to every peer (release
+ * store into the peer's flag array) and waits until every peer has published an epoch >= `epoch` to this rank.
+ *   flag_off  byte offset (multiple of 16) inside the symmetric buffer of a uint32 [world] flag array; zero it on every rank
+ *             (and barrier once) before the first call
+ *   counter   one LOCAL device uint32, zero before the first call (the kernel leaves it zero)
+ *   epoch     1, 2, 3, ... — the same sequence on every rank (one value per call)
+ * On return (in stream order) every rank's ranges are visible in this rank's buffer. */
+int cy_p2p_push_barrier(void* const* peer_bufs, int world, int rank, const unsigned long long* ranges, int n_ranges,
+                        unsigned long long flag_off, unsigned int* counter, unsigned int epoch, void* stream);
 
 #ifdef __cplusplus
 }
