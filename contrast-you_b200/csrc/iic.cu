@@ -183,9 +183,24 @@ iic_reduce_partials_kernel(const float* __restrict__ partials, int n_partials, i
     __shared__ double acc[RED_WARPS][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + lane;
+    // launched with programmatic stream serialization right behind the joint kernel: everything above overlaps its tail,
+    // the partial joints are read only after the dependency has resolved
+#if __CUDA_ARCH__ >= 900
+    cudaGridDependencySynchronize();
+#endif
     double s = 0.0;
-    if (i < nj)
-        for (int p = w; p < n_partials; p += RED_WARPS) s += (double)partials[(size_t)p * nj + i];
+    if (i < nj) {
+        // fixed order per thread; the loads of a batch of 8 are independent and in flight together (one L2 round trip per batch)
+        int p = w;
+        for (; p + 7 * RED_WARPS < n_partials; p += 8 * RED_WARPS) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(partials + (size_t)(p + u * RED_WARPS) * nj + i);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += (double)v[u];
+        }
+        for (; p < n_partials; p += RED_WARPS) s += (double)__ldcg(partials + (size_t)p * nj + i);
+    }
     acc[w][lane] = s;
     __syncthreads();
     if (w == 0 && i < nj) {
@@ -194,6 +209,23 @@ iic_reduce_partials_kernel(const float* __restrict__ partials, int n_partials, i
         for (int k = 0; k < RED_WARPS; ++k) t += acc[k][lane];
         joint[i] = t;      // kept in double: the min-shift of the epilogue amplifies a float32 rounding of J ~sqrt(pixels)-fold
     }
+}
+// launch helper: programmatic dependent launch (the kernel may start while its predecessor on the stream drains)
+static int launch_reduce_partials(const float* partials, int n_partials, int nj, double* joint, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((nj + 31) / 32));
+    cfg.blockDim = dim3(32 * RED_WARPS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, iic_reduce_partials_kernel, partials, n_partials, nj, joint);
+    count_launch();
+    if (e != cudaSuccess) { set_error("iic_reduce_partials: %s", cudaGetErrorString(e)); return (int)e; }
+    return CY_OK;
 }
 static inline int reduce_grid(int nj) { return (nj + 31) / 32; }
 
@@ -655,9 +687,7 @@ int iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int 
         int np = 0;
         rc = iic_joint_mma(x, y, dtype, B, K, H, W, pad, partials, &np, st);
         if (rc == CY_OK) {
-            iic_reduce_partials_kernel<<<reduce_grid(nj), 32 * RED_WARPS, 0, st>>>(partials, np, nj, joint);
-            CY_CHECK_LAUNCH("iic_reduce_partials");
-            return CY_OK;
+            return launch_reduce_partials(partials, np, nj, joint, st);
         }
         if (rc != CY_ERR_UNSUPPORTED) return rc;
     }
@@ -665,9 +695,7 @@ int iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int 
         int np = 0;
         rc = iic_joint_tma(x, y, dtype, B, K, H, W, pad, partials, &np, st);
         if (rc == CY_OK) {
-            iic_reduce_partials_kernel<<<reduce_grid(nj), 32 * RED_WARPS, 0, st>>>(partials, np, nj, joint);
-            CY_CHECK_LAUNCH("iic_reduce_partials");
-            return CY_OK;
+            return launch_reduce_partials(partials, np, nj, joint, st);
         }
         if (rc != CY_ERR_UNSUPPORTED) return rc;
     }
@@ -681,9 +709,7 @@ int iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int 
         rc = CY_OK;
     }
     if (rc != CY_OK) return rc;
-    iic_reduce_partials_kernel<<<reduce_grid(nj), 32 * RED_WARPS, 0, st>>>(partials, p.grid, nj, joint);
-    CY_CHECK_LAUNCH("iic_reduce_partials");
-    return CY_OK;
+    return launch_reduce_partials(partials, p.grid, nj, joint, st);
 }
 
 static size_t epilogue_scratch_doubles(int K, int pad) {

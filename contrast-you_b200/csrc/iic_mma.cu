@@ -143,6 +143,9 @@ iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
                      float* __restrict__ partials) {
     constexpr int NCW = FW_ROWS * NSPLIT;
     constexpr int THREADS = NCW * 32;
+    // the partial-joint reduction behind this kernel is a programmatic dependent launch: let its CTAs take the SMs as ours
+    // retire (they wait in cudaGridDependencySynchronize until this whole grid has completed)
+    asm volatile("griddepcontrol.launch_dependents;");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     float* stage0 = reinterpret_cast<float*>(smem);
