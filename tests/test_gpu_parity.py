@@ -933,3 +933,27 @@ def test_iic_cuda_graph_capture():
         want.backward()
         assert out.item() == pytest.approx(want.item(), rel=1e-6)
         np.testing.assert_allclose(x.grad.cpu().numpy(), xe.grad.cpu().numpy(), rtol=1e-5, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ host prefetcher
+def test_host_prefetcher_hands_out_the_refilled_buffers_in_order():
+    """contrast_you_b200.prefetch.HostPrefetcher: every next() returns the host contents as of the copy that was issued for
+    it, the two device sets alternate, and a copy never overwrites a set the compute stream still reads"""
+    from contrast_you_b200.prefetch import HostPrefetcher
+    h = torch.zeros(1 << 20, dtype=torch.float32).pin_memory()
+    pf = HostPrefetcher([h], DEV)
+    seen, ptrs = [], []
+    for i in range(6):
+        (d,) = pf.next()                       # copy for step i was issued before h changed to i + 1 ... except step 0 / 1
+        ptrs.append(d.data_ptr())
+        big = d.clone()
+        for _ in range(20):                    # keep the compute stream busy on this set while the next copy is in flight
+            big = big * 1.0000001
+        seen.append(float(d.sum().item()) / d.numel())
+        torch.cuda.synchronize()
+        h.fill_(float(i + 1))                  # refill the pinned buffer only once the copies in flight have landed
+    assert ptrs[0] == ptrs[2] == ptrs[4] and ptrs[1] == ptrs[3] == ptrs[5] and ptrs[0] != ptrs[1]
+    # step i reads what the host held when its copy was issued: copies 0 and 1 were issued while h == 0, copy i >= 2 during step i-1
+    assert seen[0] == 0.0 and seen[1] == 0.0
+    for i in range(2, 6):
+        assert seen[i] == float(i - 1), seen
