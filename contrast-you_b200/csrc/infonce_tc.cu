@@ -28,6 +28,7 @@
 // warp 3 tile-list builder (pass 2), warps 4..11 epilogue (warp w reads TMEM lanes 32*(w%4).., column half (w-4)/4).
 #include <cuda.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -986,15 +987,26 @@ static int bwd_splits(int64_t N, int64_t row_blocks, int64_t max_tps = 0) {
     return best;
 }
 
+// column splits of the forward: like the backward, minimise waves x (tiles per CTA + the fixed per-CTA cost — Zi into tensor
+// memory, pipeline fill and drain, ~6 tiles), at least 8 column tiles per CTA, at most 16 splits (the workspace holds 16
+// slabs).  Measured at N = 65536 (profiles/r2_fwd_splits_sweep.log): 512 row blocks 1.570 ms at 3 splits -> 1.527 at 2; one
+// rank's strip of an 8-GPU run (64 row blocks) 0.220 ms at 16 splits -> 0.204 at 9.
 static int fwd_splits(int64_t N, int64_t row_blocks, int bn) {
-    const int sms = sm_count();
-    const int64_t rb = row_blocks, ctiles = (N + bn - 1) / bn;
-    // enough CTAs for ~8 waves, but at least 8 column tiles per CTA so the A load and the prologue amortise
-    int64_t want = (8LL * sms + rb - 1) / rb;
-    int64_t maxs = ctiles / 8 > 0 ? ctiles / 8 : 1;
-    if (maxs > 16) maxs = 16;
-    int64_t s = want < 1 ? 1 : (want > maxs ? maxs : want);
-    return (int)s;
+    const int64_t sms = sm_count(), rb = row_blocks, ctiles = (N + bn - 1) / bn;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= 16; ++s) {
+        if (s > 1 && ctiles / s < 8) break;
+        const int64_t tps = (ctiles + s - 1) / s;
+        if ((int64_t)(s - 1) * tps >= ctiles) continue;              // the last split would be empty
+        const int64_t waves = (rb * s + sms - 1) / sms;
+        const double cost = (double)waves * (double)(tps + 6);
+        if (cost < best_cost) { best_cost = cost; best = s; }
+    }
+    static int forced = -1;      // CY_FWD_SPLITS=n pins the forward's column splits (A/B sweeps)
+    if (forced < 0) { const char* e = getenv("CY_FWD_SPLITS"); forced = e ? atoi(e) : 0; }
+    if (forced > 0 && forced <= 16 && forced <= ctiles) best = forced;
+    return best;
 }
 
 constexpr size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -1004,7 +1016,7 @@ constexpr int64_t SPLIT_MAX_TPS = 128;     // fp32 path: at most 128 column tile
 size_t infonce_tc_workspace_bytes(int64_t N, int64_t d, bool split) {
     if (d != 256 && d != 128) return 0;
     // forward: worst case over row ranges is a single 128-row block -> the most column splits
-    const int smax = fwd_splits(N, 1, 64);
+    const int smax = 16;
     const size_t fwd = (size_t)smax * 2 * 4 * (size_t)N * sizeof(float);
     // pass 2: [tile ranges | 2 slots x 2 values x N]
     const size_t p2 = align256((size_t)((N + 63) / 64) * sizeof(int2)) + (size_t)4 * N * sizeof(float);
