@@ -201,8 +201,15 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
     const long long t_entry = clock64();
 #endif
 
-    // ---- one-time setup: weights in UMMA layout (hi / lo), barriers, tensor memory
-    {
+    // this CTA's range of the row space
+    const int R0 = (int)(((long long)g.rows_total * blockIdx.x) / gridDim.x);
+    const int R1 = (int)(((long long)g.rows_total * (blockIdx.x + 1)) / gridDim.x);
+    const int plane = g.H * g.W;                 // host checks K * H * W < 2^31
+
+    // ---- one-time setup: weights in UMMA layout (hi / lo), barriers, tensor memory.  Every thread runs it exactly once (it ends
+    // in the CTA-wide barrier); the converter warps call it AFTER they have issued their first staged rows, so the cold-HBM
+    // latency of those loads overlaps the ~2 us of set-up instead of following it.
+    auto setup = [&]() {
         const float scale = gscale[0];
         for (int i = threadIdx.x; i < 2 * 3 * KS * 16 * 16; i += T_THREADS) {
             const int k = i % 16, n = (i / 16) % 16, ks = (i / 256) % KS, dyy = (i / (256 * KS)) % 3, side = i / (256 * KS * 3);
@@ -234,18 +241,16 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-    }
-    const uint32_t tmem = *tmem_slot;
+    };
+    const bool is_converter = warp >= T_CONV0 && warp < T_ISS0;
+    if (!is_converter) setup();
 #ifdef CY_TC_TIMING
     const long long t_start = clock64();
 #endif
-    // this CTA's range of the row space
-    const int R0 = (int)(((long long)g.rows_total * blockIdx.x) / gridDim.x);
-    const int R1 = (int)(((long long)g.rows_total * (blockIdx.x + 1)) / gridDim.x);
-    const int plane = g.H * g.W;                 // host checks K * H * W < 2^31
 
     if (warp >= T_ISS0 && warp < T_ISS0 + T_NISS) {
         // ------------------------------------------------------------------------------------------ MMA issuers
+        const uint32_t tmem = *tmem_slot;
         if (elect_one()) {
             TC_TDECL;
 #ifdef CY_TC_TIMING
@@ -389,6 +394,8 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
             issue_row(pf, u);
             if (!pf.done) step(pf);
         }
+        setup();
+        const uint32_t tmem = *tmem_slot;
         // Software pipeline: the tcgen05.st of row n are published (wait::st, fence, arrive) only after the shared-memory reads
         // of row n+1 have been issued, and the a_empty probe of a row is issued before its conversion work, so neither the
         // ~60-cycle store drain nor the ~100-cycle barrier probe sits on the warp's critical path.
@@ -458,6 +465,7 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
     } else if (warp < T_CONV0) {
         // ------------------------------------------------------------------------------------------ epilogue
         const int eset = (warp - T_EPI0) >> 2, quarter = warp & 3;
+        const uint32_t tmem = *tmem_slot;
         uint32_t orow = 0;
         Seg sg;
         TC_TDECL;
@@ -516,7 +524,7 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
         atomicMax(reinterpret_cast<unsigned long long*>(tc_dbg + 59), (unsigned long long)(t_start - t_entry));
     }
 #endif
-    if (warp == T_WALLOC) tmem_dealloc(tmem, 512);
+    if (warp == T_WALLOC) tmem_dealloc(*tmem_slot, 512);
 }
 
 template <int KH>
