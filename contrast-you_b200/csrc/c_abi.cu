@@ -82,6 +82,12 @@ int imsat_bwd(const void*, int, int64_t, int, int64_t, float, const float*, cons
 int p2p_push(void* const*, int, int, const unsigned long long*, int, cudaStream_t);
 int p2p_push_barrier(void* const*, int, int, const unsigned long long*, int, unsigned long long, unsigned int*, unsigned int, cudaStream_t);
 int iic_bwd(const void*, const void*, int, int, int, int, int, int, const float*, const float*, void*, void*, cudaStream_t);
+int iic_joint_heads(const void* const*, const void* const*, int, int, int, int, int, int, int, double*, long long, void*, size_t,
+                    cudaStream_t);
+int iic_epilogue_heads(const double*, long long, int, int, int, int, int, float, float, double, float*, float*, float*, long long, void*,
+                       size_t, cudaStream_t);
+int iic_bwd_heads(const void* const*, const void* const*, int, int, int, int, int, int, int, const float*, long long, const float*,
+                  void* const*, void* const*, cudaStream_t);
 
 static int check_infonce_args(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
                               const uint8_t* codes, int64_t row_begin, int64_t row_end, int variant) {
@@ -341,6 +347,41 @@ int cy_iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int
     if (rc) return rc;
     CY_CHECK_ARG(djoint && gscale && dx && dy, "null pointer");
     return iic_bwd(x, y, dtype, B, K, H, W, pad, djoint, gscale, dx, dy, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_iic_joint_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
+                       double* joint, long long joint_stride, void* workspace, size_t workspace_bytes, void* stream) {
+    CY_NVTX("cy_iic_joint_heads");
+    CY_CHECK_ARG(xs && ys && n_heads >= 1 && joint && joint_stride >= 0, "bad arguments");
+    for (int s = 0; s < n_heads; ++s) {
+        const int rc = check_iic(xs[s], ys[s], dtype, B, K, H, W, pad);
+        if (rc) return rc;
+    }
+    return iic_joint_heads(xs, ys, n_heads, dtype, B, K, H, W, pad, joint, joint_stride, workspace, workspace_bytes,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_iic_epilogue_heads(const double* joint, long long joint_stride, int n_heads, int n_slots, int K, int pad, int symmetric,
+                          float lamda, float eps, double n_pixels, float* loss, float* p00, float* djoint, long long out_stride,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    CY_NVTX("cy_iic_epilogue_heads");
+    CY_CHECK_ARG(joint && loss && p00 && n_heads >= 1 && n_slots >= 1 && K >= 1 && pad >= 0 && n_pixels > 0, "bad arguments");
+    return iic_epilogue_heads(joint, joint_stride, n_heads, n_slots, K, pad, symmetric, lamda, eps, n_pixels, loss, p00, djoint,
+                              out_stride, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_iic_bwd_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
+                     const float* djoint, long long djoint_stride, const float* gscale, void* const* dxs, void* const* dys,
+                     void* stream) {
+    CY_NVTX("cy_iic_bwd_heads");
+    CY_CHECK_ARG(xs && ys && dxs && dys && n_heads >= 1 && djoint && gscale, "bad arguments");
+    for (int s = 0; s < n_heads; ++s) {
+        const int rc = check_iic(xs[s], ys[s], dtype, B, K, H, W, pad);
+        if (rc) return rc;
+        CY_CHECK_ARG(dxs[s] && dys[s], "null pointer");
+    }
+    return iic_bwd_heads(xs, ys, n_heads, dtype, B, K, H, W, pad, djoint, djoint_stride, gscale, dxs, dys,
+                         reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -179,8 +179,11 @@ iic_joint_generic_kernel(const void* __restrict__ x, const void* __restrict__ y,
 // block = 32 joint entries (lanes) x 32 warps striding over the partials; fixed summation order: deterministic
 constexpr int RED_WARPS = 32;
 __global__ void __launch_bounds__(32 * RED_WARPS)
-iic_reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int nj, double* __restrict__ joint) {
+iic_reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int nj, double* __restrict__ joint,
+                           long long partials_stride, long long joint_stride) {
     __shared__ double acc[RED_WARPS][33];
+    partials += (size_t)blockIdx.y * partials_stride;      // blockIdx.y = sub-head of a heads launch (strides 0 otherwise)
+    joint += (size_t)blockIdx.y * joint_stride;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + lane;
     // launched with programmatic stream serialization right behind the joint kernel: everything above overlaps its tail,
@@ -211,9 +214,10 @@ iic_reduce_partials_kernel(const float* __restrict__ partials, int n_partials, i
     }
 }
 // launch helper: programmatic dependent launch (the kernel may start while its predecessor on the stream drains)
-static int launch_reduce_partials(const float* partials, int n_partials, int nj, double* joint, cudaStream_t st) {
+static int launch_reduce_partials(const float* partials, int n_partials, int nj, double* joint, cudaStream_t st, int n_heads = 1,
+                                  long long partials_stride = 0, long long joint_stride = 0) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)((nj + 31) / 32));
+    cfg.gridDim = dim3((unsigned)((nj + 31) / 32), (unsigned)n_heads);
     cfg.blockDim = dim3(32 * RED_WARPS);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
@@ -222,7 +226,7 @@ static int launch_reduce_partials(const float* partials, int n_partials, int nj,
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, iic_reduce_partials_kernel, partials, n_partials, nj, joint);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, iic_reduce_partials_kernel, partials, n_partials, nj, joint, partials_stride, joint_stride);
     count_launch();
     if (e != cudaSuccess) { set_error("iic_reduce_partials: %s", cudaGetErrorString(e)); return (int)e; }
     return CY_OK;
@@ -267,9 +271,14 @@ constexpr int EPI_THREADS = 1024;
 __global__ void __launch_bounds__(EPI_THREADS)
 iic_epilogue_kernel(const double* __restrict__ joint, int n_slots, int K, int pad, int symmetric, double lamda, double eps,
                     double n_pixels, float* __restrict__ loss, float* __restrict__ p00, float* __restrict__ p_ij,
-                    float* __restrict__ djoint, double* __restrict__ gscratch) {
+                    float* __restrict__ djoint, double* __restrict__ gscratch, long long joint_stride, long long out_stride) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
+    // one CTA per sub-head of a heads launch (gridDim.x = 1 and strides 0 otherwise); p_ij and gscratch are single-head only
+    joint += (size_t)blockIdx.x * joint_stride;
+    loss += (size_t)blockIdx.x * out_stride;
+    p00 += (size_t)blockIdx.x * out_stride;
+    if (djoint) djoint += (size_t)blockIdx.x * out_stride;
     const int T = 2 * pad + 1, TT = T * T, KK = K * K, nj = KK * TT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     double* Bm = gscratch ? gscratch : sm;      // large K / padding: the arrays live in the caller's workspace
@@ -604,6 +613,11 @@ int iic_bwd_mma(const void* x, const void* y, int dtype, int B, int K, int H, in
 
 // iic_bwd_tc.cu (tcgen05 adjoint for padding = 1, K <= 16, fp32: pixels on the TMEM lanes, A slots written by converter warps,
 // 18 small MMAs per output row; CY_ERR_UNSUPPORTED for shapes it does not take).  The default adjoint.
+int iic_joint_mma_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
+                        float* partials, int* n_partials, cudaStream_t st);
+int iic_bwd_tc_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
+                     const float* djoint, long long dj_stride, const float* gscale, void* const* dxs, void* const* dys,
+                     cudaStream_t st);
 int iic_bwd_tc(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
                const float* gscale, void* dx, void* dy, cudaStream_t st);
 
@@ -712,6 +726,37 @@ int iic_joint(const void* x, const void* y, int dtype, int B, int K, int H, int 
     return launch_reduce_partials(partials, p.grid, nj, joint, st);
 }
 
+// n_heads (x, y) pairs of one shape: head s writes joint + s * joint_stride (doubles).  workspace = n_heads *
+// iic_workspace_bytes().  One joint launch + one reduction launch when the tensor-core kernel takes the shape (heads in
+// chunks of 8), head by head otherwise.
+int iic_joint_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
+                    double* joint, long long joint_stride, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    const size_t per = iic_workspace_bytes(B, K, H, W, pad);
+    CY_CHECK_ARG(n_heads >= 1 && workspace && workspace_bytes >= per * (size_t)n_heads, "iic_joint_heads: workspace %zu < %zu",
+                 workspace_bytes, per * (size_t)n_heads);
+    const int T = 2 * pad + 1, nj = K * K * T * T;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    for (int s0 = 0; s0 < n_heads;) {
+        const int n = n_heads - s0 < 8 ? n_heads - s0 : 8;
+        int rc = CY_ERR_UNSUPPORTED;
+        if (mma_enabled() && n > 1) {
+            int np = 0;
+            float* partials = reinterpret_cast<float*>(ws + per * s0);
+            rc = iic_joint_mma_heads(xs + s0, ys + s0, n, dtype, B, K, H, W, pad, partials, &np, st);
+            if (rc == CY_OK)
+                rc = launch_reduce_partials(partials, np, nj, joint + (size_t)s0 * joint_stride, st, n, (long long)np * nj, joint_stride);
+            if (rc != CY_OK && rc != CY_ERR_UNSUPPORTED) return rc;
+        }
+        if (rc == CY_OK) { s0 += n; continue; }
+        for (int s = s0; s < s0 + n; ++s) {
+            rc = iic_joint(xs[s], ys[s], dtype, B, K, H, W, pad, joint + (size_t)s * joint_stride, ws + per * s, per, st);
+            if (rc != CY_OK) return rc;
+        }
+        s0 += n;
+    }
+    return CY_OK;
+}
+
 static size_t epilogue_scratch_doubles(int K, int pad) {
     const int T = 2 * pad + 1, TT = T * T, nj = K * K * TT;
     return (size_t)3 * nj + TT + 2 * TT * K;
@@ -722,8 +767,9 @@ size_t iic_epilogue_workspace_bytes(int K, int pad) {
     return b > 160 * 1024 ? b : 0;      // small problems keep everything in shared memory
 }
 
-int iic_epilogue(const double* joint, int n_slots, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
-                 float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+static int iic_epilogue_impl(const double* joint, int n_slots, int K, int pad, int symmetric, float lamda, float eps, double n_pixels,
+                             float* loss, float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes,
+                             cudaStream_t st, int n_heads, long long joint_stride, long long out_stride) {
     size_t smem = epilogue_scratch_doubles(K, pad) * sizeof(double);
     double* gscratch = nullptr;
     if (iic_epilogue_workspace_bytes(K, pad)) {
@@ -737,9 +783,33 @@ int iic_epilogue(const double* joint, int n_slots, int K, int pad, int symmetric
         if (e != cudaSuccess) { set_error("iic_epilogue smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr.set(smem);
     }
-    iic_epilogue_kernel<<<1, EPI_THREADS, smem, st>>>(joint, n_slots, K, pad, symmetric, (double)lamda, (double)eps, n_pixels, loss, p00,
-                                                      p_ij, djoint, gscratch);
+    iic_epilogue_kernel<<<n_heads, EPI_THREADS, smem, st>>>(joint, n_slots, K, pad, symmetric, (double)lamda, (double)eps, n_pixels, loss,
+                                                            p00, p_ij, djoint, gscratch, joint_stride, out_stride);
     CY_CHECK_LAUNCH("iic_epilogue");
+    return CY_OK;
+}
+
+int iic_epilogue(const double* joint, int n_slots, int K, int pad, int symmetric, float lamda, float eps, double n_pixels, float* loss,
+                 float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    return iic_epilogue_impl(joint, n_slots, K, pad, symmetric, lamda, eps, n_pixels, loss, p00, p_ij, djoint, workspace,
+                             workspace_bytes, st, 1, 0, 0);
+}
+
+// n_heads epilogues in one launch (one CTA each): head s reads joint + s * joint_stride (doubles; [n_slots][nj] inside) and writes
+// loss / p00 / djoint + s * out_stride (floats).  Shapes whose arrays need the global scratch run head by head.
+int iic_epilogue_heads(const double* joint, long long joint_stride, int n_heads, int n_slots, int K, int pad, int symmetric, float lamda,
+                       float eps, double n_pixels, float* loss, float* p00, float* djoint, long long out_stride, void* workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
+    CY_CHECK_ARG(n_heads >= 1, "iic_epilogue_heads: n_heads=%d", n_heads);
+    if (iic_epilogue_workspace_bytes(K, pad) == 0)
+        return iic_epilogue_impl(joint, n_slots, K, pad, symmetric, lamda, eps, n_pixels, loss, p00, nullptr, djoint, nullptr, 0, st,
+                                 n_heads, joint_stride, out_stride);
+    for (int s = 0; s < n_heads; ++s) {
+        const int rc = iic_epilogue_impl(joint + s * joint_stride, n_slots, K, pad, symmetric, lamda, eps, n_pixels, loss + s * out_stride,
+                                         p00 + s * out_stride, nullptr, djoint ? djoint + s * out_stride : nullptr, workspace,
+                                         workspace_bytes, st, 1, 0, 0);
+        if (rc != CY_OK) return rc;
+    }
     return CY_OK;
 }
 
@@ -810,6 +880,28 @@ int iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W,
     const int grid = (int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535);
     iic_bwd_generic_kernel<<<grid, 256, 0, st>>>(x, y, dtype, B, K, H, W, pad, djoint, gscale, dx, dy);
     CY_CHECK_LAUNCH("iic_bwd_generic");
+    return CY_OK;
+}
+
+// n_heads adjoints of one shape: ONE tcgen05 launch per chunk of 8 heads when the shape is eligible, head by head otherwise
+int iic_bwd_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
+                  const float* djoint, long long dj_stride, const float* gscale, void* const* dxs, void* const* dys, cudaStream_t st) {
+    CY_CHECK_ARG(n_heads >= 1, "iic_bwd_heads: n_heads=%d", n_heads);
+    for (int s0 = 0; s0 < n_heads;) {
+        const int n = n_heads - s0 < 8 ? n_heads - s0 : 8;
+        int rc = CY_ERR_UNSUPPORTED;
+        if (n > 1 && mma_enabled() && tc_enabled()) {
+            rc = iic_bwd_tc_heads(xs + s0, ys + s0, n, dtype, B, K, H, W, pad, djoint + (size_t)s0 * dj_stride, dj_stride, gscale,
+                                  dxs + s0, dys + s0, st);
+            if (rc != CY_OK && rc != CY_ERR_UNSUPPORTED) return rc;
+        }
+        if (rc != CY_OK)
+            for (int s = s0; s < s0 + n; ++s) {
+                rc = iic_bwd(xs[s], ys[s], dtype, B, K, H, W, pad, djoint + (size_t)s * dj_stride, gscale, dxs[s], dys[s], st);
+                if (rc != CY_OK) return rc;
+            }
+        s0 += n;
+    }
     return CY_OK;
 }
 

@@ -89,10 +89,19 @@ constexpr int T_THREADS = 32 * (T_ISS0 + T_NISS);
 constexpr int T_PF = CY_TC_PF;                   // converter prefetch depth (own rows): cp.async groups in flight per warp
 constexpr int T_WTILE = 512;                     // one weight tile: [n 16][k 16] bf16, no-swizzle K-major core matrices
 
+constexpr int T_MAXHEADS = 8;                    // sub-head pairs of one launch (cy_iic_bwd_heads)
 struct TcGeom {
     int B, K, H, W;
+    int S;                                       // sub-head pairs: S independent (x, y, dL/dJ) problems of one shape
     int TW2;                                     // strips per image row
-    int rows_total;                              // 2 * B * TW2 * H
+    int rows_total;                              // S * 2 * B * TW2 * H
+    long long dj_stride;                         // floats between the heads' dL/dJ tables
+};
+struct TcPtrs {                                  // per head: the two maps and the two gradient outputs
+    const float* x[T_MAXHEADS];
+    const float* y[T_MAXHEADS];
+    float* dx[T_MAXHEADS];
+    float* dy[T_MAXHEADS];
 };
 
 // The row-space range [R0, R1) of one CTA is walked as segments (a segment never crosses a strip).  Segment k starts at R0
@@ -112,10 +121,12 @@ __device__ __forceinline__ bool seg_at(int R0, int R1, int H, int k, Seg& s) {
 
 // unit -> (side, image, strip).  Images run backwards and the two sides alternate: the joint kernel has just streamed x and y
 // front to back, so the tail of both tensors is what the 126 MB L2 still holds.
-__device__ __forceinline__ void unit_decode(const TcGeom& g, int unit, int& side, int& b, int& tw) {
+__device__ __forceinline__ void unit_decode(const TcGeom& g, int unit, int& head, int& side, int& b, int& tw) {
     tw = unit % g.TW2;
     side = (unit / g.TW2) & 1;
-    b = g.B - 1 - unit / (2 * g.TW2);
+    const int rest = unit / (2 * g.TW2);
+    b = g.B - 1 - rest % g.B;
+    head = rest / g.B;
 }
 
 // (v0, v1) -> packed bf16 pairs (v0 in the low half), v = hi + lo: hi = bf16 round-to-nearest (one F2FP per pair: 5 per warp
@@ -178,8 +189,8 @@ __device__ long long tc_dbg[64];
 
 template <int KH>                                // channel pairs: K == 2 * KH or 2 * KH - 1 (the host picks KH = ceil(K / 2))
 __global__ void __launch_bounds__(T_THREADS, 1)
-iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGeom g, const float* __restrict__ djoint,
-                  const float* __restrict__ gscale, float* __restrict__ dx_out, float* __restrict__ dy_out) {
+iic_bwd_tc_kernel(const __grid_constant__ TcPtrs ptrs, const __grid_constant__ TcGeom g, const float* __restrict__ djoint,
+                  const float* __restrict__ gscale) {
     constexpr int KC = 2 * KH;                   // channels carried per pixel (zero past K)
     constexpr int KS = (3 * KH + 7) / 8;         // K-steps of 16 per input row: k = dxx * KC + c
     constexpr int PW = KS * 8;                   // 32-bit words per plane (hi or lo) of an A slot
@@ -187,8 +198,9 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
     constexpr uint32_t A0 = T_ND * 16;           // TMEM columns: [0, 128) D slots, [128, 128 + 8 * ACOLS) A slots
     static_assert(A0 + T_NA * ACOLS <= 512, "TMEM budget");
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* wsm = smem;                         // weights [side 2][dy 3][ks KS][part 2] tiles of T_WTILE bytes
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + 2 * 3 * KS * 2 * T_WTILE);
+    uint8_t* wsm = smem;                         // weights [head S][side 2][dy 3][ks KS][part 2] tiles of T_WTILE bytes
+    constexpr int HEAD_WBYTES = 2 * 3 * KS * 2 * T_WTILE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + (size_t)g.S * HEAD_WBYTES);
     uint64_t* a_full = bars;                     // [T_NA]  the four quarter warps have written the slot
     uint64_t* a_empty = a_full + T_NA;           // [T_NA]  the MMAs of the three output rows that read the slot are complete
     uint64_t* d_full = a_empty + T_NA;           // [T_ND]  the MMAs of the output row are complete
@@ -211,19 +223,21 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
     // latency of those loads overlaps the ~2 us of set-up instead of following it.
     auto setup = [&]() {
         const float scale = gscale[0];
-        for (int i = threadIdx.x; i < 2 * 3 * KS * 16 * 16; i += T_THREADS) {
-            const int k = i % 16, n = (i / 16) % 16, ks = (i / 256) % KS, dyy = (i / (256 * KS)) % 3, side = i / (256 * KS * 3);
+        for (int i = threadIdx.x; i < g.S * 2 * 3 * KS * 16 * 16; i += T_THREADS) {
+            const int k = i % 16, n = (i / 16) % 16, ks = (i / 256) % KS, dyy = (i / (256 * KS)) % 3, side = (i / (256 * KS * 3)) & 1;
+            const int head = i / (256 * KS * 3 * 2);
+            const float* dj = djoint + (size_t)head * g.dj_stride;
             const int kk = ks * 16 + k, dxx = kk / KC, c = kk % KC, o = n;
             float w = 0.f;
             if (dxx < 3 && c < K && o < K) {
                 // side 0 (dL/dy from x): Wt[o = k2][c = k1][dy][dx] = G[k1, k2, dy, dx]
                 // side 1 (dL/dx from y): Wt[o = k1][c = k2][dy][dx] = G[k1, k2, 2 - dy, 2 - dx]
-                w = side == 0 ? djoint[((c * K + o) * 3 + dyy) * 3 + dxx] : djoint[((o * K + c) * 3 + (2 - dyy)) * 3 + (2 - dxx)];
+                w = side == 0 ? dj[((c * K + o) * 3 + dyy) * 3 + dxx] : dj[((o * K + c) * 3 + (2 - dyy)) * 3 + (2 - dxx)];
                 w *= scale;
             }
             const __nv_bfloat16 hi = __float2bfloat16_rn(w);
             const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-            const uint32_t tile = (uint32_t)(((side * 3 + dyy) * KS + ks) * 2) * T_WTILE;
+            const uint32_t tile = (uint32_t)((((head * 2 + side) * 3 + dyy) * KS + ks) * 2) * T_WTILE;
             const uint32_t off = (n / 8) * 256 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2;
             *reinterpret_cast<__nv_bfloat16*>(wsm + tile + off) = hi;
             *reinterpret_cast<__nv_bfloat16*>(wsm + tile + T_WTILE + off) = lo;
@@ -261,10 +275,10 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
             uint32_t ar0 = 0, orow = 0;
             Seg sg;
             for (int k = 0; seg_at(R0, R1, g.H, k, sg); ++k) {
-                int side, b, tw;
-                unit_decode(g, sg.unit, side, b, tw);
+                int head, side, b, tw;
+                unit_decode(g, sg.unit, head, side, b, tw);
                 const int n_out = sg.n_out;
-                const uint64_t wside = wdesc0 + (uint64_t)((side * 3 * KS * 2 * T_WTILE) >> 4);
+                const uint64_t wside = wdesc0 + (uint64_t)(((head * 2 + side) * 3 * KS * 2 * T_WTILE) >> 4);
                 for (int i = 0; i < n_out; ++i, ++orow) {
                     if ((int)(orow % T_NISS) != warp - T_ISS0) continue;
                     const uint32_t a = ar0 + (uint32_t)i;
@@ -347,21 +361,29 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
             ccol[it] = 4 * jc - 4;
             coff[it] = ch * plane + ccol[it];
         }
-        auto enter = [&](Cursor& c) {                                  // position on the first own row of segment c.k
-            Seg sg;
-            c.done = !seg_at(R0, R1, g.H, c.k, sg);
-            if (c.done) return;
-            int side, b, tw;
-            unit_decode(g, sg.unit, side, b, tw);
-            const int w0q = tw * T_TWO + quarter * T_QPX;
-            c.cmask = 0u;
+        auto enter = [&](Cursor& c) {                                  // position on the first own row of segment c.k or later
+            for (;;) {
+                Seg sg;
+                c.done = !seg_at(R0, R1, g.H, c.k, sg);
+                if (c.done) return;
+                c.n_in = sg.n_out + 2;
+                c.j = (int)((cset + T_NCS - c.ar0 % T_NCS) % T_NCS);
+                if (c.j >= c.n_in) {                                   // a one-row segment (3 input rows) has no row for one of the
+                    c.ar0 += (uint32_t)c.n_in;                         // T_NCS = 4 sets: go on to the next segment (writing a row
+                    ++c.k;                                             // of its own here would arrive twice on that A slot)
+                    continue;
+                }
+                int head, side, b, tw;
+                unit_decode(g, sg.unit, head, side, b, tw);
+                const int w0q = tw * T_TWO + quarter * T_QPX;
+                c.cmask = 0u;
 #pragma unroll
-            for (int it = 0; it < NIT; ++it)
-                if (clive[it] && w0q + ccol[it] >= 0 && w0q + ccol[it] < g.W) c.cmask |= 1u << it;
-            c.n_in = sg.n_out + 2;
-            c.j = (int)((cset + T_NCS - c.ar0 % T_NCS) % T_NCS);
-            c.h = sg.hb - 1 + c.j;
-            c.p = (side ? y : x) + (size_t)b * K * plane + w0q + (long long)c.h * g.W;
+                for (int it = 0; it < NIT; ++it)
+                    if (clive[it] && w0q + ccol[it] >= 0 && w0q + ccol[it] < g.W) c.cmask |= 1u << it;
+                c.h = sg.hb - 1 + c.j;
+                c.p = (side ? ptrs.y : ptrs.x)[head] + (size_t)b * K * plane + w0q + (long long)c.h * g.W;
+                return;
+            }
         };
         auto step = [&](Cursor& c) {
             c.j += T_NCS;
@@ -386,7 +408,7 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
         };
         TC_TDECL;
         Cursor cur, pf;
-        cur.k = 0; cur.ar0 = 0; cur.cmask = 0u;
+        cur.k = 0; cur.ar0 = 0; cur.cmask = 0u; cur.p = ptrs.x[0]; cur.h = 0; cur.j = 0; cur.n_in = 0;
         enter(cur);
         pf = cur;
 #pragma unroll
@@ -470,12 +492,12 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
         Seg sg;
         TC_TDECL;
         for (int k = 0; seg_at(R0, R1, g.H, k, sg); ++k) {
-            int side, b, tw;
-            unit_decode(g, sg.unit, side, b, tw);
+            int head, side, b, tw;
+            unit_decode(g, sg.unit, head, side, b, tw);
             const int col = tw * T_TWO + quarter * T_QPX + lane;
             const bool col_ok = lane < T_QPX && col < g.W;
             int i = (int)((eset + T_NES - orow % T_NES) % T_NES);      // first own row of the segment
-            float* p = (side ? dx_out : dy_out) + (size_t)b * K * plane + (size_t)(sg.hb + i) * g.W + (col_ok ? col : 0);
+            float* p = (side ? ptrs.dx : ptrs.dy)[head] + (size_t)b * K * plane + (size_t)(sg.hb + i) * g.W + (col_ok ? col : 0);
             for (; i < sg.n_out; i += T_NES, p += T_NES * g.W) {
                 const uint32_t r_ = orow + (uint32_t)i, slot = r_ % T_ND;
                 TC_T(0, mbar_wait_backoff<CY_TC_SLEEP_EPI>(d_full + slot, (r_ / T_ND) & 1u));
@@ -527,13 +549,18 @@ iic_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ y, TcGe
     if (warp == T_WALLOC) tmem_dealloc(*tmem_slot, 512);
 }
 
+// weight tiles of every head + barriers + the converters' staging ring
+size_t tc_smem_bytes(int KH, int S) {
+    const int KS = (3 * KH + 7) / 8;
+    return (size_t)S * 2 * 3 * KS * 2 * T_WTILE + 512 + (size_t)4 * T_NCS * T_PF * (2 * KH) * 36 * 4;
+}
+
 template <int KH>
-int launch_bwd_tc(const float* x, const float* y, const TcGeom& g, const float* djoint, const float* gscale, float* dx, float* dy,
-                  cudaStream_t st) {
+int launch_bwd_tc(const TcPtrs& ptrs, const TcGeom& g, const float* djoint, const float* gscale, cudaStream_t st) {
     // one CTA per SM: the register file (>= 52 registers x 896 threads) does not hold two, so the 512-column TMEM allocation
     // never waits for a co-resident CTA
     constexpr int KS = (3 * KH + 7) / 8;
-    size_t smem = (size_t)2 * 3 * KS * 2 * T_WTILE + 512 + (size_t)4 * T_NCS * T_PF * (2 * KH) * 36 * 4;
+    size_t smem = tc_smem_bytes(KH, g.S);
     auto k = iic_bwd_tc_kernel<KH>;
     static SmemAttrCache attr;
     if (attr.need(smem)) {
@@ -543,7 +570,7 @@ int launch_bwd_tc(const float* x, const float* y, const TcGeom& g, const float* 
     }
     const int sms = device_sm_count();
     const int grid = g.rows_total < sms ? g.rows_total : sms;
-    k<<<grid, T_THREADS, smem, st>>>(x, y, g, djoint, gscale, dx, dy);
+    k<<<grid, T_THREADS, smem, st>>>(ptrs, g, djoint, gscale);
     CY_CHECK_LAUNCH("iic_bwd_tc");
 #ifdef CY_TC_TIMING
     {
@@ -568,31 +595,47 @@ int launch_bwd_tc(const float* x, const float* y, const TcGeom& g, const float* 
 
 }  // namespace
 
+// n_heads independent (x, y, dL/dJ) problems of one shape in ONE launch (the sub-head stack of IIDSegmentationLoss callers,
+// SURVEY.md 8(f2)); head s reads djoint + s * dj_stride.  Returns CY_ERR_UNSUPPORTED when the shape is not eligible or the heads'
+// weight tiles do not fit beside the staging ring (the caller then loops over the heads).
+int iic_bwd_tc_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
+                     const float* djoint, long long dj_stride, const float* gscale, void* const* dxs, void* const* dys,
+                     cudaStream_t st) {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (dtype != CY_F32 || pad != 1 || K > 16 || K < 1 || (W % 4) != 0 || n_heads < 1 || n_heads > T_MAXHEADS) return CY_ERR_UNSUPPORTED;
+    TcGeom g;
+    TcPtrs ptrs;
+    for (int s = 0; s < T_MAXHEADS; ++s) {
+        const int t = s < n_heads ? s : 0;
+        if (!al16(xs[t]) || !al16(ys[t])) return CY_ERR_UNSUPPORTED;
+        ptrs.x[s] = reinterpret_cast<const float*>(xs[t]);
+        ptrs.y[s] = reinterpret_cast<const float*>(ys[t]);
+        ptrs.dx[s] = reinterpret_cast<float*>(dxs[t]);
+        ptrs.dy[s] = reinterpret_cast<float*>(dys[t]);
+    }
+    g.B = B; g.K = K; g.H = H; g.W = W; g.S = n_heads; g.dj_stride = dj_stride;
+    g.TW2 = (W + T_TWO - 1) / T_TWO;
+    const long long rows = 2LL * n_heads * B * g.TW2 * H;
+    if (rows <= 0 || rows > 0x7fffffffLL / 2 || (long long)K * H * W > 0x7fffffffLL / 8) return CY_ERR_UNSUPPORTED;
+    g.rows_total = (int)rows;
+    const int KH = (K + 1) / 2;
+    if (tc_smem_bytes(KH, n_heads) > (size_t)227 * 1024) return CY_ERR_UNSUPPORTED;
+    switch (KH) {
+        case 1: return launch_bwd_tc<1>(ptrs, g, djoint, gscale, st);
+        case 2: return launch_bwd_tc<2>(ptrs, g, djoint, gscale, st);
+        case 3: return launch_bwd_tc<3>(ptrs, g, djoint, gscale, st);
+        case 4: return launch_bwd_tc<4>(ptrs, g, djoint, gscale, st);
+        case 5: return launch_bwd_tc<5>(ptrs, g, djoint, gscale, st);
+        case 6: return launch_bwd_tc<6>(ptrs, g, djoint, gscale, st);
+        case 7: return launch_bwd_tc<7>(ptrs, g, djoint, gscale, st);
+        default: return launch_bwd_tc<8>(ptrs, g, djoint, gscale, st);
+    }
+}
+
 // returns CY_ERR_UNSUPPORTED when the shape is not eligible (the caller then takes the mma.sync / CUDA-core kernels)
 int iic_bwd_tc(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
                const float* gscale, void* dx, void* dy, cudaStream_t st) {
-    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    if (dtype != CY_F32 || pad != 1 || K > 16 || K < 1 || (W % 4) != 0 || !al16(x) || !al16(y)) return CY_ERR_UNSUPPORTED;
-    TcGeom g;
-    g.B = B; g.K = K; g.H = H; g.W = W;
-    g.TW2 = (W + T_TWO - 1) / T_TWO;
-    const long long rows = 2LL * B * g.TW2 * H;
-    if (rows <= 0 || rows > 0x7fffffffLL / 2 || (long long)K * H * W > 0x7fffffffLL / 8) return CY_ERR_UNSUPPORTED;
-    g.rows_total = (int)rows;
-    const float* xf = reinterpret_cast<const float*>(x);
-    const float* yf = reinterpret_cast<const float*>(y);
-    float* dxf = reinterpret_cast<float*>(dx);
-    float* dyf = reinterpret_cast<float*>(dy);
-    switch ((K + 1) / 2) {
-        case 1: return launch_bwd_tc<1>(xf, yf, g, djoint, gscale, dxf, dyf, st);
-        case 2: return launch_bwd_tc<2>(xf, yf, g, djoint, gscale, dxf, dyf, st);
-        case 3: return launch_bwd_tc<3>(xf, yf, g, djoint, gscale, dxf, dyf, st);
-        case 4: return launch_bwd_tc<4>(xf, yf, g, djoint, gscale, dxf, dyf, st);
-        case 5: return launch_bwd_tc<5>(xf, yf, g, djoint, gscale, dxf, dyf, st);
-        case 6: return launch_bwd_tc<6>(xf, yf, g, djoint, gscale, dxf, dyf, st);
-        case 7: return launch_bwd_tc<7>(xf, yf, g, djoint, gscale, dxf, dyf, st);
-        default: return launch_bwd_tc<8>(xf, yf, g, djoint, gscale, dxf, dyf, st);
-    }
+    return iic_bwd_tc_heads(&x, &y, 1, dtype, B, K, H, W, pad, djoint, 0, gscale, &dx, &dy, st);
 }
 
 }  // namespace cy

@@ -137,10 +137,18 @@ constexpr int FW_ROWS = 8;       // image rows per forward tile = row-warps per 
 // one 16-pixel step (the first MMA takes C = 0) and the result is added to the running sums with round-to-nearest FADDs:
 // the joint then carries no bias that grows with the number of pixels (needed for the padding = 0 loss, whose value is
 // a 1e-3 residual of O(1) terms).
+// blockIdx.y = sub-head: S independent (x, y) pairs of one shape share a launch, each with gridDim.x CTAs and its own partial
+// joints partials[head][cta][nj] (cy_iic_joint_heads; gridDim.y = 1 for the plain call)
+constexpr int MMA_MAXHEADS = 8;
+struct JointMaps {
+    CUtensorMap x[MMA_MAXHEADS], y[MMA_MAXHEADS];
+};
 template <int MT, int NTW, int NSPLIT, int NCH>
 __global__ void __launch_bounds__(FW_ROWS * NSPLIT * 32, NSPLIT == 1 ? 2 : 1)
-iic_joint_mma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, MmaGeom g,
-                     float* __restrict__ partials) {
+iic_joint_mma_kernel(const __grid_constant__ JointMaps maps, MmaGeom g, float* __restrict__ partials) {
+    const CUtensorMap& tmx = maps.x[blockIdx.y];
+    const CUtensorMap& tmy = maps.y[blockIdx.y];
+    partials += (size_t)blockIdx.y * gridDim.x * (size_t)(g.K * g.K * g.T * g.T);
     constexpr int NCW = FW_ROWS * NSPLIT;
     constexpr int THREADS = NCW * 32;
     // the partial-joint reduction behind this kernel is a programmatic dependent launch: let its CTAs take the SMs as ours
@@ -683,8 +691,7 @@ bool fwd_geom(int B, int K, int H, int W, int pad, MmaGeom* g, int* mt, int* ntw
 }
 
 template <int MT, int NTW, int NSPLIT, int NCH>
-int launch_joint_mma(const CUtensorMap& tmx, const CUtensorMap& tmy, const MmaGeom& g, size_t smem, int grid, float* partials,
-                     cudaStream_t st) {
+int launch_joint_mma(const JointMaps& maps, int n_heads, const MmaGeom& g, size_t smem, int grid, float* partials, cudaStream_t st) {
     auto k = iic_joint_mma_kernel<MT, NTW, NSPLIT, NCH>;
     static SmemAttrCache attr;            // raise the opt-in limit only when it grows (remembered per device)
     if (attr.need(smem)) {
@@ -692,36 +699,48 @@ int launch_joint_mma(const CUtensorMap& tmx, const CUtensorMap& tmy, const MmaGe
         if (e != cudaSuccess) { set_error("iic_joint_mma smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
         attr.set(smem);
     }
-    k<<<grid, FW_ROWS * NSPLIT * 32, smem, st>>>(tmx, tmy, g, partials);
+    k<<<dim3((unsigned)grid, (unsigned)n_heads), FW_ROWS * NSPLIT * 32, smem, st>>>(maps, g, partials);
     CY_CHECK_LAUNCH("iic_joint_mma");
     return CY_OK;
 }
 
 }  // namespace
 
-// returns CY_ERR_UNSUPPORTED when the shape is not eligible (the caller then takes the CUDA-core kernels)
-int iic_joint_mma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, float* partials, int* n_partials,
-                  cudaStream_t st) {
+// returns CY_ERR_UNSUPPORTED when the shape is not eligible (the caller then takes the CUDA-core kernels).
+// n_heads (x, y) pairs of one shape in one launch: partials is [n_heads][*n_partials][nj].
+int iic_joint_mma_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
+                        float* partials, int* n_partials, cudaStream_t st) {
     MmaGeom g; int mt, ntw, nsplit; size_t smem;
-    if (dtype != CY_F32 || !aligned16(x) || !aligned16(y) || !fwd_geom(B, K, H, W, pad, &g, &mt, &ntw, &nsplit, &smem))
+    if (dtype != CY_F32 || n_heads < 1 || n_heads > MMA_MAXHEADS || !fwd_geom(B, K, H, W, pad, &g, &mt, &ntw, &nsplit, &smem))
         return CY_ERR_UNSUPPORTED;
+    for (int s = 0; s < n_heads; ++s)
+        if (!aligned16(xs[s]) || !aligned16(ys[s])) return CY_ERR_UNSUPPORTED;
     g.debug_skip = debug_skip();
-    CUtensorMap tmx, tmy;
-    int rc = make_map3d(&tmx, x, B, K, H, W, g.XW, g.HH);
-    if (rc) return rc;
-    rc = make_map3d(&tmy, y, B, K, H, W, g.YW, g.BH);
-    if (rc) return rc;
-    const int cap = sm_count_mma() * (nsplit == 1 ? 2 : 1);
+    JointMaps maps;
+    for (int s = 0; s < MMA_MAXHEADS; ++s) {
+        if (s >= n_heads) { maps.x[s] = maps.x[0]; maps.y[s] = maps.y[0]; continue; }
+        int rc = make_map3d(&maps.x[s], xs[s], B, K, H, W, g.XW, g.HH);
+        if (rc) return rc;
+        rc = make_map3d(&maps.y[s], ys[s], B, K, H, W, g.YW, g.BH);
+        if (rc) return rc;
+    }
+    int cap = sm_count_mma() * (nsplit == 1 ? 2 : 1) / n_heads;       // resident CTAs shared evenly by the heads
+    if (cap < 1) cap = 1;
     const int grid = g.n_tiles < cap ? g.n_tiles : cap;
     *n_partials = grid;
 #define CY_JM(MTV, NTWV, NSV)                                                                                     \
     if (mt == MTV && ntw == NTWV && nsplit == NSV) {                                                              \
-        if (g.TW == 32) return launch_joint_mma<MTV, NTWV, NSV, 2>(tmx, tmy, g, smem, grid, partials, st);       \
-        if (g.TW == 64) return launch_joint_mma<MTV, NTWV, NSV, 4>(tmx, tmy, g, smem, grid, partials, st);       \
+        if (g.TW == 32) return launch_joint_mma<MTV, NTWV, NSV, 2>(maps, n_heads, g, smem, grid, partials, st);  \
+        if (g.TW == 64) return launch_joint_mma<MTV, NTWV, NSV, 4>(maps, n_heads, g, smem, grid, partials, st);  \
     }
     CY_JM(1, 1, 1) CY_JM(1, 2, 1) CY_JM(2, 3, 1) CY_JM(2, 4, 1) CY_JM(3, 3, 2) CY_JM(4, 4, 2)
 #undef CY_JM
     return CY_ERR_UNSUPPORTED;
+}
+
+int iic_joint_mma(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, float* partials, int* n_partials,
+                  cudaStream_t st) {
+    return iic_joint_mma_heads(&x, &y, 1, dtype, B, K, H, W, pad, partials, n_partials, st);
 }
 
 int iic_joint_mma_max_partials() { return 2 * sm_count_mma(); }

@@ -11,6 +11,7 @@ normalisation / entropy epilogue together with its analytic derivative (cy_iic_e
 adjoint to produce both input gradients (cy_iic_bwd).
 """
 import math
+import ctypes
 import sys
 
 import torch
@@ -187,8 +188,9 @@ class _IIDSegMultiFunction(torch.autograd.Function):
 
     The hooks evaluate ``sum(criterion(x1, x2) for x1, x2 in zip(prob1, prob2)) / len(prob1)`` over the sub-heads of a
     cluster head (semi_seg/hooks/discretemi.py:111, ccblock.py:208-218): S python-level criterion calls, S autograd nodes
-    and ~8 small allocations each.  Here the S joints / epilogues / adjoints are enqueued back to back from one node
-    with one output buffer; the adjoint kernels get the head's share 1/S of the upstream gradient through ``gscale``."""
+    and ~8 small allocations each.  Here the S joints, the S epilogues and the S adjoints are ONE launch each (plus the joint's
+    reduction): cy_iic_joint_heads / cy_iic_epilogue_heads / cy_iic_bwd_heads, with one output buffer; the adjoint gets the
+    head's share 1/S of the upstream gradient through ``gscale``."""
 
     @staticmethod
     def forward(ctx, padding, symmetric, lamda, eps, *maps):
@@ -205,19 +207,20 @@ class _IIDSegMultiFunction(torch.autograd.Function):
         joints = torch.empty(S, nj, dtype=torch.float64, device=x0.device)      # raw joints stay in double (contrastyou_b200.h)
         st = L.stream_ptr(x0.device)
         ws_bytes = lib.cy_iic_workspace_bytes(B, K, H, W, padding)
-        ws = _workspace(ws_bytes, x0.device, st)
         ews_bytes = lib.cy_iic_epilogue_workspace_bytes(K, padding)
         ews = torch.empty(ews_bytes, dtype=torch.uint8, device=x0.device) if ews_bytes else None
         dt = L.dtype_code(x0)
         base = buf.data_ptr()
-        for s in range(S):
-            x, y = maps[2 * s], maps[2 * s + 1]
-            o = base + s * per * 4
-            loss_p, p00_p, dj_p, j_p = o, o + 4, o + 4 * (1 + K * K), joints.data_ptr() + 8 * s * nj
-            L.check(lib.cy_iic_joint(x.data_ptr(), y.data_ptr(), dt, B, K, H, W, padding, j_p, ws.data_ptr(), ws_bytes, st),
-                    "cy_iic_joint")
-            L.check(lib.cy_iic_epilogue(j_p, 1, K, padding, int(bool(symmetric)), float(lamda), float(eps), float(B * H * W),
-                                        loss_p, p00_p, None, dj_p, L.ptr(ews), ews_bytes, st), "cy_iic_epilogue")
+        # one joint launch (+ its reduction), one epilogue launch (a CTA per head); cy_iic_*_heads fall back to head-by-head
+        # launches inside the library for shapes the tensor-core kernels do not take
+        xs = (ctypes.c_void_p * S)(*[maps[2 * s].data_ptr() for s in range(S)])
+        ys = (ctypes.c_void_p * S)(*[maps[2 * s + 1].data_ptr() for s in range(S)])
+        ws = _workspace(S * ws_bytes, x0.device, st)
+        L.check(lib.cy_iic_joint_heads(xs, ys, S, dt, B, K, H, W, padding, joints.data_ptr(), nj, ws.data_ptr(), S * ws_bytes, st),
+                "cy_iic_joint_heads")
+        L.check(lib.cy_iic_epilogue_heads(joints.data_ptr(), nj, S, 1, K, padding, int(bool(symmetric)), float(lamda), float(eps),
+                                          float(B * H * W), base, base + 4, base + 4 * (1 + K * K), per, L.ptr(ews), ews_bytes, st),
+                "cy_iic_epilogue_heads")
         ctx.save_for_backward(buf, *maps)
         ctx.cfg = (padding, S, K, T, per)
         p00 = buf[0, 1:1 + K * K].view(K, K)
@@ -235,14 +238,13 @@ class _IIDSegMultiFunction(torch.autograd.Function):
         gscale = (grad_loss.detach().to(torch.float32) / S).reshape(1).contiguous()
         st = L.stream_ptr(buf.device)
         dt = L.dtype_code(maps[0])
-        grads = []
-        for s in range(S):
-            x, y = maps[2 * s], maps[2 * s + 1]
-            dx, dy = torch.empty_like(x), torch.empty_like(y)
-            dj_p = buf.data_ptr() + (s * per + 1 + K * K) * 4
-            L.check(lib.cy_iic_bwd(x.data_ptr(), y.data_ptr(), dt, B, K, H, W, padding, dj_p, gscale.data_ptr(), dx.data_ptr(),
-                                   dy.data_ptr(), st), "cy_iic_bwd")
-            grads += [dx, dy]
+        grads = [torch.empty_like(m) for m in maps]
+        xs = (ctypes.c_void_p * S)(*[maps[2 * s].data_ptr() for s in range(S)])
+        ys = (ctypes.c_void_p * S)(*[maps[2 * s + 1].data_ptr() for s in range(S)])
+        dxs = (ctypes.c_void_p * S)(*[grads[2 * s].data_ptr() for s in range(S)])
+        dys = (ctypes.c_void_p * S)(*[grads[2 * s + 1].data_ptr() for s in range(S)])
+        L.check(lib.cy_iic_bwd_heads(xs, ys, S, dt, B, K, H, W, padding, buf.data_ptr() + (1 + K * K) * 4, per, gscale.data_ptr(),
+                                     dxs, dys, st), "cy_iic_bwd_heads")
         return (None, None, None, None, *grads)
 
 

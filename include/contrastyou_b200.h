@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CY_ABI_VERSION 3
+#define CY_ABI_VERSION 4
 
 /* element types of embeddings / probability maps */
 #define CY_F32 0
@@ -218,6 +218,23 @@ int cy_iic_epilogue(const double* joint, int n_slots, int K, int pad, int symmet
 /* Backward: dx, dy [B,K,H,W] (dtype of x) = gscale[0] * adjoint of cy_iic_joint applied to djoint. */
 int cy_iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
                const float* gscale, void* dx, void* dy, void* stream);
+
+/* Sub-head stack.  The hooks evaluate the criterion once per sub-head pair of a cluster head and
+ * average (semi_seg/hooks/discretemi.py:111, contrastyou/arch/unet.py cluster heads): n_heads independent problems of ONE
+ * shape.  These three calls take the heads together: xs / ys / dxs / dys are HOST arrays of n_heads device pointers
+ * ([B,K,H,W] each); head s uses joint + s*joint_stride (doubles, [n_slots][K,K,T,T] inside), loss / p00 / djoint + s*out_stride
+ * (floats) and djoint + s*djoint_stride.  One joint launch + one reduction launch, one epilogue launch (a CTA per head) and one
+ * adjoint launch when the tensor-core kernels take the shape (heads in chunks of 8); otherwise they run head by head through
+ * the single-head entry points — results are identical to n_heads single-head calls either way.
+ * Workspace of cy_iic_joint_heads: n_heads * cy_iic_workspace_bytes().  cy_iic_epilogue_heads has no p_ij output. */
+int cy_iic_joint_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
+                       double* joint, long long joint_stride, void* workspace, size_t workspace_bytes, void* stream);
+int cy_iic_epilogue_heads(const double* joint, long long joint_stride, int n_heads, int n_slots, int K, int pad, int symmetric,
+                          float lamda, float eps, double n_pixels, float* loss, float* p00, float* djoint, long long out_stride,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int cy_iic_bwd_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
+                     const float* djoint, long long djoint_stride, const float* gscale, void* const* dxs, void* const* dys,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * IMSAT entropies.  Replaces imsat_loss / the marginal + conditional entropy pair of

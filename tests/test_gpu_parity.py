@@ -711,6 +711,64 @@ def test_iic_tcgen05_adjoint_shapes(B, K, H, W):
     assert _relerr(dy.cpu().numpy(), gy) <= 3e-5
 
 
+def _ptr_array(ts):
+    import ctypes
+    return (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+
+@pytest.mark.parametrize("S,B,K,H,W,pad", [(2, 2, 10, 32, 32, 1), (3, 1, 10, 64, 228, 1), (8, 1, 5, 9, 16, 1), (11, 1, 4, 6, 8, 1),
+                                            (4, 1, 16, 12, 24, 1), (7, 1, 15, 12, 24, 1), (3, 2, 6, 8, 16, 0), (2, 1, 10, 10, 10, 1)])
+def test_iic_heads_entry_points_equal_single_head_calls(S, B, K, H, W, pad):
+    """cy_iic_joint_heads / cy_iic_epilogue_heads / cy_iic_bwd_heads (one launch over the sub-head stack) vs S
+    single-head calls: the joints to fp32 summation-order noise (the heads share the resident CTAs, so each head's partial
+    sums are grouped differently), the epilogue and the adjoint BIT-EXACT on the same inputs.  Covers > 8 heads (chunks),
+    K = 16 / 15 (weight tiles of 7 heads do not fit beside the staging ring at K = 15: library-side head loop), padding 0 and
+    W % 4 != 0 (shapes the tensor-core kernels do not take)."""
+    lib = L.lib()
+    torch.manual_seed(S * 100 + K)
+    T = 2 * pad + 1
+    nj = K * K * T * T
+    xs = [(2 * torch.randn(B, K, H, W, device=DEV)).softmax(1) for _ in range(S)]
+    ys = [(2 * torch.randn(B, K, H, W, device=DEV)).softmax(1) for _ in range(S)]
+    st = L.stream_ptr()
+    wsb = lib.cy_iic_workspace_bytes(B, K, H, W, pad)
+    ws = torch.empty(max(S * wsb, 1), dtype=torch.uint8, device=DEV)
+    joints = torch.zeros(S, nj + 3, dtype=torch.float64, device=DEV)          # stride != nj on purpose
+    L.check(lib.cy_iic_joint_heads(_ptr_array(xs), _ptr_array(ys), S, 0, B, K, H, W, pad, joints.data_ptr(), nj + 3, ws.data_ptr(),
+                                   S * wsb, st), "cy_iic_joint_heads")
+    single = torch.empty(S, nj, dtype=torch.float64, device=DEV)
+    for s in range(S):
+        L.check(lib.cy_iic_joint(xs[s].data_ptr(), ys[s].data_ptr(), 0, B, K, H, W, pad, single[s].data_ptr(), ws.data_ptr(), wsb, st),
+                "cy_iic_joint")
+    assert torch.all(joints[:, nj:] == 0)
+    assert _relerr(joints[:, :nj].cpu().numpy(), single.cpu().numpy()) <= 2e-6
+    # epilogue: same joints in, bit-identical loss / p00 / dL/dJ out
+    per = 1 + K * K + nj + 5
+    out = torch.zeros(S, per, device=DEV)
+    ewb = lib.cy_iic_epilogue_workspace_bytes(K, pad)
+    ews = torch.empty(max(ewb, 1), dtype=torch.uint8, device=DEV)
+    base = out.data_ptr()
+    L.check(lib.cy_iic_epilogue_heads(single.data_ptr(), nj, S, 1, K, pad, 1, 1.5, 1e-5, float(B * H * W), base, base + 4,
+                                      base + 4 * (1 + K * K), per, ews.data_ptr(), ewb, st), "cy_iic_epilogue_heads")
+    ref = torch.zeros(S, per, device=DEV)
+    for s in range(S):
+        b = ref[s].data_ptr()
+        L.check(lib.cy_iic_epilogue(single[s].data_ptr(), 1, K, pad, 1, 1.5, 1e-5, float(B * H * W), b, b + 4, None, b + 4 * (1 + K * K),
+                                    ews.data_ptr(), ewb, st), "cy_iic_epilogue")
+    assert torch.equal(out, ref)
+    # adjoint
+    dj = torch.randn(S, nj + 7, device=DEV)
+    g = torch.full((1,), 0.37, device=DEV)
+    dxs, dys = [torch.empty_like(t) for t in xs], [torch.empty_like(t) for t in ys]
+    L.check(lib.cy_iic_bwd_heads(_ptr_array(xs), _ptr_array(ys), S, 0, B, K, H, W, pad, dj.data_ptr(), nj + 7, g.data_ptr(),
+                                 _ptr_array(dxs), _ptr_array(dys), st), "cy_iic_bwd_heads")
+    for s in range(S):
+        dx, dy = torch.empty_like(xs[s]), torch.empty_like(ys[s])
+        L.check(lib.cy_iic_bwd(xs[s].data_ptr(), ys[s].data_ptr(), 0, B, K, H, W, pad, dj[s].data_ptr(), g.data_ptr(), dx.data_ptr(),
+                               dy.data_ptr(), st), "cy_iic_bwd")
+        assert torch.equal(dxs[s], dx) and torch.equal(dys[s], dy), s
+
+
 def test_iic_mma_sync_adjoint_still_agrees():
     """CY_IIC_TC=0 pins the round-1 mma.sync adjoint (csrc/iic_mma.cu), kept for A/B timing: it must return what the tcgen05
     adjoint returns (the switch is read once per process, hence the subprocess)"""

@@ -96,3 +96,34 @@ def test_row_ring_has_no_deadlock_and_no_early_read(cfg):
     for segs in SEGMENTS:
         for seed in range(60):
             assert _run(segs, seed, **cfg) is None, (segs, seed, cfg)
+
+
+def _converter_rows(segs, cset, NCS=4):
+    """the converter cursor of csrc/iic_bwd_tc.cu (enter / step) restated: global input-row indices set ``cset`` writes"""
+    out, ar0, k = [], 0, 0
+    while k < len(segs):
+        n_in = segs[k] + 2
+        j = (cset + NCS - ar0 % NCS) % NCS
+        while j < n_in:
+            out.append(ar0 + j)
+            j += NCS
+        ar0 += n_in
+        k += 1
+    return out
+
+
+def test_converter_sets_cover_every_input_row_exactly_once():
+    """a one-row segment has 3 input rows, fewer than the 4 converter sets: the set without a row there must move on to the next
+    segment instead of writing one (it would arrive twice on the A slot of the next segment's first row — the hang that
+    [3,5,17,228] exposed).  Every global input row belongs to exactly one set, and a set's rows are 4 apart."""
+    import random
+    rng = random.Random(7)
+    for _ in range(300):
+        segs = [rng.choice([1, 1, 2, 3, 5, 17]) for _ in range(rng.randint(1, 6))]
+        total = sum(n + 2 for n in segs)
+        seen = []
+        for cset in range(4):
+            rows = _converter_rows(segs, cset)
+            assert all(r % 4 == cset for r in rows), (segs, cset, rows)
+            seen += rows
+        assert sorted(seen) == list(range(total)), segs
