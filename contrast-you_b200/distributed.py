@@ -125,6 +125,9 @@ class PeerExchange:
         # label block currently holds (ShardedSupConLoss skips re-sending unchanged labels)
         self.buf[2 * self.half_bytes:].zero_()
         self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.counter_ptr = self.counter.data_ptr()
+        self.dev_index = self.buf.device.index
+        self.stream_of = torch._C._cuda_getCurrentRawStream
         self.epoch = 0
         self.labels_token = [None, None]
         self.hdl.barrier(channel=0)
@@ -144,17 +147,19 @@ class PeerExchange:
         epoch to every peer and waits for theirs): on return (in stream order) every rank's ranges are visible here.  An empty
         range list is a plain barrier."""
         import ctypes
-        lib = L.lib()
         flat = []
         for off, nb in ranges:
             assert off % 16 == 0 and nb % 16 == 0, (off, nb)
             flat += [off, nb]
         if not flat:
             flat = [0, 0]
-        arr = (ctypes.c_ulonglong * len(flat))(*flat)
+        self.push_ranges((ctypes.c_ulonglong * len(flat))(*flat), len(flat) // 2)
+
+    def push_ranges(self, arr, n_ranges: int):
+        """``push`` with the (offset, bytes) pairs already in a ctypes array (callers that push the same ranges every step)"""
         self.epoch += 1
-        L.check(lib.cy_p2p_push_barrier(self.ptrs_dev, self.world, self.rank, arr, len(flat) // 2, 2 * self.half_bytes,
-                                        self.counter.data_ptr(), self.epoch & 0xffffffff, L.stream_ptr(self.buf.device)),
+        L.check(L.lib().cy_p2p_push_barrier(self.ptrs_dev, self.world, self.rank, arr, n_ranges, 2 * self.half_bytes,
+                                            self.counter_ptr, self.epoch & 0xffffffff, self.stream_of(self.dev_index)),
                 "cy_p2p_push_barrier")
 
 
@@ -167,12 +172,9 @@ def make_joint_reduce(group=None, exchange: str = "auto"):
     slot of a peer-mapped [world, K,K,T,T] array, pushes the slot to all peers (cy_p2p_push + signal-pad barrier) and
     cy_iic_epilogue sums the slots in rank order — identical bits on every rank, no NCCL call.  "nccl": all-reduce in place."""
     world, rank = _ws(group)
-    state = {"px": None, "failed": exchange == "nccl"}
+    state = {"px": None, "failed": exchange == "nccl", "plans": {}}
 
     def reduce(compute_into, shape, n_pixels: float, device):
-        nj = 1
-        for v in shape:
-            nj *= v
         # (a captured graph would replay ONE half of the alternating buffer every step: captures take the collective form)
         if not state["failed"] and world > 1 and not torch.cuda.is_current_stream_capturing():
             try:
@@ -181,14 +183,38 @@ def make_joint_reduce(group=None, exchange: str = "auto"):
                         raise RuntimeError("torch.distributed._symmetric_memory is not available")
                     state["px"] = PeerExchange(group)
                 px = state["px"]
-                slot_bytes = (nj * 8 + 15) // 16 * 16
-                view, base = px.acquire(world * slot_bytes, device)
-                slots = view[:world * slot_bytes].view(torch.float64).view(world, slot_bytes // 8)
-                compute_into(slots[rank, :nj].view(shape))
-                px.push([(base + rank * slot_bytes, slot_bytes)])
-                if slot_bytes == nj * 8:
-                    return slots.view(world, *shape), world, n_pixels * world
-                return slots[:, :nj].contiguous().view(world, *shape), world, n_pixels * world
+                shape = tuple(shape)
+                plan = state["plans"].get(shape)
+                if plan is None or plan[2] is not px.buf:
+                    # per shape, once: the tensor views of both halves and the push ranges (the step is host-bound at the bench
+                    # size — ~10 view / slice calls and a ctypes array per step were a fifth of its enqueue time)
+                    import ctypes
+                    nj = 1
+                    for v in shape:
+                        nj *= v
+                    slot_bytes = (nj * 8 + 15) // 16 * 16
+                    need = world * slot_bytes
+                    if px.buf is None or need > px.half_bytes:
+                        px._grow(need, device)
+                        state["plans"].clear()
+                    halves = []
+                    for half in (0, 1):
+                        base = half * px.half_bytes
+                        slots = px.buf[base:base + need].view(torch.float64).view(world, slot_bytes // 8)
+                        mine = slots[rank, :nj].view(shape)
+                        whole = slots.view(world, *shape) if slot_bytes == nj * 8 else None
+                        arr = (ctypes.c_ulonglong * 2)(base + rank * slot_bytes, slot_bytes)
+                        halves.append((slots, mine, whole, arr))
+                    plan = (halves, nj, px.buf)
+                    state["plans"][shape] = plan
+                px.half = px.step & 1
+                px.step += 1
+                slots, mine, whole, arr = plan[0][px.half]
+                compute_into(mine)
+                px.push_ranges(arr, 1)
+                if whole is not None:
+                    return whole, world, n_pixels * world
+                return slots[:, :plan[1]].contiguous().view(world, *shape), world, n_pixels * world
             except Exception as e:  # noqa  (rendezvous refused on this box: fall back for good, every rank alike)
                 if exchange == "p2p":
                     raise

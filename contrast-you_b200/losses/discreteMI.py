@@ -56,6 +56,18 @@ def _workspace(nbytes: int, device, stream: int):
     return ws
 
 
+_SIZES = {}
+
+
+def _sizes(lib, B, K, H, W, padding):
+    """(partial-joint workspace bytes, epilogue workspace bytes) of a shape — asked once per shape, not once per step"""
+    key = (B, K, H, W, padding)
+    v = _SIZES.get(key)
+    if v is None:
+        v = _SIZES[key] = (lib.cy_iic_workspace_bytes(B, K, H, W, padding), lib.cy_iic_epilogue_workspace_bytes(K, padding))
+    return v
+
+
 def _joint_forward(x, y, padding, joint=None):
     lib = L.lib()
     B, K, H, W = x.shape
@@ -64,7 +76,7 @@ def _joint_forward(x, y, padding, joint=None):
         if joint is None:      # double: see include/contrastyou_b200.h (the epilogue's min-shift amplifies a float32 rounding of J)
             joint = torch.empty(K, K, T, T, dtype=torch.float64, device=x.device)
         st = L.stream_ptr(x.device)
-        ws_bytes = lib.cy_iic_workspace_bytes(B, K, H, W, padding)
+        ws_bytes = _sizes(lib, B, K, H, W, padding)[0]
         ws = _workspace(ws_bytes, x.device, st)
         L.check(lib.cy_iic_joint(x.data_ptr(), y.data_ptr(), L.dtype_code(x), B, K, H, W, padding, joint.data_ptr(),
                                  ws.data_ptr(), ws_bytes, st), "cy_iic_joint")
@@ -149,9 +161,12 @@ class _IIDSegFunction(torch.autograd.Function):
         B, K, H, W = x.shape
         T = 2 * padding + 1
         nj = K * K * T * T
-        buf = torch.empty(1 + K * K + nj, dtype=torch.float32, device=x.device)      # one allocation for the small outputs
-        loss, p00 = buf[:1], buf[1:1 + K * K].view(K, K)
-        djoint = buf[1 + K * K:].view(K, K, T, T)
+        # the returned loss must not share storage (and hence a version counter) with the saved dL/dJ: callers scale losses in
+        # place (`loss *= w`), which would otherwise invalidate the backward — so it is its own allocation (no clone kernel)
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        buf = torch.empty(K * K + nj, dtype=torch.float32, device=x.device)
+        p00 = buf[:K * K].view(K, K)
+        djoint = buf[K * K:].view(K, K, T, T)
         n_pixels = float(B * H * W)
         n_slots = 1
         if reduce_joint is None:
@@ -161,7 +176,7 @@ class _IIDSegFunction(torch.autograd.Function):
             # visible — an NCCL all-reduce in place (1 slot) or peer-memory stores into per-rank slots that the epilogue sums
             joint, n_slots, n_pixels = reduce_joint(lambda out: _joint_forward(x, y, padding, out), (K, K, T, T), n_pixels, x.device)
         with L.guard(x):
-            ws_bytes = lib.cy_iic_epilogue_workspace_bytes(K, padding)
+            ws_bytes = _sizes(lib, B, K, H, W, padding)[1]
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
             L.check(lib.cy_iic_epilogue(joint.data_ptr(), n_slots, K, padding, int(bool(symmetric)), float(lamda), float(eps),
                                         n_pixels, loss.data_ptr(), p00.data_ptr(), None, djoint.data_ptr(), L.ptr(ws), ws_bytes,
@@ -169,9 +184,7 @@ class _IIDSegFunction(torch.autograd.Function):
         ctx.save_for_backward(x, y, djoint)
         ctx.padding = padding
         ctx.mark_non_differentiable(p00)
-        # the returned loss must not share storage (and hence a version counter) with the saved dL/dJ: callers scale losses
-        # in place (`loss *= w`), which would otherwise invalidate the backward
-        return loss.reshape(()).clone(), p00
+        return loss, p00
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_p00):
@@ -268,7 +281,7 @@ class IIDSegmentationLoss(nn.Module):
         x, y = _check_pair(x_out, x_tf_out)
         loss, p00 = _IIDSegFunction.apply(x, y, int(self.padding), bool(self.symmetric), float(self.lamda), float(self._eps),
                                           self._reduce_joint)
-        self._p_i_j = p00
+        self.__dict__["_p_i_j"] = p00      # (plain attribute; Module.__setattr__ costs ~5 us of type checks per step)
         return loss
 
     def forward_heads(self, x_outs, x_tf_outs) -> Tensor:
@@ -285,7 +298,7 @@ class IIDSegmentationLoss(nn.Module):
         if self._reduce_joint is not None:      # sharded batches need the joint all-reduce between the two kernels
             return sum(self(x, y) for x, y in zip(x_outs, x_tf_outs)) / len(x_outs)
         loss, p00 = _IIDSegMultiFunction.apply(int(self.padding), bool(self.symmetric), float(self.lamda), float(self._eps), *maps)
-        self._p_i_j = p00
+        self.__dict__["_p_i_j"] = p00      # (plain attribute; Module.__setattr__ costs ~5 us of type checks per step)
         return loss
 
     def get_joint_matrix(self):
