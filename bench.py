@@ -646,6 +646,35 @@ def main():
             "gpu_launches": int(iic_launches), "parity": iic_parity,
         }
 
+        # ---- sub-head stack: the hooks' python sum over S sub-head pairs vs forward_heads (one joint, one
+        # reduction, one epilogue and one adjoint launch for all heads), at a cluster-head shape and at the cfg3 map size
+        if world == 1:
+            heads = {}
+            for tag, (S_, Bh, Hh, Wh) in (("5 heads x 8x10x64x64", (5, 8, 64, 64)), ("3 heads x 16x10x224x224", (3, 16, 224, 224))):
+                gh = torch.Generator(device=dev).manual_seed(5)
+                hx = [(2 * torch.randn(Bh, Kc, Hh, Wh, device=dev, generator=gh)).softmax(1) for _ in range(S_)]
+                hy = [(2 * torch.randn(Bh, Kc, Hh, Wh, device=dev, generator=gh)).softmax(1) for _ in range(S_)]
+                crit_h = IIDSegmentationLoss(padding=pad)
+
+                def loop_step():
+                    xs = [t.detach().requires_grad_() for t in hx]; ys = [t.detach().requires_grad_() for t in hy]
+                    l_ = sum(crit_h(a, b) for a, b in zip(xs, ys)) / S_
+                    l_.backward()
+                    return l_
+
+                def heads_step():
+                    xs = [t.detach().requires_grad_() for t in hx]; ys = [t.detach().requires_grad_() for t in hy]
+                    l_ = crit_h.forward_heads(xs, ys)
+                    l_.backward()
+                    return l_
+                loop_ms = timed_loop(loop_step, W_, K_) / K_
+                loop_launches = counted["launches"] // K_
+                heads_ms = timed_loop(heads_step, W_, K_) / K_
+                heads[tag] = {"python_loop_ms": loop_ms, "forward_heads_ms": heads_ms, "launches_per_step": [loop_launches,
+                              counted["launches"] // K_], "loss_rel": abs(float(heads_step()) - float(loop_step())) / abs(float(loop_step()))}
+                del hx, hy
+            line["iic"]["sub_heads"] = heads
+
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"], _ = cpu_supcon_baseline(steps=3, warmup=1)
         if "iic" in line:
