@@ -87,7 +87,7 @@ int iic_joint_heads(const void* const*, const void* const*, int, int, int, int, 
 int iic_epilogue_heads(const double*, long long, int, int, int, int, int, float, float, double, float*, float*, float*, long long, void*,
                        size_t, cudaStream_t);
 int iic_bwd_heads(const void* const*, const void* const*, int, int, int, int, int, int, int, const float*, long long, const float*,
-                  void* const*, void* const*, cudaStream_t);
+                  void* const*, void* const*, float, cudaStream_t);
 
 static int check_infonce_args(const void* z, int dtype, int64_t N, int64_t d, int64_t ldz, const int32_t* labels,
                               const uint8_t* codes, int64_t row_begin, int64_t row_end, int variant) {
@@ -380,7 +380,22 @@ int cy_iic_bwd_heads(const void* const* xs, const void* const* ys, int n_heads, 
         if (rc) return rc;
         CY_CHECK_ARG(dxs[s] && dys[s], "null pointer");
     }
-    return iic_bwd_heads(xs, ys, n_heads, dtype, B, K, H, W, pad, djoint, djoint_stride, gscale, dxs, dys,
+    return iic_bwd_heads(xs, ys, n_heads, dtype, B, K, H, W, pad, djoint, djoint_stride, gscale, dxs, dys, 0.f,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_iic_bwd_logits_heads(const void* const* pxs, const void* const* pys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
+                            const float* djoint, long long djoint_stride, const float* gscale, float T, void* const* dlxs,
+                            void* const* dlys, void* stream) {
+    CY_NVTX("cy_iic_bwd_logits_heads");
+    CY_CHECK_ARG(pxs && pys && dlxs && dlys && n_heads >= 1 && djoint && gscale, "bad arguments");
+    CY_CHECK_ARG(T > 0.f && isfinite(T), "temperature %g", (double)T);
+    for (int s = 0; s < n_heads; ++s) {
+        const int rc = check_iic(pxs[s], pys[s], dtype, B, K, H, W, pad);
+        if (rc) return rc;
+        CY_CHECK_ARG(dlxs[s] && dlys[s] && dlxs[s] != pxs[s] && dlys[s] != pys[s], "null or aliased gradient pointer");
+    }
+    return iic_bwd_heads(pxs, pys, n_heads, dtype, B, K, H, W, pad, djoint, djoint_stride, gscale, dlxs, dlys, 1.0f / T,
                          reinterpret_cast<cudaStream_t>(stream));
 }
 

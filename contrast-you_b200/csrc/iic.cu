@@ -125,16 +125,21 @@ iic_joint_kernel(const void* __restrict__ x, const void* __restrict__ y, int dty
         }
     }
     __syncthreads();
-    if (active) {
-        const int dy = rr / K, k1 = rr % K;
+    // per-CTA sum over the row slots in slot order (plain read-modify-writes, one slot per barrier round): bitwise reproducible,
+    // unlike shared-memory atomics — the padding-0 loss is a 1e-3 residual of O(1) terms and shows one ulp of a partial joint
+    for (int sv = 0; sv < nslot; ++sv) {
+        if (active && slot == sv) {
+            const int dy = rr / K, k1 = rr % K;
 #pragma unroll
-        for (int kk = 0; kk < KC; ++kk) {
-            const int k2 = k2base + kk;
-            if (k2 < K) {
+            for (int kk = 0; kk < KC; ++kk) {
+                const int k2 = k2base + kk;
+                if (k2 < K) {
 #pragma unroll
-                for (int dx = 0; dx < T; ++dx) atomicAdd(&jsm[((k1 * K + k2) * T + dy) * T + dx], acc[dx][kk]);
+                    for (int dx = 0; dx < T; ++dx) jsm[((k1 * K + k2) * T + dy) * T + dx] += acc[dx][kk];
+                }
             }
         }
+        __syncthreads();
     }
     __syncthreads();
     for (int i = tid; i < nj; i += IIC_NT) partials[(size_t)blockIdx.x * nj + i] = jsm[i];
@@ -617,7 +622,7 @@ int iic_joint_mma_heads(const void* const* xs, const void* const* ys, int n_head
                         float* partials, int* n_partials, cudaStream_t st);
 int iic_bwd_tc_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
                      const float* djoint, long long dj_stride, const float* gscale, void* const* dxs, void* const* dys,
-                     cudaStream_t st);
+                     float softmax_inv_T, cudaStream_t st);
 int iic_bwd_tc(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
                const float* gscale, void* dx, void* dy, cudaStream_t st);
 
@@ -883,22 +888,53 @@ int iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W,
     return CY_OK;
 }
 
-// n_heads adjoints of one shape: ONE tcgen05 launch per chunk of 8 heads when the shape is eligible, head by head otherwise
+// in place: g <- p * (g - sum_k p_k g_k) * inv_T per pixel  (the backward of p = softmax(logits / T) over the K planes);
+// one thread per pixel of both maps, coalesced along W.  The fused form lives in the tcgen05 adjoint's epilogue; this is the
+// route of the shapes that kernel does not take.
+__global__ void __launch_bounds__(256)
+iic_softmax_bwd_kernel(const void* __restrict__ px, const void* __restrict__ py, void* __restrict__ gx, void* __restrict__ gy, int dtype,
+                       int K, long long plane, long long n_pix, float inv_T) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * n_pix; idx += (long long)gridDim.x * blockDim.x) {
+        const bool second = idx >= n_pix;
+        const long long t = second ? idx - n_pix : idx;
+        const void* p = second ? py : px;
+        void* g = second ? gy : gx;
+        const size_t base = (size_t)(t / plane) * K * plane + (size_t)(t % plane);
+        float dot = 0.f;
+        for (int k = 0; k < K; ++k) dot = fmaf(ld_as_float(p, dtype, base + (size_t)k * plane), ld_as_float(g, dtype, base + (size_t)k * plane), dot);
+        for (int k = 0; k < K; ++k) {
+            const size_t e = base + (size_t)k * plane;
+            st_from_float(g, dtype, e, ld_as_float(p, dtype, e) * (ld_as_float(g, dtype, e) - dot) * inv_T);
+        }
+    }
+}
+
+// n_heads adjoints of one shape: ONE tcgen05 launch per chunk of 8 heads when the shape is eligible, head by head otherwise.
+// softmax_inv_T != 0: xs / ys are softmax(logits / T) over the K planes and dxs / dys receive dL/dlogits (softmax backward fused
+// into the adjoint's epilogue, or applied in place behind the other adjoint kernels).
 int iic_bwd_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
-                  const float* djoint, long long dj_stride, const float* gscale, void* const* dxs, void* const* dys, cudaStream_t st) {
+                  const float* djoint, long long dj_stride, const float* gscale, void* const* dxs, void* const* dys, float softmax_inv_T,
+                  cudaStream_t st) {
     CY_CHECK_ARG(n_heads >= 1, "iic_bwd_heads: n_heads=%d", n_heads);
     for (int s0 = 0; s0 < n_heads;) {
         const int n = n_heads - s0 < 8 ? n_heads - s0 : 8;
         int rc = CY_ERR_UNSUPPORTED;
-        if (n > 1 && mma_enabled() && tc_enabled()) {
+        if ((n > 1 || softmax_inv_T != 0.f) && mma_enabled() && tc_enabled()) {
             rc = iic_bwd_tc_heads(xs + s0, ys + s0, n, dtype, B, K, H, W, pad, djoint + (size_t)s0 * dj_stride, dj_stride, gscale,
-                                  dxs + s0, dys + s0, st);
+                                  dxs + s0, dys + s0, softmax_inv_T, st);
             if (rc != CY_OK && rc != CY_ERR_UNSUPPORTED) return rc;
         }
         if (rc != CY_OK)
             for (int s = s0; s < s0 + n; ++s) {
                 rc = iic_bwd(xs[s], ys[s], dtype, B, K, H, W, pad, djoint + (size_t)s * dj_stride, gscale, dxs[s], dys[s], st);
                 if (rc != CY_OK) return rc;
+                if (softmax_inv_T != 0.f) {
+                    const long long plane = (long long)H * W, n_pix = (long long)B * plane;
+                    const long long want = (2 * n_pix + 255) / 256;
+                    const int grid = (int)(want < 8LL * sm_count_cached() ? want : 8LL * sm_count_cached());
+                    iic_softmax_bwd_kernel<<<grid, 256, 0, st>>>(xs[s], ys[s], dxs[s], dys[s], dtype, K, plane, n_pix, softmax_inv_T);
+                    CY_CHECK_LAUNCH("iic_softmax_bwd");
+                }
             }
         s0 += n;
     }

@@ -96,6 +96,7 @@ struct TcGeom {
     int TW2;                                     // strips per image row
     int rows_total;                              // S * 2 * B * TW2 * H
     long long dj_stride;                         // floats between the heads' dL/dJ tables
+    float inv_T;                                 // != 0: the maps are softmax(logits / T) and the outputs are dL/dlogits (fused softmax backward)
 };
 struct TcPtrs {                                  // per head: the two maps and the two gradient outputs
     const float* x[T_MAXHEADS];
@@ -488,6 +489,10 @@ iic_bwd_tc_kernel(const __grid_constant__ TcPtrs ptrs, const __grid_constant__ T
         // ------------------------------------------------------------------------------------------ epilogue
         const int eset = (warp - T_EPI0) >> 2, quarter = warp & 3;
         const uint32_t tmem = *tmem_slot;
+        // staging of the fused softmax backward: [warp][3 stages][KC channels][32 floats], behind the converters' ring (only
+        // allocated — and only touched — when g.inv_T != 0)
+        constexpr int E_STAGE_BYTES = KC * 32 * 4;
+        const uint32_t ering = smem_u32(ring0) + (uint32_t)(4 * T_NCS * T_PF * KC * 36 * 4) + (uint32_t)((warp - T_EPI0) * 3 * E_STAGE_BYTES);
         uint32_t orow = 0;
         Seg sg;
         TC_TDECL;
@@ -497,9 +502,46 @@ iic_bwd_tc_kernel(const __grid_constant__ TcPtrs ptrs, const __grid_constant__ T
             const int col = tw * T_TWO + quarter * T_QPX + lane;
             const bool col_ok = lane < T_QPX && col < g.W;
             int i = (int)((eset + T_NES - orow % T_NES) % T_NES);      // first own row of the segment
-            float* p = (side ? ptrs.dx : ptrs.dy)[head] + (size_t)b * K * plane + (size_t)(sg.hb + i) * g.W + (col_ok ? col : 0);
-            for (; i < sg.n_out; i += T_NES, p += T_NES * g.W) {
+            const size_t off0 = (size_t)b * K * plane + (size_t)sg.hb * g.W + (col_ok ? col : 0);     // row 0 of the segment
+            float* const pout = (side ? ptrs.dx : ptrs.dy)[head] + off0;
+            // fused softmax backward (cy_iic_bwd_logits_heads): the output map's own probabilities of the row, staged through a
+            // small shared-memory ring by cp.async two own rows ahead.  (Plain loads into registers do not work here: they share
+            // a scoreboard with the tcgen05.ld of the row, whose wait then exposes the whole L2 / HBM latency every row.)
+            const float* const pin = (side ? ptrs.x : ptrs.y)[head] + (size_t)b * K * plane + (size_t)sg.hb * g.W;
+            const bool sm_bwd = g.inv_T != 0.f;
+            const int col0 = tw * T_TWO + quarter * T_QPX;                 // first column of this quarter
+            constexpr int ECH = KC * (T_QPX / 4);                          // 16-byte chunks of one staged row: KC channels x 28 floats
+            auto stage_row = [&](int ii, int stg) {                        // (every lane commits a group, also an empty one)
+                if (sm_bwd && ii < sg.n_out) {
+                    const float* q = pin + (size_t)ii * g.W + col0;
+#pragma unroll
+                    for (int it = 0; it < (ECH + 31) / 32; ++it) {
+                        const int idx = lane + 32 * it, ch = idx / (T_QPX / 4), jc = idx % (T_QPX / 4);
+                        if (idx < ECH) {
+                            const bool ok = ch < K && col0 + 4 * jc < g.W;
+                            cp_async_16(ering + (uint32_t)(stg * E_STAGE_BYTES + (ch * 32 + 4 * jc) * 4), ok ? q + (size_t)ch * plane + 4 * jc : pin,
+                                        ok ? 16u : 0u);
+                        }
+                    }
+                }
+                cp_async_commit();
+            };
+            int stg = 0;
+            if (sm_bwd) {
+                stage_row(i, 0);
+                stage_row(i + T_NES, 1);
+            }
+            for (; i < sg.n_out; i += T_NES) {
                 const uint32_t r_ = orow + (uint32_t)i, slot = r_ % T_ND;
+                float pv[KC];
+                if (sm_bwd) {
+                    stage_row(i + 2 * T_NES, stg == 0 ? 2 : stg - 1);
+                    cp_async_wait<2>();                                    // this row's group has landed ...
+                    __syncwarp();                                          // ... for every lane
+#pragma unroll
+                    for (int o = 0; o < KC; ++o) pv[o] = lds_f32_own(ering + (uint32_t)(stg * E_STAGE_BYTES + (o * 32 + lane) * 4));
+                    stg = stg == 2 ? 0 : stg + 1;
+                }
                 TC_T(0, mbar_wait_backoff<CY_TC_SLEEP_EPI>(d_full + slot, (r_ / T_ND) & 1u));
 #ifdef CY_TC_TIMING
                 const long long te0 = clock64();
@@ -520,7 +562,14 @@ iic_bwd_tc_kernel(const __grid_constant__ TcPtrs ptrs, const __grid_constant__ T
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_empty + slot);
                 if (col_ok) {
-                    float* q = p;
+                    if (sm_bwd) {                // dL/dlogit_o = p_o (dL/dp_o - sum_k p_k dL/dp_k) / T   (channels past K: p = 0)
+                        float dot = 0.f;
+#pragma unroll
+                        for (int o = 0; o < KC; ++o) dot = fmaf(pv[o], __uint_as_float(r[o]), dot);
+#pragma unroll
+                        for (int o = 0; o < KC; ++o) r[o] = __float_as_uint(pv[o] * (__uint_as_float(r[o]) - dot) * g.inv_T);
+                    }
+                    float* q = pout + (size_t)i * g.W;
 #pragma unroll
                     for (int o = 0; o < KC; ++o) {
                         if (o < KC - 1 || o < K) *q = __uint_as_float(r[o]);
@@ -531,6 +580,10 @@ iic_bwd_tc_kernel(const __grid_constant__ TcPtrs ptrs, const __grid_constant__ T
                 tacc[1] += clock64() - te0;
                 tacc[2] += 1;
 #endif
+            }
+            if (sm_bwd) {
+                cp_async_wait<0>();                                        // nothing in flight when the next segment reuses the ring
+                __syncwarp();
             }
             orow += (uint32_t)sg.n_out;
         }
@@ -550,9 +603,10 @@ iic_bwd_tc_kernel(const __grid_constant__ TcPtrs ptrs, const __grid_constant__ T
 }
 
 // weight tiles of every head + barriers + the converters' staging ring
-size_t tc_smem_bytes(int KH, int S) {
+size_t tc_smem_bytes(int KH, int S, bool softmax_bwd) {
     const int KS = (3 * KH + 7) / 8;
-    return (size_t)S * 2 * 3 * KS * 2 * T_WTILE + 512 + (size_t)4 * T_NCS * T_PF * (2 * KH) * 36 * 4;
+    return (size_t)S * 2 * 3 * KS * 2 * T_WTILE + 512 + (size_t)4 * T_NCS * T_PF * (2 * KH) * 36 * 4 +
+           (softmax_bwd ? (size_t)4 * T_NES * 3 * (2 * KH) * 32 * 4 : 0);
 }
 
 template <int KH>
@@ -560,7 +614,7 @@ int launch_bwd_tc(const TcPtrs& ptrs, const TcGeom& g, const float* djoint, cons
     // one CTA per SM: the register file (>= 52 registers x 896 threads) does not hold two, so the 512-column TMEM allocation
     // never waits for a co-resident CTA
     constexpr int KS = (3 * KH + 7) / 8;
-    size_t smem = tc_smem_bytes(KH, g.S);
+    size_t smem = tc_smem_bytes(KH, g.S, g.inv_T != 0.f);
     auto k = iic_bwd_tc_kernel<KH>;
     static SmemAttrCache attr;
     if (attr.need(smem)) {
@@ -600,7 +654,7 @@ int launch_bwd_tc(const TcPtrs& ptrs, const TcGeom& g, const float* djoint, cons
 // weight tiles do not fit beside the staging ring (the caller then loops over the heads).
 int iic_bwd_tc_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
                      const float* djoint, long long dj_stride, const float* gscale, void* const* dxs, void* const* dys,
-                     cudaStream_t st) {
+                     float softmax_inv_T, cudaStream_t st) {
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if (dtype != CY_F32 || pad != 1 || K > 16 || K < 1 || (W % 4) != 0 || n_heads < 1 || n_heads > T_MAXHEADS) return CY_ERR_UNSUPPORTED;
     TcGeom g;
@@ -613,13 +667,13 @@ int iic_bwd_tc_heads(const void* const* xs, const void* const* ys, int n_heads, 
         ptrs.dx[s] = reinterpret_cast<float*>(dxs[t]);
         ptrs.dy[s] = reinterpret_cast<float*>(dys[t]);
     }
-    g.B = B; g.K = K; g.H = H; g.W = W; g.S = n_heads; g.dj_stride = dj_stride;
+    g.B = B; g.K = K; g.H = H; g.W = W; g.S = n_heads; g.dj_stride = dj_stride; g.inv_T = softmax_inv_T;
     g.TW2 = (W + T_TWO - 1) / T_TWO;
     const long long rows = 2LL * n_heads * B * g.TW2 * H;
     if (rows <= 0 || rows > 0x7fffffffLL / 2 || (long long)K * H * W > 0x7fffffffLL / 8) return CY_ERR_UNSUPPORTED;
     g.rows_total = (int)rows;
     const int KH = (K + 1) / 2;
-    if (tc_smem_bytes(KH, n_heads) > (size_t)227 * 1024) return CY_ERR_UNSUPPORTED;
+    if (tc_smem_bytes(KH, n_heads, softmax_inv_T != 0.f) > (size_t)227 * 1024) return CY_ERR_UNSUPPORTED;
     switch (KH) {
         case 1: return launch_bwd_tc<1>(ptrs, g, djoint, gscale, st);
         case 2: return launch_bwd_tc<2>(ptrs, g, djoint, gscale, st);
@@ -635,7 +689,7 @@ int iic_bwd_tc_heads(const void* const* xs, const void* const* ys, int n_heads, 
 // returns CY_ERR_UNSUPPORTED when the shape is not eligible (the caller then takes the mma.sync / CUDA-core kernels)
 int iic_bwd_tc(const void* x, const void* y, int dtype, int B, int K, int H, int W, int pad, const float* djoint,
                const float* gscale, void* dx, void* dy, cudaStream_t st) {
-    return iic_bwd_tc_heads(&x, &y, 1, dtype, B, K, H, W, pad, djoint, 0, gscale, &dx, &dy, st);
+    return iic_bwd_tc_heads(&x, &y, 1, dtype, B, K, H, W, pad, djoint, 0, gscale, &dx, &dy, 0.f, st);
 }
 
 }  // namespace cy

@@ -232,25 +232,30 @@ iic_joint_tma_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + s);
         }
-        if (active) {
+        // per-CTA sum over the tile rows (= compute warps) in warp order: plain read-modify-writes, one warp at a time behind a
+        // named barrier of the compute warps — bitwise reproducible, unlike shared-memory atomics (the padding-0 loss is a 1e-3
+        // residual of O(1) terms, so one ulp of a partial joint is visible in its 6th digit)
+        for (int wv = 0; wv < JT_COMPUTE_WARPS; ++wv) {
+            if (warp == wv && active) {
 #pragma unroll
-            for (int kk = 0; kk < KC; ++kk) {
-                const int k2 = k2base + kk;
-                if (k2 < K) {
+                for (int kk = 0; kk < KC; ++kk) {
+                    const int k2 = k2base + kk;
+                    if (k2 < K) {
 #pragma unroll
-                    for (int dx = 0; dx < T; ++dx)
-                    {
-                        float v;
-                        if constexpr (PK) {
-                            const float2 pr = reinterpret_cast<const float2&>(acc[dx][kk]);
-                            v = pr.x + pr.y;
-                        } else {
-                            v = accs[dx][kk];
+                        for (int dx = 0; dx < T; ++dx) {
+                            float v;
+                            if constexpr (PK) {
+                                const float2 pr = reinterpret_cast<const float2&>(acc[dx][kk]);
+                                v = pr.x + pr.y;
+                            } else {
+                                v = accs[dx][kk];
+                            }
+                            jsm[((k1 * K + k2) * T + dy) * T + dx] += v;
                         }
-                        atomicAdd(&jsm[((k1 * K + k2) * T + dy) * T + dx], v);
                     }
                 }
             }
+            asm volatile("bar.sync 1, %0;" ::"r"(JT_COMPUTE_WARPS * 32) : "memory");
         }
     }
     __syncthreads();

@@ -203,11 +203,17 @@ class _IIDSegMultiFunction(torch.autograd.Function):
     cluster head (semi_seg/hooks/discretemi.py:111, ccblock.py:208-218): S python-level criterion calls, S autograd nodes
     and ~8 small allocations each.  Here the S joints, the S epilogues and the S adjoints are ONE launch each (plus the joint's
     reduction): cy_iic_joint_heads / cy_iic_epilogue_heads / cy_iic_bwd_heads, with one output buffer; the adjoint gets the
-    head's share 1/S of the upstream gradient through ``gscale``."""
+    head's share 1/S of the upstream gradient through ``gscale``.
+
+    ``temperature`` not None: the inputs are the cluster heads' LOGITS (``DenseClusterHead(..., skip_softmax=True)``); the
+    probabilities softmax(logits / T) are formed here and only they are kept for the backward, whose adjoint launch applies the
+    softmax backward in its epilogue (cy_iic_bwd_logits_heads) — dL/dp is never written to memory."""
 
     @staticmethod
-    def forward(ctx, padding, symmetric, lamda, eps, *maps):
+    def forward(ctx, padding, symmetric, lamda, eps, temperature, *maps):
         lib = L.lib()
+        if temperature is not None:
+            maps = tuple(torch.softmax(m if temperature == 1.0 else m / temperature, dim=1) for m in maps)
         S = len(maps) // 2
         x0 = maps[0]
         B, K, H, W = x0.shape
@@ -235,7 +241,7 @@ class _IIDSegMultiFunction(torch.autograd.Function):
                                           float(B * H * W), base, base + 4, base + 4 * (1 + K * K), per, L.ptr(ews), ews_bytes, st),
                 "cy_iic_epilogue_heads")
         ctx.save_for_backward(buf, *maps)
-        ctx.cfg = (padding, S, K, T, per)
+        ctx.cfg = (padding, S, K, T, per, temperature)
         p00 = buf[0, 1:1 + K * K].view(K, K)
         ctx.mark_non_differentiable(p00)
         return buf[:, 0].mean(), p00
@@ -244,7 +250,7 @@ class _IIDSegMultiFunction(torch.autograd.Function):
     def backward(ctx, grad_loss, _grad_p00):
         lib = L.lib()
         buf, *maps = ctx.saved_tensors
-        padding, S, K, T, per = ctx.cfg
+        padding, S, K, T, per, temperature = ctx.cfg
         B, _, H, W = maps[0].shape
         if buf.device.index != torch.cuda.current_device():
             torch.cuda.set_device(buf.device)
@@ -256,9 +262,13 @@ class _IIDSegMultiFunction(torch.autograd.Function):
         ys = (ctypes.c_void_p * S)(*[maps[2 * s + 1].data_ptr() for s in range(S)])
         dxs = (ctypes.c_void_p * S)(*[grads[2 * s].data_ptr() for s in range(S)])
         dys = (ctypes.c_void_p * S)(*[grads[2 * s + 1].data_ptr() for s in range(S)])
-        L.check(lib.cy_iic_bwd_heads(xs, ys, S, dt, B, K, H, W, padding, buf.data_ptr() + (1 + K * K) * 4, per, gscale.data_ptr(),
-                                     dxs, dys, st), "cy_iic_bwd_heads")
-        return (None, None, None, None, *grads)
+        dj = buf.data_ptr() + (1 + K * K) * 4
+        if temperature is None:
+            L.check(lib.cy_iic_bwd_heads(xs, ys, S, dt, B, K, H, W, padding, dj, per, gscale.data_ptr(), dxs, dys, st), "cy_iic_bwd_heads")
+        else:
+            L.check(lib.cy_iic_bwd_logits_heads(xs, ys, S, dt, B, K, H, W, padding, dj, per, gscale.data_ptr(), float(temperature),
+                                                dxs, dys, st), "cy_iic_bwd_logits_heads")
+        return (None, None, None, None, None, *grads)
 
 
 class IIDSegmentationLoss(nn.Module):
@@ -284,11 +294,19 @@ class IIDSegmentationLoss(nn.Module):
         self.__dict__["_p_i_j"] = p00      # (plain attribute; Module.__setattr__ costs ~5 us of type checks per step)
         return loss
 
-    def forward_heads(self, x_outs, x_tf_outs) -> Tensor:
+    def forward_logits(self, x_logits: Tensor, x_tf_logits: Tensor, T: float = 1.0) -> Tensor:
+        """``self(softmax(x_logits / T, 1), softmax(x_tf_logits / T, 1))`` with SoftmaxWithT's backward fused into the adjoint
+        kernel (extension).  Feed it ``DenseClusterHead(...)(features, skip_softmax=True)``."""
+        return self.forward_heads([x_logits], [x_tf_logits], logits_T=T)
+
+    def forward_heads(self, x_outs, x_tf_outs, logits_T: float = None) -> Tensor:
         """mean of ``self(x, y)`` over the sub-head pairs, evaluated as ONE autograd node (extension).
-        Equivalent to ``sum(self(x, y) for x, y in zip(x_outs, x_tf_outs)) / len(x_outs)``; ``_p_i_j`` is head 0's."""
+        Equivalent to ``sum(self(x, y) for x, y in zip(x_outs, x_tf_outs)) / len(x_outs)``; ``_p_i_j`` is head 0's.
+        ``logits_T`` not None: the inputs are logits and every pair is softmax(. / logits_T) first (see ``forward_logits``)."""
         if self.padding < 0:
             raise ValueError(self.padding)
+        if logits_T is not None and not float(logits_T) > 0:
+            raise ValueError(f"temperature {logits_T}")
         assert len(x_outs) == len(x_tf_outs) and len(x_outs) >= 1
         maps = []
         for x, y in zip(x_outs, x_tf_outs):
@@ -296,8 +314,12 @@ class IIDSegmentationLoss(nn.Module):
             assert x.shape == x_outs[0].shape and x.dtype == x_outs[0].dtype, "sub-heads must share shape and dtype"
             maps += [x, y]
         if self._reduce_joint is not None:      # sharded batches need the joint all-reduce between the two kernels
+            if logits_T is not None:
+                x_outs = [torch.softmax(x / logits_T, 1) for x in x_outs]
+                x_tf_outs = [torch.softmax(y / logits_T, 1) for y in x_tf_outs]
             return sum(self(x, y) for x, y in zip(x_outs, x_tf_outs)) / len(x_outs)
-        loss, p00 = _IIDSegMultiFunction.apply(int(self.padding), bool(self.symmetric), float(self.lamda), float(self._eps), *maps)
+        loss, p00 = _IIDSegMultiFunction.apply(int(self.padding), bool(self.symmetric), float(self.lamda), float(self._eps),
+                                               None if logits_T is None else float(logits_T), *maps)
         self.__dict__["_p_i_j"] = p00      # (plain attribute; Module.__setattr__ costs ~5 us of type checks per step)
         return loss
 

@@ -97,8 +97,23 @@ class _DenseSubheads(_ProjectorHeadBase):
         self._headers = nn.ModuleList(_dense_stack(dims, [_tail(normalize), SoftmaxWithT(1, T=T)])
                                       for _ in range(num_subheads))
 
-    def forward(self, features) -> t.List[Tensor]:
+    def forward(self, features, skip_softmax: bool = False) -> t.List[Tensor]:
+        """``skip_softmax=True`` (extension) stops before the parameter-free ``SoftmaxWithT`` tail and returns the logits, for
+        ``IIDSegmentationLoss.forward_logits`` / ``forward_heads(..., logits_T=T)`` which fuse the softmax backward into the
+        adjoint kernel; the module tree — and with it the checkpoint keys — is unchanged."""
+        if skip_softmax:
+            out = []
+            for h in self._headers:
+                z = features
+                for m in list(h)[:-1]:
+                    z = m(z)
+                out.append(z)
+            return out
         return [h(features) for h in self._headers]
+
+    @property
+    def temperature(self) -> float:
+        return self._T
 
 
 class DenseClusterHead(_DenseSubheads):

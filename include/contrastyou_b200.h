@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CY_ABI_VERSION 4
+#define CY_ABI_VERSION 5
 
 /* element types of embeddings / probability maps */
 #define CY_F32 0
@@ -235,6 +235,17 @@ int cy_iic_epilogue_heads(const double* joint, long long joint_stride, int n_hea
 int cy_iic_bwd_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
                      const float* djoint, long long djoint_stride, const float* gscale, void* const* dxs, void* const* dys,
                      void* stream);
+
+/* Fused SoftmaxWithT backward (contrastyou/projectors/nn.py:36-44 feeds IIDSegmentationLoss through
+ * DenseClusterHead, heads.py:151-172).  pxs / pys are the PROBABILITY maps p = softmax(logits / T) over the K planes that the
+ * forward consumed; dlxs / dlys receive dLoss/dlogits = p * (dL/dp - sum_k p_k dL/dp_k) / T, formed in the adjoint's epilogue
+ * where a thread holds all K channels of a pixel — the dL/dp maps are never written and the separate softmax backward pass
+ * (read dL/dp, read p, write dL/dlogits: 3 maps of traffic per side) disappears.  Shapes the tensor-core adjoint does not take
+ * run cy_iic_bwd followed by an in-place softmax-backward kernel.  n_heads = 1 is the plain single-pair call.
+ * (The forward half of the fusion is deliberately absent: the joint kernel is issue-bound, not HBM-bound — DESIGN.md §9.) */
+int cy_iic_bwd_logits_heads(const void* const* pxs, const void* const* pys, int n_heads, int dtype, int B, int K, int H, int W,
+                            int pad, const float* djoint, long long djoint_stride, const float* gscale, float T,
+                            void* const* dlxs, void* const* dlys, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * IMSAT entropies.  Replaces imsat_loss / the marginal + conditional entropy pair of

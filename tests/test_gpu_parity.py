@@ -769,6 +769,48 @@ def test_iic_heads_entry_points_equal_single_head_calls(S, B, K, H, W, pad):
         assert torch.equal(dxs[s], dx) and torch.equal(dys[s], dy), s
 
 
+@pytest.mark.parametrize("S,B,K,H,W,pad,T", [(1, 2, 10, 32, 32, 1, 1.0), (3, 2, 10, 40, 228, 1, 0.5), (2, 1, 7, 16, 24, 1, 2.0),
+                                              (2, 2, 6, 8, 16, 0, 1.0), (1, 2, 10, 10, 10, 1, 0.7), (9, 1, 3, 6, 8, 1, 1.0)])
+def test_iic_logits_path_equals_torch_softmax_route(S, B, K, H, W, pad, T):
+    """SoftmaxWithT fused into the adjoint (cy_iic_bwd_logits_heads): forward_heads(logits, logits_T=T) vs the
+    reference route softmax(logits / T) -> criterion with torch's softmax backward.  Both routes run the same joint / adjoint
+    arithmetic, so dL/dlogits may differ only by the fp32 rounding of the softmax backward itself.  Covers odd K (a padded
+    channel in the epilogue), padding 0 and W % 4 != 0 (in-place softmax-backward kernel behind the other adjoints), > 8 heads."""
+    torch.manual_seed(S * 31 + K)
+    lx = [torch.randn(B, K, H, W, device=DEV).mul_(2).requires_grad_() for _ in range(S)]
+    ly = [torch.randn(B, K, H, W, device=DEV).mul_(2).requires_grad_() for _ in range(S)]
+    crit = IIDSegmentationLoss(padding=pad)
+    ref = sum(crit(torch.softmax(a / T, 1), torch.softmax(b / T, 1)) for a, b in zip(lx, ly)) / S
+    (2.0 * ref).backward()
+    gref = [t.grad.clone() for t in lx + ly]
+    for t in lx + ly:
+        t.grad = None
+    loss = crit.forward_heads(lx, ly, logits_T=T)
+    (2.0 * loss).backward()
+    assert loss.item() == pytest.approx(ref.item(), rel=2e-6, abs=1e-9)
+    for t, g in zip(lx + ly, gref):
+        assert _relerr(t.grad.cpu().numpy(), g.cpu().numpy()) <= 2e-5
+    if S == 1:
+        for t in lx + ly:
+            t.grad = None
+        l1 = crit.forward_logits(lx[0], ly[0], T=T)
+        l1.backward()
+        assert _relerr(lx[0].grad.cpu().numpy(), 0.5 * gref[0].cpu().numpy()) <= 2e-5
+
+
+@pytest.mark.parametrize("B,K,H,W,pad", [(2, 6, 8, 16, 0), (4, 10, 36, 64, 0), (2, 5, 19, 23, 2), (3, 10, 40, 72, 1), (2, 20, 12, 16, 1)])
+def test_iic_joint_is_bitwise_reproducible(B, K, H, W, pad):
+    """every joint kernel (CUDA-core, TMA-staged, tensor-core) sums its per-CTA partials in a fixed order — no shared-memory
+    atomics: 25 evaluations of the same inputs return the same bits.  (The padding-0 loss is a 1e-3 residual of O(1) terms: one
+    ulp of a partial joint moves its 6th digit, which is how the atomics that used to be there were noticed.)"""
+    torch.manual_seed(B + K + H)
+    x = (2 * torch.randn(B, K, H, W, device=DEV)).softmax(1)
+    y = (2 * torch.randn(B, K, H, W, device=DEV)).softmax(1)
+    first = raw_joint(x, y, pad).clone()
+    for _ in range(25):
+        assert torch.equal(raw_joint(x, y, pad), first)
+
+
 def test_iic_mma_sync_adjoint_still_agrees():
     """CY_IIC_TC=0 pins the round-1 mma.sync adjoint (csrc/iic_mma.cu), kept for A/B timing: it must return what the tcgen05
     adjoint returns (the switch is read once per process, hence the subprocess)"""

@@ -160,3 +160,19 @@ def test_bench_reference_arm_contract():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_cluster_head_skip_softmax_returns_the_logits_of_the_same_module_tree():
+    """DenseClusterHead(features, skip_softmax=True): logits such that softmax(logits / T) == the stock forward; state_dict
+    keys unchanged (the SoftmaxWithT tail stays a member, it is bypassed at call time — SURVEY.md 8b)"""
+    import torch
+    from contrast_you_b200.projectors import DenseClusterHead
+    torch.manual_seed(0)
+    head = DenseClusterHead(input_dim=8, num_clusters=5, num_subheads=3, T=2.0, head_type="mlp", hidden_dim=16)
+    feats = torch.randn(2, 8, 6, 6)
+    logits = head(feats, skip_softmax=True)
+    probs = head(feats)
+    assert len(logits) == 3 and head.temperature == 2.0
+    for lg, pr in zip(logits, probs):
+        assert torch.allclose(torch.softmax(lg / 2.0, 1), pr, atol=1e-6)
+    assert sorted(head.state_dict()) == sorted(f"_headers.{s}.{i}.{w}" for s in range(3) for i in (0, 2) for w in ("weight", "bias"))
