@@ -82,6 +82,7 @@ int imsat_bwd(const void*, int, int64_t, int, int64_t, float, const float*, cons
 int p2p_push(void* const*, int, int, const unsigned long long*, int, cudaStream_t);
 int p2p_push_barrier(void* const*, int, int, const unsigned long long*, int, unsigned long long, unsigned int*, unsigned int, cudaStream_t);
 int iic_bwd(const void*, const void*, int, int, int, int, int, int, const float*, const float*, void*, void*, cudaStream_t);
+int softmax_t_fwd(const void* const*, void* const*, int, int, int, int, int, int, float, cudaStream_t);
 int iic_joint_heads(const void* const*, const void* const*, int, int, int, int, int, int, int, double*, long long, void*, size_t,
                     cudaStream_t);
 int iic_epilogue_heads(const double*, long long, int, int, int, int, int, float, float, double, float*, float*, float*, long long, void*,
@@ -397,6 +398,17 @@ int cy_iic_bwd_logits_heads(const void* const* pxs, const void* const* pys, int 
     }
     return iic_bwd_heads(pxs, pys, n_heads, dtype, B, K, H, W, pad, djoint, djoint_stride, gscale, dlxs, dlys, 1.0f / T,
                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+int cy_softmax_t_fwd(const void* const* logits, void* const* probs, int n_maps, int dtype, int B, int K, int H, int W, float T,
+                     void* stream) {
+    CY_NVTX("cy_softmax_t_fwd");
+    CY_CHECK_ARG(logits && probs && n_maps >= 1, "bad arguments");
+    CY_CHECK_ARG(dtype == CY_F32 || dtype == CY_BF16 || dtype == CY_F16, "unknown dtype %d", dtype);
+    CY_CHECK_ARG(B >= 1 && K >= 1 && H >= 1 && W >= 1, "bad shape [%d,%d,%d,%d]", B, K, H, W);
+    CY_CHECK_ARG(T > 0.f && isfinite(T), "temperature %g", (double)T);
+    for (int i = 0; i < n_maps; ++i) CY_CHECK_ARG(logits[i] && probs[i], "null map %d", i);
+    return softmax_t_fwd(logits, probs, n_maps, dtype, B, K, H, W, T, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -892,7 +892,7 @@ int iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int W,
 // one thread per pixel of both maps, coalesced along W.  The fused form lives in the tcgen05 adjoint's epilogue; this is the
 // route of the shapes that kernel does not take.
 __global__ void __launch_bounds__(256)
-iic_softmax_bwd_kernel(const void* __restrict__ px, const void* __restrict__ py, void* __restrict__ gx, void* __restrict__ gy, int dtype,
+iic_softmax_bwd_kernel(const void* __restrict__ px, const void* __restrict__ py, void* gx, void* gy, int dtype,
                        int K, long long plane, long long n_pix, float inv_T) {
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * n_pix; idx += (long long)gridDim.x * blockDim.x) {
         const bool second = idx >= n_pix;
@@ -900,11 +900,17 @@ iic_softmax_bwd_kernel(const void* __restrict__ px, const void* __restrict__ py,
         const void* p = second ? py : px;
         void* g = second ? gy : gx;
         const size_t base = (size_t)(t / plane) * K * plane + (size_t)(t % plane);
+        // (g is read AND written here: plain loads, not the read-only path of ld_as_float)
+        auto ld_g = [&](size_t e) {
+            if (dtype == CY_F32) return reinterpret_cast<const float*>(g)[e];
+            if (dtype == CY_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g)[e]);
+            return __half2float(reinterpret_cast<const __half*>(g)[e]);
+        };
         float dot = 0.f;
-        for (int k = 0; k < K; ++k) dot = fmaf(ld_as_float(p, dtype, base + (size_t)k * plane), ld_as_float(g, dtype, base + (size_t)k * plane), dot);
+        for (int k = 0; k < K; ++k) dot = fmaf(ld_as_float(p, dtype, base + (size_t)k * plane), ld_g(base + (size_t)k * plane), dot);
         for (int k = 0; k < K; ++k) {
             const size_t e = base + (size_t)k * plane;
-            st_from_float(g, dtype, e, ld_as_float(p, dtype, e) * (ld_as_float(g, dtype, e) - dot) * inv_T);
+            st_from_float(g, dtype, e, ld_as_float(p, dtype, e) * (ld_g(e) - dot) * inv_T);
         }
     }
 }

@@ -223,7 +223,7 @@ iic_bwd_tc_kernel(const __grid_constant__ TcPtrs ptrs, const __grid_constant__ T
     // in the CTA-wide barrier); the converter warps call it AFTER they have issued their first staged rows, so the cold-HBM
     // latency of those loads overlaps the ~2 us of set-up instead of following it.
     auto setup = [&]() {
-        const float scale = gscale[0];
+        const float scale = gscale[0] * (g.inv_T != 0.f ? g.inv_T : 1.f);      // (1/T of the fused softmax backward rides on the weights)
         for (int i = threadIdx.x; i < g.S * 2 * 3 * KS * 16 * 16; i += T_THREADS) {
             const int k = i % 16, n = (i / 16) % 16, ks = (i / 256) % KS, dyy = (i / (256 * KS)) % 3, side = (i / (256 * KS * 3)) & 1;
             const int head = i / (256 * KS * 3 * 2);
@@ -562,12 +562,12 @@ iic_bwd_tc_kernel(const __grid_constant__ TcPtrs ptrs, const __grid_constant__ T
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_empty + slot);
                 if (col_ok) {
-                    if (sm_bwd) {                // dL/dlogit_o = p_o (dL/dp_o - sum_k p_k dL/dp_k) / T   (channels past K: p = 0)
+                    if (sm_bwd) {                // dL/dlogit_o = p_o (dL/dp_o - sum_k p_k dL/dp_k) / T   (1/T is in the weights; channels past K: p = 0)
                         float dot = 0.f;
 #pragma unroll
                         for (int o = 0; o < KC; ++o) dot = fmaf(pv[o], __uint_as_float(r[o]), dot);
 #pragma unroll
-                        for (int o = 0; o < KC; ++o) r[o] = __float_as_uint(pv[o] * (__uint_as_float(r[o]) - dot) * g.inv_T);
+                        for (int o = 0; o < KC; ++o) r[o] = __float_as_uint(pv[o] * (__uint_as_float(r[o]) - dot));
                     }
                     float* q = pout + (size_t)i * g.W;
 #pragma unroll

@@ -19,7 +19,7 @@ from torch import Tensor, nn
 
 from .. import _lib as L
 
-__all__ = ["IIDSegmentationLoss", "IIDLoss", "compute_joint", "compute_joint_2D", "compute_joint_2D_with_padding_zeros",
+__all__ = ["IIDSegmentationLoss", "IIDLoss", "softmax_with_t", "compute_joint", "compute_joint_2D", "compute_joint_2D_with_padding_zeros",
            "raw_joint", "simplex"]
 
 
@@ -151,6 +151,25 @@ def compute_joint(x_out: Tensor, x_tf_out: Tensor, symmetric=True) -> Tensor:
     return p_i_j.contiguous()
 
 
+def softmax_with_t(logits, T: float = 1.0):
+    """``[softmax(l / T, dim=1) for l in logits]`` for [B, K, H, W] maps of one shape and dtype — SoftmaxWithT (reference
+    projectors/nn.py:36-44) for all maps in ONE streaming launch (cy_softmax_t_fwd).  No autograd: the backward is fused into
+    the IIC adjoint (``IIDSegmentationLoss.forward_logits``)."""
+    logits = [m.contiguous() for m in logits]
+    m0 = logits[0]
+    L.require_cuda(*logits)
+    for m in logits:
+        assert m.shape == m0.shape and m.dtype == m0.dtype and m.dim() == 4, "maps must share shape and dtype"
+    B, K, H, W = m0.shape
+    out = [torch.empty_like(m) for m in logits]
+    n = len(logits)
+    with L.guard(m0):
+        L.check(L.lib().cy_softmax_t_fwd((ctypes.c_void_p * n)(*[m.data_ptr() for m in logits]),
+                                         (ctypes.c_void_p * n)(*[m.data_ptr() for m in out]), n, L.dtype_code(m0), B, K, H, W,
+                                         float(T), L.stream_ptr(m0.device)), "cy_softmax_t_fwd")
+    return tuple(out)
+
+
 class _IIDSegFunction(torch.autograd.Function):
     """(x, y) -> (loss, p_i_j[0][0]) with the fused epilogue; ``reduce_joint`` all-reduces the raw joint when the batch
     is sharded over ranks (the epilogue is non-linear in J, so it must see the global joint)."""
@@ -213,7 +232,7 @@ class _IIDSegMultiFunction(torch.autograd.Function):
     def forward(ctx, padding, symmetric, lamda, eps, temperature, *maps):
         lib = L.lib()
         if temperature is not None:
-            maps = tuple(torch.softmax(m if temperature == 1.0 else m / temperature, dim=1) for m in maps)
+            maps = softmax_with_t(maps, temperature)
         S = len(maps) // 2
         x0 = maps[0]
         B, K, H, W = x0.shape

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CY_ABI_VERSION 5
+#define CY_ABI_VERSION 6
 
 /* element types of embeddings / probability maps */
 #define CY_F32 0
@@ -243,6 +243,12 @@ int cy_iic_bwd_heads(const void* const* xs, const void* const* ys, int n_heads, 
  * (read dL/dp, read p, write dL/dlogits: 3 maps of traffic per side) disappears.  Shapes the tensor-core adjoint does not take
  * run cy_iic_bwd followed by an in-place softmax-backward kernel.  n_heads = 1 is the plain single-pair call.
  * (The forward half of the fusion is deliberately absent: the joint kernel is issue-bound, not HBM-bound — DESIGN.md §9.) */
+/* SoftmaxWithT forward (nn.py:36-44): probs[i][b, :, h, w] = softmax(logits[i][b, :, h, w] / T) over the K planes, for n_maps
+ * maps of one shape [B,K,H,W] (both views of every sub-head) in ONE streaming launch: each map read once, written once.
+ * probs[i] may equal logits[i] (in place, like the reference's `input /= T`).  Host arrays of device pointers. */
+int cy_softmax_t_fwd(const void* const* logits, void* const* probs, int n_maps, int dtype, int B, int K, int H, int W, float T,
+                     void* stream);
+
 int cy_iic_bwd_logits_heads(const void* const* pxs, const void* const* pys, int n_heads, int dtype, int B, int K, int H, int W,
                             int pad, const float* djoint, long long djoint_stride, const float* gscale, float T,
                             void* const* dlxs, void* const* dlys, void* stream);

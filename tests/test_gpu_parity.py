@@ -787,9 +787,11 @@ def test_iic_logits_path_equals_torch_softmax_route(S, B, K, H, W, pad, T):
         t.grad = None
     loss = crit.forward_heads(lx, ly, logits_T=T)
     (2.0 * loss).backward()
-    assert loss.item() == pytest.approx(ref.item(), rel=2e-6, abs=1e-9)
+    # the probabilities of the two routes differ by ~1e-7 (cy_softmax_t_fwd vs torch.softmax); the padding-0 loss is a 1e-3
+    # residual of O(1) terms and amplifies that ~100-fold
+    assert loss.item() == pytest.approx(ref.item(), rel=2e-6 if pad else 1e-4, abs=1e-9)
     for t, g in zip(lx + ly, gref):
-        assert _relerr(t.grad.cpu().numpy(), g.cpu().numpy()) <= 2e-5
+        assert _relerr(t.grad.cpu().numpy(), g.cpu().numpy()) <= (2e-5 if pad else 1e-3)
     if S == 1:
         for t in lx + ly:
             t.grad = None
@@ -809,6 +811,27 @@ def test_iic_joint_is_bitwise_reproducible(B, K, H, W, pad):
     first = raw_joint(x, y, pad).clone()
     for _ in range(25):
         assert torch.equal(raw_joint(x, y, pad), first)
+
+
+@pytest.mark.parametrize("n,B,K,H,W,T,dtype", [(2, 4, 10, 56, 56, 1.0, torch.float32), (1, 2, 3, 8, 12, 0.5, torch.float32),
+                                                (3, 1, 20, 16, 16, 2.0, torch.float32), (2, 1, 33, 8, 8, 1.0, torch.float32),
+                                                (2, 2, 10, 5, 7, 1.3, torch.float32), (17, 1, 4, 4, 4, 1.0, torch.float32),
+                                                (2, 2, 10, 16, 16, 1.0, torch.bfloat16), (2, 2, 7, 16, 16, 0.7, torch.float16)])
+def test_softmax_with_t_matches_torch(n, B, K, H, W, T, dtype):
+    """cy_softmax_t_fwd (SoftmaxWithT, nn.py:36-44) vs torch.softmax(l / T, 1): the float4 kernel at K <= 32 for every register
+    tile (K = 3, 10, 20), the scalar kernel (K = 33, planes that are not a multiple of 4, 16-bit maps), > 16 maps (two launches),
+    large logits (no overflow: the maximum is subtracted first)"""
+    from contrast_you_b200.losses.discreteMI import softmax_with_t
+    torch.manual_seed(n * 7 + K)
+    logits = [(8 * torch.randn(B, K, H, W, device=DEV)).to(dtype) for _ in range(n)]
+    logits[0][0, 0, 0, 0] = 80.0
+    got = softmax_with_t(logits, T)
+    for l, p in zip(logits, got):
+        ref = torch.softmax(l.float() / T, 1)
+        assert p.dtype == dtype and torch.isfinite(p).all()
+        tol = 2e-6 if dtype == torch.float32 else (4e-3 if dtype == torch.bfloat16 else 6e-4)
+        assert float((p.float() - ref).abs().max()) <= tol
+        assert float((p.float().sum(1) - 1).abs().max()) <= (1e-5 if dtype == torch.float32 else 2e-2)
 
 
 def test_iic_mma_sync_adjoint_still_agrees():
