@@ -17,7 +17,7 @@ CY_F32, CY_BF16, CY_F16, CY_F32_SPLIT = 0, 1, 2, 3
 CY_SUPCON, CY_SUPCON_EXCLUDE, CY_SELFPACED_HARD, CY_SELFPACED_SOFT = 0, 1, 2, 3
 CY_PATH_AUTO, CY_PATH_SIMT, CY_PATH_TCGEN05 = 0, 1, 2
 CY_NSTAT = 8
-CY_ABI_VERSION = 6
+CY_ABI_VERSION = 7
 CY_STAT_LOGDEN, CY_STAT_INVC, CY_STAT_COEF, CY_STAT_AUX = 0, 1, 2, 3
 
 _c = ctypes
@@ -49,7 +49,7 @@ SIGNATURES = {
     "cy_iic_epilogue": (_i32, [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _f64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cy_iic_bwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cy_iic_joint_heads": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _c.c_longlong, _vp, _sz, _vp]),
-    "cy_iic_epilogue_heads": (_i32, [_vp, _c.c_longlong, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f64, _vp, _vp, _vp,
+    "cy_iic_epilogue_heads": (_i32, [_vp, _c.c_longlong, _c.c_longlong, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f64, _vp, _vp, _vp,
                                      _c.c_longlong, _vp, _sz, _vp]),
     "cy_iic_bwd_heads": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _c.c_longlong, _vp, _vp, _vp, _vp]),
     "cy_softmax_t_fwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),

@@ -85,8 +85,8 @@ int iic_bwd(const void*, const void*, int, int, int, int, int, int, const float*
 int softmax_t_fwd(const void* const*, void* const*, int, int, int, int, int, int, float, cudaStream_t);
 int iic_joint_heads(const void* const*, const void* const*, int, int, int, int, int, int, int, double*, long long, void*, size_t,
                     cudaStream_t);
-int iic_epilogue_heads(const double*, long long, int, int, int, int, int, float, float, double, float*, float*, float*, long long, void*,
-                       size_t, cudaStream_t);
+int iic_epilogue_heads(const double*, long long, long long, int, int, int, int, int, float, float, double, float*, float*, float*, long long,
+                       void*, size_t, cudaStream_t);
 int iic_bwd_heads(const void* const*, const void* const*, int, int, int, int, int, int, int, const float*, long long, const float*,
                   void* const*, void* const*, float, cudaStream_t);
 
@@ -362,12 +362,13 @@ int cy_iic_joint_heads(const void* const* xs, const void* const* ys, int n_heads
                            reinterpret_cast<cudaStream_t>(stream));
 }
 
-int cy_iic_epilogue_heads(const double* joint, long long joint_stride, int n_heads, int n_slots, int K, int pad, int symmetric,
-                          float lamda, float eps, double n_pixels, float* loss, float* p00, float* djoint, long long out_stride,
-                          void* workspace, size_t workspace_bytes, void* stream) {
+int cy_iic_epilogue_heads(const double* joint, long long joint_stride, long long slot_stride, int n_heads, int n_slots, int K, int pad,
+                          int symmetric, float lamda, float eps, double n_pixels, float* loss, float* p00, float* djoint,
+                          long long out_stride, void* workspace, size_t workspace_bytes, void* stream) {
     CY_NVTX("cy_iic_epilogue_heads");
-    CY_CHECK_ARG(joint && loss && p00 && n_heads >= 1 && n_slots >= 1 && K >= 1 && pad >= 0 && n_pixels > 0, "bad arguments");
-    return iic_epilogue_heads(joint, joint_stride, n_heads, n_slots, K, pad, symmetric, lamda, eps, n_pixels, loss, p00, djoint,
+    CY_CHECK_ARG(joint && loss && p00 && n_heads >= 1 && n_slots >= 1 && K >= 1 && pad >= 0 && n_pixels > 0 && slot_stride >= 0,
+                 "bad arguments");
+    return iic_epilogue_heads(joint, joint_stride, slot_stride, n_heads, n_slots, K, pad, symmetric, lamda, eps, n_pixels, loss, p00, djoint,
                               out_stride, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 

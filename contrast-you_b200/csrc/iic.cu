@@ -276,7 +276,8 @@ constexpr int EPI_THREADS = 1024;
 __global__ void __launch_bounds__(EPI_THREADS)
 iic_epilogue_kernel(const double* __restrict__ joint, int n_slots, int K, int pad, int symmetric, double lamda, double eps,
                     double n_pixels, float* __restrict__ loss, float* __restrict__ p00, float* __restrict__ p_ij,
-                    float* __restrict__ djoint, double* __restrict__ gscratch, long long joint_stride, long long out_stride) {
+                    float* __restrict__ djoint, double* __restrict__ gscratch, long long joint_stride, long long out_stride,
+                    long long slot_stride) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
     // one CTA per sub-head of a heads launch (gridDim.x = 1 and strides 0 otherwise); p_ij and gscratch are single-head only
@@ -301,7 +302,7 @@ iic_epilogue_kernel(const double* __restrict__ joint, int n_slots, int K, int pa
     // through peer memory); they are summed here in slot order, so every rank forms the identical global joint
     auto JV = [&](int i) {
         double t = joint[i];
-        for (int sl = 1; sl < n_slots; ++sl) t += joint[(size_t)sl * nj + i];
+        for (int sl = 1; sl < n_slots; ++sl) t += joint[(size_t)sl * slot_stride + i];
         return t;
     };
     double total = 1.0;
@@ -774,7 +775,7 @@ size_t iic_epilogue_workspace_bytes(int K, int pad) {
 
 static int iic_epilogue_impl(const double* joint, int n_slots, int K, int pad, int symmetric, float lamda, float eps, double n_pixels,
                              float* loss, float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes,
-                             cudaStream_t st, int n_heads, long long joint_stride, long long out_stride) {
+                             cudaStream_t st, int n_heads, long long joint_stride, long long out_stride, long long slot_stride = 0) {
     size_t smem = epilogue_scratch_doubles(K, pad) * sizeof(double);
     double* gscratch = nullptr;
     if (iic_epilogue_workspace_bytes(K, pad)) {
@@ -789,7 +790,8 @@ static int iic_epilogue_impl(const double* joint, int n_slots, int K, int pad, i
         attr.set(smem);
     }
     iic_epilogue_kernel<<<n_heads, EPI_THREADS, smem, st>>>(joint, n_slots, K, pad, symmetric, (double)lamda, (double)eps, n_pixels, loss,
-                                                            p00, p_ij, djoint, gscratch, joint_stride, out_stride);
+                                                            p00, p_ij, djoint, gscratch, joint_stride, out_stride,
+                                                            slot_stride > 0 ? slot_stride : (long long)K * K * (2 * pad + 1) * (2 * pad + 1));
     CY_CHECK_LAUNCH("iic_epilogue");
     return CY_OK;
 }
@@ -801,18 +803,19 @@ int iic_epilogue(const double* joint, int n_slots, int K, int pad, int symmetric
 }
 
 // n_heads epilogues in one launch (one CTA each): head s reads joint + s * joint_stride (doubles; [n_slots][nj] inside) and writes
-// loss / p00 / djoint + s * out_stride (floats).  Shapes whose arrays need the global scratch run head by head.
-int iic_epilogue_heads(const double* joint, long long joint_stride, int n_heads, int n_slots, int K, int pad, int symmetric, float lamda,
-                       float eps, double n_pixels, float* loss, float* p00, float* djoint, long long out_stride, void* workspace,
-                       size_t workspace_bytes, cudaStream_t st) {
+// loss / p00 / djoint + s * out_stride (floats); slot sl of a head lies slot_stride doubles further (0: K*K*T*T, slots back to
+// back).  Shapes whose arrays need the global scratch run head by head.
+int iic_epilogue_heads(const double* joint, long long joint_stride, long long slot_stride, int n_heads, int n_slots, int K, int pad,
+                       int symmetric, float lamda, float eps, double n_pixels, float* loss, float* p00, float* djoint, long long out_stride,
+                       void* workspace, size_t workspace_bytes, cudaStream_t st) {
     CY_CHECK_ARG(n_heads >= 1, "iic_epilogue_heads: n_heads=%d", n_heads);
     if (iic_epilogue_workspace_bytes(K, pad) == 0)
         return iic_epilogue_impl(joint, n_slots, K, pad, symmetric, lamda, eps, n_pixels, loss, p00, nullptr, djoint, nullptr, 0, st,
-                                 n_heads, joint_stride, out_stride);
+                                 n_heads, joint_stride, out_stride, slot_stride);
     for (int s = 0; s < n_heads; ++s) {
         const int rc = iic_epilogue_impl(joint + s * joint_stride, n_slots, K, pad, symmetric, lamda, eps, n_pixels, loss + s * out_stride,
                                          p00 + s * out_stride, nullptr, djoint ? djoint + s * out_stride : nullptr, workspace,
-                                         workspace_bytes, st, 1, 0, 0);
+                                         workspace_bytes, st, 1, 0, 0, slot_stride);
         if (rc != CY_OK) return rc;
     }
     return CY_OK;

@@ -229,7 +229,7 @@ class _IIDSegMultiFunction(torch.autograd.Function):
     softmax backward in its epilogue (cy_iic_bwd_logits_heads) — dL/dp is never written to memory."""
 
     @staticmethod
-    def forward(ctx, padding, symmetric, lamda, eps, temperature, *maps):
+    def forward(ctx, padding, symmetric, lamda, eps, temperature, reduce_joint, *maps):
         lib = L.lib()
         if temperature is not None:
             maps = softmax_with_t(maps, temperature)
@@ -242,7 +242,6 @@ class _IIDSegMultiFunction(torch.autograd.Function):
         if x0.device.index != torch.cuda.current_device():
             torch.cuda.set_device(x0.device)      # (rare) model on a non-current device: make it current for the launches
         buf = torch.empty(S, per, dtype=torch.float32, device=x0.device)
-        joints = torch.empty(S, nj, dtype=torch.float64, device=x0.device)      # raw joints stay in double (contrastyou_b200.h)
         st = L.stream_ptr(x0.device)
         ws_bytes = lib.cy_iic_workspace_bytes(B, K, H, W, padding)
         ews_bytes = lib.cy_iic_epilogue_workspace_bytes(K, padding)
@@ -254,10 +253,20 @@ class _IIDSegMultiFunction(torch.autograd.Function):
         xs = (ctypes.c_void_p * S)(*[maps[2 * s].data_ptr() for s in range(S)])
         ys = (ctypes.c_void_p * S)(*[maps[2 * s + 1].data_ptr() for s in range(S)])
         ws = _workspace(S * ws_bytes, x0.device, st)
-        L.check(lib.cy_iic_joint_heads(xs, ys, S, dt, B, K, H, W, padding, joints.data_ptr(), nj, ws.data_ptr(), S * ws_bytes, st),
-                "cy_iic_joint_heads")
-        L.check(lib.cy_iic_epilogue_heads(joints.data_ptr(), nj, S, 1, K, padding, int(bool(symmetric)), float(lamda), float(eps),
-                                          float(B * H * W), base, base + 4, base + 4 * (1 + K * K), per, L.ptr(ews), ews_bytes, st),
+
+        def joints_into(out):                     # out: [S, K, K, T, T] float64, contiguous
+            L.check(lib.cy_iic_joint_heads(xs, ys, S, dt, B, K, H, W, padding, out.data_ptr(), nj, ws.data_ptr(), S * ws_bytes, st),
+                    "cy_iic_joint_heads")
+        n_pixels, n_slots = float(B * H * W), 1
+        if reduce_joint is None:
+            joints = torch.empty(S, nj, dtype=torch.float64, device=x0.device)      # raw joints stay in double (contrastyou_b200.h)
+            joints_into(joints)
+        else:
+            # batch-sharded: the stack of S partial joints is exchanged as ONE array — per-rank slots [world][S][K,K,T,T] in peer
+            # memory (summed by the epilogue in rank order) or one in-place NCCL all-reduce
+            joints, n_slots, n_pixels = reduce_joint(joints_into, (S, K, K, T, T), n_pixels, x0.device)
+        L.check(lib.cy_iic_epilogue_heads(joints.data_ptr(), nj, S * nj, S, n_slots, K, padding, int(bool(symmetric)), float(lamda),
+                                          float(eps), n_pixels, base, base + 4, base + 4 * (1 + K * K), per, L.ptr(ews), ews_bytes, st),
                 "cy_iic_epilogue_heads")
         ctx.save_for_backward(buf, *maps)
         ctx.cfg = (padding, S, K, T, per, temperature)
@@ -287,7 +296,7 @@ class _IIDSegMultiFunction(torch.autograd.Function):
         else:
             L.check(lib.cy_iic_bwd_logits_heads(xs, ys, S, dt, B, K, H, W, padding, dj, per, gscale.data_ptr(), float(temperature),
                                                 dxs, dys, st), "cy_iic_bwd_logits_heads")
-        return (None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, *grads)
 
 
 class IIDSegmentationLoss(nn.Module):
@@ -332,13 +341,9 @@ class IIDSegmentationLoss(nn.Module):
             x, y = _check_pair(x, y)
             assert x.shape == x_outs[0].shape and x.dtype == x_outs[0].dtype, "sub-heads must share shape and dtype"
             maps += [x, y]
-        if self._reduce_joint is not None:      # sharded batches need the joint all-reduce between the two kernels
-            if logits_T is not None:
-                x_outs = [torch.softmax(x / logits_T, 1) for x in x_outs]
-                x_tf_outs = [torch.softmax(y / logits_T, 1) for y in x_tf_outs]
-            return sum(self(x, y) for x, y in zip(x_outs, x_tf_outs)) / len(x_outs)
+        # (a criterion sharded with shard_iic_loss exchanges the whole stack of partial joints between the two kernels)
         loss, p00 = _IIDSegMultiFunction.apply(int(self.padding), bool(self.symmetric), float(self.lamda), float(self._eps),
-                                               None if logits_T is None else float(logits_T), *maps)
+                                               None if logits_T is None else float(logits_T), self._reduce_joint, *maps)
         self.__dict__["_p_i_j"] = p00      # (plain attribute; Module.__setattr__ costs ~5 us of type checks per step)
         return loss
 

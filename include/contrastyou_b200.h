@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CY_ABI_VERSION 6
+#define CY_ABI_VERSION 7
 
 /* element types of embeddings / probability maps */
 #define CY_F32 0
@@ -226,12 +226,15 @@ int cy_iic_bwd(const void* x, const void* y, int dtype, int B, int K, int H, int
  * (floats) and djoint + s*djoint_stride.  One joint launch + one reduction launch, one epilogue launch (a CTA per head) and one
  * adjoint launch when the tensor-core kernels take the shape (heads in chunks of 8); otherwise they run head by head through
  * the single-head entry points — results are identical to n_heads single-head calls either way.
- * Workspace of cy_iic_joint_heads: n_heads * cy_iic_workspace_bytes().  cy_iic_epilogue_heads has no p_ij output. */
+ * Workspace of cy_iic_joint_heads: n_heads * cy_iic_workspace_bytes().  cy_iic_epilogue_heads has no p_ij output; slot sl of head s
+ * (multi-GPU: rank sl's partial joint) lies at joint + s*joint_stride + sl*slot_stride, slot_stride = 0 meaning K*K*T*T (slots back
+ * to back) — the peer-memory exchange lays the stack out as [world][n_heads][K,K,T,T], i.e. joint_stride = K*K*T*T and slot_stride =
+ * n_heads*K*K*T*T. */
 int cy_iic_joint_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
                        double* joint, long long joint_stride, void* workspace, size_t workspace_bytes, void* stream);
-int cy_iic_epilogue_heads(const double* joint, long long joint_stride, int n_heads, int n_slots, int K, int pad, int symmetric,
-                          float lamda, float eps, double n_pixels, float* loss, float* p00, float* djoint, long long out_stride,
-                          void* workspace, size_t workspace_bytes, void* stream);
+int cy_iic_epilogue_heads(const double* joint, long long joint_stride, long long slot_stride, int n_heads, int n_slots, int K, int pad,
+                          int symmetric, float lamda, float eps, double n_pixels, float* loss, float* p00, float* djoint,
+                          long long out_stride, void* workspace, size_t workspace_bytes, void* stream);
 int cy_iic_bwd_heads(const void* const* xs, const void* const* ys, int n_heads, int dtype, int B, int K, int H, int W, int pad,
                      const float* djoint, long long djoint_stride, const float* gscale, void* const* dxs, void* const* dys,
                      void* stream);

@@ -80,6 +80,34 @@ def main():
         ok &= good
         print(f"[rank {rank}] iic pad={pad} sym={sym}: loss {loss.item():.7f} ref {ref.item():.7f} rel {e_loss:.2e} "
               f"grad rel {e_grad:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    # the sub-head stack under sharding: forward_heads exchanges ALL heads' partial joints as one array ([world][S][K,K,T,T]
+    # peer slots, or one NCCL all-reduce) and must equal the mean of single-process criteria on the gathered batches; from
+    # probabilities and from logits (fused SoftmaxWithT)
+    S = 3
+    lx = [2 * torch.randn(Bt, K, H, W, generator=g) for _ in range(S)]
+    ly = [2 * torch.randn(Bt, K, H, W, generator=g) for _ in range(S)]
+    for exchange in ("auto", "nccl"):
+        for from_logits in (False, True):
+            crit = cyd.shard_iic_loss(IIDSegmentationLoss(padding=1), exchange=exchange)
+            loc_x = [t[sl].to(dev).requires_grad_() for t in lx]
+            loc_y = [t[sl].to(dev).requires_grad_() for t in ly]
+            if from_logits:
+                loss = crit.forward_heads(loc_x, loc_y, logits_T=0.5)
+            else:
+                loss = crit.forward_heads([t.softmax(1) for t in loc_x], [t.softmax(1) for t in loc_y])
+            loss.backward()
+            X = [t.to(dev).requires_grad_() for t in lx]
+            Y = [t.to(dev).requires_grad_() for t in ly]
+            Tm = 0.5 if from_logits else 1.0
+            plain = IIDSegmentationLoss(padding=1)
+            ref = sum(plain(torch.softmax(a / Tm, 1), torch.softmax(b / Tm, 1)) for a, b in zip(X, Y)) / S
+            ref.backward()
+            e_loss = abs(loss.item() - ref.item()) / abs(ref.item())
+            e_grad = max(((a.grad - A.grad[sl]).abs().max() / A.grad.abs().max()).item() for a, A in zip(loc_x + loc_y, X + Y))
+            good = e_loss < 1e-4 and e_grad < 1e-4
+            ok &= good
+            print(f"[rank {rank}] iic forward_heads S={S} exchange={exchange} logits={from_logits}: loss {loss.item():.7f} ref "
+                  f"{ref.item():.7f} rel {e_loss:.2e} grad rel {e_grad:.2e} {'OK' if good else 'FAIL'}", flush=True)
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

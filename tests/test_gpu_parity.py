@@ -748,7 +748,7 @@ def test_iic_heads_entry_points_equal_single_head_calls(S, B, K, H, W, pad):
     ewb = lib.cy_iic_epilogue_workspace_bytes(K, pad)
     ews = torch.empty(max(ewb, 1), dtype=torch.uint8, device=DEV)
     base = out.data_ptr()
-    L.check(lib.cy_iic_epilogue_heads(single.data_ptr(), nj, S, 1, K, pad, 1, 1.5, 1e-5, float(B * H * W), base, base + 4,
+    L.check(lib.cy_iic_epilogue_heads(single.data_ptr(), nj, 0, S, 1, K, pad, 1, 1.5, 1e-5, float(B * H * W), base, base + 4,
                                       base + 4 * (1 + K * K), per, ews.data_ptr(), ewb, st), "cy_iic_epilogue_heads")
     ref = torch.zeros(S, per, device=DEV)
     for s in range(S):
@@ -756,6 +756,20 @@ def test_iic_heads_entry_points_equal_single_head_calls(S, B, K, H, W, pad):
         L.check(lib.cy_iic_epilogue(single[s].data_ptr(), 1, K, pad, 1, 1.5, 1e-5, float(B * H * W), b, b + 4, None, b + 4 * (1 + K * K),
                                     ews.data_ptr(), ewb, st), "cy_iic_epilogue")
     assert torch.equal(out, ref)
+    # multi-GPU layout [slots 3][S][nj] (every rank's stack of partial joints): the heads launch sums a head's slots like the
+    # single-head call sums its [3][nj] array
+    slots = torch.stack([single * w for w in (0.5, 0.25, 0.25)]).contiguous()          # [3, S, nj]
+    out3 = torch.zeros(S, per, device=DEV)
+    L.check(lib.cy_iic_epilogue_heads(slots.data_ptr(), nj, S * nj, S, 3, K, pad, 1, 1.5, 1e-5, float(B * H * W), out3.data_ptr(),
+                                      out3.data_ptr() + 4, out3.data_ptr() + 4 * (1 + K * K), per, ews.data_ptr(), ewb, st),
+            "cy_iic_epilogue_heads")
+    ref3 = torch.zeros(S, per, device=DEV)
+    for s in range(S):
+        b = ref3[s].data_ptr()
+        one_head = slots[:, s].contiguous()                                            # [3, nj]
+        L.check(lib.cy_iic_epilogue(one_head.data_ptr(), 3, K, pad, 1, 1.5, 1e-5, float(B * H * W), b, b + 4, None,
+                                    b + 4 * (1 + K * K), ews.data_ptr(), ewb, st), "cy_iic_epilogue")
+    assert torch.equal(out3, ref3)
     # adjoint
     dj = torch.randn(S, nj + 7, device=DEV)
     g = torch.full((1,), 0.37, device=DEV)
@@ -832,6 +846,26 @@ def test_softmax_with_t_matches_torch(n, B, K, H, W, T, dtype):
         tol = 2e-6 if dtype == torch.float32 else (4e-3 if dtype == torch.bfloat16 else 6e-4)
         assert float((p.float() - ref).abs().max()) <= tol
         assert float((p.float().sum(1) - 1).abs().max()) <= (1e-5 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("K,dtype,tol", [(20, torch.float32, 2e-5), (10, torch.bfloat16, 3e-2), (5, torch.float16, 5e-3)])
+def test_iic_logits_path_other_kernels(K, dtype, tol):
+    """forward_logits where the tcgen05 adjoint does not apply (K > 16, 16-bit maps): cy_softmax_t_fwd's scalar kernel, the
+    other adjoint kernels and the in-place softmax-backward kernel behind them, vs the same computation in float32 torch"""
+    torch.manual_seed(K)
+    B, H, W, T = 2, 24, 32, 0.9
+    lx = (2 * torch.randn(B, K, H, W, device=DEV)).to(dtype).requires_grad_()
+    ly = (2 * torch.randn(B, K, H, W, device=DEV)).to(dtype).requires_grad_()
+    crit = IIDSegmentationLoss(padding=1)
+    loss = crit.forward_logits(lx, ly, T=T)
+    loss.backward()
+    rx, ry = lx.detach().float().requires_grad_(), ly.detach().float().requires_grad_()
+    ref = crit(torch.softmax(rx / T, 1), torch.softmax(ry / T, 1))
+    ref.backward()
+    assert lx.grad.dtype == dtype
+    assert loss.item() == pytest.approx(ref.item(), rel=max(tol, 1e-5))
+    assert _relerr(lx.grad.float().cpu().numpy(), rx.grad.cpu().numpy()) <= tol
+    assert _relerr(ly.grad.float().cpu().numpy(), ry.grad.cpu().numpy()) <= tol
 
 
 def test_iic_mma_sync_adjoint_still_agrees():
