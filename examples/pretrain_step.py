@@ -79,13 +79,15 @@ class PretrainModel(nn.Module):
 
     def forward(self, x):
         conv5, up2 = self.net(x)
-        return self.infonce_head(conv5), self.mi_head(up2)
+        # fused_softmax: the cluster head stops before SoftmaxWithT and the criterion takes the logits (forward_heads(..., logits_T))
+        return self.infonce_head(conv5), self.mi_head(up2, skip_softmax=getattr(self, "fused_softmax", False))
 
 
 def ddp_gradient_check(model, fwd, infonce, mi, mi_scale, img, img_tf, labels, dev, rank, world):
     """one fp32 backward through DDP with the global-batch criteria vs a single-process backward on the concatenated batch
     of all ranks, same weights, BatchNorm in eval mode.  Returns the max relative parameter-gradient error (over ranks)."""
     model.eval()
+    fused, model.fused_softmax = getattr(model, "fused_softmax", False), False      # the check compares the plain modules
     x = torch.cat((img.to(dev), img_tf.to(dev)))
     model.zero_grad(set_to_none=True)
     z, probs = fwd(x)
@@ -127,6 +129,7 @@ def ddp_gradient_check(model, fwd, infonce, mi, mi_scale, img, img_tf, labels, d
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     model.zero_grad(set_to_none=True)
     model.train()
+    model.fused_softmax = fused
     return {"global_grad_rel_err": float(t[1]), "max_param_grad_rel_err": float(t[0]), "worst_param": worst_name,
             "loss_abs_diff": float(t[2]), "ok": bool(t[1] < 1e-3)}
 
@@ -142,6 +145,9 @@ def main():
     ap.add_argument("--subheads", type=int, default=5)
     ap.add_argument("--no-amp", action="store_true")
     ap.add_argument("--batched-heads", action="store_true", help="IIDSegmentationLoss.forward_heads instead of the python sum")
+    ap.add_argument("--fused-softmax", action="store_true",
+                    help="cluster head returns logits; SoftmaxWithT runs inside the criterion (one streaming launch forward, "
+                         "backward in the IIC adjoint's epilogue); implies --batched-heads")
     ap.add_argument("--local-criteria", action="store_true", help="under DDP: per-rank criteria (no exchange), as the reference would run")
     ap.add_argument("--check", action="store_true", help="DDP global-batch gradients == single-process gradients on the concatenated batch")
     args = ap.parse_args()
@@ -156,6 +162,8 @@ def main():
     torch.manual_seed(0)
 
     model = PretrainModel(args.max_channel, args.clusters, args.subheads).to(dev)
+    model.fused_softmax = bool(args.fused_softmax)
+    mi_temperature = float(model.mi_head.temperature)
     fwd = nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if world > 1 else model
     global_batch = world > 1 and not args.local_criteria
     if global_batch:
@@ -189,7 +197,9 @@ def main():
             loss_nce = infonce(z1, z2, target=labels)
             # --- discrete-MI hook (discretemi.py:99-113): sub-head list, chunk, mean of the criterion over the heads
             pairs = [torch.chunk(p.float(), 2, 0) for p in probs]
-            if args.batched_heads:
+            if args.fused_softmax:
+                loss_mi = mi.forward_heads([a for a, _ in pairs], [b for _, b in pairs], logits_T=mi_temperature)
+            elif args.batched_heads:
                 loss_mi = mi.forward_heads([a for a, _ in pairs], [b for _, b in pairs])
             else:
                 loss_mi = sum(mi(a, b) for a, b in pairs) / len(pairs)
@@ -230,7 +240,8 @@ def main():
             "n_gpus": world, "ms_per_step": ms, "criteria_fwd_ms_per_step": t_crit[0] / args.steps,
             "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / args.steps, "amp": amp,
             "config": {"images_per_rank": 2 * n_img, "size": args.size, "max_channel": args.max_channel,
-                       "clusters": args.clusters, "subheads": args.subheads, "padding": 1},
+                       "clusters": args.clusters, "subheads": args.subheads, "padding": 1,
+                       "iic_heads": "fused softmax (logits)" if args.fused_softmax else ("batched" if args.batched_heads else "python loop")},
             "criteria": "global-batch (row-sharded InfoNCE + batch-sharded IIC)" if global_batch else "per-rank",
             "ddp_gradient_check": check,
             "last_losses": {"infonce": meters[0], "discrete_mi": meters[1]}, "data": "synthetic"}))
