@@ -559,7 +559,7 @@ def main():
     roofline = {"bound": "tensor", "kernel": "cy_infonce_bwd (recompute S tile + W.Z, 4*rows*N*d FLOP per launch)",
                 "achieved": bwd_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": bwd_tf / peak_tf,
                 # DRAM bytes per launch from the committed ncu capture of this exact workload (1 GPU, N=65536)
-                "traffic": traffic.get("infonce_bwd_tc_kernel<0> N=65536 d=256 bf16", {}).get("bytes")
+                "traffic": traffic.get("infonce_bwd_tc_kernel<256,0,0,0> N=65536 d=256 bf16", {}).get("bytes")
                 if (world == 1 and N == 65536 and path != 1) else None,
                 "peak_source": peaks["source"] + " bf16 burst",
                 "fwd": {"kernel": "cy_infonce_fwd (2*rows*N*d FLOP)", "ms": fwd_ms, "achieved": fwd_tf, "frac": fwd_tf / peak_tf},
