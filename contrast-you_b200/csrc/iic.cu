@@ -236,7 +236,6 @@ static int launch_reduce_partials(const float* partials, int n_partials, int nj,
     if (e != cudaSuccess) { set_error("iic_reduce_partials: %s", cudaGetErrorString(e)); return (int)e; }
     return CY_OK;
 }
-static inline int reduce_grid(int nj) { return (nj + 31) / 32; }
 
 __device__ double block_reduce_sum(double v, double* red) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

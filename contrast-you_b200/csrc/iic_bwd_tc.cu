@@ -613,7 +613,6 @@ template <int KH>
 int launch_bwd_tc(const TcPtrs& ptrs, const TcGeom& g, const float* djoint, const float* gscale, cudaStream_t st) {
     // one CTA per SM: the register file (>= 52 registers x 896 threads) does not hold two, so the 512-column TMEM allocation
     // never waits for a co-resident CTA
-    constexpr int KS = (3 * KH + 7) / 8;
     size_t smem = tc_smem_bytes(KH, g.S, g.inv_T != 0.f);
     auto k = iic_bwd_tc_kernel<KH>;
     static SmemAttrCache attr;

@@ -668,7 +668,6 @@ bool fwd_geom(int B, int K, int H, int W, int pad, MmaGeom* g, int* mt, int* ntw
     g->HH = g->BH + 2 * pad;
     g->CO = 4;
     g->n_combo = nc;
-    const int nj = K * K * T * T;
     const size_t budget = (*nsplit == 1) ? 113 * 1024 : 225 * 1024;
     // widest tile (fewest barrier rounds) that does not waste columns and still leaves a 2-deep ring
     const int first = pick_tw(W);

@@ -70,7 +70,7 @@ __device__ __forceinline__ void ffma2_u(u64& d, const u64 a, const u64 b) {
 #endif
 }
 __device__ __forceinline__ u64 pack_hi_lo(const u64 left, const u64 right) {     // (hi half of left, lo half of right)
-    uint32_t l0, l1, r0, r1;
+    [[maybe_unused]] uint32_t l0, l1, r0, r1;      // (l0 and r1 are only sinks of the unpacking moves)
     asm("mov.b64 {%0, %1}, %2;" : "=r"(l0), "=r"(l1) : "l"(left));
     asm("mov.b64 {%0, %1}, %2;" : "=r"(r0), "=r"(r1) : "l"(right));
     u64 o;
