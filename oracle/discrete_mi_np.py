@@ -115,6 +115,32 @@ def iid_segmentation_loss(x, y, *, lamda=1.0, padding=0, eps=1e-5, symmetric=Fal
     return dict(loss=loss, grad_x=gx, grad_y=gy, joint=P[0][0], p_i_j=P, raw_joint=J, grad_raw_joint=gJ)
 
 
+def softmax_with_t(logits, T=1.0, dtype=np.float64):
+    """SoftmaxWithT.forward (contrastyou/projectors/nn.py:36-44): ``input /= T`` then softmax over dim 1."""
+    z = np.asarray(logits, dtype=dtype) / T
+    z = z - z.max(axis=1, keepdims=True)
+    e = np.exp(z)
+    return e / e.sum(axis=1, keepdims=True)
+
+
+def iid_segmentation_loss_from_logits(logits_x, logits_y, T=1.0, **kw):
+    """The discrete-MI hook's criterion call on a cluster head's sub-heads (semi_seg/hooks/discretemi.py:106-111:
+    ``sum(criterion(x1, x2) for x1, x2 in zip(prob1, prob2)) / len(prob1)``) with the heads' SoftmaxWithT tail
+    (projectors/nn.py:36-44; heads.py:64-70) made explicit: logits_x / logits_y are sequences of S maps [B,K,H,W].
+
+    returns dict(loss, grad_x [S,...], grad_y [S,...]) — gradients w.r.t. the LOGITS: dL/dz = p * (g - sum_k p_k g_k) / T."""
+    S = len(logits_x)
+    loss, gxs, gys = 0.0, [], []
+    for lx, ly in zip(logits_x, logits_y):
+        px, py = softmax_with_t(lx, T), softmax_with_t(ly, T)
+        r = iid_segmentation_loss(px, py, **kw)
+        loss += r["loss"] / S
+        for p, g, out in ((px, r["grad_x"], gxs), (py, r["grad_y"], gys)):
+            g = g / S
+            out.append(p * (g - (p * g).sum(axis=1, keepdims=True)) / T)
+    return dict(loss=loss, grad_x=np.stack(gxs), grad_y=np.stack(gys))
+
+
 def compute_joint(x, y, symmetric=True):
     """discreteMI.py:201-222 — J = sum_b x_b y_b^T, optional symmetrise, normalise to mass 1."""
     J = np.einsum("bi,bj->ij", x, y)

@@ -148,6 +148,28 @@ def iic_case(name, B, K, H, W, seed, *, padding, symmetric=False, lamda=1.0, eps
     return loss.item()
 
 
+def logits_case(name, S, B, K, H, W, seed, *, T, padding, symmetric=False):
+    """the cluster-head tail + the discrete-MI hook's criterion call, run by the reference itself: ``SoftmaxWithT(1, T)``
+    (projectors/nn.py:36-44) on S pairs of logits, then ``sum(criterion(x1, x2) ...) / S`` (semi_seg/hooks/discretemi.py:111);
+    gradients w.r.t. the LOGITS.  Pins IIDSegmentationLoss.forward_heads(..., logits_T=T)."""
+    from contrastyou.losses.discreteMI import IIDSegmentationLoss
+    from contrastyou.projectors.nn import SoftmaxWithT
+    g = torch.Generator().manual_seed(seed)
+    lx = [(2 * torch.randn(B, K, H, W, dtype=torch.float64, generator=g)).requires_grad_() for _ in range(S)]
+    ly = [(2 * torch.randn(B, K, H, W, dtype=torch.float64, generator=g)).requires_grad_() for _ in range(S)]
+    tail = SoftmaxWithT(1, T=T)
+    crit = IIDSegmentationLoss(padding=padding, symmetric=symmetric)
+    # the tail divides in place (nn.py:43): feed non-leaf copies, as the 1x1 conv output is in the reference
+    loss = sum(crit(tail(a * 1.0), tail(b * 1.0)) for a, b in zip(lx, ly)) / S
+    loss.backward()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), logits_x=np.stack([_np(t) for t in lx]),
+                        logits_y=np.stack([_np(t) for t in ly]), loss=_np(loss), grad_x=np.stack([_np(t.grad) for t in lx]),
+                        grad_y=np.stack([_np(t.grad) for t in ly]), T=np.float64(T), padding=np.int64(padding),
+                        symmetric=np.bool_(symmetric))
+    print(f"{name}: loss={loss.item()!r} sum|glx0|={lx[0].grad.abs().sum().item()!r}")
+    return loss.item()
+
+
 def iid_case(name, bn, K, seed, lamb=1.0):
     from contrastyou.losses.discreteMI import IIDLoss
     g = torch.Generator().manual_seed(seed)
@@ -309,9 +331,22 @@ def region_cases():
     print("regions:", [len(c["coords"]) for c in cases])
 
 
+def logits_cases():
+    logits_case("logits_iic_pad1_T05", 2, 2, 10, 12, 16, 40, T=0.5, padding=1)
+    logits_case("logits_iic_pad1_sym_T2", 2, 2, 6, 12, 16, 41, T=2.0, padding=1, symmetric=True)
+    logits_case("logits_iic_pad0_T1", 2, 3, 5, 8, 8, 42, T=1.0, padding=0)
+
+
 def main():
     scratch = _import_reference()
     known = {}
+    if "--only-logits" in sys.argv:      # added after the other fixtures: regenerate these alone
+        try:
+            logits_cases()
+        finally:
+            sys.path.remove(scratch)
+            shutil.rmtree(scratch, ignore_errors=True)
+        return
     try:
         # --- SupConLoss1 (contrastive.py:23-100)
         # survey-time known answers: torch.manual_seed(0) global stream
@@ -368,6 +403,7 @@ def main():
         # --- IIDLoss (discreteMI.py:90-124, 201-222)
         iid_case("iid_k20", 18, 20, 30)
         iid_case("iid_k5_lam2", 7, 5, 31, lamb=2.0)
+        logits_cases()
         sibling_cases()
         label_cases()
         region_cases()

@@ -868,6 +868,23 @@ def test_iic_logits_path_other_kernels(K, dtype, tol):
     assert _relerr(ly.grad.float().cpu().numpy(), ry.grad.cpu().numpy()) <= tol
 
 
+@pytest.mark.parametrize("name", ["logits_iic_pad1_T05", "logits_iic_pad1_sym_T2", "logits_iic_pad0_T1"])
+def test_iic_from_logits_golden(name):
+    """forward_heads(..., logits_T=T) against the fixture the REFERENCE produced (its SoftmaxWithT tail + the hook's sub-head mean
+    of IIDSegmentationLoss, float64, gradients w.r.t. the logits): cy_softmax_t_fwd + the heads kernels + the fused softmax
+    backward, at the fp32 bar"""
+    g = load_golden(name)
+    lx = [_t(a, grad=True) for a in g["logits_x"]]
+    ly = [_t(a, grad=True) for a in g["logits_y"]]
+    crit = IIDSegmentationLoss(padding=int(g["padding"]), symmetric=bool(g["symmetric"]))
+    loss = crit.forward_heads(lx, ly, logits_T=float(g["T"]))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= FP32_TOL * abs(float(g["loss"]))
+    for s_, (a, b) in enumerate(zip(lx, ly)):
+        assert _relerr(a.grad.cpu().numpy(), g["grad_x"][s_]) <= FP32_TOL
+        assert _relerr(b.grad.cpu().numpy(), g["grad_y"][s_]) <= FP32_TOL
+
+
 def test_iic_mma_sync_adjoint_still_agrees():
     """CY_IIC_TC=0 pins the round-1 mma.sync adjoint (csrc/iic_mma.cu), kept for A/B timing: it must return what the tcgen05
     adjoint returns (the switch is read once per process, hence the subprocess)"""

@@ -93,6 +93,21 @@ def test_iic_golden(name):
         np.testing.assert_allclose(o[k], g[k], rtol=0, atol=np.abs(g[k]).max() * 1e-8)
 
 
+IIC_LOGITS = ["logits_iic_pad1_T05", "logits_iic_pad1_sym_T2", "logits_iic_pad0_T1"]
+
+
+@pytest.mark.parametrize("name", IIC_LOGITS)
+def test_iic_from_logits_golden(name):
+    """the reference's own SoftmaxWithT tail + sub-head mean of IIDSegmentationLoss, gradients w.r.t. the logits
+    (tests/golden/make_golden.py logits_case): pins oracle.discrete_mi_np.iid_segmentation_loss_from_logits"""
+    g = load_golden(name)
+    o = M.iid_segmentation_loss_from_logits(list(g["logits_x"]), list(g["logits_y"]), float(g["T"]), padding=int(g["padding"]),
+                                            symmetric=bool(g["symmetric"]))
+    assert o["loss"] == pytest.approx(float(g["loss"]), rel=1e-10, abs=1e-14)
+    for k in ("grad_x", "grad_y"):
+        np.testing.assert_allclose(o[k], g[k], rtol=0, atol=np.abs(g[k]).max() * 1e-8)
+
+
 def test_iic_negative_padding_raises():
     g = load_golden("iic_pad1")
     with pytest.raises(ValueError):
