@@ -237,16 +237,40 @@ static int launch_reduce_partials(const float* partials, int n_partials, int nj,
     return CY_OK;
 }
 
-__device__ double block_reduce_sum(double v, double* red) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+// Block-wide reductions of the one-CTA epilogue, two butterfly levels (lanes, then the <= 32 warp totals re-read by every warp): the
+// kernel is a chain of ~15 dependent phases whose cost is instruction latency per warp, so the second level is 5 shuffle steps,
+// not a 32-long serial chain of shared-memory adds.  Fixed order: bitwise reproducible.  red: 64 doubles.
+__device__ __noinline__ double block_reduce_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
+    __syncthreads();                     // (the previous use of red is over)
     if (lane == 0) red[w] = v;
     __syncthreads();
-    double t = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    double t = lane < nw ? red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     return t;
+}
+
+// two sums at once (same barriers)
+__device__ __noinline__ void block_reduce_sum2(double& a, double& b, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    __syncthreads();
+    if (lane == 0) { red[w] = a; red[32 + w] = b; }
+    __syncthreads();
+    a = lane < nw ? red[lane] : 0.0;
+    b = lane < nw ? red[32 + lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
 }
 
 // sum of v[0..n) by one warp (fixed order per lane, then a butterfly): every lane returns the total
@@ -258,19 +282,27 @@ __device__ __forceinline__ double warp_sum_n(const double* v, int n, int lane) {
     return s;
 }
 
-__device__ double block_reduce_min(double v, double* red) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+__device__ __noinline__ double block_reduce_min(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     __syncthreads();
     if (lane == 0) red[w] = v;
     __syncthreads();
-    double t = red[0];
-    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) t = fmin(t, red[i]);
+    double t = lane < nw ? red[lane] : red[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = fmin(t, __shfl_xor_sync(0xffffffffu, t, o));
     return t;
 }
 
-// dynamic smem: double A[nj] (B matrix, [dd][k1][k2]), P[nj], G[nj], sdisp[TT], colsum[TT*K], rowsum[TT*K]
+// One copy each of the long fp64 sequences (log ~100 instructions, division ~40): the epilogue is ONE CTA that runs straight-line
+// code once, and ncu showed it waiting for instruction fetch as much as for anything else (58 k warp instructions in 20 us,
+// "no instruction" the second largest stall) — inlining six logs and eight divisions made the kernel mostly cold code.
+__device__ __noinline__ double ep_log(double v) { return log(v); }
+__device__ __noinline__ double ep_div(double a, double b) { return a / b; }
+
+// dynamic smem: double A[nj] (B matrix, [dd][k1][k2]), P[nj], G[nj], sdisp[TT], colsum[TT*K], rowsum[TT*K], then the marginals'
+// log(m + eps) and m / (m + eps) for both ([4][TT*K]): computed once per marginal instead of once per joint entry
 constexpr int EPI_THREADS = 1024;
 __global__ void __launch_bounds__(EPI_THREADS)
 iic_epilogue_kernel(const double* __restrict__ joint, int n_slots, int K, int pad, int symmetric, double lamda, double eps,
@@ -278,7 +310,7 @@ iic_epilogue_kernel(const double* __restrict__ joint, int n_slots, int K, int pa
                     float* __restrict__ djoint, double* __restrict__ gscratch, long long joint_stride, long long out_stride,
                     long long slot_stride) {
     extern __shared__ __align__(16) double sm[];
-    __shared__ double red[32];
+    __shared__ double red[64];
     // one CTA per sub-head of a heads launch (gridDim.x = 1 and strides 0 otherwise); p_ij and gscratch are single-head only
     joint += (size_t)blockIdx.x * joint_stride;
     loss += (size_t)blockIdx.x * out_stride;
@@ -292,7 +324,20 @@ iic_epilogue_kernel(const double* __restrict__ joint, int n_slots, int K, int pa
     double* sd = G + nj;
     double* asum = sd + TT;        // [TT][K]  sum over k1 -> function of k2 ("p_i_mat", dim 2)
     double* bsum = asum + TT * K;  // [TT][K]  sum over k2 -> function of k1 ("p_j_mat", dim 3)
+    double* la = bsum + TT * K;    // log(asum + eps), asum / (asum + eps), and the same for bsum
+    double* ra = la + TT * K;
+    double* lb = ra + TT * K;
+    double* rb = lb + TT * K;
     const int tid = threadIdx.x, nt = blockDim.x;
+    // index splits by the runtime K / T: floor(n / d) = int((n + 0.5) * (1 / d)) is exact in fp32 for n < 2^22 (the host checks
+    // K*K*T*T against it) and three instructions instead of the ~25 of an integer division, of which there were 20 per thread
+    const float invK = 1.f / (float)K, invTT = 1.f / (float)TT, invKK = 1.f / (float)KK;
+    auto qK = [&](int n) { return __float2int_rz(((float)n + 0.5f) * invK); };
+    auto qTT = [&](int n) { return __float2int_rz(((float)n + 0.5f) * invTT); };
+    auto qKK = [&](int n) { return __float2int_rz(((float)n + 0.5f) * invKK); };
+    // i -> (k1, k2, dd) for the external layout [k1][k2][dd] and for the internal layout [dd][k1][k2]
+    auto split_ext = [&](int i, int& k1, int& k2, int& dd) { const int t = qTT(i); dd = i - t * TT; k1 = qK(t); k2 = t - k1 * K; };
+    auto split_int = [&](int i, int& k1, int& k2, int& dd) { dd = qKK(i); const int t = qK(i); k2 = i - t * K; k1 = t - dd * K; };
     // joint is [k1][k2][dd]; internal layout [dd][k1][k2]
     auto JIDX = [&](int k1, int k2, int dd) { return (k1 * K + k2) * TT + dd; };
     auto PIDX = [&](int dd, int k1, int k2) { return (dd * K + k1) * K + k2; };
@@ -301,80 +346,101 @@ iic_epilogue_kernel(const double* __restrict__ joint, int n_slots, int K, int pa
     // through peer memory); they are summed here in slot order, so every rank forms the identical global joint
     auto JV = [&](int i) {
         double t = joint[i];
+        #pragma unroll 1
         for (int sl = 1; sl < n_slots; ++sl) t += joint[(size_t)sl * slot_stride + i];
         return t;
     };
     double total = 1.0;
     if (pad > 0) {
         double mn = 1e300;
+        #pragma unroll 1
         for (int i = tid; i < nj; i += nt) mn = fmin(mn, JV(i));
         mn = block_reduce_min(mn, red);
+        #pragma unroll 1
         for (int i = tid; i < nj; i += nt) {
-            const int dd = i % TT, k2 = (i / TT) % K, k1 = i / (TT * K);
+            int k1, k2, dd;
+            split_ext(i, k1, k2, dd);
             Bm[PIDX(dd, k1, k2)] = JV(i) - mn + 1e-8;
         }
         __syncthreads();
+        #pragma unroll 1
         for (int dd = warp; dd < TT; dd += nwarp) {          // one warp per displacement
             const double s = warp_sum_n(Bm + dd * KK, KK, lane);
             if (lane == 0) sd[dd] = s;
         }
         __syncthreads();
-        for (int i = tid; i < nj; i += nt) Bm[i] /= sd[i / KK];
+        #pragma unroll 1
+        for (int i = tid; i < nj; i += nt) Bm[i] = ep_div(Bm[i], sd[qKK(i)]);
         __syncthreads();
         double part = 0.0;
+        #pragma unroll 1
         for (int i = tid; i < nj; i += nt) {
-            const int k2 = i % K, k1 = (i / K) % K, dd = i / KK;
+            int k1, k2, dd;
+            split_int(i, k1, k2, dd);
             const double c = symmetric ? 0.5 * (Bm[i] + Bm[PIDX(dd, k2, k1)]) : Bm[i];
             P[i] = c;
             part += c;
         }
         total = block_reduce_sum(part, red);
-        for (int i = tid; i < nj; i += nt) P[i] /= total;
+        #pragma unroll 1
+        for (int i = tid; i < nj; i += nt) P[i] = ep_div(P[i], total);
     } else {
-        for (int i = tid; i < nj; i += nt) Bm[i] = JV(i) / n_pixels;   // TT == 1: layouts coincide
+        #pragma unroll 1
+        for (int i = tid; i < nj; i += nt) Bm[i] = ep_div(JV(i), n_pixels);   // TT == 1: layouts coincide
         __syncthreads();
+        #pragma unroll 1
         for (int i = tid; i < nj; i += nt) {
-            const int k2 = i % K, k1 = i / K;
+            const int k1 = qK(i), k2 = i - k1 * K;
             P[i] = symmetric ? 0.5 * (Bm[i] + Bm[k2 * K + k1]) : Bm[i];
         }
     }
     __syncthreads();
-    for (int i = tid; i < TT * K; i += nt) {
-        const int dd = i / K, k = i % K;
-        double a = 0.0, b = 0.0;
-        for (int q = 0; q < K; ++q) {
-            a += P[PIDX(dd, q, k)];
-            b += P[PIDX(dd, k, q)];
-        }
-        asum[i] = a;
-        bsum[i] = b;
+    // marginals: threads [0, TT*K) sum over k1 (asum), threads [TT*K, 2*TT*K) over k2 (bsum); each also takes the logarithm and
+    // the ratio its marginal contributes to every entry of its row / column
+    #pragma unroll 1
+    for (int i = tid; i < 2 * TT * K; i += nt) {
+        const bool second = i >= TT * K;
+        const int r = second ? i - TT * K : i, dd = qK(r), k = r - dd * K;
+        double m = 0.0;
+        #pragma unroll 1
+        for (int q = 0; q < K; ++q) m += second ? P[PIDX(dd, k, q)] : P[PIDX(dd, q, k)];
+        (second ? bsum : asum)[r] = m;
+        (second ? lb : la)[r] = ep_log(m + eps);
+        (second ? rb : ra)[r] = ep_div(m, m + eps);
     }
     __syncthreads();
     double lpart = 0.0, gpart = 0.0;
+    #pragma unroll 1
     for (int i = tid; i < nj; i += nt) {
-        const int k2 = i % K, k1 = (i / K) % K, dd = i / KK;
-        const double p = P[i], a = asum[dd * K + k2], b = bsum[dd * K + k1];
-        lpart += -p * (log(p + eps) - lamda * log(a + eps) - lamda * log(b + eps));
-        const double gq = -(log(p + eps) + p / (p + eps) - lamda * (log(a + eps) + a / (a + eps)) -
-                            lamda * (log(b + eps) + b / (b + eps))) / (double)TT;
+        int k1, k2, dd;
+        split_int(i, k1, k2, dd);
+        const double p = P[i];
+        const double lp = ep_log(p + eps), la_ = la[dd * K + k2], lb_ = lb[dd * K + k1];
+        lpart += -p * (lp - lamda * la_ - lamda * lb_);
+        const double gq = -(lp + ep_div(p, p + eps) - lamda * (la_ + ra[dd * K + k2]) - lamda * (lb_ + rb[dd * K + k1])) / (double)TT;
         G[i] = gq;
         gpart += gq * p;
     }
-    const double L = block_reduce_sum(lpart, red);
-    const double gdotP = block_reduce_sum(gpart, red);
+    block_reduce_sum2(lpart, gpart, red);
+    const double L = lpart, gdotP = gpart;
     if (tid == 0) loss[0] = (float)(L / (double)TT);
+    #pragma unroll 1
     for (int i = tid; i < KK; i += nt) p00[i] = (float)P[i];
     if (p_ij)
+        #pragma unroll 1
         for (int i = tid; i < nj; i += nt) p_ij[i] = (float)P[i];
     if (!djoint) return;
     if (pad > 0) {
-        for (int i = tid; i < nj; i += nt) G[i] = (G[i] - gdotP) / total;
+        #pragma unroll 1
+        for (int i = tid; i < nj; i += nt) G[i] = ep_div(G[i] - gdotP, total);
         __syncthreads();
         // per displacement: dot = sum gB * B
+        #pragma unroll 1
         for (int dd = warp; dd < TT; dd += nwarp) {          // one warp per displacement
             double dot = 0.0;
+            #pragma unroll 1
             for (int e = lane; e < KK; e += 32) {
-                const int k1 = e / K, k2 = e % K;
+                const int k1 = qK(e), k2 = e - k1 * K;
                 const double gb = symmetric ? 0.5 * (G[PIDX(dd, k1, k2)] + G[PIDX(dd, k2, k1)]) : G[PIDX(dd, k1, k2)];
                 dot += gb * Bm[PIDX(dd, k1, k2)];
             }
@@ -383,16 +449,19 @@ iic_epilogue_kernel(const double* __restrict__ joint, int n_slots, int K, int pa
             if (lane == 0) asum[dd] = dot;   // reuse
         }
         __syncthreads();
+        #pragma unroll 1
         for (int i = tid; i < nj; i += nt) {
-            const int k2 = i % K, k1 = (i / K) % K, dd = i / KK;
+            int k1, k2, dd;
+            split_int(i, k1, k2, dd);
             const double gb = symmetric ? 0.5 * (G[i] + G[PIDX(dd, k2, k1)]) : G[i];
-            djoint[JIDX(k1, k2, dd)] = (float)((gb - asum[dd]) / sd[dd]);
+            djoint[JIDX(k1, k2, dd)] = (float)ep_div(gb - asum[dd], sd[dd]);
         }
     } else {
+        #pragma unroll 1
         for (int i = tid; i < nj; i += nt) {
-            const int k2 = i % K, k1 = i / K;
+            const int k1 = qK(i), k2 = i - k1 * K;
             const double gb = symmetric ? 0.5 * (G[i] + G[k2 * K + k1]) : G[i];
-            djoint[i] = (float)(gb / n_pixels);
+            djoint[i] = (float)ep_div(gb, n_pixels);
         }
     }
 }
@@ -764,7 +833,7 @@ int iic_joint_heads(const void* const* xs, const void* const* ys, int n_heads, i
 
 static size_t epilogue_scratch_doubles(int K, int pad) {
     const int T = 2 * pad + 1, TT = T * T, nj = K * K * TT;
-    return (size_t)3 * nj + TT + 2 * TT * K;
+    return (size_t)3 * nj + TT + 6 * TT * K;
 }
 
 size_t iic_epilogue_workspace_bytes(int K, int pad) {
