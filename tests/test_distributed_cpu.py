@@ -100,6 +100,21 @@ def _worker(rank, port, results):
                                                                    torch.device("cpu"))
         assert npx == 2 * WORLD * 9 * 11 and n_slots == 1 and J.dtype == torch.float64
         np.testing.assert_allclose(J.numpy(), OM.raw_joint_2d(x, y, 1), rtol=1e-13)
+        # the sub-head stack (forward_heads under sharding): S partial joints travel as ONE [S, K,K,T,T] array and the mean of the
+        # per-head losses on the reduced joints equals the single-process sub-head mean on the gathered batch
+        S = 3
+        xs = [torch.randn(2 * WORLD, 5, 9, 11, generator=g, dtype=torch.float64).softmax(1).numpy() for _ in range(S)]
+        ys = [torch.randn(2 * WORLD, 5, 9, 11, generator=g, dtype=torch.float64).softmax(1).numpy() for _ in range(S)]
+        stack_loc = torch.from_numpy(np.stack([OM.raw_joint_2d(a[bs], b[bs], 1) for a, b in zip(xs, ys)]))
+        Js, n_slots, npx = cyd.make_joint_reduce(exchange="nccl")(lambda out: out.copy_(stack_loc), tuple(stack_loc.shape),
+                                                                    float(2 * 9 * 11), torch.device("cpu"))
+        assert tuple(Js.shape) == (S, 5, 5, 3, 3) and n_slots == 1 and npx == 2 * WORLD * 9 * 11
+        got = 0.0
+        for s_ in range(S):
+            P, _aux = OM.joint_epilogue(Js[s_].numpy(), padding=1, symmetric=False, n_pixels=npx)
+            got += OM.mi_loss_and_grad_wrt_pij(P, 1.0, 1e-5)[0] / S
+        want = sum(OM.iid_segmentation_loss(a, b, padding=1)["loss"] for a, b in zip(xs, ys)) / S
+        assert abs(got - want) < 1e-12 * abs(want)
         results[rank] = "ok"
     except Exception as e:  # noqa
         import traceback
