@@ -844,6 +844,8 @@ size_t iic_epilogue_workspace_bytes(int K, int pad) {
 static int iic_epilogue_impl(const double* joint, int n_slots, int K, int pad, int symmetric, float lamda, float eps, double n_pixels,
                              float* loss, float* p00, float* p_ij, float* djoint, void* workspace, size_t workspace_bytes,
                              cudaStream_t st, int n_heads, long long joint_stride, long long out_stride, long long slot_stride = 0) {
+    // (the kernel splits indices through fp32 reciprocals: exact below 2^22 entries)
+    CY_CHECK_ARG((long long)K * K * (2 * pad + 1) * (2 * pad + 1) < (1LL << 22), "iic_epilogue: K=%d pad=%d: joint too large", K, pad);
     size_t smem = epilogue_scratch_doubles(K, pad) * sizeof(double);
     double* gscratch = nullptr;
     if (iic_epilogue_workspace_bytes(K, pad)) {

@@ -176,3 +176,13 @@ def test_cluster_head_skip_softmax_returns_the_logits_of_the_same_module_tree():
     for lg, pr in zip(logits, probs):
         assert torch.allclose(torch.softmax(lg / 2.0, 1), pr, atol=1e-6)
     assert sorted(head.state_dict()) == sorted(f"_headers.{s}.{i}.{w}" for s in range(3) for i in (0, 2) for w in ("weight", "bias"))
+
+
+def test_fp32_reciprocal_index_split_is_exact_below_2_22():
+    """cy_iic_epilogue splits flat indices by the runtime K / T*T / K*K as int((n + 0.5f) * (1.0f / d)) (csrc/iic.cu): exact for
+    every n < 2^22 — the bound its host wrapper enforces — restated with numpy float32 for the divisors that can occur"""
+    n = np.arange(1 << 22, dtype=np.int64)
+    nf = n.astype(np.float32) + np.float32(0.5)
+    for d in list(range(1, 65)) + [100, 121, 225, 256, 400, 49, 25, 9, 4096, 65536]:
+        q = (nf * (np.float32(1.0) / np.float32(d))).astype(np.int32)
+        assert np.array_equal(q, (n // d).astype(np.int32)), d
