@@ -186,3 +186,19 @@ def test_fp32_reciprocal_index_split_is_exact_below_2_22():
     for d in list(range(1, 65)) + [100, 121, 225, 256, 400, 49, 25, 9, 4096, 65536]:
         q = (nf * (np.float32(1.0) / np.float32(d))).astype(np.int32)
         assert np.array_equal(q, (n // d).astype(np.int32)), d
+
+
+def test_header_is_plain_c():
+    """the drop-in boundary is a C ABI: include/contrastyou_b200.h must compile as C99 (and as C++) on its own — plain pointers and
+    sizes, no torch / CUDA types in the signatures"""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "contrastyou_b200.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    for args in (["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c"], ["g++", "-std=c++17", "-fsyntax-only", "-x", "c++"]):
+        out = subprocess.run(args + [hdr], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)      # declarations only, comments stripped
+    assert "torch" not in code.lower() and "cudaStream_t" not in code and "at::" not in code
