@@ -192,8 +192,10 @@ iic_reduce_partials_kernel(const float* __restrict__ partials, int n_partials, i
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + lane;
     // launched with programmatic stream serialization right behind the joint kernel: everything above overlaps its tail,
-    // the partial joints are read only after the dependency has resolved
+    // the partial joints are read only after the dependency has resolved; the epilogue behind THIS kernel is launched the same
+    // way (its CTA may become resident now and waits in its own cudaGridDependencySynchronize until this grid is complete)
 #if __CUDA_ARCH__ >= 900
+    asm volatile("griddepcontrol.launch_dependents;");
     cudaGridDependencySynchronize();
 #endif
     double s = 0.0;
@@ -311,6 +313,11 @@ iic_epilogue_kernel(const double* __restrict__ joint, int n_slots, int K, int pa
                     long long slot_stride) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[64];
+    // programmatic dependent launch behind the partial-joint reduction (or any other producer of `joint`: a kernel that never
+    // signals simply completes first): the launch latency and this prologue overlap the producer's tail
+#if __CUDA_ARCH__ >= 900
+    cudaGridDependencySynchronize();
+#endif
     // one CTA per sub-head of a heads launch (gridDim.x = 1 and strides 0 otherwise); p_ij and gscratch are single-head only
     joint += (size_t)blockIdx.x * joint_stride;
     loss += (size_t)blockIdx.x * out_stride;
@@ -859,10 +866,21 @@ static int iic_epilogue_impl(const double* joint, int n_slots, int K, int pad, i
         if (e != cudaSuccess) { set_error("iic_epilogue smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr.set(smem);
     }
-    iic_epilogue_kernel<<<n_heads, EPI_THREADS, smem, st>>>(joint, n_slots, K, pad, symmetric, (double)lamda, (double)eps, n_pixels, loss,
-                                                            p00, p_ij, djoint, gscratch, joint_stride, out_stride,
-                                                            slot_stride > 0 ? slot_stride : (long long)K * K * (2 * pad + 1) * (2 * pad + 1));
-    CY_CHECK_LAUNCH("iic_epilogue");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_heads);
+    cfg.blockDim = dim3(EPI_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute lattr[1];
+    lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    lattr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = lattr;
+    cfg.numAttrs = 1;
+    const long long sstride = slot_stride > 0 ? slot_stride : (long long)K * K * (2 * pad + 1) * (2 * pad + 1);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, iic_epilogue_kernel, joint, n_slots, K, pad, symmetric, (double)lamda, (double)eps, n_pixels,
+                                        loss, p00, p_ij, djoint, gscratch, joint_stride, out_stride, sstride);
+    count_launch();
+    if (le != cudaSuccess) { set_error("iic_epilogue: %s", cudaGetErrorString(le)); return (int)le; }
     return CY_OK;
 }
 
